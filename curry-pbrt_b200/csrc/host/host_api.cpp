@@ -1,0 +1,81 @@
+// extern "C" surface of the host side (see include/cpbrt.h, "Host side").
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "scene_host.h"
+
+using namespace cpbrt_host;
+
+static thread_local std::string g_host_error;
+
+extern "C" {
+
+const char* cpbrt_host_last_error(void) { return g_host_error.c_str(); }
+
+static int load_impl(const std::vector<Segment>& segs, uint64_t perm_seed, cpbrt_scene** out) {
+    cpbrt_scene* s = new cpbrt_scene();
+    try {
+        build_scene_from_segments(segs, perm_seed, &s->data);
+    } catch (...) {
+        delete s;
+        throw;
+    }
+    *out = s;
+    return CPBRT_OK;
+}
+
+int cpbrt_scene_load(const char* pbrt_path, uint64_t perm_seed, cpbrt_scene** out) {
+    if (!pbrt_path || !out) { g_host_error = "null argument"; return CPBRT_ERR_BAD_ARG; }
+    try {
+        std::vector<Segment> segs = segments_from_tokens(lex_file(pbrt_path));
+        return load_impl(segs, perm_seed, out);
+    } catch (const std::exception& e) {
+        g_host_error = e.what();
+        return CPBRT_ERR_PARSE;
+    }
+}
+
+int cpbrt_scene_parse(const char* text, const char* base_dir, uint64_t perm_seed, cpbrt_scene** out) {
+    if (!text || !out) { g_host_error = "null argument"; return CPBRT_ERR_BAD_ARG; }
+    try {
+        std::string label = join_path(base_dir ? base_dir : "", "<memory>.pbrt");
+        std::vector<Segment> segs = segments_from_tokens(lex_text(text, label));
+        return load_impl(segs, perm_seed, out);
+    } catch (const std::exception& e) {
+        g_host_error = e.what();
+        return CPBRT_ERR_PARSE;
+    }
+}
+
+void cpbrt_scene_free(cpbrt_scene* scene) { delete scene; }
+
+const cpbrt_scene_desc* cpbrt_scene_get_desc(const cpbrt_scene* scene) { return scene ? &scene->data.desc : nullptr; }
+
+const char* cpbrt_scene_film_filename(const cpbrt_scene* scene) { return scene ? scene->data.film_filename.c_str() : nullptr; }
+
+int cpbrt_scene_set_spp(cpbrt_scene* scene, uint32_t spp) {
+    if (!scene || spp == 0) return CPBRT_ERR_BAD_ARG;
+    scene->data.desc.sampler.spp = spp;
+    return CPBRT_OK;
+}
+
+int cpbrt_scene_set_integrator(cpbrt_scene* scene, uint32_t integrator, uint32_t max_depth) {
+    if (!scene || integrator > CPBRT_INTEGRATOR_DIRECT) return CPBRT_ERR_BAD_ARG;
+    scene->data.desc.integrator = integrator;
+    scene->data.desc.max_depth = max_depth;
+    return CPBRT_OK;
+}
+
+void cpbrt_make_permutation(uint64_t seed, uint16_t* out) { make_permutation(seed, out); }
+
+int cpbrt_write_png(const char* path, const float* film_rgb, uint32_t width, uint32_t height) {
+    if (!path || !film_rgb) { g_host_error = "null argument"; return CPBRT_ERR_BAD_ARG; }
+    std::vector<uint8_t> rgb(size_t(width) * height * 3);
+    film_to_rgb8(film_rgb, rgb.size(), rgb.data());
+    std::string err;
+    if (!write_png_rgb8(path, rgb.data(), width, height, &err)) { g_host_error = err; return CPBRT_ERR_IO; }
+    return CPBRT_OK;
+}
+
+}  // extern "C"
