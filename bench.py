@@ -1,0 +1,247 @@
+#!/usr/bin/env python3
+"""Benchmark of the curry-pbrt rendering hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--spp S] [--impl reference]
+
+One "step" = one complete render() of scenes/cornel_box.pbrt (900x900, path integrator,
+maxdepth 5) at --spp samples per pixel (default 1024, the configuration BASELINE.json's target is
+quoted on).  The metric is camera samples per second (Msamples/s); Mrays/s, the traversal
+roofline and the CPU baseline ride along in the same JSON line.
+
+  value   scene and BVH resident in HBM, film left on the device; device time, max over ranks
+  e2e     the same render through the C-ABI with host buffers: cpbrt_upload_scene (H2D of the
+          scene + Halton tables) + cpbrt_build_bvh + cpbrt_render into a host film (D2H)
+  N > 1   one process per GPU (torchrun); every rank renders its share of the sample indices of
+          every pixel, one ncclReduce sums the film accumulators on rank 0 ("strong" scaling:
+          the job is fixed, each GPU gets 1/N of it)
+
+--impl reference times the CPU restatement of the reference's render loop (oracle/, all host
+threads) on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+SCENE = os.path.join(ROOT, "scenes", "cornel_box.pbrt")
+PEAKS = os.path.join(ROOT, "MEASURED_PEAKS.json")
+FALLBACK_HBM_GBS = 6650.0   # B200_PROFILING.md fallback
+
+
+def cpu_sample_rect(width, height):
+    """Bounded CPU sample: the central third of the film (all materials of the scene are in it)."""
+    return (width // 3, height // 3, 2 * width // 3, 2 * height // 3)
+
+
+def run_cpu_baseline(cpbrt, spp_sample, threads, count_visits):
+    """Oracle (C++ restatement of src/render.rs:7-50) on the central-third crop at spp_sample."""
+    import oracle_api
+    scene = cpbrt.Scene.load(SCENE)
+    scene.set_spp(spp_sample)
+    world = oracle_api.OracleWorld(scene)
+    w, h = scene.resolution
+    rect = cpu_sample_rect(w, h)
+    _, sec, st = world.render(rect=rect, threads=threads, count_visits=count_visits)
+    n = (rect[2] - rect[0]) * (rect[3] - rect[1]) * spp_sample
+    return dict(samples=n, seconds=sec, msamples_s=n / sec / 1e6, mrays_s=(st["rays_closest"] + st["rays_any"]) / sec / 1e6,
+                stats=st, rect=rect, spp=spp_sample)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons while the timed region runs (B200_PROFILING.md)."""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.samples = []
+        self.stop_flag = threading.Event()
+        self.gpu = gpu_index
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([f.strip() for f in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples for i in range(4) if len(s) >= 7 and s[3 + i].lower().startswith("active")})
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons, n=len(self.samples))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--spp", type=int, default=1024)
+    ap.add_argument("--impl", default="cpbrt", choices=["cpbrt", "reference"])
+    ap.add_argument("--cpu-spp", type=int, default=16, help="spp of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    import __graft_entry__
+    cpbrt = __graft_entry__.build()
+    config = dict(workload="scenes/cornel_box.pbrt 900x900 path maxdepth=5 halton %d spp" % args.spp, spp=args.spp,
+                  film=[900, 900], primitives=33, partition="sample-index" if world > 1 else "none",
+                  l2_policy="inputs exceed L2: %.0f MB of path state + queues are rewritten every pass" % 0.0)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        threads = os.cpu_count() or 1
+        vals = []
+        for i in range(args.warmup + args.steps):
+            r = run_cpu_baseline(cpbrt, args.cpu_spp, threads, False)
+            if i >= args.warmup:
+                vals.append(r)
+        sec = sum(v["seconds"] for v in vals)
+        n = sum(v["samples"] for v in vals)
+        v = n / sec / 1e6
+        sample = "central-third crop %s at %d spp (%d samples) per step" % (list(vals[0]["rect"]), args.cpu_spp, vals[0]["samples"])
+        print(json.dumps(dict(metric="Msamples/s", value=v, unit="Msamples/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                              ms_per_step=1e3 * sec / len(vals), higher_is_better=True, scaling="strong", vs_baseline=None,
+                              dtype="f32", data="synthetic", impl="reference", config=config,
+                              mrays_s=sum(x["mrays_s"] * x["seconds"] for x in vals) / sec,
+                              cpu_baseline=dict(value=v, unit="Msamples/s", cores=threads, kind="port", sample=sample),
+                              e2e=dict(value=v, unit="Msamples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
+        return 0
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    scene = cpbrt.Scene.load(SCENE)
+    scene.set_spp(args.spp)
+    W, H = scene.resolution
+    r = cpbrt.Renderer(local_rank)
+    r.upload(scene)
+    r.build_bvh()
+    if world > 1:
+        idt = torch.zeros(cpbrt.abi.COMM_ID_BYTES, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.tensor(list(cpbrt.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        r.comm_init(world, rank, bytes(idt.cpu().tolist()))
+    film_dev = torch.zeros(H * W * 3, dtype=torch.float32, device="cuda")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(profile=False):
+        _, st = r.render(device_film_ptr=film_dev.data_ptr(), profile_stages=profile) if (rank == 0) else r.render(profile_stages=profile)
+        return st
+
+    for _ in range(args.warmup):
+        step()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    barrier()
+    t0 = time.perf_counter()
+    dev_ms, launches, rays_c, rays_a = 0.0, 0, 0, 0
+    for _ in range(args.steps):
+        st = step()
+        dev_ms += st.ms_total; launches += st.kernel_launches; rays_c += st.rays_closest; rays_a += st.rays_any
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks.stop_flag.set()
+
+    # max over ranks of the device time; totals over ranks for rays / launches
+    agg = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(launches), float(rays_c), float(rays_a)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(agg, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    dev_ms, wall_ms = float(agg[0]), float(agg[1])
+    launches, rays_c, rays_a = (int(x) for x in tot.tolist())
+    samples = W * H * args.spp * args.steps
+    # the step time is the larger of the summed device time and the barrier-to-barrier wall time
+    step_ms = max(dev_ms, wall_ms) / args.steps
+    value = samples / args.steps / (step_ms * 1e-3) / 1e6
+
+    # ---- stage profile + e2e + roofline + CPU baseline on rank 0 / N == 1 ---------------------
+    extra = {}
+    if world == 1:
+        st = step(profile=True)
+        trace_ms = st.ms_trace_closest
+        extra["stage_ms"] = dict(trace_closest=st.ms_trace_closest, trace_shadow=st.ms_trace_shadow, shade=st.ms_shade,
+                                 raygen_film=st.ms_raygen_film, total=st.ms_total)
+        # e2e: upload + BVH build + render into a host film, all inside the timed region
+        d = scene.desc
+        h2d = (int(d.n_primitives) * 24 + int(d.n_triangles) * 60 + int(d.n_spheres) * 4 + int(d.n_transforms) * 144 +
+               int(d.n_materials) * 48 + int(d.n_textures) * 40 + int(d.n_texels) * 4 + int(d.n_lights) * 48 +
+               cpbrt.abi.PERM_TABLE_LEN * 2 + 8000)
+        host_film = np.zeros((H, W, 3), np.float32)
+        e2e_steps = max(1, min(args.steps, 2))
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        for _ in range(e2e_steps):
+            r.upload(scene)
+            r.build_bvh()
+            r.render(film=host_film)
+        e2e_s = (time.perf_counter() - t1) / e2e_steps
+        extra["e2e"] = dict(value=W * H * args.spp / e2e_s / 1e6, unit="Msamples/s", h2d_bytes_per_step=h2d,
+                            d2h_bytes_per_step=host_film.nbytes, ms_per_step=e2e_s * 1e3)
+        # CPU baseline (also yields the algorithmic traversal bytes per ray)
+        cores = os.cpu_count() or 1
+        if not args.no_cpu_baseline:
+            cb = run_cpu_baseline(cpbrt, args.cpu_spp, cores, True)
+            s = cb["stats"]
+            bytes_closest = 48.0 + (32.0 * s["closest_parent_visits"] + 48.0 * s["closest_prim_tests"]) / max(1, s["rays_closest"])
+            extra["cpu_baseline"] = dict(value=cb["msamples_s"], unit="Msamples/s", cores=cores, kind="port", mrays_s=cb["mrays_s"],
+                                         sample="central-third crop %s at %d spp (%d samples), C++ restatement of the reference CPU path"
+                                                % (list(cb["rect"]), cb["spp"], cb["samples"]))
+            peak = FALLBACK_HBM_GBS; which = "fallback"
+            if os.path.exists(PEAKS):
+                peak = float(json.load(open(PEAKS))["hbm_gbs"]); which = "measured"
+            n_closest = st.rays_closest
+            achieved = bytes_closest * n_closest / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else 0.0
+            extra["roofline"] = dict(bound="hbm", kernel="k_trace_closest", achieved=achieved, peak=peak, unit="GB/s",
+                                     frac=achieved / peak, traffic=None, peak_source=which,
+                                     algorithmic_bytes_per_ray=bytes_closest, rays_per_launch=n_closest / max(1, st.trace_launches),
+                                     avg_launch_ms=trace_ms / max(1, st.trace_launches),
+                                     note="33-primitive scene: the BVH lives in L1/L2, so this is not an HBM-bound kernel; "
+                                          "see DESIGN.md and profiles/ for the 1M-triangle traversal roofline")
+    if rank == 0:
+        out = dict(metric="Msamples/s", value=value, unit="Msamples/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+                   ms_per_step=step_ms, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32", data="synthetic",
+                   config=config, mrays_s=(rays_c + rays_a) / args.steps / (step_ms * 1e-3) / 1e6, gpu_launches=launches,
+                   device_ms_per_step=dev_ms / args.steps, wall_ms_per_step=wall_ms / args.steps, clocks=clocks.summary())
+        out.update(extra)
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

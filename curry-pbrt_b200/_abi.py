@@ -97,7 +97,8 @@ class BvhDump(C.Structure):
 
 class RenderParams(C.Structure):
     _fields_ = [("sample_begin", C.c_uint32), ("sample_end", C.c_uint32), ("first_hit_only", C.c_uint32),
-                ("resolve", C.c_uint32), ("samples_per_pass", C.c_uint32), ("film_on_device", C.c_uint32)]
+                ("resolve", C.c_uint32), ("samples_per_pass", C.c_uint32), ("film_on_device", C.c_uint32),
+                ("profile_stages", C.c_uint32)]
 
 
 class Stats(C.Structure):
@@ -105,7 +106,8 @@ class Stats(C.Structure):
                 ("nan_dropped", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("ms_total", C.c_double), ("ms_trace", C.c_double), ("ms_shade", C.c_double),
                 ("ms_raygen_film", C.c_double), ("ms_reduce", C.c_double),
-                ("trace_parent_visits", C.c_uint64), ("trace_prim_tests", C.c_uint64)]
+                ("trace_parent_visits", C.c_uint64), ("trace_prim_tests", C.c_uint64),
+                ("trace_launches", C.c_uint64), ("ms_trace_closest", C.c_double), ("ms_trace_shadow", C.c_double)]
 
 
 # name -> (restype, argtypes); every symbol include/cpbrt.h declares
@@ -121,6 +123,7 @@ HOST_SYMBOLS = {
     "cpbrt_make_permutation": (None, [C.c_uint64, C.POINTER(C.c_uint16)]),
     "cpbrt_write_png": (C.c_int, [C.c_char_p, C.POINTER(C.c_float), C.c_uint32, C.c_uint32]),
     "cpbrt_render_from_file": (C.c_int, [C.c_char_p, C.c_int]),
+    "cpbrt_host_build_bvh": (C.c_int, [C.POINTER(SceneDesc), C.POINTER(C.c_uint32), C.POINTER(BvhDump)]),
 }
 DEVICE_SYMBOLS = {
     "cpbrt_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),

@@ -1,0 +1,69 @@
+"""Builds libcpbrt.so (host parser + sm_100a CUDA kernels) in-tree with nvcc.
+
+    python curry-pbrt_b200/build.py            # incremental
+    python curry-pbrt_b200/build.py --force
+
+-fmad=false / -ffp-contract=off are part of the contract, not tuning: BVH slots and Halton
+indices must be bit-identical to the reference's unfused f32 arithmetic (see csrc/device/dmath.cuh).
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "libcpbrt.so")
+OBJ = os.path.join(HERE, "build")
+
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+HOST_CXX = ["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-Wall", "-Wextra", "-pthread"]
+NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
+              "-Xcompiler", "-fPIC,-ffp-contract=off,-pthread", "-Xptxas", "-v"]
+
+HOST_SOURCES = ["host/parser.cpp", "host/scene_build.cpp", "host/halton_tables.cpp", "host/host_api.cpp",
+                "host/image_io.cpp", "bvh_build.cpp"]
+CUDA_SOURCES = ["cpbrt_api.cu"]
+
+
+def _deps():
+    deps = [os.path.join(HERE, "..", "include", "cpbrt.h")]
+    for root, _, files in os.walk(CSRC):
+        deps += [os.path.join(root, f) for f in files]
+    return deps
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    deps = _deps()
+    if not force and not _stale(OUT, deps):
+        return OUT
+    os.makedirs(OBJ, exist_ok=True)
+    objs = []
+    for src in HOST_SOURCES:
+        o = os.path.join(OBJ, src.replace("/", "_") + ".o")
+        subprocess.check_call(HOST_CXX + ["-c", os.path.join(CSRC, src), "-o", o])
+        objs.append(o)
+    for src in CUDA_SOURCES:
+        o = os.path.join(OBJ, src.replace("/", "_") + ".o")
+        r = subprocess.run([NVCC] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", o], capture_output=True, text=True)
+        with open(os.path.join(OBJ, src.replace("/", "_") + ".ptxas.log"), "w") as f:
+            f.write(r.stderr)
+        if r.returncode != 0:
+            sys.stderr.write(r.stderr)
+            raise RuntimeError("nvcc failed on " + src)
+        if verbose:
+            sys.stderr.write(r.stderr)
+        objs.append(o)
+    subprocess.check_call([NVCC, "-shared", "-o", OUT] + objs + ["-lz", "-ldl", "-lpthread", "-cudart", "static"])
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

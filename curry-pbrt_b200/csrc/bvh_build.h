@@ -1,0 +1,44 @@
+// Exact full-sweep SAH build of the reference (BVHAggregate::create_sah_node,
+// src/aggregate/bvh.rs:24-124) -- same split decisions, same primitive order, same node
+// numbering -- organised for large inputs: keys are sorted as packed integers, the three
+// axes of a big node are swept by separate threads, and independent subtrees are built in
+// parallel.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "../../include/cpbrt.h"
+
+namespace cpbrt {
+
+struct BuildBounds { float mn[3], mx[3]; };
+
+struct BuildNode {      // BVHNode (bvh.rs:13-21)
+    bool leaf;
+    uint8_t axis;
+    uint32_t a, b;      // Leaf: slot range [a, b) ; Parent: arena indices of left / right
+    BuildBounds bound;  // Parent: union of its primitives' bounds
+};
+
+struct BvhBuildResult {
+    std::vector<uint32_t> order;      // BVH slot -> uploaded primitive index
+    std::vector<BuildNode> arena;     // nodes in allocation order
+    uint32_t root = 0;                // arena index
+    // the reference's numbering: nodes are pushed after their children (post-order), root last
+    std::vector<uint32_t> post_order; // arena index of reference node k
+    std::vector<uint32_t> ref_index;  // reference node number of arena node i
+};
+
+// Primitive::bound() of every uploaded primitive (triangle.rs:114-119, sphere.rs:22-27,
+// TransformShape::bound transform.rs:52-54 with Bounds3f::apply bounds.rs:292-300).
+void primitive_bounds(const cpbrt_primitive* prims, uint64_t n, const cpbrt_triangle* triangles, const float* sphere_radius,
+                      const cpbrt_transform* transforms, std::vector<BuildBounds>* out);
+
+// Fills a caller-allocated cpbrt_bvh_dump / order array in the reference's node numbering.
+// Returns false when dump->capacity is too small.
+bool export_bvh(const BvhBuildResult& r, uint32_t* prim_order_out, cpbrt_bvh_dump* dump);
+
+// bounds[i] = Primitive::bound() of uploaded primitive i.  n_threads == 0 -> hardware.
+void build_sah_bvh(const std::vector<BuildBounds>& bounds, unsigned n_threads, BvhBuildResult* out);
+
+}  // namespace cpbrt

@@ -1,0 +1,691 @@
+// Device half of include/cpbrt.h: context, scene upload, BVH conversion, the wavefront render
+// loop and the batch parity entry points.  There is deliberately no CPU path here: every
+// entry point fails with an error code when no CUDA device is usable.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/cpbrt.h"
+#include "bvh_build.h"
+#include "device/wavefront.cuh"
+
+using namespace cpbrt;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr; size_t bytes = 0;
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+};
+
+// ---- NCCL through dlopen: the library is only needed when a communicator is attached -------
+typedef struct ncclComm* ncclComm_t;
+struct NcclUniqueId { char internal[128]; };
+struct NcclApi {
+    void* handle = nullptr;
+    int (*GetUniqueId)(NcclUniqueId*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, NcclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*Reduce)(const void*, void*, size_t, int, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool load(std::string* err) {
+        if (handle) return true;
+        handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!handle) handle = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!handle) { *err = std::string("cannot load libnccl: ") + dlerror(); return false; }
+        GetUniqueId = (int (*)(NcclUniqueId*))dlsym(handle, "ncclGetUniqueId");
+        CommInitRank = (int (*)(ncclComm_t*, int, NcclUniqueId, int))dlsym(handle, "ncclCommInitRank");
+        CommDestroy = (int (*)(ncclComm_t))dlsym(handle, "ncclCommDestroy");
+        Reduce = (int (*)(const void*, void*, size_t, int, int, int, ncclComm_t, cudaStream_t))dlsym(handle, "ncclReduce");
+        GetErrorString = (const char* (*)(int))dlsym(handle, "ncclGetErrorString");
+        if (!GetUniqueId || !CommInitRank || !CommDestroy || !Reduce) { *err = "libnccl lacks a required symbol"; return false; }
+        return true;
+    }
+};
+NcclApi g_nccl;
+const int kNcclFloat32 = 7, kNcclSum = 0;
+
+}  // namespace
+
+struct cpbrt_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    std::string error;
+
+    // host copy of what the BVH build needs
+    bool has_scene = false, has_bvh = false;
+    std::vector<cpbrt_primitive> primitives;
+    std::vector<cpbrt_triangle> triangles;
+    std::vector<float> sphere_radius;
+    std::vector<cpbrt_transform> transforms;
+    BvhBuildResult bvh;
+
+    DevScene scene;   // by-value kernel argument
+    DevBuf d_prims, d_prim_uv, d_nodes, d_transforms, d_materials, d_textures, d_texels, d_lights, d_perm, d_primes, d_primsum;
+
+    // wavefront state
+    uint32_t path_capacity = 0;
+    DevBuf d_path, d_queues, d_counts, d_pixels;
+    PathArrays P; Queues Q; PixelArrays PX;
+    Totals* d_totals = nullptr;
+    DevBuf d_totals_buf, d_film_out;
+
+    // multi-GPU
+    ncclComm_t comm = nullptr; int n_ranks = 1, rank = 0;
+
+    int fail(int code, const char* fmt, ...) {
+        char buf[512];
+        va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+        error = buf;
+        return code;
+    }
+};
+
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess) return ctx->fail(CPBRT_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__)); \
+    } while (0)
+
+namespace {
+
+int alloc_upload(cpbrt_ctx* ctx, DevBuf& b, const void* src, size_t bytes) {
+    b.release();
+    if (bytes == 0) bytes = 16;
+    CU(cudaMalloc(&b.p, bytes));
+    b.bytes = bytes;
+    if (src) CU(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    else CU(cudaMemsetAsync(b.p, 0, bytes, ctx->stream));
+    return 0;
+}
+
+float host_tri_area(const float p[9]) {   // triangle.rs:110-113
+    float a[3] = {p[3] - p[0], p[4] - p[1], p[5] - p[2]}, b[3] = {p[6] - p[0], p[7] - p[1], p[8] - p[2]};
+    float c[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+    return 0.5f * sqrtf((c[0] * c[0] + c[1] * c[1]) + c[2] * c[2]);
+}
+
+uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+
+int grid_for(const cpbrt_ctx* ctx, int blocks_per_sm) { return ctx->sm_count * blocks_per_sm; }
+
+}  // namespace
+
+extern "C" {
+
+const char* cpbrt_last_error(const cpbrt_ctx* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+int cpbrt_create(cpbrt_ctx** out, int device_id) {
+    if (!out) { g_create_error = "null out pointer"; return CPBRT_ERR_BAD_ARG; }
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        g_create_error = std::string("no usable CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return CPBRT_ERR_NO_DEVICE;
+    }
+    if (device_id < 0) device_id = 0;
+    if (device_id >= n) { g_create_error = "device_id out of range"; return CPBRT_ERR_BAD_ARG; }
+    e = cudaSetDevice(device_id);
+    if (e != cudaSuccess) { g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e); return CPBRT_ERR_CUDA; }
+    cpbrt_ctx* ctx = new cpbrt_ctx();
+    ctx->device = device_id;
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device_id);
+    e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e); delete ctx; return CPBRT_ERR_CUDA; }
+    memset(&ctx->scene, 0, sizeof ctx->scene);
+    *out = ctx;
+    return CPBRT_OK;
+}
+
+void cpbrt_destroy(cpbrt_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+    DevBuf* bufs[] = {&ctx->d_prims, &ctx->d_prim_uv, &ctx->d_nodes, &ctx->d_transforms, &ctx->d_materials, &ctx->d_textures, &ctx->d_texels,
+                      &ctx->d_lights, &ctx->d_perm, &ctx->d_primes, &ctx->d_primsum, &ctx->d_path, &ctx->d_queues, &ctx->d_counts,
+                      &ctx->d_pixels, &ctx->d_totals_buf, &ctx->d_film_out};
+    for (DevBuf* b : bufs) b->release();
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int cpbrt_upload_scene(cpbrt_ctx* ctx, const cpbrt_scene_desc* d) {
+    if (!ctx) return CPBRT_ERR_BAD_CTX;
+    if (!d || d->abi_version != CPBRT_ABI_VERSION) return ctx->fail(CPBRT_ERR_BAD_ARG, "null or wrong-version scene description");
+    CU(cudaSetDevice(ctx->device));
+    if (d->film_width == 0 || d->film_height == 0) return ctx->fail(CPBRT_ERR_BAD_ARG, "empty film");
+    if (d->n_primitives >= 0x40000000ull) return ctx->fail(CPBRT_ERR_UNSUPPORTED, "more than 2^30 primitives");
+    if (!d->sampler.permutation) return ctx->fail(CPBRT_ERR_BAD_ARG, "sampler.permutation is null");
+    // validation: every index must be in range; unsupported features fail loudly
+    for (uint64_t i = 0; i < d->n_primitives; ++i) {
+        const cpbrt_primitive& p = d->primitives[i];
+        if (p.shape.kind > CPBRT_SHAPE_SPHERE) return ctx->fail(CPBRT_ERR_BAD_ARG, "primitive %llu: bad shape kind", (unsigned long long)i);
+        if (p.shape.kind == CPBRT_SHAPE_TRIANGLE ? p.shape.data >= d->n_triangles : p.shape.data >= d->n_spheres)
+            return ctx->fail(CPBRT_ERR_BAD_ARG, "primitive %llu: shape data index out of range", (unsigned long long)i);
+        if (p.shape.xform >= (int32_t)d->n_transforms) return ctx->fail(CPBRT_ERR_BAD_ARG, "primitive %llu: transform out of range", (unsigned long long)i);
+        if ((p.material < 0) == (p.light < 0)) return ctx->fail(CPBRT_ERR_BAD_ARG, "primitive %llu: needs exactly one of material / light", (unsigned long long)i);
+        if (p.material >= (int32_t)d->n_materials || p.light >= (int32_t)d->n_lights) return ctx->fail(CPBRT_ERR_BAD_ARG, "primitive %llu: source out of range", (unsigned long long)i);
+    }
+    for (uint32_t i = 0; i < d->n_transforms; ++i) {
+        int hops = 0;
+        for (int32_t x = (int32_t)i; x >= 0; x = d->transforms[x].outer) {
+            if (x >= (int32_t)d->n_transforms || ++hops > 8) return ctx->fail(CPBRT_ERR_UNSUPPORTED, "transform chain %u: longer than 8 links or out of range", i);
+        }
+    }
+    for (uint32_t i = 0; i < d->n_materials; ++i) {
+        const cpbrt_material& m = d->materials[i];
+        if (m.type > CPBRT_MAT_GLASS) return ctx->fail(CPBRT_ERR_UNSUPPORTED, "material %u: type %u has no device implementation yet (matte, mirror, glass do)", i, m.type);
+        const int need = m.type == CPBRT_MAT_MATTE ? 2 : (m.type == CPBRT_MAT_MIRROR ? 1 : 3);
+        for (int k = 0; k < need; ++k) if (m.tex[k] < 0 || m.tex[k] >= (int32_t)d->n_textures) return ctx->fail(CPBRT_ERR_BAD_ARG, "material %u: texture slot %d out of range", i, k);
+    }
+    for (uint32_t i = 0; i < d->n_textures; ++i) {
+        const cpbrt_texture& t = d->textures[i];
+        if (t.kind == CPBRT_TEX_IMAGE && (t.width == 0 || t.height == 0 || t.offset + (uint64_t)t.width * t.height * t.channels > d->n_texels))
+            return ctx->fail(CPBRT_ERR_BAD_ARG, "texture %u: texel range out of bounds", i);
+    }
+    for (uint32_t i = 0; i < d->n_lights; ++i) {
+        const cpbrt_light& l = d->lights[i];
+        if (l.type > CPBRT_LIGHT_DISTANT) return ctx->fail(CPBRT_ERR_UNSUPPORTED, "light %u: infinite area lights have no device implementation yet", i);
+        if (l.type == CPBRT_LIGHT_AREA) {
+            if (l.shape.kind > CPBRT_SHAPE_SPHERE || (l.shape.kind == CPBRT_SHAPE_TRIANGLE ? l.shape.data >= d->n_triangles : l.shape.data >= d->n_spheres) ||
+                l.shape.xform >= (int32_t)d->n_transforms)
+                return ctx->fail(CPBRT_ERR_BAD_ARG, "light %u: bad shape", i);
+        }
+    }
+    if (d->integrator == CPBRT_INTEGRATOR_DIRECT && d->max_depth > 1) {
+        for (uint32_t i = 0; i < d->n_materials; ++i)
+            if (d->materials[i].type != CPBRT_MAT_MATTE)
+                return ctx->fail(CPBRT_ERR_UNSUPPORTED, "directlighting with maxdepth > 1 and specular materials (recursive delta lobes) is not implemented on the device");
+    }
+    if (d->max_depth > 200) return ctx->fail(CPBRT_ERR_UNSUPPORTED, "max_depth > 200");
+
+    ctx->has_scene = false; ctx->has_bvh = false;
+    ctx->primitives.assign(d->primitives, d->primitives + d->n_primitives);
+    ctx->triangles.assign(d->triangles, d->triangles + d->n_triangles);
+    ctx->sphere_radius.assign(d->sphere_radius, d->sphere_radius + d->n_spheres);
+    ctx->transforms.assign(d->transforms, d->transforms + d->n_transforms);
+
+    DevScene& S = ctx->scene;
+    memset(&S, 0, sizeof S);
+    S.n_prims = (uint32_t)d->n_primitives;
+    S.n_lights = d->n_lights;
+    S.integrator = d->integrator; S.max_depth = d->max_depth;
+    S.width = d->film_width; S.height = d->film_height;
+    memcpy(S.camera.raster_to_camera, d->camera.raster_to_camera, 64);
+    memcpy(S.camera.camera_to_world, d->camera.camera_to_world, 64);
+    S.camera.has_camera_to_world = d->camera.has_camera_to_world; S.camera.has_lens = d->camera.has_lens;
+    S.camera.lens_radius = d->camera.lens_radius; S.camera.focal_distance = d->camera.focal_distance;
+
+    // transforms / materials / textures / lights
+    {
+        std::vector<DevTransform> t(d->n_transforms);
+        for (uint32_t i = 0; i < d->n_transforms; ++i) { memcpy(t[i].m, d->transforms[i].m, 64); memcpy(t[i].m_inv, d->transforms[i].m_inv, 64); t[i].outer = d->transforms[i].outer; t[i].pad[0] = t[i].pad[1] = t[i].pad[2] = 0; }
+        if (int rc = alloc_upload(ctx, ctx->d_transforms, t.data(), t.size() * sizeof(DevTransform))) return rc;
+        std::vector<DevMaterial> m(d->n_materials);
+        for (uint32_t i = 0; i < d->n_materials; ++i) { m[i].type = d->materials[i].type; memcpy(m[i].tex, d->materials[i].tex, sizeof m[i].tex); m[i].sub[0] = d->materials[i].sub[0]; m[i].sub[1] = d->materials[i].sub[1]; }
+        if (int rc = alloc_upload(ctx, ctx->d_materials, m.data(), m.size() * sizeof(DevMaterial))) return rc;
+        std::vector<DevTexture> tx(d->n_textures);
+        for (uint32_t i = 0; i < d->n_textures; ++i) {
+            const cpbrt_texture& s = d->textures[i];
+            tx[i].kind = s.kind; tx[i].channels = s.channels; memcpy(tx[i].value, s.value, 12); tx[i].width = s.width; tx[i].height = s.height; tx[i].pad = 0; tx[i].offset = s.offset;
+        }
+        if (int rc = alloc_upload(ctx, ctx->d_textures, tx.data(), tx.size() * sizeof(DevTexture))) return rc;
+        if (int rc = alloc_upload(ctx, ctx->d_texels, d->texels, d->n_texels * sizeof(float))) return rc;
+        std::vector<DevLight> L(d->n_lights);
+        for (uint32_t i = 0; i < d->n_lights; ++i) {
+            const cpbrt_light& s = d->lights[i];
+            DevLight& o = L[i]; memset(&o, 0, sizeof o);
+            o.type = s.type; o.shape_kind = s.shape.kind; o.shape_data = s.shape.data; o.shape_xform = s.type == CPBRT_LIGHT_AREA ? s.shape.xform : -1;
+            memcpy(o.v, s.v, 12); memcpy(o.L, s.L, 12); o.tex = s.tex;
+            if (s.type == CPBRT_LIGHT_AREA) {
+                if (s.shape.kind == CPBRT_SHAPE_SPHERE) { o.radius = d->sphere_radius[s.shape.data]; o.area = o.radius * o.radius * 3.14159265358979323846f * 4.f; }   // sphere.rs:106-108
+                else { memcpy(o.tri, d->triangles[s.shape.data].p, 36); o.area = host_tri_area(o.tri); }
+            }
+        }
+        if (int rc = alloc_upload(ctx, ctx->d_lights, L.data(), L.size() * sizeof(DevLight))) return rc;
+    }
+    // sampler tables: PRIMS / PRIMSUM (halton.rs:141-214) and the caller's permutation
+    {
+        std::vector<uint32_t> primes, sums(CPBRT_N_PRIMES, 0);
+        for (uint32_t c = 2; primes.size() < CPBRT_N_PRIMES; ++c) {
+            bool is_p = true;
+            for (uint32_t q = 2; q * q <= c; ++q) if (c % q == 0) { is_p = false; break; }
+            if (is_p) primes.push_back(c);
+        }
+        for (int i = 1; i < CPBRT_N_PRIMES; ++i) sums[i] = sums[i - 1] + primes[i - 1];
+        if (int rc = alloc_upload(ctx, ctx->d_primes, primes.data(), primes.size() * 4)) return rc;
+        if (int rc = alloc_upload(ctx, ctx->d_primsum, sums.data(), sums.size() * 4)) return rc;
+        if (int rc = alloc_upload(ctx, ctx->d_perm, d->sampler.permutation, (size_t)CPBRT_PERM_TABLE_LEN * 2)) return rc;
+        DevSampler& sm = S.sampler;
+        sm.spp = d->sampler.spp;
+        for (int i = 0; i < 2; ++i) { sm.exp[i] = d->sampler.exp[i]; sm.scale[i] = d->sampler.scale[i]; sm.mult_inverse[i] = d->sampler.mult_inverse[i]; }
+        sm.stride = sm.scale[0] * sm.scale[1];
+        if (sm.scale[0] != (1ull << sm.exp[0])) return ctx->fail(CPBRT_ERR_BAD_ARG, "sampler.scale[0] must be 2^exp[0]");
+        sm.permutation = (const uint16_t*)ctx->d_perm.p; sm.primes = (const uint32_t*)ctx->d_primes.p; sm.primsum = (const uint32_t*)ctx->d_primsum.p;
+    }
+    S.transforms = (const DevTransform*)ctx->d_transforms.p;
+    S.materials = (const DevMaterial*)ctx->d_materials.p;
+    S.textures = (const DevTexture*)ctx->d_textures.p;
+    S.texels = (const float*)ctx->d_texels.p;
+    S.lights = (const DevLight*)ctx->d_lights.p;
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->has_scene = true;
+    return CPBRT_OK;
+}
+
+int cpbrt_build_bvh(cpbrt_ctx* ctx, uint32_t* prim_order_out, cpbrt_bvh_dump* dump) {
+    if (!ctx) return CPBRT_ERR_BAD_CTX;
+    if (!ctx->has_scene) return ctx->fail(CPBRT_ERR_BAD_CTX, "cpbrt_build_bvh before cpbrt_upload_scene");
+    CU(cudaSetDevice(ctx->device));
+    const uint32_t n = (uint32_t)ctx->primitives.size();
+    std::vector<BuildBounds> bounds;
+    primitive_bounds(ctx->primitives.data(), n, ctx->triangles.data(), ctx->sphere_radius.data(), ctx->transforms.data(), &bounds);
+    build_sah_bvh(bounds, 0, &ctx->bvh);
+    const BvhBuildResult& R = ctx->bvh;
+
+    // primitive records in BVH order
+    std::vector<float4> prims(3ull * n);
+    bool any_uv = false;
+    for (uint32_t i = 0; i < n && !any_uv; ++i) {
+        const cpbrt_primitive& p = ctx->primitives[i];
+        if (p.shape.kind == CPBRT_SHAPE_TRIANGLE) {
+            const cpbrt_triangle& t = ctx->triangles[p.shape.data];
+            any_uv = !(t.uv[0][0] == 0.f && t.uv[0][1] == 0.f && t.uv[1][0] == 1.f && t.uv[1][1] == 0.f && t.uv[2][0] == 1.f && t.uv[2][1] == 1.f);
+        }
+    }
+    std::vector<float> uvs(any_uv ? 6ull * n : 0);
+    for (uint32_t slot = 0; slot < n; ++slot) {
+        const uint32_t up = R.order[slot];
+        const cpbrt_primitive& p = ctx->primitives[up];
+        uint32_t meta = ((uint32_t)(p.shape.xform + 1)) << 2;
+        float4 q0 = make_float4(0, 0, 0, 0), q1 = q0, q2 = q0;
+        if (p.shape.kind == CPBRT_SHAPE_SPHERE) { meta |= kMetaSphere; q0.x = ctx->sphere_radius[p.shape.data]; }
+        else {
+            const cpbrt_triangle& t = ctx->triangles[p.shape.data];
+            q0 = make_float4(t.p[0][0], t.p[0][1], t.p[0][2], t.p[1][0]);
+            q1 = make_float4(t.p[1][1], t.p[1][2], t.p[2][0], t.p[2][1]);
+            q2.x = t.p[2][2];
+            if (any_uv) { meta |= kMetaHasUv; memcpy(&uvs[6ull * slot], t.uv, 24); }
+        }
+        q2.y = u2f(up); q2.z = u2f(meta);
+        q2.w = u2f(p.material >= 0 ? (uint32_t)p.material : (kSourceLight | (uint32_t)p.light));
+        prims[3ull * slot] = q0; prims[3ull * slot + 1] = q1; prims[3ull * slot + 2] = q2;
+    }
+    if (int rc = alloc_upload(ctx, ctx->d_prims, prims.data(), prims.size() * sizeof(float4))) return rc;
+    if (int rc = alloc_upload(ctx, ctx->d_prim_uv, any_uv ? uvs.data() : nullptr, uvs.size() * 4)) return rc;
+
+    // Parent nodes in depth-first order, far... the device layout (see scene_dev.cuh)
+    DevScene& S = ctx->scene;
+    S.n_nodes = 0; S.root_ref = 0; S.root_cnt = 0; memset(S.root_box, 0, sizeof S.root_box);
+    std::vector<float4> nodes;
+    if (n > 0) {
+        const BuildNode& root = R.arena[R.root];
+        if (root.leaf) { S.root_ref = root.a; S.root_cnt = root.b - root.a; }
+        else {
+            std::vector<uint32_t> dev_index(R.arena.size(), 0xFFFFFFFFu), dfs;
+            std::vector<uint32_t> stack(1, R.root);
+            while (!stack.empty()) {
+                uint32_t a = stack.back(); stack.pop_back();
+                const BuildNode& nd = R.arena[a];
+                if (nd.leaf) continue;
+                dev_index[a] = (uint32_t)dfs.size(); dfs.push_back(a);
+                stack.push_back(nd.b); stack.push_back(nd.a);
+            }
+            nodes.resize(4ull * dfs.size());
+            for (uint32_t k = 0; k < dfs.size(); ++k) {
+                const BuildNode& nd = R.arena[dfs[k]];
+                const BuildNode& l = R.arena[nd.a]; const BuildNode& r = R.arena[nd.b];
+                uint32_t lref = l.leaf ? l.a : dev_index[nd.a], lcnt = l.leaf ? l.b - l.a : 0;
+                uint32_t rref = r.leaf ? r.a : dev_index[nd.b], rcnt = r.leaf ? r.b - r.a : 0;
+                nodes[4ull * k] = make_float4(l.bound.mn[0], l.bound.mn[1], l.bound.mn[2], l.bound.mx[0]);
+                nodes[4ull * k + 1] = make_float4(l.bound.mx[1], l.bound.mx[2], r.bound.mn[0], r.bound.mn[1]);
+                nodes[4ull * k + 2] = make_float4(r.bound.mn[2], r.bound.mx[0], r.bound.mx[1], r.bound.mx[2]);
+                nodes[4ull * k + 3] = make_float4(u2f(lref), u2f(rref), u2f(lcnt | ((uint32_t)nd.axis << 30)), u2f(rcnt));
+            }
+            S.n_nodes = (uint32_t)dfs.size();
+            S.root_ref = 0; S.root_cnt = 0;
+            for (int k = 0; k < 3; ++k) { S.root_box[k] = root.bound.mn[k]; S.root_box[3 + k] = root.bound.mx[k]; }
+        }
+    }
+    if (int rc = alloc_upload(ctx, ctx->d_nodes, nodes.empty() ? nullptr : nodes.data(), nodes.size() * sizeof(float4))) return rc;
+    S.prims = (const float4*)ctx->d_prims.p;
+    S.prim_uv = any_uv ? (const float*)ctx->d_prim_uv.p : nullptr;
+    S.nodes = (const float4*)ctx->d_nodes.p;
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->has_bvh = true;
+
+    if (!export_bvh(R, prim_order_out, dump))
+        return ctx->fail(CPBRT_ERR_BAD_ARG, "bvh dump capacity %llu < %llu nodes", (unsigned long long)dump->capacity, (unsigned long long)dump->n_nodes);
+    return CPBRT_OK;
+}
+
+static int ensure_totals(cpbrt_ctx* ctx) {
+    if (!ctx->d_totals) {
+        if (int rc = alloc_upload(ctx, ctx->d_totals_buf, nullptr, sizeof(Totals) + 4 * sizeof(unsigned long long))) return rc;
+        ctx->d_totals = (Totals*)ctx->d_totals_buf.p;
+    }
+    return 0;
+}
+
+static int check_overflow(cpbrt_ctx* ctx, const Totals& t) {
+    if (t.overflow) return ctx->fail(CPBRT_ERR_UNSUPPORTED, "BVH deeper than the %d-entry traversal stack", kStackSize);
+    return 0;
+}
+
+int cpbrt_trace_closest(cpbrt_ctx* ctx, const cpbrt_ray* rays, uint64_t n, cpbrt_hit* hits_out, int on_device, cpbrt_stats* stats) {
+    if (!ctx) return CPBRT_ERR_BAD_CTX;
+    if (!ctx->has_bvh) return ctx->fail(CPBRT_ERR_BAD_CTX, "cpbrt_trace_closest before cpbrt_build_bvh");
+    if ((!rays || !hits_out) && n) return ctx->fail(CPBRT_ERR_BAD_ARG, "null ray / hit buffer");
+    CU(cudaSetDevice(ctx->device));
+    if (int rc = ensure_totals(ctx)) return rc;
+    CU(cudaMemsetAsync(ctx->d_totals, 0, ctx->d_totals_buf.bytes, ctx->stream));
+    unsigned long long* counters = (unsigned long long*)(ctx->d_totals + 1);
+    const float4* d_rays = (const float4*)rays; float4* d_hits = (float4*)hits_out;
+    DevBuf br, bh;
+    if (!on_device) {
+        if (int rc = alloc_upload(ctx, br, rays, n * sizeof(cpbrt_ray))) return rc;
+        if (int rc = alloc_upload(ctx, bh, nullptr, n * sizeof(cpbrt_hit))) { br.release(); return rc; }
+        d_rays = (const float4*)br.p; d_hits = (float4*)bh.p;
+    }
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, ctx->stream);
+    if (n) {
+        if (stats) k_batch_closest<true><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, d_rays, n, d_hits, counters, ctx->d_totals);
+        else k_batch_closest<false><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, d_rays, n, d_hits, counters, ctx->d_totals);
+    }
+    cudaEventRecord(e1, ctx->stream);
+    cudaError_t err = cudaGetLastError();
+    if (err == cudaSuccess && !on_device && n) err = cudaMemcpyAsync(hits_out, d_hits, n * sizeof(cpbrt_hit), cudaMemcpyDeviceToHost, ctx->stream);
+    Totals t; unsigned long long c[2] = {0, 0};
+    if (err == cudaSuccess) err = cudaMemcpyAsync(&t, ctx->d_totals, sizeof t, cudaMemcpyDeviceToHost, ctx->stream);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(c, counters, sizeof c, cudaMemcpyDeviceToHost, ctx->stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(ctx->stream);
+    float ms = 0.f; if (err == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    br.release(); bh.release();
+    if (err != cudaSuccess) return ctx->fail(CPBRT_ERR_CUDA, "trace_closest: %s", cudaGetErrorString(err));
+    if (stats) { memset(stats, 0, sizeof *stats); stats->rays_closest = n; stats->kernel_launches = n ? 1 : 0; stats->ms_total = ms; stats->ms_trace = ms; stats->trace_parent_visits = c[0]; stats->trace_prim_tests = c[1]; }
+    return check_overflow(ctx, t);
+}
+
+int cpbrt_trace_any(cpbrt_ctx* ctx, const cpbrt_ray* rays, uint64_t n, uint8_t* out, int on_device, cpbrt_stats* stats) {
+    if (!ctx) return CPBRT_ERR_BAD_CTX;
+    if (!ctx->has_bvh) return ctx->fail(CPBRT_ERR_BAD_CTX, "cpbrt_trace_any before cpbrt_build_bvh");
+    if ((!rays || !out) && n) return ctx->fail(CPBRT_ERR_BAD_ARG, "null ray / result buffer");
+    CU(cudaSetDevice(ctx->device));
+    if (int rc = ensure_totals(ctx)) return rc;
+    CU(cudaMemsetAsync(ctx->d_totals, 0, ctx->d_totals_buf.bytes, ctx->stream));
+    unsigned long long* counters = (unsigned long long*)(ctx->d_totals + 1);
+    const float4* d_rays = (const float4*)rays; uint8_t* d_out = out;
+    DevBuf br, bo;
+    if (!on_device) {
+        if (int rc = alloc_upload(ctx, br, rays, n * sizeof(cpbrt_ray))) return rc;
+        if (int rc = alloc_upload(ctx, bo, nullptr, n)) { br.release(); return rc; }
+        d_rays = (const float4*)br.p; d_out = (uint8_t*)bo.p;
+    }
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, ctx->stream);
+    if (n) {
+        if (stats) k_batch_any<true><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, d_rays, n, d_out, counters, ctx->d_totals);
+        else k_batch_any<false><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, d_rays, n, d_out, counters, ctx->d_totals);
+    }
+    cudaEventRecord(e1, ctx->stream);
+    cudaError_t err = cudaGetLastError();
+    if (err == cudaSuccess && !on_device && n) err = cudaMemcpyAsync(out, d_out, n, cudaMemcpyDeviceToHost, ctx->stream);
+    Totals t; unsigned long long c[2] = {0, 0};
+    if (err == cudaSuccess) err = cudaMemcpyAsync(&t, ctx->d_totals, sizeof t, cudaMemcpyDeviceToHost, ctx->stream);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(c, counters, sizeof c, cudaMemcpyDeviceToHost, ctx->stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(ctx->stream);
+    float ms = 0.f; if (err == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    br.release(); bo.release();
+    if (err != cudaSuccess) return ctx->fail(CPBRT_ERR_CUDA, "trace_any: %s", cudaGetErrorString(err));
+    if (stats) { memset(stats, 0, sizeof *stats); stats->rays_any = n; stats->kernel_launches = n ? 1 : 0; stats->ms_total = ms; stats->ms_trace = ms; stats->trace_parent_visits = c[0]; stats->trace_prim_tests = c[1]; }
+    return check_overflow(ctx, t);
+}
+
+int cpbrt_halton(cpbrt_ctx* ctx, const uint32_t* px, const uint32_t* py, const uint32_t* sample, const uint32_t* dim, uint64_t n,
+                 uint64_t* index_out, float* value_out) {
+    if (!ctx) return CPBRT_ERR_BAD_CTX;
+    if (!ctx->has_scene) return ctx->fail(CPBRT_ERR_BAD_CTX, "cpbrt_halton before cpbrt_upload_scene");
+    if (n == 0) return CPBRT_OK;
+    if (!px || !py || !sample || !dim) return ctx->fail(CPBRT_ERR_BAD_ARG, "null input array");
+    CU(cudaSetDevice(ctx->device));
+    DevBuf b[4], bi, bv;
+    const uint32_t* src[4] = {px, py, sample, dim};
+    int rc = 0;
+    for (int i = 0; i < 4 && !rc; ++i) rc = alloc_upload(ctx, b[i], src[i], n * 4);
+    if (!rc && index_out) rc = alloc_upload(ctx, bi, nullptr, n * 8);
+    if (!rc && value_out) rc = alloc_upload(ctx, bv, nullptr, n * 4);
+    cudaError_t err = cudaSuccess;
+    if (!rc) {
+        k_batch_halton<<<grid_for(ctx, 4), 256, 0, ctx->stream>>>(ctx->scene, (const uint32_t*)b[0].p, (const uint32_t*)b[1].p, (const uint32_t*)b[2].p,
+                                                                  (const uint32_t*)b[3].p, n, (unsigned long long*)bi.p, (float*)bv.p);
+        err = cudaGetLastError();
+        if (err == cudaSuccess && index_out) err = cudaMemcpyAsync(index_out, bi.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        if (err == cudaSuccess && value_out) err = cudaMemcpyAsync(value_out, bv.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        if (err == cudaSuccess) err = cudaStreamSynchronize(ctx->stream);
+    }
+    for (int i = 0; i < 4; ++i) b[i].release();
+    bi.release(); bv.release();
+    if (rc) return rc;
+    if (err != cudaSuccess) return ctx->fail(CPBRT_ERR_CUDA, "halton: %s", cudaGetErrorString(err));
+    return CPBRT_OK;
+}
+
+int cpbrt_camera_rays(cpbrt_ctx* ctx, uint32_t sample, cpbrt_ray* rays_out, int on_device) {
+    if (!ctx) return CPBRT_ERR_BAD_CTX;
+    if (!ctx->has_scene) return ctx->fail(CPBRT_ERR_BAD_CTX, "cpbrt_camera_rays before cpbrt_upload_scene");
+    if (!rays_out) return ctx->fail(CPBRT_ERR_BAD_ARG, "null output");
+    CU(cudaSetDevice(ctx->device));
+    const size_t npix = (size_t)ctx->scene.width * ctx->scene.height;
+    DevBuf b; float4* d = (float4*)rays_out;
+    if (!on_device) { if (int rc = alloc_upload(ctx, b, nullptr, npix * sizeof(cpbrt_ray))) return rc; d = (float4*)b.p; }
+    k_batch_camera_rays<<<grid_for(ctx, 4), 256, 0, ctx->stream>>>(ctx->scene, sample, d);
+    cudaError_t err = cudaGetLastError();
+    if (err == cudaSuccess && !on_device) err = cudaMemcpyAsync(rays_out, d, npix * sizeof(cpbrt_ray), cudaMemcpyDeviceToHost, ctx->stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(ctx->stream);
+    b.release();
+    if (err != cudaSuccess) return ctx->fail(CPBRT_ERR_CUDA, "camera_rays: %s", cudaGetErrorString(err));
+    return CPBRT_OK;
+}
+
+// ---- wavefront state ---------------------------------------------------------------------------
+static int ensure_wavefront(cpbrt_ctx* ctx, uint32_t n_paths) {
+    const uint32_t npix = ctx->scene.width * ctx->scene.height;
+    if (ctx->d_pixels.bytes < (size_t)npix * 32) {
+        if (int rc = alloc_upload(ctx, ctx->d_pixels, nullptr, (size_t)npix * 32)) return rc;
+    }
+    char* pp = (char*)ctx->d_pixels.p;
+    ctx->PX.base_index = (uint2*)pp; ctx->PX.film_point = (float2*)(pp + (size_t)npix * 8); ctx->PX.sum = (float4*)(pp + (size_t)npix * 16);
+    if (ctx->path_capacity < n_paths) {
+        const size_t per_path = 13 * 16 + 8 + 4 + 4 + 4;   // 13 float4 + index + dim + hit_t + hit_slot
+        if (int rc = alloc_upload(ctx, ctx->d_path, nullptr, per_path * n_paths)) return rc;
+        if (int rc = alloc_upload(ctx, ctx->d_queues, nullptr, (size_t)n_paths * 4 * (3 + SHADE_KINDS))) return rc;
+        ctx->path_capacity = n_paths;
+        char* p = (char*)ctx->d_path.p;
+        float4** f4s[13] = {&ctx->P.ray_o, &ctx->P.ray_d, &ctx->P.beta, &ctx->P.L, &ctx->P.sh_o, &ctx->P.sh_d, &ctx->P.nee_light,
+                            &ctx->P.mis_o, &ctx->P.mis_d, &ctx->P.mis_A, &ctx->P.mis_p, &ctx->P.nee_bsdf, &ctx->P.beta_prev};
+        for (int i = 0; i < 13; ++i) { *f4s[i] = (float4*)p; p += (size_t)n_paths * 16; }
+        ctx->P.smp_index = (uint2*)p; p += (size_t)n_paths * 8;
+        ctx->P.smp_dim = (uint32_t*)p; p += (size_t)n_paths * 4;
+        ctx->P.hit_t = (float*)p; p += (size_t)n_paths * 4;
+        ctx->P.hit_slot = (uint32_t*)p;
+        uint32_t* q = (uint32_t*)ctx->d_queues.p;
+        ctx->Q.closest[0] = q; q += n_paths; ctx->Q.closest[1] = q; q += n_paths; ctx->Q.shadow = q; q += n_paths;
+        for (int k = 0; k < SHADE_KINDS; ++k) { ctx->Q.shade[k] = q; q += n_paths; }
+    }
+    if (!ctx->d_counts.p) { if (int rc = alloc_upload(ctx, ctx->d_counts, nullptr, 64 * 4)) return rc; }
+    ctx->Q.counts = (uint32_t*)ctx->d_counts.p;
+    return ensure_totals(ctx);
+}
+
+int cpbrt_render(cpbrt_ctx* ctx, const cpbrt_render_params* params, float* film_out, cpbrt_stats* stats) {
+    if (!ctx) return CPBRT_ERR_BAD_CTX;
+    if (!ctx->has_bvh) return ctx->fail(CPBRT_ERR_BAD_CTX, "cpbrt_render before cpbrt_build_bvh");
+    CU(cudaSetDevice(ctx->device));
+    cpbrt_render_params rp; memset(&rp, 0, sizeof rp); rp.resolve = 1;
+    if (params) rp = *params;
+    DevScene S = ctx->scene;
+    if (rp.first_hit_only) { S.integrator = CPBRT_INTEGRATOR_DIRECT; S.max_depth = 0; }
+    const uint32_t spp = S.sampler.spp;
+    uint32_t s_begin = rp.sample_begin, s_end = rp.sample_end;
+    if (s_begin == 0 && s_end == 0) {
+        // whole job, or this rank's contiguous share of the sample indices
+        s_begin = (uint32_t)((uint64_t)spp * ctx->rank / ctx->n_ranks);
+        s_end = (uint32_t)((uint64_t)spp * (ctx->rank + 1) / ctx->n_ranks);
+    }
+    if (s_end > spp || s_begin > s_end) return ctx->fail(CPBRT_ERR_BAD_ARG, "sample range [%u,%u) outside [0,%u)", s_begin, s_end, spp);
+    const bool root = ctx->rank == 0;
+    if (root && !film_out) return ctx->fail(CPBRT_ERR_BAD_ARG, "film_rgb_out is null on rank 0");
+    if (ctx->comm && !rp.resolve) return ctx->fail(CPBRT_ERR_BAD_ARG, "resolve = 0 is not available with a communicator attached");
+
+    const uint32_t npix = S.width * S.height;
+    uint32_t spass = rp.samples_per_pass;
+    if (spass == 0) { spass = (4u << 20) / npix; if (spass < 1) spass = 1; if (spass > 16) spass = 16; }
+    if ((uint64_t)spass * npix >= 0x7FFFFFFFull) return ctx->fail(CPBRT_ERR_UNSUPPORTED, "film too large for one pass");
+    if (int rc = ensure_wavefront(ctx, spass * npix)) return rc;
+    const PathArrays P = ctx->P; const Queues Q = ctx->Q; const PixelArrays PX = ctx->PX;
+    Totals* T = ctx->d_totals;
+    cudaStream_t st = ctx->stream;
+    CU(cudaMemsetAsync(T, 0, sizeof(Totals), st));
+    CU(cudaMemsetAsync(Q.counts, 0, 64 * 4, st));
+
+    cudaEvent_t e0, e1, e2; cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
+    // optional per-stage timing: event pairs around each stage, read back after the final sync
+    struct Span { cudaEvent_t a, b; int stage; };   // 0 raygen/film, 1 trace closest, 2 trace shadow, 3 shade
+    std::vector<Span> spans;
+    const bool prof = rp.profile_stages != 0;
+    auto span_begin = [&](int stage) { if (prof) { Span s; cudaEventCreate(&s.a); cudaEventCreate(&s.b); s.stage = stage; cudaEventRecord(s.a, st); spans.push_back(s); } };
+    auto span_end = [&]() { if (prof) cudaEventRecord(spans.back().b, st); };
+    cudaEventRecord(e0, st);
+    uint64_t launches = 0, trace_launches = 0;
+    const int g_trace = grid_for(ctx, 8), g_shade = grid_for(ctx, 8), g_pix = grid_for(ctx, 4);
+    k_pixel_setup<<<g_pix, 256, 0, st>>>(S, PX); ++launches;
+    const uint32_t n_iters = S.integrator == CPBRT_INTEGRATOR_PATH ? S.max_depth + 1 : 2;
+    bool first_pass = true;
+    for (uint32_t k0 = s_begin; k0 < s_end; k0 += spass) {
+        const uint32_t Sn = std::min(spass, s_end - k0);
+        // a rank that starts in the middle of the sample range first replays the film-point drift
+        const uint32_t skip = first_pass ? k0 : 0;
+        first_pass = false;
+        span_begin(0);
+        k_raygen<<<g_pix, 128, 0, st>>>(S, PX, P, Q, k0, Sn, skip); ++launches;
+        span_end();
+        int cur = 0;
+        for (uint32_t it = 0; it < n_iters; ++it) {
+            span_begin(1);
+            k_trace_closest<<<g_trace, 128, 0, st>>>(S, P, Q, cur, T); ++trace_launches;
+            span_end();
+            span_begin(2);
+            k_trace_shadow<<<g_trace, 128, 0, st>>>(S, P, Q, T);
+            span_end();
+            k_queue_reset<<<1, 32, 0, st>>>(Q, cur, 0, T);
+            const int next = cur ^ 1;
+            span_begin(3);
+            k_shade_terminal<<<g_shade, 128, 0, st>>>(S, P, Q);
+            k_shade<SHADE_MATTE><<<g_shade, 128, 0, st>>>(S, P, Q, next);
+            k_shade<SHADE_MIRROR><<<g_shade, 128, 0, st>>>(S, P, Q, next);
+            k_shade<SHADE_GLASS><<<g_shade, 128, 0, st>>>(S, P, Q, next);
+            span_end();
+            k_queue_reset<<<1, 32, 0, st>>>(Q, cur, 1, T);
+            launches += 8;
+            cur = next;
+        }
+        span_begin(0);
+        k_film<<<g_pix, 128, 0, st>>>(S, PX, P, Sn, T); ++launches;
+        span_end();
+    }
+    cudaEventRecord(e1, st);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) {
+        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+        for (auto& sp : spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+        return ctx->fail(CPBRT_ERR_CUDA, "render launch: %s", cudaGetErrorString(err));
+    }
+
+    // film: single GPU -> resolve straight into the output.  With a communicator every GPU
+    // writes its raw {sum, count} accumulator, one ncclReduce sums them on rank 0, and the
+    // resolve kernel there consumes the reduced buffer directly.
+    const size_t out_floats = (size_t)npix * (rp.resolve ? 3 : 4);
+    float* d_out = film_out;
+    if (!rp.film_on_device) {
+        if (ctx->d_film_out.bytes < out_floats * 4) { if (int rc = alloc_upload(ctx, ctx->d_film_out, nullptr, out_floats * 4)) return rc; }
+        d_out = (float*)ctx->d_film_out.p;
+    }
+    if (ctx->comm) {
+        // the path-state buffer is idle now: first npix*16 bytes = contribution, next = reduce target
+        float* contrib = (float*)ctx->d_path.p;
+        float* red = contrib + (size_t)npix * 4;
+        k_film_resolve<<<g_pix, 256, 0, st>>>(S, PX.sum, contrib, 0); ++launches;
+        int nrc = g_nccl.Reduce(contrib, red, (size_t)npix * 4, kNcclFloat32, kNcclSum, 0, ctx->comm, st);
+        if (nrc != 0) return ctx->fail(CPBRT_ERR_NCCL, "ncclReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "error");
+        if (root) { k_film_resolve<<<g_pix, 256, 0, st>>>(S, (const float4*)red, d_out, 2); ++launches; }
+    } else {
+        k_film_resolve<<<g_pix, 256, 0, st>>>(S, PX.sum, d_out, rp.resolve ? 1 : 0); ++launches;
+    }
+    cudaEventRecord(e2, st);
+    Totals t; memset(&t, 0, sizeof t);
+    err = cudaGetLastError();
+    if (err == cudaSuccess) err = cudaMemcpyAsync(&t, T, sizeof t, cudaMemcpyDeviceToHost, st);
+    if (err == cudaSuccess && root && !rp.film_on_device) err = cudaMemcpyAsync(film_out, d_out, out_floats * 4, cudaMemcpyDeviceToHost, st);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(st);
+    float ms_render = 0.f, ms_film = 0.f;
+    if (err == cudaSuccess) { cudaEventElapsedTime(&ms_render, e0, e1); cudaEventElapsedTime(&ms_film, e1, e2); }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    double ms_stage[4] = {0, 0, 0, 0};
+    for (auto& sp : spans) {
+        float ms = 0.f;
+        if (err == cudaSuccess) cudaEventElapsedTime(&ms, sp.a, sp.b);
+        ms_stage[sp.stage] += ms;
+        cudaEventDestroy(sp.a); cudaEventDestroy(sp.b);
+    }
+    if (err != cudaSuccess) return ctx->fail(CPBRT_ERR_CUDA, "render: %s", cudaGetErrorString(err));
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        stats->camera_samples = (uint64_t)npix * (s_end - s_begin);
+        stats->rays_closest = t.rays_closest; stats->rays_any = t.rays_any; stats->nan_dropped = t.nan_dropped;
+        stats->kernel_launches = launches; stats->ms_total = ms_render + ms_film;
+        stats->ms_reduce = ctx->comm ? ms_film : 0.0; stats->ms_raygen_film = ms_film;
+        if (prof) {
+            stats->ms_raygen_film = ms_stage[0] + ms_film; stats->ms_trace_closest = ms_stage[1]; stats->ms_trace_shadow = ms_stage[2];
+            stats->ms_trace = ms_stage[1] + ms_stage[2]; stats->ms_shade = ms_stage[3]; stats->trace_launches = trace_launches;
+        }
+    }
+    return check_overflow(ctx, t);
+}
+
+int cpbrt_comm_unique_id(uint8_t id_out[CPBRT_COMM_ID_BYTES]) {
+    std::string err;
+    if (!g_nccl.load(&err)) { g_create_error = err; return CPBRT_ERR_NCCL; }
+    NcclUniqueId id;
+    if (g_nccl.GetUniqueId(&id) != 0) { g_create_error = "ncclGetUniqueId failed"; return CPBRT_ERR_NCCL; }
+    memcpy(id_out, &id, CPBRT_COMM_ID_BYTES);
+    return CPBRT_OK;
+}
+
+int cpbrt_comm_init(cpbrt_ctx* ctx, int n_ranks, int rank, const uint8_t id_bytes[CPBRT_COMM_ID_BYTES]) {
+    if (!ctx) return CPBRT_ERR_BAD_CTX;
+    if (n_ranks < 1 || rank < 0 || rank >= n_ranks || !id_bytes) return ctx->fail(CPBRT_ERR_BAD_ARG, "bad communicator arguments");
+    CU(cudaSetDevice(ctx->device));
+    std::string err;
+    if (!g_nccl.load(&err)) return ctx->fail(CPBRT_ERR_NCCL, "%s", err.c_str());
+    NcclUniqueId id; memcpy(&id, id_bytes, CPBRT_COMM_ID_BYTES);
+    int rc = g_nccl.CommInitRank(&ctx->comm, n_ranks, id, rank);
+    if (rc != 0) return ctx->fail(CPBRT_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
+    ctx->n_ranks = n_ranks; ctx->rank = rank;
+    return CPBRT_OK;
+}
+
+}  // extern "C"

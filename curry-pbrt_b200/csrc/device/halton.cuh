@@ -1,0 +1,82 @@
+// Halton sampler on the device: HaltonSampler::{set_pixel,next_sample,get_sample} and the
+// Sampler trait defaults (src/sampler/halton.rs:24-136, src/sampler/mod.rs:10-36).
+// All index arithmetic is integer and must match the reference bit for bit; indices exceed
+// 2^32 for large films x sample counts, so they are carried as u64 with a 32-bit fast path
+// for the digit loop (the quotient sequence is the same either way).
+#pragma once
+#include "scene_dev.cuh"
+
+namespace cpbrt {
+
+struct SamplerState { uint64_t index; uint32_t dim; };
+
+// inverse (halton.rs:36-47) for base_index 0/1, returning base^digit_count in *pw
+CP_DEV uint64_t digit_inverse(uint64_t x, uint32_t base, uint64_t* pw, uint32_t* count) {
+    uint64_t acc = 0, p = 1; uint32_t c = 0;
+    if (base == 2) {
+        if (x) { c = 64 - __clzll((long long)x); acc = __brevll(x) >> (64 - c); p = c == 64 ? 0 : (1ull << c); }
+    } else {
+        while ((x >> 32) != 0) { uint64_t q = x / base; uint64_t digit = x - q * base; acc = acc * base + digit; p *= base; ++c; x = q; }
+        uint32_t xs = (uint32_t)x;
+        while (xs != 0) { uint32_t q = xs / base; uint32_t digit = xs - q * base; acc = acc * base + digit; p *= base; ++c; xs = q; }
+    }
+    *pw = p; *count = c;
+    return acc;
+}
+
+// radical_inverse (halton.rs:65-70)
+CP_DEV float radical_inverse(uint64_t x, uint32_t base) {
+    uint64_t pw; uint32_t c;
+    uint64_t acc = digit_inverse(x, base, &pw, &c);
+    float inv_base_n = 1.f / __ull2float_rn(pw);
+    return inv_base_n * __ull2float_rn(acc);
+}
+
+// scrambled_radical_inverse (halton.rs:56-64)
+CP_DEV float scrambled_radical_inverse(const DevSampler& S, uint64_t x, uint32_t dim) {
+    const uint32_t base = __ldg(&S.primes[dim]);
+    const uint16_t* __restrict__ pm = S.permutation + __ldg(&S.primsum[dim]);
+    uint64_t acc = 0, pw = 1;
+    while ((x >> 32) != 0) { uint64_t q = x / base; uint32_t digit = (uint32_t)(x - q * base); acc = acc * base + __ldg(&pm[digit]); pw *= base; x = q; }
+    uint32_t xs = (uint32_t)x;
+    while (xs != 0) { uint32_t q = xs / base; uint32_t digit = xs - q * base; acc = acc * base + __ldg(&pm[digit]); pw *= base; xs = q; }
+    float inv_base_n = 1.f / __ull2float_rn(pw);
+    float inv_base = 1.f / (float)base;
+    return inv_base_n * (__ull2float_rn(acc) + inv_base * (float)__ldg(&pm[0]) / (1.f - inv_base));
+}
+
+// set_pixel (halton.rs:108-119) with inverse_exp (halton.rs:48-55)
+CP_DEV uint64_t halton_pixel_index(const DevSampler& S, uint32_t px, uint32_t py) {
+    uint64_t idx = 0;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const uint32_t base = i == 0 ? 2u : 3u;
+        uint64_t pw; uint32_t c;
+        uint64_t r = digit_inverse(i == 0 ? px : py, base, &pw, &c);
+        for (uint32_t k = c; k < S.exp[i]; ++k) r *= base;
+        idx += r * S.scale[1 - i] * S.mult_inverse[i];
+    }
+    return idx % S.stride;
+}
+
+// get_sample (halton.rs:124-136)
+CP_DEV float sampler_get_sample(const DevSampler& S, SamplerState& st) {
+    float r;
+    if (st.dim == 0) r = radical_inverse(st.index / S.scale[0], 2u);
+    else if (st.dim == 1) r = radical_inverse(st.index / S.scale[1], 3u);
+    else if (st.dim < 1000) r = scrambled_radical_inverse(S, st.index, st.dim);
+    else r = 0.5f;   // reference draws rand::random() here; unreachable for sane max_depth
+    ++st.dim;
+    return r;
+}
+// get_1d (sampler/mod.rs:10-17): the clamp constant 0.9999999999999 is 1.0 in f32
+CP_DEV float sampler_get_1d(const DevSampler& S, SamplerState& st) { float r = sampler_get_sample(S, st); return r >= 1.f ? 1.f : r; }
+CP_DEV P2 sampler_get_2d(const DevSampler& S, SamplerState& st) { P2 p; p.x = sampler_get_1d(S, st); p.y = sampler_get_1d(S, st); return p; }
+// get_usize (sampler/mod.rs:24-33)
+CP_DEV uint32_t sampler_get_usize(const DevSampler& S, SamplerState& st, uint32_t max) {
+    float f = sampler_get_sample(S, st) * (float)max;
+    uint32_t r = f32_to_u32_sat(truncf(f));
+    return r == max ? max - 1 : r;
+}
+
+}  // namespace cpbrt

@@ -1,0 +1,83 @@
+// Device-resident scene: how the flattened cpbrt_scene_desc is laid out in HBM.
+//
+//   prims  48 B per BVH slot, three 16-byte vectors (one LDG.128 each), in BVH order so that a
+//          leaf's primitives are contiguous:
+//            q0 = p0.x p0.y p0.z p1.x      (sphere: radius, -, -, -)
+//            q1 = p1.y p1.z p2.x p2.y
+//            q2 = p2.z  upload_index  meta  source
+//          meta   bit 0 = shape kind (0 triangle, 1 sphere), bit 1 = has explicit uv triple,
+//                 bits 2.. = innermost transform index + 1 (0 = none)
+//          source material index, or 0x80000000 | light index for emissive primitives
+//   nodes  64 B per Parent node = both children's boxes + links, four 16-byte vectors:
+//            q0 = L.min.x L.min.y L.min.z L.max.x
+//            q1 = L.max.y L.max.z R.min.x R.min.y
+//            q2 = R.min.z R.max.x R.max.y R.max.z
+//            q3 = left_ref  right_ref  left_cnt | axis << 30  right_cnt
+//          child with cnt > 0 is a Leaf: ref = first BVH slot, cnt = number of primitives, and
+//          its box is unused (the reference tests no box for leaves, bvh.rs:158-165);
+//          child with cnt == 0 is a Parent: ref = node index, box = that Parent's own `bound`.
+//          The reference stores each Parent's bound in the Parent itself (bvh.rs:13-21) and
+//          tests it on entry; keeping both children's bounds in the parent lets one 64-byte
+//          fetch decide both children, with identical arithmetic.
+#pragma once
+#include "dmath.cuh"
+
+namespace cpbrt {
+
+struct DevTransform { float m[16]; float m_inv[16]; int32_t outer; int32_t pad[3]; };   // 144 B
+struct DevTexture { uint32_t kind, channels; float value[3]; uint32_t width, height; uint32_t pad; uint64_t offset; };
+struct DevMaterial { uint32_t type; int32_t tex[9]; int32_t sub[2]; };
+struct DevLight {
+    uint32_t type;
+    uint32_t shape_kind, shape_data; int32_t shape_xform;   // AREA: its own shape
+    float v[3]; float L[3];
+    int32_t tex;
+    float tri[9];        // AREA + triangle: object-space vertices
+    float radius;        // AREA + sphere
+    float area;          // Shape::area of the light's shape
+};
+
+static constexpr uint32_t kMetaSphere = 1u, kMetaHasUv = 2u;
+static constexpr uint32_t kSourceLight = 0x80000000u;
+
+struct DevCamera {
+    float raster_to_camera[16];
+    float camera_to_world[16];
+    int32_t has_camera_to_world, has_lens;
+    float lens_radius, focal_distance;
+};
+
+struct DevSampler {
+    uint32_t spp;
+    uint32_t exp[2];
+    uint64_t scale[2];
+    uint64_t mult_inverse[2];
+    uint64_t stride;                 // scale[0] * scale[1]
+    const uint16_t* permutation;     // digit permutations, block of prime k at primsum[k]
+    const uint32_t* primes;          // first 1000 primes
+    const uint32_t* primsum;
+};
+
+struct DevScene {
+    // geometry
+    const float4* prims;        // 3 per BVH slot
+    const float* prim_uv;       // 6 per BVH slot, only if any triangle has explicit uvs (else null)
+    const float4* nodes;        // 4 per Parent node
+    const DevTransform* transforms;
+    uint32_t n_prims, n_nodes;
+    // root: either a Parent (root_cnt == 0, own bound in root_box) or a single Leaf
+    uint32_t root_ref, root_cnt;
+    float root_box[6];
+    // shading
+    const DevMaterial* materials;
+    const DevTexture* textures;
+    const float* texels;
+    const DevLight* lights;
+    uint32_t n_lights;
+    uint32_t integrator, max_depth;
+    uint32_t width, height;
+    DevCamera camera;
+    DevSampler sampler;
+};
+
+}  // namespace cpbrt

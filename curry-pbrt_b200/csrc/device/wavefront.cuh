@@ -1,0 +1,522 @@
+// Wavefront path tracer kernels: the per-ray loop of render() (src/render.rs:20-47) split into
+// stages that each run over a compacted queue of paths.
+//
+//   k_pixel_setup      set_pixel for every pixel            halton.rs:108-119
+//   k_raygen           jittered film point + camera ray      render.rs:26-32, camera/*.rs
+//   k_trace_closest    Scene::intersect for continuation and MIS rays (scene.rs:20-22) and
+//                      routing of hits to the per-material shading queues
+//   k_trace_shadow     Scene::intersect_predicate for shadow rays   scene.rs:17-19, light/mod.rs:112-114
+//   k_shade<KIND>      one bounce of PathIntegrator::li / DirectLightIntegrator::li_depth for
+//                      hits on one material kind             path.rs:19-64, direct_light.rs:12-41,
+//                      integrator/mod.rs:13-97
+//   k_film             NaN drop + per-pixel sums             render.rs:34-43, film.rs:7-18
+//
+// Queues hold path ids; producers reserve slots with one atomicAdd per warp
+// (ballot + popc + shuffle).  A path owns its state slot for a whole pass, so no two threads
+// ever write the same field of the same path in one kernel.
+#pragma once
+#include "bvh_trace.cuh"
+#include "shading.cuh"
+
+namespace cpbrt {
+
+enum ShadeKind : int { SHADE_TERMINAL = 0, SHADE_MATTE = 1, SHADE_MIRROR = 2, SHADE_GLASS = 3, SHADE_KINDS = 4 };
+
+// flag bits kept in ray_d.w
+static constexpr uint32_t kFlagSpecular = 0x100u;      // low 8 bits: bounce
+// pending-NEE bits kept in beta_prev.w
+static constexpr uint32_t kPendAny = 1u, kPendLight = 2u, kPendMis = 4u;
+static constexpr uint32_t kMisRayBit = 0x80000000u;    // queue entry: path id | kMisRayBit for a MIS ray
+
+struct PathArrays {
+    float4* ray_o;      // continuation ray origin
+    float4* ray_d;      // direction, w = bits(bounce | specular flag)
+    float4* beta;       // path throughput
+    float4* L;          // radiance accumulated so far
+    uint2* smp_index;   // Halton index (u64)
+    uint32_t* smp_dim;  // next sampler dimension
+    float* hit_t; uint32_t* hit_slot;
+    float4* sh_o;       // shadow ray origin, w = t_max
+    float4* sh_d;       // shadow ray direction
+    float4* nee_light;  // light-sampling term of uniform_sample_one_light (zeroed when occluded)
+    float4* mis_o;      // MIS ray origin, w = f_pdf
+    float4* mis_d;      // MIS ray direction, w = bits(light id)
+    float4* mis_A;      // (le * f) * |n.wi|
+    float4* mis_p;      // shading point
+    float4* nee_bsdf;   // BSDF-sampling term
+    float4* beta_prev;  // throughput the pending terms are weighted with, w = bits(pending flags)
+};
+
+struct Queues {
+    uint32_t* closest[2];     // path id (| kMisRayBit)
+    uint32_t* shadow;
+    uint32_t* shade[SHADE_KINDS];
+    // counters: [0],[1] closest; [2] shadow; [3..3+SHADE_KINDS) shade; then totals
+    uint32_t* counts;
+};
+static constexpr int kCntClosest0 = 0, kCntShadow = 2, kCntShade0 = 3, kCntN = 3 + SHADE_KINDS;
+// 64-bit totals that live after the counters: rays_closest, rays_any, nan_dropped, stack_overflow
+struct Totals { unsigned long long rays_closest, rays_any, nan_dropped, overflow; };
+
+struct PixelArrays {
+    uint2* base_index;   // Halton index of sample 0 (set_pixel)
+    float2* film_point;  // running film_point_f (render.rs:26,31)
+    float4* sum;         // sum of kept samples, w = bits(kept count)
+};
+
+// warp-aggregated queue push: every lane calls it, `want` says whether it has an item
+CP_DEV void queue_push(uint32_t* q, uint32_t* count, bool want, uint32_t item) {
+    const unsigned mask = __ballot_sync(0xFFFFFFFFu, want);
+    if (mask == 0) return;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(count, (uint32_t)__popc(mask));
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    if (want) q[base + __popc(mask & ((1u << lane) - 1u))] = item;
+}
+
+CP_DEV V3 f4_xyz(float4 v) { return v3(v.x, v.y, v.z); }
+CP_DEV Spec f4_rgb(float4 v) { return spec3(v.x, v.y, v.z); }
+CP_DEV float4 mk4(V3 v, float w) { return make_float4(v.x, v.y, v.z, w); }
+CP_DEV float4 mk4(Spec v, float w) { return make_float4(v.r, v.g, v.b, w); }
+
+// l += beta * uniform_sample_one_light(...) of the previously shaded bounce, now that its
+// shadow and MIS rays are back (path.rs:37-40, integrator/mod.rs:20-96).
+CP_DEV Spec resolve_pending(const DevScene& sc, const PathArrays& P, uint32_t pid, Spec L) {
+    float4 bp = P.beta_prev[pid];
+    const uint32_t flags = __float_as_uint(bp.w);
+    if (!(flags & kPendAny)) return L;
+    Spec l = spec(0.f);
+    if (flags & kPendLight) l = l + f4_rgb(P.nee_light[pid]);
+    if (flags & kPendMis) l = l + f4_rgb(P.nee_bsdf[pid]);
+    l = l * (float)sc.n_lights;
+    bp.w = __uint_as_float(0u);
+    P.beta_prev[pid] = bp;
+    return L + f4_rgb(bp) * l;
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void k_pixel_setup(DevScene sc, PixelArrays px) {
+    const uint32_t npix = sc.width * sc.height;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x) {
+        const uint32_t x = i % sc.width, y = i / sc.width;
+        const uint64_t idx = halton_pixel_index(sc.sampler, x, y);
+        px.base_index[i] = make_uint2((uint32_t)idx, (uint32_t)(idx >> 32));
+        px.film_point[i] = make_float2((float)x, (float)y);
+        px.sum[i] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0u));
+    }
+}
+
+// Camera::generate_ray: perspective (perspective.rs:47-51), thin lens (lens.rs:24-33),
+// camera-to-world (camera/mod.rs:66-68).
+CP_DEV Ray camera_generate_ray(const DevScene& sc, P2 film, SamplerState& st) {
+    const DevCamera& cam = sc.camera;
+    V3 cp = apply_point(cam.raster_to_camera, v3(film.x, film.y, 0.f));
+    Ray ray; ray.o = v3(0.f, 0.f, 0.f); ray.d = normalize(cp); ray.t_max = kFloatMax;
+    if (cam.has_lens) {
+        P2 disk = concentric_sample_disk(sampler_get_2d(sc.sampler, st));
+        float lx = cam.lens_radius * disk.x, ly = cam.lens_radius * disk.y;
+        float ft = cam.focal_distance / ray.d.z;
+        V3 focus = ray.o + ray.d * ft;
+        V3 o = v3(lx, ly, 0.f);
+        ray.o = o; ray.d = normalize(focus - o);
+    }
+    if (cam.has_camera_to_world) { ray.o = apply_point(cam.camera_to_world, ray.o); ray.d = apply_vector(cam.camera_to_world, ray.d); }
+    return ray;
+}
+
+// One thread per pixel; samples [k0, k0 + S) of that pixel go to paths s * npix + pixel.
+// `skip` > 0 replays the film-point drift of samples that belong to another GPU's share
+// (sample partitioning): only dimensions 0 and 1 are evaluated for them.
+__global__ void k_raygen(DevScene sc, PixelArrays px, PathArrays P, Queues Q, uint32_t k0, uint32_t S, uint32_t skip) {
+    const uint32_t npix = sc.width * sc.height;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x) {
+        const uint2 bi = px.base_index[i];
+        const uint64_t base = ((uint64_t)bi.y << 32) | bi.x;
+        float2 fp = px.film_point[i];
+        for (uint32_t s = 0; s < skip; ++s) {
+            SamplerState st; st.index = base + (uint64_t)(k0 - skip + s) * sc.sampler.stride; st.dim = 0;
+            P2 u = sampler_get_2d(sc.sampler, st);
+            fp.x += u.x - 0.5f; fp.y += u.y - 0.5f;
+        }
+        for (uint32_t s = 0; s < S; ++s) {
+            SamplerState st; st.index = base + (uint64_t)(k0 + s) * sc.sampler.stride; st.dim = 0;
+            P2 u = sampler_get_2d(sc.sampler, st);
+            fp.x += u.x - 0.5f; fp.y += u.y - 0.5f;           // render.rs:30-31
+            P2 film; film.x = fp.x; film.y = fp.y;
+            Ray r = camera_generate_ray(sc, film, st);
+            const uint32_t pid = s * npix + i;
+            P.ray_o[pid] = mk4(r.o, 0.f);
+            P.ray_d[pid] = mk4(r.d, __uint_as_float(0u));
+            P.beta[pid] = make_float4(1.f, 1.f, 1.f, 0.f);
+            P.L[pid] = make_float4(0.f, 0.f, 0.f, 0.f);
+            P.smp_index[pid] = make_uint2((uint32_t)st.index, (uint32_t)(st.index >> 32));
+            P.smp_dim[pid] = st.dim;
+            P.beta_prev[pid] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0u));
+            Q.closest[0][pid] = pid;
+        }
+        px.film_point[i] = fp;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) Q.counts[kCntClosest0] = S * npix;
+}
+
+// ------------------------------------------------------------------------------------------
+// Closest-hit stage.  `cur` selects the input queue.
+__global__ void __launch_bounds__(128) k_trace_closest(DevScene sc, PathArrays P, Queues Q, int cur, Totals* totals) {
+    const uint32_t n = Q.counts[kCntClosest0 + cur];
+    const uint32_t n_round = (n + 31u) & ~31u;   // whole warps stay in the loop for the ballots
+    uint32_t overflow = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        const bool active = i < n;
+        int kind = -1;
+        uint32_t pid = 0;
+        if (active) {
+            const uint32_t e = Q.closest[cur][i];
+            pid = e & ~kMisRayBit;
+            if (e & kMisRayBit) {
+                // BSDF-sampled ray of uniform_sample_one_light (integrator/mod.rs:54-89)
+                const float4 mo = P.mis_o[pid], md = P.mis_d[pid];
+                Ray ray; ray.o = f4_xyz(mo); ray.d = f4_xyz(md); ray.t_max = kFloatMax;
+                float t;
+                const uint32_t slot = bvh_closest<false>(sc, ray, &t, nullptr, &overflow);
+                Spec ld = spec(0.f);
+                if (slot != 0xFFFFFFFFu) {
+                    const PrimRecord pr = load_prim(sc, slot);
+                    const uint32_t li = __float_as_uint(md.w);
+                    if (prim_source(pr) == (kSourceLight | li)) {   // Arc::ptr_eq(light, &intersect_light)
+                        const DevLight& light = sc.lights[li];
+                        ShapePoint hsp = prim_shape_point(sc, slot, pr, ray, t);
+                        const float li_pdf = shape_by_point_pdf(sc, light, f4_xyz(P.mis_p[pid]), hsp);
+                        const float f_pdf = mo.w;
+                        if (li_pdf != 0.f) ld = f4_rgb(P.mis_A[pid]) * power_heuristic(f_pdf, li_pdf) / f_pdf;
+                    }
+                }
+                P.nee_bsdf[pid] = mk4(ld, 0.f);
+            } else {
+                const float4 ro = P.ray_o[pid], rd = P.ray_d[pid];
+                Ray ray; ray.o = f4_xyz(ro); ray.d = f4_xyz(rd); ray.t_max = kFloatMax;
+                float t;
+                const uint32_t slot = bvh_closest<false>(sc, ray, &t, nullptr, &overflow);
+                P.hit_t[pid] = t; P.hit_slot[pid] = slot;
+                kind = SHADE_TERMINAL;
+                if (slot != 0xFFFFFFFFu) {
+                    const uint32_t src = __float_as_uint(__ldg(&sc.prims[3ull * slot + 2].w));
+                    const uint32_t bounce = __float_as_uint(rd.w) & 0xFFu;
+                    if (!(src & kSourceLight) && !(sc.integrator == 0 && bounce >= sc.max_depth)) {
+                        const uint32_t mt = sc.materials[src].type;
+                        kind = mt == 0 ? SHADE_MATTE : (mt == 1 ? SHADE_MIRROR : SHADE_GLASS);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < SHADE_KINDS; ++k) queue_push(Q.shade[k], &Q.counts[kCntShade0 + k], kind == k, pid);
+    }
+    if (overflow) atomicAdd(&totals->overflow, 1ull);
+}
+
+// Shadow-ray stage: VisibilityTester::unoccluded (light/mod.rs:112-114).
+__global__ void __launch_bounds__(128) k_trace_shadow(DevScene sc, PathArrays P, Queues Q, Totals* totals) {
+    const uint32_t n = Q.counts[kCntShadow];
+    uint32_t overflow = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t pid = Q.shadow[i];
+        const float4 so = P.sh_o[pid], sd = P.sh_d[pid];
+        Ray ray; ray.o = f4_xyz(so); ray.d = f4_xyz(sd); ray.t_max = so.w;
+        if (bvh_any<false>(sc, ray, nullptr, &overflow)) P.nee_light[pid] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (overflow) atomicAdd(&totals->overflow, 1ull);
+}
+
+// Between the trace and shade stages: fold the consumed queue sizes into the ray totals and
+// empty those queues; `which` 0 = after trace, 1 = after shade.
+__global__ void k_queue_reset(Queues Q, int cur, int which, Totals* totals) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (which == 0) {
+        totals->rays_closest += Q.counts[kCntClosest0 + cur];
+        totals->rays_any += Q.counts[kCntShadow];
+        Q.counts[kCntClosest0 + cur] = 0;
+        Q.counts[kCntShadow] = 0;
+    } else {
+        for (int k = 0; k < SHADE_KINDS; ++k) Q.counts[kCntShade0 + k] = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Material::compute_scattering_functions for the three material kinds with dedicated kernels
+template <int KIND> struct BsdfFor;
+template <> struct BsdfFor<SHADE_MATTE> { typedef BSDF<1, 0> type; };
+template <> struct BsdfFor<SHADE_MIRROR> { typedef BSDF<0, 1> type; };
+template <> struct BsdfFor<SHADE_GLASS> { typedef BSDF<0, 2> type; };
+
+template <int KIND>
+CP_DEV void build_bsdf(const DevScene& sc, const DevMaterial& m, const ShapePoint& sp, typename BsdfFor<KIND>::type& b) {
+    b.init(sp.n);
+    if constexpr (KIND == SHADE_MATTE) {   // matte.rs:17-28
+        Spec kd = tex_eval(sc, m.tex[0], sp.uv);
+        float sigma = rclamp(tex_eval(sc, m.tex[1], sp.uv).r, 0.f, 90.f);
+        Lobe& l = b.lobes[0]; b.n_lobes = 1;
+        l.r = kd;
+        if (sigma == 0.f) { l.kind = LOBE_LAMBERT_R; l.a = 0.f; l.b = 0.f; }
+        else {   // OrenNayar::new (oren_nayar.rs:8-16)
+            l.kind = LOBE_OREN_NAYAR;
+            float s = sigma * (kPi / 180.f), s2 = s * s;
+            l.a = 1.f - (s2 / (2.f * (s + 0.33f)));
+            l.b = 0.45f * s2 / (s2 + 0.09f);
+        }
+    } else if constexpr (KIND == SHADE_MIRROR) {   // mirror.rs:15-23
+        DeltaLobe& d = b.deltas[0]; b.n_deltas = 1;
+        d.kind = DELTA_SPEC_R_NOOP; d.r = tex_eval(sc, m.tex[0], sp.uv); d.eta_a = 1.f; d.eta_b = 1.f;
+    } else {   // glass.rs:17-29
+        Spec r = tex_eval(sc, m.tex[0], sp.uv), t = tex_eval(sc, m.tex[1], sp.uv);
+        float eta = tex_eval(sc, m.tex[2], sp.uv).r;
+        b.n_deltas = 2;
+        b.deltas[0].kind = DELTA_SPEC_R_DIELECTRIC; b.deltas[0].r = r; b.deltas[0].eta_a = 1.f; b.deltas[0].eta_b = eta;
+        b.deltas[1].kind = DELTA_SPEC_T; b.deltas[1].r = t; b.deltas[1].eta_a = 1.f; b.deltas[1].eta_b = eta;
+    }
+}
+
+// uniform_sample_one_light (integrator/mod.rs:13-97) up to the point where its two rays are
+// needed: the light term is stored assuming visibility (the shadow stage zeroes it), the BSDF
+// term is finished by the closest-hit stage.  Returns the pending flags.
+template <class B>
+CP_DEV void emit_direct_lighting(const DevScene& sc, const PathArrays& P, const Queues& Q, int next, uint32_t pid, bool lane_active,
+                                 const ShapePoint& sp, const B& bsdf, V3 wo, SamplerState& st, Spec beta) {
+    bool want_shadow = false, want_mis = false;
+    if (lane_active) {
+        uint32_t flags = kPendAny;
+        if (sc.n_lights != 0) {
+            const uint32_t li = sampler_get_usize(sc.sampler, st, sc.n_lights);
+            const DevLight& light = sc.lights[li];
+            const V3 n = sp.n;
+            LightSample ls = light_sample_li(sc, light, sp, st);
+            if (ls.has_li && ls.pdf != 0.f) {
+                Spec f; float f_pdf;
+                if (bsdf.no_delta_f_pdf(wo, ls.wi, &f, &f_pdf) && f_pdf != 0.f) {
+                    Spec ld;
+                    if (light_is_delta(light)) ld = ls.li * f * fabsf(dot(n, ls.wi)) / ls.pdf;
+                    else ld = ls.li * f * fabsf(dot(n, ls.wi)) * power_heuristic(ls.pdf, f_pdf) / ls.pdf;
+                    P.sh_o[pid] = mk4(ls.vis.o, ls.vis.t_max);
+                    P.sh_d[pid] = mk4(ls.vis.d, 0.f);
+                    P.nee_light[pid] = mk4(ld, 0.f);
+                    flags |= kPendLight;
+                    want_shadow = true;
+                }
+            }
+            if (!light_is_delta(light)) {
+                P2 u = sampler_get_2d(sc.sampler, st);
+                V3 wi; Spec f; float f_pdf;
+                if (bsdf.sample_no_delta_f(wo, u, &wi, &f, &f_pdf) && f_pdf != 0.f) {
+                    const V3 o = point_offset_by_error(sp, wi);   // Ray::new_shape_point_d
+                    const Spec A = spec3(light.L[0], light.L[1], light.L[2]) * f * fabsf(dot(n, wi));
+                    P.mis_o[pid] = mk4(o, f_pdf);
+                    P.mis_d[pid] = mk4(wi, __uint_as_float(li));
+                    P.mis_A[pid] = mk4(A, 0.f);
+                    P.mis_p[pid] = mk4(sp.p, 0.f);
+                    P.nee_bsdf[pid] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    flags |= kPendMis;
+                    want_mis = true;
+                }
+            }
+        }
+        P.beta_prev[pid] = mk4(beta, __uint_as_float(flags));
+    }
+    queue_push(Q.shadow, &Q.counts[kCntShadow], want_shadow, pid);
+    queue_push(Q.closest[next], &Q.counts[kCntClosest0 + next], want_mis, pid | kMisRayBit);
+}
+
+// Hits that end a path without a BSDF: misses, emissive primitives, and (path integrator)
+// hits at bounce == max_depth.  path.rs:21-33, direct_light.rs:32-39.
+__global__ void k_shade_terminal(DevScene sc, PathArrays P, Queues Q) {
+    const uint32_t n = Q.counts[kCntShade0 + SHADE_TERMINAL];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t pid = Q.shade[SHADE_TERMINAL][i];
+        Spec L = resolve_pending(sc, P, pid, f4_rgb(P.L[pid]));
+        const uint32_t flags = __float_as_uint(P.ray_d[pid].w);
+        const uint32_t bounce = flags & 0xFFu;
+        const uint32_t slot = P.hit_slot[pid];
+        const Spec beta = sc.integrator == 0 ? f4_rgb(P.beta[pid]) : spec(1.f);
+        if (sc.integrator != 0 || bounce == 0 || (flags & kFlagSpecular)) {
+            if (slot != 0xFFFFFFFFu) {
+                const uint32_t src = __float_as_uint(__ldg(&sc.prims[3ull * slot + 2].w));
+                Spec le = spec(0.f);   // intersect.le(): None for material primitives
+                if (src & kSourceLight) { const DevLight& l = sc.lights[src & ~kSourceLight]; le = spec3(l.L[0], l.L[1], l.L[2]); }
+                L = sc.integrator == 0 ? L + beta * le : L + le;
+            } else {
+                // le_out_scene of every light: None (-> 0) for area, point and distant lights
+                for (uint32_t k = 0; k < sc.n_lights; ++k) L = sc.integrator == 0 ? L + beta * spec(0.f) : L + spec(0.f);
+            }
+        }
+        P.L[pid] = mk4(L, 0.f);
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(128) k_shade(DevScene sc, PathArrays P, Queues Q, int next) {
+    typedef typename BsdfFor<KIND>::type B;
+    const uint32_t n = Q.counts[kCntShade0 + KIND];
+    const uint32_t n_round = (n + 31u) & ~31u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        const bool active = i < n;
+        uint32_t pid = 0;
+        bool cont = false;
+        ShapePoint sp; B bsdf; V3 wo = v3(0.f, 0.f, 0.f); SamplerState st; st.index = 0; st.dim = 0;
+        Spec beta = spec(1.f), L = spec(0.f);
+        uint32_t bounce = 0, flags = 0;
+        float4 rd = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (active) {
+            pid = Q.shade[KIND][i];
+            L = resolve_pending(sc, P, pid, f4_rgb(P.L[pid]));
+            const float4 ro = P.ray_o[pid];
+            rd = P.ray_d[pid];
+            flags = __float_as_uint(rd.w);
+            bounce = flags & 0xFFu;
+            beta = f4_rgb(P.beta[pid]);
+            const uint2 si = P.smp_index[pid];
+            st.index = ((uint64_t)si.y << 32) | si.x; st.dim = P.smp_dim[pid];
+            const uint32_t slot = P.hit_slot[pid];
+            Ray ray; ray.o = f4_xyz(ro); ray.d = f4_xyz(rd); ray.t_max = kFloatMax;
+            const PrimRecord pr = load_prim(sc, slot);
+            sp = prim_shape_point(sc, slot, pr, ray, P.hit_t[pid]);
+            build_bsdf<KIND>(sc, sc.materials[prim_source(pr)], sp, bsdf);
+            if (sc.integrator == 0) {
+                if (bounce == 0 || (flags & kFlagSpecular)) L = L + beta * spec(0.f);   // intersect.le() == None
+                wo = -ray.d;
+            } else {
+                wo = -normalize(ray.d);
+            }
+        }
+        // direct lighting: the path integrator skips it for all-delta BSDFs (path.rs:37),
+        // the direct-lighting integrator does not (direct_light.rs:25)
+        const bool do_nee = active && (sc.integrator != 0 || bsdf.n_lobes != 0);
+        emit_direct_lighting(sc, P, Q, next, pid, do_nee, sp, bsdf, wo, st, sc.integrator == 0 ? beta : spec(1.f));
+        if (active && sc.integrator == 0) {
+            V3 wi; Spec f; float f_pdf; bool is_delta;
+            if (bsdf.sample_f(sc.sampler, st, wo, &wi, &f, &f_pdf, &is_delta) && f_pdf != 0.f) {
+                beta = beta * (f * fabsf(dot(wi, sp.n)) / f_pdf);
+                const V3 o = point_offset_by_error(sp, wi);
+                cont = true;
+                if (bounce > 3) {   // Russian roulette (path.rs:47-56)
+                    const float q = rmax(0.05f, 1.f - lum(beta));
+                    if (sampler_get_1d(sc.sampler, st) < q) cont = false;
+                    else beta = beta / (1.f - q);
+                }
+                if (cont) {
+                    P.ray_o[pid] = mk4(o, 0.f);
+                    P.ray_d[pid] = mk4(wi, __uint_as_float((bounce + 1u) | (is_delta ? kFlagSpecular : 0u)));
+                    P.beta[pid] = mk4(beta, 0.f);
+                    P.smp_index[pid] = make_uint2((uint32_t)st.index, (uint32_t)(st.index >> 32));
+                    P.smp_dim[pid] = st.dim;
+                }
+            }
+        }
+        if (active) P.L[pid] = mk4(L, 0.f);
+        queue_push(Q.closest[next], &Q.counts[kCntClosest0 + next], cont, pid);
+    }
+}
+
+// End of a pass: flush the last pending direct-lighting term of every path, drop NaN samples
+// and add the rest to the pixel's running sum in sample order (render.rs:34-43, film.rs:11-15).
+__global__ void k_film(DevScene sc, PixelArrays px, PathArrays P, uint32_t S, Totals* totals) {
+    const uint32_t npix = sc.width * sc.height;
+    unsigned long long dropped = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x) {
+        float4 acc = px.sum[i];
+        Spec sum = f4_rgb(acc);
+        uint32_t kept = __float_as_uint(acc.w);
+        for (uint32_t s = 0; s < S; ++s) {
+            const uint32_t pid = s * npix + i;
+            Spec L = resolve_pending(sc, P, pid, f4_rgb(P.L[pid]));
+            if (has_nan(L)) ++dropped; else { sum = sum + L; ++kept; }
+        }
+        px.sum[i] = mk4(sum, __uint_as_float(kept));
+    }
+    if (dropped) atomicAdd(&totals->nan_dropped, dropped);
+}
+
+// Film: mean of the kept samples, added into a zeroed pixel (film.rs:16, 7-10, 60-64).
+//   mode 0  write the raw accumulator {sum.rgb, count as float} (4 floats / pixel): what each
+//           GPU contributes to the NCCL reduce
+//   mode 1  resolve this GPU's own accumulator (count kept as integer bits)
+//   mode 2  resolve a reduced accumulator (count is a float) -- the consumer of the reduce
+__global__ void k_film_resolve(DevScene sc, const float4* __restrict__ sum, float* __restrict__ out, int mode) {
+    const uint32_t npix = sc.width * sc.height;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x) {
+        const float4 a = sum[i];
+        if (mode == 0) {
+            out[4ull * i] = a.x; out[4ull * i + 1] = a.y; out[4ull * i + 2] = a.z; out[4ull * i + 3] = (float)__float_as_uint(a.w);
+        } else {
+            const float n = mode == 1 ? (float)__float_as_uint(a.w) : a.w;
+            out[3ull * i] = 0.f + a.x / n; out[3ull * i + 1] = 0.f + a.y / n; out[3ull * i + 2] = 0.f + a.z / n;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Batch entry points used by the parity tests and the traversal benchmark.
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_batch_closest(DevScene sc, const float4* __restrict__ rays, uint64_t n, float4* __restrict__ hits,
+                                                       unsigned long long* counters, Totals* totals) {
+    uint32_t overflow = 0;
+    TraceStats ts; ts.parent_visits = 0; ts.prim_tests = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const float4 a = __ldg(&rays[2 * i]), b = __ldg(&rays[2 * i + 1]);
+        Ray ray; ray.o = v3(a.x, a.y, a.z); ray.t_max = a.w; ray.d = v3(b.x, b.y, b.z);
+        float t;
+        const uint32_t slot = bvh_closest<COUNT>(sc, ray, &t, &ts, &overflow);
+        float4 h = make_float4(0.f, __uint_as_float(0xFFFFFFFFu), 0.f, 0.f);
+        if (slot != 0xFFFFFFFFu) {
+            const PrimRecord pr = load_prim(sc, slot);
+            ShapePoint sp = prim_shape_point(sc, slot, pr, ray, t);
+            h = make_float4(t, __uint_as_float(prim_upload_index(pr)), sp.uv.x, sp.uv.y);
+        }
+        hits[i] = h;
+    }
+    if (COUNT) { atomicAdd(&counters[0], (unsigned long long)ts.parent_visits); atomicAdd(&counters[1], (unsigned long long)ts.prim_tests); }
+    if (overflow) atomicAdd(&totals->overflow, 1ull);
+}
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_batch_any(DevScene sc, const float4* __restrict__ rays, uint64_t n, uint8_t* __restrict__ out,
+                                                   unsigned long long* counters, Totals* totals) {
+    uint32_t overflow = 0;
+    TraceStats ts; ts.parent_visits = 0; ts.prim_tests = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const float4 a = __ldg(&rays[2 * i]), b = __ldg(&rays[2 * i + 1]);
+        Ray ray; ray.o = v3(a.x, a.y, a.z); ray.t_max = a.w; ray.d = v3(b.x, b.y, b.z);
+        out[i] = bvh_any<COUNT>(sc, ray, &ts, &overflow) ? 1 : 0;
+    }
+    if (COUNT) { atomicAdd(&counters[0], (unsigned long long)ts.parent_visits); atomicAdd(&counters[1], (unsigned long long)ts.prim_tests); }
+    if (overflow) atomicAdd(&totals->overflow, 1ull);
+}
+
+__global__ void k_batch_halton(DevScene sc, const uint32_t* __restrict__ px, const uint32_t* __restrict__ py, const uint32_t* __restrict__ sample,
+                               const uint32_t* __restrict__ dim, uint64_t n, unsigned long long* __restrict__ index_out, float* __restrict__ value_out) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        SamplerState st;
+        st.index = halton_pixel_index(sc.sampler, px[i], py[i]) + (uint64_t)sample[i] * sc.sampler.stride;
+        st.dim = dim[i];
+        if (index_out) index_out[i] = st.index;
+        if (value_out) value_out[i] = sampler_get_sample(sc.sampler, st);
+    }
+}
+
+__global__ void k_batch_camera_rays(DevScene sc, uint32_t sample, float4* __restrict__ rays) {
+    const uint32_t npix = sc.width * sc.height;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x) {
+        const uint32_t x = i % sc.width, y = i / sc.width;
+        const uint64_t base = halton_pixel_index(sc.sampler, x, y);
+        P2 film; film.x = (float)x; film.y = (float)y;
+        Ray r; r.o = v3(0.f, 0.f, 0.f); r.d = v3(0.f, 0.f, 0.f); r.t_max = kFloatMax;
+        for (uint32_t k = 0; k <= sample; ++k) {
+            SamplerState st; st.index = base + (uint64_t)k * sc.sampler.stride; st.dim = 0;
+            P2 u = sampler_get_2d(sc.sampler, st);
+            film.x += u.x - 0.5f; film.y += u.y - 0.5f;
+            if (k == sample) r = camera_generate_ray(sc, film, st);
+        }
+        rays[2ull * i] = mk4(r.o, r.t_max);
+        rays[2ull * i + 1] = mk4(r.d, 0.f);
+    }
+}
+
+}  // namespace cpbrt

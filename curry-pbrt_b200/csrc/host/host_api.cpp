@@ -4,6 +4,7 @@
 #include <string>
 
 #include "scene_host.h"
+#include "../bvh_build.h"
 
 using namespace cpbrt_host;
 
@@ -78,4 +79,45 @@ int cpbrt_write_png(const char* path, const float* film_rgb, uint32_t width, uin
     return CPBRT_OK;
 }
 
+// Aggregate::build without a device: the same exact-SAH builder cpbrt_build_bvh runs, so the
+// primitive order / node list can be checked (and reused by a host) on a machine with no GPU.
+int cpbrt_host_build_bvh(const cpbrt_scene_desc* d, uint32_t* prim_order_out, cpbrt_bvh_dump* nodes_out) {
+    if (!d) { g_host_error = "null scene description"; return CPBRT_ERR_BAD_ARG; }
+    try {
+        std::vector<cpbrt::BuildBounds> bounds;
+        cpbrt::primitive_bounds(d->primitives, d->n_primitives, d->triangles, d->sphere_radius, d->transforms, &bounds);
+        cpbrt::BvhBuildResult r;
+        cpbrt::build_sah_bvh(bounds, 0, &r);
+        if (!cpbrt::export_bvh(r, prim_order_out, nodes_out)) { g_host_error = "bvh dump capacity too small"; return CPBRT_ERR_BAD_ARG; }
+    } catch (const std::exception& e) {
+        g_host_error = e.what();
+        return CPBRT_ERR_BAD_ARG;
+    }
+    return CPBRT_OK;
+}
+
 }  // extern "C"
+
+// render_from_file (src/render.rs:63-82): parse, clip, build the aggregate, render on the GPU,
+// write the Film's PNG and print its file name.
+extern "C" int cpbrt_render_from_file(const char* pbrt_path, int device_id) {
+    cpbrt_scene* scene = nullptr;
+    int rc = cpbrt_scene_load(pbrt_path, 1, &scene);
+    if (rc != CPBRT_OK) return rc;
+    cpbrt_ctx* ctx = nullptr;
+    rc = cpbrt_create(&ctx, device_id);
+    if (rc != CPBRT_OK) { g_host_error = cpbrt_last_error(nullptr); cpbrt_scene_free(scene); return rc; }
+    const cpbrt_scene_desc* d = cpbrt_scene_get_desc(scene);
+    std::vector<float> film((size_t)d->film_width * d->film_height * 3);
+    rc = cpbrt_upload_scene(ctx, d);
+    if (rc == CPBRT_OK) rc = cpbrt_build_bvh(ctx, nullptr, nullptr);
+    if (rc == CPBRT_OK) rc = cpbrt_render(ctx, nullptr, film.data(), nullptr);
+    if (rc != CPBRT_OK) g_host_error = cpbrt_last_error(ctx);
+    if (rc == CPBRT_OK) {
+        rc = cpbrt_write_png(scene->data.film_filename.c_str(), film.data(), d->film_width, d->film_height);
+        if (rc == CPBRT_OK) printf("%s\n", scene->data.film_filename.c_str());
+    }
+    cpbrt_destroy(ctx);
+    cpbrt_scene_free(scene);
+    return rc;
+}

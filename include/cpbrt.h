@@ -211,6 +211,8 @@ typedef struct cpbrt_render_params {
     uint32_t resolve;                   /* 1 = divide by the valid-sample count (film.rs:16); 0 = leave sums */
     uint32_t samples_per_pass;          /* 0 = auto */
     uint32_t film_on_device;            /* 1 = film_rgb_out is a device pointer */
+    uint32_t profile_stages;            /* 1 = bracket every stage with CUDA events and fill ms_trace / ms_shade /
+                                           ms_raygen_film and the *_launches counts (a little slower) */
 } cpbrt_render_params;
 
 typedef struct cpbrt_stats {
@@ -226,6 +228,9 @@ typedef struct cpbrt_stats {
     double   ms_reduce;             /* NCCL film reduce + resolve */
     uint64_t trace_parent_visits;   /* only filled by cpbrt_trace_* with counting on */
     uint64_t trace_prim_tests;
+    uint64_t trace_launches;        /* profile_stages: launches of the closest-hit traversal kernel */
+    double   ms_trace_closest;      /* profile_stages: device time inside those launches */
+    double   ms_trace_shadow;
 } cpbrt_stats;
 
 /* ------------------------------------------------------------------------------------------
@@ -291,6 +296,10 @@ const char* cpbrt_host_last_error(void);
 /* Overrides (the reference takes these from the file only): */
 int cpbrt_scene_set_spp(cpbrt_scene* scene, uint32_t spp);
 int cpbrt_scene_set_integrator(cpbrt_scene* scene, uint32_t integrator, uint32_t max_depth);
+
+/* Aggregate::build (src/aggregate/bvh.rs:194-207) on the host, no device involved: the same
+ * exact-SAH builder cpbrt_build_bvh uses.  Outputs as for cpbrt_build_bvh. */
+int cpbrt_host_build_bvh(const cpbrt_scene_desc* desc, uint32_t* prim_order_out, cpbrt_bvh_dump* nodes_out);
 
 /* Fisher-Yates per prime block driven by a 64-bit LCG (x <- x*6364136223846793005 +
  * 1442695040888963407); stands in for the reference's thread_rng shuffle (halton.rs:216-231). */

@@ -1155,9 +1155,9 @@ static LightSample light_sample_li(const World& w, uint32_t li, const ShapePoint
 // =============================================================================================
 // Integrators (src/integrator/*.rs)
 // =============================================================================================
-struct RenderCounters { uint64_t rays_closest = 0, rays_any = 0, nan_dropped = 0; };
+struct RenderCounters { uint64_t rays_closest = 0, rays_any = 0, nan_dropped = 0; TraceCounters closest, any; bool count_visits = false; };
 
-static Hit trace(const World& w, const Ray& r, RenderCounters& c) { ++c.rays_closest; return scene_intersect(w.scene, r); }
+static Hit trace(const World& w, const Ray& r, RenderCounters& c) { ++c.rays_closest; return scene_intersect(w.scene, r, c.count_visits ? &c.closest : nullptr); }
 
 // uniform_sample_one_light (integrator/mod.rs:13-97)
 static Spectrum uniform_sample_one_light(const World& w, const ShapePoint& sp, const BSDF& bsdf, V3 wo, Sampler& smp, RenderCounters& c) {
@@ -1173,7 +1173,7 @@ static Spectrum uniform_sample_one_light(const World& w, const ShapePoint& sp, c
             Spectrum f; Float f_pdf;
             if (bsdf.no_delta_f_pdf(wo, ls.wi, &f, &f_pdf) && f_pdf != 0.f) {
                 ++c.rays_any;
-                if (!scene_intersect_predicate(sc, ls.vis)) {
+                if (!scene_intersect_predicate(sc, ls.vis, c.count_visits ? &c.any : nullptr)) {
                     Spectrum ld;
                     if (light_is_delta(light)) ld = ls.li * f * std::fabs(dot(n, ls.wi)) / ls.pdf;
                     else ld = ls.li * f * std::fabs(dot(n, ls.wi)) * power_heuristic(ls.pdf, f_pdf) / ls.pdf;
@@ -1349,7 +1349,7 @@ static void render(const World& w, const RenderOptions& opt, Float* film, Render
     std::atomic<size_t> next(0);
     std::mutex mu;
     auto worker = [&]() {
-        RenderCounters c;
+        RenderCounters c; c.count_visits = total->count_visits;
         Sampler smp; smp.cfg = &d->sampler; smp.index = 0; smp.dim = 0;   // sampler.box_clone() (render.rs:22)
         for (;;) {
             size_t j = next.fetch_add(1);
@@ -1361,6 +1361,8 @@ static void render(const World& w, const RenderOptions& opt, Float* film, Render
         }
         std::lock_guard<std::mutex> g(mu);
         total->rays_closest += c.rays_closest; total->rays_any += c.rays_any; total->nan_dropped += c.nan_dropped;
+        total->closest.parent_visits += c.closest.parent_visits; total->closest.prim_tests += c.closest.prim_tests;
+        total->any.parent_visits += c.any.parent_visits; total->any.prim_tests += c.any.prim_tests;
     };
     uint32_t nt = opt.threads ? opt.threads : std::max(1u, std::thread::hardware_concurrency());
     std::vector<std::thread> pool;
@@ -1485,9 +1487,11 @@ void orc_trace_closest_plain(const orc_world* o, const cpbrt_ray* rays, uint64_t
 
 // Renders pixels [x0,x1) x [y0,y1) (0,0,0,0 = whole film) into film (W*H*3, untouched outside
 // the rectangle).  integrator / max_depth < 0 = take them from the description.
-// stats_out: [0] rays_closest [1] rays_any [2] nan_dropped ; returns render seconds.
+// stats_out: [0] rays_closest [1] rays_any [2] nan_dropped, and when count_visits != 0 also
+// [3] closest Parent visits [4] closest primitive tests [5] any-hit Parent visits [6] any-hit
+// primitive tests (the algorithmic traversal work of SURVEY 8d); returns render seconds.
 double orc_render(const orc_world* o, int integrator, int max_depth, uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1,
-                  uint32_t threads, float* film, uint64_t* stats_out) {
+                  uint32_t threads, float* film, uint64_t* stats_out, int count_visits) {
     const cpbrt_scene_desc* d = o->w.scene.d;
     RenderOptions opt;
     opt.integrator = integrator < 0 ? d->integrator : (uint32_t)integrator;
@@ -1495,11 +1499,14 @@ double orc_render(const orc_world* o, int integrator, int max_depth, uint32_t x0
     if (x1 == 0 && y1 == 0) { x1 = d->film_width; y1 = d->film_height; }
     opt.x0 = x0; opt.y0 = y0; opt.x1 = std::min(x1, d->film_width); opt.y1 = std::min(y1, d->film_height);
     opt.threads = threads;
-    RenderCounters c;
+    RenderCounters c; c.count_visits = count_visits != 0;
     auto t0 = std::chrono::steady_clock::now();
     render(o->w, opt, film, &c);
     double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    if (stats_out) { stats_out[0] = c.rays_closest; stats_out[1] = c.rays_any; stats_out[2] = c.nan_dropped; }
+    if (stats_out) {
+        stats_out[0] = c.rays_closest; stats_out[1] = c.rays_any; stats_out[2] = c.nan_dropped;
+        if (count_visits) { stats_out[3] = c.closest.parent_visits; stats_out[4] = c.closest.prim_tests; stats_out[5] = c.any.parent_visits; stats_out[6] = c.any.prim_tests; }
+    }
     return sec;
 }
 

@@ -1,0 +1,67 @@
+"""The C-ABI library loads without a GPU, exports every symbol include/cpbrt.h declares, and
+refuses to compute without a device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_every_declared_symbol_is_exported(cpbrt):
+    header = open(os.path.join(ROOT, "include", "cpbrt.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(cpbrt_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 20
+    for name in sorted(declared):
+        assert hasattr(cpbrt.lib, name), "libcpbrt.so does not export " + name
+    assert declared == set(cpbrt.abi.ALL_SYMBOLS), "ctypes prototypes out of sync with the header"
+
+
+def test_struct_sizes_match_header(cpbrt):
+    abi = cpbrt.abi
+    assert C.sizeof(abi.Ray) == 32 and C.sizeof(abi.Hit) == 16
+    assert C.sizeof(abi.Transform) == 144
+    assert C.sizeof(abi.Triangle) == 60
+    assert C.sizeof(abi.Primitive) == 24
+
+
+def test_no_device_means_error_not_fallback(cpbrt):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    ctx = C.c_void_p()
+    rc = cpbrt.lib.cpbrt_create(C.byref(ctx), 0)
+    assert rc == cpbrt.abi.ERR_NO_DEVICE
+    assert b"CUDA" in cpbrt.lib.cpbrt_last_error(None)
+    # compute entry points reject a null context
+    assert cpbrt.lib.cpbrt_render(None, None, None, None) == cpbrt.abi.ERR_BAD_CTX
+    assert cpbrt.lib.cpbrt_trace_closest(None, None, 0, None, 0, None) == cpbrt.abi.ERR_BAD_CTX
+    with pytest.raises(cpbrt.CpbrtError):
+        cpbrt.Renderer(0)
+
+
+def test_parse_errors_are_codes_not_crashes(cpbrt):
+    with pytest.raises(cpbrt.CpbrtError) as e:
+        cpbrt.Scene.load("/nonexistent/scene.pbrt")
+    assert e.value.code == cpbrt.abi.ERR_PARSE
+    with pytest.raises(cpbrt.CpbrtError):
+        cpbrt.Scene.parse('Camera "perspective"\nWorldBegin\nWorldEnd\n')          # no Sampler
+    with pytest.raises(cpbrt.CpbrtError):
+        cpbrt.Scene.parse('Camera "perspective" "float fov" [40\n')                 # unpaired [ then EOF word
+
+
+def test_write_png_roundtrip(cpbrt, tmp_path):
+    from PIL import Image
+    film = np.zeros((4, 6, 3), np.float32)
+    film[..., 0] = 0.5; film[1, 2] = (1.0, 0.0031308, 2.0); film[0, 0] = (-1.0, np.nan, 0.001)
+    path = str(tmp_path / "x.png")
+    cpbrt.write_png(path, film)
+    img = np.asarray(Image.open(path))
+    assert img.shape == (4, 6, 3)
+    # gamma_correct(0.5) = 1.055*0.5^(1/2.4)-0.055 = 0.7354 -> 188
+    assert img[2, 2, 0] == 188
+    assert tuple(img[1, 2]) == (255, int(12.92 * 0.0031308 * 255 + 0.5), 255)
+    assert tuple(img[0, 0]) == (0, 0, int(12.92 * 0.001 * 255 + 0.5))

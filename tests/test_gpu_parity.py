@@ -1,0 +1,285 @@
+"""Parity of the CUDA path (through the C-ABI) with the CPU oracle.
+
+Bars (BASELINE.json north_star): Halton indices, BVH primitive order and first-hit primitive
+ids bit-exact; first-hit shading within 1e-3 relative per pixel; full-path images within the
+Monte-Carlo noise band (here they are in fact compared per pixel, because oracle and GPU share
+the permutation table and the float operation order).
+"""
+import numpy as np
+import pytest
+
+from conftest import SCENES, lcg_rays, scene_text
+from test_oracle import _synthetic_mesh_scene
+
+pytestmark = pytest.mark.gpu
+
+NO_HIT = 0xFFFFFFFF
+
+
+@pytest.fixture(scope="module")
+def cornell(cpbrt, oracle, make_scene):
+    scene = make_scene("cornel_box.pbrt", xres=128, yres=128, spp=8)
+    r = cpbrt.Renderer(0)
+    r.upload(scene)
+    order = r.build_bvh()
+    return scene, r, oracle.OracleWorld(scene), order
+
+
+@pytest.fixture(scope="module")
+def spheres(cpbrt, oracle, make_scene):
+    scene = make_scene("sphere.pbrt", xres=160, yres=90, spp=8)
+    r = cpbrt.Renderer(0)
+    r.upload(scene)
+    order = r.build_bvh()
+    return scene, r, oracle.OracleWorld(scene), order
+
+
+@pytest.fixture(scope="module")
+def mesh(cpbrt, oracle):
+    scene = cpbrt.Scene.parse(_synthetic_mesh_scene(120, 100, res=96))
+    r = cpbrt.Renderer(0)
+    r.upload(scene)
+    order = r.build_bvh()
+    return scene, r, oracle.OracleWorld(scene), order
+
+
+def edge_case_rays():
+    """Hand-made hard cases: axis-aligned directions with zero components, rays
+    through shared quad diagonals / vertices / edges of the Cornell walls, rays starting on
+    surfaces and on box planes, zero-length and huge t_max."""
+    rays = []
+    fmax = np.finfo(np.float32).max
+    for ox in (0.0, 100.0, 278.0, 549.6, 556.0):
+        for oz in (0.0, 100.0, 279.6, 559.2):
+            for d in ((0, 1, 0), (0, -1, 0), (1, 0, 0), (-1, 0, 0), (0, 0, 1), (0, 0, -1), (0, -0.0, 1)):
+                rays.append((ox, 273.0, oz, fmax) + d + (0.0,))
+    # through the diagonal of the floor / back wall / ceiling quads and their corners
+    for t in np.linspace(0, 1, 41):
+        x, z = 552.8 * t, 559.2 * t
+        rays.append((x, 300.0, z, fmax, 0, -1, 0, 0))
+        rays.append((x, 100.0, z, fmax, 0, 1, 0, 0))
+        rays.append((549.6 * t, 548.8 * t, -100.0, fmax, 0, 0, 1, 0))
+        rays.append((278.0, 273.0, -800.0, fmax, x - 278.0, -273.0, z + 800.0, 0))
+    # starting exactly on geometry, short t_max
+    for tm in (0.0, 1e-6, 1.0, 547.0, 548.8, 1e30):
+        rays.append((278.0, 0.0, 279.0, tm, 0, 1, 0, 0))
+        rays.append((278.0, 548.8, 279.0, tm, 0, -1, 0, 0))
+    # glass sphere: centre, tangent, from inside
+    for dx in (0.0, 82.5, 82.4999, 82.5001, 40.0):
+        rays.append((188.0 + dx, 247.5, -800.0, fmax, 0, 0, 1, 0))
+    rays.append((188.0, 247.5, 176.5, fmax, 0.3, 0.4, 0.5, 0))
+    a = np.array(rays, np.float32)
+    reps = int(np.ceil(4096 / len(a)))
+    jitter = np.tile(a, (reps, 1))[:4096]
+    # later copies: scaled (unnormalised) directions -- t changes, the hit must not
+    scale = np.repeat(np.float32(2.0) ** np.arange(reps, dtype=np.float32), len(a))[:4096]
+    jitter[:, 4:7] *= scale[:, None]
+    return jitter
+
+
+def test_halton_bit_exact(cornell):
+    _, r, w, _ = cornell
+    rng = np.random.RandomState(1)
+    n = 200000
+    px = rng.randint(0, r.width, n).astype(np.uint32); py = rng.randint(0, r.height, n).astype(np.uint32)
+    sample = rng.randint(0, 1 << 20, n).astype(np.uint32)        # indices far beyond 2^32
+    dim = rng.randint(0, 1000, n).astype(np.uint32)
+    dim[:1000] = np.arange(1000)
+    gi, gv = r.halton(px, py, sample, dim)
+    oi, ov = w.halton(px, py, sample, dim)
+    assert gi.max() > 2 ** 32
+    assert np.array_equal(gi, oi)
+    assert np.array_equal(gv.view(np.uint32), ov.view(np.uint32))
+
+
+def test_halton_every_pixel_base_index(spheres):
+    _, r, w, _ = spheres
+    ys, xs = np.mgrid[0:r.height, 0:r.width]
+    px, py = xs.ravel().astype(np.uint32), ys.ravel().astype(np.uint32)
+    z = np.zeros_like(px)
+    gi, _ = r.halton(px, py, z, z)
+    oi, _ = w.halton(px, py, z, z)
+    assert np.array_equal(gi, oi)
+    assert len(np.unique(gi)) == len(gi)
+
+
+@pytest.mark.parametrize("sample", [0, 5])
+def test_camera_rays_bit_exact(cornell, spheres, sample):
+    for _, r, w, _ in (cornell, spheres):
+        assert np.array_equal(r.camera_rays(sample).view(np.uint32), w.camera_rays(sample).view(np.uint32))
+
+
+def test_bvh_order_and_nodes_bit_exact(cpbrt, cornell, spheres, mesh):
+    for scene, r, w, order in (cornell, spheres, mesh):
+        assert np.array_equal(order, w.bvh_order())
+        _, nodes = r.build_bvh(want_nodes=True)
+        ref = w.bvh_nodes()
+        assert nodes["root"] == ref["root"]
+        for k in ("is_leaf", "axis", "a", "b"):
+            assert np.array_equal(nodes[k], ref[k]), k
+        assert np.array_equal(nodes["bound"].view(np.uint32), ref["bound"].view(np.uint32))
+
+
+def _check_closest(r, w, rays):
+    g, gs = r.trace_closest(rays, count=True)
+    o, oc = w.trace_closest(rays, count=True)
+    assert np.array_equal(g["prim"], o["prim"])
+    assert np.array_equal(g["t"].view(np.uint32), o["t"].view(np.uint32))
+    hit = o["prim"] != NO_HIT
+    # uv goes through atan2/acos for spheres: tolerance; triangles are exact
+    np.testing.assert_allclose(g["u"][hit], o["u"][hit], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(g["v"][hit], o["v"][hit], rtol=1e-5, atol=1e-6)
+    # same visiting order => same number of Parent visits and primitive tests
+    assert gs.trace_parent_visits == int(oc[0]) and gs.trace_prim_tests == int(oc[1])
+    # the uncounted kernel is the one the renderer uses
+    g2 = r.trace_closest(rays)
+    assert np.array_equal(g2["prim"], o["prim"]) and np.array_equal(g2["t"].view(np.uint32), o["t"].view(np.uint32))
+    return hit.mean()
+
+
+def test_first_hit_ids_camera_rays(cornell, spheres, mesh):
+    for _, r, w, _ in (cornell, spheres, mesh):
+        assert _check_closest(r, w, w.camera_rays(0)) > 0.3
+
+
+def test_first_hit_ids_random_rays(cornell, spheres, mesh):
+    _, r, w, _ = cornell
+    assert _check_closest(r, w, lcg_rays(1 << 18, (-50, -50, -50), (610, 600, 610), seed=7)) > 0.5
+    _, r, w, _ = mesh
+    assert _check_closest(r, w, lcg_rays(1 << 18, (-50, -50, -50), (610, 600, 610), seed=7)) > 0.3
+    _, r, w, _ = spheres
+    assert _check_closest(r, w, lcg_rays(1 << 16, (-8, -8, -2), (8, 8, 22), seed=7)) > 0.3
+
+
+def test_first_hit_ids_edge_cases(cornell):
+    _, r, w, _ = cornell
+    _check_closest(r, w, edge_case_rays())
+
+
+def test_any_hit_bit_exact(cornell, spheres, mesh):
+    for (_, r, w, _), box in ((cornell, ((-50, -50, -50), (610, 600, 610))), (mesh, ((-50, -50, -50), (610, 600, 610))),
+                              (spheres, ((-8, -8, -2), (8, 8, 22)))):
+        rays = lcg_rays(1 << 16, box[0], box[1], seed=13)
+        rays[:, 3] = np.float32(1.0 - 1e-5)            # shadow-ray convention: unnormalised d, t_max just below 1
+        rays[:, 4:7] *= np.float32(np.linalg.norm(np.subtract(box[1], box[0])) / 3)
+        g = r.trace_any(rays)
+        o = w.trace_any(rays)
+        assert np.array_equal(g, o)
+        assert 0.05 < o.mean() < 0.95
+    _, r, w, _ = cornell
+    e = edge_case_rays()
+    assert np.array_equal(r.trace_any(e), w.trace_any(e))
+
+
+def test_empty_and_ragged_batches(cornell):
+    _, r, w, _ = cornell
+    assert len(r.trace_closest(np.zeros((0, 8), np.float32))["prim"]) == 0
+    assert len(r.trace_any(np.zeros((0, 8), np.float32))) == 0
+    for n in (1, 31, 33, 129):
+        rays = lcg_rays(n, (0, 0, 0), (550, 540, 550), seed=n)
+        assert np.array_equal(r.trace_closest(rays)["prim"], w.trace_closest(rays)["prim"])
+    bad = lcg_rays(8, (0, 0, 0), (550, 540, 550), seed=3)
+    bad[0, 4:7] = 0; bad[1, 0] = np.nan; bad[2, 4] = np.inf; bad[3, 3] = -1.0
+    assert np.array_equal(r.trace_closest(bad)["prim"], w.trace_closest(bad)["prim"])
+    assert np.array_equal(r.trace_any(bad), w.trace_any(bad))
+
+
+def _relerr(a, b):
+    return np.abs(a - b) / (np.abs(b) + 1e-3)
+
+
+def test_first_hit_shading(cornell, spheres, mesh):
+    """Direct lighting at the first hit (DirectLightIntegrator depth 0): <= 1e-3 relative per
+    pixel.  A pixel may exceed it only when an ulp-level libm difference flips a discrete
+    decision (light choice, shadow test on a silhouette): bounded at 0.1% of the pixels."""
+    for _, r, w, _ in (cornell, spheres, mesh):
+        g, gs = r.render(first_hit_only=True)
+        o, _, os_ = w.render(integrator=1, max_depth=0)
+        assert gs.rays_closest == os_["rays_closest"] or abs(gs.rays_closest - os_["rays_closest"]) <= 1e-4 * os_["rays_closest"]
+        bad = (_relerr(g, o).max(axis=2) > 1e-3)
+        assert bad.mean() <= 1e-3, bad.mean()
+        assert np.isfinite(g).all() and g.mean() > 1e-3
+
+
+def test_full_path_image(cornell, mesh):
+    """PathIntegrator, maxdepth 5, NEE + MIS + Russian roulette."""
+    for _, r, w, _ in (cornell, mesh):
+        g, gs = r.render()
+        o, _, os_ = w.render()
+        bad = (_relerr(g, o).max(axis=2) > 1e-3)
+        assert bad.mean() <= 0.01, bad.mean()
+        # image-level: RMSE far inside the MC noise band (the noise itself is ~0.1-0.3 of the mean at 8 spp)
+        rmse = float(np.sqrt(np.mean((g - o) ** 2)))
+        assert rmse <= 0.02 * float(o.mean()) + 1e-4, rmse
+        assert abs(gs.rays_closest - os_["rays_closest"]) <= 2e-3 * os_["rays_closest"]
+        assert abs(gs.rays_any - os_["rays_any"]) <= 2e-3 * os_["rays_any"]
+        assert gs.nan_dropped == os_["nan_dropped"]
+
+
+def test_directlighting_scene(spheres):
+    """sphere.pbrt: directlighting maxdepth 0, point + spherical area + distant light."""
+    _, r, w, _ = spheres
+    g, gs = r.render()
+    o, _, os_ = w.render()
+    bad = (_relerr(g, o).max(axis=2) > 1e-3)
+    assert bad.mean() <= 2e-3, bad.mean()
+    assert gs.rays_any == os_["rays_any"] or abs(gs.rays_any - os_["rays_any"]) <= 1e-3 * os_["rays_any"]
+
+
+def test_sample_ranges_compose(cornell):
+    """Sample-index partition (multi-GPU layout): rendering [0,3) and [3,8) separately and
+    combining the sums equals one render of [0,8) -- including the replayed film-point drift."""
+    _, r, w, _ = cornell
+    full, _ = r.render()
+    a, sa = r.render(sample_begin=0, sample_end=3)
+    b, sb = r.render(sample_begin=3, sample_end=8)
+    assert sa.camera_samples + sb.camera_samples == r.width * r.height * 8
+    combined = (a * 3 + b * 5) / 8
+    np.testing.assert_allclose(combined, full, rtol=2e-5, atol=1e-6)
+    # different pass sizes do not change the result
+    c, _ = r.render(samples_per_pass=3)
+    assert np.array_equal(c.view(np.uint32), full.view(np.uint32))
+
+
+def test_textured_matte(cpbrt, oracle):
+    """Config C3's ingredient: Cornell walls with box-texture.png as matte Kd."""
+    text = scene_text("cornel_box.pbrt", xres=96, yres=96, spp=4)
+    text = text.replace('WorldBegin\n', 'WorldBegin\nTexture "boxtex" "spectrum" "imagemap" "string filename" "box-texture.png"\n', 1)
+    # the third Material "matte" is the white one everything else uses
+    parts = text.split('Material "matte"\n"spectrum Kd"')
+    assert len(parts) >= 5
+    head = 'Material "matte"\n"spectrum Kd"'.join(parts[:4])
+    rest = parts[4]
+    rest = rest[rest.index(']') + 1:]
+    text = head + 'Material "matte" "texture Kd" "boxtex"' + rest
+    scene = cpbrt.Scene.parse(text, base_dir=SCENES)
+    assert any(scene.desc.textures[i].kind == cpbrt.abi.TEX_IMAGE for i in range(scene.desc.n_textures))
+    r = cpbrt.Renderer(0); r.upload(scene); r.build_bvh()
+    w = oracle.OracleWorld(scene)
+    g, _ = r.render()
+    o, _, _ = w.render()
+    bad = (_relerr(g, o).max(axis=2) > 1e-3)
+    assert bad.mean() <= 0.01, bad.mean()
+
+
+def test_render_from_file_writes_png(cpbrt, tmp_path):
+    import shutil
+    from PIL import Image
+    text = scene_text("cornel_box.pbrt", xres=64, yres=48, spp=2)
+    p = tmp_path / "scene.pbrt"
+    p.write_text(text.replace("image/cornel_test.png", str(tmp_path / "out.png")))
+    cpbrt.render_from_file(str(p))
+    img = np.asarray(Image.open(tmp_path / "out.png"))
+    assert img.shape == (48, 64, 3) and img.mean() > 5
+
+
+def test_unsupported_features_fail_loudly(cpbrt):
+    head = ('Camera "perspective" "float fov" [40]\nSampler "halton" "integer pixelsamples" [1]\n'
+            'Film "image" "integer xresolution" [8] "integer yresolution" [8]\nIntegrator "path"\nWorldBegin\n')
+    scene = cpbrt.Scene.parse(head + 'Material "plastic"\nShape "sphere"\nWorldEnd\n')
+    r = cpbrt.Renderer(0)
+    with pytest.raises(cpbrt.CpbrtError) as e:
+        r.upload(scene)
+    assert e.value.code == cpbrt.abi.ERR_UNSUPPORTED
+    with pytest.raises(cpbrt.CpbrtError):
+        r.render()            # no scene / BVH yet

@@ -1,0 +1,135 @@
+"""Host parser / scene builder against facts derived from the reference's sources
+ -- not produced by a reference run."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import SCENES, scene_text
+
+
+def test_cornell_tables(cpbrt):
+    s = cpbrt.Scene.load(os.path.join(SCENES, "cornel_box.pbrt"))
+    d = s.desc
+    abi = cpbrt.abi
+    assert (d.film_width, d.film_height) == (900, 900)
+    assert d.integrator == abi.INTEGRATOR_PATH and d.max_depth == 5
+    assert d.n_primitives == 33 and d.n_triangles == 32 and d.n_spheres == 1 and d.n_lights == 2
+    assert s.film_filename == "image/cornel_test.png"
+    prims = [d.primitives[i] for i in range(33)]
+    assert [p.light for p in prims[:2]] == [0, 1] and all(p.material < 0 for p in prims[:2])
+    assert sum(p.shape.kind == abi.SHAPE_SPHERE for p in prims) == 1
+    sphere = [p for p in prims if p.shape.kind == abi.SHAPE_SPHERE][0]
+    assert d.materials[sphere.material].type == abi.MAT_GLASS
+    t = d.transforms[sphere.shape.xform]
+    assert (t.m[3], t.m[7], t.m[11]) == (188.0, 247.5, 176.5) and t.outer == -1
+    assert abs(d.sphere_radius[sphere.shape.data] - 82.5) == 0
+    assert [d.materials[p.material].type for p in prims[-10:]] == [abi.MAT_MIRROR] * 10
+    # spectrum -> RGB through from_sampled (rgb_spectrum.rs:85-96) and the CIE tables
+    np.testing.assert_allclose(list(d.lights[0].L), [18.487453, 11.010248, 2.757321], rtol=1e-5)
+    kd = lambda m: list(d.textures[d.materials[m].tex[0]].value)
+    np.testing.assert_allclose(kd(prims[2].material), [0.582553, 0.043657, 0.044207], rtol=2e-5)
+    np.testing.assert_allclose(kd(prims[4].material), [0.100772, 0.376082, 0.078298], rtol=2e-5)
+    np.testing.assert_allclose(kd(prims[6].material), [0.886975, 0.696752, 0.667831], rtol=2e-5)
+    # HaltonSampler::new(1, (900, 900))
+    assert list(d.sampler.scale) == [1024, 2187] and list(d.sampler.exp) == [10, 7]
+    assert (d.sampler.mult_inverse[0] * 2187) % 1024 == 1 and (d.sampler.mult_inverse[1] * 1024) % 2187 == 1
+    # LookAt 278 273 -800 -> camera-to-world is a pure translation here
+    c2w = np.array(list(d.camera.camera_to_world)).reshape(4, 4)
+    np.testing.assert_array_equal(c2w, [[1, 0, 0, 278], [0, 1, 0, 273], [0, 0, 1, -800], [0, 0, 0, 1]])
+
+
+def test_sphere_scene_tables(cpbrt):
+    s = cpbrt.Scene.load(os.path.join(SCENES, "sphere.pbrt"))
+    d = s.desc
+    abi = cpbrt.abi
+    assert (d.film_width, d.film_height, d.sampler.spp) == (1600, 900, 8)
+    assert d.integrator == abi.INTEGRATOR_DIRECT and d.max_depth == 0
+    assert d.n_primitives == 4 and d.n_spheres == 4
+    assert [d.lights[i].type for i in range(3)] == [abi.LIGHT_POINT, abi.LIGHT_AREA, abi.LIGHT_DISTANT]
+    assert list(d.lights[0].v) == [-1.0, 1.0, 3.0]
+    assert list(d.lights[2].v) == [0.0, 0.0, 1.0]           # normalize(to - from), translation does not move a vector
+    assert d.primitives[3].light == 1 and d.primitives[3].material == -1
+    # only the first top-level transform directive becomes the camera transform (render.rs:65)
+    c2w = np.array(list(d.camera.camera_to_world)).reshape(4, 4)
+    np.testing.assert_array_equal(c2w[:3, 3], [1, 1, -4])
+
+
+def test_perspective_works_kat(cpbrt, oracle):
+    """src/camera/perspective.rs:88-105: PerspectiveCamera::new(40, (1024, 768))."""
+    s = cpbrt.Scene.parse('Camera "perspective" "float fov" [40]\nSampler "halton" "integer pixelsamples" [1]\n'
+                          'Film "image" "integer xresolution" [1024] "integer yresolution" [768]\nIntegrator "path"\nWorldBegin\nWorldEnd\n')
+    d = s.desc
+    m = np.array(list(d.camera.camera_to_raster), np.float32).reshape(4, 4)
+    p = np.array([0, 0, 1000, 1], np.float32)
+    r = np.zeros(4, np.float32)
+    for i in range(4):
+        r[i] = np.float32(np.float32(np.float32(m[i, 0] * p[0] + m[i, 1] * p[1]) + m[i, 2] * p[2]) + m[i, 3] * p[3])
+    assert tuple(r[:3] / r[3]) == (512.0, 384.0, 1.0)
+    ray = oracle.OracleWorld(s).camera_ray_at(512.0, 384.0)
+    assert tuple(ray[:3]) == (0.0, 0.0, 0.0) and tuple(ray[4:7]) == (0.0, 0.0, 1.0) and ray[3] == np.finfo(np.float32).max
+    # the stored pair is a true inverse pair
+    inv = np.array(list(d.camera.raster_to_camera), np.float64).reshape(4, 4)
+    np.testing.assert_allclose(inv @ m.astype(np.float64), np.eye(4), atol=2e-3)
+
+
+def test_transform_semantics(cpbrt):
+    """CTM composition is new * old and Rotate is the transpose of pbrt's (Q17); instancing
+    wraps instead of composing (primitive.rs:115-130)."""
+    head = ('Camera "perspective" "float fov" [90]\nSampler "halton" "integer pixelsamples" [1]\n'
+            'Film "image" "integer xresolution" [64] "integer yresolution" [64]\nIntegrator "path"\nWorldBegin\nMaterial "matte"\n')
+    s = cpbrt.Scene.parse(head + 'AttributeBegin\nTranslate 1 2 3\nScale 2 2 2\nShape "sphere"\nAttributeEnd\nWorldEnd\n')
+    d = s.desc
+    assert d.n_primitives == 1
+    t = d.transforms[d.primitives[0].shape.xform]
+    m = np.array(list(t.m)).reshape(4, 4)
+    # new * old = Scale * Translate: the translation gets scaled
+    np.testing.assert_array_equal(m, [[2, 0, 0, 2], [0, 2, 0, 4], [0, 0, 2, 6], [0, 0, 0, 1]])
+    s = cpbrt.Scene.parse(head + 'AttributeBegin\nRotate 90 0 0 1\nShape "sphere"\nAttributeEnd\nWorldEnd\n')
+    m = np.array(list(s.desc.transforms[0].m)).reshape(4, 4)
+    np.testing.assert_allclose(m[:2, :2], [[0, 1], [-1, 0]], atol=1e-6)       # pbrt would give [[0,-1],[1,0]]
+    s = cpbrt.Scene.parse(head + 'ObjectBegin "o"\nTranslate 0 0 5\nShape "sphere"\nObjectEnd\n'
+                          'AttributeBegin\nTranslate 1 0 0\nObjectInstance "o"\nAttributeEnd\nWorldEnd\n')
+    d = s.desc
+    assert d.n_primitives == 1
+    inner = d.transforms[d.primitives[0].shape.xform]
+    assert inner.m[11] == 5.0 and inner.outer >= 0 and d.transforms[inner.outer].m[3] == 1.0
+
+
+def test_clipper_drops_offscreen_material_primitives(cpbrt):
+    """perspective.rs:54-78 tests only the bbox min and max corners; emissive primitives are kept."""
+    head = ('Camera "perspective" "float fov" [40]\nSampler "halton" "integer pixelsamples" [1]\n'
+            'Film "image" "integer xresolution" [64] "integer yresolution" [64]\nIntegrator "path"\nWorldBegin\nMaterial "matte"\n')
+    tri = lambda x: ('Shape "trianglemesh" "integer indices" [0 1 2] "point P" [%g -0.1 5 %g 0.1 5 %g 0.1 5]\n' % (x, x + 0.1, x))
+    s = cpbrt.Scene.parse(head + tri(0) + tri(100) + 'AttributeBegin\nAreaLightSource "diffuse"\n' + tri(100) + 'AttributeEnd\nWorldEnd\n')
+    d = s.desc
+    assert d.n_primitives == 2                      # on-screen matte + off-screen emitter; off-screen matte dropped
+    assert d.primitives[0].material >= 0 and d.primitives[1].light == 0
+
+
+def test_image_texture_load(cpbrt):
+    """`Texture "name" "spectrum" "imagemap"`: PNG bytes / 255 then the 1.05 inverse gamma (Q19)."""
+    from PIL import Image
+    head = ('Camera "perspective" "float fov" [40]\nSampler "halton" "integer pixelsamples" [1]\n'
+            'Film "image" "integer xresolution" [8] "integer yresolution" [8]\nIntegrator "path"\nWorldBegin\n')
+    s = cpbrt.Scene.parse(head + 'Texture "boxtex" "spectrum" "imagemap" "string filename" "box-texture.png"\n'
+                          'Material "matte" "texture Kd" "boxtex"\nShape "sphere"\nWorldEnd\n', base_dir=SCENES)
+    d = s.desc
+    tex = d.textures[d.materials[0].tex[0]]
+    assert (tex.kind, tex.channels, tex.width, tex.height) == (cpbrt.abi.TEX_IMAGE, 3, 474, 474)
+    img = np.asarray(Image.open(os.path.join(SCENES, "box-texture.png")).convert("RGB")).astype(np.float32) / np.float32(255)
+    expect = np.where(img <= 0.04045, img / 12.92, ((img + 0.055) / 1.05) ** 2.4)
+    got = np.ctypeslib.as_array(d.texels, shape=(int(d.n_texels),))[tex.offset:tex.offset + 474 * 474 * 3].reshape(474, 474, 3)
+    np.testing.assert_allclose(got, expect, rtol=2e-5, atol=1e-7)
+
+
+def test_imported_scene_fixture_matches_reference_file_when_available(cpbrt):
+    ref = "/root/reference/scenes/cornel_box.pbrt"
+    if not os.path.exists(ref):
+        pytest.skip("reference checkout not present (GPU box)")
+    a, b = cpbrt.Scene.load(ref).desc, cpbrt.Scene.load(os.path.join(SCENES, "cornel_box.pbrt")).desc
+    assert a.n_primitives == b.n_primitives and a.n_triangles == b.n_triangles
+    ta = np.ctypeslib.as_array(a.triangles, shape=(int(a.n_triangles),)).view(np.uint8)
+    tb = np.ctypeslib.as_array(b.triangles, shape=(int(b.n_triangles),)).view(np.uint8)
+    assert np.array_equal(ta, tb)
+    assert list(a.lights[0].L) == list(b.lights[0].L)

@@ -1,0 +1,184 @@
+"""Pins the CPU oracle: the reference's own unit tests, values derived from its sources, an
+independent brute-force aggregate, committed golden vectors, and the product's host-side BVH
+builder (same exact SAH, different implementation)."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import SCENES, lcg_rays, scene_text
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_halton_works_kat(cpbrt, oracle):
+    """src/sampler/halton.rs:232-249: HaltonSampler::new(16, (9, 4)), four pixels."""
+    s = cpbrt.Scene.parse('Camera "perspective"\nSampler "halton" "integer pixelsamples" [16]\n'
+                          'Film "image" "integer xresolution" [9] "integer yresolution" [4]\nIntegrator "path"\nWorldBegin\nWorldEnd\n')
+    d = s.desc
+    assert list(d.sampler.scale) == [16, 9] and list(d.sampler.exp) == [4, 2]
+    expect = {(3, 3): 28, (5, 3): 10, (4, 3): 82, (8, 0): 81}
+    for (x, y), index in expect.items():
+        got = oracle.lib.orc_halton_pixel_index(C.cast(C.pointer(d.sampler), C.c_void_p), x, y)
+        assert got == index
+        rx = int(np.float32(oracle.lib.orc_radical_inverse(got, 0)) * np.float32(16))
+        ry = int(np.float32(oracle.lib.orc_radical_inverse(got, 1)) * np.float32(9))
+        assert (rx, ry) == (x, y)
+
+
+def test_halton_example_points(cpbrt, oracle):
+    """examples/halton_sampler.rs prints get_2d() of samples 0.. for a 1024x768 sampler starting
+    at index 0; dims 0,1 involve no permutation."""
+    s = cpbrt.Scene.parse('Camera "perspective"\nSampler "halton" "integer pixelsamples" [128]\n'
+                          'Film "image" "integer xresolution" [1024] "integer yresolution" [768]\nIntegrator "path"\nWorldBegin\nWorldEnd\n')
+    w = oracle.OracleWorld(s)
+    # pixel (0,0) has base index 0
+    k = np.arange(4, dtype=np.uint32)
+    z = np.zeros(4, np.uint32)
+    idx, x = w.halton(z, z, k, np.zeros(4, np.uint32))
+    _, y = w.halton(z, z, k, np.ones(4, np.uint32))
+    assert list(idx) == [i * 1024 * 2187 for i in range(4)]
+    np.testing.assert_array_equal(x, np.array([0, 0.8166504, 0.4083252, 0.5218506], np.float32))
+    np.testing.assert_array_equal(y, np.array([0, 0.6438043, 0.85962504, 0.21460143], np.float32))
+
+
+def test_radical_inverse_against_python(cpbrt, oracle):
+    def rad_inv(x, base):
+        acc, cnt = 0, 0
+        while x:
+            acc = acc * base + x % base; x //= base; cnt += 1
+        return np.float32(np.float32(1) / np.float32(base ** cnt)) * np.float32(acc)
+    rng = np.random.RandomState(0)
+    for x in list(rng.randint(0, 2 ** 31, 200)) + [0, 1, 2 ** 36 + 12345]:
+        for bi, base in ((0, 2), (1, 3)):
+            assert np.float32(oracle.lib.orc_radical_inverse(int(x), bi)) == rad_inv(int(x), base)
+
+
+def test_permutation_table_is_blockwise_permutation(cpbrt):
+    perm = np.zeros(cpbrt.abi.PERM_TABLE_LEN, np.uint16)
+    cpbrt.lib.cpbrt_make_permutation(1, perm.ctypes.data_as(C.POINTER(C.c_uint16)))
+    primes = [p for p in range(2, 8000) if all(p % q for q in range(2, int(p ** 0.5) + 1))][:1000]
+    assert sum(primes) == cpbrt.abi.PERM_TABLE_LEN
+    off = 0
+    for p in primes[:200]:
+        assert sorted(perm[off:off + p]) == list(range(p))
+        off += p
+    perm2 = np.zeros_like(perm)
+    cpbrt.lib.cpbrt_make_permutation(2, perm2.ctypes.data_as(C.POINTER(C.c_uint16)))
+    assert not np.array_equal(perm, perm2)
+
+
+def _scene_bbox_rays(n, seed=7):
+    return lcg_rays(n, (-50, -50, -50), (610, 600, 610), seed)
+
+
+def test_bvh_closest_equals_brute_force(make_scene, oracle):
+    """Closest hit through the BVH == PlainAggregate-style linear scan (plain.rs:17-36), except
+    for exact-distance ties where the two visit orders legitimately pick different primitives."""
+    w = oracle.OracleWorld(make_scene("cornel_box.pbrt"))
+    rays = _scene_bbox_rays(20000)
+    a, b = w.trace_closest(rays), w.trace_closest_plain(rays)
+    hit_a, hit_b = a["prim"] != 0xFFFFFFFF, b["prim"] != 0xFFFFFFFF
+    assert np.array_equal(hit_a, hit_b)
+    assert hit_a.mean() > 0.5
+    np.testing.assert_array_equal(a["t"][hit_a], b["t"][hit_a])
+    differ = a["prim"] != b["prim"]
+    assert differ.mean() < 1e-3          # only ties
+
+
+def test_any_hit_consistent_with_closest(make_scene, oracle):
+    w = oracle.OracleWorld(make_scene("cornel_box.pbrt"))
+    rays = _scene_bbox_rays(20000, seed=11)
+    rays[:, 3] = 300.0
+    occluded = w.trace_any(rays)
+    closest = w.trace_closest(rays)
+    assert np.array_equal(occluded.astype(bool), closest["prim"] != 0xFFFFFFFF)
+
+
+def test_product_bvh_builder_matches_oracle(cpbrt, make_scene, oracle):
+    """a8: primitive order, topology, axes and bounds of the exact SAH build -- product host
+    builder (cpbrt_host_build_bvh) vs the oracle's restatement of bvh.rs:24-124."""
+    for name in ("cornel_box.pbrt", "sphere.pbrt"):
+        scene = make_scene(name)
+        w = oracle.OracleWorld(scene)
+        n = int(scene.desc.n_primitives)
+        order = np.zeros(n, np.uint32)
+        cap = 2 * n
+        arr = dict(is_leaf=np.zeros(cap, np.uint8), axis=np.zeros(cap, np.uint8), a=np.zeros(cap, np.uint32),
+                   b=np.zeros(cap, np.uint32), bound=np.zeros((cap, 6), np.float32))
+        dump = cpbrt.abi.BvhDump(capacity=cap, **{k: v.ctypes.data_as(C.POINTER({"is_leaf": C.c_uint8, "axis": C.c_uint8, "a": C.c_uint32, "b": C.c_uint32, "bound": C.c_float}[k])) for k, v in arr.items()})
+        assert cpbrt.lib.cpbrt_host_build_bvh(scene.desc_ptr, order.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(dump)) == 0
+        ref = w.bvh_nodes()
+        assert np.array_equal(order, w.bvh_order())
+        assert sorted(order) == list(range(n))
+        nn = int(dump.n_nodes)
+        assert nn == len(ref["a"]) and int(dump.root) == ref["root"] == nn - 1
+        for k in ("is_leaf", "axis", "a", "b"):
+            assert np.array_equal(arr[k][:nn], ref[k]), k
+        assert np.array_equal(arr["bound"][:nn].view(np.uint32), ref["bound"].view(np.uint32))
+
+
+def _synthetic_mesh_scene(nx, nz, seed=3, res=64):
+    """Small height-field trianglemesh in the spirit of config C4."""
+    rng = np.random.RandomState(seed)
+    xs, zs = np.linspace(0, 556, nx + 1), np.linspace(0, 559, nz + 1)
+    h = 40 * rng.rand(nz + 1, nx + 1)
+    P = np.stack([np.tile(xs, nz + 1), h.ravel(), np.repeat(zs, nx + 1)], 1)
+    idx = []
+    for j in range(nz):
+        for i in range(nx):
+            v = j * (nx + 1) + i
+            idx += [v, v + 1, v + nx + 2, v + nx + 2, v + nx + 1, v]
+    return ('LookAt 278 273 -800 278 273 0 0 1 0\nCamera "perspective" "float fov" [37.5]\nSampler "halton" "integer pixelsamples" [2]\n'
+            'Film "image" "integer xresolution" [%d] "integer yresolution" [%d]\nIntegrator "path" "integer maxdepth" [5]\nWorldBegin\n'
+            'AttributeBegin\nAreaLightSource "diffuse" "rgb L" [17 12 4]\nShape "trianglemesh" "integer indices" [0 1 2 2 3 0] '
+            '"point P" [343 548.7 227 343 548.7 332 213 548.7 332 213 548.7 227]\nAttributeEnd\n'
+            'Material "matte" "rgb Kd" [0.5 0.5 0.5]\nShape "trianglemesh" "integer indices" [%s] "point P" [%s]\nWorldEnd\n'
+            % (res, res, " ".join(map(str, idx)), " ".join("%.6g" % v for v in P.ravel())))
+
+
+def test_product_bvh_builder_matches_oracle_on_mesh(cpbrt, oracle):
+    """Same as above on a grid mesh: massive key ties (every quad column shares a centre x) and
+    2-primitive leaves (quad halves share a bbox, Q7)."""
+    scene = cpbrt.Scene.parse(_synthetic_mesh_scene(40, 30))
+    n = int(scene.desc.n_primitives)
+    assert n == 2 * 40 * 30 + 2
+    w = oracle.OracleWorld(scene)
+    order = np.zeros(n, np.uint32)
+    assert cpbrt.lib.cpbrt_host_build_bvh(scene.desc_ptr, order.ctypes.data_as(C.POINTER(C.c_uint32)), None) == 0
+    assert np.array_equal(order, w.bvh_order())
+    nodes = w.bvh_nodes()
+    leaf_sizes = (nodes["b"] - nodes["a"])[nodes["is_leaf"] == 1]
+    assert (leaf_sizes == 2).sum() > 100 and leaf_sizes.max() <= 4
+
+
+def test_render_is_deterministic_and_thread_count_independent(make_scene, oracle):
+    scene = make_scene("cornel_box.pbrt", xres=40, yres=40, spp=2)
+    w = oracle.OracleWorld(scene)
+    a, _, sa = w.render(threads=1)
+    b, _, sb = w.render(threads=8)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and sa == sb
+    assert np.isfinite(a).all() and a.mean() > 0.01
+
+
+def test_golden_vectors(make_scene, oracle):
+    """Committed oracle outputs (tests/golden/make_golden.py): guards the oracle itself against
+    accidental change, here and on the GPU box."""
+    g = np.load(os.path.join(GOLDEN, "cornell_golden.npz"))
+    scene = make_scene("cornel_box.pbrt", xres=int(g["xres"]), yres=int(g["yres"]), spp=int(g["spp"]))
+    w = oracle.OracleWorld(scene)
+    assert np.array_equal(w.bvh_order(), g["bvh_order"])
+    rays = w.camera_rays(0)
+    assert np.array_equal(rays.view(np.uint32), g["camera_rays"].view(np.uint32))
+    hits = w.trace_closest(rays)
+    assert np.array_equal(hits["prim"], g["first_hit_prim"])
+    assert np.array_equal(hits["t"].view(np.uint32), g["first_hit_t"].view(np.uint32))
+    idx, val = w.halton(g["h_px"], g["h_py"], g["h_sample"], g["h_dim"])
+    assert np.array_equal(idx, g["h_index"])
+    assert np.array_equal(val.view(np.uint32), g["h_value"].view(np.uint32))
+    film, _, st = w.render(threads=8)
+    # libm (sin/cos/atan2/acos/pow) may differ by an ulp between machines: compare loosely
+    np.testing.assert_allclose(film, g["film"], rtol=2e-3, atol=2e-4)
+    assert abs(st["rays_closest"] - int(g["rays_closest"])) <= 0.001 * int(g["rays_closest"])
