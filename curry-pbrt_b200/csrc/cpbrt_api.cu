@@ -512,7 +512,8 @@ static int ensure_wavefront(cpbrt_ctx* ctx, uint32_t n_paths) {
     if (ctx->path_capacity < n_paths) {
         const size_t per_path = 13 * 16 + 8 + 4 + 4 + 4;   // 13 float4 + index + dim + hit_t + hit_slot
         if (int rc = alloc_upload(ctx, ctx->d_path, nullptr, per_path * n_paths)) return rc;
-        if (int rc = alloc_upload(ctx, ctx->d_queues, nullptr, (size_t)n_paths * 4 * (3 + SHADE_KINDS))) return rc;
+        // a path can have a MIS ray and a continuation ray queued at once: 2 entries per path
+        if (int rc = alloc_upload(ctx, ctx->d_queues, nullptr, (size_t)n_paths * 4 * (5 + SHADE_KINDS))) return rc;
         ctx->path_capacity = n_paths;
         char* p = (char*)ctx->d_path.p;
         float4** f4s[13] = {&ctx->P.ray_o, &ctx->P.ray_d, &ctx->P.beta, &ctx->P.L, &ctx->P.sh_o, &ctx->P.sh_d, &ctx->P.nee_light,
@@ -523,7 +524,7 @@ static int ensure_wavefront(cpbrt_ctx* ctx, uint32_t n_paths) {
         ctx->P.hit_t = (float*)p; p += (size_t)n_paths * 4;
         ctx->P.hit_slot = (uint32_t*)p;
         uint32_t* q = (uint32_t*)ctx->d_queues.p;
-        ctx->Q.closest[0] = q; q += n_paths; ctx->Q.closest[1] = q; q += n_paths; ctx->Q.shadow = q; q += n_paths;
+        ctx->Q.closest[0] = q; q += 2 * (size_t)n_paths; ctx->Q.closest[1] = q; q += 2 * (size_t)n_paths; ctx->Q.shadow = q; q += n_paths;
         for (int k = 0; k < SHADE_KINDS; ++k) { ctx->Q.shade[k] = q; q += n_paths; }
     }
     if (!ctx->d_counts.p) { if (int rc = alloc_upload(ctx, ctx->d_counts, nullptr, 64 * 4)) return rc; }
