@@ -144,8 +144,8 @@ class Renderer:
         rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
         hits = np.zeros((rays.shape[0], 4), np.float32)
         stats = abi.Stats()
-        self._check(lib.cpbrt_trace_closest(self._ctx, rays.ctypes.data, rays.shape[0], hits.ctypes.data, 0,
-                                            C.byref(stats) if count else None))
+        self._check(lib.cpbrt_trace_closest(self._ctx, rays.ctypes.data, rays.shape[0], hits.ctypes.data,
+                                            2 if count else 0, C.byref(stats)))
         out = dict(t=hits[:, 0].copy(), prim=hits[:, 1].view(np.uint32).copy(), u=hits[:, 2].copy(), v=hits[:, 3].copy())
         return (out, stats) if count else out
 
@@ -153,9 +153,20 @@ class Renderer:
         rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
         out = np.zeros(rays.shape[0], np.uint8)
         stats = abi.Stats()
-        self._check(lib.cpbrt_trace_any(self._ctx, rays.ctypes.data, rays.shape[0], out.ctypes.data, 0,
-                                        C.byref(stats) if count else None))
+        self._check(lib.cpbrt_trace_any(self._ctx, rays.ctypes.data, rays.shape[0], out.ctypes.data,
+                                        2 if count else 0, C.byref(stats)))
         return (out, stats) if count else out
+
+    def trace_closest_device(self, rays_ptr, n, hits_ptr, count=False):
+        """Batch already resident in HBM (device pointers); returns Stats (ms_trace = kernel time)."""
+        stats = abi.Stats()
+        self._check(lib.cpbrt_trace_closest(self._ctx, C.c_void_p(rays_ptr), n, C.c_void_p(hits_ptr), 1 | (2 if count else 0), C.byref(stats)))
+        return stats
+
+    def trace_any_device(self, rays_ptr, n, out_ptr, count=False):
+        stats = abi.Stats()
+        self._check(lib.cpbrt_trace_any(self._ctx, C.c_void_p(rays_ptr), n, C.c_void_p(out_ptr), 1 | (2 if count else 0), C.byref(stats)))
+        return stats
 
     def halton(self, px, py, sample, dim):
         px, py, sample, dim = (np.ascontiguousarray(a, np.uint32) for a in (px, py, sample, dim))

@@ -383,7 +383,8 @@ static int check_overflow(cpbrt_ctx* ctx, const Totals& t) {
     return 0;
 }
 
-int cpbrt_trace_closest(cpbrt_ctx* ctx, const cpbrt_ray* rays, uint64_t n, cpbrt_hit* hits_out, int on_device, cpbrt_stats* stats) {
+int cpbrt_trace_closest(cpbrt_ctx* ctx, const cpbrt_ray* rays, uint64_t n, cpbrt_hit* hits_out, int flags, cpbrt_stats* stats) {
+    const int on_device = flags & CPBRT_TRACE_ON_DEVICE; const bool count = (flags & CPBRT_TRACE_COUNT) != 0;
     if (!ctx) return CPBRT_ERR_BAD_CTX;
     if (!ctx->has_bvh) return ctx->fail(CPBRT_ERR_BAD_CTX, "cpbrt_trace_closest before cpbrt_build_bvh");
     if ((!rays || !hits_out) && n) return ctx->fail(CPBRT_ERR_BAD_ARG, "null ray / hit buffer");
@@ -401,7 +402,7 @@ int cpbrt_trace_closest(cpbrt_ctx* ctx, const cpbrt_ray* rays, uint64_t n, cpbrt
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0, ctx->stream);
     if (n) {
-        if (stats) k_batch_closest<true><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, d_rays, n, d_hits, counters, ctx->d_totals);
+        if (count) k_batch_closest<true><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, d_rays, n, d_hits, counters, ctx->d_totals);
         else k_batch_closest<false><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, d_rays, n, d_hits, counters, ctx->d_totals);
     }
     cudaEventRecord(e1, ctx->stream);
@@ -419,7 +420,8 @@ int cpbrt_trace_closest(cpbrt_ctx* ctx, const cpbrt_ray* rays, uint64_t n, cpbrt
     return check_overflow(ctx, t);
 }
 
-int cpbrt_trace_any(cpbrt_ctx* ctx, const cpbrt_ray* rays, uint64_t n, uint8_t* out, int on_device, cpbrt_stats* stats) {
+int cpbrt_trace_any(cpbrt_ctx* ctx, const cpbrt_ray* rays, uint64_t n, uint8_t* out, int flags, cpbrt_stats* stats) {
+    const int on_device = flags & CPBRT_TRACE_ON_DEVICE; const bool count = (flags & CPBRT_TRACE_COUNT) != 0;
     if (!ctx) return CPBRT_ERR_BAD_CTX;
     if (!ctx->has_bvh) return ctx->fail(CPBRT_ERR_BAD_CTX, "cpbrt_trace_any before cpbrt_build_bvh");
     if ((!rays || !out) && n) return ctx->fail(CPBRT_ERR_BAD_ARG, "null ray / result buffer");
@@ -437,7 +439,7 @@ int cpbrt_trace_any(cpbrt_ctx* ctx, const cpbrt_ray* rays, uint64_t n, uint8_t* 
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0, ctx->stream);
     if (n) {
-        if (stats) k_batch_any<true><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, d_rays, n, d_out, counters, ctx->d_totals);
+        if (count) k_batch_any<true><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, d_rays, n, d_out, counters, ctx->d_totals);
         else k_batch_any<false><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, d_rays, n, d_out, counters, ctx->d_totals);
     }
     cudaEventRecord(e1, ctx->stream);

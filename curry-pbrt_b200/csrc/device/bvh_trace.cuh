@@ -50,137 +50,123 @@ CP_DEV bool box_test_static(const RayBoxSetup& s, float mnx, float mny, float mn
     return t_max > 0.f;
 }
 
-static constexpr int kStackSize = 96;
+static constexpr int kStackSize = 64;
 static constexpr uint32_t kLeafBit = 0x80000000u;
+static constexpr uint32_t kDone = 0xFFFFFFFFu;      // "no more work": has the leaf bit set on purpose
 
 struct TraceStats { uint32_t parent_visits, prim_tests; };
+
+// Work items of the traversal ("tasks"), packed in a uint2:
+//   Parent task  x = node index,             y = bits(t_min of that node's own box test)
+//   Leaf task    x = kLeafBit | first slot,  y = primitive count
+// The loop keeps exactly ONE place in the code where Parent nodes are expanded and ONE where
+// primitives are tested, so the lanes of a warp that are at different depths of different
+// subtrees still execute the same instructions (SIMT "while-while" form).
+struct TaskStack {
+    uint2 e[kStackSize];
+    int n = 0;
+    CP_DEV void push(uint2 t, uint32_t* overflow) { if (n < kStackSize) e[n++] = t; else *overflow = 1; }
+    CP_DEV uint2 pop() { return n ? e[--n] : make_uint2(kDone, 0u); }
+};
+
+struct NodeChildren { uint32_t ref[2], cnt[2]; bool ok[2]; float tmin[2]; uint32_t axis; };
+
+// Reads one Parent node (64 B) and runs the t_max-independent part of both children's box tests.
+template <bool COUNT>
+CP_DEV NodeChildren expand_node(const DevScene& sc, uint32_t node, const RayBoxSetup& bs, TraceStats* st) {
+    const float4* np = sc.nodes + 4ull * node;
+    const float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2), q3 = __ldg(np + 3);
+    NodeChildren c;
+    c.ref[0] = __float_as_uint(q3.x); c.ref[1] = __float_as_uint(q3.y);
+    const uint32_t lw = __float_as_uint(q3.z);
+    c.cnt[0] = lw & 0x3FFFFFFFu; c.cnt[1] = __float_as_uint(q3.w); c.axis = lw >> 30;
+    c.tmin[0] = 0.f; c.tmin[1] = 0.f;
+    c.ok[0] = c.cnt[0] > 0 || box_test_static(bs, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, &c.tmin[0]);
+    c.ok[1] = c.cnt[1] > 0 || box_test_static(bs, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, &c.tmin[1]);
+    if (COUNT) st->parent_visits += (c.cnt[0] == 0) + (c.cnt[1] == 0);
+    return c;
+}
+CP_DEV uint2 child_task(const NodeChildren& c, int k) {
+    return c.cnt[k] > 0 ? make_uint2(c.ref[k] | kLeafBit, c.cnt[k]) : make_uint2(c.ref[k], __float_as_uint(c.tmin[k]));
+}
 
 // Closest hit.  Returns the BVH slot (or 0xFFFFFFFF) and leaves the hit distance in *t_hit.
 template <bool COUNT>
 __device__ uint32_t bvh_closest(const DevScene& sc, Ray ray, float* t_hit, TraceStats* st, uint32_t* overflow) {
     uint32_t best = 0xFFFFFFFFu;
+    *t_hit = ray.t_max;
     if (sc.n_prims == 0) return best;
     const RayBoxSetup bs = ray_box_setup(ray);
     const TriRaySetup ts = tri_ray_setup(ray.d);
-    uint2 stack[kStackSize];
-    int sp = 0;
-
-    auto leaf = [&](uint32_t first, uint32_t cnt) {
-        for (uint32_t s = first; s < first + cnt; ++s) {
+    TaskStack stack;
+    uint2 task;
+    if (sc.root_cnt > 0) task = make_uint2(sc.root_ref | kLeafBit, sc.root_cnt);
+    else {
+        if (COUNT) ++st->parent_visits;
+        float tmin;
+        const bool ok = box_test_static(bs, sc.root_box[0], sc.root_box[1], sc.root_box[2], sc.root_box[3], sc.root_box[4], sc.root_box[5], &tmin);
+        task = ok ? make_uint2(sc.root_ref, __float_as_uint(tmin)) : make_uint2(kDone, 0u);
+    }
+    for (;;) {
+        // ---- Parent tasks: descend until the next leaf (or until nothing is left) ----------
+        while (!(task.x & kLeafBit)) {
+            // the part of the box test that depends on t_max, with the t_max current NOW
+            if (!(__uint_as_float(task.y) < ray.t_max)) { task = stack.pop(); continue; }
+            const NodeChildren c = expand_node<COUNT>(sc, task.x, bs, st);
+            // reference order: positive direction along the split axis -> right child first
+            const bool positive = c.axis == 0 ? bs.pos[0] : (c.axis == 1 ? bs.pos[1] : bs.pos[2]);
+            const int first = positive ? 1 : 0, second = first ^ 1;
+            if (c.ok[second]) stack.push(child_task(c, second), overflow);
+            task = c.ok[first] ? child_task(c, first) : stack.pop();
+        }
+        if (task.x == kDone) break;
+        // ---- Leaf task: every primitive, no box test, later hit wins ties -------------------
+        const uint32_t first = task.x & ~kLeafBit, end = first + task.y;
+        for (uint32_t s = first; s < end; ++s) {
             if (COUNT) ++st->prim_tests;
-            PrimRecord pr = load_prim(sc, s);
+            const PrimRecord pr = load_prim(sc, s);
             float t;
             if (prim_intersect_t(sc, pr, ray, ts, &t)) { ray.t_max = t; best = s; }
         }
-    };
-
-    uint32_t cur;
-    if (sc.root_cnt > 0) { leaf(sc.root_ref, sc.root_cnt); *t_hit = ray.t_max; return best; }
-    {
-        if (COUNT) ++st->parent_visits;
-        float tmin;
-        if (!(box_test_static(bs, sc.root_box[0], sc.root_box[1], sc.root_box[2], sc.root_box[3], sc.root_box[4], sc.root_box[5], &tmin) && tmin < ray.t_max)) {
-            *t_hit = ray.t_max; return best;
-        }
-        cur = sc.root_ref;
+        task = stack.pop();
     }
-    for (;;) {
-        const float4* np = sc.nodes + 4ull * cur;
-        const float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2), q3 = __ldg(np + 3);
-        const uint32_t lref = __float_as_uint(q3.x), rref = __float_as_uint(q3.y);
-        const uint32_t lw = __float_as_uint(q3.z), rcnt = __float_as_uint(q3.w);
-        const uint32_t lcnt = lw & 0x3FFFFFFFu, axis = lw >> 30;
-        const bool positive = axis == 0 ? bs.pos[0] : (axis == 1 ? bs.pos[1] : bs.pos[2]);
-        // reference: positive -> visit `right` first, then `left`; otherwise left first
-        const bool first_is_right = positive;
-        const uint32_t f_ref = first_is_right ? rref : lref, f_cnt = first_is_right ? rcnt : lcnt;
-        const uint32_t s_ref = first_is_right ? lref : rref, s_cnt = first_is_right ? lcnt : rcnt;
-
-        // deferred child
-        if (s_cnt > 0) {
-            if (sp < kStackSize) stack[sp++] = make_uint2(s_ref | kLeafBit, s_cnt); else *overflow = 1;
-        } else {
-            if (COUNT) ++st->parent_visits;
-            float tmin; bool ok;
-            if (first_is_right) ok = box_test_static(bs, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, &tmin);
-            else ok = box_test_static(bs, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, &tmin);
-            if (ok) { if (sp < kStackSize) stack[sp++] = make_uint2(s_ref, __float_as_uint(tmin)); else *overflow = 1; }
-        }
-        // first child
-        bool descend = false;
-        if (f_cnt > 0) {
-            leaf(f_ref, f_cnt);
-        } else {
-            if (COUNT) ++st->parent_visits;
-            float tmin; bool ok;
-            if (first_is_right) ok = box_test_static(bs, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, &tmin);
-            else ok = box_test_static(bs, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, &tmin);
-            if (ok && tmin < ray.t_max) { cur = f_ref; descend = true; }
-        }
-        while (!descend) {
-            if (sp == 0) { *t_hit = ray.t_max; return best; }
-            const uint2 e = stack[--sp];
-            if (e.x & kLeafBit) leaf(e.x & ~kLeafBit, e.y);
-            else if (__uint_as_float(e.y) < ray.t_max) { cur = e.x; descend = true; }
-        }
-    }
+    *t_hit = ray.t_max;
+    return best;
 }
 
-// Any hit (shadow rays): left then right, first accepted primitive ends the search.
+// Any hit (shadow rays): left then right, first accepted primitive ends the search.  t_max
+// never changes, so a Parent child whose full box test fails is dropped when its parent is read.
 template <bool COUNT>
 __device__ bool bvh_any(const DevScene& sc, const Ray& ray, TraceStats* st, uint32_t* overflow) {
     if (sc.n_prims == 0) return false;
     const RayBoxSetup bs = ray_box_setup(ray);
     const TriRaySetup ts = tri_ray_setup(ray.d);
-    uint2 stack[kStackSize];
-    int sp = 0;
-
-    auto leaf = [&](uint32_t first, uint32_t cnt) -> bool {
-        for (uint32_t s = first; s < first + cnt; ++s) {
+    TaskStack stack;
+    uint2 task;
+    if (sc.root_cnt > 0) task = make_uint2(sc.root_ref | kLeafBit, sc.root_cnt);
+    else {
+        if (COUNT) ++st->parent_visits;
+        float tmin;
+        const bool ok = box_test_static(bs, sc.root_box[0], sc.root_box[1], sc.root_box[2], sc.root_box[3], sc.root_box[4], sc.root_box[5], &tmin);
+        task = (ok && tmin < ray.t_max) ? make_uint2(sc.root_ref, 0u) : make_uint2(kDone, 0u);
+    }
+    for (;;) {
+        while (!(task.x & kLeafBit)) {
+            const NodeChildren c = expand_node<COUNT>(sc, task.x, bs, st);
+            const bool ok0 = c.ok[0] && (c.cnt[0] > 0 || c.tmin[0] < ray.t_max);
+            const bool ok1 = c.ok[1] && (c.cnt[1] > 0 || c.tmin[1] < ray.t_max);
+            if (ok1) stack.push(child_task(c, 1), overflow);
+            task = ok0 ? child_task(c, 0) : stack.pop();
+        }
+        if (task.x == kDone) return false;
+        const uint32_t first = task.x & ~kLeafBit, end = first + task.y;
+        for (uint32_t s = first; s < end; ++s) {
             if (COUNT) ++st->prim_tests;
-            PrimRecord pr = load_prim(sc, s);
+            const PrimRecord pr = load_prim(sc, s);
             float t;
             if (prim_intersect_t(sc, pr, ray, ts, &t)) return true;
         }
-        return false;
-    };
-    if (sc.root_cnt > 0) return leaf(sc.root_ref, sc.root_cnt);
-    uint32_t cur;
-    {
-        if (COUNT) ++st->parent_visits;
-        float tmin;
-        if (!(box_test_static(bs, sc.root_box[0], sc.root_box[1], sc.root_box[2], sc.root_box[3], sc.root_box[4], sc.root_box[5], &tmin) && tmin < ray.t_max)) return false;
-        cur = sc.root_ref;
-    }
-    for (;;) {
-        const float4* np = sc.nodes + 4ull * cur;
-        const float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2), q3 = __ldg(np + 3);
-        const uint32_t lref = __float_as_uint(q3.x), rref = __float_as_uint(q3.y);
-        const uint32_t lcnt = __float_as_uint(q3.z) & 0x3FFFFFFFu, rcnt = __float_as_uint(q3.w);
-        // right child: decided now (t_max never changes for a predicate ray), visited after left
-        if (rcnt > 0) {
-            if (sp < kStackSize) stack[sp++] = make_uint2(rref | kLeafBit, rcnt); else *overflow = 1;
-        } else {
-            if (COUNT) ++st->parent_visits;
-            float tmin;
-            if (box_test_static(bs, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, &tmin) && tmin < ray.t_max) {
-                if (sp < kStackSize) stack[sp++] = make_uint2(rref, 0u); else *overflow = 1;
-            }
-        }
-        bool descend = false;
-        if (lcnt > 0) {
-            if (leaf(lref, lcnt)) return true;
-        } else {
-            if (COUNT) ++st->parent_visits;
-            float tmin;
-            if (box_test_static(bs, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, &tmin) && tmin < ray.t_max) { cur = lref; descend = true; }
-        }
-        while (!descend) {
-            if (sp == 0) return false;
-            const uint2 e = stack[--sp];
-            if (e.x & kLeafBit) { if (leaf(e.x & ~kLeafBit, e.y)) return true; }
-            else { cur = e.x; descend = true; }
-        }
+        task = stack.pop();
     }
 }
 

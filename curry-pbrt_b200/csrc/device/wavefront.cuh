@@ -174,30 +174,29 @@ __global__ void __launch_bounds__(128) k_trace_closest(DevScene sc, PathArrays P
         if (active) {
             const uint32_t e = Q.closest[cur][i];
             pid = e & ~kMisRayBit;
-            if (e & kMisRayBit) {
+            const bool is_mis = (e & kMisRayBit) != 0;
+            // one traversal call site for both ray kinds (keeps the warp converged inside it)
+            const float4 ro = is_mis ? P.mis_o[pid] : P.ray_o[pid];
+            const float4 rd = is_mis ? P.mis_d[pid] : P.ray_d[pid];
+            Ray ray; ray.o = f4_xyz(ro); ray.d = f4_xyz(rd); ray.t_max = kFloatMax;
+            float t;
+            const uint32_t slot = bvh_closest<false>(sc, ray, &t, nullptr, &overflow);
+            if (is_mis) {
                 // BSDF-sampled ray of uniform_sample_one_light (integrator/mod.rs:54-89)
-                const float4 mo = P.mis_o[pid], md = P.mis_d[pid];
-                Ray ray; ray.o = f4_xyz(mo); ray.d = f4_xyz(md); ray.t_max = kFloatMax;
-                float t;
-                const uint32_t slot = bvh_closest<false>(sc, ray, &t, nullptr, &overflow);
                 Spec ld = spec(0.f);
                 if (slot != 0xFFFFFFFFu) {
                     const PrimRecord pr = load_prim(sc, slot);
-                    const uint32_t li = __float_as_uint(md.w);
+                    const uint32_t li = __float_as_uint(rd.w);
                     if (prim_source(pr) == (kSourceLight | li)) {   // Arc::ptr_eq(light, &intersect_light)
                         const DevLight& light = sc.lights[li];
                         ShapePoint hsp = prim_shape_point(sc, slot, pr, ray, t);
                         const float li_pdf = shape_by_point_pdf(sc, light, f4_xyz(P.mis_p[pid]), hsp);
-                        const float f_pdf = mo.w;
+                        const float f_pdf = ro.w;
                         if (li_pdf != 0.f) ld = f4_rgb(P.mis_A[pid]) * power_heuristic(f_pdf, li_pdf) / f_pdf;
                     }
                 }
                 P.nee_bsdf[pid] = mk4(ld, 0.f);
             } else {
-                const float4 ro = P.ray_o[pid], rd = P.ray_d[pid];
-                Ray ray; ray.o = f4_xyz(ro); ray.d = f4_xyz(rd); ray.t_max = kFloatMax;
-                float t;
-                const uint32_t slot = bvh_closest<false>(sc, ray, &t, nullptr, &overflow);
                 P.hit_t[pid] = t; P.hit_slot[pid] = slot;
                 kind = SHADE_TERMINAL;
                 if (slot != 0xFFFFFFFFu) {

@@ -251,12 +251,15 @@ int cpbrt_upload_scene(cpbrt_ctx* ctx, const cpbrt_scene_desc* desc);
 int cpbrt_build_bvh(cpbrt_ctx* ctx, uint32_t* prim_order_out, cpbrt_bvh_dump* nodes_out);
 
 /* Scene::intersect (src/scene.rs:20-22) / Scene::intersect_predicate (scene.rs:17-19) over a
- * ray batch.  Host pointers unless on_device != 0.  stats_out nullable; when non-null the
- * kernels also count Parent visits and primitive tests (slower). */
+ * ray batch.  flags: CPBRT_TRACE_ON_DEVICE = rays / results are device pointers;
+ * CPBRT_TRACE_COUNT = also count Parent visits and primitive tests (slower kernel variant).
+ * stats_out (nullable) receives the kernel's device time and, with COUNT, the counters. */
+#define CPBRT_TRACE_ON_DEVICE 1
+#define CPBRT_TRACE_COUNT 2
 int cpbrt_trace_closest(cpbrt_ctx* ctx, const cpbrt_ray* rays, uint64_t n, cpbrt_hit* hits_out,
-                        int on_device, cpbrt_stats* stats_out);
+                        int flags, cpbrt_stats* stats_out);
 int cpbrt_trace_any(cpbrt_ctx* ctx, const cpbrt_ray* rays, uint64_t n, uint8_t* occluded_out,
-                    int on_device, cpbrt_stats* stats_out);
+                    int flags, cpbrt_stats* stats_out);
 
 /* HaltonSampler::set_pixel + next_sample x sample[i] + get_sample at dimension dim[i]
  * (src/sampler/halton.rs:108-136).  index_out / value_out nullable. */

@@ -293,3 +293,32 @@ def test_unsupported_features_fail_loudly(cpbrt):
     assert e.value.code == cpbrt.abi.ERR_UNSUPPORTED
     with pytest.raises(cpbrt.CpbrtError):
         r.render()            # no scene / BVH yet
+
+
+def test_c4_million_triangles(cpbrt, oracle):
+    """Config C4's geometry (1,000,008 primitives): BVH primitive order and first-hit ids at
+    full size; the oracle traces a subset of the rays, the device all of them."""
+    import importlib
+    syn = importlib.import_module("curry-pbrt_b200.synthetic")
+    scene = cpbrt.Scene.parse(syn.heightfield_scene(1000, 500, 480, 270, 1))
+    assert scene.desc.n_primitives == 1000008
+    r = cpbrt.Renderer(0); r.upload(scene)
+    order = r.build_bvh()
+    w = oracle.OracleWorld(scene)
+    assert np.array_equal(order, w.bvh_order())
+    cam = r.camera_rays(0)
+    rnd = lcg_rays(1 << 15, (0, 0, 0), (556, 548, 559), seed=7)
+    for rays in (cam[::4], rnd):
+        g, gs = r.trace_closest(rays, count=True)
+        o, oc = w.trace_closest(rays, count=True)
+        assert np.array_equal(g["prim"], o["prim"])
+        assert np.array_equal(g["t"].view(np.uint32), o["t"].view(np.uint32))
+        assert gs.trace_parent_visits == int(oc[0]) and gs.trace_prim_tests == int(oc[1])
+        assert (o["prim"] != NO_HIT).mean() > 0.5
+    sh = lcg_rays(1 << 15, (0, 0, 0), (556, 548, 559), seed=13)
+    sh[:, 3] = np.float32(1 - 1e-5); sh[:, 4:7] *= np.float32(300)
+    assert np.array_equal(r.trace_any(sh), w.trace_any(sh))
+    # full-size property: every camera ray that hits reports a primitive whose slot exists
+    full = r.trace_closest(cam)
+    hit = full["prim"] != NO_HIT
+    assert hit.mean() > 0.9 and full["prim"][hit].max() < 1000008 and (full["t"][hit] > 0).all()
