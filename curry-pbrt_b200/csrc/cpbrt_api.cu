@@ -343,9 +343,21 @@ int cpbrt_build_bvh(cpbrt_ctx* ctx, uint32_t* prim_order_out, cpbrt_bvh_dump* du
                 stack.push_back(nd.b); stack.push_back(nd.a);
             }
             nodes.resize(4ull * dfs.size());
+            auto leaf_bound = [&](const BuildNode& leaf) {   // union of the leaf's primitive bounds
+                BuildNode out = leaf;
+                for (uint32_t sl = leaf.a; sl < leaf.b; ++sl) {
+                    const BuildBounds& pb = bounds[R.order[sl]];
+                    for (int c = 0; c < 3; ++c) {
+                        out.bound.mn[c] = sl == leaf.a ? pb.mn[c] : std::min(out.bound.mn[c], pb.mn[c]);
+                        out.bound.mx[c] = sl == leaf.a ? pb.mx[c] : std::max(out.bound.mx[c], pb.mx[c]);
+                    }
+                }
+                return out;
+            };
             for (uint32_t k = 0; k < dfs.size(); ++k) {
                 const BuildNode& nd = R.arena[dfs[k]];
-                const BuildNode& l = R.arena[nd.a]; const BuildNode& r = R.arena[nd.b];
+                const BuildNode l = R.arena[nd.a].leaf ? leaf_bound(R.arena[nd.a]) : R.arena[nd.a];
+                const BuildNode r = R.arena[nd.b].leaf ? leaf_bound(R.arena[nd.b]) : R.arena[nd.b];
                 uint32_t lref = l.leaf ? l.a : dev_index[nd.a], lcnt = l.leaf ? l.b - l.a : 0;
                 uint32_t rref = r.leaf ? r.a : dev_index[nd.b], rcnt = r.leaf ? r.b - r.a : 0;
                 nodes[4ull * k] = make_float4(l.bound.mn[0], l.bound.mn[1], l.bound.mn[2], l.bound.mx[0]);
@@ -388,6 +400,7 @@ int cpbrt_trace_closest(cpbrt_ctx* ctx, const cpbrt_ray* rays, uint64_t n, cpbrt
     if (!ctx) return CPBRT_ERR_BAD_CTX;
     if (!ctx->has_bvh) return ctx->fail(CPBRT_ERR_BAD_CTX, "cpbrt_trace_closest before cpbrt_build_bvh");
     if ((!rays || !hits_out) && n) return ctx->fail(CPBRT_ERR_BAD_ARG, "null ray / hit buffer");
+    if (n >= 0xFFFFFFFFull) return ctx->fail(CPBRT_ERR_UNSUPPORTED, "more than 2^32-1 rays in one batch");
     CU(cudaSetDevice(ctx->device));
     if (int rc = ensure_totals(ctx)) return rc;
     CU(cudaMemsetAsync(ctx->d_totals, 0, ctx->d_totals_buf.bytes, ctx->stream));
@@ -425,6 +438,7 @@ int cpbrt_trace_any(cpbrt_ctx* ctx, const cpbrt_ray* rays, uint64_t n, uint8_t* 
     if (!ctx) return CPBRT_ERR_BAD_CTX;
     if (!ctx->has_bvh) return ctx->fail(CPBRT_ERR_BAD_CTX, "cpbrt_trace_any before cpbrt_build_bvh");
     if ((!rays || !out) && n) return ctx->fail(CPBRT_ERR_BAD_ARG, "null ray / result buffer");
+    if (n >= 0xFFFFFFFFull) return ctx->fail(CPBRT_ERR_UNSUPPORTED, "more than 2^32-1 rays in one batch");
     CU(cudaSetDevice(ctx->device));
     if (int rc = ensure_totals(ctx)) return rc;
     CU(cudaMemsetAsync(ctx->d_totals, 0, ctx->d_totals_buf.bytes, ctx->stream));

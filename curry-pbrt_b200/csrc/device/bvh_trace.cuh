@@ -19,12 +19,14 @@ namespace cpbrt {
 struct RayBoxSetup {   // RayIntersectCache (bounds.rs:326-368)
     V3 o, inv_d;
     bool pos[3];       // is_positive_d: d >= 0
+    bool any_neg_zero; // some d component is -0.0: the reference then pairs d >= 0 (true) with 1/d = -inf
 };
 CP_DEV RayBoxSetup ray_box_setup(const Ray& r) {
     RayBoxSetup s;
     s.o = r.o;
     s.inv_d = v3(1.f / r.d.x, 1.f / r.d.y, 1.f / r.d.z);
     s.pos[0] = r.d.x >= 0.f; s.pos[1] = r.d.y >= 0.f; s.pos[2] = r.d.z >= 0.f;
+    s.any_neg_zero = (r.d.x == 0.f && signbit(r.d.x)) || (r.d.y == 0.f && signbit(r.d.y)) || (r.d.z == 0.f && signbit(r.d.z));
     return s;
 }
 
@@ -167,6 +169,390 @@ __device__ bool bvh_any(const DevScene& sc, const Ray& ray, TraceStats* st, uint
             if (prim_intersect_t(sc, pr, ray, ts, &t)) return true;
         }
         task = stack.pop();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Persistent-warp driver: the traversal above, restructured so that a lane whose ray is
+// finished pulls the next ray from a global counter instead of idling until the slowest ray
+// of its warp is done (ray costs are heavy-tailed: a ray grazing the terrain pierces thousands
+// of boxes, its warp neighbours a few dozen).  One outer iteration =
+//     refill idle lanes -> every lane descends to its next leaf -> every lane tests one leaf
+// so lanes only ever wait for one descent, not for a whole ray.
+//   fetch(i, &ray, &user)            load work item i
+//   finish(done, user, ray, slot, t) called by ALL lanes whenever any lane finished a ray
+//                                    (`done` marks the lanes that did) -- may use warp votes
+// Visiting order, box arithmetic and primitive tests are exactly those of bvh_closest /
+// bvh_any; only the scheduling differs.
+template <bool ANY, bool COUNT, class User, class Fetch, class Finish>
+__device__ void trace_persistent(const DevScene& sc, uint32_t n_items, uint32_t* work_counter, TraceStats* st, uint32_t* overflow,
+                                 Fetch fetch, Finish finish) {
+    const int lane = threadIdx.x & 31;
+    Ray ray; ray.o = v3(0.f, 0.f, 0.f); ray.d = v3(0.f, 0.f, 1.f); ray.t_max = 0.f;
+    RayBoxSetup bs = ray_box_setup(ray);
+    TriRaySetup ts = tri_ray_setup(ray.d);
+    TaskStack stack;
+    uint2 task = make_uint2(kDone, 0u);
+    uint32_t best = 0xFFFFFFFFu;
+    User user = User();
+    bool have_ray = false, exhausted = false;
+
+    for (;;) {
+        // ---- refill -------------------------------------------------------------------------
+        const unsigned idle = __ballot_sync(0xFFFFFFFFu, !have_ray);
+        if (idle && !exhausted) {
+            const int leader = __ffs(idle) - 1;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(work_counter, (uint32_t)__popc(idle));
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            if (base >= n_items) exhausted = true;   // warp-uniform
+            if (!have_ray) {
+                const uint32_t i = base + __popc(idle & ((1u << lane) - 1u));
+                if (i < n_items) {
+                    fetch(i, &ray, &user);
+                    have_ray = true; best = 0xFFFFFFFFu; stack.n = 0;
+                    bs = ray_box_setup(ray); ts = tri_ray_setup(ray.d);
+                    if (sc.n_prims == 0) task = make_uint2(kDone, 0u);
+                    else if (sc.root_cnt > 0) task = make_uint2(sc.root_ref | kLeafBit, sc.root_cnt);
+                    else {
+                        if (COUNT) ++st->parent_visits;
+                        float tmin;
+                        bool ok = box_test_static(bs, sc.root_box[0], sc.root_box[1], sc.root_box[2], sc.root_box[3], sc.root_box[4], sc.root_box[5], &tmin);
+                        if (ANY) ok = ok && tmin < ray.t_max;
+                        task = ok ? make_uint2(sc.root_ref, __float_as_uint(tmin)) : make_uint2(kDone, 0u);
+                    }
+                }
+            }
+        }
+        if (__all_sync(0xFFFFFFFFu, !have_ray)) break;
+
+        // ---- Parent tasks: descend to the next leaf -----------------------------------------
+        while (have_ray && !(task.x & kLeafBit)) {
+            if (!ANY && !(__uint_as_float(task.y) < ray.t_max)) { task = stack.pop(); continue; }
+            const NodeChildren c = expand_node<COUNT>(sc, task.x, bs, st);
+            if (ANY) {
+                const bool ok0 = c.ok[0] && (c.cnt[0] > 0 || c.tmin[0] < ray.t_max);
+                const bool ok1 = c.ok[1] && (c.cnt[1] > 0 || c.tmin[1] < ray.t_max);
+                if (ok1) stack.push(child_task(c, 1), overflow);
+                task = ok0 ? child_task(c, 0) : stack.pop();
+            } else {
+                const bool positive = c.axis == 0 ? bs.pos[0] : (c.axis == 1 ? bs.pos[1] : bs.pos[2]);
+                const int first = positive ? 1 : 0, second = first ^ 1;
+                if (c.ok[second]) stack.push(child_task(c, second), overflow);
+                task = c.ok[first] ? child_task(c, first) : stack.pop();
+            }
+        }
+        // ---- Leaf task ----------------------------------------------------------------------
+        bool finished = false;
+        if (have_ray) {
+            if (task.x != kDone) {
+                const uint32_t first = task.x & ~kLeafBit, end = first + task.y;
+                bool stop = false;
+                for (uint32_t s = first; s < end && !stop; ++s) {
+                    if (COUNT) ++st->prim_tests;
+                    const PrimRecord pr = load_prim(sc, s);
+                    float t;
+                    if (prim_intersect_t(sc, pr, ray, ts, &t)) { best = s; if (ANY) stop = true; else ray.t_max = t; }
+                }
+                task = stop ? make_uint2(kDone, 0u) : stack.pop();
+            }
+            finished = task.x == kDone;
+        }
+        // ---- results -------------------------------------------------------------------------
+        if (__any_sync(0xFFFFFFFFu, finished)) {
+            finish(finished, user, ray, best, ray.t_max);
+            if (finished) have_ray = false;
+        }
+    }
+}
+
+// ==========================================================================================
+// Two-phase closest hit: same answer as the reference-order traversal above, far less work.
+//
+// The reference visits the FAR child first and its box test is loose (Q5, Q6), so a ray
+// touches every box near its whole length -- tens of thousands of dependent fetches for a ray
+// grazing a terrain.  What the reference returns, though, is easy to characterise: process the
+// reachable hit primitives in reference order, accept P when t_scaled_P <= t_max * det_P
+// (i.e. t_P <= t_max up to a few ulp), and return the last accepted one.  Removing any other
+// primitive from that sequence, or starting with a smaller t_max that is still safely above
+// the final t, does not change the last accepted primitive.  Hence:
+//   phase 1 (search)  near-first traversal with a tight slab test; finds the smallest t and
+//                     whether a rival hit lies within `margin` of it.  A primitive only
+//                     counts if every ancestor passes the reference's own box predicate, so
+//                     nothing the reference cannot reach is ever reported.
+//   phase 2 (replay)  only when a rival exists (ray through a shared edge / vertex, coincident
+//                     surfaces): reference-order traversal, reference box and primitive tests,
+//                     started at t_max = t_best + margin and restricted to boxes that overlap
+//                     [t_best - margin, t_best + margin]; this reproduces the reference's
+//                     tie-breaking exactly.
+// `margin` covers the rounding of the acceptance test and of the slab distances (relative
+// 2e-5 plus 2e-5 * max|bound - o| / max|d|); it only decides how often phase 2 runs.
+struct TightSetup { float abs_m, t_init; };
+
+struct ChildTests {
+    uint32_t ref[2], cnt[2]; uint32_t axis;
+    bool ref_ok[2]; float ref_tmin[2];     // reference predicate (t_max-independent part) and its t_min
+    float entry[2], exit[2];               // tight slab interval (exit widened by 1 + 2*gamma(3))
+};
+
+CP_DEV void slab_tests(const RayBoxSetup& s, float mnx, float mny, float mnz, float mxx, float mxy, float mxz,
+                       bool* ref_ok, float* ref_tmin, float* entry, float* exit) {
+    const float widen = 1.f + 2.f * gamma_n(3);
+    const float lo0 = ((s.pos[0] ? mnx : mxx) - s.o.x) * s.inv_d.x, hi0 = ((s.pos[0] ? mxx : mnx) - s.o.x) * s.inv_d.x * widen;
+    const float lo1 = ((s.pos[1] ? mny : mxy) - s.o.y) * s.inv_d.y, hi1 = ((s.pos[1] ? mxy : mny) - s.o.y) * s.inv_d.y * widen;
+    const float lo2 = ((s.pos[2] ? mnz : mxz) - s.o.z) * s.inv_d.z, hi2 = ((s.pos[2] ? mxz : mnz) - s.o.z) * s.inv_d.z * widen;
+    // reference predicate, same sequence of comparisons as box_test_static
+    bool ok = true;
+    float t_min = lo0, t_max = hi0;
+    if (t_min > hi1 || lo1 > t_max) ok = false;
+    t_min = rmin(t_min, lo1); t_max = rmax(t_max, hi1);
+    if (t_min > hi2 || lo2 > t_max) ok = false;
+    t_min = rmin(t_min, lo2); t_max = rmax(t_max, hi2);
+    *ref_ok = ok && t_max > 0.f;
+    *ref_tmin = t_min;
+    // tight interval; fmaxf / fminf drop NaNs, which only makes the interval more permissive.
+    // With a -0.0 direction component the reference's near/far choice (d >= 0) disagrees with
+    // the sign of 1/d and its slab comes out inverted; the tight test orders each slab itself.
+    if (s.any_neg_zero) {
+        *entry = fmaxf(fmaxf(fminf(lo0, hi0), fminf(lo1, hi1)), fminf(lo2, hi2));
+        *exit = fminf(fminf(fmaxf(lo0, hi0), fmaxf(lo1, hi1)), fmaxf(lo2, hi2));
+    } else {
+        *entry = fmaxf(fmaxf(lo0, lo1), lo2);
+        *exit = fminf(fminf(hi0, hi1), hi2);
+    }
+}
+
+CP_DEV ChildTests expand_node2(const DevScene& sc, uint32_t node, const RayBoxSetup& bs) {
+    const float4* np = sc.nodes + 4ull * node;
+    const float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2), q3 = __ldg(np + 3);
+    ChildTests c;
+    c.ref[0] = __float_as_uint(q3.x); c.ref[1] = __float_as_uint(q3.y);
+    const uint32_t lw = __float_as_uint(q3.z);
+    c.cnt[0] = lw & 0x3FFFFFFFu; c.cnt[1] = __float_as_uint(q3.w); c.axis = lw >> 30;
+    slab_tests(bs, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, &c.ref_ok[0], &c.ref_tmin[0], &c.entry[0], &c.exit[0]);
+    slab_tests(bs, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, &c.ref_ok[1], &c.ref_tmin[1], &c.entry[1], &c.exit[1]);
+    return c;
+}
+
+CP_DEV float hit_margin(float t, float abs_m) { return 2e-5f * fabsf(t) + abs_m; }
+CP_DEV float slab_slack(float a, float b, float abs_m) { return 1e-5f * fmaxf(fabsf(a), fabsf(b)) + abs_m; }
+
+// Scale of the numbers entering the slab / triangle arithmetic for this ray: 2e-5 * max|bound - o| / max|d|
+CP_DEV float ray_abs_margin(const DevScene& sc, const Ray& ray) {
+    float m = 0.f;
+    m = fmaxf(m, fmaxf(fabsf(sc.root_box[0] - ray.o.x), fabsf(sc.root_box[3] - ray.o.x)));
+    m = fmaxf(m, fmaxf(fabsf(sc.root_box[1] - ray.o.y), fabsf(sc.root_box[4] - ray.o.y)));
+    m = fmaxf(m, fmaxf(fabsf(sc.root_box[2] - ray.o.z), fabsf(sc.root_box[5] - ray.o.z)));
+    const float dmax = fmaxf(fmaxf(fabsf(ray.d.x), fabsf(ray.d.y)), fabsf(ray.d.z));
+    const float r = 2e-5f * m / dmax;
+    return (r == r && r < 3.0e38f) ? r : 3.0e38f;   // degenerate rays: every hit is a "rival" -> replay decides
+}
+
+enum TraceMode : int { MODE_SEARCH = 0, MODE_REPLAY = 1 };
+
+// Persistent-warp closest hit (two-phase).  fetch / finish as in trace_persistent.
+template <class User, class Fetch, class Finish>
+__device__ void closest_persistent(const DevScene& sc, uint32_t n_items, uint32_t* work_counter, uint32_t* overflow, Fetch fetch, Finish finish) {
+    const int lane = threadIdx.x & 31;
+    Ray ray; ray.o = v3(0.f, 0.f, 0.f); ray.d = v3(0.f, 0.f, 1.f); ray.t_max = 0.f;
+    RayBoxSetup bs = ray_box_setup(ray);
+    TriRaySetup ts = tri_ray_setup(ray.d);
+    TaskStack stack;
+    uint2 task = make_uint2(kDone, 0u);
+    User user = User();
+    bool have_ray = false, exhausted = false;
+    int mode = MODE_SEARCH;
+    float t_init = 0.f, abs_m = 0.f;
+    // search state: best / second-best accepted distance; replay state: ray.t_max and `best`
+    uint32_t best = 0xFFFFFFFFu;
+    float t_best = 0.f, t_second = 0.f, t_cut = 0.f, t_lo = 0.f;
+
+    auto root_task = [&](bool replay) -> uint2 {
+        if (sc.n_prims == 0) return make_uint2(kDone, 0u);
+        if (sc.root_cnt > 0) return make_uint2(sc.root_ref | kLeafBit, sc.root_cnt);
+        bool rok; float rtmin, en, ex;
+        slab_tests(bs, sc.root_box[0], sc.root_box[1], sc.root_box[2], sc.root_box[3], sc.root_box[4], sc.root_box[5], &rok, &rtmin, &en, &ex);
+        if (!rok) return make_uint2(kDone, 0u);
+        if (replay) return make_uint2(sc.root_ref, __float_as_uint(rtmin));          // t_min < t_max checked when the task is taken
+        if (!(rtmin < t_init)) return make_uint2(kDone, 0u);
+        return make_uint2(sc.root_ref, __float_as_uint(en));
+    };
+
+    for (;;) {
+        // ---- refill -------------------------------------------------------------------------
+        const unsigned idle = __ballot_sync(0xFFFFFFFFu, !have_ray);
+        if (idle && !exhausted) {
+            const int leader = __ffs(idle) - 1;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(work_counter, (uint32_t)__popc(idle));
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            if (base >= n_items) exhausted = true;
+            if (!have_ray) {
+                const uint32_t i = base + __popc(idle & ((1u << lane) - 1u));
+                if (i < n_items) {
+                    fetch(i, &ray, &user);
+                    have_ray = true; stack.n = 0; mode = MODE_SEARCH;
+                    bs = ray_box_setup(ray); ts = tri_ray_setup(ray.d);
+                    t_init = ray.t_max; abs_m = ray_abs_margin(sc, ray);
+                    best = 0xFFFFFFFFu; t_best = t_init; t_second = kFloatMax; t_cut = t_init;
+                    task = root_task(false);
+                }
+            }
+        }
+        if (__all_sync(0xFFFFFFFFu, !have_ray)) break;
+
+        // ---- Parent tasks ---------------------------------------------------------------------
+        while (have_ray && !(task.x & kLeafBit)) {
+            const float key = __uint_as_float(task.y);
+            if (mode == MODE_SEARCH ? (key > t_cut) : !(key < ray.t_max)) { task = stack.pop(); continue; }
+            const ChildTests c = expand_node2(sc, task.x, bs);
+            if (mode == MODE_SEARCH) {
+                // near-first; a child is entered if the reference could reach it (its own
+                // predicate, against the initial t_max) and the tight interval meets [0, t_cut]
+                bool go[2]; float key2[2];
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const float sl = slab_slack(c.entry[k], c.exit[k], abs_m);
+                    const bool tight = !(c.entry[k] > c.exit[k] + sl) && !(c.exit[k] + sl < 0.f) && !(c.entry[k] - sl > t_cut);
+                    // a Leaf has no box in the reference (always entered there); its stored
+                    // box only prunes primitives that cannot be hit within [0, t_cut]
+                    go[k] = tight && (c.cnt[k] > 0 || (c.ref_ok[k] && c.ref_tmin[k] < t_init));
+                    key2[k] = c.entry[k] - sl;
+                }
+                const int near = (go[0] && (!go[1] || key2[0] <= key2[1])) ? 0 : 1, far = near ^ 1;
+                if (go[far]) stack.push(c.cnt[far] > 0 ? make_uint2(c.ref[far] | kLeafBit, c.cnt[far]) : make_uint2(c.ref[far], __float_as_uint(key2[far])), overflow);
+                task = go[near] ? (c.cnt[near] > 0 ? make_uint2(c.ref[near] | kLeafBit, c.cnt[near]) : make_uint2(c.ref[near], __float_as_uint(key2[near]))) : stack.pop();
+            } else {
+                // reference order and reference box rule, skipping boxes that cannot hold a
+                // hit inside the replay window
+                bool go[2];
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const float sl = slab_slack(c.entry[k], c.exit[k], abs_m);
+                    const bool window = !(c.exit[k] + sl < t_lo) && !(c.entry[k] - sl > t_cut);
+                    go[k] = window && (c.cnt[k] > 0 || c.ref_ok[k]);
+                }
+                const bool positive = c.axis == 0 ? bs.pos[0] : (c.axis == 1 ? bs.pos[1] : bs.pos[2]);
+                const int first = positive ? 1 : 0, second = first ^ 1;
+                if (go[second]) stack.push(c.cnt[second] > 0 ? make_uint2(c.ref[second] | kLeafBit, c.cnt[second]) : make_uint2(c.ref[second], __float_as_uint(c.ref_tmin[second])), overflow);
+                task = go[first] ? (c.cnt[first] > 0 ? make_uint2(c.ref[first] | kLeafBit, c.cnt[first]) : make_uint2(c.ref[first], __float_as_uint(c.ref_tmin[first]))) : stack.pop();
+            }
+        }
+        // ---- Leaf task --------------------------------------------------------------------------
+        bool finished = false;
+        if (have_ray) {
+            if (task.x != kDone) {
+                const uint32_t first = task.x & ~kLeafBit, end = first + task.y;
+                for (uint32_t s = first; s < end; ++s) {
+                    const PrimRecord pr = load_prim(sc, s);
+                    float t;
+                    if (mode == MODE_SEARCH) {
+                        Ray probe = ray; probe.t_max = fminf(t_init, t_cut);
+                        if (prim_intersect_t(sc, pr, probe, ts, &t)) {
+                            if (best == 0xFFFFFFFFu || t < t_best) { if (best != 0xFFFFFFFFu) t_second = fminf(t_second, t_best); t_best = t; best = s; }
+                            else t_second = fminf(t_second, t);
+                            t_cut = t_best + hit_margin(t_best, abs_m);
+                        }
+                    } else {
+                        if (prim_intersect_t(sc, pr, ray, ts, &t)) { ray.t_max = t; best = s; }
+                    }
+                }
+                task = stack.pop();
+            }
+            if (task.x == kDone) {
+                if (mode == MODE_SEARCH && best != 0xFFFFFFFFu && !(t_second > t_cut)) {
+                    // a rival within the margin: let the reference's own order decide
+                    mode = MODE_REPLAY;
+                    t_lo = t_best - hit_margin(t_best, abs_m);
+                    ray.t_max = fminf(t_init, t_cut);
+                    best = 0xFFFFFFFFu; stack.n = 0;
+                    task = root_task(true);
+                    // (t_cut stays t_best + margin: upper edge of the replay window)
+                } else {
+                    if (mode == MODE_SEARCH) ray.t_max = best != 0xFFFFFFFFu ? t_best : t_init;
+                    finished = true;
+                }
+            }
+        }
+        // ---- results ----------------------------------------------------------------------------
+        if (__any_sync(0xFFFFFFFFu, finished)) {
+            finish(finished, user, ray, best, ray.t_max);
+            if (finished) have_ray = false;
+        }
+    }
+}
+
+// Persistent-warp any hit.  The result is a pure existence test against a constant t_max, so
+// the visiting order is free: nearer child first, reference predicate (required for parity)
+// plus the tight interval (prunes what the reference's loose test lets through).
+template <class User, class Fetch, class Finish>
+__device__ void any_persistent(const DevScene& sc, uint32_t n_items, uint32_t* work_counter, uint32_t* overflow, Fetch fetch, Finish finish) {
+    const int lane = threadIdx.x & 31;
+    Ray ray; ray.o = v3(0.f, 0.f, 0.f); ray.d = v3(0.f, 0.f, 1.f); ray.t_max = 0.f;
+    RayBoxSetup bs = ray_box_setup(ray);
+    TriRaySetup ts = tri_ray_setup(ray.d);
+    TaskStack stack;
+    uint2 task = make_uint2(kDone, 0u);
+    User user = User();
+    bool have_ray = false, exhausted = false, hit = false;
+    float abs_m = 0.f;
+    for (;;) {
+        const unsigned idle = __ballot_sync(0xFFFFFFFFu, !have_ray);
+        if (idle && !exhausted) {
+            const int leader = __ffs(idle) - 1;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(work_counter, (uint32_t)__popc(idle));
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            if (base >= n_items) exhausted = true;
+            if (!have_ray) {
+                const uint32_t i = base + __popc(idle & ((1u << lane) - 1u));
+                if (i < n_items) {
+                    fetch(i, &ray, &user);
+                    have_ray = true; stack.n = 0; hit = false;
+                    bs = ray_box_setup(ray); ts = tri_ray_setup(ray.d);
+                    abs_m = ray_abs_margin(sc, ray);
+                    if (sc.n_prims == 0) task = make_uint2(kDone, 0u);
+                    else if (sc.root_cnt > 0) task = make_uint2(sc.root_ref | kLeafBit, sc.root_cnt);
+                    else {
+                        bool rok; float rtmin, en, ex;
+                        slab_tests(bs, sc.root_box[0], sc.root_box[1], sc.root_box[2], sc.root_box[3], sc.root_box[4], sc.root_box[5], &rok, &rtmin, &en, &ex);
+                        task = (rok && rtmin < ray.t_max) ? make_uint2(sc.root_ref, 0u) : make_uint2(kDone, 0u);
+                    }
+                }
+            }
+        }
+        if (__all_sync(0xFFFFFFFFu, !have_ray)) break;
+        while (have_ray && !(task.x & kLeafBit)) {
+            const ChildTests c = expand_node2(sc, task.x, bs);
+            bool go[2]; float key[2];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const float sl = slab_slack(c.entry[k], c.exit[k], abs_m);
+                const bool tight = !(c.entry[k] > c.exit[k] + sl) && !(c.exit[k] + sl < 0.f) && !(c.entry[k] - sl > ray.t_max);
+                go[k] = tight && (c.cnt[k] > 0 || (c.ref_ok[k] && c.ref_tmin[k] < ray.t_max));
+                key[k] = c.entry[k];
+            }
+            const int near = (go[0] && (!go[1] || key[0] <= key[1])) ? 0 : 1, far = near ^ 1;
+            if (go[far]) stack.push(c.cnt[far] > 0 ? make_uint2(c.ref[far] | kLeafBit, c.cnt[far]) : make_uint2(c.ref[far], 0u), overflow);
+            task = go[near] ? (c.cnt[near] > 0 ? make_uint2(c.ref[near] | kLeafBit, c.cnt[near]) : make_uint2(c.ref[near], 0u)) : stack.pop();
+        }
+        bool finished = false;
+        if (have_ray) {
+            if (task.x != kDone) {
+                const uint32_t first = task.x & ~kLeafBit, end = first + task.y;
+                for (uint32_t s = first; s < end && !hit; ++s) {
+                    const PrimRecord pr = load_prim(sc, s);
+                    float t;
+                    if (prim_intersect_t(sc, pr, ray, ts, &t)) hit = true;
+                }
+                task = hit ? make_uint2(kDone, 0u) : stack.pop();
+            }
+            finished = task.x == kDone;
+        }
+        if (__any_sync(0xFFFFFFFFu, finished)) {
+            finish(finished, user, ray, hit ? 0u : 0xFFFFFFFFu, ray.t_max);
+            if (finished) have_ray = false;
+        }
     }
 }
 

@@ -13,8 +13,10 @@
 //            q1 = L.max.y L.max.z R.min.x R.min.y
 //            q2 = R.min.z R.max.x R.max.y R.max.z
 //            q3 = left_ref  right_ref  left_cnt | axis << 30  right_cnt
-//          child with cnt > 0 is a Leaf: ref = first BVH slot, cnt = number of primitives, and
-//          its box is unused (the reference tests no box for leaves, bvh.rs:158-165);
+//          child with cnt > 0 is a Leaf: ref = first BVH slot, cnt = number of primitives; the
+//          reference tests no box for leaves (bvh.rs:158-165), so its predicate ignores this
+//          box -- it holds the union of the leaf's primitive bounds and is used only by the
+//          two-phase traversal to skip primitives that cannot be hit (bvh_trace.cuh);
 //          child with cnt == 0 is a Parent: ref = node index, box = that Parent's own `bound`.
 //          The reference stores each Parent's bound in the Parent itself (bvh.rs:13-21) and
 //          tests it on entry; keeping both children's bounds in the parent lets one 64-byte

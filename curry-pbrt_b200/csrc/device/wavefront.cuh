@@ -55,6 +55,7 @@ struct Queues {
     uint32_t* counts;
 };
 static constexpr int kCntClosest0 = 0, kCntShadow = 2, kCntShade0 = 3, kCntN = 3 + SHADE_KINDS;
+static constexpr int kCntWorkClosest = kCntN, kCntWorkShadow = kCntN + 1;   // work-distribution cursors of the persistent trace kernels
 // 64-bit totals that live after the counters: rays_closest, rays_any, nan_dropped, stack_overflow
 struct Totals { unsigned long long rays_closest, rays_any, nan_dropped, overflow; };
 
@@ -162,36 +163,37 @@ __global__ void k_raygen(DevScene sc, PixelArrays px, PathArrays P, Queues Q, ui
 }
 
 // ------------------------------------------------------------------------------------------
-// Closest-hit stage.  `cur` selects the input queue.
+// Closest-hit stage.  `cur` selects the input queue.  Persistent warps: lanes pull queue
+// entries one by one (bvh_trace.cuh, trace_persistent).
+struct ClosestItem { uint32_t pid; uint32_t is_mis; float w_o, w_d; };   // w_* = the .w of the ray's two float4
+
 __global__ void __launch_bounds__(128) k_trace_closest(DevScene sc, PathArrays P, Queues Q, int cur, Totals* totals) {
     const uint32_t n = Q.counts[kCntClosest0 + cur];
-    const uint32_t n_round = (n + 31u) & ~31u;   // whole warps stay in the loop for the ballots
     uint32_t overflow = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
-        const bool active = i < n;
+    const uint32_t* __restrict__ queue = Q.closest[cur];
+    auto fetch = [&](uint32_t i, Ray* ray, ClosestItem* it) {
+        const uint32_t e = queue[i];
+        it->pid = e & ~kMisRayBit; it->is_mis = (e & kMisRayBit) ? 1u : 0u;
+        const float4 ro = it->is_mis ? P.mis_o[it->pid] : P.ray_o[it->pid];
+        const float4 rd = it->is_mis ? P.mis_d[it->pid] : P.ray_d[it->pid];
+        ray->o = f4_xyz(ro); ray->d = f4_xyz(rd); ray->t_max = kFloatMax;
+        it->w_o = ro.w; it->w_d = rd.w;
+    };
+    auto finish = [&](bool done, const ClosestItem& it, const Ray& ray, uint32_t slot, float t) {
         int kind = -1;
-        uint32_t pid = 0;
-        if (active) {
-            const uint32_t e = Q.closest[cur][i];
-            pid = e & ~kMisRayBit;
-            const bool is_mis = (e & kMisRayBit) != 0;
-            // one traversal call site for both ray kinds (keeps the warp converged inside it)
-            const float4 ro = is_mis ? P.mis_o[pid] : P.ray_o[pid];
-            const float4 rd = is_mis ? P.mis_d[pid] : P.ray_d[pid];
-            Ray ray; ray.o = f4_xyz(ro); ray.d = f4_xyz(rd); ray.t_max = kFloatMax;
-            float t;
-            const uint32_t slot = bvh_closest<false>(sc, ray, &t, nullptr, &overflow);
-            if (is_mis) {
+        const uint32_t pid = it.pid;
+        if (done) {
+            if (it.is_mis) {
                 // BSDF-sampled ray of uniform_sample_one_light (integrator/mod.rs:54-89)
                 Spec ld = spec(0.f);
                 if (slot != 0xFFFFFFFFu) {
                     const PrimRecord pr = load_prim(sc, slot);
-                    const uint32_t li = __float_as_uint(rd.w);
+                    const uint32_t li = __float_as_uint(it.w_d);
                     if (prim_source(pr) == (kSourceLight | li)) {   // Arc::ptr_eq(light, &intersect_light)
                         const DevLight& light = sc.lights[li];
                         ShapePoint hsp = prim_shape_point(sc, slot, pr, ray, t);
                         const float li_pdf = shape_by_point_pdf(sc, light, f4_xyz(P.mis_p[pid]), hsp);
-                        const float f_pdf = ro.w;
+                        const float f_pdf = it.w_o;
                         if (li_pdf != 0.f) ld = f4_rgb(P.mis_A[pid]) * power_heuristic(f_pdf, li_pdf) / f_pdf;
                     }
                 }
@@ -201,7 +203,7 @@ __global__ void __launch_bounds__(128) k_trace_closest(DevScene sc, PathArrays P
                 kind = SHADE_TERMINAL;
                 if (slot != 0xFFFFFFFFu) {
                     const uint32_t src = __float_as_uint(__ldg(&sc.prims[3ull * slot + 2].w));
-                    const uint32_t bounce = __float_as_uint(rd.w) & 0xFFu;
+                    const uint32_t bounce = __float_as_uint(it.w_d) & 0xFFu;
                     if (!(src & kSourceLight) && !(sc.integrator == 0 && bounce >= sc.max_depth)) {
                         const uint32_t mt = sc.materials[src].type;
                         kind = mt == 0 ? SHADE_MATTE : (mt == 1 ? SHADE_MIRROR : SHADE_GLASS);
@@ -211,7 +213,8 @@ __global__ void __launch_bounds__(128) k_trace_closest(DevScene sc, PathArrays P
         }
 #pragma unroll
         for (int k = 0; k < SHADE_KINDS; ++k) queue_push(Q.shade[k], &Q.counts[kCntShade0 + k], kind == k, pid);
-    }
+    };
+    closest_persistent<ClosestItem>(sc, n, &Q.counts[kCntWorkClosest], &overflow, fetch, finish);
     if (overflow) atomicAdd(&totals->overflow, 1ull);
 }
 
@@ -219,12 +222,15 @@ __global__ void __launch_bounds__(128) k_trace_closest(DevScene sc, PathArrays P
 __global__ void __launch_bounds__(128) k_trace_shadow(DevScene sc, PathArrays P, Queues Q, Totals* totals) {
     const uint32_t n = Q.counts[kCntShadow];
     uint32_t overflow = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t pid = Q.shadow[i];
-        const float4 so = P.sh_o[pid], sd = P.sh_d[pid];
-        Ray ray; ray.o = f4_xyz(so); ray.d = f4_xyz(sd); ray.t_max = so.w;
-        if (bvh_any<false>(sc, ray, nullptr, &overflow)) P.nee_light[pid] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+    auto fetch = [&](uint32_t i, Ray* ray, uint32_t* pid) {
+        *pid = Q.shadow[i];
+        const float4 so = P.sh_o[*pid], sd = P.sh_d[*pid];
+        ray->o = f4_xyz(so); ray->d = f4_xyz(sd); ray->t_max = so.w;
+    };
+    auto finish = [&](bool done, uint32_t pid, const Ray&, uint32_t slot, float) {
+        if (done && slot != 0xFFFFFFFFu) P.nee_light[pid] = make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    any_persistent<uint32_t>(sc, n, &Q.counts[kCntWorkShadow], &overflow, fetch, finish);
     if (overflow) atomicAdd(&totals->overflow, 1ull);
 }
 
@@ -237,6 +243,8 @@ __global__ void k_queue_reset(Queues Q, int cur, int which, Totals* totals) {
         totals->rays_any += Q.counts[kCntShadow];
         Q.counts[kCntClosest0 + cur] = 0;
         Q.counts[kCntShadow] = 0;
+        Q.counts[kCntWorkClosest] = 0;
+        Q.counts[kCntWorkShadow] = 0;
     } else {
         for (int k = 0; k < SHADE_KINDS; ++k) Q.counts[kCntShade0 + k] = 0;
     }
@@ -454,24 +462,31 @@ __global__ void k_film_resolve(DevScene sc, const float4* __restrict__ sum, floa
 
 // ------------------------------------------------------------------------------------------
 // Batch entry points used by the parity tests and the traversal benchmark.
+// counters: [0] Parent visits, [1] primitive tests, [2] work cursor (zeroed by the caller)
 template <bool COUNT>
 __global__ void __launch_bounds__(128) k_batch_closest(DevScene sc, const float4* __restrict__ rays, uint64_t n, float4* __restrict__ hits,
                                                        unsigned long long* counters, Totals* totals) {
     uint32_t overflow = 0;
     TraceStats ts; ts.parent_visits = 0; ts.prim_tests = 0;
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const float4 a = __ldg(&rays[2 * i]), b = __ldg(&rays[2 * i + 1]);
-        Ray ray; ray.o = v3(a.x, a.y, a.z); ray.t_max = a.w; ray.d = v3(b.x, b.y, b.z);
-        float t;
-        const uint32_t slot = bvh_closest<COUNT>(sc, ray, &t, &ts, &overflow);
+    auto fetch = [&](uint32_t i, Ray* ray, uint32_t* idx) {
+        const float4 a = __ldg(&rays[2ull * i]), b = __ldg(&rays[2ull * i + 1]);
+        ray->o = v3(a.x, a.y, a.z); ray->t_max = a.w; ray->d = v3(b.x, b.y, b.z);
+        *idx = i;
+    };
+    auto finish = [&](bool done, uint32_t idx, const Ray& ray, uint32_t slot, float t) {
+        if (!done) return;
         float4 h = make_float4(0.f, __uint_as_float(0xFFFFFFFFu), 0.f, 0.f);
         if (slot != 0xFFFFFFFFu) {
             const PrimRecord pr = load_prim(sc, slot);
             ShapePoint sp = prim_shape_point(sc, slot, pr, ray, t);
             h = make_float4(t, __uint_as_float(prim_upload_index(pr)), sp.uv.x, sp.uv.y);
         }
-        hits[i] = h;
-    }
+        hits[idx] = h;
+    };
+    // COUNT = the reference-order traversal with its visit counters (algorithmic work of SURVEY 8d);
+    // otherwise the two-phase traversal the renderer uses.  Both must return the same hits.
+    if (COUNT) trace_persistent<false, true, uint32_t>(sc, (uint32_t)n, (uint32_t*)&counters[2], &ts, &overflow, fetch, finish);
+    else closest_persistent<uint32_t>(sc, (uint32_t)n, (uint32_t*)&counters[2], &overflow, fetch, finish);
     if (COUNT) { atomicAdd(&counters[0], (unsigned long long)ts.parent_visits); atomicAdd(&counters[1], (unsigned long long)ts.prim_tests); }
     if (overflow) atomicAdd(&totals->overflow, 1ull);
 }
@@ -480,11 +495,16 @@ __global__ void __launch_bounds__(128) k_batch_any(DevScene sc, const float4* __
                                                    unsigned long long* counters, Totals* totals) {
     uint32_t overflow = 0;
     TraceStats ts; ts.parent_visits = 0; ts.prim_tests = 0;
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const float4 a = __ldg(&rays[2 * i]), b = __ldg(&rays[2 * i + 1]);
-        Ray ray; ray.o = v3(a.x, a.y, a.z); ray.t_max = a.w; ray.d = v3(b.x, b.y, b.z);
-        out[i] = bvh_any<COUNT>(sc, ray, &ts, &overflow) ? 1 : 0;
-    }
+    auto fetch = [&](uint32_t i, Ray* ray, uint32_t* idx) {
+        const float4 a = __ldg(&rays[2ull * i]), b = __ldg(&rays[2ull * i + 1]);
+        ray->o = v3(a.x, a.y, a.z); ray->t_max = a.w; ray->d = v3(b.x, b.y, b.z);
+        *idx = i;
+    };
+    auto finish = [&](bool done, uint32_t idx, const Ray&, uint32_t slot, float) {
+        if (done) out[idx] = slot != 0xFFFFFFFFu ? 1 : 0;
+    };
+    if (COUNT) trace_persistent<true, true, uint32_t>(sc, (uint32_t)n, (uint32_t*)&counters[2], &ts, &overflow, fetch, finish);
+    else any_persistent<uint32_t>(sc, (uint32_t)n, (uint32_t*)&counters[2], &overflow, fetch, finish);
     if (COUNT) { atomicAdd(&counters[0], (unsigned long long)ts.parent_visits); atomicAdd(&counters[1], (unsigned long long)ts.prim_tests); }
     if (overflow) atomicAdd(&totals->overflow, 1ull);
 }

