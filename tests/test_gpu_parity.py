@@ -322,3 +322,15 @@ def test_c4_million_triangles(cpbrt, oracle):
     full = r.trace_closest(cam)
     hit = full["prim"] != NO_HIT
     assert hit.mean() > 0.4 and full["prim"][hit].max() < 1000008 and (full["t"][hit] > 0).all()
+
+
+def test_two_gpu_sample_partition_and_nccl_reduce():
+    """Needs 2 GPUs on the box (skipped on the 1-GPU test box): torchrun x2 -> tools/check_multi_gpu.py."""
+    import subprocess, sys, os, torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29533", os.path.join(root, "tools", "check_multi_gpu.py")], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "-> OK" in out.stdout

@@ -1,0 +1,46 @@
+#!/usr/bin/env python3
+"""Run under torchrun with N >= 2 ranks: sample-partitioned render + NCCL film reduce must equal
+the single-GPU render of the same scene (up to f32 summation order)."""
+import importlib
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__
+    cpbrt = __graft_entry__.build()
+    from conftest import SCENES, scene_text
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    scene = cpbrt.Scene.parse(scene_text("cornel_box.pbrt", xres=160, yres=120, spp=16), base_dir=SCENES)
+    r = cpbrt.Renderer(local); r.upload(scene); r.build_bvh()
+    idt = torch.zeros(cpbrt.abi.COMM_ID_BYTES, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt.copy_(torch.tensor(list(cpbrt.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt, 0)
+    r.comm_init(world, rank, bytes(idt.cpu().tolist()))
+    film, st = r.render()
+    total = torch.tensor([float(st.camera_samples)], device="cuda", dtype=torch.float64)
+    dist.all_reduce(total)
+    ok = True
+    if rank == 0:
+        single = cpbrt.Renderer(local); single.upload(scene); single.build_bvh()
+        ref, _ = single.render()
+        err = np.abs(film - ref) / (np.abs(ref) + 1e-3)
+        ok = bool(err.max() < 1e-4) and int(total.item()) == 160 * 120 * 16
+        print("multi-gpu check: ranks=%d max rel err=%.3g samples=%d reduce_ms=%.3f -> %s" % (world, err.max(), int(total.item()), st.ms_reduce, "OK" if ok else "FAIL"))
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0 if ok else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())
