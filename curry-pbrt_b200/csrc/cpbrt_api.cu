@@ -70,11 +70,11 @@ struct cpbrt_ctx {
     BvhBuildResult bvh;
 
     DevScene scene;   // by-value kernel argument
-    DevBuf d_prims, d_prim_uv, d_nodes, d_transforms, d_materials, d_textures, d_texels, d_lights, d_perm, d_primes, d_primsum;
+    DevBuf d_prims, d_prim_uv, d_nodes, d_transforms, d_materials, d_textures, d_texels, d_lights, d_perm, d_primes, d_primsum, d_magic;
 
     // wavefront state
     uint32_t path_capacity = 0;
-    DevBuf d_path, d_queues, d_counts, d_pixels;
+    DevBuf d_path, d_kind, d_queues, d_counts, d_pixels;
     PathArrays P; Queues Q; PixelArrays PX;
     Totals* d_totals = nullptr;
     DevBuf d_totals_buf, d_film_out;
@@ -153,7 +153,7 @@ void cpbrt_destroy(cpbrt_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     DevBuf* bufs[] = {&ctx->d_prims, &ctx->d_prim_uv, &ctx->d_nodes, &ctx->d_transforms, &ctx->d_materials, &ctx->d_textures, &ctx->d_texels,
-                      &ctx->d_lights, &ctx->d_perm, &ctx->d_primes, &ctx->d_primsum, &ctx->d_path, &ctx->d_queues, &ctx->d_counts,
+                      &ctx->d_lights, &ctx->d_perm, &ctx->d_primes, &ctx->d_primsum, &ctx->d_magic, &ctx->d_path, &ctx->d_kind, &ctx->d_queues, &ctx->d_counts,
                       &ctx->d_pixels, &ctx->d_totals_buf, &ctx->d_film_out};
     for (DevBuf* b : bufs) b->release();
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -266,13 +266,16 @@ int cpbrt_upload_scene(cpbrt_ctx* ctx, const cpbrt_scene_desc* d) {
         for (int i = 1; i < CPBRT_N_PRIMES; ++i) sums[i] = sums[i - 1] + primes[i - 1];
         if (int rc = alloc_upload(ctx, ctx->d_primes, primes.data(), primes.size() * 4)) return rc;
         if (int rc = alloc_upload(ctx, ctx->d_primsum, sums.data(), sums.size() * 4)) return rc;
+        std::vector<uint64_t> magic(CPBRT_N_PRIMES);
+        for (int i = 0; i < CPBRT_N_PRIMES; ++i) magic[i] = 0xFFFFFFFFFFFFFFFFull / primes[i] + 1;   // floor(2^64/p)+1 (p never divides 2^64)
+        if (int rc = alloc_upload(ctx, ctx->d_magic, magic.data(), magic.size() * 8)) return rc;
         if (int rc = alloc_upload(ctx, ctx->d_perm, d->sampler.permutation, (size_t)CPBRT_PERM_TABLE_LEN * 2)) return rc;
         DevSampler& sm = S.sampler;
         sm.spp = d->sampler.spp;
         for (int i = 0; i < 2; ++i) { sm.exp[i] = d->sampler.exp[i]; sm.scale[i] = d->sampler.scale[i]; sm.mult_inverse[i] = d->sampler.mult_inverse[i]; }
         sm.stride = sm.scale[0] * sm.scale[1];
         if (sm.scale[0] != (1ull << sm.exp[0])) return ctx->fail(CPBRT_ERR_BAD_ARG, "sampler.scale[0] must be 2^exp[0]");
-        sm.permutation = (const uint16_t*)ctx->d_perm.p; sm.primes = (const uint32_t*)ctx->d_primes.p; sm.primsum = (const uint32_t*)ctx->d_primsum.p;
+        sm.permutation = (const uint16_t*)ctx->d_perm.p; sm.primes = (const uint32_t*)ctx->d_primes.p; sm.primsum = (const uint32_t*)ctx->d_primsum.p; sm.prime_magic = (const uint64_t*)ctx->d_magic.p;
     }
     S.transforms = (const DevTransform*)ctx->d_transforms.p;
     S.materials = (const DevMaterial*)ctx->d_materials.p;
@@ -526,19 +529,23 @@ static int ensure_wavefront(cpbrt_ctx* ctx, uint32_t n_paths) {
     char* pp = (char*)ctx->d_pixels.p;
     ctx->PX.base_index = (uint2*)pp; ctx->PX.film_point = (float2*)(pp + (size_t)npix * 8); ctx->PX.sum = (float4*)(pp + (size_t)npix * 16);
     if (ctx->path_capacity < n_paths) {
-        const size_t per_path = 13 * 16 + 8 + 4 + 4 + 4;   // 13 float4 + index + dim + hit_t + hit_slot
-        if (int rc = alloc_upload(ctx, ctx->d_path, nullptr, per_path * n_paths)) return rc;
+        if (int rc = alloc_upload(ctx, ctx->d_path, nullptr, kPathBytes * n_paths)) return rc;
+        if (int rc = alloc_upload(ctx, ctx->d_kind, nullptr, (size_t)n_paths + 4)) return rc;   // k_classify reads whole 32-bit words
+        CU(cudaMemsetAsync(ctx->d_kind.p, 0xFF, (size_t)n_paths + 4, ctx->stream));
+        ctx->P.shade_kind = (uint8_t*)ctx->d_kind.p;
         // a path can have a MIS ray and a continuation ray queued at once: 2 entries per path
         if (int rc = alloc_upload(ctx, ctx->d_queues, nullptr, (size_t)n_paths * 4 * (5 + SHADE_KINDS))) return rc;
         ctx->path_capacity = n_paths;
         char* p = (char*)ctx->d_path.p;
-        float4** f4s[13] = {&ctx->P.ray_o, &ctx->P.ray_d, &ctx->P.beta, &ctx->P.L, &ctx->P.sh_o, &ctx->P.sh_d, &ctx->P.nee_light,
-                            &ctx->P.mis_o, &ctx->P.mis_d, &ctx->P.mis_A, &ctx->P.mis_p, &ctx->P.nee_bsdf, &ctx->P.beta_prev};
-        for (int i = 0; i < 13; ++i) { *f4s[i] = (float4*)p; p += (size_t)n_paths * 16; }
-        ctx->P.smp_index = (uint2*)p; p += (size_t)n_paths * 8;
-        ctx->P.smp_dim = (uint32_t*)p; p += (size_t)n_paths * 4;
-        ctx->P.hit_t = (float*)p; p += (size_t)n_paths * 4;
-        ctx->P.hit_slot = (uint32_t*)p;
+        const size_t rec = (size_t)n_paths * 32;
+        PathArrays& P = ctx->P;
+        P.ray_o.base = (float4*)p; P.ray_d.base = (float4*)p + 1; P.hit_t.base = p; p += rec;
+        P.beta.base = (float4*)p; P.L.base = (float4*)p + 1; p += rec;
+        P.sh_o.base = (float4*)p; P.sh_d.base = (float4*)p + 1; p += rec;
+        P.mis_o.base = (float4*)p; P.mis_d.base = (float4*)p + 1; p += rec;
+        P.mis_A.base = (float4*)p; P.mis_p.base = (float4*)p + 1; p += rec;
+        P.nee_light.base = (float4*)p; P.nee_bsdf.base = (float4*)p + 1; p += rec;
+        P.beta_prev.base = (float4*)p; P.smp_index.base = p; P.smp_dim.base = p; P.hit_slot.base = p;
         uint32_t* q = (uint32_t*)ctx->d_queues.p;
         ctx->Q.closest[0] = q; q += 2 * (size_t)n_paths; ctx->Q.closest[1] = q; q += 2 * (size_t)n_paths; ctx->Q.shadow = q; q += n_paths;
         for (int k = 0; k < SHADE_KINDS; ++k) { ctx->Q.shade[k] = q; q += n_paths; }
@@ -611,6 +618,7 @@ int cpbrt_render(cpbrt_ctx* ctx, const cpbrt_render_params* params, float* film_
             k_queue_reset<<<1, 32, 0, st>>>(Q, cur, 0, T);
             const int next = cur ^ 1;
             span_begin(3);
+            k_classify<<<g_pix, 256, 0, st>>>(P, Q, Sn * npix); ++launches;
             k_shade_terminal<<<g_shade, 128, 0, st>>>(S, P, Q);
             k_shade<SHADE_MATTE><<<g_shade, 128, 0, st>>>(S, P, Q, next);
             k_shade<SHADE_MIRROR><<<g_shade, 128, 0, st>>>(S, P, Q, next);

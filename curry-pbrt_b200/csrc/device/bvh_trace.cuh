@@ -349,6 +349,7 @@ CP_DEV float ray_abs_margin(const DevScene& sc, const Ray& ray) {
 }
 
 enum TraceMode : int { MODE_SEARCH = 0, MODE_REPLAY = 1 };
+static constexpr int kRefillLanes = 8;
 
 // Persistent-warp closest hit (two-phase).  fetch / finish as in trace_persistent.
 template <class User, class Fetch, class Finish>
@@ -381,7 +382,8 @@ __device__ void closest_persistent(const DevScene& sc, uint32_t n_items, uint32_
     for (;;) {
         // ---- refill -------------------------------------------------------------------------
         const unsigned idle = __ballot_sync(0xFFFFFFFFu, !have_ray);
-        if (idle && !exhausted) {
+        // refill in groups: one atomic per >= kRefillLanes idle lanes (or when the warp is empty)
+        if (!exhausted && (__popc(idle) >= kRefillLanes || idle == 0xFFFFFFFFu)) {
             const int leader = __ffs(idle) - 1;
             uint32_t base = 0;
             if (lane == leader) base = atomicAdd(work_counter, (uint32_t)__popc(idle));
@@ -419,9 +421,15 @@ __device__ void closest_persistent(const DevScene& sc, uint32_t n_items, uint32_
                     go[k] = tight && (c.cnt[k] > 0 || (c.ref_ok[k] && c.ref_tmin[k] < t_init));
                     key2[k] = c.entry[k] - sl;
                 }
-                const int near = (go[0] && (!go[1] || key2[0] <= key2[1])) ? 0 : 1, far = near ^ 1;
-                if (go[far]) stack.push(c.cnt[far] > 0 ? make_uint2(c.ref[far] | kLeafBit, c.cnt[far]) : make_uint2(c.ref[far], __float_as_uint(key2[far])), overflow);
-                task = go[near] ? (c.cnt[near] > 0 ? make_uint2(c.ref[near] | kLeafBit, c.cnt[near]) : make_uint2(c.ref[near], __float_as_uint(key2[near]))) : stack.pop();
+                // both candidate tasks are formed with straight-line selects (no indexed access
+                // into the small per-child arrays, which would push them to local memory)
+                const uint2 t0 = c.cnt[0] > 0 ? make_uint2(c.ref[0] | kLeafBit, c.cnt[0]) : make_uint2(c.ref[0], __float_as_uint(key2[0]));
+                const uint2 t1 = c.cnt[1] > 0 ? make_uint2(c.ref[1] | kLeafBit, c.cnt[1]) : make_uint2(c.ref[1], __float_as_uint(key2[1]));
+                const bool near0 = go[0] && (!go[1] || key2[0] <= key2[1]);
+                const bool go_near = near0 ? go[0] : go[1], go_far = near0 ? go[1] : go[0];
+                const uint2 t_near = near0 ? t0 : t1, t_far = near0 ? t1 : t0;
+                if (go_far) stack.push(t_far, overflow);
+                task = go_near ? t_near : stack.pop();
             } else {
                 // reference order and reference box rule, skipping boxes that cannot hold a
                 // hit inside the replay window
@@ -433,9 +441,13 @@ __device__ void closest_persistent(const DevScene& sc, uint32_t n_items, uint32_
                     go[k] = window && (c.cnt[k] > 0 || c.ref_ok[k]);
                 }
                 const bool positive = c.axis == 0 ? bs.pos[0] : (c.axis == 1 ? bs.pos[1] : bs.pos[2]);
-                const int first = positive ? 1 : 0, second = first ^ 1;
-                if (go[second]) stack.push(c.cnt[second] > 0 ? make_uint2(c.ref[second] | kLeafBit, c.cnt[second]) : make_uint2(c.ref[second], __float_as_uint(c.ref_tmin[second])), overflow);
-                task = go[first] ? (c.cnt[first] > 0 ? make_uint2(c.ref[first] | kLeafBit, c.cnt[first]) : make_uint2(c.ref[first], __float_as_uint(c.ref_tmin[first]))) : stack.pop();
+                const uint2 t0 = c.cnt[0] > 0 ? make_uint2(c.ref[0] | kLeafBit, c.cnt[0]) : make_uint2(c.ref[0], __float_as_uint(c.ref_tmin[0]));
+                const uint2 t1 = c.cnt[1] > 0 ? make_uint2(c.ref[1] | kLeafBit, c.cnt[1]) : make_uint2(c.ref[1], __float_as_uint(c.ref_tmin[1]));
+                // positive direction along the split axis -> right child (1) first
+                const bool go_first = positive ? go[1] : go[0], go_second = positive ? go[0] : go[1];
+                const uint2 t_first = positive ? t1 : t0, t_second = positive ? t0 : t1;
+                if (go_second) stack.push(t_second, overflow);
+                task = go_first ? t_first : stack.pop();
             }
         }
         // ---- Leaf task --------------------------------------------------------------------------
@@ -498,7 +510,8 @@ __device__ void any_persistent(const DevScene& sc, uint32_t n_items, uint32_t* w
     float abs_m = 0.f;
     for (;;) {
         const unsigned idle = __ballot_sync(0xFFFFFFFFu, !have_ray);
-        if (idle && !exhausted) {
+        // refill in groups: one atomic per >= kRefillLanes idle lanes (or when the warp is empty)
+        if (!exhausted && (__popc(idle) >= kRefillLanes || idle == 0xFFFFFFFFu)) {
             const int leader = __ffs(idle) - 1;
             uint32_t base = 0;
             if (lane == leader) base = atomicAdd(work_counter, (uint32_t)__popc(idle));
@@ -532,9 +545,13 @@ __device__ void any_persistent(const DevScene& sc, uint32_t n_items, uint32_t* w
                 go[k] = tight && (c.cnt[k] > 0 || (c.ref_ok[k] && c.ref_tmin[k] < ray.t_max));
                 key[k] = c.entry[k];
             }
-            const int near = (go[0] && (!go[1] || key[0] <= key[1])) ? 0 : 1, far = near ^ 1;
-            if (go[far]) stack.push(c.cnt[far] > 0 ? make_uint2(c.ref[far] | kLeafBit, c.cnt[far]) : make_uint2(c.ref[far], 0u), overflow);
-            task = go[near] ? (c.cnt[near] > 0 ? make_uint2(c.ref[near] | kLeafBit, c.cnt[near]) : make_uint2(c.ref[near], 0u)) : stack.pop();
+            const uint2 t0 = c.cnt[0] > 0 ? make_uint2(c.ref[0] | kLeafBit, c.cnt[0]) : make_uint2(c.ref[0], 0u);
+            const uint2 t1 = c.cnt[1] > 0 ? make_uint2(c.ref[1] | kLeafBit, c.cnt[1]) : make_uint2(c.ref[1], 0u);
+            const bool near0 = go[0] && (!go[1] || key[0] <= key[1]);
+            const bool go_near = near0 ? go[0] : go[1], go_far = near0 ? go[1] : go[0];
+            const uint2 t_near = near0 ? t0 : t1, t_far = near0 ? t1 : t0;
+            if (go_far) stack.push(t_far, overflow);
+            task = go_near ? t_near : stack.pop();
         }
         bool finished = false;
         if (have_ray) {

@@ -58,6 +58,7 @@ struct DevSampler {
     const uint16_t* permutation;     // digit permutations, block of prime k at primsum[k]
     const uint32_t* primes;          // first 1000 primes
     const uint32_t* primsum;
+    const uint64_t* prime_magic;     // floor(2^64 / p) + 1: x / p == umul64hi(x, magic) exactly for x < 2^32
 };
 
 struct DevScene {

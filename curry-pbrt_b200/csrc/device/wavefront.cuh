@@ -28,24 +28,40 @@ static constexpr uint32_t kFlagSpecular = 0x100u;      // low 8 bits: bounce
 static constexpr uint32_t kPendAny = 1u, kPendLight = 2u, kPendMis = 4u;
 static constexpr uint32_t kMisRayBit = 0x80000000u;    // queue entry: path id | kMisRayBit for a MIS ray
 
-struct PathArrays {
-    float4* ray_o;      // continuation ray origin
-    float4* ray_d;      // direction, w = bits(bounce | specular flag)
-    float4* beta;       // path throughput
-    float4* L;          // radiance accumulated so far
-    uint2* smp_index;   // Halton index (u64)
-    uint32_t* smp_dim;  // next sampler dimension
-    float* hit_t; uint32_t* hit_slot;
-    float4* sh_o;       // shadow ray origin, w = t_max
-    float4* sh_d;       // shadow ray direction
-    float4* nee_light;  // light-sampling term of uniform_sample_one_light (zeroed when occluded)
-    float4* mis_o;      // MIS ray origin, w = f_pdf
-    float4* mis_d;      // MIS ray direction, w = bits(light id)
-    float4* mis_A;      // (le * f) * |n.wi|
-    float4* mis_p;      // shading point
-    float4* nee_bsdf;   // BSDF-sampling term
-    float4* beta_prev;  // throughput the pending terms are weighted with, w = bits(pending flags)
+// Path state: seven 32-byte records per path, each record an array of its own (SoA of small
+// AoS).  Paths reach the shading and trace stages in queue order, i.e. scattered, so a field
+// pair that is always used together shares one 32-byte DRAM sector instead of two half-used
+// ones.  The accessors below keep the per-field view (`P.ray_o[pid]`).
+struct F4Field {   // one float4 of a 32-byte record
+    float4* base;
+    CP_DEV float4& operator[](uint32_t i) const { return base[2ull * i]; }
 };
+template <class T, int OFFSET>
+struct ScalarField {   // a 4- or 8-byte member at byte OFFSET of a 32-byte record
+    char* base;
+    CP_DEV T& operator[](uint32_t i) const { return *reinterpret_cast<T*>(base + 32ull * i + OFFSET); }
+};
+struct PathArrays {
+    // RayRec    {o.xyz, hit_t}{d.xyz, bits(bounce | specular flag)}   continuation ray + its hit distance
+    F4Field ray_o, ray_d; ScalarField<float, 12> hit_t;
+    // ThruRec   {beta.rgb, -}{L.rgb, -}                               throughput, radiance so far
+    F4Field beta, L;
+    // ShadowRec {o.xyz, t_max}{d.xyz, -}                              shadow ray
+    F4Field sh_o, sh_d;
+    // MisRec    {o.xyz, f_pdf}{d.xyz, bits(light id)}                 BSDF-sampled ray of the light loop
+    F4Field mis_o, mis_d;
+    // MisAux    {(le * f) * |n.wi|, -}{shading point, -}
+    F4Field mis_A, mis_p;
+    // NeeRec    {light-sampling term (zeroed when occluded), -}{BSDF-sampling term, -}
+    F4Field nee_light, nee_bsdf;
+    // StateRec  {beta_prev.rgb, bits(pending flags)}{Halton index u64, next dimension, hit slot}
+    F4Field beta_prev; ScalarField<uint2, 16> smp_index; ScalarField<uint32_t, 24> smp_dim; ScalarField<uint32_t, 28> hit_slot;
+    // which shading queue the path's latest hit belongs to (kShadeNone = nothing to shade);
+    // written by the closest-hit stage, consumed (and reset) by k_classify
+    uint8_t* shade_kind;
+};
+static constexpr uint8_t kShadeNone = 0xFF;
+static constexpr size_t kPathBytes = 7 * 32;
 
 struct Queues {
     uint32_t* closest[2];     // path id (| kMisRayBit)
@@ -76,7 +92,6 @@ CP_DEV void queue_push(uint32_t* q, uint32_t* count, bool want, uint32_t item) {
     base = __shfl_sync(0xFFFFFFFFu, base, leader);
     if (want) q[base + __popc(mask & ((1u << lane) - 1u))] = item;
 }
-
 CP_DEV V3 f4_xyz(float4 v) { return v3(v.x, v.y, v.z); }
 CP_DEV Spec f4_rgb(float4 v) { return spec3(v.x, v.y, v.z); }
 CP_DEV float4 mk4(V3 v, float w) { return make_float4(v.x, v.y, v.z, w); }
@@ -167,7 +182,7 @@ __global__ void k_raygen(DevScene sc, PixelArrays px, PathArrays P, Queues Q, ui
 // entries one by one (bvh_trace.cuh, trace_persistent).
 struct ClosestItem { uint32_t pid; uint32_t is_mis; float w_o, w_d; };   // w_* = the .w of the ray's two float4
 
-__global__ void __launch_bounds__(128) k_trace_closest(DevScene sc, PathArrays P, Queues Q, int cur, Totals* totals) {
+__global__ void __launch_bounds__(128, 6) k_trace_closest(DevScene sc, PathArrays P, Queues Q, int cur, Totals* totals) {
     const uint32_t n = Q.counts[kCntClosest0 + cur];
     uint32_t overflow = 0;
     const uint32_t* __restrict__ queue = Q.closest[cur];
@@ -211,11 +226,54 @@ __global__ void __launch_bounds__(128) k_trace_closest(DevScene sc, PathArrays P
                 }
             }
         }
-#pragma unroll
-        for (int k = 0; k < SHADE_KINDS; ++k) queue_push(Q.shade[k], &Q.counts[kCntShade0 + k], kind == k, pid);
+        if (kind >= 0) P.shade_kind[pid] = (uint8_t)kind;
     };
     closest_persistent<ClosestItem>(sc, n, &Q.counts[kCntWorkClosest], &overflow, fetch, finish);
     if (overflow) atomicAdd(&totals->overflow, 1ull);
+}
+
+// Builds the per-material shading queues in PATH ORDER.  The persistent trace kernel finishes
+// rays in arbitrary order; queueing from there would hand the shading stage scattered path ids
+// and every 32-byte state record would be its own DRAM transaction.  Walking the path ids in
+// order keeps neighbouring pixels' paths adjacent in each queue, so shading reads and writes
+// its state in full cache lines.
+__global__ void k_classify(PathArrays P, Queues Q, uint32_t n_paths) {
+    // four consecutive paths per thread (one 32-bit load of their kind bytes), 128 per warp;
+    // per kind one reservation per warp, all reservations issued before any is waited for
+    const int lane = threadIdx.x & 31;
+    const unsigned below = (1u << lane) - 1u;
+    const uint32_t n_quads = (n_paths + 3u) >> 2;               // capacity is a multiple of 4 bytes (cudaMalloc granularity)
+    const uint32_t n_round = (n_quads + 31u) & ~31u;
+    uint32_t* kinds32 = reinterpret_cast<uint32_t*>(P.shade_kind);
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n_round; q += gridDim.x * blockDim.x) {
+        uint32_t w = 0xFFFFFFFFu;
+        if (q < n_quads) { w = kinds32[q]; if (w != 0xFFFFFFFFu) kinds32[q] = 0xFFFFFFFFu; }
+        uint32_t base[SHADE_KINDS], mine[SHADE_KINDS], before[SHADE_KINDS];
+#pragma unroll
+        for (int k = 0; k < SHADE_KINDS; ++k) {
+            uint32_t tot = 0, bef = 0, cnt = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const bool is = ((w >> (8 * j)) & 0xFFu) == (uint32_t)k;
+                const unsigned m = __ballot_sync(0xFFFFFFFFu, is);
+                tot += __popc(m); bef += __popc(m & below); cnt += is ? 1u : 0u;
+            }
+            // entries of lower lanes come first, then this thread's own in path order
+            before[k] = bef; mine[k] = cnt;
+            base[k] = 0;
+            if (lane == 0 && tot) base[k] = atomicAdd(&Q.counts[kCntShade0 + k], tot);
+        }
+#pragma unroll
+        for (int k = 0; k < SHADE_KINDS; ++k) {
+            const uint32_t b = __shfl_sync(0xFFFFFFFFu, base[k], 0);
+            if (mine[k]) {
+                uint32_t pos = b + before[k];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (((w >> (8 * j)) & 0xFFu) == (uint32_t)k) Q.shade[k][pos++] = 4u * q + j;
+            }
+        }
+    }
 }
 
 // Shadow-ray stage: VisibilityTester::unoccluded (light/mod.rs:112-114).
@@ -288,8 +346,8 @@ CP_DEV void build_bsdf(const DevScene& sc, const DevMaterial& m, const ShapePoin
 // needed: the light term is stored assuming visibility (the shadow stage zeroes it), the BSDF
 // term is finished by the closest-hit stage.  Returns the pending flags.
 template <class B>
-CP_DEV void emit_direct_lighting(const DevScene& sc, const PathArrays& P, const Queues& Q, int next, uint32_t pid, bool lane_active,
-                                 const ShapePoint& sp, const B& bsdf, V3 wo, SamplerState& st, Spec beta) {
+CP_DEV void emit_direct_lighting(const DevScene& sc, const PathArrays& P, uint32_t pid, bool lane_active,
+                                 const ShapePoint& sp, const B& bsdf, V3 wo, SamplerState& st, Spec beta, bool* want_shadow_out, bool* want_mis_out) {
     bool want_shadow = false, want_mis = false;
     if (lane_active) {
         uint32_t flags = kPendAny;
@@ -329,8 +387,7 @@ CP_DEV void emit_direct_lighting(const DevScene& sc, const PathArrays& P, const 
         }
         P.beta_prev[pid] = mk4(beta, __uint_as_float(flags));
     }
-    queue_push(Q.shadow, &Q.counts[kCntShadow], want_shadow, pid);
-    queue_push(Q.closest[next], &Q.counts[kCntClosest0 + next], want_mis, pid | kMisRayBit);
+    *want_shadow_out = want_shadow; *want_mis_out = want_mis;
 }
 
 // Hits that end a path without a BSDF: misses, emissive primitives, and (path integrator)
@@ -360,7 +417,7 @@ __global__ void k_shade_terminal(DevScene sc, PathArrays P, Queues Q) {
 }
 
 template <int KIND>
-__global__ void __launch_bounds__(128) k_shade(DevScene sc, PathArrays P, Queues Q, int next) {
+__global__ void __launch_bounds__(128, 8) k_shade(DevScene sc, PathArrays P, Queues Q, int next) {
     typedef typename BsdfFor<KIND>::type B;
     const uint32_t n = Q.counts[kCntShade0 + KIND];
     const uint32_t n_round = (n + 31u) & ~31u;
@@ -397,7 +454,8 @@ __global__ void __launch_bounds__(128) k_shade(DevScene sc, PathArrays P, Queues
         // direct lighting: the path integrator skips it for all-delta BSDFs (path.rs:37),
         // the direct-lighting integrator does not (direct_light.rs:25)
         const bool do_nee = active && (sc.integrator != 0 || bsdf.n_lobes != 0);
-        emit_direct_lighting(sc, P, Q, next, pid, do_nee, sp, bsdf, wo, st, sc.integrator == 0 ? beta : spec(1.f));
+        bool want_shadow, want_mis;
+        emit_direct_lighting(sc, P, pid, do_nee, sp, bsdf, wo, st, sc.integrator == 0 ? beta : spec(1.f), &want_shadow, &want_mis);
         if (active && sc.integrator == 0) {
             V3 wi; Spec f; float f_pdf; bool is_delta;
             if (bsdf.sample_f(sc.sampler, st, wo, &wi, &f, &f_pdf, &is_delta) && f_pdf != 0.f) {
@@ -419,7 +477,23 @@ __global__ void __launch_bounds__(128) k_shade(DevScene sc, PathArrays P, Queues
             }
         }
         if (active) P.L[pid] = mk4(L, 0.f);
-        queue_push(Q.closest[next], &Q.counts[kCntClosest0 + next], cont, pid);
+        // the MIS ray and the continuation ray go to the same queue: one reservation for both
+        {
+            const unsigned mm = __ballot_sync(0xFFFFFFFFu, want_mis), mc = __ballot_sync(0xFFFFFFFFu, cont), ms = __ballot_sync(0xFFFFFFFFu, want_shadow);
+            if (mm | mc | ms) {
+                const int lane = threadIdx.x & 31;
+                uint32_t bc = 0, bsh = 0;
+                if (lane == 0) {
+                    if (mm | mc) bc = atomicAdd(&Q.counts[kCntClosest0 + next], (uint32_t)(__popc(mm) + __popc(mc)));
+                    if (ms) bsh = atomicAdd(&Q.counts[kCntShadow], (uint32_t)__popc(ms));
+                }
+                bc = __shfl_sync(0xFFFFFFFFu, bc, 0); bsh = __shfl_sync(0xFFFFFFFFu, bsh, 0);
+                const unsigned below = (1u << lane) - 1u;
+                if (want_mis) Q.closest[next][bc + __popc(mm & below)] = pid | kMisRayBit;
+                if (cont) Q.closest[next][bc + __popc(mm) + __popc(mc & below)] = pid;
+                if (want_shadow) Q.shadow[bsh + __popc(ms & below)] = pid;
+            }
+        }
     }
 }
 
