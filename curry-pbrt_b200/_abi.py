@@ -107,7 +107,8 @@ class Stats(C.Structure):
                 ("ms_total", C.c_double), ("ms_trace", C.c_double), ("ms_shade", C.c_double),
                 ("ms_raygen_film", C.c_double), ("ms_reduce", C.c_double),
                 ("trace_parent_visits", C.c_uint64), ("trace_prim_tests", C.c_uint64),
-                ("trace_launches", C.c_uint64), ("ms_trace_closest", C.c_double), ("ms_trace_shadow", C.c_double)]
+                ("trace_launches", C.c_uint64), ("ms_trace_closest", C.c_double), ("ms_trace_shadow", C.c_double),
+                ("rays_closest_traced", C.c_uint64)]
 
 
 # name -> (restype, argtypes); every symbol include/cpbrt.h declares

@@ -68,6 +68,7 @@ struct cpbrt_ctx {
     std::vector<float> sphere_radius;
     std::vector<cpbrt_transform> transforms;
     BvhBuildResult bvh;
+    std::vector<DevLight> host_lights;
 
     DevScene scene;   // by-value kernel argument
     DevBuf d_prims, d_prim_uv, d_nodes, d_transforms, d_materials, d_textures, d_texels, d_lights, d_perm, d_primes, d_primsum, d_magic;
@@ -99,10 +100,12 @@ struct cpbrt_ctx {
 namespace {
 
 int alloc_upload(cpbrt_ctx* ctx, DevBuf& b, const void* src, size_t bytes) {
-    b.release();
     if (bytes == 0) bytes = 16;
-    CU(cudaMalloc(&b.p, bytes));
-    b.bytes = bytes;
+    if (b.bytes != bytes) {   // re-uploading a scene of the same shape reuses its buffers
+        b.release();
+        CU(cudaMalloc(&b.p, bytes));
+        b.bytes = bytes;
+    }
     if (src) CU(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
     else CU(cudaMemsetAsync(b.p, 0, bytes, ctx->stream));
     return 0;
@@ -253,7 +256,9 @@ int cpbrt_upload_scene(cpbrt_ctx* ctx, const cpbrt_scene_desc* d) {
                 else { memcpy(o.tri, d->triangles[s.shape.data].p, 36); o.area = host_tri_area(o.tri); }
             }
         }
+        for (auto& l : L) l.slot = 0xFFFFFFFFu;
         if (int rc = alloc_upload(ctx, ctx->d_lights, L.data(), L.size() * sizeof(DevLight))) return rc;
+        ctx->host_lights = L;
     }
     // sampler tables: PRIMS / PRIMSUM (halton.rs:141-214) and the caller's permutation
     {
@@ -374,6 +379,18 @@ int cpbrt_build_bvh(cpbrt_ctx* ctx, uint32_t* prim_order_out, cpbrt_bvh_dump* du
         }
     }
     if (int rc = alloc_upload(ctx, ctx->d_nodes, nodes.empty() ? nullptr : nodes.data(), nodes.size() * sizeof(float4))) return rc;
+    // BVH slot of each area light's primitive (when exactly one primitive carries the light)
+    {
+        std::vector<uint32_t> count(ctx->host_lights.size(), 0);
+        for (auto& l : ctx->host_lights) l.slot = 0xFFFFFFFFu;
+        for (uint32_t slot = 0; slot < n; ++slot) {
+            const cpbrt_primitive& p = ctx->primitives[R.order[slot]];
+            if (p.light >= 0) { ctx->host_lights[p.light].slot = slot; ++count[p.light]; }
+        }
+        for (size_t i = 0; i < count.size(); ++i) if (count[i] != 1) ctx->host_lights[i].slot = 0xFFFFFFFFu;
+        if (int rc = alloc_upload(ctx, ctx->d_lights, ctx->host_lights.data(), ctx->host_lights.size() * sizeof(DevLight))) return rc;
+        S.lights = (const DevLight*)ctx->d_lights.p;
+    }
     S.prims = (const float4*)ctx->d_prims.p;
     S.prim_uv = any_uv ? (const float*)ctx->d_prim_uv.p : nullptr;
     S.nodes = (const float4*)ctx->d_nodes.p;
@@ -577,7 +594,9 @@ int cpbrt_render(cpbrt_ctx* ctx, const cpbrt_render_params* params, float* film_
 
     const uint32_t npix = S.width * S.height;
     uint32_t spass = rp.samples_per_pass;
-    if (spass == 0) { spass = (4u << 20) / npix; if (spass < 1) spass = 1; if (spass > 16) spass = 16; }
+    // ~16 M paths per pass (3.6 GB of path state): long enough stages that launch gaps and the
+    // thinning later bounces do not matter, far below the 180 GB of HBM
+    if (spass == 0) { spass = (16u << 20) / npix; if (spass < 1) spass = 1; if (spass > 32) spass = 32; }
     if ((uint64_t)spass * npix >= 0x7FFFFFFFull) return ctx->fail(CPBRT_ERR_UNSUPPORTED, "film too large for one pass");
     if (int rc = ensure_wavefront(ctx, spass * npix)) return rc;
     const PathArrays P = ctx->P; const Queues Q = ctx->Q; const PixelArrays PX = ctx->PX;
@@ -620,9 +639,9 @@ int cpbrt_render(cpbrt_ctx* ctx, const cpbrt_render_params* params, float* film_
             span_begin(3);
             k_classify<<<g_pix, 256, 0, st>>>(P, Q, Sn * npix); ++launches;
             k_shade_terminal<<<g_shade, 128, 0, st>>>(S, P, Q);
-            k_shade<SHADE_MATTE><<<g_shade, 128, 0, st>>>(S, P, Q, next);
-            k_shade<SHADE_MIRROR><<<g_shade, 128, 0, st>>>(S, P, Q, next);
-            k_shade<SHADE_GLASS><<<g_shade, 128, 0, st>>>(S, P, Q, next);
+            k_shade<SHADE_MATTE><<<g_shade, 128, 0, st>>>(S, P, Q, next, T);
+            k_shade<SHADE_MIRROR><<<g_shade, 128, 0, st>>>(S, P, Q, next, T);
+            k_shade<SHADE_GLASS><<<g_shade, 128, 0, st>>>(S, P, Q, next, T);
             span_end();
             k_queue_reset<<<1, 32, 0, st>>>(Q, cur, 1, T);
             launches += 8;
@@ -680,7 +699,7 @@ int cpbrt_render(cpbrt_ctx* ctx, const cpbrt_render_params* params, float* film_
     if (stats) {
         memset(stats, 0, sizeof *stats);
         stats->camera_samples = (uint64_t)npix * (s_end - s_begin);
-        stats->rays_closest = t.rays_closest; stats->rays_any = t.rays_any; stats->nan_dropped = t.nan_dropped;
+        stats->rays_closest = t.rays_closest + t.elided_closest; stats->rays_closest_traced = t.rays_closest; stats->rays_any = t.rays_any; stats->nan_dropped = t.nan_dropped;
         stats->kernel_launches = launches; stats->ms_total = ms_render + ms_film;
         stats->ms_reduce = ctx->comm ? ms_film : 0.0; stats->ms_raygen_film = ms_film;
         if (prof) {

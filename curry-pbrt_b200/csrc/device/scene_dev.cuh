@@ -37,6 +37,7 @@ struct DevLight {
     float tri[9];        // AREA + triangle: object-space vertices
     float radius;        // AREA + sphere
     float area;          // Shape::area of the light's shape
+    uint32_t slot;       // AREA: BVH slot of the one primitive that carries this light, 0xFFFFFFFF if none or several
 };
 
 static constexpr uint32_t kMetaSphere = 1u, kMetaHasUv = 2u;

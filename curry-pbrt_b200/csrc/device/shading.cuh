@@ -101,6 +101,7 @@ CP_DEV bool delta_sample_f(const DeltaLobe& l, V3 wo, V3* wi, Spec* s) {
 
 template <int NL, int ND>
 struct BSDF {
+    static constexpr bool kNoDelta = ND == 0;
     V3 n, sn, snx, sny;
     Lobe lobes[NL > 0 ? NL : 1]; int n_lobes;
     DeltaLobe deltas[ND > 0 ? ND : 1]; int n_deltas;

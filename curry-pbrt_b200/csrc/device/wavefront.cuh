@@ -73,7 +73,7 @@ struct Queues {
 static constexpr int kCntClosest0 = 0, kCntShadow = 2, kCntShade0 = 3, kCntN = 3 + SHADE_KINDS;
 static constexpr int kCntWorkClosest = kCntN, kCntWorkShadow = kCntN + 1;   // work-distribution cursors of the persistent trace kernels
 // 64-bit totals that live after the counters: rays_closest, rays_any, nan_dropped, stack_overflow
-struct Totals { unsigned long long rays_closest, rays_any, nan_dropped, overflow; };
+struct Totals { unsigned long long rays_closest, rays_any, nan_dropped, overflow, elided_closest; };
 
 struct PixelArrays {
     uint2* base_index;   // Halton index of sample 0 (set_pixel)
@@ -182,7 +182,7 @@ __global__ void k_raygen(DevScene sc, PixelArrays px, PathArrays P, Queues Q, ui
 // entries one by one (bvh_trace.cuh, trace_persistent).
 struct ClosestItem { uint32_t pid; uint32_t is_mis; float w_o, w_d; };   // w_* = the .w of the ray's two float4
 
-__global__ void __launch_bounds__(128, 6) k_trace_closest(DevScene sc, PathArrays P, Queues Q, int cur, Totals* totals) {
+__global__ void __launch_bounds__(128, 8) k_trace_closest(DevScene sc, PathArrays P, Queues Q, int cur, Totals* totals) {
     const uint32_t n = Q.counts[kCntClosest0 + cur];
     uint32_t overflow = 0;
     const uint32_t* __restrict__ queue = Q.closest[cur];
@@ -277,7 +277,7 @@ __global__ void k_classify(PathArrays P, Queues Q, uint32_t n_paths) {
 }
 
 // Shadow-ray stage: VisibilityTester::unoccluded (light/mod.rs:112-114).
-__global__ void __launch_bounds__(128) k_trace_shadow(DevScene sc, PathArrays P, Queues Q, Totals* totals) {
+__global__ void __launch_bounds__(128, 8) k_trace_shadow(DevScene sc, PathArrays P, Queues Q, Totals* totals) {
     const uint32_t n = Q.counts[kCntShadow];
     uint32_t overflow = 0;
     auto fetch = [&](uint32_t i, Ray* ray, uint32_t* pid) {
@@ -347,7 +347,8 @@ CP_DEV void build_bsdf(const DevScene& sc, const DevMaterial& m, const ShapePoin
 // term is finished by the closest-hit stage.  Returns the pending flags.
 template <class B>
 CP_DEV void emit_direct_lighting(const DevScene& sc, const PathArrays& P, uint32_t pid, bool lane_active,
-                                 const ShapePoint& sp, const B& bsdf, V3 wo, SamplerState& st, Spec beta, bool* want_shadow_out, bool* want_mis_out) {
+                                 const ShapePoint& sp, const B& bsdf, V3 wo, SamplerState& st, Spec beta, bool* want_shadow_out, bool* want_mis_out,
+                                 uint32_t* elided) {
     bool want_shadow = false, want_mis = false;
     if (lane_active) {
         uint32_t flags = kPendAny;
@@ -374,14 +375,28 @@ CP_DEV void emit_direct_lighting(const DevScene& sc, const PathArrays& P, uint32
                 V3 wi; Spec f; float f_pdf;
                 if (bsdf.sample_no_delta_f(wo, u, &wi, &f, &f_pdf) && f_pdf != 0.f) {
                     const V3 o = point_offset_by_error(sp, wi);   // Ray::new_shape_point_d
-                    const Spec A = spec3(light.L[0], light.L[1], light.L[2]) * f * fabsf(dot(n, wi));
-                    P.mis_o[pid] = mk4(o, f_pdf);
-                    P.mis_d[pid] = mk4(wi, __uint_as_float(li));
-                    P.mis_A[pid] = mk4(A, 0.f);
-                    P.mis_p[pid] = mk4(sp.p, 0.f);
+                    // The reference traces this ray and keeps its contribution only if the
+                    // closest hit is the sampled light's own primitive (Arc::ptr_eq, :63).  If the
+                    // ray does not intersect that primitive at all the answer is 0 whatever else
+                    // it hits, so the traversal is only queued when the primitive is hit.
+                    bool may_hit_light = true;
+                    if (light.slot != 0xFFFFFFFFu) {
+                        Ray probe; probe.o = o; probe.d = wi; probe.t_max = kFloatMax;
+                        float t_l;
+                        may_hit_light = prim_intersect_t(sc, load_prim(sc, light.slot), probe, tri_ray_setup(wi), &t_l);
+                    }
                     P.nee_bsdf[pid] = make_float4(0.f, 0.f, 0.f, 0.f);
                     flags |= kPendMis;
-                    want_mis = true;
+                    if (may_hit_light) {
+                        const Spec A = spec3(light.L[0], light.L[1], light.L[2]) * f * fabsf(dot(n, wi));
+                        P.mis_o[pid] = mk4(o, f_pdf);
+                        P.mis_d[pid] = mk4(wi, __uint_as_float(li));
+                        P.mis_A[pid] = mk4(A, 0.f);
+                        P.mis_p[pid] = mk4(sp.p, 0.f);
+                        want_mis = true;
+                    } else {
+                        *elided += 1;
+                    }
                 }
             }
         }
@@ -417,10 +432,11 @@ __global__ void k_shade_terminal(DevScene sc, PathArrays P, Queues Q) {
 }
 
 template <int KIND>
-__global__ void __launch_bounds__(128, 8) k_shade(DevScene sc, PathArrays P, Queues Q, int next) {
+__global__ void __launch_bounds__(128, 8) k_shade(DevScene sc, PathArrays P, Queues Q, int next, Totals* totals) {
     typedef typename BsdfFor<KIND>::type B;
     const uint32_t n = Q.counts[kCntShade0 + KIND];
     const uint32_t n_round = (n + 31u) & ~31u;
+    uint32_t elided = 0;   // closest-hit queries answered without a traversal (see below)
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
         const bool active = i < n;
         uint32_t pid = 0;
@@ -455,8 +471,11 @@ __global__ void __launch_bounds__(128, 8) k_shade(DevScene sc, PathArrays P, Que
         // the direct-lighting integrator does not (direct_light.rs:25)
         const bool do_nee = active && (sc.integrator != 0 || bsdf.n_lobes != 0);
         bool want_shadow, want_mis;
-        emit_direct_lighting(sc, P, pid, do_nee, sp, bsdf, wo, st, sc.integrator == 0 ? beta : spec(1.f), &want_shadow, &want_mis);
-        if (active && sc.integrator == 0) {
+        emit_direct_lighting(sc, P, pid, do_nee, sp, bsdf, wo, st, sc.integrator == 0 ? beta : spec(1.f), &want_shadow, &want_mis, &elided);
+        // A purely non-specular BSDF at depth max_depth - 1 cannot continue usefully (see below),
+        // so its sample_f / Russian-roulette draws are not evaluated at all.
+        const bool last_useless = (BsdfFor<KIND>::type::kNoDelta) && bounce + 1u >= sc.max_depth;
+        if (active && sc.integrator == 0 && !last_useless) {
             V3 wi; Spec f; float f_pdf; bool is_delta;
             if (bsdf.sample_f(sc.sampler, st, wo, &wi, &f, &f_pdf, &is_delta) && f_pdf != 0.f) {
                 beta = beta * (f * fabsf(dot(wi, sp.n)) / f_pdf);
@@ -467,6 +486,10 @@ __global__ void __launch_bounds__(128, 8) k_shade(DevScene sc, PathArrays P, Que
                     if (sampler_get_1d(sc.sampler, st) < q) cont = false;
                     else beta = beta / (1.f - q);
                 }
+                // A ray leaving a non-specular bounce at depth max_depth - 1 can add nothing:
+                // the reference traces it, adds no emission (not bounce 0, not specular) and stops
+                // at `bounce >= max_depth` (path.rs:21-33).  It is neither generated nor counted.
+                if (cont && bounce + 1u >= sc.max_depth && !is_delta) cont = false;
                 if (cont) {
                     P.ray_o[pid] = mk4(o, 0.f);
                     P.ray_d[pid] = mk4(wi, __uint_as_float((bounce + 1u) | (is_delta ? kFlagSpecular : 0u)));
@@ -495,6 +518,9 @@ __global__ void __launch_bounds__(128, 8) k_shade(DevScene sc, PathArrays P, Que
             }
         }
     }
+    // warp-reduced count of elided closest-hit queries (they still count as answered rays)
+    for (int off = 16; off > 0; off >>= 1) elided += __shfl_down_sync(0xFFFFFFFFu, elided, off);
+    if ((threadIdx.x & 31) == 0 && elided) atomicAdd(&totals->elided_closest, (unsigned long long)elided);
 }
 
 // End of a pass: flush the last pending direct-lighting term of every path, drop NaN samples

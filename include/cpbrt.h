@@ -217,7 +217,8 @@ typedef struct cpbrt_render_params {
 
 typedef struct cpbrt_stats {
     uint64_t camera_samples;        /* W*H*(sample_end-sample_begin) */
-    uint64_t rays_closest;          /* Scene::intersect calls (camera + continuation + MIS rays) */
+    uint64_t rays_closest;          /* Scene::intersect calls of the reference (camera + continuation + MIS rays),
+                                       whether answered by a traversal or elided (see rays_closest_traced) */
     uint64_t rays_any;              /* Scene::intersect_predicate calls (shadow rays) */
     uint64_t nan_dropped;           /* samples dropped by li.has_nan() (render.rs:34-37) */
     uint64_t kernel_launches;       /* CUDA kernels launched by this call */
@@ -231,6 +232,8 @@ typedef struct cpbrt_stats {
     uint64_t trace_launches;        /* profile_stages: launches of the closest-hit traversal kernel */
     double   ms_trace_closest;      /* profile_stages: device time inside those launches */
     double   ms_trace_shadow;
+    uint64_t rays_closest_traced;   /* closest-hit queries that needed a BVH traversal: MIS rays that miss their
+                                       light's primitive and last-depth non-specular rays are answered without one */
 } cpbrt_stats;
 
 /* ------------------------------------------------------------------------------------------

@@ -1155,7 +1155,7 @@ static LightSample light_sample_li(const World& w, uint32_t li, const ShapePoint
 // =============================================================================================
 // Integrators (src/integrator/*.rs)
 // =============================================================================================
-struct RenderCounters { uint64_t rays_closest = 0, rays_any = 0, nan_dropped = 0; TraceCounters closest, any; bool count_visits = false; };
+struct RenderCounters { uint64_t rays_closest = 0, rays_any = 0, nan_dropped = 0, rays_unused_last = 0; TraceCounters closest, any; bool count_visits = false; };
 
 static Hit trace(const World& w, const Ray& r, RenderCounters& c) { ++c.rays_closest; return scene_intersect(w.scene, r, c.count_visits ? &c.closest : nullptr); }
 
@@ -1225,6 +1225,8 @@ static Spectrum path_li(const World& w, Ray ray, Sampler& smp, uint32_t max_dept
     uint32_t bounce = 0; bool specular_bounce = false;
     for (;;) {
         Hit h = trace(w, ray, c);
+        // bookkeeping only: this ray's result cannot influence the estimate (no emission added, loop ends below)
+        if (bounce >= max_depth && !(bounce == 0 || specular_bounce)) ++c.rays_unused_last;
         if (bounce == 0 || specular_bounce) {
             if (h.hit) {
                 const cpbrt_primitive& hp = sc.prim_at(h.slot);
@@ -1360,7 +1362,7 @@ static void render(const World& w, const RenderOptions& opt, Float* film, Render
                     render_pixel(w, opt, x, y, smp, film + (size_t(y) * W + x) * 3, c);
         }
         std::lock_guard<std::mutex> g(mu);
-        total->rays_closest += c.rays_closest; total->rays_any += c.rays_any; total->nan_dropped += c.nan_dropped;
+        total->rays_closest += c.rays_closest; total->rays_any += c.rays_any; total->nan_dropped += c.nan_dropped; total->rays_unused_last += c.rays_unused_last;
         total->closest.parent_visits += c.closest.parent_visits; total->closest.prim_tests += c.closest.prim_tests;
         total->any.parent_visits += c.any.parent_visits; total->any.prim_tests += c.any.prim_tests;
     };
@@ -1489,7 +1491,9 @@ void orc_trace_closest_plain(const orc_world* o, const cpbrt_ray* rays, uint64_t
 // the rectangle).  integrator / max_depth < 0 = take them from the description.
 // stats_out: [0] rays_closest [1] rays_any [2] nan_dropped, and when count_visits != 0 also
 // [3] closest Parent visits [4] closest primitive tests [5] any-hit Parent visits [6] any-hit
-// primitive tests (the algorithmic traversal work of SURVEY 8d); returns render seconds.
+// primitive tests (the algorithmic traversal work of SURVEY 8d); [7] closest-hit rays whose result
+// cannot affect the estimate (traced at bounce == max_depth after a non-specular bounce);
+// returns render seconds.
 double orc_render(const orc_world* o, int integrator, int max_depth, uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1,
                   uint32_t threads, float* film, uint64_t* stats_out, int count_visits) {
     const cpbrt_scene_desc* d = o->w.scene.d;
@@ -1504,7 +1508,7 @@ double orc_render(const orc_world* o, int integrator, int max_depth, uint32_t x0
     render(o->w, opt, film, &c);
     double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (stats_out) {
-        stats_out[0] = c.rays_closest; stats_out[1] = c.rays_any; stats_out[2] = c.nan_dropped;
+        stats_out[0] = c.rays_closest; stats_out[1] = c.rays_any; stats_out[2] = c.nan_dropped; stats_out[7] = c.rays_unused_last;
         if (count_visits) { stats_out[3] = c.closest.parent_visits; stats_out[4] = c.closest.prim_tests; stats_out[5] = c.any.parent_visits; stats_out[6] = c.any.prim_tests; }
     }
     return sec;

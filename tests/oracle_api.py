@@ -126,10 +126,10 @@ class OracleWorld:
         """Returns (film[H, W, 3], seconds, dict(rays_closest, rays_any, nan_dropped[, visit counts]))."""
         if film is None:
             film = np.zeros((self.height, self.width, 3), np.float32)
-        st = np.zeros(7, np.uint64)
+        st = np.zeros(8, np.uint64)
         sec = lib.orc_render(self._w, integrator, max_depth, rect[0], rect[1], rect[2], rect[3], threads,
                              film.ctypes.data, st.ctypes.data, int(count_visits))
-        out = dict(rays_closest=int(st[0]), rays_any=int(st[1]), nan_dropped=int(st[2]))
+        out = dict(rays_closest=int(st[0]), rays_any=int(st[1]), nan_dropped=int(st[2]), rays_unused_last=int(st[7]))
         if count_visits:
             out.update(closest_parent_visits=int(st[3]), closest_prim_tests=int(st[4]),
                        any_parent_visits=int(st[5]), any_prim_tests=int(st[6]))
