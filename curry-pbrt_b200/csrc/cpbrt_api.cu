@@ -639,7 +639,7 @@ int cpbrt_render(cpbrt_ctx* ctx, const cpbrt_render_params* params, float* film_
             span_begin(3);
             k_classify<<<g_pix, 256, 0, st>>>(P, Q, Sn * npix); ++launches;
             k_shade_terminal<<<g_shade, 128, 0, st>>>(S, P, Q);
-            k_shade<SHADE_MATTE><<<g_shade, 128, 0, st>>>(S, P, Q, next, T);
+            k_shade<SHADE_MATTE><<<grid_for(ctx, ShadeBlocks<SHADE_MATTE>::value), 128, 0, st>>>(S, P, Q, next, T);
             k_shade<SHADE_MIRROR><<<g_shade, 128, 0, st>>>(S, P, Q, next, T);
             k_shade<SHADE_GLASS><<<g_shade, 128, 0, st>>>(S, P, Q, next, T);
             span_end();

@@ -35,7 +35,19 @@ CP_DEV V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
 CP_DEV V3 operator-(V3 a) { return v3(-a.x, -a.y, -a.z); }
 CP_DEV V3 operator*(V3 a, float s) { return v3(a.x * s, a.y * s, a.z * s); }
 CP_DEV V3 operator*(float s, V3 a) { return v3(s * a.x, s * a.y, s * a.z); }
-CP_DEV V3 operator/(V3 a, float s) { return v3(a.x / s, a.y / s, a.z / s); }
+// IEEE a / s, same bits as the plain operator.  nvcc's inline division leaves a ZERO dividend to an
+// out-of-line path that the whole warp then walks through (FCHK), and zero components are the
+// common case here (axis-aligned normals, black channels): 0 / s is answered as 0 * s (same
+// signed zero) whenever s is an ordinary number, everything else takes the normal sequence.
+CP_DEV bool div_ordinary(float s) { const float a = fabsf(s); return a >= 1e-30f && a <= 1e30f; }
+CP_DEV float div_by(float a, float s, bool ordinary) {
+    const bool z = ordinary && a == 0.f;
+    float num = z ? 1.f : a;
+    asm("" : "+f"(num));   // opaque: keeps the compiler from folding this back into a / s
+    const float q = num / s;
+    return z ? a * s : q;
+}
+CP_DEV V3 operator/(V3 a, float s) { const bool o = div_ordinary(s); return v3(div_by(a.x, s, o), div_by(a.y, s, o), div_by(a.z, s, o)); }
 CP_DEV float dot(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
 CP_DEV float length_sq(V3 a) { return dot(a, a); }
 CP_DEV float length(V3 a) { return sqrtf(dot(a, a)); }
@@ -53,7 +65,7 @@ CP_DEV Spec operator+(Spec a, Spec b) { return spec3(a.r + b.r, a.g + b.g, a.b +
 CP_DEV Spec operator-(Spec a, Spec b) { return spec3(a.r - b.r, a.g - b.g, a.b - b.b); }
 CP_DEV Spec operator*(Spec a, Spec b) { return spec3(a.r * b.r, a.g * b.g, a.b * b.b); }
 CP_DEV Spec operator*(Spec a, float s) { return spec3(a.r * s, a.g * s, a.b * s); }
-CP_DEV Spec operator/(Spec a, float s) { return spec3(a.r / s, a.g / s, a.b / s); }
+CP_DEV Spec operator/(Spec a, float s) { const bool o = div_ordinary(s); return spec3(div_by(a.r, s, o), div_by(a.g, s, o), div_by(a.b, s, o)); }
 CP_DEV float lum(Spec s) { return (0.212671f * s.r + 0.715160f * s.g) + 0.072169f * s.b; }   // y()
 CP_DEV bool is_black(Spec s) { return s.r == 0.f && s.g == 0.f && s.b == 0.f; }
 CP_DEV bool has_nan(Spec s) { return s.r != s.r || s.g != s.g || s.b != s.b; }

@@ -171,6 +171,46 @@ def test_any_hit_bit_exact(cornell, spheres, mesh):
     assert np.array_equal(r.trace_any(e), w.trace_any(e))
 
 
+def edge_grazing_rays(scene, n_per_edge=96, seed=5):
+    """Rays aimed at points on (and a hair off) every triangle edge and vertex of the scene from
+    origins inside its box: where a conservative pre-test and the exact test could disagree."""
+    rng = np.random.default_rng(seed)
+    d = scene.desc
+    tris = np.array([[list(d.triangles[i].p[k]) for k in range(3)] for i in range(d.n_triangles)], np.float64)
+    lo, hi = tris.reshape(-1, 3).min(0), tris.reshape(-1, 3).max(0)
+    rays = []
+    for tri in tris:
+        for e in range(3):
+            a, b = tri[e], tri[(e + 1) % 3]
+            s = rng.random(n_per_edge); s[:8] = (0, 1, 0, 1, 0.5, 0.5, 1e-7, 1 - 1e-7)
+            pts = a + s[:, None] * (b - a)
+            off = rng.normal(size=(n_per_edge, 3)); off /= np.linalg.norm(off, axis=1, keepdims=True)
+            mag = np.linalg.norm(b - a) * rng.choice([0.0, 1e-7, 1e-6, 1e-5, 1e-4, 1e-2], n_per_edge)
+            pts = pts + off * mag[:, None]
+            org = lo + rng.random((n_per_edge, 3)) * (hi - lo)
+            org[::7] = (278.0, 273.0, -800.0)
+            dirs = pts - org
+            scale = rng.choice([1.0, 0.37, 1e-3], n_per_edge)[:, None]
+            dirs = dirs / np.linalg.norm(dirs, axis=1, keepdims=True) * np.where(scale == 1.0, np.linalg.norm(dirs, axis=1, keepdims=True), scale)
+            r = np.zeros((n_per_edge, 8), np.float32)
+            r[:, 0:3] = org; r[:, 3] = np.finfo(np.float32).max; r[:, 4:7] = dirs
+            rays.append(r)
+    return np.concatenate(rays)
+
+
+def test_edge_grazing_rays(cornell):
+    """Hit ids and distance bits on rays through edges / vertices of every triangle, and the same
+    rays as shadow rays with t_max just short of / just past the targeted point."""
+    scene, r, w, _ = cornell
+    rays = edge_grazing_rays(scene)
+    a = r.trace_closest(rays)
+    o = w.trace_closest(rays)
+    assert np.array_equal(a["prim"], o["prim"]) and np.array_equal(a["t"].view(np.uint32), o["t"].view(np.uint32))
+    for tm in (0.999, 1.0, 1.001):
+        sh = rays.copy(); sh[:, 3] = np.float32(tm)
+        assert np.array_equal(r.trace_any(sh), w.trace_any(sh))
+
+
 def test_empty_and_ragged_batches(cornell):
     _, r, w, _ = cornell
     assert len(r.trace_closest(np.zeros((0, 8), np.float32))["prim"]) == 0
