@@ -62,7 +62,7 @@ struct cpbrt_ctx {
     std::string error;
 
     // host copy of what the BVH build needs
-    bool has_scene = false, has_bvh = false;
+    bool has_scene = false, has_bvh = false, has_general_materials = false;
     std::vector<cpbrt_primitive> primitives;
     std::vector<cpbrt_triangle> triangles;
     std::vector<float> sphere_radius;
@@ -71,7 +71,7 @@ struct cpbrt_ctx {
     std::vector<DevLight> host_lights;
 
     DevScene scene;   // by-value kernel argument
-    DevBuf d_prims, d_prim_uv, d_nodes, d_transforms, d_materials, d_textures, d_texels, d_lights, d_perm, d_primes, d_primsum, d_magic;
+    DevBuf d_prims, d_prim_uv, d_nodes, d_env, d_transforms, d_materials, d_textures, d_texels, d_lights, d_perm, d_primes, d_primsum, d_magic;
 
     // wavefront state
     uint32_t path_capacity = 0;
@@ -155,7 +155,7 @@ void cpbrt_destroy(cpbrt_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
-    DevBuf* bufs[] = {&ctx->d_prims, &ctx->d_prim_uv, &ctx->d_nodes, &ctx->d_transforms, &ctx->d_materials, &ctx->d_textures, &ctx->d_texels,
+    DevBuf* bufs[] = {&ctx->d_prims, &ctx->d_prim_uv, &ctx->d_nodes, &ctx->d_env, &ctx->d_transforms, &ctx->d_materials, &ctx->d_textures, &ctx->d_texels,
                       &ctx->d_lights, &ctx->d_perm, &ctx->d_primes, &ctx->d_primsum, &ctx->d_magic, &ctx->d_path, &ctx->d_kind, &ctx->d_queues, &ctx->d_counts,
                       &ctx->d_pixels, &ctx->d_totals_buf, &ctx->d_film_out};
     for (DevBuf* b : bufs) b->release();
@@ -186,11 +186,45 @@ int cpbrt_upload_scene(cpbrt_ctx* ctx, const cpbrt_scene_desc* d) {
             if (x >= (int32_t)d->n_transforms || ++hops > 8) return ctx->fail(CPBRT_ERR_UNSUPPORTED, "transform chain %u: longer than 8 links or out of range", i);
         }
     }
+    bool has_general = false;
     for (uint32_t i = 0; i < d->n_materials; ++i) {
         const cpbrt_material& m = d->materials[i];
-        if (m.type > CPBRT_MAT_GLASS) return ctx->fail(CPBRT_ERR_UNSUPPORTED, "material %u: type %u has no device implementation yet (matte, mirror, glass do)", i, m.type);
-        const int need = m.type == CPBRT_MAT_MATTE ? 2 : (m.type == CPBRT_MAT_MIRROR ? 1 : 3);
-        for (int k = 0; k < need; ++k) if (m.tex[k] < 0 || m.tex[k] >= (int32_t)d->n_textures) return ctx->fail(CPBRT_ERR_BAD_ARG, "material %u: texture slot %d out of range", i, k);
+        if (m.type > CPBRT_MAT_MIX) return ctx->fail(CPBRT_ERR_BAD_ARG, "material %u: unknown type %u", i, m.type);
+        // texture slots every material type reads (include/cpbrt.h); uber's urough / vrough (5, 6) are optional
+        static const int need_n[7] = {2, 1, 3, 3, 9, 5, 1};
+        for (int k = 0; k < need_n[m.type]; ++k) {
+            const bool optional = m.type == CPBRT_MAT_UBER && (k == 5 || k == 6);
+            if (m.tex[k] >= (int32_t)d->n_textures || (m.tex[k] < 0 && !optional)) return ctx->fail(CPBRT_ERR_BAD_ARG, "material %u: texture slot %d out of range", i, k);
+        }
+        if (m.type == CPBRT_MAT_MIX) {
+            for (int k = 0; k < 2; ++k) if (m.sub[k] < 0 || m.sub[k] >= (int32_t)d->n_materials) return ctx->fail(CPBRT_ERR_BAD_ARG, "material %u: mix operand %d out of range", i, k);
+        }
+        if (m.type > CPBRT_MAT_GLASS) has_general = true;
+    }
+    // mix trees: no cycles, nesting no deeper than the scale stack of a lobe (bsdf_general.cuh)
+    {
+        std::vector<int> depth(d->n_materials, -1);   // -1 unknown, -2 on the stack
+        std::vector<std::pair<uint32_t, int>> stack;
+        for (uint32_t i = 0; i < d->n_materials; ++i) {
+            if (depth[i] >= 0) continue;
+            stack.assign(1, std::make_pair(i, 0));
+            while (!stack.empty()) {
+                const uint32_t mi = stack.back().first; const int phase = stack.back().second;
+                const cpbrt_material& m = d->materials[mi];
+                if (m.type != CPBRT_MAT_MIX) { depth[mi] = 0; stack.pop_back(); continue; }
+                if (phase < 2) {
+                    depth[mi] = -2;
+                    stack.back().second = phase + 1;
+                    const uint32_t c = (uint32_t)m.sub[phase];
+                    if (depth[c] == -2) return ctx->fail(CPBRT_ERR_BAD_ARG, "material %u: mix materials form a cycle", mi);
+                    if (depth[c] < 0) stack.push_back(std::make_pair(c, 0));
+                } else {
+                    depth[mi] = 1 + std::max(depth[m.sub[0]], depth[m.sub[1]]);
+                    if (depth[mi] > kMaxScales) return ctx->fail(CPBRT_ERR_UNSUPPORTED, "material %u: mix nesting deeper than %d", mi, kMaxScales);
+                    stack.pop_back();
+                }
+            }
+        }
     }
     for (uint32_t i = 0; i < d->n_textures; ++i) {
         const cpbrt_texture& t = d->textures[i];
@@ -199,7 +233,8 @@ int cpbrt_upload_scene(cpbrt_ctx* ctx, const cpbrt_scene_desc* d) {
     }
     for (uint32_t i = 0; i < d->n_lights; ++i) {
         const cpbrt_light& l = d->lights[i];
-        if (l.type > CPBRT_LIGHT_DISTANT) return ctx->fail(CPBRT_ERR_UNSUPPORTED, "light %u: infinite area lights have no device implementation yet", i);
+        if (l.type > CPBRT_LIGHT_INFINITE) return ctx->fail(CPBRT_ERR_BAD_ARG, "light %u: unknown type %u", i, l.type);
+        if (l.type == CPBRT_LIGHT_INFINITE && (l.tex < 0 || l.tex >= (int32_t)d->n_textures)) return ctx->fail(CPBRT_ERR_BAD_ARG, "light %u: environment texture out of range", i);
         if (l.type == CPBRT_LIGHT_AREA) {
             if (l.shape.kind > CPBRT_SHAPE_SPHERE || (l.shape.kind == CPBRT_SHAPE_TRIANGLE ? l.shape.data >= d->n_triangles : l.shape.data >= d->n_spheres) ||
                 l.shape.xform >= (int32_t)d->n_transforms)
@@ -213,7 +248,7 @@ int cpbrt_upload_scene(cpbrt_ctx* ctx, const cpbrt_scene_desc* d) {
     }
     if (d->max_depth > 200) return ctx->fail(CPBRT_ERR_UNSUPPORTED, "max_depth > 200");
 
-    ctx->has_scene = false; ctx->has_bvh = false;
+    ctx->has_scene = false; ctx->has_bvh = false; ctx->has_general_materials = has_general;
     ctx->primitives.assign(d->primitives, d->primitives + d->n_primitives);
     ctx->triangles.assign(d->triangles, d->triangles + d->n_triangles);
     ctx->sphere_radius.assign(d->sphere_radius, d->sphere_radius + d->n_spheres);
@@ -257,6 +292,37 @@ int cpbrt_upload_scene(cpbrt_ctx* ctx, const cpbrt_scene_desc* d) {
             }
         }
         for (auto& l : L) l.slot = 0xFFFFFFFFu;
+        // InfiniteAreaLight::new (infinite_area.rs:10-26): Distribution2D over luminance * sin(theta),
+        // with theta = (row + 0.5) / rows exactly as written there (no factor pi)
+        std::vector<float> env;
+        for (uint32_t i = 0; i < d->n_lights; ++i) {
+            if (d->lights[i].type != CPBRT_LIGHT_INFINITE) continue;
+            const cpbrt_texture& t = d->textures[d->lights[i].tex];
+            const uint32_t w = t.kind == CPBRT_TEX_IMAGE ? t.width : 1, h = t.kind == CPBRT_TEX_IMAGE ? t.height : 1;
+            if (t.kind == CPBRT_TEX_IMAGE && t.channels != 3) return ctx->fail(CPBRT_ERR_BAD_ARG, "light %u: environment map must be a spectrum texture", i);
+            L[i].env_w = w; L[i].env_h = h; L[i].env_off = env.size();
+            env.resize(env.size() + 2ull * h + 2ull * h * w);
+            float* row_pdf = env.data() + L[i].env_off; float* row_cdf = row_pdf + h; float* col_pdf = row_cdf + h; float* col_cdf = col_pdf + (size_t)h * w;
+            std::vector<float> f(w), fsum(h);
+            auto distribution = [](const float* fv, size_t len, float* pdf, float* cdf) {   // Distribution1D::from (distribution.rs:16-33)
+                const float n = (float)len; float last = 0.f;
+                for (size_t k = 0; k < len; ++k) { cdf[k] = last + fv[k] / n; last = cdf[k]; }
+                const float f_sum = cdf[len - 1];
+                for (size_t k = 0; k < len; ++k) { cdf[k] /= f_sum; pdf[k] = fv[k] / (n * f_sum); }
+                return f_sum;
+            };
+            for (uint32_t y = 0; y < h; ++y) {
+                const float theta = ((float)y + 0.5f) / (float)h;
+                for (uint32_t x = 0; x < w; ++x) {
+                    const float* px = t.kind == CPBRT_TEX_IMAGE ? d->texels + t.offset + ((size_t)x + (size_t)y * w) * 3 : t.value;
+                    const float lum = (0.212671f * px[0] + 0.715160f * px[1]) + 0.072169f * px[2];   // RGBSpectrum::y
+                    f[x] = lum * sinf(theta);
+                }
+                fsum[y] = distribution(f.data(), w, col_pdf + (size_t)y * w, col_cdf + (size_t)y * w);
+            }
+            distribution(fsum.data(), h, row_pdf, row_cdf);
+        }
+        if (int rc = alloc_upload(ctx, ctx->d_env, env.empty() ? nullptr : env.data(), env.size() * sizeof(float))) return rc;
         if (int rc = alloc_upload(ctx, ctx->d_lights, L.data(), L.size() * sizeof(DevLight))) return rc;
         ctx->host_lights = L;
     }
@@ -287,6 +353,7 @@ int cpbrt_upload_scene(cpbrt_ctx* ctx, const cpbrt_scene_desc* d) {
     S.textures = (const DevTexture*)ctx->d_textures.p;
     S.texels = (const float*)ctx->d_texels.p;
     S.lights = (const DevLight*)ctx->d_lights.p;
+    S.env = (const float*)ctx->d_env.p;
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->has_scene = true;
     return CPBRT_OK;
@@ -412,6 +479,7 @@ static int ensure_totals(cpbrt_ctx* ctx) {
 
 static int check_overflow(cpbrt_ctx* ctx, const Totals& t) {
     if (t.overflow) return ctx->fail(CPBRT_ERR_UNSUPPORTED, "BVH deeper than the %d-entry traversal stack", kStackSize);
+    if (t.bsdf_overflow) return ctx->fail(CPBRT_ERR_UNSUPPORTED, "a material expands to more than %d lobes of one kind", kMaxLobes);
     return 0;
 }
 
@@ -642,6 +710,7 @@ int cpbrt_render(cpbrt_ctx* ctx, const cpbrt_render_params* params, float* film_
             k_shade<SHADE_MATTE><<<grid_for(ctx, ShadeBlocks<SHADE_MATTE>::value), 128, 0, st>>>(S, P, Q, next, T);
             k_shade<SHADE_MIRROR><<<g_shade, 128, 0, st>>>(S, P, Q, next, T);
             k_shade<SHADE_GLASS><<<g_shade, 128, 0, st>>>(S, P, Q, next, T);
+            if (ctx->has_general_materials) { k_shade<SHADE_GENERAL><<<grid_for(ctx, ShadeBlocks<SHADE_GENERAL>::value), 128, 0, st>>>(S, P, Q, next, T); ++launches; }
             span_end();
             k_queue_reset<<<1, 32, 0, st>>>(Q, cur, 1, T);
             launches += 8;

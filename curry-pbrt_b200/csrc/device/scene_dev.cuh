@@ -38,6 +38,10 @@ struct DevLight {
     float radius;        // AREA + sphere
     float area;          // Shape::area of the light's shape
     uint32_t slot;       // AREA: BVH slot of the one primitive that carries this light, 0xFFFFFFFF if none or several
+    // INFINITE: Distribution2D over the environment map (infinite_area.rs:11-26), four f32 tables at
+    // DevScene::env + env_off: row pdf [h], row cdf [h], per-row pdf [h * w], per-row cdf [h * w]
+    uint32_t env_w, env_h;
+    uint64_t env_off;
 };
 
 static constexpr uint32_t kMetaSphere = 1u, kMetaHasUv = 2u;
@@ -77,6 +81,7 @@ struct DevScene {
     const DevTexture* textures;
     const float* texels;
     const DevLight* lights;
+    const float* env;           // distribution tables of the infinite lights
     uint32_t n_lights;
     uint32_t integrator, max_depth;
     uint32_t width, height;

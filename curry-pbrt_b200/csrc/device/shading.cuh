@@ -271,6 +271,53 @@ CP_DEV Ray visibility_new(const ShapePoint& from, const ShapePoint& to) {   // l
 }
 CP_DEV bool light_is_delta(const DevLight& l) { return l.type == 1 || l.type == 2; }
 
+// ---- InfiniteAreaLight (src/light/infinite_area.rs) -------------------------------------------
+CP_DEV P2 spherical_to_normalize_phi_theta(V3 w) {   // math/mod.rs:135-141
+    const float p = atan2f(w.y, w.x);
+    P2 r;
+    r.x = (p < 0.f ? p + 2.f * kPi : p) / 2.f * kInvPi;
+    r.y = acosf(rclamp(w.z, -1.f, 1.f)) * kInvPi;
+    return r;
+}
+CP_DEV V3 normalize_phi_theta_to_spherical(P2 pt) {   // math/mod.rs:143-151
+    const float theta = pt.y * kPi, phi = pt.x * kPi * 2.f;
+    const float ct = cosf(theta), st = sinf(theta), cp = cosf(phi), sp = sinf(phi);
+    return v3(st * cp, st * sp, ct);
+}
+// Distribution1D::sample_remap (distribution.rs:48-56): first i with u <= cdf[i].  The reference
+// scans linearly; the cdf is non-decreasing, so a binary search lands on the same entry (and on
+// the same "nothing matched" fallback when the table is all NaN).
+CP_DEV void dist_sample_remap(const float* __restrict__ pdf, const float* __restrict__ cdf, uint32_t len, float u, uint32_t* idx, float* p, float* remap) {
+    uint32_t lo = 0, hi = len;
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (u <= __ldg(&cdf[mid])) hi = mid; else lo = mid + 1; }
+    if (lo < len) { const float c = __ldg(&cdf[lo]), q = __ldg(&pdf[lo]); *idx = lo; *p = q; *remap = (c - u) / q; }
+    else { *idx = len - 1; *p = __ldg(&pdf[len - 1]); *remap = 1.f; }
+}
+CP_DEV Spec infinite_le(const DevScene& sc, const DevLight& l, V3 d, P2* uv_out) {   // le_out_scene (:35-39)
+    P2 uv = spherical_to_normalize_phi_theta(normalize(d));
+    uv.y = 1.f - uv.y;
+    if (uv_out) *uv_out = uv;
+    return tex_eval(sc, l.tex, uv);
+}
+CP_DEV float infinite_out_scene_pdf(const DevScene& sc, const DevLight& l, P2 uv) {   // out_scene_pdf (:40-51) + Distribution2D::continuous_pdf (distribution.rs:119-126)
+    const float nx = (float)l.env_h, ny = (float)l.env_w;   // n = (row distribution, first row)
+    const uint32_t r = f32_to_u32_sat(rmin(uv.x * nx, nx - 1.f)), c = f32_to_u32_sat(rmin(uv.y * ny, ny - 1.f));
+    const float* t = sc.env + l.env_off;
+    const float pdf = (__ldg(&t[r]) * __ldg(&t[2ull * l.env_h + (uint64_t)r * l.env_w + c])) * nx * ny;
+    const float st = sinf(uv.y * kPi);
+    return st != 0.f ? pdf / (2.f * kPi * kPi * st) : 0.f;
+}
+// le_out_scene of every light summed into `L` with weight beta (path.rs:26-31, direct_light.rs:36-38):
+// only infinite lights answer with Some(..), the others add zero
+CP_DEV Spec add_out_scene(const DevScene& sc, V3 d, Spec L, Spec beta, bool weighted) {
+    for (uint32_t k = 0; k < sc.n_lights; ++k) {
+        const DevLight& l = sc.lights[k];
+        const Spec le = l.type == 3 ? infinite_le(sc, l, d, nullptr) : spec(0.f);
+        L = weighted ? L + beta * le : L + le;
+    }
+    return L;
+}
+
 CP_DEV LightSample light_sample_li(const DevScene& sc, const DevLight& l, const ShapePoint& point, SamplerState& st) {
     LightSample r; r.has_li = false; r.pdf = 0.f; r.wi = v3(0.f, 0.f, 0.f); r.li = spec(0.f);
     if (l.type == 0) {   // AreaLight::sample_li (area.rs:30-51)
@@ -286,6 +333,22 @@ CP_DEV LightSample light_sample_li(const DevScene& sc, const DevLight& l, const 
         r.li = spec3(l.L[0], l.L[1], l.L[2]) / length_sq(wi);
         ShapePoint to; to.p = lp; to.n = normalize(-wi); to.uv.x = 0.f; to.uv.y = 0.f; to.p_error = v3(0.f, 0.f, 0.f);
         r.wi = normalize(wi); r.has_li = true; r.pdf = 1.f; r.vis = visibility_new(point, to);
+    } else if (l.type == 3) {   // InfiniteAreaLight::sample_li (infinite_area.rs:52-72)
+        const P2 u = sampler_get_2d(sc.sampler, st);
+        const float* t = sc.env + l.env_off;
+        const uint32_t w = l.env_w, h = l.env_h;
+        uint32_t row, col; float rp, cp, xr, yr;
+        dist_sample_remap(t, t + h, h, u.x, &row, &rp, &xr);                         // sample_continuous (distribution.rs:57-60)
+        const float row_pdf = rp * (float)h, x = ((float)row + xr) / (float)h;
+        dist_sample_remap(t + 2ull * h + (uint64_t)row * w, t + 2ull * h + (uint64_t)h * w + (uint64_t)row * w, w, u.y, &col, &cp, &yr);
+        const float col_pdf = cp * (float)w, y = ((float)col + yr) / (float)w;
+        float pdf = row_pdf * col_pdf;
+        P2 uv; uv.x = x; uv.y = 1.f - y;
+        const V3 wi = normalize_phi_theta_to_spherical(uv);
+        const float sth = sinf(uv.y * kPi);
+        pdf = sth != 0.f ? pdf / (2.f * kPi * kPi * sth) : 0.f;
+        r.wi = wi; r.has_li = true; r.li = tex_eval(sc, l.tex, uv); r.pdf = pdf;
+        r.vis.o = point_offset_by_error(point, wi); r.vis.d = wi; r.vis.t_max = kFloatMax;
     } else {   // DistantLight (distant.rs:28-34), VisibilityTester::new_od
         sampler_get_2d(sc.sampler, st);
         V3 w = v3(l.v[0], l.v[1], l.v[2]);

@@ -17,10 +17,12 @@
 #pragma once
 #include "bvh_trace.cuh"
 #include "shading.cuh"
+#include "bsdf_general.cuh"
 
 namespace cpbrt {
 
-enum ShadeKind : int { SHADE_TERMINAL = 0, SHADE_MATTE = 1, SHADE_MIRROR = 2, SHADE_GLASS = 3, SHADE_KINDS = 4 };
+// SHADE_GENERAL: plastic / uber / translucent / mix, through the variable-lobe GBSDF (bsdf_general.cuh)
+enum ShadeKind : int { SHADE_TERMINAL = 0, SHADE_MATTE = 1, SHADE_MIRROR = 2, SHADE_GLASS = 3, SHADE_GENERAL = 4, SHADE_KINDS = 5 };
 
 // flag bits kept in ray_d.w
 static constexpr uint32_t kFlagSpecular = 0x100u;      // low 8 bits: bounce
@@ -73,7 +75,7 @@ struct Queues {
 static constexpr int kCntClosest0 = 0, kCntShadow = 2, kCntShade0 = 3, kCntN = 3 + SHADE_KINDS;
 static constexpr int kCntWorkClosest = kCntN, kCntWorkShadow = kCntN + 1;   // work-distribution cursors of the persistent trace kernels
 // 64-bit totals that live after the counters: rays_closest, rays_any, nan_dropped, stack_overflow
-struct Totals { unsigned long long rays_closest, rays_any, nan_dropped, overflow, elided_closest; };
+struct Totals { unsigned long long rays_closest, rays_any, nan_dropped, overflow, elided_closest, bsdf_overflow; };
 
 struct PixelArrays {
     uint2* base_index;   // Halton index of sample 0 (set_pixel)
@@ -201,7 +203,13 @@ __global__ void __launch_bounds__(128, 8) k_trace_closest(DevScene sc, PathArray
             if (it.is_mis) {
                 // BSDF-sampled ray of uniform_sample_one_light (integrator/mod.rs:54-89)
                 Spec ld = spec(0.f);
-                if (slot != 0xFFFFFFFFu) {
+                if (slot == 0xFFFFFFFFu) {
+                    // escaped: light.le_out_scene_pdf (integrator/mod.rs:81-85) -- only an infinite light
+                    // answers, and both of its values depend on the direction alone: the shading
+                    // stage already put le into mis_A and the pdf next to the shading point
+                    const float le_pdf = P.mis_p[pid].w, f_pdf = it.w_o;
+                    if (sc.lights[__float_as_uint(it.w_d)].type == 3 && le_pdf != 0.f) ld = f4_rgb(P.mis_A[pid]) * power_heuristic(f_pdf, le_pdf) / f_pdf;
+                } else {
                     const PrimRecord pr = load_prim(sc, slot);
                     const uint32_t li = __float_as_uint(it.w_d);
                     if (prim_source(pr) == (kSourceLight | li)) {   // Arc::ptr_eq(light, &intersect_light)
@@ -221,7 +229,7 @@ __global__ void __launch_bounds__(128, 8) k_trace_closest(DevScene sc, PathArray
                     const uint32_t bounce = __float_as_uint(it.w_d) & 0xFFu;
                     if (!(src & kSourceLight) && !(sc.integrator == 0 && bounce >= sc.max_depth)) {
                         const uint32_t mt = sc.materials[src].type;
-                        kind = mt == 0 ? SHADE_MATTE : (mt == 1 ? SHADE_MIRROR : SHADE_GLASS);
+                        kind = mt == 0 ? SHADE_MATTE : (mt == 1 ? SHADE_MIRROR : (mt == 2 ? SHADE_GLASS : SHADE_GENERAL));
                     }
                 }
             }
@@ -314,9 +322,12 @@ template <int KIND> struct BsdfFor;
 template <> struct BsdfFor<SHADE_MATTE> { typedef BSDF<1, 0> type; };
 template <> struct BsdfFor<SHADE_MIRROR> { typedef BSDF<0, 1> type; };
 template <> struct BsdfFor<SHADE_GLASS> { typedef BSDF<0, 2> type; };
+template <> struct BsdfFor<SHADE_GENERAL> { typedef GBSDF type; };
 
 template <int KIND>
-CP_DEV void build_bsdf(const DevScene& sc, const DevMaterial& m, const ShapePoint& sp, typename BsdfFor<KIND>::type& b) {
+CP_DEV void build_bsdf(const DevScene& sc, uint32_t mat, const ShapePoint& sp, typename BsdfFor<KIND>::type& b) {
+    if constexpr (KIND == SHADE_GENERAL) { build_general_bsdf(sc, mat, sp, b); return; }
+    const DevMaterial& m = sc.materials[mat];
     b.init(sp.n);
     if constexpr (KIND == SHADE_MATTE) {   // matte.rs:17-28
         Spec kd = tex_eval(sc, m.tex[0], sp.uv);
@@ -333,7 +344,7 @@ CP_DEV void build_bsdf(const DevScene& sc, const DevMaterial& m, const ShapePoin
     } else if constexpr (KIND == SHADE_MIRROR) {   // mirror.rs:15-23
         DeltaLobe& d = b.deltas[0]; b.n_deltas = 1;
         d.kind = DELTA_SPEC_R_NOOP; d.r = tex_eval(sc, m.tex[0], sp.uv); d.eta_a = 1.f; d.eta_b = 1.f;
-    } else {   // glass.rs:17-29
+    } else if constexpr (KIND == SHADE_GLASS) {   // glass.rs:17-29
         Spec r = tex_eval(sc, m.tex[0], sp.uv), t = tex_eval(sc, m.tex[1], sp.uv);
         float eta = tex_eval(sc, m.tex[2], sp.uv).r;
         b.n_deltas = 2;
@@ -388,11 +399,14 @@ CP_DEV void emit_direct_lighting(const DevScene& sc, const PathArrays& P, uint32
                     P.nee_bsdf[pid] = make_float4(0.f, 0.f, 0.f, 0.f);
                     flags |= kPendMis;
                     if (may_hit_light) {
-                        const Spec A = spec3(light.L[0], light.L[1], light.L[2]) * f * fabsf(dot(n, wi));
+                        Spec le = spec3(light.L[0], light.L[1], light.L[2]);
+                        float le_pdf = 0.f;
+                        if (light.type == 3) { P2 uv; le = infinite_le(sc, light, wi, &uv); le_pdf = infinite_out_scene_pdf(sc, light, uv); }
+                        const Spec A = le * f * fabsf(dot(n, wi));
                         P.mis_o[pid] = mk4(o, f_pdf);
                         P.mis_d[pid] = mk4(wi, __uint_as_float(li));
                         P.mis_A[pid] = mk4(A, 0.f);
-                        P.mis_p[pid] = mk4(sp.p, 0.f);
+                        P.mis_p[pid] = mk4(sp.p, le_pdf);
                         want_mis = true;
                     } else {
                         *elided += 1;
@@ -423,8 +437,7 @@ __global__ void k_shade_terminal(DevScene sc, PathArrays P, Queues Q) {
                 if (src & kSourceLight) { const DevLight& l = sc.lights[src & ~kSourceLight]; le = spec3(l.L[0], l.L[1], l.L[2]); }
                 L = sc.integrator == 0 ? L + beta * le : L + le;
             } else {
-                // le_out_scene of every light: None (-> 0) for area, point and distant lights
-                for (uint32_t k = 0; k < sc.n_lights; ++k) L = sc.integrator == 0 ? L + beta * spec(0.f) : L + spec(0.f);
+                L = add_out_scene(sc, f4_xyz(P.ray_d[pid]), L, beta, sc.integrator == 0);
             }
         }
         P.L[pid] = mk4(L, 0.f);
@@ -434,7 +447,7 @@ __global__ void k_shade_terminal(DevScene sc, PathArrays P, Queues Q) {
 // Resident blocks per SM: the matte kernel (NEE + MIS + continuation) spills heavily at the 64
 // registers that 8 blocks allow; 5 blocks (96 registers, 76 B of spills) measured ~5% faster,
 // 4 and 6 no better.  The short mirror / glass kernels keep 8.
-template <int KIND> struct ShadeBlocks { static constexpr int value = KIND == SHADE_MATTE ? 5 : 8; };
+template <int KIND> struct ShadeBlocks { static constexpr int value = KIND == SHADE_MATTE ? 5 : (KIND == SHADE_GENERAL ? 2 : 8); };
 template <int KIND>
 __global__ void __launch_bounds__(128, ShadeBlocks<KIND>::value) k_shade(DevScene sc, PathArrays P, Queues Q, int next, Totals* totals) {
     typedef typename BsdfFor<KIND>::type B;
@@ -463,7 +476,8 @@ __global__ void __launch_bounds__(128, ShadeBlocks<KIND>::value) k_shade(DevScen
             Ray ray; ray.o = f4_xyz(ro); ray.d = f4_xyz(rd); ray.t_max = kFloatMax;
             const PrimRecord pr = load_prim(sc, slot);
             sp = prim_shape_point(sc, slot, pr, ray, P.hit_t[pid]);
-            build_bsdf<KIND>(sc, sc.materials[prim_source(pr)], sp, bsdf);
+            build_bsdf<KIND>(sc, prim_source(pr), sp, bsdf);
+            if constexpr (KIND == SHADE_GENERAL) { if (bsdf.overflow) atomicAdd(&totals->bsdf_overflow, 1ull); }
             if (sc.integrator == 0) {
                 if (bounce == 0 || (flags & kFlagSpecular)) L = L + beta * spec(0.f);   // intersect.le() == None
                 wo = -ray.d;

@@ -5,6 +5,8 @@ ids bit-exact; first-hit shading within 1e-3 relative per pixel; full-path image
 Monte-Carlo noise band (here they are in fact compared per pixel, because oracle and GPU share
 the permutation table and the float operation order).
 """
+import re
+
 import numpy as np
 import pytest
 
@@ -326,10 +328,89 @@ def test_render_from_file_writes_png(cpbrt, tmp_path):
     assert img.shape == (48, 64, 3) and img.mean() > 5
 
 
+GENERAL_MATERIALS = {
+    "plastic": 'Material "plastic" "rgb Kd" [0.3 0.5 0.2] "rgb Ks" [0.4 0.4 0.4] "float roughness" [0.15]',
+    "plastic_rough": 'Material "plastic" "rgb Kd" [0 0 0] "rgb Ks" [0.6 0.5 0.4] "float roughness" [0.6]',
+    "uber": 'Material "uber" "rgb Kd" [0.3 0.3 0.5] "rgb Ks" [0.3 0.3 0.3] "rgb Kr" [0.2 0.2 0.2] "rgb Kt" [0.1 0.1 0.1] '
+            '"float uroughness" [0.1] "float vroughness" [0.3] "float index" [1.4] "rgb opacity" [0.8 0.8 0.8]',
+    "translucent": 'Material "translucent" "rgb Kd" [0.4 0.4 0.3] "rgb Ks" [0.3 0.3 0.3] "float roughness" [0.2] '
+                   '"rgb reflect" [0.6 0.6 0.6] "rgb transmit" [0.4 0.4 0.4]',
+    "mix": 'MakeNamedMaterial "a" "string type" "plastic" "rgb Kd" [0.5 0.2 0.2] "rgb Ks" [0.3 0.3 0.3] "float roughness" [0.1]\n'
+           'MakeNamedMaterial "b" "string type" "glass" "float index" [1.5]\n'
+           'MakeNamedMaterial "c" "string type" "mix" "string namedmaterial1" "a" "string namedmaterial2" "b" "rgb amount" [0.6 0.5 0.4]\n'
+           'MakeNamedMaterial "d" "string type" "matte" "rgb Kd" [0.2 0.4 0.6] "float sigma" [20]\n'
+           'Material "mix" "string namedmaterial1" "c" "string namedmaterial2" "d" "rgb amount" [0.7 0.7 0.7]',
+    "mix_black_amount": 'MakeNamedMaterial "a" "string type" "mirror"\n'
+                        'MakeNamedMaterial "b" "string type" "plastic" "rgb Kd" [0.5 0.5 0.2] "rgb Ks" [0.2 0.2 0.2]\n'
+                        'Material "mix" "string namedmaterial1" "a" "string namedmaterial2" "b" "rgb amount" [0 0 0]',
+}
+
+
+def _cornell_with_white_material(material_text, xres=80, yres=80, spp=4, integrator=None):
+    """cornel_box.pbrt with its white matte (floor, ceiling, back wall, both blocks) replaced."""
+    text = scene_text("cornel_box.pbrt", xres=xres, yres=yres, spp=spp, integrator=integrator)
+    parts = text.split('Material "matte"\n"spectrum Kd"')
+    assert len(parts) >= 5
+    head = 'Material "matte"\n"spectrum Kd"'.join(parts[:4])
+    rest = parts[4]
+    rest = rest[rest.index(']') + 1:]
+    return head + material_text.replace("\\n", "\n") + rest
+
+
+@pytest.mark.parametrize("name", sorted(GENERAL_MATERIALS))
+def test_general_materials(cpbrt, oracle, name):
+    """plastic / uber / translucent / mix: Trowbridge-Reitz microfacet lobes,
+    Lambertian transmission and BSDF::mix through the variable-lobe device BSDF; full paths
+    against the oracle, per pixel."""
+    scene = cpbrt.Scene.parse(_cornell_with_white_material(GENERAL_MATERIALS[name]), base_dir=SCENES)
+    assert any(scene.desc.materials[i].type > cpbrt.abi.MAT_GLASS for i in range(scene.desc.n_materials))
+    r = cpbrt.Renderer(0); r.upload(scene); r.build_bvh()
+    w = oracle.OracleWorld(scene)
+    g, gs = r.render()
+    o, _, os_ = w.render()
+    assert np.isfinite(g).all()
+    bad = (_relerr(g, o).max(axis=2) > 1e-3)
+    assert bad.mean() <= 0.02, (name, bad.mean())
+    rmse = float(np.sqrt(np.mean((g - o) ** 2)))
+    assert rmse <= 0.03 * float(o.mean()) + 1e-4, (name, rmse)
+    assert gs.nan_dropped == os_["nan_dropped"]
+    # first-hit shading of the same scene
+    g1, _ = r.render(first_hit_only=True)
+    o1, _, _ = w.render(integrator=1, max_depth=0)
+    assert (_relerr(g1, o1).max(axis=2) > 1e-3).mean() <= 2e-3
+
+
+@pytest.mark.parametrize("envmap", [False, True])
+@pytest.mark.parametrize("integrator", ["path", "directlighting"])
+def test_infinite_area_light(cpbrt, oracle, envmap, integrator):
+    """InfiniteAreaLight: Distribution2D importance sampling of the environment map,
+    le_out_scene for escaped camera / specular rays, MIS of escaped BSDF-sampled rays; with a
+    constant environment and with box-texture.png as the map, next to an area light."""
+    light = 'LightSource "infinite"' + (' "string mapname" "box-texture.png"' if envmap else '')
+    text = scene_text("cornel_box.pbrt", xres=72, yres=72, spp=4)
+    text = text.replace('WorldBegin\n', 'WorldBegin\n' + light + '\n', 1)
+    if integrator == "directlighting":
+        text = re.sub(r'Integrator "path"[^\n]*\n(\s*"integer maxdepth"[^\n]*\n)?', 'Integrator "directlighting" "integer maxdepth" [1]\n', text)
+    scene = cpbrt.Scene.parse(text, base_dir=SCENES)
+    assert any(scene.desc.lights[i].type == cpbrt.abi.LIGHT_INFINITE for i in range(scene.desc.n_lights))
+    r = cpbrt.Renderer(0); r.upload(scene); r.build_bvh()
+    w = oracle.OracleWorld(scene)
+    g, gs = r.render()
+    o, _, os_ = w.render()
+    assert np.isfinite(g).all() and o.mean() > 0.05
+    bad = (_relerr(g, o).max(axis=2) > 1e-3)
+    assert bad.mean() <= 0.02, bad.mean()
+    rmse = float(np.sqrt(np.mean((g - o) ** 2)))
+    assert rmse <= 0.03 * float(o.mean()) + 1e-4, rmse
+    assert abs(gs.rays_any - os_["rays_any"]) <= 2e-3 * os_["rays_any"]
+
+
 def test_unsupported_features_fail_loudly(cpbrt):
     head = ('Camera "perspective" "float fov" [40]\nSampler "halton" "integer pixelsamples" [1]\n'
             'Film "image" "integer xresolution" [8] "integer yresolution" [8]\nIntegrator "path"\nWorldBegin\n')
-    scene = cpbrt.Scene.parse(head + 'Material "plastic"\nShape "sphere"\nWorldEnd\n')
+    # directlighting with recursion over specular lobes is the one path the device still refuses
+    head = head.replace('Integrator "path"', 'Integrator "directlighting" "integer maxdepth" [3]')
+    scene = cpbrt.Scene.parse(head + 'LightSource "point"\nMaterial "glass"\nShape "sphere"\nWorldEnd\n')
     r = cpbrt.Renderer(0)
     with pytest.raises(cpbrt.CpbrtError) as e:
         r.upload(scene)
