@@ -62,7 +62,7 @@ struct cpbrt_ctx {
     std::string error;
 
     // host copy of what the BVH build needs
-    bool has_scene = false, has_bvh = false, has_general_materials = false;
+    bool has_scene = false, has_bvh = false, has_general_materials = false, recursive_direct = false;
     std::vector<cpbrt_primitive> primitives;
     std::vector<cpbrt_triangle> triangles;
     std::vector<float> sphere_radius;
@@ -241,14 +241,20 @@ int cpbrt_upload_scene(cpbrt_ctx* ctx, const cpbrt_scene_desc* d) {
                 return ctx->fail(CPBRT_ERR_BAD_ARG, "light %u: bad shape", i);
         }
     }
+    // directlighting recursing over delta lobes (direct_light.rs:26-31) is a ray TREE per sample: rendered
+    // by k_direct_recursive, whose explicit stack bounds the depth
+    bool recursive_direct = false;
     if (d->integrator == CPBRT_INTEGRATOR_DIRECT && d->max_depth > 1) {
-        for (uint32_t i = 0; i < d->n_materials; ++i)
-            if (d->materials[i].type != CPBRT_MAT_MATTE)
-                return ctx->fail(CPBRT_ERR_UNSUPPORTED, "directlighting with maxdepth > 1 and specular materials (recursive delta lobes) is not implemented on the device");
+        for (uint32_t i = 0; i < d->n_materials; ++i) {
+            const uint32_t t = d->materials[i].type;
+            if (t == CPBRT_MAT_MIRROR || t == CPBRT_MAT_GLASS || t == CPBRT_MAT_UBER) recursive_direct = true;
+        }
+        if (recursive_direct && d->max_depth > (uint32_t)kMaxDirectDepth)
+            return ctx->fail(CPBRT_ERR_UNSUPPORTED, "directlighting over specular materials with maxdepth > %d", kMaxDirectDepth);
     }
     if (d->max_depth > 200) return ctx->fail(CPBRT_ERR_UNSUPPORTED, "max_depth > 200");
 
-    ctx->has_scene = false; ctx->has_bvh = false; ctx->has_general_materials = has_general;
+    ctx->has_scene = false; ctx->has_bvh = false; ctx->has_general_materials = has_general; ctx->recursive_direct = recursive_direct;
     ctx->primitives.assign(d->primitives, d->primitives + d->n_primitives);
     ctx->triangles.assign(d->triangles, d->triangles + d->n_triangles);
     ctx->sphere_radius.assign(d->sphere_radius, d->sphere_radius + d->n_spheres);
@@ -685,6 +691,7 @@ int cpbrt_render(cpbrt_ctx* ctx, const cpbrt_render_params* params, float* film_
     const int g_trace = grid_for(ctx, 8), g_shade = grid_for(ctx, 8), g_pix = grid_for(ctx, 4);
     k_pixel_setup<<<g_pix, 256, 0, st>>>(S, PX); ++launches;
     const uint32_t n_iters = S.integrator == CPBRT_INTEGRATOR_PATH ? S.max_depth + 1 : 2;
+    const bool recursive = ctx->recursive_direct && !rp.first_hit_only;
     bool first_pass = true;
     for (uint32_t k0 = s_begin; k0 < s_end; k0 += spass) {
         const uint32_t Sn = std::min(spass, s_end - k0);
@@ -695,7 +702,12 @@ int cpbrt_render(cpbrt_ctx* ctx, const cpbrt_render_params* params, float* film_
         k_raygen<<<g_pix, 128, 0, st>>>(S, PX, P, Q, k0, Sn, skip); ++launches;
         span_end();
         int cur = 0;
-        for (uint32_t it = 0; it < n_iters; ++it) {
+        if (recursive) {
+            span_begin(3);
+            k_direct_recursive<<<grid_for(ctx, 8), 64, 0, st>>>(S, P, Sn * npix, T); ++launches;
+            span_end();
+        }
+        for (uint32_t it = 0; it < n_iters && !recursive; ++it) {
             span_begin(1);
             k_trace_closest<<<g_trace, 128, 0, st>>>(S, P, Q, cur, T); ++trace_launches;
             span_end();

@@ -18,6 +18,7 @@
 #include "bvh_trace.cuh"
 #include "shading.cuh"
 #include "bsdf_general.cuh"
+#include "direct_recursive.cuh"
 
 namespace cpbrt {
 
@@ -539,6 +540,47 @@ __global__ void __launch_bounds__(128, ShadeBlocks<KIND>::value) k_shade(DevScen
     // warp-reduced count of elided closest-hit queries (they still count as answered rays)
     for (int off = 16; off > 0; off >>= 1) elided += __shfl_down_sync(0xFFFFFFFFu, elided, off);
     if ((threadIdx.x & 31) == 0 && elided) atomicAdd(&totals->elided_closest, (unsigned long long)elided);
+}
+
+// directlighting with recursion over delta lobes (direct_recursive.cuh): one thread per camera
+// sample of the pass walks its ray tree depth-first; the result lands where k_film expects it.
+__global__ void __launch_bounds__(64) k_direct_recursive(DevScene sc, PathArrays P, uint32_t n_paths, Totals* totals) {
+    RayCounts rc; rc.closest = 0; rc.any = 0;
+    uint32_t overflow = 0, bsdf_overflow = 0;
+    for (uint32_t pid = blockIdx.x * blockDim.x + threadIdx.x; pid < n_paths; pid += gridDim.x * blockDim.x) {
+        SamplerState st;
+        const uint2 si = P.smp_index[pid];
+        st.index = ((uint64_t)si.y << 32) | si.x; st.dim = P.smp_dim[pid];
+        DirectFrame stack[kMaxDirectDepth];
+        Ray ray; ray.o = f4_xyz(P.ray_o[pid]); ray.d = f4_xyz(P.ray_d[pid]); ray.t_max = kFloatMax;
+        int d = -1;
+        bool visit = true;       // `ray` is waiting to become frame d + 1
+        for (;;) {
+            if (visit) {
+                ++d;
+                direct_visit(sc, ray, (uint32_t)d, st, stack[d], &rc, &overflow, &bsdf_overflow);
+                visit = false;
+            }
+            DirectFrame& f = stack[d];
+            if (f.next < f.n && d + 1 < kMaxDirectDepth) {
+                const int c = f.next++;
+                ray.o = f4_xyz(f.child_o[c]); ray.d = f4_xyz(f.child_d[c]); ray.t_max = kFloatMax;
+                visit = true;
+            } else {
+                if (d == 0) break;
+                const Spec r = f.l;
+                --d;
+                DirectFrame& p = stack[d];
+                const int c = p.next - 1;
+                p.l = p.l + r * p.child_s[c] * p.child_o[c].w;      // li_depth(..) * s * |n . wi|
+            }
+        }
+        P.L[pid] = mk4(stack[0].l, 0.f);
+    }
+    atomicAdd(&totals->rays_closest, (unsigned long long)rc.closest);
+    atomicAdd(&totals->rays_any, (unsigned long long)rc.any);
+    if (overflow) atomicAdd(&totals->overflow, 1ull);
+    if (bsdf_overflow) atomicAdd(&totals->bsdf_overflow, 1ull);
 }
 
 // End of a pass: flush the last pending direct-lighting term of every path, drop NaN samples
