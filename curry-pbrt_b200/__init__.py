@@ -183,11 +183,12 @@ class Renderer:
         return rays
 
     def render(self, sample_begin=0, sample_end=0, first_hit_only=False, samples_per_pass=0, film=None, device_film_ptr=None,
-               profile_stages=False):
-        """render() of src/render.rs:7-50.  Returns (film[H, W, 3] float32, Stats)."""
+               profile_stages=False, srgb8=False):
+        """render() of src/render.rs:7-50.  Returns (film[H, W, 3] float32, Stats); with srgb8 the
+        film is the uint8 image the reference writes to its PNG (gamma + quantise on the device)."""
         params = abi.RenderParams(sample_begin=sample_begin, sample_end=sample_end, first_hit_only=int(first_hit_only),
                                   resolve=1, samples_per_pass=samples_per_pass, film_on_device=0,
-                                  profile_stages=int(profile_stages))
+                                  profile_stages=int(profile_stages), output_srgb8=int(srgb8))
         stats = abi.Stats()
         if device_film_ptr is not None:
             params.film_on_device = 1
@@ -197,7 +198,7 @@ class Renderer:
             self._check(lib.cpbrt_render(self._ctx, C.byref(params), None, C.byref(stats)))
             return None, stats
         if film is None:
-            film = np.zeros((self.height, self.width, 3), np.float32)
+            film = np.zeros((self.height, self.width, 3), np.uint8 if srgb8 else np.float32)
         self._check(lib.cpbrt_render(self._ctx, C.byref(params), film.ctypes.data, C.byref(stats)))
         return film, stats
 

@@ -4,7 +4,7 @@ Only the declarations live here; nothing in this module computes anything.
 """
 import ctypes as C
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 N_PRIMES = 1000
 PERM_TABLE_LEN = 3682913
 NO_HIT = 0xFFFFFFFF
@@ -98,7 +98,7 @@ class BvhDump(C.Structure):
 class RenderParams(C.Structure):
     _fields_ = [("sample_begin", C.c_uint32), ("sample_end", C.c_uint32), ("first_hit_only", C.c_uint32),
                 ("resolve", C.c_uint32), ("samples_per_pass", C.c_uint32), ("film_on_device", C.c_uint32),
-                ("profile_stages", C.c_uint32)]
+                ("profile_stages", C.c_uint32), ("output_srgb8", C.c_uint32)]
 
 
 class Stats(C.Structure):

@@ -665,6 +665,7 @@ int cpbrt_render(cpbrt_ctx* ctx, const cpbrt_render_params* params, float* film_
     const bool root = ctx->rank == 0;
     if (root && !film_out) return ctx->fail(CPBRT_ERR_BAD_ARG, "film_rgb_out is null on rank 0");
     if (ctx->comm && !rp.resolve) return ctx->fail(CPBRT_ERR_BAD_ARG, "resolve = 0 is not available with a communicator attached");
+    if (rp.output_srgb8 && !rp.resolve) return ctx->fail(CPBRT_ERR_BAD_ARG, "output_srgb8 needs resolve = 1");
 
     const uint32_t npix = S.width * S.height;
     uint32_t spass = rp.samples_per_pass;
@@ -743,10 +744,10 @@ int cpbrt_render(cpbrt_ctx* ctx, const cpbrt_render_params* params, float* film_
     // film: single GPU -> resolve straight into the output.  With a communicator every GPU
     // writes its raw {sum, count} accumulator, one ncclReduce sums them on rank 0, and the
     // resolve kernel there consumes the reduced buffer directly.
-    const size_t out_floats = (size_t)npix * (rp.resolve ? 3 : 4);
+    const size_t out_bytes = rp.output_srgb8 ? (size_t)npix * 3 : (size_t)npix * (rp.resolve ? 3 : 4) * 4;
     float* d_out = film_out;
     if (!rp.film_on_device) {
-        if (ctx->d_film_out.bytes < out_floats * 4) { if (int rc = alloc_upload(ctx, ctx->d_film_out, nullptr, out_floats * 4)) return rc; }
+        if (ctx->d_film_out.bytes < out_bytes) { if (int rc = alloc_upload(ctx, ctx->d_film_out, nullptr, out_bytes)) return rc; }
         d_out = (float*)ctx->d_film_out.p;
     }
     if (ctx->comm) {
@@ -756,15 +757,21 @@ int cpbrt_render(cpbrt_ctx* ctx, const cpbrt_render_params* params, float* film_
         k_film_resolve<<<g_pix, 256, 0, st>>>(S, PX.sum, contrib, 0); ++launches;
         int nrc = g_nccl.Reduce(contrib, red, (size_t)npix * 4, kNcclFloat32, kNcclSum, 0, ctx->comm, st);
         if (nrc != 0) return ctx->fail(CPBRT_ERR_NCCL, "ncclReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "error");
-        if (root) { k_film_resolve<<<g_pix, 256, 0, st>>>(S, (const float4*)red, d_out, 2); ++launches; }
+        if (root) {
+            if (rp.output_srgb8) k_film_resolve_srgb8<<<g_pix, 256, 0, st>>>(S, (const float4*)red, (uint8_t*)d_out, 1);
+            else k_film_resolve<<<g_pix, 256, 0, st>>>(S, (const float4*)red, d_out, 2);
+            ++launches;
+        }
     } else {
-        k_film_resolve<<<g_pix, 256, 0, st>>>(S, PX.sum, d_out, rp.resolve ? 1 : 0); ++launches;
+        if (rp.output_srgb8) k_film_resolve_srgb8<<<g_pix, 256, 0, st>>>(S, PX.sum, (uint8_t*)d_out, 0);
+        else k_film_resolve<<<g_pix, 256, 0, st>>>(S, PX.sum, d_out, rp.resolve ? 1 : 0);
+        ++launches;
     }
     cudaEventRecord(e2, st);
     Totals t; memset(&t, 0, sizeof t);
     err = cudaGetLastError();
     if (err == cudaSuccess) err = cudaMemcpyAsync(&t, T, sizeof t, cudaMemcpyDeviceToHost, st);
-    if (err == cudaSuccess && root && !rp.film_on_device) err = cudaMemcpyAsync(film_out, d_out, out_floats * 4, cudaMemcpyDeviceToHost, st);
+    if (err == cudaSuccess && root && !rp.film_on_device) err = cudaMemcpyAsync(film_out, d_out, out_bytes, cudaMemcpyDeviceToHost, st);
     if (err == cudaSuccess) err = cudaStreamSynchronize(st);
     float ms_render = 0.f, ms_film = 0.f;
     if (err == cudaSuccess) { cudaEventElapsedTime(&ms_render, e0, e1); cudaEventElapsedTime(&ms_film, e1, e2); }

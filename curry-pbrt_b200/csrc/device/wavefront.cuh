@@ -620,6 +620,22 @@ __global__ void k_film_resolve(DevScene sc, const float4* __restrict__ sum, floa
     }
 }
 
+// Film output stage: mean of the kept samples, gamma_correct (math/mod.rs:51-57) and the 8-bit
+// quantisation of ImageTexture::into_file (image.rs:124, `clamp(f * 255 + 0.5, 0, 255) as u8`:
+// truncation, NaN -> 0) in one pass; three bytes per pixel leave the device instead of twelve.
+CP_DEV float gamma_correct(float f) { return f <= 0.0031308f ? 12.92f * f : 1.055f * powf(f, 1.f / 2.4f) - 0.055f; }
+CP_DEV uint8_t quantise_u8(float f) { return (uint8_t)f32_to_u32_sat(rclamp(f * 255.f + 0.5f, 0.f, 255.f)); }
+__global__ void k_film_resolve_srgb8(DevScene sc, const float4* __restrict__ sum, uint8_t* __restrict__ out, int count_is_float) {
+    const uint32_t npix = sc.width * sc.height;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x) {
+        const float4 a = sum[i];
+        const float n = count_is_float ? a.w : (float)__float_as_uint(a.w);
+        out[3ull * i] = quantise_u8(gamma_correct(0.f + a.x / n));
+        out[3ull * i + 1] = quantise_u8(gamma_correct(0.f + a.y / n));
+        out[3ull * i + 2] = quantise_u8(gamma_correct(0.f + a.z / n));
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // Batch entry points used by the parity tests and the traversal benchmark.
 // counters: [0] Parent visits, [1] primitive tests, [2] work cursor (zeroed by the caller)

@@ -108,13 +108,16 @@ extern "C" int cpbrt_render_from_file(const char* pbrt_path, int device_id) {
     rc = cpbrt_create(&ctx, device_id);
     if (rc != CPBRT_OK) { g_host_error = cpbrt_last_error(nullptr); cpbrt_scene_free(scene); return rc; }
     const cpbrt_scene_desc* d = cpbrt_scene_get_desc(scene);
-    std::vector<float> film((size_t)d->film_width * d->film_height * 3);
+    // the film comes back as the 8-bit sRGB image: gamma_correct and the quantisation run on the device
+    std::vector<uint8_t> rgb((size_t)d->film_width * d->film_height * 3);
+    cpbrt_render_params rp; memset(&rp, 0, sizeof rp); rp.resolve = 1; rp.output_srgb8 = 1;
     rc = cpbrt_upload_scene(ctx, d);
     if (rc == CPBRT_OK) rc = cpbrt_build_bvh(ctx, nullptr, nullptr);
-    if (rc == CPBRT_OK) rc = cpbrt_render(ctx, nullptr, film.data(), nullptr);
+    if (rc == CPBRT_OK) rc = cpbrt_render(ctx, &rp, (float*)rgb.data(), nullptr);
     if (rc != CPBRT_OK) g_host_error = cpbrt_last_error(ctx);
     if (rc == CPBRT_OK) {
-        rc = cpbrt_write_png(scene->data.film_filename.c_str(), film.data(), d->film_width, d->film_height);
+        std::string err;
+        if (!write_png_rgb8(scene->data.film_filename, rgb.data(), d->film_width, d->film_height, &err)) { g_host_error = err; rc = CPBRT_ERR_IO; }
         if (rc == CPBRT_OK) printf("%s\n", scene->data.film_filename.c_str());
     }
     cpbrt_destroy(ctx);

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define CPBRT_ABI_VERSION 1
+#define CPBRT_ABI_VERSION 2
 
 typedef enum cpbrt_status {
     CPBRT_OK = 0,
@@ -213,6 +213,10 @@ typedef struct cpbrt_render_params {
     uint32_t film_on_device;            /* 1 = film_rgb_out is a device pointer */
     uint32_t profile_stages;            /* 1 = bracket every stage with CUDA events and fill ms_trace / ms_shade /
                                            ms_raygen_film and the *_launches counts (a little slower) */
+    uint32_t output_srgb8;              /* 1 = film_rgb_out receives W*H*3 BYTES: gamma_correct (src/math/mod.rs:51-57) and the
+                                           `clamp(f * 255 + 0.5, 0, 255) as u8` of ImageTexture::into_file
+                                           (src/texture/image.rs:124) are applied on the device, fused with the
+                                           per-pixel mean; needs resolve = 1 */
 } cpbrt_render_params;
 
 typedef struct cpbrt_stats {

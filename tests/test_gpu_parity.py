@@ -317,6 +317,23 @@ def test_textured_matte(cpbrt, oracle):
     assert bad.mean() <= 0.01, bad.mean()
 
 
+def test_device_film_output_stage(cornell):
+    """gamma_correct + 8-bit quantisation on the device (math/mod.rs:51-57, image.rs:124)
+    against the same formulas applied to the float film on the host: equal up to one level where
+    powf differs by an ulp at a rounding boundary."""
+    _, r, _, _ = cornell
+    film, _ = r.render()
+    img, _ = r.render(srgb8=True)
+    assert img.dtype == np.uint8 and img.shape == film.shape
+    f = film.astype(np.float32)
+    with np.errstate(invalid="ignore"):
+        g = np.where(f <= np.float32(0.0031308), np.float32(12.92) * f, np.float32(1.055) * np.power(f, np.float32(1 / 2.4), dtype=np.float32) - np.float32(0.055))
+    expect = np.clip(g * np.float32(255) + np.float32(0.5), 0, 255).astype(np.uint8)
+    diff = np.abs(img.astype(np.int32) - expect.astype(np.int32))
+    assert diff.max() <= 1 and (diff > 0).mean() < 1e-3
+    assert img.max() == 255 and img.min() < 10
+
+
 def test_render_from_file_writes_png(cpbrt, tmp_path):
     import shutil
     from PIL import Image

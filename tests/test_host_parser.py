@@ -123,6 +123,43 @@ def test_image_texture_load(cpbrt):
     np.testing.assert_allclose(got, expect, rtol=2e-5, atol=1e-7)
 
 
+def test_plymesh_and_include(cpbrt, tmp_path):
+    """Binary little-endian PLY meshes (geometry/shape/plymesh.rs:14-131: float x y z nx ny nz u v
+    per vertex, `uint8 int` faces) and the `Include` directive (lex.rs:98-105): the same mesh as
+    `trianglemesh` text, as a .ply file, and through an included file gives identical triangles."""
+    import struct
+    rng = np.random.default_rng(3)
+    verts = (rng.random((40, 3)).astype(np.float32) * 2 - 1) * np.float32(0.5) + np.array([0, 0, 5], np.float32)
+    faces = rng.integers(0, 40, size=(60, 3)).astype(np.int32)
+    with open(tmp_path / "m.ply", "wb") as f:
+        f.write(b"ply\nformat binary_little_endian 1.0\nelement vertex 40\n")
+        for name in ("x", "y", "z", "nx", "ny", "nz", "u", "v"):
+            f.write(("property float %s\n" % name).encode())
+        f.write(b"element face 60\nproperty list uint8 int vertex_indices\nend_header\n")
+        for v in verts:
+            f.write(struct.pack("<8f", v[0], v[1], v[2], 0.0, 0.0, 1.0, 0.25, 0.75))
+        for t in faces:
+            f.write(struct.pack("<B3i", 3, *t))
+    head = ('Camera "perspective" "float fov" [60]\nSampler "halton" "integer pixelsamples" [1]\n'
+            'Film "image" "integer xresolution" [32] "integer yresolution" [32]\nIntegrator "path"\nWorldBegin\nMaterial "matte"\n')
+    mesh_text = 'Shape "trianglemesh" "integer indices" [%s] "point P" [%s]\n' % (
+        " ".join(str(i) for i in faces.ravel()), " ".join(repr(float(x)) for x in verts.ravel()))
+    (tmp_path / "inc.pbrt").write_text('Shape "plymesh" "string filename" "m.ply"\n')
+    a = cpbrt.Scene.parse(head + mesh_text + "WorldEnd\n", base_dir=str(tmp_path)).desc
+    b = cpbrt.Scene.parse(head + 'Shape "plymesh" "string filename" "m.ply"\nWorldEnd\n', base_dir=str(tmp_path)).desc
+    c = cpbrt.Scene.parse(head + 'Include "inc.pbrt"\nWorldEnd\n', base_dir=str(tmp_path)).desc
+    assert a.n_triangles > 0
+    ta = np.ctypeslib.as_array(a.triangles, shape=(int(a.n_triangles),)).view(np.uint8).copy()
+    for other in (b, c):
+        assert other.n_triangles == a.n_triangles and other.n_primitives == a.n_primitives
+        assert np.array_equal(np.ctypeslib.as_array(other.triangles, shape=(int(other.n_triangles),)).view(np.uint8), ta)
+    # a truncated file is an error code, not a crash
+    data = (tmp_path / "m.ply").read_bytes()
+    (tmp_path / "bad.ply").write_bytes(data[:len(data) // 2])
+    with pytest.raises(cpbrt.CpbrtError):
+        cpbrt.Scene.parse(head + 'Shape "plymesh" "string filename" "bad.ply"\nWorldEnd\n', base_dir=str(tmp_path))
+
+
 def test_imported_scene_fixture_matches_reference_file_when_available(cpbrt):
     ref = "/root/reference/scenes/cornel_box.pbrt"
     if not os.path.exists(ref):
