@@ -202,6 +202,12 @@ class Renderer:
         self._check(lib.cpbrt_render(self._ctx, C.byref(params), film.ctypes.data, C.byref(stats)))
         return film, stats
 
+    def read_bandwidth(self, nbytes, repeats=20):
+        """GB/s of a read-only streaming kernel over a device buffer (roofline denominators)."""
+        v = C.c_double()
+        self._check(lib.cpbrt_measure_read_bandwidth(self._ctx, nbytes, repeats, C.byref(v)))
+        return v.value
+
     def comm_init(self, n_ranks, rank, unique_id):
         buf = (C.c_uint8 * abi.COMM_ID_BYTES).from_buffer_copy(bytes(unique_id))
         self._check(lib.cpbrt_comm_init(self._ctx, n_ranks, rank, buf))

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -121,6 +122,18 @@ uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 
 int grid_for(const cpbrt_ctx* ctx, int blocks_per_sm) { return ctx->sm_count * blocks_per_sm; }
+
+// Warp schedule of the traversal kernels (bvh_trace.cuh): vote-scheduled node / primitive steps pay
+// off once rays spend many node steps between leaves (1M triangles, incoherent rays: 1.5x), the
+// descend-then-test loop is ahead on small trees (33-primitive Cornell box: 1.2x).
+// CPBRT_SCHEDULE=vote|loop overrides (used to measure the crossover).
+static constexpr uint32_t kVoteMinPrims = 256;    // measured: equal at 264 primitives, vote +12% at 4k, +23% at 40k, +32% at 1M (tools/schedule_crossover.py)
+bool use_vote(const cpbrt_ctx* ctx) {
+    const char* e = getenv("CPBRT_SCHEDULE");
+    if (e && strcmp(e, "vote") == 0) return true;
+    if (e && strcmp(e, "loop") == 0) return false;
+    return ctx->scene.n_prims >= kVoteMinPrims;
+}
 
 }  // namespace
 
@@ -509,8 +522,9 @@ int cpbrt_trace_closest(cpbrt_ctx* ctx, const cpbrt_ray* rays, uint64_t n, cpbrt
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0, ctx->stream);
     if (n) {
-        if (count) k_batch_closest<true><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, d_rays, n, d_hits, counters, ctx->d_totals);
-        else k_batch_closest<false><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, d_rays, n, d_hits, counters, ctx->d_totals);
+        if (count) k_batch_closest<1><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, d_rays, n, d_hits, counters, ctx->d_totals);
+        else if (use_vote(ctx)) k_batch_closest<2><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, d_rays, n, d_hits, counters, ctx->d_totals);
+        else k_batch_closest<0><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, d_rays, n, d_hits, counters, ctx->d_totals);
     }
     cudaEventRecord(e1, ctx->stream);
     cudaError_t err = cudaGetLastError();
@@ -547,8 +561,9 @@ int cpbrt_trace_any(cpbrt_ctx* ctx, const cpbrt_ray* rays, uint64_t n, uint8_t* 
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0, ctx->stream);
     if (n) {
-        if (count) k_batch_any<true><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, d_rays, n, d_out, counters, ctx->d_totals);
-        else k_batch_any<false><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, d_rays, n, d_out, counters, ctx->d_totals);
+        if (count) k_batch_any<1><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, d_rays, n, d_out, counters, ctx->d_totals);
+        else if (use_vote(ctx)) k_batch_any<2><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, d_rays, n, d_out, counters, ctx->d_totals);
+        else k_batch_any<0><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, d_rays, n, d_out, counters, ctx->d_totals);
     }
     cudaEventRecord(e1, ctx->stream);
     cudaError_t err = cudaGetLastError();
@@ -689,6 +704,7 @@ int cpbrt_render(cpbrt_ctx* ctx, const cpbrt_render_params* params, float* film_
     auto span_end = [&]() { if (prof) cudaEventRecord(spans.back().b, st); };
     cudaEventRecord(e0, st);
     uint64_t launches = 0, trace_launches = 0;
+    const bool vote = use_vote(ctx);
     const int g_trace = grid_for(ctx, 8), g_shade = grid_for(ctx, 8), g_pix = grid_for(ctx, 4);
     k_pixel_setup<<<g_pix, 256, 0, st>>>(S, PX); ++launches;
     const uint32_t n_iters = S.integrator == CPBRT_INTEGRATOR_PATH ? S.max_depth + 1 : 2;
@@ -710,10 +726,13 @@ int cpbrt_render(cpbrt_ctx* ctx, const cpbrt_render_params* params, float* film_
         }
         for (uint32_t it = 0; it < n_iters && !recursive; ++it) {
             span_begin(1);
-            k_trace_closest<<<g_trace, 128, 0, st>>>(S, P, Q, cur, T); ++trace_launches;
+            if (vote) k_trace_closest<true><<<g_trace, 128, 0, st>>>(S, P, Q, cur, T);
+            else k_trace_closest<false><<<g_trace, 128, 0, st>>>(S, P, Q, cur, T);
+            ++trace_launches;
             span_end();
             span_begin(2);
-            k_trace_shadow<<<g_trace, 128, 0, st>>>(S, P, Q, T);
+            if (vote) k_trace_shadow<true><<<g_trace, 128, 0, st>>>(S, P, Q, T);
+            else k_trace_shadow<false><<<g_trace, 128, 0, st>>>(S, P, Q, T);
             span_end();
             k_queue_reset<<<1, 32, 0, st>>>(Q, cur, 0, T);
             const int next = cur ^ 1;
@@ -796,6 +815,29 @@ int cpbrt_render(cpbrt_ctx* ctx, const cpbrt_render_params* params, float* film_
         }
     }
     return check_overflow(ctx, t);
+}
+
+int cpbrt_measure_read_bandwidth(cpbrt_ctx* ctx, uint64_t bytes, uint32_t repeats, double* gb_per_s) {
+    if (!ctx) return CPBRT_ERR_BAD_CTX;
+    if (!gb_per_s || bytes < 4096 || repeats == 0) return ctx->fail(CPBRT_ERR_BAD_ARG, "bad bandwidth probe arguments");
+    CU(cudaSetDevice(ctx->device));
+    DevBuf b, sink;
+    if (int rc = alloc_upload(ctx, b, nullptr, bytes)) return rc;
+    if (int rc = alloc_upload(ctx, sink, nullptr, 16)) { b.release(); return rc; }
+    const uint64_t n = bytes / 16;
+    const int grid = grid_for(ctx, 8);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int k = 0; k < 3; ++k) k_read_bandwidth<<<grid, 256, 0, ctx->stream>>>((const float4*)b.p, n, (float*)sink.p);   // warm (and fill L2 when it fits)
+    cudaEventRecord(e0, ctx->stream);
+    for (uint32_t k = 0; k < repeats; ++k) k_read_bandwidth<<<grid, 256, 0, ctx->stream>>>((const float4*)b.p, n, (float*)sink.p);
+    cudaEventRecord(e1, ctx->stream);
+    cudaError_t err = cudaStreamSynchronize(ctx->stream);
+    float ms = 0.f; if (err == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    b.release(); sink.release();
+    if (err != cudaSuccess) return ctx->fail(CPBRT_ERR_CUDA, "bandwidth probe: %s", cudaGetErrorString(err));
+    *gb_per_s = (double)n * 16.0 * repeats / (ms * 1e-3) / 1e9;
+    return CPBRT_OK;
 }
 
 int cpbrt_comm_unique_id(uint8_t id_out[CPBRT_COMM_ID_BYTES]) {

@@ -351,9 +351,11 @@ CP_DEV float ray_abs_margin(const DevScene& sc, const Ray& ray) {
 enum TraceMode : int { MODE_SEARCH = 0, MODE_REPLAY = 1 };
 static constexpr int kRefillLanes = 8;
 
-// Persistent-warp closest hit (two-phase).  fetch / finish as in trace_persistent.
+// Persistent-warp closest hit (two-phase), loop-scheduled: every lane descends to its next leaf,
+// then every lane tests that leaf.  The better schedule for small trees and coherent rays (a few
+// node steps per leaf, little to wait for); see closest_persistent below for the other one.
 template <class User, class Fetch, class Finish>
-__device__ void closest_persistent(const DevScene& sc, uint32_t n_items, uint32_t* work_counter, uint32_t* overflow, Fetch fetch, Finish finish) {
+__device__ void closest_persistent_loop(const DevScene& sc, uint32_t n_items, uint32_t* work_counter, uint32_t* overflow, Fetch fetch, Finish finish) {
     const int lane = threadIdx.x & 31;
     Ray ray; ray.o = v3(0.f, 0.f, 0.f); ray.d = v3(0.f, 0.f, 1.f); ray.t_max = 0.f;
     RayBoxSetup bs = ray_box_setup(ray);
@@ -494,11 +496,11 @@ __device__ void closest_persistent(const DevScene& sc, uint32_t n_items, uint32_
     }
 }
 
-// Persistent-warp any hit.  The result is a pure existence test against a constant t_max, so
+// Persistent-warp any hit, loop-scheduled.  The result is a pure existence test against a constant t_max, so
 // the visiting order is free: nearer child first, reference predicate (required for parity)
 // plus the tight interval (prunes what the reference's loose test lets through).
 template <class User, class Fetch, class Finish>
-__device__ void any_persistent(const DevScene& sc, uint32_t n_items, uint32_t* work_counter, uint32_t* overflow, Fetch fetch, Finish finish) {
+__device__ void any_persistent_loop(const DevScene& sc, uint32_t n_items, uint32_t* work_counter, uint32_t* overflow, Fetch fetch, Finish finish) {
     const int lane = threadIdx.x & 31;
     Ray ray; ray.o = v3(0.f, 0.f, 0.f); ray.d = v3(0.f, 0.f, 1.f); ray.t_max = 0.f;
     RayBoxSetup bs = ray_box_setup(ray);
@@ -569,6 +571,247 @@ __device__ void any_persistent(const DevScene& sc, uint32_t n_items, uint32_t* w
         if (__any_sync(0xFFFFFFFFu, finished)) {
             finish(finished, user, ray, hit ? 0u : 0xFFFFFFFFu, ray.t_max);
             if (finished) have_ray = false;
+        }
+    }
+}
+
+// Persistent-warp closest hit (two-phase), vote-scheduled.  fetch / finish as in trace_persistent.
+//
+// A ray alternates between node steps (expand one Parent) and primitive steps (test one primitive
+// of a leaf).  Running "all node steps until every lane has a leaf, then the leaves" leaves most
+// of the warp idle on incoherent rays: the lanes reach their next leaf after very different
+// numbers of node steps (5 of 32 lanes active on random rays through a million triangles).  Here
+// every iteration the warp VOTES: the kind of step more lanes are waiting for is executed, for
+// exactly those lanes, and the others simply wait for their kind's turn.  Finished rays are
+// written back, and their lanes refilled, in groups of kRefillLanes.
+//   lane state   EMPTY (have_ray = false) | ACTIVE (task is a Parent or a leaf cursor) | DONE (task = kDone)
+//   leaf cursor  x = kLeafBit | next slot, y = primitives left
+template <class User, class Fetch, class Finish>
+__device__ void closest_persistent(const DevScene& sc, uint32_t n_items, uint32_t* work_counter, uint32_t* overflow, Fetch fetch, Finish finish) {
+    const int lane = threadIdx.x & 31;
+    Ray ray; ray.o = v3(0.f, 0.f, 0.f); ray.d = v3(0.f, 0.f, 1.f); ray.t_max = 0.f;
+    RayBoxSetup bs = ray_box_setup(ray);
+    TriRaySetup ts = tri_ray_setup(ray.d);
+    TaskStack stack;
+    uint2 task = make_uint2(kDone, 0u);
+    User user = User();
+    bool have_ray = false, exhausted = false;
+    int mode = MODE_SEARCH;
+    float t_init = 0.f, abs_m = 0.f;
+    // search state: best / second-best accepted distance; replay state: ray.t_max and `best`
+    uint32_t best = 0xFFFFFFFFu;
+    float t_best = 0.f, t_second = 0.f, t_cut = 0.f, t_lo = 0.f;
+
+    auto root_task = [&](bool replay) -> uint2 {
+        if (sc.n_prims == 0) return make_uint2(kDone, 0u);
+        if (sc.root_cnt > 0) return make_uint2(sc.root_ref | kLeafBit, sc.root_cnt);
+        bool rok; float rtmin, en, ex;
+        slab_tests(bs, sc.root_box[0], sc.root_box[1], sc.root_box[2], sc.root_box[3], sc.root_box[4], sc.root_box[5], &rok, &rtmin, &en, &ex);
+        if (!rok) return make_uint2(kDone, 0u);
+        if (replay) return make_uint2(sc.root_ref, __float_as_uint(rtmin));          // t_min < t_max checked when the task is taken
+        if (!(rtmin < t_init)) return make_uint2(kDone, 0u);
+        return make_uint2(sc.root_ref, __float_as_uint(en));
+    };
+
+    for (;;) {
+        // ---- a ray whose search ended with a rival inside the margin starts its replay ----------
+        if (have_ray && task.x == kDone && mode == MODE_SEARCH && best != 0xFFFFFFFFu && !(t_second > t_cut)) {
+            mode = MODE_REPLAY;
+            t_lo = t_best - hit_margin(t_best, abs_m);
+            ray.t_max = fminf(t_init, t_cut);      // t_cut stays t_best + margin: upper edge of the replay window
+            best = 0xFFFFFFFFu; stack.n = 0;
+            task = root_task(true);
+        }
+        const bool want_node = have_ray && !(task.x & kLeafBit);
+        const bool want_prim = have_ray && (task.x & kLeafBit) && task.x != kDone;
+        const unsigned m_node = __ballot_sync(0xFFFFFFFFu, want_node), m_prim = __ballot_sync(0xFFFFFFFFu, want_prim);
+        const unsigned m_active = m_node | m_prim;
+        // ---- write back finished rays and refill, in groups ---------------------------------------
+        if (__popc(~m_active) >= kRefillLanes || m_active == 0u) {
+            const bool finished = have_ray && task.x == kDone;
+            if (__any_sync(0xFFFFFFFFu, finished)) {
+                if (finished && mode == MODE_SEARCH) ray.t_max = best != 0xFFFFFFFFu ? t_best : t_init;
+                finish(finished, user, ray, best, ray.t_max);
+                if (finished) have_ray = false;
+            }
+            if (!exhausted) {
+                const unsigned idle = ~m_active;
+                const int leader = __ffs(idle) - 1;
+                uint32_t base = 0;
+                if (lane == leader) base = atomicAdd(work_counter, (uint32_t)__popc(idle));
+                base = __shfl_sync(0xFFFFFFFFu, base, leader);
+                if (base >= n_items) exhausted = true;
+                if (!have_ray) {
+                    const uint32_t i = base + __popc(idle & ((1u << lane) - 1u));
+                    if (i < n_items) {
+                        fetch(i, &ray, &user);
+                        have_ray = true; stack.n = 0; mode = MODE_SEARCH;
+                        bs = ray_box_setup(ray); ts = tri_ray_setup(ray.d);
+                        t_init = ray.t_max; abs_m = ray_abs_margin(sc, ray);
+                        best = 0xFFFFFFFFu; t_best = t_init; t_second = kFloatMax; t_cut = t_init;
+                        task = root_task(false);
+                    }
+                }
+                continue;      // vote again with the new rays
+            }
+            if (m_active == 0u) break;      // nothing left anywhere in this warp
+        }
+
+        if (__popc(m_node) >= __popc(m_prim)) {
+            // ---- node step ------------------------------------------------------------------------
+            if (want_node) {
+                const float key = __uint_as_float(task.y);
+                if (mode == MODE_SEARCH ? (key > t_cut) : !(key < ray.t_max)) { task = stack.pop(); }
+                else {
+                    const ChildTests c = expand_node2(sc, task.x, bs);
+                    if (mode == MODE_SEARCH) {
+                        // near-first; a child is entered if the reference could reach it (its own
+                        // predicate, against the initial t_max) and the tight interval meets [0, t_cut]
+                        bool go[2]; float key2[2];
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) {
+                            const float sl = slab_slack(c.entry[k], c.exit[k], abs_m);
+                            const bool tight = !(c.entry[k] > c.exit[k] + sl) && !(c.exit[k] + sl < 0.f) && !(c.entry[k] - sl > t_cut);
+                            // a Leaf has no box in the reference (always entered there); its stored
+                            // box only prunes primitives that cannot be hit within [0, t_cut]
+                            go[k] = tight && (c.cnt[k] > 0 || (c.ref_ok[k] && c.ref_tmin[k] < t_init));
+                            key2[k] = c.entry[k] - sl;
+                        }
+                        // both candidate tasks are formed with straight-line selects (no indexed access
+                        // into the small per-child arrays, which would push them to local memory)
+                        const uint2 t0 = c.cnt[0] > 0 ? make_uint2(c.ref[0] | kLeafBit, c.cnt[0]) : make_uint2(c.ref[0], __float_as_uint(key2[0]));
+                        const uint2 t1 = c.cnt[1] > 0 ? make_uint2(c.ref[1] | kLeafBit, c.cnt[1]) : make_uint2(c.ref[1], __float_as_uint(key2[1]));
+                        const bool near0 = go[0] && (!go[1] || key2[0] <= key2[1]);
+                        const bool go_near = near0 ? go[0] : go[1], go_far = near0 ? go[1] : go[0];
+                        const uint2 t_near = near0 ? t0 : t1, t_far = near0 ? t1 : t0;
+                        if (go_far) stack.push(t_far, overflow);
+                        task = go_near ? t_near : stack.pop();
+                    } else {
+                        // reference order and reference box rule, skipping boxes that cannot hold a
+                        // hit inside the replay window
+                        bool go[2];
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) {
+                            const float sl = slab_slack(c.entry[k], c.exit[k], abs_m);
+                            const bool window = !(c.exit[k] + sl < t_lo) && !(c.entry[k] - sl > t_cut);
+                            go[k] = window && (c.cnt[k] > 0 || c.ref_ok[k]);
+                        }
+                        const bool positive = c.axis == 0 ? bs.pos[0] : (c.axis == 1 ? bs.pos[1] : bs.pos[2]);
+                        const uint2 t0 = c.cnt[0] > 0 ? make_uint2(c.ref[0] | kLeafBit, c.cnt[0]) : make_uint2(c.ref[0], __float_as_uint(c.ref_tmin[0]));
+                        const uint2 t1 = c.cnt[1] > 0 ? make_uint2(c.ref[1] | kLeafBit, c.cnt[1]) : make_uint2(c.ref[1], __float_as_uint(c.ref_tmin[1]));
+                        // positive direction along the split axis -> right child (1) first
+                        const bool go_first = positive ? go[1] : go[0], go_second = positive ? go[0] : go[1];
+                        const uint2 t_first = positive ? t1 : t0, t_second_task = positive ? t0 : t1;
+                        if (go_second) stack.push(t_second_task, overflow);
+                        task = go_first ? t_first : stack.pop();
+                    }
+                }
+            }
+        } else {
+            // ---- primitive step: one primitive of the lane's leaf ----------------------------------
+            if (want_prim) {
+                const uint32_t s = task.x & ~kLeafBit;
+                const PrimRecord pr = load_prim(sc, s);
+                float t;
+                if (mode == MODE_SEARCH) {
+                    Ray probe = ray; probe.t_max = fminf(t_init, t_cut);
+                    if (prim_intersect_t(sc, pr, probe, ts, &t)) {
+                        if (best == 0xFFFFFFFFu || t < t_best) { if (best != 0xFFFFFFFFu) t_second = fminf(t_second, t_best); t_best = t; best = s; }
+                        else t_second = fminf(t_second, t);
+                        t_cut = t_best + hit_margin(t_best, abs_m);
+                    }
+                } else {
+                    if (prim_intersect_t(sc, pr, ray, ts, &t)) { ray.t_max = t; best = s; }
+                }
+                task.x += 1u; task.y -= 1u;
+                if (task.y == 0u) task = stack.pop();
+            }
+        }
+    }
+}
+
+// Persistent-warp any hit, vote-scheduled like closest_persistent.  The result is a pure
+// existence test against a constant t_max, so the visiting order is free: nearer child first,
+// reference predicate (required for parity) plus the tight interval (prunes what the reference's
+// loose test lets through).
+template <class User, class Fetch, class Finish>
+__device__ void any_persistent(const DevScene& sc, uint32_t n_items, uint32_t* work_counter, uint32_t* overflow, Fetch fetch, Finish finish) {
+    const int lane = threadIdx.x & 31;
+    Ray ray; ray.o = v3(0.f, 0.f, 0.f); ray.d = v3(0.f, 0.f, 1.f); ray.t_max = 0.f;
+    RayBoxSetup bs = ray_box_setup(ray);
+    TriRaySetup ts = tri_ray_setup(ray.d);
+    TaskStack stack;
+    uint2 task = make_uint2(kDone, 0u);
+    User user = User();
+    bool have_ray = false, exhausted = false, hit = false;
+    float abs_m = 0.f;
+    for (;;) {
+        const bool want_node = have_ray && !(task.x & kLeafBit);
+        const bool want_prim = have_ray && (task.x & kLeafBit) && task.x != kDone;
+        const unsigned m_node = __ballot_sync(0xFFFFFFFFu, want_node), m_prim = __ballot_sync(0xFFFFFFFFu, want_prim);
+        const unsigned m_active = m_node | m_prim;
+        if (__popc(~m_active) >= kRefillLanes || m_active == 0u) {
+            const bool finished = have_ray && task.x == kDone;
+            if (__any_sync(0xFFFFFFFFu, finished)) {
+                finish(finished, user, ray, hit ? 0u : 0xFFFFFFFFu, ray.t_max);
+                if (finished) have_ray = false;
+            }
+            if (!exhausted) {
+                const unsigned idle = ~m_active;
+                const int leader = __ffs(idle) - 1;
+                uint32_t base = 0;
+                if (lane == leader) base = atomicAdd(work_counter, (uint32_t)__popc(idle));
+                base = __shfl_sync(0xFFFFFFFFu, base, leader);
+                if (base >= n_items) exhausted = true;
+                if (!have_ray) {
+                    const uint32_t i = base + __popc(idle & ((1u << lane) - 1u));
+                    if (i < n_items) {
+                        fetch(i, &ray, &user);
+                        have_ray = true; stack.n = 0; hit = false;
+                        bs = ray_box_setup(ray); ts = tri_ray_setup(ray.d);
+                        abs_m = ray_abs_margin(sc, ray);
+                        if (sc.n_prims == 0) task = make_uint2(kDone, 0u);
+                        else if (sc.root_cnt > 0) task = make_uint2(sc.root_ref | kLeafBit, sc.root_cnt);
+                        else {
+                            bool rok; float rtmin, en, ex;
+                            slab_tests(bs, sc.root_box[0], sc.root_box[1], sc.root_box[2], sc.root_box[3], sc.root_box[4], sc.root_box[5], &rok, &rtmin, &en, &ex);
+                            task = (rok && rtmin < ray.t_max) ? make_uint2(sc.root_ref, 0u) : make_uint2(kDone, 0u);
+                        }
+                    }
+                }
+                continue;
+            }
+            if (m_active == 0u) break;
+        }
+        if (__popc(m_node) >= __popc(m_prim)) {
+            if (want_node) {
+                const ChildTests c = expand_node2(sc, task.x, bs);
+                bool go[2]; float key[2];
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const float sl = slab_slack(c.entry[k], c.exit[k], abs_m);
+                    const bool tight = !(c.entry[k] > c.exit[k] + sl) && !(c.exit[k] + sl < 0.f) && !(c.entry[k] - sl > ray.t_max);
+                    go[k] = tight && (c.cnt[k] > 0 || (c.ref_ok[k] && c.ref_tmin[k] < ray.t_max));
+                    key[k] = c.entry[k];
+                }
+                const uint2 t0 = c.cnt[0] > 0 ? make_uint2(c.ref[0] | kLeafBit, c.cnt[0]) : make_uint2(c.ref[0], 0u);
+                const uint2 t1 = c.cnt[1] > 0 ? make_uint2(c.ref[1] | kLeafBit, c.cnt[1]) : make_uint2(c.ref[1], 0u);
+                const bool near0 = go[0] && (!go[1] || key[0] <= key[1]);
+                const bool go_near = near0 ? go[0] : go[1], go_far = near0 ? go[1] : go[0];
+                const uint2 t_near = near0 ? t0 : t1, t_far = near0 ? t1 : t0;
+                if (go_far) stack.push(t_far, overflow);
+                task = go_near ? t_near : stack.pop();
+            }
+        } else {
+            if (want_prim) {
+                const PrimRecord pr = load_prim(sc, task.x & ~kLeafBit);
+                float t;
+                if (prim_intersect_t(sc, pr, ray, ts, &t)) { hit = true; task = make_uint2(kDone, 0u); }
+                else {
+                    task.x += 1u; task.y -= 1u;
+                    if (task.y == 0u) task = stack.pop();
+                }
+            }
         }
     }
 }

@@ -185,6 +185,9 @@ __global__ void k_raygen(DevScene sc, PixelArrays px, PathArrays P, Queues Q, ui
 // entries one by one (bvh_trace.cuh, trace_persistent).
 struct ClosestItem { uint32_t pid; uint32_t is_mis; float w_o, w_d; };   // w_* = the .w of the ray's two float4
 
+// VOTE selects the warp schedule of the traversal (bvh_trace.cuh): vote-scheduled steps for big
+// trees, the descend-then-test loop for small ones.
+template <bool VOTE>
 __global__ void __launch_bounds__(128, 8) k_trace_closest(DevScene sc, PathArrays P, Queues Q, int cur, Totals* totals) {
     const uint32_t n = Q.counts[kCntClosest0 + cur];
     uint32_t overflow = 0;
@@ -237,7 +240,8 @@ __global__ void __launch_bounds__(128, 8) k_trace_closest(DevScene sc, PathArray
         }
         if (kind >= 0) P.shade_kind[pid] = (uint8_t)kind;
     };
-    closest_persistent<ClosestItem>(sc, n, &Q.counts[kCntWorkClosest], &overflow, fetch, finish);
+    if (VOTE) closest_persistent<ClosestItem>(sc, n, &Q.counts[kCntWorkClosest], &overflow, fetch, finish);
+    else closest_persistent_loop<ClosestItem>(sc, n, &Q.counts[kCntWorkClosest], &overflow, fetch, finish);
     if (overflow) atomicAdd(&totals->overflow, 1ull);
 }
 
@@ -286,6 +290,7 @@ __global__ void k_classify(PathArrays P, Queues Q, uint32_t n_paths) {
 }
 
 // Shadow-ray stage: VisibilityTester::unoccluded (light/mod.rs:112-114).
+template <bool VOTE>
 __global__ void __launch_bounds__(128, 8) k_trace_shadow(DevScene sc, PathArrays P, Queues Q, Totals* totals) {
     const uint32_t n = Q.counts[kCntShadow];
     uint32_t overflow = 0;
@@ -297,7 +302,8 @@ __global__ void __launch_bounds__(128, 8) k_trace_shadow(DevScene sc, PathArrays
     auto finish = [&](bool done, uint32_t pid, const Ray&, uint32_t slot, float) {
         if (done && slot != 0xFFFFFFFFu) P.nee_light[pid] = make_float4(0.f, 0.f, 0.f, 0.f);
     };
-    any_persistent<uint32_t>(sc, n, &Q.counts[kCntWorkShadow], &overflow, fetch, finish);
+    if (VOTE) any_persistent<uint32_t>(sc, n, &Q.counts[kCntWorkShadow], &overflow, fetch, finish);
+    else any_persistent_loop<uint32_t>(sc, n, &Q.counts[kCntWorkShadow], &overflow, fetch, finish);
     if (overflow) atomicAdd(&totals->overflow, 1ull);
 }
 
@@ -639,7 +645,9 @@ __global__ void k_film_resolve_srgb8(DevScene sc, const float4* __restrict__ sum
 // ------------------------------------------------------------------------------------------
 // Batch entry points used by the parity tests and the traversal benchmark.
 // counters: [0] Parent visits, [1] primitive tests, [2] work cursor (zeroed by the caller)
-template <bool COUNT>
+// MODE: 0 = two-phase traversal, loop-scheduled; 1 = reference-order traversal with visit counters;
+//       2 = two-phase traversal, vote-scheduled
+template <int MODE>
 __global__ void __launch_bounds__(128) k_batch_closest(DevScene sc, const float4* __restrict__ rays, uint64_t n, float4* __restrict__ hits,
                                                        unsigned long long* counters, Totals* totals) {
     uint32_t overflow = 0;
@@ -661,12 +669,13 @@ __global__ void __launch_bounds__(128) k_batch_closest(DevScene sc, const float4
     };
     // COUNT = the reference-order traversal with its visit counters (algorithmic work of SURVEY 8d);
     // otherwise the two-phase traversal the renderer uses.  Both must return the same hits.
-    if (COUNT) trace_persistent<false, true, uint32_t>(sc, (uint32_t)n, (uint32_t*)&counters[2], &ts, &overflow, fetch, finish);
-    else closest_persistent<uint32_t>(sc, (uint32_t)n, (uint32_t*)&counters[2], &overflow, fetch, finish);
-    if (COUNT) { atomicAdd(&counters[0], (unsigned long long)ts.parent_visits); atomicAdd(&counters[1], (unsigned long long)ts.prim_tests); }
+    if (MODE == 1) trace_persistent<false, true, uint32_t>(sc, (uint32_t)n, (uint32_t*)&counters[2], &ts, &overflow, fetch, finish);
+    else if (MODE == 2) closest_persistent<uint32_t>(sc, (uint32_t)n, (uint32_t*)&counters[2], &overflow, fetch, finish);
+    else closest_persistent_loop<uint32_t>(sc, (uint32_t)n, (uint32_t*)&counters[2], &overflow, fetch, finish);
+    if (MODE == 1) { atomicAdd(&counters[0], (unsigned long long)ts.parent_visits); atomicAdd(&counters[1], (unsigned long long)ts.prim_tests); }
     if (overflow) atomicAdd(&totals->overflow, 1ull);
 }
-template <bool COUNT>
+template <int MODE>
 __global__ void __launch_bounds__(128) k_batch_any(DevScene sc, const float4* __restrict__ rays, uint64_t n, uint8_t* __restrict__ out,
                                                    unsigned long long* counters, Totals* totals) {
     uint32_t overflow = 0;
@@ -679,9 +688,10 @@ __global__ void __launch_bounds__(128) k_batch_any(DevScene sc, const float4* __
     auto finish = [&](bool done, uint32_t idx, const Ray&, uint32_t slot, float) {
         if (done) out[idx] = slot != 0xFFFFFFFFu ? 1 : 0;
     };
-    if (COUNT) trace_persistent<true, true, uint32_t>(sc, (uint32_t)n, (uint32_t*)&counters[2], &ts, &overflow, fetch, finish);
-    else any_persistent<uint32_t>(sc, (uint32_t)n, (uint32_t*)&counters[2], &overflow, fetch, finish);
-    if (COUNT) { atomicAdd(&counters[0], (unsigned long long)ts.parent_visits); atomicAdd(&counters[1], (unsigned long long)ts.prim_tests); }
+    if (MODE == 1) trace_persistent<true, true, uint32_t>(sc, (uint32_t)n, (uint32_t*)&counters[2], &ts, &overflow, fetch, finish);
+    else if (MODE == 2) any_persistent<uint32_t>(sc, (uint32_t)n, (uint32_t*)&counters[2], &overflow, fetch, finish);
+    else any_persistent_loop<uint32_t>(sc, (uint32_t)n, (uint32_t*)&counters[2], &overflow, fetch, finish);
+    if (MODE == 1) { atomicAdd(&counters[0], (unsigned long long)ts.parent_visits); atomicAdd(&counters[1], (unsigned long long)ts.prim_tests); }
     if (overflow) atomicAdd(&totals->overflow, 1ull);
 }
 
@@ -712,6 +722,21 @@ __global__ void k_batch_camera_rays(DevScene sc, uint32_t sample, float4* __rest
         rays[2ull * i] = mk4(r.o, r.t_max);
         rays[2ull * i + 1] = mk4(r.d, 0.f);
     }
+}
+
+// Read-only streaming kernel for the roofline denominators: every thread sums 16-byte loads over
+// `n` float4 (grid-stride); with a 64 MB buffer read repeatedly this measures L2 read bandwidth,
+// with a buffer far larger than L2 the HBM read bandwidth.
+__global__ void __launch_bounds__(256) k_read_bandwidth(const float4* __restrict__ buf, uint64_t n, float* __restrict__ sink) {
+    float acc = 0.f;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n; i += 4 * stride) {
+        const float4 a = __ldg(&buf[i]), b = __ldg(&buf[i + stride]), c = __ldg(&buf[i + 2 * stride]), d = __ldg(&buf[i + 3 * stride]);
+        acc += (a.x + a.w) + (b.y + b.w) + (c.z + c.w) + (d.x + d.w);
+    }
+    for (; i < n; i += stride) { const float4 a = __ldg(&buf[i]); acc += a.x + a.w; }
+    if (acc == 123456.789f) *sink = acc;      // never true for the zero-filled buffer: keeps the loads alive
 }
 
 }  // namespace cpbrt

@@ -283,6 +283,11 @@ int cpbrt_camera_rays(cpbrt_ctx* ctx, uint32_t sample, cpbrt_ray* rays_out, int 
 int cpbrt_render(cpbrt_ctx* ctx, const cpbrt_render_params* params, float* film_rgb_out,
                  cpbrt_stats* stats_out);
 
+/* Roofline denominators: read bandwidth of a zero-filled device buffer of `bytes` bytes
+ * streamed `repeats` times by a read-only kernel (16-byte loads).  64 MB stays resident in the 126 MB
+ * L2 and gives the L2 read peak; a multi-GB buffer gives the HBM read peak.  No reference equivalent. */
+int cpbrt_measure_read_bandwidth(cpbrt_ctx* ctx, uint64_t bytes, uint32_t repeats, double* gb_per_s);
+
 /* Multi-GPU: one NCCL communicator over the per-GPU contexts.  id_bytes = ncclUniqueId (128 B). */
 #define CPBRT_COMM_ID_BYTES 128
 int cpbrt_comm_unique_id(uint8_t id_bytes_out[CPBRT_COMM_ID_BYTES]);

@@ -213,6 +213,32 @@ def test_edge_grazing_rays(cornell):
         assert np.array_equal(r.trace_any(sh), w.trace_any(sh))
 
 
+def test_both_warp_schedules_agree(cornell, mesh, monkeypatch):
+    """The traversal kernels exist in two warp schedules (bvh_trace.cuh: descend-then-test loop for
+    small trees, vote-scheduled steps for big ones, picked by primitive count).  Forcing either one
+    (CPBRT_SCHEDULE) must not change a single hit, distance bit, shadow result or film value."""
+    for scene, r, w, _ in (cornell, mesh):
+        rays = [w.camera_rays(0), lcg_rays(1 << 16, (-50, -50, -50), (610, 600, 610), seed=31)]
+        if r is cornell[1]:
+            rays += [edge_case_rays(), edge_grazing_rays(scene)]
+        results = []
+        for sched in ("loop", "vote"):
+            monkeypatch.setenv("CPBRT_SCHEDULE", sched)
+            res = []
+            for b in rays:
+                h = r.trace_closest(b)
+                sh = b.copy(); sh[:, 3] = np.float32(0.9)
+                res += [h["prim"].copy(), h["t"].view(np.uint32).copy(), r.trace_any(sh).copy()]
+            film, _ = r.render()
+            res.append(film.view(np.uint32).copy())
+            results.append(res)
+        monkeypatch.delenv("CPBRT_SCHEDULE", raising=False)
+        for a, b in zip(*results):
+            assert np.array_equal(a, b)
+        o = w.trace_closest(rays[1])
+        assert np.array_equal(results[1][3], o["prim"])
+
+
 def test_empty_and_ragged_batches(cornell):
     _, r, w, _ = cornell
     assert len(r.trace_closest(np.zeros((0, 8), np.float32))["prim"]) == 0

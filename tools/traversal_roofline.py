@@ -41,6 +41,10 @@ def main():
     r = cpbrt.Renderer(0)
     t0 = time.time(); r.upload(scene); r.build_bvh(); build_s = time.time() - t0
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+    # measured read peaks of this GPU: 64 MB stays in the 126 MB L2, 4 GB streams from HBM
+    l2_gbs = r.read_bandwidth(64 << 20, 50)
+    hbm_read_gbs = r.read_bandwidth(4 << 30, 5)
+    print(json.dumps(dict(probe="read_bandwidth", l2_64MB_gbs=l2_gbs, hbm_4GB_gbs=hbm_read_gbs, hbm_copy_gbs_measured_peaks=peak)))
     world = None
     if not args.no_oracle:
         import oracle_api
@@ -86,7 +90,9 @@ def main():
             per_ray = per_ray_dev
             out.update(algorithmic_bytes_per_ray=per_ray, note="bytes from the device counters (oracle skipped)")
         achieved = per_ray * n / (np.mean(ms) * 1e-3) / 1e9
-        out.update(roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak))
+        out.update(roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak),
+                   roofline_l2=dict(bound="l2", achieved=achieved, peak=l2_gbs, unit="GB/s", frac=achieved / l2_gbs,
+                                    note="nodes + triangles of C4 (94 MB) fit the L2; peak = read-only kernel over 64 MB"))
         print(json.dumps(out))
         sys.stdout.flush()
 
