@@ -76,6 +76,15 @@ CP_DEV float sampler_get_sample(const DevSampler& S, SamplerState& st) {
     ++st.dim;
     return r;
 }
+// get_2d for dimensions 0 and 1 given the two quotients index / scale[0] and index / scale[1]
+// (get_sample halton.rs:125-128 + the get_1d clamp): what the film-point jitter of every camera
+// sample draws (render.rs:30)
+CP_DEV P2 halton_film_sample(uint64_t q0, uint64_t q1) {
+    P2 p;
+    const float a = radical_inverse(q0, 2u), b = radical_inverse(q1, 3u);
+    p.x = a >= 1.f ? 1.f : a; p.y = b >= 1.f ? 1.f : b;
+    return p;
+}
 // get_1d (sampler/mod.rs:10-17): the clamp constant 0.9999999999999 is 1.0 in f32
 CP_DEV float sampler_get_1d(const DevSampler& S, SamplerState& st) { float r = sampler_get_sample(S, st); return r >= 1.f ? 1.f : r; }
 CP_DEV P2 sampler_get_2d(const DevSampler& S, SamplerState& st) { P2 p; p.x = sampler_get_1d(S, st); p.y = sampler_get_1d(S, st); return p; }

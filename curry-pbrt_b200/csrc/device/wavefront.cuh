@@ -154,14 +154,19 @@ __global__ void k_raygen(DevScene sc, PixelArrays px, PathArrays P, Queues Q, ui
         const uint2 bi = px.base_index[i];
         const uint64_t base = ((uint64_t)bi.y << 32) | bi.x;
         float2 fp = px.film_point[i];
+        // Dimensions 0 and 1 of sample k are radical inverses of index_k / scale[0] and index_k / scale[1]
+        // with index_k = base + k * scale[0] * scale[1] (halton.rs:124-129): both quotients are linear
+        // in k, so the two 64-bit divisions are done once per pixel instead of once per sample.
+        const uint64_t q0_base = base >> sc.sampler.exp[0], q1_base = base / sc.sampler.scale[1];
         for (uint32_t s = 0; s < skip; ++s) {
-            SamplerState st; st.index = base + (uint64_t)(k0 - skip + s) * sc.sampler.stride; st.dim = 0;
-            P2 u = sampler_get_2d(sc.sampler, st);
+            const uint64_t k = k0 - skip + s;
+            P2 u = halton_film_sample(q0_base + k * sc.sampler.scale[1], q1_base + k * sc.sampler.scale[0]);
             fp.x += u.x - 0.5f; fp.y += u.y - 0.5f;
         }
         for (uint32_t s = 0; s < S; ++s) {
-            SamplerState st; st.index = base + (uint64_t)(k0 + s) * sc.sampler.stride; st.dim = 0;
-            P2 u = sampler_get_2d(sc.sampler, st);
+            const uint64_t k = k0 + s;
+            SamplerState st; st.index = base + k * sc.sampler.stride; st.dim = 2;
+            P2 u = halton_film_sample(q0_base + k * sc.sampler.scale[1], q1_base + k * sc.sampler.scale[0]);
             fp.x += u.x - 0.5f; fp.y += u.y - 0.5f;           // render.rs:30-31
             P2 film; film.x = fp.x; film.y = fp.y;
             Ray r = camera_generate_ray(sc, film, st);
