@@ -202,6 +202,10 @@ class Renderer:
         self._check(lib.cpbrt_render(self._ctx, C.byref(params), film.ctypes.data, C.byref(stats)))
         return film, stats
 
+    def bvh_gpu_levels(self):
+        """Levels of the last cpbrt_build_bvh that ran on the device (0: pure host build)."""
+        return int(lib.cpbrt_bvh_gpu_levels(self._ctx))
+
     def read_bandwidth(self, nbytes, repeats=20):
         """GB/s of a read-only streaming kernel over a device buffer (roofline denominators)."""
         v = C.c_double()

@@ -23,7 +23,7 @@ NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a",
 
 HOST_SOURCES = ["host/parser.cpp", "host/scene_build.cpp", "host/halton_tables.cpp", "host/host_api.cpp",
                 "host/image_io.cpp", "bvh_build.cpp"]
-CUDA_SOURCES = ["cpbrt_api.cu"]
+CUDA_SOURCES = ["cpbrt_api.cu", "bvh_build_gpu.cu"]
 
 
 def _deps():
@@ -40,27 +40,56 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+# which headers each CUDA translation unit depends on (besides itself and include/cpbrt.h)
+CUDA_DEPS = {
+    "cpbrt_api.cu": ["device", "bvh_build.h"],
+    "bvh_build_gpu.cu": ["bvh_build.h"],
+}
+
+
+def _unit_deps(src):
+    deps = [os.path.join(CSRC, src), os.path.join(HERE, "..", "include", "cpbrt.h"), os.path.abspath(__file__)]
+    for d in CUDA_DEPS.get(src, []):
+        path = os.path.join(CSRC, d)
+        if os.path.isdir(path):
+            deps += [os.path.join(path, f) for f in os.listdir(path)]
+        else:
+            deps.append(path)
+    return deps
+
+
+def _compile_cuda(src, obj, verbose):
+    r = subprocess.run([NVCC] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj], capture_output=True, text=True)
+    with open(os.path.join(OBJ, src.replace("/", "_") + ".ptxas.log"), "w") as f:
+        f.write(r.stderr)
+    if r.returncode != 0:
+        sys.stderr.write(r.stderr)
+        raise RuntimeError("nvcc failed on " + src)
+    if verbose:
+        sys.stderr.write(r.stderr)
+
+
 def build(force=False, verbose=False):
     deps = _deps()
     if not force and not _stale(OUT, deps):
         return OUT
     os.makedirs(OBJ, exist_ok=True)
     objs = []
-    for src in HOST_SOURCES:
-        o = os.path.join(OBJ, src.replace("/", "_") + ".o")
-        subprocess.check_call(HOST_CXX + ["-c", os.path.join(CSRC, src), "-o", o])
-        objs.append(o)
-    for src in CUDA_SOURCES:
-        o = os.path.join(OBJ, src.replace("/", "_") + ".o")
-        r = subprocess.run([NVCC] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", o], capture_output=True, text=True)
-        with open(os.path.join(OBJ, src.replace("/", "_") + ".ptxas.log"), "w") as f:
-            f.write(r.stderr)
-        if r.returncode != 0:
-            sys.stderr.write(r.stderr)
-            raise RuntimeError("nvcc failed on " + src)
-        if verbose:
-            sys.stderr.write(r.stderr)
-        objs.append(o)
+    # CUDA translation units in parallel threads (nvcc is a subprocess), each only when it is stale
+    from concurrent.futures import ThreadPoolExecutor
+    jobs = []
+    with ThreadPoolExecutor(max_workers=len(CUDA_SOURCES)) as pool:
+        for src in CUDA_SOURCES:
+            o = os.path.join(OBJ, src.replace("/", "_") + ".o")
+            if force or _stale(o, _unit_deps(src)):
+                jobs.append(pool.submit(_compile_cuda, src, o, verbose))
+            objs.append(o)
+        for src in HOST_SOURCES:
+            o = os.path.join(OBJ, src.replace("/", "_") + ".o")
+            subprocess.check_call(HOST_CXX + ["-c", os.path.join(CSRC, src), "-o", o])
+            objs.append(o)
+        for j in jobs:
+            j.result()
     subprocess.check_call([NVCC, "-shared", "-o", OUT] + objs + ["-lz", "-ldl", "-lpthread", "-cudart", "static"])
     return OUT
 

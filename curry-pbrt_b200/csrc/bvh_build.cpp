@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstring>
+#include <functional>
 #include <thread>
 
 namespace cpbrt {
@@ -49,16 +50,23 @@ struct Builder {
         return id;
     }
 
+    // Per-thread scratch: millions of small nodes would otherwise spend their time in malloc.  A
+    // node is done with its scratch before it recurses, and a forked subtree runs on its own thread.
+    struct Scratch { std::vector<uint64_t> keyed; std::vector<float> back_sa; std::vector<uint32_t> idx[3], o; std::vector<float> cost[3]; std::vector<BuildBounds> b; };
+    static Scratch& scratch() { static thread_local Scratch s; return s; }
+
     // one axis of the sweep: sorted local order and the cost of every split position
     void sweep_axis(uint32_t start, uint32_t len, int axis, float full_sa, std::vector<uint32_t>& idx, std::vector<float>& cost) const {
-        std::vector<uint64_t> keyed(len);
+        Scratch& S = scratch();
+        std::vector<uint64_t>& keyed = S.keyed;
+        keyed.resize(len);
         for (uint32_t i = 0; i < len; ++i) keyed[i] = ((uint64_t)sort_key(center(pb[start + i], axis)) << 32) | i;
         std::sort(keyed.begin(), keyed.end());   // ties fall back to the local index == stable sort
         idx.resize(len);
         for (uint32_t i = 0; i < len; ++i) idx[i] = (uint32_t)keyed[i];
-        keyed.clear(); keyed.shrink_to_fit();
         // suffix areas first, then a running prefix box
-        std::vector<float> back_sa(len - 1);
+        std::vector<float>& back_sa = S.back_sa;
+        back_sa.resize(len - 1);
         BuildBounds acc = pb[start + idx[len - 1]];
         back_sa[len - 2] = surface_area(acc);
         for (uint32_t i = len - 2; i-- > 0;) { unite(acc, pb[start + idx[i + 1]]); back_sa[i] = surface_area(acc); }
@@ -77,9 +85,13 @@ struct Builder {
         for (uint32_t i = start + 1; i < end; ++i) unite(full, pb[i]);
         const float full_sa = surface_area(full);
 
-        std::vector<uint32_t> idx[3];
-        std::vector<float> cost[3];
+        // big nodes sweep their axes on separate threads and need their own vectors; small ones reuse the thread's scratch
         const bool big = len >= (1u << 16);
+        std::vector<uint32_t> own_idx[3];
+        std::vector<float> own_cost[3];
+        Scratch& S = scratch();
+        std::vector<uint32_t>* idx = big ? own_idx : S.idx;
+        std::vector<float>* cost = big ? own_cost : S.cost;
         if (big && spare_threads.fetch_sub(2) >= 2) {
             std::thread t1([&] { sweep_axis(start, len, 1, full_sa, idx[1], cost[1]); });
             std::thread t2([&] { sweep_axis(start, len, 2, full_sa, idx[2], cost[2]); });
@@ -103,12 +115,14 @@ struct Builder {
 
         {   // bvh.rs:100-112: slot j receives the primitive that was at local index best[j]
             const std::vector<uint32_t>& best = idx[min_axis];
-            std::vector<uint32_t> o(len); std::vector<BuildBounds> b(len);
+            std::vector<uint32_t>& o = S.o; std::vector<BuildBounds>& b = S.b;
+            o.resize(len); b.resize(len);
             for (uint32_t j = 0; j < len; ++j) { o[j] = order[start + best[j]]; b[j] = pb[start + best[j]]; }
             memcpy(&order[start], o.data(), len * sizeof(uint32_t));
             memcpy(&pb[start], b.data(), len * sizeof(BuildBounds));
+            if (big) { std::vector<uint32_t>().swap(o); std::vector<BuildBounds>().swap(b); }   // do not keep 10M-entry scratch alive
         }
-        for (int a = 0; a < 3; ++a) { std::vector<uint32_t>().swap(idx[a]); std::vector<float>().swap(cost[a]); }
+        if (big) for (int a = 0; a < 3; ++a) { std::vector<uint32_t>().swap(own_idx[a]); std::vector<float>().swap(own_cost[a]); }
 
         const uint32_t mid = start + min_i + 1;
         uint32_t left, right;
@@ -139,10 +153,21 @@ static void apply_point(const float* m, const float p[3], float out[3]) {   // p
     else { out[0] = r[0]; out[1] = r[1]; out[2] = r[2]; }
 }
 
+void parallel_for(uint64_t n, uint64_t min_chunk, const std::function<void(uint64_t, uint64_t)>& body) {
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const uint64_t chunks = std::max<uint64_t>(1, std::min<uint64_t>(hw, n / std::max<uint64_t>(1, min_chunk)));
+    if (chunks <= 1) { body(0, n); return; }
+    std::vector<std::thread> pool;
+    for (uint64_t c = 1; c < chunks; ++c) pool.emplace_back([&, c] { body(n * c / chunks, n * (c + 1) / chunks); });
+    body(0, n / chunks);
+    for (auto& t : pool) t.join();
+}
+
 void primitive_bounds(const cpbrt_primitive* prims, uint64_t n, const cpbrt_triangle* triangles, const float* sphere_radius,
                       const cpbrt_transform* transforms, std::vector<BuildBounds>* out) {
     out->resize(n);
-    for (uint64_t i = 0; i < n; ++i) {
+    parallel_for(n, 1 << 16, [&](uint64_t lo, uint64_t hi) {
+    for (uint64_t i = lo; i < hi; ++i) {
         const cpbrt_shape& sh = prims[i].shape;
         BuildBounds b;
         if (sh.kind == CPBRT_SHAPE_SPHERE) {
@@ -171,6 +196,7 @@ void primitive_bounds(const cpbrt_primitive* prims, uint64_t n, const cpbrt_tria
         }
         (*out)[i] = b;
     }
+    });
 }
 
 bool export_bvh(const BvhBuildResult& R, uint32_t* prim_order_out, cpbrt_bvh_dump* dump) {
@@ -191,6 +217,58 @@ bool export_bvh(const BvhBuildResult& R, uint32_t* prim_order_out, cpbrt_bvh_dum
     return true;
 }
 
+static void number_post_order(BvhBuildResult* out);
+
+void finish_sah_bvh(TopPhase&& top, unsigned n_threads, BvhBuildResult* out) {
+    const uint32_t n = (uint32_t)top.order.size();
+    out->order.clear(); out->arena.clear(); out->post_order.clear(); out->ref_index.clear(); out->root = 0;
+    if (n == 0) return;
+    if (n_threads == 0) n_threads = std::max(1u, std::thread::hardware_concurrency());
+    Builder b;
+    b.pb.swap(top.pb);
+    b.order.swap(top.order);
+    b.arena.resize(2ull * n + top.nodes.size());
+    // arena ids of the device-built Parents first, then the host subtrees
+    const uint32_t n_top = (uint32_t)top.nodes.size();
+    b.n_nodes = n_top;
+    const uint32_t np = (uint32_t)top.pending.size();
+    std::vector<uint32_t> pending_id(np, 0);
+    // many segments: one worker per thread pulls segments; few segments: let build() fork inside them
+    const unsigned workers = std::max(1u, std::min<unsigned>(n_threads, np));
+    b.spare_threads = (int)n_threads - (int)workers;
+    std::atomic<uint32_t> next{0};
+    auto work = [&]() {
+        for (;;) {
+            const uint32_t k = next.fetch_add(1);
+            if (k >= np) break;
+            const PendingSegment& p = top.pending[k];
+            pending_id[k] = p.force_leaf ? b.make_leaf(p.start, p.end) : b.build(p.start, p.end);
+        }
+    };
+    {
+        std::vector<std::thread> pool;
+        for (unsigned t = 1; t < workers; ++t) pool.emplace_back(work);
+        work();
+        for (auto& t : pool) t.join();
+    }
+    for (uint32_t i = 0; i < n_top; ++i) {
+        BuildNode& nd = b.arena[i];
+        nd.leaf = false; nd.axis = top.nodes[i].axis; nd.bound = top.nodes[i].bound;
+        nd.a = (uint32_t)top.nodes[i].child[0]; nd.b = (uint32_t)top.nodes[i].child[1];
+    }
+    uint32_t root = top.root == 0x7FFFFFFF ? 0u : (uint32_t)top.root;
+    for (uint32_t k = 0; k < np; ++k) {
+        if (top.pending_parent[k] < 0) root = pending_id[k];
+        else if (top.pending_side[k] == 0) b.arena[top.pending_parent[k]].a = pending_id[k];
+        else b.arena[top.pending_parent[k]].b = pending_id[k];
+    }
+    out->root = root;
+    b.arena.resize(b.n_nodes.load());
+    out->order.swap(b.order);
+    out->arena.swap(b.arena);
+    number_post_order(out);
+}
+
 void build_sah_bvh(const std::vector<BuildBounds>& bounds, unsigned n_threads, BvhBuildResult* out) {
     const uint32_t n = (uint32_t)bounds.size();
     out->order.clear(); out->arena.clear(); out->post_order.clear(); out->ref_index.clear(); out->root = 0;
@@ -206,8 +284,11 @@ void build_sah_bvh(const std::vector<BuildBounds>& bounds, unsigned n_threads, B
     b.arena.resize(b.n_nodes.load());
     out->order.swap(b.order);
     out->arena.swap(b.arena);
+    number_post_order(out);
+}
 
-    // reference numbering: post-order, left subtree first (bvh.rs:113-123)
+// reference numbering: post-order, left subtree first (bvh.rs:113-123)
+static void number_post_order(BvhBuildResult* out) {
     const uint32_t nn = (uint32_t)out->arena.size();
     out->post_order.reserve(nn);
     out->ref_index.assign(nn, 0);

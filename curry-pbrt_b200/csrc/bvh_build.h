@@ -5,6 +5,7 @@
 // parallel.
 #pragma once
 #include <cstdint>
+#include <functional>
 #include <vector>
 
 #include "../../include/cpbrt.h"
@@ -29,6 +30,9 @@ struct BvhBuildResult {
     std::vector<uint32_t> ref_index;  // reference node number of arena node i
 };
 
+// body(lo, hi) over [0, n) split across the host threads (chunks of at least min_chunk items)
+void parallel_for(uint64_t n, uint64_t min_chunk, const std::function<void(uint64_t, uint64_t)>& body);
+
 // Primitive::bound() of every uploaded primitive (triangle.rs:114-119, sphere.rs:22-27,
 // TransformShape::bound transform.rs:52-54 with Bounds3f::apply bounds.rs:292-300).
 void primitive_bounds(const cpbrt_primitive* prims, uint64_t n, const cpbrt_triangle* triangles, const float* sphere_radius,
@@ -40,5 +44,25 @@ bool export_bvh(const BvhBuildResult& r, uint32_t* prim_order_out, cpbrt_bvh_dum
 
 // bounds[i] = Primitive::bound() of uploaded primitive i.  n_threads == 0 -> hardware.
 void build_sah_bvh(const std::vector<BuildBounds>& bounds, unsigned n_threads, BvhBuildResult* out);
+
+// ---- hybrid build: the top of the tree on the GPU (bvh_build_gpu.cu), the rest on the host ------
+struct TopNode {            // a Parent created by the device phase
+    uint8_t axis;
+    BuildBounds bound;
+    int32_t child[2];       // TopNode index once known; pending segments attach through pending_parent / pending_side
+};
+struct PendingSegment { uint32_t start, end, force_leaf; };   // slot range the host still has to build (force_leaf: the SAH said "leaf")
+struct TopPhase {
+    std::vector<BuildBounds> pb;          // bound of the primitive now in each slot
+    std::vector<uint32_t> order;          // slot -> uploaded primitive index, as permuted by the device levels
+    std::vector<TopNode> nodes;
+    std::vector<PendingSegment> pending;
+    std::vector<int32_t> pending_parent;  // TopNode that owns pending segment k (-1: it is the root)
+    std::vector<uint32_t> pending_side;
+    int32_t root = 0x7FFFFFFF;            // TopNode index of the root (0x7FFFFFFF: the root is a pending segment)
+    int levels = 0;
+};
+// Builds every pending segment with the host builder (in parallel) and stitches the tree together.
+void finish_sah_bvh(TopPhase&& top, unsigned n_threads, BvhBuildResult* out);
 
 }  // namespace cpbrt

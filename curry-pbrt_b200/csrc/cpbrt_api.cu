@@ -5,6 +5,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -16,6 +17,10 @@
 #include "bvh_build.h"
 #include "device/wavefront.cuh"
 
+namespace cpbrt {
+// bvh_build_gpu.cu: the levels of the SAH build whose segments hold at least `min_len` primitives
+bool gpu_sah_top_phase(const std::vector<BuildBounds>& bounds, uint32_t min_len, int max_levels, cudaStream_t stream, TopPhase* out, std::string* err);
+}
 using namespace cpbrt;
 
 namespace {
@@ -69,6 +74,7 @@ struct cpbrt_ctx {
     std::vector<float> sphere_radius;
     std::vector<cpbrt_transform> transforms;
     BvhBuildResult bvh;
+    int bvh_gpu_levels = 0;   // levels of the last BVH build that ran on the device
     std::vector<DevLight> host_lights;
 
     DevScene scene;   // by-value kernel argument
@@ -383,9 +389,36 @@ int cpbrt_build_bvh(cpbrt_ctx* ctx, uint32_t* prim_order_out, cpbrt_bvh_dump* du
     if (!ctx->has_scene) return ctx->fail(CPBRT_ERR_BAD_CTX, "cpbrt_build_bvh before cpbrt_upload_scene");
     CU(cudaSetDevice(ctx->device));
     const uint32_t n = (uint32_t)ctx->primitives.size();
+    const bool timing = getenv("CPBRT_TIMING") != nullptr;
+    auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_mark = now();
+    auto lap = [&](const char* what) { if (timing) { const double t = now(); fprintf(stderr, "[cpbrt_build_bvh] %-28s %.3f s\n", what, t - t_mark); t_mark = t; } };
     std::vector<BuildBounds> bounds;
     primitive_bounds(ctx->primitives.data(), n, ctx->triangles.data(), ctx->sphere_radius.data(), ctx->transforms.data(), &bounds);
-    build_sah_bvh(bounds, 0, &ctx->bvh);
+    // Big scenes: the top of the tree (segments of >= min_len primitives) is built on the device, the
+    // host builder finishes the many small subtrees in parallel; same order and topology either way.
+    // CPBRT_BVH_BUILD=host|gpu and CPBRT_BVH_GPU_MINLEN override the defaults (tests use both).
+    {
+        const char* how = getenv("CPBRT_BVH_BUILD");
+        const char* ml = getenv("CPBRT_BVH_GPU_MINLEN");
+        const uint32_t min_len = ml ? (uint32_t)std::max(2, atoi(ml)) : 256u;   // measured flat between 16 and 1024 (tools/bvh_build_bench.py)
+        bool on_gpu = how ? strcmp(how, "gpu") == 0 : n >= (1u << 17);
+        ctx->bvh_gpu_levels = 0;
+        if (on_gpu && n >= min_len && n >= 2) {
+            TopPhase top; std::string why;
+            lap("primitive bounds");
+            if (gpu_sah_top_phase(bounds, min_len, 48, ctx->stream, &top, &why)) {
+                lap("device top levels");
+                ctx->bvh_gpu_levels = top.levels;
+                finish_sah_bvh(std::move(top), 0, &ctx->bvh);
+                lap("host subtrees");
+            } else {
+                cudaGetLastError();
+                on_gpu = false;
+            }
+        } else on_gpu = false;
+        if (!on_gpu) { build_sah_bvh(bounds, 0, &ctx->bvh); lap("host build"); }
+    }
     const BvhBuildResult& R = ctx->bvh;
 
     // primitive records in BVH order
@@ -399,7 +432,8 @@ int cpbrt_build_bvh(cpbrt_ctx* ctx, uint32_t* prim_order_out, cpbrt_bvh_dump* du
         }
     }
     std::vector<float> uvs(any_uv ? 6ull * n : 0);
-    for (uint32_t slot = 0; slot < n; ++slot) {
+    parallel_for(n, 1 << 16, [&](uint64_t slot_lo, uint64_t slot_hi) {
+    for (uint32_t slot = (uint32_t)slot_lo; slot < (uint32_t)slot_hi; ++slot) {
         const uint32_t up = R.order[slot];
         const cpbrt_primitive& p = ctx->primitives[up];
         uint32_t meta = ((uint32_t)(p.shape.xform + 1)) << 2;
@@ -416,6 +450,8 @@ int cpbrt_build_bvh(cpbrt_ctx* ctx, uint32_t* prim_order_out, cpbrt_bvh_dump* du
         q2.w = u2f(p.material >= 0 ? (uint32_t)p.material : (kSourceLight | (uint32_t)p.light));
         prims[3ull * slot] = q0; prims[3ull * slot + 1] = q1; prims[3ull * slot + 2] = q2;
     }
+    });
+    lap("primitive records");
     if (int rc = alloc_upload(ctx, ctx->d_prims, prims.data(), prims.size() * sizeof(float4))) return rc;
     if (int rc = alloc_upload(ctx, ctx->d_prim_uv, any_uv ? uvs.data() : nullptr, uvs.size() * 4)) return rc;
 
@@ -448,7 +484,8 @@ int cpbrt_build_bvh(cpbrt_ctx* ctx, uint32_t* prim_order_out, cpbrt_bvh_dump* du
                 }
                 return out;
             };
-            for (uint32_t k = 0; k < dfs.size(); ++k) {
+            parallel_for(dfs.size(), 1 << 15, [&](uint64_t k_lo, uint64_t k_hi) {
+            for (uint32_t k = (uint32_t)k_lo; k < (uint32_t)k_hi; ++k) {
                 const BuildNode& nd = R.arena[dfs[k]];
                 const BuildNode l = R.arena[nd.a].leaf ? leaf_bound(R.arena[nd.a]) : R.arena[nd.a];
                 const BuildNode r = R.arena[nd.b].leaf ? leaf_bound(R.arena[nd.b]) : R.arena[nd.b];
@@ -459,11 +496,13 @@ int cpbrt_build_bvh(cpbrt_ctx* ctx, uint32_t* prim_order_out, cpbrt_bvh_dump* du
                 nodes[4ull * k + 2] = make_float4(r.bound.mn[2], r.bound.mx[0], r.bound.mx[1], r.bound.mx[2]);
                 nodes[4ull * k + 3] = make_float4(u2f(lref), u2f(rref), u2f(lcnt | ((uint32_t)nd.axis << 30)), u2f(rcnt));
             }
+            });
             S.n_nodes = (uint32_t)dfs.size();
             S.root_ref = 0; S.root_cnt = 0;
             for (int k = 0; k < 3; ++k) { S.root_box[k] = root.bound.mn[k]; S.root_box[3 + k] = root.bound.mx[k]; }
         }
     }
+    lap("node layout");
     if (int rc = alloc_upload(ctx, ctx->d_nodes, nodes.empty() ? nullptr : nodes.data(), nodes.size() * sizeof(float4))) return rc;
     // BVH slot of each area light's primitive (when exactly one primitive carries the light)
     {
@@ -483,6 +522,7 @@ int cpbrt_build_bvh(cpbrt_ctx* ctx, uint32_t* prim_order_out, cpbrt_bvh_dump* du
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->has_bvh = true;
 
+    lap("uploads");
     if (!export_bvh(R, prim_order_out, dump))
         return ctx->fail(CPBRT_ERR_BAD_ARG, "bvh dump capacity %llu < %llu nodes", (unsigned long long)dump->capacity, (unsigned long long)dump->n_nodes);
     return CPBRT_OK;
@@ -820,6 +860,8 @@ int cpbrt_render(cpbrt_ctx* ctx, const cpbrt_render_params* params, float* film_
     }
     return check_overflow(ctx, t);
 }
+
+int cpbrt_bvh_gpu_levels(const cpbrt_ctx* ctx) { return ctx ? ctx->bvh_gpu_levels : 0; }
 
 int cpbrt_measure_read_bandwidth(cpbrt_ctx* ctx, uint64_t bytes, uint32_t repeats, double* gb_per_s) {
     if (!ctx) return CPBRT_ERR_BAD_CTX;

@@ -283,6 +283,11 @@ int cpbrt_camera_rays(cpbrt_ctx* ctx, uint32_t sample, cpbrt_ray* rays_out, int 
 int cpbrt_render(cpbrt_ctx* ctx, const cpbrt_render_params* params, float* film_rgb_out,
                  cpbrt_stats* stats_out);
 
+/* How many levels of the last cpbrt_build_bvh ran on the device (0 = the exact SAH build ran on the host only).
+ * Scenes of >= 131072 primitives build the top of the tree (segments of >= 256 primitives) on the GPU and
+ * finish the small subtrees on the host threads; the result is identical either way (bvh.rs:24-124). */
+int cpbrt_bvh_gpu_levels(const cpbrt_ctx* ctx);
+
 /* Roofline denominators: read bandwidth of a zero-filled device buffer of `bytes` bytes
  * streamed `repeats` times by a read-only kernel (16-byte loads).  64 MB stays resident in the 126 MB
  * L2 and gives the L2 read peak; a multi-GB buffer gives the HBM read peak.  No reference equivalent. */

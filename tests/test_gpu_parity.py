@@ -122,6 +122,54 @@ def test_bvh_order_and_nodes_bit_exact(cpbrt, cornell, spheres, mesh):
         assert np.array_equal(nodes["bound"].view(np.uint32), ref["bound"].view(np.uint32))
 
 
+def _random_soup_scene(cpbrt, n_tris, seed, grid=False):
+    """Triangles with many exactly equal bound centres (grid=True: a regular lattice) or none."""
+    rng = np.random.default_rng(seed)
+    if grid:
+        side = int(np.sqrt(n_tris / 2))
+        xs, zs = np.meshgrid(np.arange(side, dtype=np.float32), np.arange(side, dtype=np.float32))
+        base = np.stack([xs.ravel(), np.zeros(side * side, np.float32), zs.ravel()], 1)
+        t0 = np.stack([base, base + [1, 0, 0], base + [1, 0, 1]], 1)
+        t1 = np.stack([base + [1, 0, 1], base + [0, 0, 1], base], 1)
+        tris = np.concatenate([t0, t1]).astype(np.float32)
+        tris[:, :, 1] = rng.integers(0, 3, size=(len(tris), 1)).astype(np.float32) * 0.25     # a few height levels: more ties
+    else:
+        c = rng.random((n_tris, 1, 3)).astype(np.float32) * 20
+        tris = (c + rng.normal(scale=0.3, size=(n_tris, 3, 3))).astype(np.float32)
+    tris = tris * np.float32(0.05) + np.array([-0.5, -0.3, 3.0], np.float32)
+    P = " ".join(repr(float(v)) for v in tris.ravel())
+    I = " ".join(str(i) for i in range(3 * len(tris)))
+    text = ('Camera "perspective" "float fov" [60]\nSampler "halton" "integer pixelsamples" [1]\n'
+            'Film "image" "integer xresolution" [32] "integer yresolution" [32]\nIntegrator "path"\nWorldBegin\n'
+            'AttributeBegin\nAreaLightSource "diffuse" "rgb L" [5 5 5]\nShape "trianglemesh" "integer indices" [0 1 2] "point P" [0 2 3 1 2 3 1 2 4]\nAttributeEnd\n'
+            'Material "matte"\nShape "trianglemesh" "integer indices" [%s] "point P" [%s]\nWorldEnd\n' % (I, P))
+    return cpbrt.Scene.parse(text)
+
+
+@pytest.mark.parametrize("min_len", [2, 7, 64, 1000])
+def test_gpu_bvh_top_phase_equals_host_build(cpbrt, oracle, cornell, mesh, monkeypatch, min_len):
+    """the top levels of the exact SAH build on the device (bvh_build_gpu.cu: radix sort
+    per axis, prefix / suffix bound scans, first-minimum pick, level by level), the small subtrees
+    on the host.  Primitive order, topology, split axes and Parent bounds must equal the oracle's
+    whatever segment length the hand-over happens at -- including lattices full of equal centres."""
+    scenes = [cornell[0], mesh[0], _random_soup_scene(cpbrt, 3000, 1), _random_soup_scene(cpbrt, 5000, 2, grid=True)]
+    monkeypatch.setenv("CPBRT_BVH_BUILD", "gpu")
+    monkeypatch.setenv("CPBRT_BVH_GPU_MINLEN", str(min_len))
+    for scene in scenes:
+        w = oracle.OracleWorld(scene)
+        r = cpbrt.Renderer(0); r.upload(scene)
+        order, nodes = r.build_bvh(want_nodes=True)
+        assert np.array_equal(order, w.bvh_order())
+        ref = w.bvh_nodes()
+        assert nodes["root"] == ref["root"]
+        for k in ("is_leaf", "axis", "a", "b"):
+            assert np.array_equal(nodes[k], ref[k]), k
+        assert np.array_equal(nodes["bound"], ref["bound"])
+        if scene.desc.n_primitives >= max(min_len, 2):
+            assert r.bvh_gpu_levels() > 0
+        r.close()
+
+
 def _check_closest(r, w, rays):
     g, gs = r.trace_closest(rays, count=True)
     o, oc = w.trace_closest(rays, count=True)
