@@ -255,18 +255,22 @@ __global__ void __launch_bounds__(128, 8) k_trace_closest(DevScene sc, PathArray
 // and every 32-byte state record would be its own DRAM transaction.  Walking the path ids in
 // order keeps neighbouring pixels' paths adjacent in each queue, so shading reads and writes
 // its state in full cache lines.
-__global__ void k_classify(PathArrays P, Queues Q, uint32_t n_paths) {
-    // four consecutive paths per thread (one 32-bit load of their kind bytes), 128 per warp;
-    // per kind one reservation per warp, all reservations issued before any is waited for
-    const int lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(256) k_classify(PathArrays P, Queues Q, uint32_t n_paths) {
+    // four consecutive paths per thread (one 32-bit load of their kind bytes), 1024 per block
+    // iteration; per kind ONE reservation per block: every reservation of a kind hits the same
+    // counter, and same-address atomics are served one at a time (one per warp made this kernel
+    // 0.28 ms per bounce for 16 M paths, atomic-bound)
+    __shared__ uint32_t warp_tot[8][SHADE_KINDS];
+    __shared__ uint32_t warp_base[8][SHADE_KINDS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned below = (1u << lane) - 1u;
     const uint32_t n_quads = (n_paths + 3u) >> 2;               // capacity is a multiple of 4 bytes (cudaMalloc granularity)
-    const uint32_t n_round = (n_quads + 31u) & ~31u;
+    const uint32_t n_round = (n_quads + 255u) & ~255u;          // whole blocks: every thread of a block makes the same trips
     uint32_t* kinds32 = reinterpret_cast<uint32_t*>(P.shade_kind);
     for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n_round; q += gridDim.x * blockDim.x) {
         uint32_t w = 0xFFFFFFFFu;
         if (q < n_quads) { w = kinds32[q]; if (w != 0xFFFFFFFFu) kinds32[q] = 0xFFFFFFFFu; }
-        uint32_t base[SHADE_KINDS], mine[SHADE_KINDS], before[SHADE_KINDS];
+        uint32_t mine[SHADE_KINDS], before[SHADE_KINDS];
 #pragma unroll
         for (int k = 0; k < SHADE_KINDS; ++k) {
             uint32_t tot = 0, bef = 0, cnt = 0;
@@ -278,19 +282,29 @@ __global__ void k_classify(PathArrays P, Queues Q, uint32_t n_paths) {
             }
             // entries of lower lanes come first, then this thread's own in path order
             before[k] = bef; mine[k] = cnt;
-            base[k] = 0;
-            if (lane == 0 && tot) base[k] = atomicAdd(&Q.counts[kCntShade0 + k], tot);
+            if (lane == 0) warp_tot[warp][k] = tot;
         }
+        __syncthreads();
+        if (threadIdx.x < SHADE_KINDS) {
+            const int k = threadIdx.x;
+            uint32_t run = 0;
+#pragma unroll
+            for (int v = 0; v < 8; ++v) { warp_base[v][k] = run; run += warp_tot[v][k]; }
+            const uint32_t base = run ? atomicAdd(&Q.counts[kCntShade0 + k], run) : 0u;
+#pragma unroll
+            for (int v = 0; v < 8; ++v) warp_base[v][k] += base;
+        }
+        __syncthreads();
 #pragma unroll
         for (int k = 0; k < SHADE_KINDS; ++k) {
-            const uint32_t b = __shfl_sync(0xFFFFFFFFu, base[k], 0);
             if (mine[k]) {
-                uint32_t pos = b + before[k];
+                uint32_t pos = warp_base[warp][k] + before[k];
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     if (((w >> (8 * j)) & 0xFFu) == (uint32_t)k) Q.shade[k][pos++] = 4u * q + j;
             }
         }
+        __syncthreads();      // warp_tot / warp_base are reused by the next trip
     }
 }
 
