@@ -65,6 +65,9 @@ struct cpbrt_ctx {
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
+    // two auxiliary streams + a handful of timing-less events: independent stages of a bounce overlap (cpbrt_render)
+    cudaStream_t aux[2] = {nullptr, nullptr};
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     std::string error;
 
     // host copy of what the BVH build needs
@@ -165,6 +168,9 @@ int cpbrt_create(cpbrt_ctx** out, int device_id) {
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device_id);
     e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e); delete ctx; return CPBRT_ERR_CUDA; }
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking);
+    for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming);
+    if (e != cudaSuccess) { g_create_error = std::string("cudaStreamCreate / cudaEventCreate: ") + cudaGetErrorString(e); cpbrt_destroy(ctx); return CPBRT_ERR_CUDA; }
     memset(&ctx->scene, 0, sizeof ctx->scene);
     *out = ctx;
     return CPBRT_OK;
@@ -178,6 +184,8 @@ void cpbrt_destroy(cpbrt_ctx* ctx) {
                       &ctx->d_lights, &ctx->d_perm, &ctx->d_primes, &ctx->d_primsum, &ctx->d_magic, &ctx->d_path, &ctx->d_kind, &ctx->d_queues, &ctx->d_counts,
                       &ctx->d_pixels, &ctx->d_totals_buf, &ctx->d_film_out};
     for (DevBuf* b : bufs) b->release();
+    for (int i = 0; i < 6; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 2; ++i) if (ctx->aux[i]) cudaStreamDestroy(ctx->aux[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -768,27 +776,44 @@ int cpbrt_render(cpbrt_ctx* ctx, const cpbrt_render_params* params, float* film_
             k_direct_recursive<<<grid_for(ctx, 8), 64, 0, st>>>(S, P, Sn * npix, T); ++launches;
             span_end();
         }
+        // One bounce = closest-hit stage (K1), shadow stage (K2), queue bookkeeping (K3), classify (K4),
+        // the per-kind shading kernels (K5..) and their bookkeeping (K9).  K1 and K2 are independent, K4
+        // only needs K1, and the shading kernels of different kinds touch different paths: they are put
+        // on three streams so that the short, poorly filled kernels (terminal / mirror / glass / classify,
+        // ~8 % of a bounce when run back to back) and the tails of the persistent trace kernels overlap
+        // with the long ones.  `st` is the join point.  With profile_stages the bounce runs back to back
+        // on one stream so that the per-stage times mean something.
+        cudaStream_t sa = prof ? st : ctx->aux[0], sb = prof ? st : ctx->aux[1];
+        cudaEvent_t eK1 = ctx->ev[0], eK3 = ctx->ev[1], eK4 = ctx->ev[2], eS = ctx->ev[3], ePrev = ctx->ev[4];
+        if (!prof && !recursive) cudaEventRecord(ePrev, st);          // after raygen
         for (uint32_t it = 0; it < n_iters && !recursive; ++it) {
+            const int next = cur ^ 1;
             span_begin(1);
             if (vote) k_trace_closest<true><<<g_trace, 128, 0, st>>>(S, P, Q, cur, T);
             else k_trace_closest<false><<<g_trace, 128, 0, st>>>(S, P, Q, cur, T);
             ++trace_launches;
             span_end();
+            if (!prof) { cudaEventRecord(eK1, st); cudaStreamWaitEvent(sa, ePrev, 0); }
             span_begin(2);
-            if (vote) k_trace_shadow<true><<<g_trace, 128, 0, st>>>(S, P, Q, T);
-            else k_trace_shadow<false><<<g_trace, 128, 0, st>>>(S, P, Q, T);
+            if (vote) k_trace_shadow<true><<<g_trace, 128, 0, sa>>>(S, P, Q, T);
+            else k_trace_shadow<false><<<g_trace, 128, 0, sa>>>(S, P, Q, T);
             span_end();
-            k_queue_reset<<<1, 32, 0, st>>>(Q, cur, 0, T);
-            const int next = cur ^ 1;
+            if (!prof) cudaStreamWaitEvent(sa, eK1, 0);
+            k_queue_reset<<<1, 32, 0, sa>>>(Q, cur, 0, T);
+            if (!prof) cudaEventRecord(eK3, sa);
             span_begin(3);
             k_classify<<<g_pix, 256, 0, st>>>(P, Q, Sn * npix); ++launches;
-            k_shade_terminal<<<g_shade, 128, 0, st>>>(S, P, Q);
+            if (!prof) { cudaEventRecord(eK4, st); cudaStreamWaitEvent(sb, eK4, 0); cudaStreamWaitEvent(sb, eK3, 0); }
+            k_shade_terminal<<<g_shade, 128, 0, sb>>>(S, P, Q);
+            k_shade<SHADE_MIRROR><<<g_shade, 128, 0, sb>>>(S, P, Q, next, T);
+            k_shade<SHADE_GLASS><<<g_shade, 128, 0, sb>>>(S, P, Q, next, T);
+            if (ctx->has_general_materials) { k_shade<SHADE_GENERAL><<<grid_for(ctx, ShadeBlocks<SHADE_GENERAL>::value), 128, 0, sb>>>(S, P, Q, next, T); ++launches; }
+            if (!prof) { cudaEventRecord(eS, sb); cudaStreamWaitEvent(st, eK3, 0); }
             k_shade<SHADE_MATTE><<<grid_for(ctx, ShadeBlocks<SHADE_MATTE>::value), 128, 0, st>>>(S, P, Q, next, T);
-            k_shade<SHADE_MIRROR><<<g_shade, 128, 0, st>>>(S, P, Q, next, T);
-            k_shade<SHADE_GLASS><<<g_shade, 128, 0, st>>>(S, P, Q, next, T);
-            if (ctx->has_general_materials) { k_shade<SHADE_GENERAL><<<grid_for(ctx, ShadeBlocks<SHADE_GENERAL>::value), 128, 0, st>>>(S, P, Q, next, T); ++launches; }
             span_end();
+            if (!prof) cudaStreamWaitEvent(st, eS, 0);
             k_queue_reset<<<1, 32, 0, st>>>(Q, cur, 1, T);
+            if (!prof) cudaEventRecord(ePrev, st);
             launches += 8;
             cur = next;
         }
