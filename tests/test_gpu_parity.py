@@ -540,6 +540,35 @@ def test_directlighting_recursion_over_delta_lobes(cpbrt, oracle, material):
     assert os_["rays_closest"] > 1.5 * 80 * 80 * 4
 
 
+def test_degenerate_scenes(cpbrt, oracle):
+    """Edge cases of render(): no primitives at all (every ray escapes), a 1x1 film at 1 spp, a film
+    whose pixels all miss the geometry, and a scene without lights -- all against the oracle."""
+    head = ('Camera "perspective" "float fov" [40]\nSampler "halton" "integer pixelsamples" [%d]\n'
+            'Film "image" "integer xresolution" [%d] "integer yresolution" [%d]\nIntegrator "path" "integer maxdepth" [3]\nWorldBegin\n')
+    cases = [
+        head % (2, 8, 8) + 'WorldEnd\n',                                                              # empty world
+        head % (2, 8, 8) + 'LightSource "infinite"\nWorldEnd\n',                                      # only an environment light
+        head % (1, 1, 1) + 'LightSource "point" "point from" [0 2 0]\nMaterial "matte"\nTranslate 0 0 5\nShape "sphere"\nWorldEnd\n',
+        head % (3, 16, 4) + 'Material "matte"\nTranslate 0 0 5\nShape "sphere" "float radius" [0.5]\nWorldEnd\n',   # no lights
+        head % (2, 12, 12) + 'LightSource "distant"\nMaterial "mirror"\nTranslate 100 0 5\nShape "sphere"\nWorldEnd\n',  # everything clipped / missed
+    ]
+    for text in cases:
+        scene = cpbrt.Scene.parse(text, base_dir=SCENES)
+        r = cpbrt.Renderer(0); r.upload(scene)
+        order = r.build_bvh()
+        w = oracle.OracleWorld(scene)
+        assert np.array_equal(order, w.bvh_order())
+        g, gs = r.render()
+        o, _, os_ = w.render()
+        assert g.shape == o.shape and np.isfinite(g).all()
+        np.testing.assert_allclose(g, o, rtol=1e-4, atol=1e-6)
+        assert gs.camera_samples == g.shape[0] * g.shape[1] * scene.desc.sampler.spp
+        rays = lcg_rays(100, (-2, -2, 0), (2, 2, 8), seed=5)
+        assert np.array_equal(r.trace_closest(rays)["prim"], w.trace_closest(rays)["prim"])
+        assert np.array_equal(r.trace_any(rays), w.trace_any(rays))
+        r.close()
+
+
 def test_unsupported_features_fail_loudly(cpbrt):
     head = ('Camera "perspective" "float fov" [40]\nSampler "halton" "integer pixelsamples" [1]\n'
             'Film "image" "integer xresolution" [8] "integer yresolution" [8]\nIntegrator "path"\nWorldBegin\n')
