@@ -41,6 +41,7 @@ struct NcclApi {
     int (*CommInitRank)(ncclComm_t*, int, NcclUniqueId, int) = nullptr;
     int (*CommDestroy)(ncclComm_t) = nullptr;
     int (*Reduce)(const void*, void*, size_t, int, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
     bool load(std::string* err) {
         if (handle) return true;
@@ -51,13 +52,14 @@ struct NcclApi {
         CommInitRank = (int (*)(ncclComm_t*, int, NcclUniqueId, int))dlsym(handle, "ncclCommInitRank");
         CommDestroy = (int (*)(ncclComm_t))dlsym(handle, "ncclCommDestroy");
         Reduce = (int (*)(const void*, void*, size_t, int, int, int, ncclComm_t, cudaStream_t))dlsym(handle, "ncclReduce");
+        Broadcast = (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(handle, "ncclBroadcast");
         GetErrorString = (const char* (*)(int))dlsym(handle, "ncclGetErrorString");
         if (!GetUniqueId || !CommInitRank || !CommDestroy || !Reduce) { *err = "libnccl lacks a required symbol"; return false; }
         return true;
     }
 };
 NcclApi g_nccl;
-const int kNcclFloat32 = 7, kNcclSum = 0;
+const int kNcclFloat32 = 7, kNcclUint8 = 1, kNcclSum = 0;
 
 }  // namespace
 
@@ -392,11 +394,81 @@ int cpbrt_upload_scene(cpbrt_ctx* ctx, const cpbrt_scene_desc* d) {
     return CPBRT_OK;
 }
 
+// ---- one build for all ranks ---------------------------------------------------------------------
+// With a communicator attached BEFORE the build, rank 0 builds the BVH and its device layout and the
+// other ranks receive the finished arrays over NVLink (ncclBroadcast) instead of repeating the same
+// build on the same host cores: eight ranks share one CPU, and the host part of a 10-million-primitive
+// build would otherwise run eight times at an eighth of the threads.
+struct BvhShareHeader { uint32_t n_prims, n_nodes, root_ref, root_cnt, any_uv, pad[3]; float root_box[6]; float pad2[2]; };
+static bool share_bvh(const cpbrt_ctx* ctx, uint32_t n) {
+    if (!ctx->comm || ctx->n_ranks <= 1 || !g_nccl.Broadcast) return false;
+    const char* e = getenv("CPBRT_BVH_SHARE");
+    return e ? atoi(e) != 0 : n >= (1u << 16);
+}
+static int bcast(cpbrt_ctx* ctx, void* buf, size_t bytes) {
+    if (bytes == 0) return 0;
+    const int rc = g_nccl.Broadcast(buf, buf, bytes, kNcclUint8, 0, ctx->comm, ctx->stream);
+    if (rc != 0) return ctx->fail(CPBRT_ERR_NCCL, "ncclBroadcast: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
+    return 0;
+}
+// both sides: header first (sizes), then the arrays, all on the context's stream
+static int exchange_bvh(cpbrt_ctx* ctx, uint32_t n, bool any_uv, const uint32_t* order_host, uint32_t* prim_order_out) {
+    DevScene& S = ctx->scene;
+    const bool root = ctx->rank == 0;
+    DevBuf d_hdr, d_order;
+    BvhShareHeader h; memset(&h, 0, sizeof h);
+    if (root) { h.n_prims = n; h.n_nodes = S.n_nodes; h.root_ref = S.root_ref; h.root_cnt = S.root_cnt; h.any_uv = any_uv ? 1u : 0u; memcpy(h.root_box, S.root_box, sizeof h.root_box); }
+    if (int rc = alloc_upload(ctx, d_hdr, root ? &h : nullptr, sizeof h)) return rc;
+    int rc = bcast(ctx, d_hdr.p, sizeof h);
+    if (!rc && !root) {
+        cudaError_t e = cudaMemcpyAsync(&h, d_hdr.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = ctx->fail(CPBRT_ERR_CUDA, "bvh header: %s", cudaGetErrorString(e));
+        else if (h.n_prims != n) rc = ctx->fail(CPBRT_ERR_BAD_ARG, "rank 0 built a BVH over %u primitives, this rank uploaded %u", h.n_prims, n);
+        if (!rc) {
+            S.n_nodes = h.n_nodes; S.root_ref = h.root_ref; S.root_cnt = h.root_cnt; memcpy(S.root_box, h.root_box, sizeof h.root_box);
+            any_uv = h.any_uv != 0;
+            rc = alloc_upload(ctx, ctx->d_prims, nullptr, 3ull * n * sizeof(float4));
+            if (!rc) rc = alloc_upload(ctx, ctx->d_prim_uv, nullptr, any_uv ? 6ull * n * 4 : 0);
+            if (!rc) rc = alloc_upload(ctx, ctx->d_nodes, nullptr, 4ull * h.n_nodes * sizeof(float4));
+            if (!rc) rc = alloc_upload(ctx, ctx->d_lights, ctx->host_lights.data(), ctx->host_lights.size() * sizeof(DevLight));
+        }
+    }
+    if (!rc) rc = alloc_upload(ctx, d_order, root ? order_host : nullptr, (size_t)n * 4);
+    if (!rc) rc = bcast(ctx, ctx->d_prims.p, 3ull * n * sizeof(float4));
+    if (!rc && any_uv) rc = bcast(ctx, ctx->d_prim_uv.p, 6ull * n * 4);
+    if (!rc) rc = bcast(ctx, ctx->d_nodes.p, 4ull * S.n_nodes * sizeof(float4));
+    if (!rc) rc = bcast(ctx, ctx->d_lights.p, ctx->host_lights.size() * sizeof(DevLight));
+    if (!rc) rc = bcast(ctx, d_order.p, (size_t)n * 4);
+    if (!rc) {
+        cudaError_t e = cudaSuccess;
+        if (!root && prim_order_out && n) e = cudaMemcpyAsync(prim_order_out, d_order.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = ctx->fail(CPBRT_ERR_CUDA, "bvh exchange: %s", cudaGetErrorString(e));
+    }
+    d_hdr.release(); d_order.release();
+    if (!rc && !root) {
+        S.prims = (const float4*)ctx->d_prims.p;
+        S.prim_uv = any_uv ? (const float*)ctx->d_prim_uv.p : nullptr;
+        S.nodes = (const float4*)ctx->d_nodes.p;
+        S.lights = (const DevLight*)ctx->d_lights.p;
+    }
+    return rc;
+}
+
 int cpbrt_build_bvh(cpbrt_ctx* ctx, uint32_t* prim_order_out, cpbrt_bvh_dump* dump) {
     if (!ctx) return CPBRT_ERR_BAD_CTX;
     if (!ctx->has_scene) return ctx->fail(CPBRT_ERR_BAD_CTX, "cpbrt_build_bvh before cpbrt_upload_scene");
     CU(cudaSetDevice(ctx->device));
     const uint32_t n = (uint32_t)ctx->primitives.size();
+    const bool shared = share_bvh(ctx, n);
+    if (shared && ctx->rank != 0) {
+        if (dump) return ctx->fail(CPBRT_ERR_BAD_ARG, "the node dump of a shared build is only available on rank 0");
+        ctx->bvh = BvhBuildResult(); ctx->bvh_gpu_levels = 0;
+        if (int rc = exchange_bvh(ctx, n, false, nullptr, prim_order_out)) return rc;
+        ctx->has_bvh = true;
+        return CPBRT_OK;
+    }
     const bool timing = getenv("CPBRT_TIMING") != nullptr;
     auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     double t_mark = now();
@@ -528,6 +600,7 @@ int cpbrt_build_bvh(cpbrt_ctx* ctx, uint32_t* prim_order_out, cpbrt_bvh_dump* du
     S.prim_uv = any_uv ? (const float*)ctx->d_prim_uv.p : nullptr;
     S.nodes = (const float4*)ctx->d_nodes.p;
     CU(cudaStreamSynchronize(ctx->stream));
+    if (shared) { if (int rc = exchange_bvh(ctx, n, any_uv, R.order.data(), nullptr)) return rc; lap("broadcast to the other ranks"); }
     ctx->has_bvh = true;
 
     lap("uploads");

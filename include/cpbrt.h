@@ -293,7 +293,11 @@ int cpbrt_bvh_gpu_levels(const cpbrt_ctx* ctx);
  * L2 and gives the L2 read peak; a multi-GB buffer gives the HBM read peak.  No reference equivalent. */
 int cpbrt_measure_read_bandwidth(cpbrt_ctx* ctx, uint64_t bytes, uint32_t repeats, double* gb_per_s);
 
-/* Multi-GPU: one NCCL communicator over the per-GPU contexts.  id_bytes = ncclUniqueId (128 B). */
+/* Multi-GPU: one NCCL communicator over the per-GPU contexts.  id_bytes = ncclUniqueId (128 B).
+ * cpbrt_render then renders this rank's share of the sample indices and reduces the film to rank 0.
+ * If the communicator is attached BEFORE cpbrt_build_bvh, scenes of >= 65536 primitives are built once,
+ * on rank 0, and broadcast to the other ranks (every rank must then call cpbrt_build_bvh; the node dump
+ * is only available on rank 0). */
 #define CPBRT_COMM_ID_BYTES 128
 int cpbrt_comm_unique_id(uint8_t id_bytes_out[CPBRT_COMM_ID_BYTES]);
 int cpbrt_comm_init(cpbrt_ctx* ctx, int n_ranks, int rank, const uint8_t id_bytes[CPBRT_COMM_ID_BYTES]);

@@ -37,6 +37,28 @@ def main():
         err = np.abs(film - ref) / (np.abs(ref) + 1e-3)
         ok = bool(err.max() < 1e-4) and int(total.item()) == 160 * 120 * 16
         print("multi-gpu check: ranks=%d max rel err=%.3g samples=%d reduce_ms=%.3f -> %s" % (world, err.max(), int(total.item()), st.ms_reduce, "OK" if ok else "FAIL"))
+    # second phase: communicator attached BEFORE the build -> rank 0 builds, the others receive the
+    # finished BVH by ncclBroadcast (forced here; by default only scenes of >= 65536 primitives share)
+    os.environ["CPBRT_BVH_SHARE"] = "1"
+    r2 = cpbrt.Renderer(local); r2.upload(scene)
+    idt2 = torch.zeros(cpbrt.abi.COMM_ID_BYTES, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt2.copy_(torch.tensor(list(cpbrt.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt2, 0)
+    r2.comm_init(world, rank, bytes(idt2.cpu().tolist()))
+    order2 = r2.build_bvh()
+    o = torch.from_numpy(order2.astype(np.int64)).cuda()
+    o0 = o.clone(); dist.broadcast(o0, 0)
+    same_order = torch.tensor([1.0 if bool((o == o0).all()) else 0.0], device="cuda")
+    dist.all_reduce(same_order, op=dist.ReduceOp.MIN)
+    film2, _ = r2.render()
+    ok2 = True
+    if rank == 0:
+        err2 = np.abs(film2 - ref) / (np.abs(ref) + 1e-3)
+        ok2 = bool(err2.max() < 1e-4) and same_order.item() == 1.0 and np.array_equal(film2.view(np.uint32), film.view(np.uint32))
+        print("shared-build check: same order on all ranks=%s, max rel err=%.3g, film identical to the replicated-build run=%s -> %s" % (
+            same_order.item() == 1.0, err2.max(), np.array_equal(film2.view(np.uint32), film.view(np.uint32)), "OK" if ok2 else "FAIL"))
+    ok = ok and ok2
     dist.barrier()
     dist.destroy_process_group()
     return 0 if ok else 1
