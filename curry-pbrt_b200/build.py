@@ -33,13 +33,6 @@ def _deps():
     return deps
 
 
-def _stale(target, deps):
-    if not os.path.exists(target):
-        return True
-    t = os.path.getmtime(target)
-    return any(os.path.getmtime(d) > t for d in deps)
-
-
 # which headers each CUDA translation unit depends on (besides itself and include/cpbrt.h)
 CUDA_DEPS = {
     "cpbrt_api.cu": ["device", "bvh_build.h"],
@@ -69,28 +62,65 @@ def _compile_cuda(src, obj, verbose):
         sys.stderr.write(r.stderr)
 
 
+def _fingerprint(paths, extra=""):
+    """Content hash of the sources: staleness must not depend on file times (a snapshot copied to
+    another machine keeps contents, not necessarily mtimes)."""
+    import hashlib
+    h = hashlib.sha256(extra.encode())
+    for p in sorted(os.path.abspath(x) for x in paths):
+        if os.path.isfile(p) and not p.endswith((".pyc",)):
+            h.update(os.path.relpath(p, HERE).encode())
+            with open(p, "rb") as f:
+                h.update(f.read())
+    return h.hexdigest()
+
+
+def _read(path):
+    try:
+        with open(path) as f:
+            return f.read().strip()
+    except OSError:
+        return ""
+
+
 def build(force=False, verbose=False):
-    deps = _deps()
-    if not force and not _stale(OUT, deps):
-        return OUT
+    """Idempotent and safe to call from several processes at once (torchrun ranks): one holds the
+    lock and builds, the others wait and find the library up to date."""
+    import fcntl
     os.makedirs(OBJ, exist_ok=True)
-    objs = []
-    # CUDA translation units in parallel threads (nvcc is a subprocess), each only when it is stale
-    from concurrent.futures import ThreadPoolExecutor
-    jobs = []
-    with ThreadPoolExecutor(max_workers=len(CUDA_SOURCES)) as pool:
-        for src in CUDA_SOURCES:
-            o = os.path.join(OBJ, src.replace("/", "_") + ".o")
-            if force or _stale(o, _unit_deps(src)):
-                jobs.append(pool.submit(_compile_cuda, src, o, verbose))
-            objs.append(o)
-        for src in HOST_SOURCES:
-            o = os.path.join(OBJ, src.replace("/", "_") + ".o")
-            subprocess.check_call(HOST_CXX + ["-c", os.path.join(CSRC, src), "-o", o])
-            objs.append(o)
-        for j in jobs:
-            j.result()
-    subprocess.check_call([NVCC, "-shared", "-o", OUT] + objs + ["-lz", "-ldl", "-lpthread", "-cudart", "static"])
+    flags = " ".join(NVCC_FLAGS + HOST_CXX)
+    want = _fingerprint(_deps(), flags)
+    stamp = os.path.join(OBJ, "libcpbrt.stamp")
+    if not force and os.path.exists(OUT) and _read(stamp) == want:
+        return OUT
+    with open(os.path.join(OBJ, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and os.path.exists(OUT) and _read(stamp) == want:
+            return OUT
+        objs = []
+        # CUDA translation units in parallel threads (nvcc is a subprocess), each only when its inputs changed
+        from concurrent.futures import ThreadPoolExecutor
+        jobs = []
+        with ThreadPoolExecutor(max_workers=len(CUDA_SOURCES)) as pool:
+            for src in CUDA_SOURCES:
+                o = os.path.join(OBJ, src.replace("/", "_") + ".o")
+                unit = _fingerprint(_unit_deps(src), flags)
+                if force or not os.path.exists(o) or _read(o + ".stamp") != unit:
+                    jobs.append((pool.submit(_compile_cuda, src, o, verbose), o, unit))
+                objs.append(o)
+            for src in HOST_SOURCES:
+                o = os.path.join(OBJ, src.replace("/", "_") + ".o")
+                subprocess.check_call(HOST_CXX + ["-c", os.path.join(CSRC, src), "-o", o])
+                objs.append(o)
+            for j, o, unit in jobs:
+                j.result()
+                with open(o + ".stamp", "w") as f:
+                    f.write(unit)
+        tmp = OUT + ".tmp.%d" % os.getpid()
+        subprocess.check_call([NVCC, "-shared", "-o", tmp] + objs + ["-lz", "-ldl", "-lpthread", "-cudart", "static"])
+        os.replace(tmp, OUT)
+        with open(stamp, "w") as f:
+            f.write(want)
     return OUT
 
 

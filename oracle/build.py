@@ -13,11 +13,38 @@ SRC = [os.path.join(HERE, "oracle.cpp")]
 DEPS = SRC + [os.path.join(HERE, "oracle_math.h"), os.path.join(HERE, "..", "include", "cpbrt.h")]
 
 
+def _fingerprint():
+    import hashlib
+    h = hashlib.sha256()
+    for p in DEPS:
+        with open(p, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def build(force=False):
-    if not force and os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in DEPS):
+    """Content-stamped and locked: safe to call from several processes at once, independent of file times."""
+    import fcntl
+    stamp = OUT + ".stamp"
+    want = _fingerprint()
+
+    def fresh():
+        try:
+            return os.path.exists(OUT) and open(stamp).read().strip() == want
+        except OSError:
+            return False
+    if not force and fresh():
         return OUT
-    subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-pthread",
-                           "-Wall", "-Wextra"] + SRC + ["-o", OUT])
+    with open(os.path.join(HERE, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and fresh():
+            return OUT
+        tmp = OUT + ".tmp.%d" % os.getpid()
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-pthread",
+                               "-Wall", "-Wextra"] + SRC + ["-o", tmp])
+        os.replace(tmp, OUT)
+        with open(stamp, "w") as f:
+            f.write(want)
     return OUT
 
 
