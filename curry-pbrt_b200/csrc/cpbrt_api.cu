@@ -794,8 +794,7 @@ int cpbrt_render(cpbrt_ctx* ctx, const cpbrt_render_params* params, float* film_
     uint32_t s_begin = rp.sample_begin, s_end = rp.sample_end;
     if (s_begin == 0 && s_end == 0) {
         // whole job, or this rank's contiguous share of the sample indices
-        s_begin = (uint32_t)((uint64_t)spp * ctx->rank / ctx->n_ranks);
-        s_end = (uint32_t)((uint64_t)spp * (ctx->rank + 1) / ctx->n_ranks);
+        cpbrt_sample_share(spp, ctx->rank, ctx->n_ranks, &s_begin, &s_end);
     }
     if (s_end > spp || s_begin > s_end) return ctx->fail(CPBRT_ERR_BAD_ARG, "sample range [%u,%u) outside [0,%u)", s_begin, s_end, spp);
     const bool root = ctx->rank == 0;

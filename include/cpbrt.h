@@ -329,6 +329,11 @@ int cpbrt_host_build_bvh(const cpbrt_scene_desc* desc, uint32_t* prim_order_out,
  * 1442695040888963407); stands in for the reference's thread_rng shuffle (halton.rs:216-231). */
 void cpbrt_make_permutation(uint64_t seed, uint16_t* out /* CPBRT_PERM_TABLE_LEN */);
 
+/* The contiguous range [*begin, *end) of sample indices rank `rank` of `n_ranks` renders when cpbrt_render is
+ * called without an explicit range.  The shares tile [0, spp) and shrink slightly with the rank: a rank that
+ * starts at sample s first replays the film-point drift of the s samples before it (src/render.rs:26-31). */
+void cpbrt_sample_share(uint32_t spp, int rank, int n_ranks, uint32_t* begin, uint32_t* end);
+
 /* Film::write_image (src/film.rs:35-38 -> src/texture/image.rs:108-127): gamma_correct,
  * clamp(v*255+0.5,0,255) as u8, RGB8 PNG. */
 int cpbrt_write_png(const char* path, const float* film_rgb, uint32_t width, uint32_t height);
