@@ -129,6 +129,18 @@ float host_tri_area(const float p[9]) {   // triangle.rs:110-113
     return 0.5f * sqrtf((c[0] * c[0] + c[1] * c[1]) + c[2] * c[2]);
 }
 
+// Triangle::normal (triangle.rs:78-82): normalize(cross(p0 - p2, p1 - p2)), normalized once more by Normal3f::from;
+// nalgebra's dot is (x*x + y*y) + z*z and normalize divides each component by the norm
+void host_tri_normal(const float p[9], float out[3]) {
+    const float a[3] = {p[0] - p[6], p[1] - p[7], p[2] - p[8]}, b[3] = {p[3] - p[6], p[4] - p[7], p[5] - p[8]};
+    float c[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+    for (int pass = 0; pass < 2; ++pass) {
+        const float len = sqrtf((c[0] * c[0] + c[1] * c[1]) + c[2] * c[2]);
+        c[0] = c[0] / len; c[1] = c[1] / len; c[2] = c[2] / len;
+    }
+    out[0] = c[0]; out[1] = c[1]; out[2] = c[2];
+}
+
 uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 
@@ -323,7 +335,7 @@ int cpbrt_upload_scene(cpbrt_ctx* ctx, const cpbrt_scene_desc* d) {
             memcpy(o.v, s.v, 12); memcpy(o.L, s.L, 12); o.tex = s.tex;
             if (s.type == CPBRT_LIGHT_AREA) {
                 if (s.shape.kind == CPBRT_SHAPE_SPHERE) { o.radius = d->sphere_radius[s.shape.data]; o.area = o.radius * o.radius * 3.14159265358979323846f * 4.f; }   // sphere.rs:106-108
-                else { memcpy(o.tri, d->triangles[s.shape.data].p, 36); o.area = host_tri_area(o.tri); }
+                else { memcpy(o.tri, d->triangles[s.shape.data].p, 36); o.area = host_tri_area(o.tri); host_tri_normal(o.tri, o.tri_n); }
             }
         }
         for (auto& l : L) l.slot = 0xFFFFFFFFu;

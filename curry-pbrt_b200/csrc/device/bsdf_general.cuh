@@ -211,6 +211,9 @@ struct GBSDF {   // BSDF (bxdf/mod.rs:71-270)
         return normalize(v3((snx.x * w.x + sny.x * w.y) + sn.x * w.z, (snx.y * w.x + sny.y * w.y) + sn.y * w.z, (snx.z * w.x + sny.z * w.y) + sn.z * w.z));
     }
     CP_DEV V3 world_to_local(V3 w) const { return normalize(v3(dot(w, snx), dot(w, sny), dot(w, sn))); }
+    // wo in the local frame: every sampling / evaluation routine below needs it, computed once per hit (set_wo)
+    V3 wo_local;
+    CP_DEV void set_wo(V3 wo) { wo_local = world_to_local(wo); }
 
     CP_DEV GLobe* add_lobe(int kind, Spec r) {
         if (n_lobes == kMaxLobes) { overflow = true; return &lobes[kMaxLobes - 1]; }
@@ -236,7 +239,7 @@ struct GBSDF {   // BSDF (bxdf/mod.rs:71-270)
         const float tr = truncf(fl), remap = fl - tr;
         const uint32_t index = min(f32_to_u32_sat(tr), (uint32_t)n_lobes - 1);
         P2 u2; u2.x = remap; u2.y = u.y;
-        const V3 wo_l = world_to_local(wo); V3 wi_l; float p;
+        const V3 wo_l = wo_local; V3 wi_l; float p;
         const bool has = lobes[index].sample_f(wo_l, u2, &wi_l, f, &p);
         *wi = local_to_world(wi_l);
         *pdf = p / (float)n_lobes;
@@ -246,7 +249,7 @@ struct GBSDF {   // BSDF (bxdf/mod.rs:71-270)
     CP_DEV bool sample_delta_f(V3 wo, float u, V3* wi, Spec* f, float* pdf) const {
         *wi = v3(0.f, 0.f, 0.f); *pdf = 0.f;
         if (n_deltas == 0) return false;
-        const V3 wo_l = world_to_local(wo);
+        const V3 wo_l = wo_local;
         V3 w[kMaxLobes]; Spec s[kMaxLobes]; float lm[kMaxLobes]; int cnt = 0;
         for (int i = 0; i < n_deltas; ++i) { if (deltas[i].sample_f(wo_l, &w[cnt], &s[cnt])) { lm[cnt] = lum(s[cnt]); ++cnt; } }
         if (cnt == 0) return false;   // the reference panics on an empty table
@@ -259,7 +262,7 @@ struct GBSDF {   // BSDF (bxdf/mod.rs:71-270)
     // transmissive ones otherwise; pdf = mean of the default pdfs over that subset
     CP_DEV bool no_delta_f_pdf(V3 wo_w, V3 wi_w, Spec* f, float* pdf) const {
         if (n_lobes == 0) { *pdf = 0.f; return false; }
-        const V3 wo = world_to_local(wo_w), wi = world_to_local(wi_w);
+        const V3 wo = wo_local, wi = world_to_local(wi_w);
         const bool reflect = dot(wo, n) * dot(wi, n) > 0.f;
         bool has = false; Spec acc = spec(0.f); float p = 0.f; int len = 0;
         for (int i = 0; i < n_lobes; ++i) {

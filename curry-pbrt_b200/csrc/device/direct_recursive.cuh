@@ -96,9 +96,10 @@ CP_DEV void direct_visit(const DevScene& sc, const Ray& ray, uint32_t depth, Sam
     build_general_bsdf(sc, src, sp, bsdf);
     if (bsdf.overflow) *bsdf_overflow = 1;
     const V3 wo = -normalize(ray.d);
+    bsdf.set_wo(wo);
     fr.l = fr.l + uniform_sample_one_light_inline(sc, sp, bsdf, wo, st, rc, overflow);
     if (depth + 1 < sc.max_depth) {
-        const V3 wo_l = bsdf.world_to_local(wo);
+        const V3 wo_l = bsdf.wo_local;
         for (int i = 0; i < bsdf.n_deltas; ++i) {      // sample_all_delta_f
             V3 wi_l; Spec s;
             if (!bsdf.deltas[i].sample_f(wo_l, &wi_l, &s)) continue;

@@ -35,6 +35,7 @@ struct DevLight {
     float v[3]; float L[3];
     int32_t tex;
     float tri[9];        // AREA + triangle: object-space vertices
+    float tri_n[3];      // ... and Triangle::normal of them (triangle.rs:78-82), computed once on the host with the same f32 operations
     float radius;        // AREA + sphere
     float area;          // Shape::area of the light's shape
     uint32_t slot;       // AREA: BVH slot of the one primitive that carries this light, 0xFFFFFFFF if none or several

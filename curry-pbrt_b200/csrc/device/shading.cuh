@@ -116,6 +116,9 @@ struct BSDF {
         return normalize(v3((snx.x * w.x + sny.x * w.y) + sn.x * w.z, (snx.y * w.x + sny.y * w.y) + sn.y * w.z, (snx.z * w.x + sny.z * w.y) + sn.z * w.z));
     }
     CP_DEV V3 world_to_local(V3 w) const { return normalize(v3(dot(w, snx), dot(w, sny), dot(w, sn))); }
+    // wo in the local frame: every sampling / evaluation routine below needs it, computed once per hit (set_wo)
+    V3 wo_local;
+    CP_DEV void set_wo(V3 wo) { wo_local = world_to_local(wo); }
 
     // sample_no_delta_f (bxdf/mod.rs:136-159)
     CP_DEV bool sample_no_delta_f(V3 wo, P2 u, V3* wi, Spec* f, float* pdf) const {
@@ -124,7 +127,7 @@ struct BSDF {
         float tr = truncf(fl), remap = fl - tr;
         uint32_t index = min(f32_to_u32_sat(tr), (uint32_t)n_lobes - 1);
         P2 u2; u2.x = remap; u2.y = u.y;
-        V3 wo_l = world_to_local(wo), wi_l; float p;
+        V3 wo_l = wo_local, wi_l; float p;
         lobe_sample_f(lobes[NL == 1 ? 0 : index], wo_l, u2, &wi_l, f, &p);
         *wi = local_to_world(wi_l);
         *pdf = p / (float)n_lobes;
@@ -133,7 +136,7 @@ struct BSDF {
     // sample_delta_f (bxdf/mod.rs:160-175)
     CP_DEV bool sample_delta_f(V3 wo, float u, V3* wi, Spec* f, float* pdf) const {
         if (ND == 0 || n_deltas == 0) { *wi = v3(0.f, 0.f, 0.f); *pdf = 0.f; return false; }
-        V3 wo_l = world_to_local(wo);
+        V3 wo_l = wo_local;
         V3 w[ND > 0 ? ND : 1]; Spec s[ND > 0 ? ND : 1]; float lm[ND > 0 ? ND : 1]; int cnt = 0;
 #pragma unroll
         for (int i = 0; i < ND; ++i) if (i < n_deltas) { V3 wi_l; Spec si; if (delta_sample_f(deltas[i], wo_l, &wi_l, &si)) { w[cnt] = wi_l; s[cnt] = si; lm[cnt] = lum(si); ++cnt; } }
@@ -149,7 +152,7 @@ struct BSDF {
     // no_delta_f_pdf (bxdf/mod.rs:176-198); all supported non-delta lobes are reflective
     CP_DEV bool no_delta_f_pdf(V3 wo_w, V3 wi_w, Spec* f, float* pdf) const {
         if (NL == 0 || n_lobes == 0) { *pdf = 0.f; return false; }
-        V3 wo = world_to_local(wo_w), wi = world_to_local(wi_w);
+        V3 wo = wo_local, wi = world_to_local(wi_w);
         bool reflect = dot(wo, n) * dot(wi, n) > 0.f;
         if (!reflect) { *pdf = 0.f / 0.f; return false; }   // empty transmit list: f = None
         Spec acc = spec(0.f); float p = 0.f;
@@ -189,7 +192,7 @@ CP_DEV void bare_sample(const DevScene& sc, const DevLight& l, SamplerState& st,
         TriVerts t = light_tri(l);
         P2 b = uniform_sample_triangle(sampler_get_2d(sc.sampler, st));
         float b0 = b.x, b1 = b.y, b2 = 1.f - b.x - b.y;
-        sp->p = tri_point(t, b0, b1, b2); sp->n = tri_normal(t); sp->uv = tri_uv(nullptr, b0, b1, b2);
+        sp->p = tri_point(t, b0, b1, b2); sp->n = v3(l.tri_n[0], l.tri_n[1], l.tri_n[2]); sp->uv = tri_uv(nullptr, b0, b1, b2);
         sp->p_error = gamma_n(6) * tri_abs_sum(t, b0, b1, b2);
     }
     *pdf = 1.f / l.area;

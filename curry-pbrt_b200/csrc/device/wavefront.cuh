@@ -510,6 +510,7 @@ __global__ void __launch_bounds__(128, ShadeBlocks<KIND>::value) k_shade(DevScen
             } else {
                 wo = -normalize(ray.d);
             }
+            bsdf.set_wo(wo);
         }
         // direct lighting: the path integrator skips it for all-delta BSDFs (path.rs:37),
         // the direct-lighting integrator does not (direct_light.rs:25)
