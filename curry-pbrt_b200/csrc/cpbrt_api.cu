@@ -83,7 +83,7 @@ struct cpbrt_ctx {
     std::vector<DevLight> host_lights;
 
     DevScene scene;   // by-value kernel argument
-    DevBuf d_prims, d_prim_uv, d_nodes, d_env, d_transforms, d_materials, d_textures, d_texels, d_lights, d_perm, d_primes, d_primsum, d_magic;
+    DevBuf d_prims, d_prim_uv, d_nodes, d_env, d_transforms, d_materials, d_textures, d_texels, d_lights, d_perm, d_primes, d_primsum, d_magic, d_halton_dims, d_halton_inv_pow;
 
     // wavefront state
     uint32_t path_capacity = 0;
@@ -195,7 +195,7 @@ void cpbrt_destroy(cpbrt_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     DevBuf* bufs[] = {&ctx->d_prims, &ctx->d_prim_uv, &ctx->d_nodes, &ctx->d_env, &ctx->d_transforms, &ctx->d_materials, &ctx->d_textures, &ctx->d_texels,
-                      &ctx->d_lights, &ctx->d_perm, &ctx->d_primes, &ctx->d_primsum, &ctx->d_magic, &ctx->d_path, &ctx->d_kind, &ctx->d_queues, &ctx->d_counts,
+                      &ctx->d_lights, &ctx->d_perm, &ctx->d_primes, &ctx->d_primsum, &ctx->d_magic, &ctx->d_halton_dims, &ctx->d_halton_inv_pow, &ctx->d_path, &ctx->d_kind, &ctx->d_queues, &ctx->d_counts,
                       &ctx->d_pixels, &ctx->d_totals_buf, &ctx->d_film_out};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < 6; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -388,12 +388,31 @@ int cpbrt_upload_scene(cpbrt_ctx* ctx, const cpbrt_scene_desc* d) {
         for (int i = 0; i < CPBRT_N_PRIMES; ++i) magic[i] = 0xFFFFFFFFFFFFFFFFull / primes[i] + 1;   // floor(2^64/p)+1 (p never divides 2^64)
         if (int rc = alloc_upload(ctx, ctx->d_magic, magic.data(), magic.size() * 8)) return rc;
         if (int rc = alloc_upload(ctx, ctx->d_perm, d->sampler.permutation, (size_t)CPBRT_PERM_TABLE_LEN * 2)) return rc;
+        // Per-dimension constants of scrambled_radical_inverse (halton.rs:56-64), evaluated once here with the
+        // reference's f32 operations instead of per sample on the device:
+        //   tail[d]       = inv_base * perm_d(0) / (1 - inv_base)        (the infinite tail of permuted zero digits)
+        //   inv_pow[d][c] = 1 / (base^c as f32)                           (usize pow, wrapping like release Rust)
+        {
+            std::vector<DevHaltonDim> dims(CPBRT_N_PRIMES);
+            std::vector<float> inv_pow((size_t)CPBRT_N_PRIMES * kHaltonMaxDigits);
+            for (int i = 0; i < CPBRT_N_PRIMES; ++i) {
+                const float inv_base = 1.f / (float)primes[i];
+                dims[i].magic = magic[i]; dims[i].base = primes[i]; dims[i].primsum = sums[i];
+                dims[i].tail = inv_base * (float)d->sampler.permutation[sums[i]] / (1.f - inv_base);
+                dims[i].pad[0] = dims[i].pad[1] = dims[i].pad[2] = 0;
+                uint64_t pw = 1;
+                for (int c = 0; c < kHaltonMaxDigits; ++c) { inv_pow[(size_t)i * kHaltonMaxDigits + c] = 1.f / (float)pw; pw *= primes[i]; }
+            }
+            if (int rc = alloc_upload(ctx, ctx->d_halton_dims, dims.data(), dims.size() * sizeof(DevHaltonDim))) return rc;
+            if (int rc = alloc_upload(ctx, ctx->d_halton_inv_pow, inv_pow.data(), inv_pow.size() * 4)) return rc;
+        }
         DevSampler& sm = S.sampler;
         sm.spp = d->sampler.spp;
         for (int i = 0; i < 2; ++i) { sm.exp[i] = d->sampler.exp[i]; sm.scale[i] = d->sampler.scale[i]; sm.mult_inverse[i] = d->sampler.mult_inverse[i]; }
         sm.stride = sm.scale[0] * sm.scale[1];
         if (sm.scale[0] != (1ull << sm.exp[0])) return ctx->fail(CPBRT_ERR_BAD_ARG, "sampler.scale[0] must be 2^exp[0]");
         sm.permutation = (const uint16_t*)ctx->d_perm.p; sm.primes = (const uint32_t*)ctx->d_primes.p; sm.primsum = (const uint32_t*)ctx->d_primsum.p; sm.prime_magic = (const uint64_t*)ctx->d_magic.p;
+        sm.dims = (const DevHaltonDim*)ctx->d_halton_dims.p; sm.inv_pow = (const float*)ctx->d_halton_inv_pow.p;
     }
     S.transforms = (const DevTransform*)ctx->d_transforms.p;
     S.materials = (const DevMaterial*)ctx->d_materials.p;

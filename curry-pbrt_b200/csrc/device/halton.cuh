@@ -36,20 +36,23 @@ CP_DEV float radical_inverse(uint64_t x, uint32_t base) {
 // division by the prime is one 64-bit multiply-high with floor(2^64/p)+1, which is exact for
 // x < 2^32 and p < 2^13 (error term x / 2^64 < 1 / p); same quotients, same digits.
 CP_DEV float scrambled_radical_inverse(const DevSampler& S, uint64_t x, uint32_t dim) {
-    const uint32_t base = __ldg(&S.primes[dim]);
-    const uint64_t magic = __ldg(&S.prime_magic[dim]);
-    const uint16_t* __restrict__ pm = S.permutation + __ldg(&S.primsum[dim]);
-    uint64_t acc = 0, pw = 1;
-    while ((x >> 32) != 0) { uint64_t q = x / base; uint32_t digit = (uint32_t)(x - q * base); acc = acc * base + __ldg(&pm[digit]); pw *= base; x = q; }
+    const float4* rec = reinterpret_cast<const float4*>(S.dims + dim);
+    const float4 r0 = __ldg(rec), r1 = __ldg(rec + 1);
+    const uint64_t magic = ((uint64_t)__float_as_uint(r0.y) << 32) | __float_as_uint(r0.x);
+    const uint32_t base = __float_as_uint(r0.z);
+    const uint16_t* __restrict__ pm = S.permutation + __float_as_uint(r0.w);
+    const float tail = r1.x;
+    uint64_t acc = 0; uint32_t count = 0;
+    while ((x >> 32) != 0) { uint64_t q = x / base; uint32_t digit = (uint32_t)(x - q * base); acc = acc * base + __ldg(&pm[digit]); ++count; x = q; }
     uint32_t xs = (uint32_t)x;
     while (xs != 0) {
         const uint32_t q = (uint32_t)__umul64hi((uint64_t)xs, magic);
         const uint32_t digit = xs - q * base;
-        acc = acc * base + __ldg(&pm[digit]); pw *= base; xs = q;
+        acc = acc * base + __ldg(&pm[digit]); ++count; xs = q;
     }
-    float inv_base_n = 1.f / __ull2float_rn(pw);
-    float inv_base = 1.f / (float)base;
-    return inv_base_n * (__ull2float_rn(acc) + inv_base * (float)__ldg(&pm[0]) / (1.f - inv_base));
+    // inv_base_n and the tail of permuted zero digits were evaluated on the host with the same f32 operations
+    const float inv_base_n = __ldg(&S.inv_pow[dim * kHaltonMaxDigits + count]);
+    return inv_base_n * (__ull2float_rn(acc) + tail);
 }
 
 // set_pixel (halton.rs:108-119) with inverse_exp (halton.rs:48-55)

@@ -55,6 +55,16 @@ struct DevCamera {
     float lens_radius, focal_distance;
 };
 
+// one 32-byte record per Halton dimension (two 16-byte loads): everything scrambled_radical_inverse needs
+struct DevHaltonDim {
+    uint64_t magic;      // floor(2^64 / base) + 1: x / base == umul64hi(x, magic) exactly for x < 2^32
+    uint32_t base;       // PRIMS[d]
+    uint32_t primsum;    // offset of the dimension's permutation block
+    float tail;          // inv_base * perm(0) / (1 - inv_base), evaluated on the host in f32 (halton.rs:61-63)
+    uint32_t pad[3];
+};
+static constexpr int kHaltonMaxDigits = 32;   // base >= 5 from dimension 2 on: at most 28 digits in 64 bits
+
 struct DevSampler {
     uint32_t spp;
     uint32_t exp[2];
@@ -65,6 +75,8 @@ struct DevSampler {
     const uint32_t* primes;          // first 1000 primes
     const uint32_t* primsum;
     const uint64_t* prime_magic;     // floor(2^64 / p) + 1: x / p == umul64hi(x, magic) exactly for x < 2^32
+    const DevHaltonDim* dims;        // the same per-dimension data gathered in one record
+    const float* inv_pow;            // [dim][digit count] = 1 / (base^count as f32)
 };
 
 struct DevScene {
