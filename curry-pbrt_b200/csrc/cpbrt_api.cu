@@ -83,7 +83,7 @@ struct cpbrt_ctx {
     std::vector<DevLight> host_lights;
 
     DevScene scene;   // by-value kernel argument
-    DevBuf d_prims, d_prim_uv, d_nodes, d_env, d_transforms, d_materials, d_textures, d_texels, d_lights, d_perm, d_primes, d_primsum, d_magic, d_halton_dims, d_halton_inv_pow;
+    DevBuf d_prims, d_prim_uv, d_prim_frame, d_nodes, d_env, d_transforms, d_materials, d_textures, d_texels, d_lights, d_perm, d_primes, d_primsum, d_magic, d_halton_dims, d_halton_inv_pow;
 
     // wavefront state
     uint32_t path_capacity = 0;
@@ -141,6 +141,23 @@ void host_tri_normal(const float p[9], float out[3]) {
     out[0] = c[0]; out[1] = c[1]; out[2] = c[2];
 }
 
+// Triangle::normal plus the frame BSDF::new(n, n) derives from it (bxdf/mod.rs:83-97): snx, sny from
+// coordinate_system (math/mod.rs:67-74), n in that frame (normalised).  Layout: DevScene::prim_frame.
+void host_tri_frame(const float p[9], float4 out[3]) {
+    float n[3];
+    host_tri_normal(p, n);
+    float x[3], y[3];
+    if (fabsf(n[0]) > fabsf(n[1])) { const float l = sqrtf(n[0] * n[0] + n[2] * n[2]); x[0] = -n[2] / l; x[1] = 0.f / l; x[2] = n[0] / l; }
+    else { const float l = sqrtf(n[1] * n[1] + n[2] * n[2]); x[0] = 0.f / l; x[1] = n[2] / l; x[2] = -n[1] / l; }
+    y[0] = n[1] * x[2] - n[2] * x[1]; y[1] = n[2] * x[0] - n[0] * x[2]; y[2] = n[0] * x[1] - n[1] * x[0];
+    float nl[3] = {(n[0] * x[0] + n[1] * x[1]) + n[2] * x[2], (n[0] * y[0] + n[1] * y[1]) + n[2] * y[2], (n[0] * n[0] + n[1] * n[1]) + n[2] * n[2]};
+    const float len = sqrtf((nl[0] * nl[0] + nl[1] * nl[1]) + nl[2] * nl[2]);
+    nl[0] = nl[0] / len; nl[1] = nl[1] / len; nl[2] = nl[2] / len;
+    out[0] = make_float4(n[0], n[1], n[2], x[0]);
+    out[1] = make_float4(x[1], x[2], y[0], y[1]);
+    out[2] = make_float4(y[2], nl[0], nl[1], nl[2]);
+}
+
 uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 
@@ -194,7 +211,7 @@ void cpbrt_destroy(cpbrt_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
-    DevBuf* bufs[] = {&ctx->d_prims, &ctx->d_prim_uv, &ctx->d_nodes, &ctx->d_env, &ctx->d_transforms, &ctx->d_materials, &ctx->d_textures, &ctx->d_texels,
+    DevBuf* bufs[] = {&ctx->d_prims, &ctx->d_prim_uv, &ctx->d_prim_frame, &ctx->d_nodes, &ctx->d_env, &ctx->d_transforms, &ctx->d_materials, &ctx->d_textures, &ctx->d_texels,
                       &ctx->d_lights, &ctx->d_perm, &ctx->d_primes, &ctx->d_primsum, &ctx->d_magic, &ctx->d_halton_dims, &ctx->d_halton_inv_pow, &ctx->d_path, &ctx->d_kind, &ctx->d_queues, &ctx->d_counts,
                       &ctx->d_pixels, &ctx->d_totals_buf, &ctx->d_film_out};
     for (DevBuf* b : bufs) b->release();
@@ -461,6 +478,7 @@ static int exchange_bvh(cpbrt_ctx* ctx, uint32_t n, bool any_uv, const uint32_t*
             any_uv = h.any_uv != 0;
             rc = alloc_upload(ctx, ctx->d_prims, nullptr, 3ull * n * sizeof(float4));
             if (!rc) rc = alloc_upload(ctx, ctx->d_prim_uv, nullptr, any_uv ? 6ull * n * 4 : 0);
+            if (!rc) rc = alloc_upload(ctx, ctx->d_prim_frame, nullptr, 3ull * n * sizeof(float4));
             if (!rc) rc = alloc_upload(ctx, ctx->d_nodes, nullptr, 4ull * h.n_nodes * sizeof(float4));
             if (!rc) rc = alloc_upload(ctx, ctx->d_lights, ctx->host_lights.data(), ctx->host_lights.size() * sizeof(DevLight));
         }
@@ -468,6 +486,7 @@ static int exchange_bvh(cpbrt_ctx* ctx, uint32_t n, bool any_uv, const uint32_t*
     if (!rc) rc = alloc_upload(ctx, d_order, root ? order_host : nullptr, (size_t)n * 4);
     if (!rc) rc = bcast(ctx, ctx->d_prims.p, 3ull * n * sizeof(float4));
     if (!rc && any_uv) rc = bcast(ctx, ctx->d_prim_uv.p, 6ull * n * 4);
+    if (!rc) rc = bcast(ctx, ctx->d_prim_frame.p, 3ull * n * sizeof(float4));
     if (!rc) rc = bcast(ctx, ctx->d_nodes.p, 4ull * S.n_nodes * sizeof(float4));
     if (!rc) rc = bcast(ctx, ctx->d_lights.p, ctx->host_lights.size() * sizeof(DevLight));
     if (!rc) rc = bcast(ctx, d_order.p, (size_t)n * 4);
@@ -481,6 +500,7 @@ static int exchange_bvh(cpbrt_ctx* ctx, uint32_t n, bool any_uv, const uint32_t*
     if (!rc && !root) {
         S.prims = (const float4*)ctx->d_prims.p;
         S.prim_uv = any_uv ? (const float*)ctx->d_prim_uv.p : nullptr;
+        S.prim_frame = n ? (const float4*)ctx->d_prim_frame.p : nullptr;
         S.nodes = (const float4*)ctx->d_nodes.p;
         S.lights = (const DevLight*)ctx->d_lights.p;
     }
@@ -543,6 +563,7 @@ int cpbrt_build_bvh(cpbrt_ctx* ctx, uint32_t* prim_order_out, cpbrt_bvh_dump* du
         }
     }
     std::vector<float> uvs(any_uv ? 6ull * n : 0);
+    std::vector<float4> frames(3ull * n);
     parallel_for(n, 1 << 16, [&](uint64_t slot_lo, uint64_t slot_hi) {
     for (uint32_t slot = (uint32_t)slot_lo; slot < (uint32_t)slot_hi; ++slot) {
         const uint32_t up = R.order[slot];
@@ -556,6 +577,7 @@ int cpbrt_build_bvh(cpbrt_ctx* ctx, uint32_t* prim_order_out, cpbrt_bvh_dump* du
             q1 = make_float4(t.p[1][1], t.p[1][2], t.p[2][0], t.p[2][1]);
             q2.x = t.p[2][2];
             if (any_uv) { meta |= kMetaHasUv; memcpy(&uvs[6ull * slot], t.uv, 24); }
+            host_tri_frame(&t.p[0][0], &frames[3ull * slot]);
         }
         q2.y = u2f(up); q2.z = u2f(meta);
         q2.w = u2f(p.material >= 0 ? (uint32_t)p.material : (kSourceLight | (uint32_t)p.light));
@@ -565,6 +587,7 @@ int cpbrt_build_bvh(cpbrt_ctx* ctx, uint32_t* prim_order_out, cpbrt_bvh_dump* du
     lap("primitive records");
     if (int rc = alloc_upload(ctx, ctx->d_prims, prims.data(), prims.size() * sizeof(float4))) return rc;
     if (int rc = alloc_upload(ctx, ctx->d_prim_uv, any_uv ? uvs.data() : nullptr, uvs.size() * 4)) return rc;
+    if (int rc = alloc_upload(ctx, ctx->d_prim_frame, frames.data(), frames.size() * sizeof(float4))) return rc;
 
     // Parent nodes in depth-first order, far... the device layout (see scene_dev.cuh)
     DevScene& S = ctx->scene;
@@ -629,6 +652,7 @@ int cpbrt_build_bvh(cpbrt_ctx* ctx, uint32_t* prim_order_out, cpbrt_bvh_dump* du
     }
     S.prims = (const float4*)ctx->d_prims.p;
     S.prim_uv = any_uv ? (const float*)ctx->d_prim_uv.p : nullptr;
+    S.prim_frame = n ? (const float4*)ctx->d_prim_frame.p : nullptr;
     S.nodes = (const float4*)ctx->d_nodes.p;
     CU(cudaStreamSynchronize(ctx->stream));
     if (shared) { if (int rc = exchange_bvh(ctx, n, any_uv, R.order.data(), nullptr)) return rc; lap("broadcast to the other ranks"); }

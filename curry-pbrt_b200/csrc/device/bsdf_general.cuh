@@ -207,6 +207,12 @@ struct GBSDF {   // BSDF (bxdf/mod.rs:71-270)
         n = normalize(v3(dot(normal, snx), dot(normal, sny), dot(normal, sn)));
         n_lobes = 0; n_deltas = 0; overflow = false;
     }
+    CP_DEV void init_frame(const float4* __restrict__ f) { load_frame(f); n_lobes = 0; n_deltas = 0; overflow = false; }
+    // the same frame read from DevScene::prim_frame (host-evaluated, see scene_dev.cuh)
+    CP_DEV void load_frame(const float4* __restrict__ f) {
+        const float4 f0 = __ldg(f), f1 = __ldg(f + 1), f2 = __ldg(f + 2);
+        sn = v3(f0.x, f0.y, f0.z); snx = v3(f0.w, f1.x, f1.y); sny = v3(f1.z, f1.w, f2.x); n = v3(f2.y, f2.z, f2.w);
+    }
     CP_DEV V3 local_to_world(V3 w) const {
         return normalize(v3((snx.x * w.x + sny.x * w.y) + sn.x * w.z, (snx.y * w.x + sny.y * w.y) + sn.y * w.z, (snx.z * w.x + sny.z * w.y) + sn.z * w.z));
     }
@@ -367,8 +373,8 @@ CP_DEV void append_material(const DevScene& sc, const DevMaterial& m, P2 uv, GBS
 // BSDF::mix bxdf/mod.rs:218-269).  mix(A, B, s): A's lobes get the scale s appended, B's lobes
 // follow with 1 - s; a black s keeps only B, a black 1 - s only A.  The tree is walked with an
 // explicit stack; lobes of A and B land in the same arrays, in the order BSDF::mix produces.
-CP_DEV void build_general_bsdf(const DevScene& sc, uint32_t mat, const ShapePoint& sp, GBSDF& b) {
-    b.init(sp.n);
+CP_DEV void build_general_bsdf(const DevScene& sc, uint32_t mat, const ShapePoint& sp, GBSDF& b, const float4* frame = nullptr) {
+    if (frame) b.init_frame(frame); else b.init(sp.n);
     // frame: material, phase (0 = enter, 1 = left done, 2 = right done), lobe / delta counts at entry and after left
     struct Frame { uint32_t mat; int phase; int l0, d0, l1, d1; };
     Frame st[kMaxScales + 1];

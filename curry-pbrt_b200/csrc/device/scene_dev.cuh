@@ -83,6 +83,11 @@ struct DevScene {
     // geometry
     const float4* prims;        // 3 per BVH slot
     const float* prim_uv;       // 6 per BVH slot, only if any triangle has explicit uvs (else null)
+    // 3 per BVH slot (triangles): {n.xyz, snx.x}{snx.yz, sny.xy}{sny.z, n_local.xyz} -- Triangle::normal
+    // (triangle.rs:78-82) and, for an untransformed triangle, the shading frame BSDF::new builds from it
+    // (bxdf/mod.rs:83-97, coordinate_system math/mod.rs:67-74), evaluated once on the host with the same
+    // f32 operations instead of at every hit
+    const float4* prim_frame;
     const float4* nodes;        // 4 per Parent node
     const DevTransform* transforms;
     uint32_t n_prims, n_nodes;

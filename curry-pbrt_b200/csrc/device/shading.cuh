@@ -112,6 +112,12 @@ struct BSDF {
         n = normalize(v3(dot(normal, snx), dot(normal, sny), dot(normal, sn)));
         n_lobes = 0; n_deltas = 0;
     }
+    CP_DEV void init_frame(const float4* __restrict__ f) { load_frame(f); n_lobes = 0; n_deltas = 0; }
+    // the same frame read from DevScene::prim_frame (host-evaluated, see scene_dev.cuh)
+    CP_DEV void load_frame(const float4* __restrict__ f) {
+        const float4 f0 = __ldg(f), f1 = __ldg(f + 1), f2 = __ldg(f + 2);
+        sn = v3(f0.x, f0.y, f0.z); snx = v3(f0.w, f1.x, f1.y); sny = v3(f1.z, f1.w, f2.x); n = v3(f2.y, f2.z, f2.w);
+    }
     CP_DEV V3 local_to_world(V3 w) const {
         return normalize(v3((snx.x * w.x + sny.x * w.y) + sn.x * w.z, (snx.y * w.x + sny.y * w.y) + sn.y * w.z, (snx.z * w.x + sny.z * w.y) + sn.z * w.z));
     }

@@ -202,7 +202,8 @@ CP_DEV ShapePoint prim_shape_point(const DevScene& sc, uint32_t slot, const Prim
         tri_intersect_core(tv, r.o, r.t_max, rs, &t, b);   // same arithmetic as the accepted test; t_max only gates acceptance
         s.p_error = gamma_n(7) * tri_abs_sum(tv, b[0], b[1], b[2]);
         s.p = tri_point(tv, b[0], b[1], b[2]);
-        s.n = tri_normal(tv);
+        if (sc.prim_frame) { const float4 f0 = __ldg(&sc.prim_frame[3ull * slot]); s.n = v3(f0.x, f0.y, f0.z); }
+        else s.n = tri_normal(tv);
         s.uv = tri_uv((meta & kMetaHasUv) ? sc.prim_uv + 6ull * slot : nullptr, b[0], b[1], b[2]);
     }
     if (xform >= 0) s = shape_point_to_world(sc, xform, s);

@@ -351,10 +351,10 @@ template <> struct BsdfFor<SHADE_GLASS> { typedef BSDF<0, 2> type; };
 template <> struct BsdfFor<SHADE_GENERAL> { typedef GBSDF type; };
 
 template <int KIND>
-CP_DEV void build_bsdf(const DevScene& sc, uint32_t mat, const ShapePoint& sp, typename BsdfFor<KIND>::type& b) {
-    if constexpr (KIND == SHADE_GENERAL) { build_general_bsdf(sc, mat, sp, b); return; }
+CP_DEV void build_bsdf(const DevScene& sc, uint32_t mat, const ShapePoint& sp, typename BsdfFor<KIND>::type& b, const float4* frame) {
+    if constexpr (KIND == SHADE_GENERAL) { build_general_bsdf(sc, mat, sp, b, frame); return; }
     const DevMaterial& m = sc.materials[mat];
-    b.init(sp.n);
+    if (frame) b.init_frame(frame); else b.init(sp.n);
     if constexpr (KIND == SHADE_MATTE) {   // matte.rs:17-28
         Spec kd = tex_eval(sc, m.tex[0], sp.uv);
         float sigma = rclamp(tex_eval(sc, m.tex[1], sp.uv).r, 0.f, 90.f);
@@ -502,7 +502,9 @@ __global__ void __launch_bounds__(128, ShadeBlocks<KIND>::value) k_shade(DevScen
             Ray ray; ray.o = f4_xyz(ro); ray.d = f4_xyz(rd); ray.t_max = kFloatMax;
             const PrimRecord pr = load_prim(sc, slot);
             sp = prim_shape_point(sc, slot, pr, ray, P.hit_t[pid]);
-            build_bsdf<KIND>(sc, prim_source(pr), sp, bsdf);
+            // untransformed triangle: its shading frame was evaluated on the host
+            const float4* frame = (sc.prim_frame && prim_meta(pr) <= kMetaHasUv) ? sc.prim_frame + 3ull * slot : nullptr;
+            build_bsdf<KIND>(sc, prim_source(pr), sp, bsdf, frame);
             if constexpr (KIND == SHADE_GENERAL) { if (bsdf.overflow) atomicAdd(&totals->bsdf_overflow, 1ull); }
             if (sc.integrator == 0) {
                 if (bounce == 0 || (flags & kFlagSpecular)) L = L + beta * spec(0.f);   // intersect.le() == None
