@@ -101,14 +101,18 @@ CP_DEV P2 concentric_sample_disk(P2 u) {   // src/math/mod.rs:98-110
     float rad, theta;
     if (fabsf(o.x) > fabsf(o.y)) { rad = o.x; theta = (kPi / 4.f) * (o.y / o.x); }
     else { rad = o.y; theta = (kPi / 2.f) - (kPi / 4.f) * (o.x / o.y); }
-    r.x = rad * cosf(theta); r.y = rad * sinf(theta);
+    float sn, cs;
+    sincosf(theta, &sn, &cs);          // one range reduction for both (same accuracy as sinf / cosf)
+    r.x = rad * cs; r.y = rad * sn;
     return r;
 }
 CP_DEV V3 uniform_sample_sphere_q21(P2 u) {   // uniform_sample_hemisphere (math/mod.rs:111-116)
     float z = 1.f - 2.f * u.x;
     float r = sqrtf(rmax(0.f, 1.f - z * z));
     float phi = 2.f * kPi * u.y;
-    return v3(r * cosf(phi), r * sinf(phi), z);
+    float sn, cs;
+    sincosf(phi, &sn, &cs);
+    return v3(r * cs, r * sn, z);
 }
 CP_DEV V3 cosine_sample_hemisphere(P2 u, float* pdf) {   // math/mod.rs:117-121
     P2 d = concentric_sample_disk(u);

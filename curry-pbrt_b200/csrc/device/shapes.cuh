@@ -85,6 +85,29 @@ CP_DEV bool tri_intersect_core(const TriVerts& tv, V3 o, float t_max, const TriR
     return true;
 }
 
+// Barycentrics of a hit that the acceptance test above has already accepted: the same e0, e1, e2 and
+// det (same operations, so the same bits) without the distance and error-bound arithmetic that only
+// decides acceptance (triangle.rs:213-262 computes b from exactly these values).
+CP_DEV void tri_barycentrics(const TriVerts& tv, V3 o, V3 d, float b[3]) {
+    const V3 a = vabs(d);
+    int kz = 0; float m = a.x;
+    if (a.y > m) { m = a.y; kz = 1; }
+    if (a.z > m) { kz = 2; }
+    TriRaySetup rs; rs.kz = kz; rs.kx = kz + 1 == 3 ? 0 : kz + 1; rs.ky = rs.kx + 1 == 3 ? 0 : rs.kx + 1;
+    const float dx = comp(d, rs.kx), dy = comp(d, rs.ky), dz = comp(d, rs.kz);
+    const float sx = -dx / dz, sy = -dy / dz;
+    V3 p0t = permute(tv.p0 - o, rs), p1t = permute(tv.p1 - o, rs), p2t = permute(tv.p2 - o, rs);
+    p0t.x += sx * p0t.z; p0t.y += sy * p0t.z;
+    p1t.x += sx * p1t.z; p1t.y += sy * p1t.z;
+    p2t.x += sx * p2t.z; p2t.y += sy * p2t.z;
+    const float e0 = p1t.x * p2t.y - p1t.y * p2t.x;
+    const float e1 = p2t.x * p0t.y - p2t.y * p0t.x;
+    const float e2 = p0t.x * p1t.y - p0t.y * p1t.x;
+    const float det = e0 + e1 + e2;
+    const float inv_det = 1.f / det;
+    b[0] = e0 * inv_det; b[1] = e1 * inv_det; b[2] = e2 * inv_det;
+}
+
 CP_DEV V3 tri_normal(const TriVerts& t) { return normalize(normalize(cross(t.p0 - t.p2, t.p1 - t.p2))); }   // triangle.rs:78-82
 CP_DEV V3 tri_point(const TriVerts& t, float b0, float b1, float b2) { return b0 * t.p0 + b1 * t.p1 + b2 * t.p2; }
 CP_DEV V3 tri_abs_sum(const TriVerts& t, float b0, float b1, float b2) { return vabs(b0 * t.p0) + vabs(b1 * t.p1) + vabs(b2 * t.p2); }
@@ -197,9 +220,8 @@ CP_DEV ShapePoint prim_shape_point(const DevScene& sc, uint32_t slot, const Prim
         s = sphere_shape_point(pr.q0.x, r, t_hit);
     } else {
         TriVerts tv = prim_tri(pr);
-        TriRaySetup rs = tri_ray_setup(r.d);
-        float t, b[3] = {0.f, 0.f, 0.f};
-        tri_intersect_core(tv, r.o, r.t_max, rs, &t, b);   // same arithmetic as the accepted test; t_max only gates acceptance
+        float b[3];
+        tri_barycentrics(tv, r.o, r.d, b);   // same arithmetic as the accepted test, minus what only gates acceptance
         s.p_error = gamma_n(7) * tri_abs_sum(tv, b[0], b[1], b[2]);
         s.p = tri_point(tv, b[0], b[1], b[2]);
         if (sc.prim_frame) { const float4 f0 = __ldg(&sc.prim_frame[3ull * slot]); s.n = v3(f0.x, f0.y, f0.z); }
