@@ -17,7 +17,8 @@ import numpy as np
 from . import _abi as abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcpbrt.so")
+# CPBRT_LIB: load another build of the same library (tools/variant_sweep.py compares tuning variants)
+LIB_PATH = os.environ.get("CPBRT_LIB") or os.path.join(_HERE, "libcpbrt.so")
 
 
 class CpbrtError(RuntimeError):

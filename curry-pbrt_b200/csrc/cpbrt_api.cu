@@ -881,7 +881,7 @@ int cpbrt_render(cpbrt_ctx* ctx, const cpbrt_render_params* params, float* film_
     cudaEventRecord(e0, st);
     uint64_t launches = 0, trace_launches = 0;
     const bool vote = use_vote(ctx);
-    const int g_trace = grid_for(ctx, 8), g_shade = grid_for(ctx, 8), g_pix = grid_for(ctx, 4);
+    const int g_closest = grid_for(ctx, vote ? CPBRT_BLOCKS_CLOSEST_VOTE : CPBRT_BLOCKS_CLOSEST_LOOP), g_shadow = grid_for(ctx, vote ? CPBRT_BLOCKS_SHADOW_VOTE : CPBRT_BLOCKS_SHADOW_LOOP), g_shade = grid_for(ctx, 8), g_pix = grid_for(ctx, 4);
     // one thread per pixel where possible: each walks a dependent chain of radical inverses (all of a
     // rank's skipped samples on the first pass), which only many resident warps can hide
     const int g_raygen = (int)std::min<uint64_t>(((uint64_t)npix + 127) / 128, (uint64_t)ctx->sm_count * 16);
@@ -916,14 +916,14 @@ int cpbrt_render(cpbrt_ctx* ctx, const cpbrt_render_params* params, float* film_
         for (uint32_t it = 0; it < n_iters && !recursive; ++it) {
             const int next = cur ^ 1;
             span_begin(1);
-            if (vote) k_trace_closest<true><<<g_trace, 128, 0, st>>>(S, P, Q, cur, T);
-            else k_trace_closest<false><<<g_trace, 128, 0, st>>>(S, P, Q, cur, T);
+            if (vote) k_trace_closest<true><<<g_closest, 128, 0, st>>>(S, P, Q, cur, T);
+            else k_trace_closest<false><<<g_closest, 128, 0, st>>>(S, P, Q, cur, T);
             ++trace_launches;
             span_end();
             if (!prof) { cudaEventRecord(eK1, st); cudaStreamWaitEvent(sa, ePrev, 0); }
             span_begin(2);
-            if (vote) k_trace_shadow<true><<<g_trace, 128, 0, sa>>>(S, P, Q, T);
-            else k_trace_shadow<false><<<g_trace, 128, 0, sa>>>(S, P, Q, T);
+            if (vote) k_trace_shadow<true><<<g_shadow, 128, 0, sa>>>(S, P, Q, T);
+            else k_trace_shadow<false><<<g_shadow, 128, 0, sa>>>(S, P, Q, T);
             span_end();
             if (!prof) cudaStreamWaitEvent(sa, eK1, 0);
             k_queue_reset<<<1, 32, 0, sa>>>(Q, cur, 0, T);

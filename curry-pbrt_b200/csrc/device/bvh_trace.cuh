@@ -71,6 +71,37 @@ struct TaskStack {
     CP_DEV uint2 pop() { return n ? e[--n] : make_uint2(kDone, 0u); }
 };
 
+// Tuning constants of the persistent-warp kernels (128 threads per block), per traversal kind and
+// warp schedule; measured with tools/variant_sweep.py.
+//   blocks  resident blocks per SM the wavefront kernel is compiled for (register budget
+//           65536 / (128 * blocks): 8 -> 64 registers, 6 -> 80)
+//   refill  idle lanes a warp waits for before it writes results back and fetches new rays
+static constexpr int kTraceBlock = 128;
+#ifndef CPBRT_BLOCKS_CLOSEST_LOOP
+#define CPBRT_BLOCKS_CLOSEST_LOOP 8
+#endif
+#ifndef CPBRT_BLOCKS_CLOSEST_VOTE
+#define CPBRT_BLOCKS_CLOSEST_VOTE 6
+#endif
+#ifndef CPBRT_BLOCKS_SHADOW_LOOP
+#define CPBRT_BLOCKS_SHADOW_LOOP 8
+#endif
+#ifndef CPBRT_BLOCKS_SHADOW_VOTE
+#define CPBRT_BLOCKS_SHADOW_VOTE 8
+#endif
+#ifndef CPBRT_REFILL_CLOSEST_LOOP
+#define CPBRT_REFILL_CLOSEST_LOOP 16
+#endif
+#ifndef CPBRT_REFILL_SHADOW_LOOP
+#define CPBRT_REFILL_SHADOW_LOOP 20
+#endif
+#ifndef CPBRT_REFILL_CLOSEST_VOTE
+#define CPBRT_REFILL_CLOSEST_VOTE 12
+#endif
+#ifndef CPBRT_REFILL_SHADOW_VOTE
+#define CPBRT_REFILL_SHADOW_VOTE 12
+#endif
+
 struct NodeChildren { uint32_t ref[2], cnt[2]; bool ok[2]; float tmin[2]; uint32_t axis; };
 
 // Reads one Parent node (64 B) and runs the t_max-independent part of both children's box tests.
@@ -349,7 +380,6 @@ CP_DEV float ray_abs_margin(const DevScene& sc, const Ray& ray) {
 }
 
 enum TraceMode : int { MODE_SEARCH = 0, MODE_REPLAY = 1 };
-static constexpr int kRefillLanes = 8;
 
 // Persistent-warp closest hit (two-phase), loop-scheduled: every lane descends to its next leaf,
 // then every lane tests that leaf.  The better schedule for small trees and coherent rays (a few
@@ -384,8 +414,8 @@ __device__ void closest_persistent_loop(const DevScene& sc, uint32_t n_items, ui
     for (;;) {
         // ---- refill -------------------------------------------------------------------------
         const unsigned idle = __ballot_sync(0xFFFFFFFFu, !have_ray);
-        // refill in groups: one atomic per >= kRefillLanes idle lanes (or when the warp is empty)
-        if (!exhausted && (__popc(idle) >= kRefillLanes || idle == 0xFFFFFFFFu)) {
+        // refill in groups: one atomic per >= CPBRT_REFILL_* idle lanes (or when the warp is empty)
+        if (!exhausted && (__popc(idle) >= CPBRT_REFILL_CLOSEST_LOOP || idle == 0xFFFFFFFFu)) {
             const int leader = __ffs(idle) - 1;
             uint32_t base = 0;
             if (lane == leader) base = atomicAdd(work_counter, (uint32_t)__popc(idle));
@@ -512,8 +542,8 @@ __device__ void any_persistent_loop(const DevScene& sc, uint32_t n_items, uint32
     float abs_m = 0.f;
     for (;;) {
         const unsigned idle = __ballot_sync(0xFFFFFFFFu, !have_ray);
-        // refill in groups: one atomic per >= kRefillLanes idle lanes (or when the warp is empty)
-        if (!exhausted && (__popc(idle) >= kRefillLanes || idle == 0xFFFFFFFFu)) {
+        // refill in groups: one atomic per >= CPBRT_REFILL_* idle lanes (or when the warp is empty)
+        if (!exhausted && (__popc(idle) >= CPBRT_REFILL_SHADOW_LOOP || idle == 0xFFFFFFFFu)) {
             const int leader = __ffs(idle) - 1;
             uint32_t base = 0;
             if (lane == leader) base = atomicAdd(work_counter, (uint32_t)__popc(idle));
@@ -583,7 +613,7 @@ __device__ void any_persistent_loop(const DevScene& sc, uint32_t n_items, uint32
 // numbers of node steps (5 of 32 lanes active on random rays through a million triangles).  Here
 // every iteration the warp VOTES: the kind of step more lanes are waiting for is executed, for
 // exactly those lanes, and the others simply wait for their kind's turn.  Finished rays are
-// written back, and their lanes refilled, in groups of kRefillLanes.
+// written back, and their lanes refilled, in groups of CPBRT_REFILL_* lanes.
 //   lane state   EMPTY (have_ray = false) | ACTIVE (task is a Parent or a leaf cursor) | DONE (task = kDone)
 //   leaf cursor  x = kLeafBit | next slot, y = primitives left
 template <class User, class Fetch, class Finish>
@@ -627,7 +657,7 @@ __device__ void closest_persistent(const DevScene& sc, uint32_t n_items, uint32_
         const unsigned m_node = __ballot_sync(0xFFFFFFFFu, want_node), m_prim = __ballot_sync(0xFFFFFFFFu, want_prim);
         const unsigned m_active = m_node | m_prim;
         // ---- write back finished rays and refill, in groups ---------------------------------------
-        if (__popc(~m_active) >= kRefillLanes || m_active == 0u) {
+        if (__popc(~m_active) >= CPBRT_REFILL_CLOSEST_VOTE || m_active == 0u) {
             const bool finished = have_ray && task.x == kDone;
             if (__any_sync(0xFFFFFFFFu, finished)) {
                 if (finished && mode == MODE_SEARCH) ray.t_max = best != 0xFFFFFFFFu ? t_best : t_init;
@@ -750,7 +780,7 @@ __device__ void any_persistent(const DevScene& sc, uint32_t n_items, uint32_t* w
         const bool want_prim = have_ray && (task.x & kLeafBit) && task.x != kDone;
         const unsigned m_node = __ballot_sync(0xFFFFFFFFu, want_node), m_prim = __ballot_sync(0xFFFFFFFFu, want_prim);
         const unsigned m_active = m_node | m_prim;
-        if (__popc(~m_active) >= kRefillLanes || m_active == 0u) {
+        if (__popc(~m_active) >= CPBRT_REFILL_SHADOW_VOTE || m_active == 0u) {
             const bool finished = have_ray && task.x == kDone;
             if (__any_sync(0xFFFFFFFFu, finished)) {
                 finish(finished, user, ray, hit ? 0u : 0xFFFFFFFFu, ray.t_max);

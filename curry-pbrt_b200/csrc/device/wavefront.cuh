@@ -193,7 +193,7 @@ struct ClosestItem { uint32_t pid; uint32_t is_mis; float w_o, w_d; };   // w_* 
 // VOTE selects the warp schedule of the traversal (bvh_trace.cuh): vote-scheduled steps for big
 // trees, the descend-then-test loop for small ones.
 template <bool VOTE>
-__global__ void __launch_bounds__(128, 8) k_trace_closest(DevScene sc, PathArrays P, Queues Q, int cur, Totals* totals) {
+__global__ void __launch_bounds__(kTraceBlock, VOTE ? CPBRT_BLOCKS_CLOSEST_VOTE : CPBRT_BLOCKS_CLOSEST_LOOP) k_trace_closest(DevScene sc, PathArrays P, Queues Q, int cur, Totals* totals) {
     const uint32_t n = Q.counts[kCntClosest0 + cur];
     uint32_t overflow = 0;
     const uint32_t* __restrict__ queue = Q.closest[cur];
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(256) k_classify(PathArrays P, Queues Q, uint32
 
 // Shadow-ray stage: VisibilityTester::unoccluded (light/mod.rs:112-114).
 template <bool VOTE>
-__global__ void __launch_bounds__(128, 8) k_trace_shadow(DevScene sc, PathArrays P, Queues Q, Totals* totals) {
+__global__ void __launch_bounds__(kTraceBlock, VOTE ? CPBRT_BLOCKS_SHADOW_VOTE : CPBRT_BLOCKS_SHADOW_LOOP) k_trace_shadow(DevScene sc, PathArrays P, Queues Q, Totals* totals) {
     const uint32_t n = Q.counts[kCntShadow];
     uint32_t overflow = 0;
     auto fetch = [&](uint32_t i, Ray* ray, uint32_t* pid) {
@@ -670,7 +670,7 @@ __global__ void k_film_resolve_srgb8(DevScene sc, const float4* __restrict__ sum
 // MODE: 0 = two-phase traversal, loop-scheduled; 1 = reference-order traversal with visit counters;
 //       2 = two-phase traversal, vote-scheduled
 template <int MODE>
-__global__ void __launch_bounds__(128) k_batch_closest(DevScene sc, const float4* __restrict__ rays, uint64_t n, float4* __restrict__ hits,
+__global__ void __launch_bounds__(kTraceBlock, MODE == 2 ? CPBRT_BLOCKS_CLOSEST_VOTE : 1) k_batch_closest(DevScene sc, const float4* __restrict__ rays, uint64_t n, float4* __restrict__ hits,
                                                        unsigned long long* counters, Totals* totals) {
     uint32_t overflow = 0;
     TraceStats ts; ts.parent_visits = 0; ts.prim_tests = 0;

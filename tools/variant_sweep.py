@@ -1,0 +1,91 @@
+#!/usr/bin/env python3
+"""Compile-time tuning variants of libcpbrt.so, built here (nvcc cross-compiles) and timed on the GPU box.
+
+    tools/variant_sweep.py build            # here: one libcpbrt_<name>.so per variant under curry-pbrt_b200/build/variants/
+    tools/variant_sweep.py run [--spp 256]  # on the GPU box: bench.py (and config_bench.py C4 with --c4) per variant -> gpurun_out/variants.jsonl
+
+A variant is a set of -D macros for cpbrt_api.cu (the only translation unit with device code of the
+render path); every other object is shared with the normal build.  The library is chosen with
+CPBRT_LIB (curry-pbrt_b200/__init__.py)."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "curry-pbrt_b200")
+VAR = os.path.join(PKG, "build", "variants")
+
+VARIANTS = {
+    "base": [],
+    "loop12": ["-DCPBRT_REFILL_CLOSEST_LOOP=12", "-DCPBRT_REFILL_SHADOW_LOOP=12"],
+    "loop20": ["-DCPBRT_REFILL_CLOSEST_LOOP=20", "-DCPBRT_REFILL_SHADOW_LOOP=20"],
+    "loop24": ["-DCPBRT_REFILL_CLOSEST_LOOP=24", "-DCPBRT_REFILL_SHADOW_LOOP=24"],
+    "loop28": ["-DCPBRT_REFILL_CLOSEST_LOOP=28", "-DCPBRT_REFILL_SHADOW_LOOP=28"],
+    "vote12_cvb6": ["-DCPBRT_REFILL_CLOSEST_VOTE=12", "-DCPBRT_REFILL_SHADOW_VOTE=12", "-DCPBRT_BLOCKS_CLOSEST_VOTE=6"],
+    "vote16_cvb5": ["-DCPBRT_REFILL_CLOSEST_VOTE=16", "-DCPBRT_REFILL_SHADOW_VOTE=16", "-DCPBRT_BLOCKS_CLOSEST_VOTE=5"],
+    "vote8_b7": ["-DCPBRT_BLOCKS_CLOSEST_VOTE=7", "-DCPBRT_BLOCKS_SHADOW_VOTE=7"],
+}
+
+
+def build(names):
+    sys.path.insert(0, PKG)
+    import build as B
+    B.build()
+    os.makedirs(VAR, exist_ok=True)
+    others = [os.path.join(B.OBJ, f) for f in os.listdir(B.OBJ) if f.endswith(".o") and f != "cpbrt_api.cu.o"]
+    procs = []
+    for name in names:
+        obj = os.path.join(VAR, "cpbrt_api_%s.o" % name)
+        cmd = [B.NVCC] + B.NVCC_FLAGS + VARIANTS[name] + ["-c", os.path.join(B.CSRC, "cpbrt_api.cu"), "-o", obj]
+        procs.append((name, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for name, obj, p in procs:
+        out = p.communicate()[0]
+        open(os.path.join(VAR, "ptxas_%s.log" % name), "w").write(out)
+        if p.returncode:
+            sys.stderr.write(out)
+            raise SystemExit("variant %s failed to compile" % name)
+        so = os.path.join(VAR, "libcpbrt_%s.so" % name)
+        subprocess.check_call([B.NVCC, "-shared", "-o", so, obj] + others + ["-lz", "-ldl", "-lpthread", "-cudart", "static"])
+        print("built", so)
+
+
+def run(names, spp, c4):
+    out_path = os.path.join(ROOT, "gpurun_out", "variants.jsonl")
+    os.makedirs(os.path.dirname(out_path), exist_ok=True)
+    with open(out_path, "a") as out:
+        for name in names:
+            so = os.path.join(VAR, "libcpbrt_%s.so" % name)
+            if not os.path.exists(so):
+                continue
+            env = dict(os.environ, CPBRT_LIB=so)
+            rec = dict(variant=name, flags=VARIANTS[name])
+            if not name.startswith("vote"):      # vote* variants only change the big-tree schedule
+                r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--spp", str(spp), "--steps", "2", "--warmup", "2", "--no-cpu-baseline"],
+                                   env=env, capture_output=True, text=True, cwd=ROOT)
+                try:
+                    j = json.loads(r.stdout.strip().splitlines()[-1])
+                    rec.update(msamples_s=j["value"], stage_ms=j.get("stage_ms"))
+                except Exception:
+                    rec.update(error=(r.stderr or r.stdout)[-400:])
+            if c4 and not name.startswith("loop"):
+                r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "config_bench.py"), "--configs", "C4"],
+                                   env=env, capture_output=True, text=True, cwd=ROOT)
+                try:
+                    j = json.loads(r.stdout.strip().splitlines()[-1])
+                    rec.update(c4_msamples_s=j["msamples_s"], c4_stage_ms=j.get("stage_ms"), c4_checks=j.get("checks"))
+                except Exception:
+                    rec.update(c4_error=(r.stderr or r.stdout)[-400:])
+            out.write(json.dumps(rec) + "\n")
+            out.flush()
+            print(json.dumps(rec))
+
+
+if __name__ == "__main__":
+    mode = sys.argv[1] if len(sys.argv) > 1 else "build"
+    names = [a for a in sys.argv[2:] if a in VARIANTS] or list(VARIANTS)
+    spp = int(sys.argv[sys.argv.index("--spp") + 1]) if "--spp" in sys.argv else 256
+    if mode == "build":
+        build(names)
+    else:
+        run(names, spp, "--c4" in sys.argv)
