@@ -1,10 +1,12 @@
-// PNG in (texture load, src/texture/image/png.rs:6-27: 8-bit RGB assumed) and PNG out
-// (Film::write_image, src/film.rs:35-38 -> src/texture/image.rs:108-127).  zlib does the
-// inflate/deflate; the container format and scanline filters are handled here.
+// PNG in (texture load, src/texture/image/png.rs:6-27: 8-bit RGB assumed), OpenEXR in
+// (src/texture/image/exr.rs:7-61) and PNG out (Film::write_image, src/film.rs:35-38 ->
+// src/texture/image.rs:108-127).  zlib does the inflate/deflate; the container formats, scanline
+// filters and EXR predictors are handled here.
 #include "scene_host.h"
 
 #include <zlib.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -72,6 +74,150 @@ bool read_png_rgb8(const std::string& path, uint32_t* w, uint32_t* h, std::vecto
         }
     }
     *w = W; *h = H;
+    return true;
+}
+
+// ---- OpenEXR ------------------------------------------------------------------------------------
+// ExrImageFileReader::read_file (src/texture/image/exr.rs:7-61) reads layer 0 of the file with the
+// `exr` crate (0.7.4) and copies the channels named R, G and B -- f16, f32 or u32 samples, each
+// converted to f32 -- into an RGB buffer in data-window row order; any other channel name panics
+// there and is an error here.  This reader covers single-part scanline files, uncompressed or with
+// the RLE / ZIPS / ZIP codecs (the byte-level ones; zlib is already linked for PNG).  Tiled, deep and
+// multi-part files and the lossy / wavelet codecs (PIZ, PXR24, B44, DWA) are rejected by name.
+static float half_to_float(uint16_t h) {
+    const uint32_t sign = (uint32_t)(h & 0x8000u) << 16;
+    uint32_t exp = (h >> 10) & 0x1Fu, man = h & 0x3FFu, bits;
+    if (exp == 0) {
+        if (man == 0) bits = sign;
+        else {   // subnormal half -> normal float
+            int e = -1;
+            do { ++e; man <<= 1; } while (!(man & 0x400u));
+            bits = sign | ((uint32_t)(127 - 15 - e) << 23) | ((man & 0x3FFu) << 13);
+        }
+    } else if (exp == 31) bits = sign | 0x7F800000u | (man << 13);
+    else bits = sign | ((exp + 127 - 15) << 23) | (man << 13);
+    float f; memcpy(&f, &bits, 4);
+    return f;
+}
+
+namespace {
+struct ExrCursor {
+    const uint8_t* p; size_t n, pos = 0; bool ok = true;
+    bool need(size_t k) { if (pos + k > n) ok = false; return ok; }
+    uint8_t u8() { return need(1) ? p[pos++] : 0; }
+    uint32_t u32() { if (!need(4)) return 0; uint32_t v; memcpy(&v, p + pos, 4); pos += 4; return v; }   // little-endian host
+    uint64_t u64() { if (!need(8)) return 0; uint64_t v; memcpy(&v, p + pos, 8); pos += 8; return v; }
+    std::string cstr() { std::string s; while (need(1) && p[pos]) s.push_back((char)p[pos++]); if (ok) ++pos; return s; }
+};
+struct ExrChannel { std::string name; uint32_t type; int rgb; };
+}  // namespace
+
+// undo the byte predictor and the even / odd split the RLE and ZIP codecs apply before compressing
+static void exr_unfilter(std::vector<uint8_t>& t, std::vector<uint8_t>& out) {
+    for (size_t i = 1; i < t.size(); ++i) t[i] = (uint8_t)(t[i - 1] + t[i] - 128);
+    out.resize(t.size());
+    const size_t half = (t.size() + 1) / 2;
+    for (size_t i = 0; i < t.size(); ++i) out[i] = (i & 1) ? t[half + i / 2] : t[i / 2];
+}
+
+bool read_exr_rgb(const std::string& path, uint32_t* w, uint32_t* h, std::vector<float>* rgb, std::string* err) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) { *err = "cannot open image '" + path + "'"; return false; }
+    std::stringstream ss; ss << f.rdbuf();
+    const std::string d = ss.str();
+    ExrCursor c{(const uint8_t*)d.data(), d.size()};
+    if (c.u32() != 20000630u) { *err = "not an OpenEXR file: " + path; return false; }
+    const uint32_t version = c.u32();
+    if ((version & 0xFFu) != 2 || (version & (0x200u | 0x800u | 0x1000u))) { *err = "only single-part scanline OpenEXR files are supported: " + path; return false; }
+    std::vector<ExrChannel> channels;
+    int compression = -1; int32_t win[4] = {0, 0, -1, -1}; bool have_window = false;
+    for (;;) {
+        const std::string name = c.cstr();
+        if (!c.ok) { *err = "truncated OpenEXR header: " + path; return false; }
+        if (name.empty()) break;
+        const std::string type = c.cstr();
+        const uint32_t size = c.u32();
+        if (!c.need(size)) { *err = "truncated OpenEXR header: " + path; return false; }
+        ExrCursor a{c.p + c.pos, size};
+        if (name == "channels" && type == "chlist") {
+            for (;;) {
+                ExrChannel ch; ch.name = a.cstr();
+                if (!a.ok || ch.name.empty()) break;
+                ch.type = a.u32(); a.u32();                 // pixel type; pLinear + 3 reserved bytes
+                const uint32_t xs = a.u32(), ys = a.u32();
+                if (!a.ok) break;
+                if (xs != 1 || ys != 1) { *err = "sub-sampled OpenEXR channels are not supported: " + path; return false; }
+                // the reference accepts exactly the names R, G, B and panics on anything else (exr.rs:35-46)
+                ch.rgb = ch.name == "R" ? 0 : ch.name == "G" ? 1 : ch.name == "B" ? 2 : -1;
+                if (ch.rgb < 0) { *err = "OpenEXR channel '" + ch.name + "' is neither R, G nor B: " + path; return false; }
+                if (ch.type > 2) { *err = "unknown OpenEXR pixel type: " + path; return false; }
+                channels.push_back(ch);
+            }
+        } else if (name == "compression" && size >= 1) compression = a.u8();
+        else if (name == "dataWindow" && size >= 16) { for (int k = 0; k < 4; ++k) win[k] = (int32_t)a.u32(); have_window = true; }
+        c.pos += size;
+    }
+    if (channels.empty() || compression < 0 || !have_window || win[2] < win[0] || win[3] < win[1]) { *err = "incomplete OpenEXR header: " + path; return false; }
+    static const char* codec_names[] = {"NONE", "RLE", "ZIPS", "ZIP", "PIZ", "PXR24", "B44", "B44A", "DWAA", "DWAB"};
+    if (compression > 3) {
+        *err = std::string("OpenEXR compression ") + (compression < 10 ? codec_names[compression] : "?") + " is not supported (NONE, RLE, ZIPS, ZIP are): " + path;
+        return false;
+    }
+    const uint64_t W = (uint64_t)((int64_t)win[2] - win[0] + 1), H = (uint64_t)((int64_t)win[3] - win[1] + 1);
+    if (W > (1u << 20) || H > (1u << 20)) { *err = "OpenEXR data window too large: " + path; return false; }
+    const uint32_t lines_per_block = compression == 3 ? 16u : 1u;
+    const uint64_t n_blocks = (H + lines_per_block - 1) / lines_per_block;
+    size_t line_bytes = 0;
+    for (const auto& ch : channels) line_bytes += (ch.type == 1 ? 2 : 4) * (size_t)W;
+    std::vector<uint64_t> offsets(n_blocks);
+    for (auto& o : offsets) o = c.u64();
+    if (!c.ok) { *err = "truncated OpenEXR offset table: " + path; return false; }
+    rgb->assign((size_t)W * H * 3, 0.f);
+    std::vector<uint8_t> tmp, raw;
+    for (uint64_t b = 0; b < n_blocks; ++b) {
+        ExrCursor k{c.p, c.n, (size_t)offsets[b]};
+        const int32_t y0 = (int32_t)k.u32();
+        const uint32_t size = k.u32();
+        if (!k.ok || !k.need(size) || y0 < win[1] || y0 > win[3]) { *err = "bad OpenEXR chunk: " + path; return false; }
+        const uint64_t row0 = (uint64_t)((int64_t)y0 - win[1]);
+        const uint64_t rows = std::min<uint64_t>(lines_per_block, H - row0);
+        const size_t want = line_bytes * rows;
+        const uint8_t* src = k.p + k.pos;
+        if (compression == 0 || size == want) {      // a block that does not shrink is stored raw
+            if (size != want) { *err = "bad OpenEXR chunk size: " + path; return false; }
+            raw.assign(src, src + want);
+        } else if (compression == 1) {               // RLE: n < 0 -> -n literal bytes, n >= 0 -> next byte n + 1 times
+            tmp.clear();
+            size_t i = 0;
+            while (i < size) {
+                const int n = (int8_t)src[i++];
+                if (n < 0) { if (i + (size_t)(-n) > size) break; tmp.insert(tmp.end(), src + i, src + i + (size_t)(-n)); i += (size_t)(-n); }
+                else { if (i >= size) break; tmp.insert(tmp.end(), (size_t)n + 1, src[i++]); }
+            }
+            if (tmp.size() != want) { *err = "OpenEXR RLE block has the wrong length: " + path; return false; }
+            exr_unfilter(tmp, raw);
+        } else {                                     // ZIPS / ZIP: zlib stream
+            tmp.assign(want, 0);
+            uLongf out_len = want;
+            if (uncompress(tmp.data(), &out_len, src, size) != Z_OK || out_len != want) { *err = "OpenEXR inflate failed: " + path; return false; }
+            exr_unfilter(tmp, raw);
+        }
+        // within a block: scanline by scanline, inside a scanline channel by channel (file order = alphabetical)
+        const uint8_t* q = raw.data();
+        for (uint64_t r = 0; r < rows; ++r) {
+            for (const auto& ch : channels) {
+                float* out = rgb->data() + ((row0 + r) * W) * 3 + ch.rgb;
+                for (uint64_t x = 0; x < W; ++x) {
+                    float v;
+                    if (ch.type == 1) { uint16_t hv; memcpy(&hv, q, 2); q += 2; v = half_to_float(hv); }
+                    else if (ch.type == 2) { memcpy(&v, q, 4); q += 4; }
+                    else { uint32_t u; memcpy(&u, q, 4); q += 4; v = (float)u; }
+                    out[x * 3] = v;
+                }
+            }
+        }
+    }
+    *w = (uint32_t)W; *h = (uint32_t)H;
     return true;
 }
 

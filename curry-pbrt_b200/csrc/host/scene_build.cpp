@@ -223,10 +223,13 @@ struct Builder {
         if (it != image_cache.end()) return it->second.second;
         size_t dot = path.find_last_of('.');
         std::string ext = dot == std::string::npos ? "" : path.substr(dot + 1);
-        if (ext == "exr") fail("EXR textures are not supported by this build: " + path);
-        if (ext != "png") fail("unknown image extension: " + path);
-        uint32_t w, h; std::vector<uint8_t> rgb; std::string err;
-        if (!read_png_rgb8(path, &w, &h, &rgb, &err)) fail(err);
+        if (ext != "png" && ext != "exr") fail("unknown image extension: " + path);   // image.rs:73-77
+        uint32_t w, h; std::vector<uint8_t> rgb; std::vector<float> frgb; std::string err;
+        if (ext == "png") {
+            if (!read_png_rgb8(path, &w, &h, &rgb, &err)) fail(err);
+            frgb.resize(rgb.size());
+            for (size_t i = 0; i < rgb.size(); ++i) frgb[i] = rgb[i] / 255.f;   // to_rgb (png.rs:25-27)
+        } else if (!read_exr_rgb(path, &w, &h, &frgb, &err)) fail(err);
         cpbrt_texture t{};
         t.kind = CPBRT_TEX_IMAGE; t.channels = (uint32_t)channels; t.width = w; t.height = h;
         t.offset = sd->texels.size();
@@ -235,7 +238,7 @@ struct Builder {
             return std::pow((f + 0.055f) / 1.05f, 2.4f);
         };
         for (size_t i = 0; i < size_t(w) * h; ++i) {
-            float s[3] = {rgb[i * 3] / 255.f, rgb[i * 3 + 1] / 255.f, rgb[i * 3 + 2] / 255.f};   // to_rgb (png.rs:25-27)
+            const float s[3] = {frgb[i * 3], frgb[i * 3 + 1], frgb[i * 3 + 2]};
             if (channels == 3) {
                 for (int c = 0; c < 3; ++c) sd->texels.push_back(inverse_gamma ? inv_gamma(s[c]) : s[c]);
             } else {

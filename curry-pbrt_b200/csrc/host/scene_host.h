@@ -11,6 +11,8 @@
 namespace cpbrt_host {
 
 bool read_png_rgb8(const std::string& path, uint32_t* w, uint32_t* h, std::vector<uint8_t>* rgb, std::string* err);
+// OpenEXR scanline files (NONE / RLE / ZIPS / ZIP), channels R, G, B as f16 / f32 / u32 -> packed RGB f32 (texture/image/exr.rs:7-61)
+bool read_exr_rgb(const std::string& path, uint32_t* w, uint32_t* h, std::vector<float>* rgb, std::string* err);
 bool write_png_rgb8(const std::string& path, const uint8_t* rgb, uint32_t w, uint32_t h, std::string* err);
 void film_to_rgb8(const float* film, size_t n_floats, uint8_t* out);
 

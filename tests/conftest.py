@@ -80,3 +80,64 @@ def lcg_rays(n, lo, hi, seed=7):
     rays = np.zeros((n, 8), np.float32)
     rays[:, 0:3] = o; rays[:, 3] = np.finfo(np.float32).max; rays[:, 4:7] = d
     return rays
+
+
+def write_exr(path, img, compression, pixel_type, origin=(0, 0)):
+    """Minimal OpenEXR scanline writer (test fixture): img is (H, W, 3) float32 in R, G, B order;
+    compression 0 NONE / 1 RLE / 2 ZIPS / 3 ZIP; pixel_type 0 UINT / 1 HALF / 2 FLOAT."""
+    import struct
+    import zlib
+    H, W, _ = img.shape
+    x0, y0 = origin
+
+    def attr(name, typ, payload):
+        return name.encode() + b"\0" + typ.encode() + b"\0" + struct.pack("<i", len(payload)) + payload
+
+    chlist = b"".join(n + b"\0" + struct.pack("<iBxxxii", pixel_type, 0, 1, 1) for n in (b"B", b"G", b"R")) + b"\0"
+    box = struct.pack("<4i", x0, y0, x0 + W - 1, y0 + H - 1)
+    header = struct.pack("<II", 20000630, 2)
+    header += attr("channels", "chlist", chlist) + attr("compression", "compression", bytes([compression]))
+    header += attr("dataWindow", "box2i", box) + attr("displayWindow", "box2i", box)
+    header += attr("lineOrder", "lineOrder", b"\0") + attr("pixelAspectRatio", "float", struct.pack("<f", 1.0))
+    header += attr("screenWindowCenter", "v2f", struct.pack("<2f", 0, 0)) + attr("screenWindowWidth", "float", struct.pack("<f", 1.0))
+    header += b"\0"
+    dt = {0: np.uint32, 1: np.float16, 2: np.float32}[pixel_type]
+    lines = 16 if compression == 3 else 1
+
+    def rle(b):
+        out, i = bytearray(), 0
+        while i < len(b):
+            j = i
+            while j + 1 < len(b) and b[j + 1] == b[i] and j - i < 126:
+                j += 1
+            if j - i >= 2:
+                out += struct.pack("b", j - i) + bytes([b[i]])
+                i = j + 1
+            else:
+                k = i
+                while k < len(b) and k - i < 127 and not (k + 2 < len(b) and b[k] == b[k + 1] == b[k + 2]):
+                    k += 1
+                out += struct.pack("b", -(k - i)) + bytes(b[i:k])
+                i = k
+        return bytes(out)
+
+    blocks = []
+    for r0 in range(0, H, lines):
+        raw = b"".join(img[r, :, c].astype(dt).tobytes() for r in range(r0, min(H, r0 + lines)) for c in (2, 1, 0))
+        data = raw
+        if compression:
+            a = np.frombuffer(raw, np.uint8)
+            t = np.concatenate([a[0::2], a[1::2]]).astype(np.int32)
+            p = t.copy()
+            p[1:] = (t[1:] - t[:-1] + 128) & 0xFF
+            packed = rle(bytes(p.astype(np.uint8))) if compression == 1 else zlib.compress(bytes(p.astype(np.uint8)))
+            if len(packed) < len(raw):
+                data = packed
+        blocks.append(struct.pack("<ii", y0 + r0, len(data)) + data)
+    table_at = len(header)
+    offsets, pos = [], table_at + 8 * len(blocks)
+    for b in blocks:
+        offsets.append(pos)
+        pos += len(b)
+    with open(path, "wb") as f:
+        f.write(header + struct.pack("<%dQ" % len(blocks), *offsets) + b"".join(blocks))

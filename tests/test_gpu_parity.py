@@ -10,7 +10,7 @@ import re
 import numpy as np
 import pytest
 
-from conftest import SCENES, lcg_rays, scene_text
+from conftest import SCENES, lcg_rays, scene_text, write_exr
 from test_oracle import _synthetic_mesh_scene
 
 pytestmark = pytest.mark.gpu
@@ -493,6 +493,28 @@ def test_infinite_area_light(cpbrt, oracle, envmap, integrator):
     assert bad.mean() <= 0.02, bad.mean()
     rmse = float(np.sqrt(np.mean((g - o) ** 2)))
     assert rmse <= 0.03 * float(o.mean()) + 1e-4, rmse
+    assert abs(gs.rays_any - os_["rays_any"]) <= 2e-3 * os_["rays_any"]
+
+
+def test_hdr_exr_environment_map(cpbrt, oracle, tmp_path):
+    """An OpenEXR environment (texture/image/exr.rs) with a small very bright region: the radiance
+    is far from the 8-bit range of the PNG case, so Distribution2D's marginal / conditional tables
+    are strongly peaked and nearly every light sample lands in a few texels."""
+    yy, xx = np.mgrid[0:32, 0:64]
+    img = np.full((32, 64, 3), 0.05, np.float32)
+    img[(yy - 9) ** 2 + (xx - 40) ** 2 <= 4] = (900.0, 700.0, 400.0)
+    img[20:, :, 2] += 0.3
+    write_exr(str(tmp_path / "sky.exr"), img, 3, 1)
+    text = scene_text("cornel_box.pbrt", xres=72, yres=72, spp=4)
+    text = text.replace('WorldBegin\n', 'WorldBegin\nLightSource "infinite" "string mapname" "%s"\n' % str(tmp_path / "sky.exr"), 1)
+    scene = cpbrt.Scene.parse(text, base_dir=SCENES)
+    r = cpbrt.Renderer(0); r.upload(scene); r.build_bvh()
+    w = oracle.OracleWorld(scene)
+    g, gs = r.render()
+    o, _, os_ = w.render()
+    assert np.isfinite(g).all() and o.mean() > 0.05
+    bad = (_relerr(g, o).max(axis=2) > 1e-3)
+    assert bad.mean() <= 0.02, bad.mean()
     assert abs(gs.rays_any - os_["rays_any"]) <= 2e-3 * os_["rays_any"]
 
 

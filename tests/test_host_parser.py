@@ -5,7 +5,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import SCENES, scene_text
+from conftest import SCENES, scene_text, write_exr
 
 
 def test_cornell_tables(cpbrt):
@@ -170,3 +170,50 @@ def test_imported_scene_fixture_matches_reference_file_when_available(cpbrt):
     tb = np.ctypeslib.as_array(b.triangles, shape=(int(b.n_triangles),)).view(np.uint8)
     assert np.array_equal(ta, tb)
     assert list(a.lights[0].L) == list(b.lights[0].L)
+
+
+def test_exr_texture_and_environment_map(cpbrt, tmp_path):
+    """OpenEXR images (texture/image/exr.rs:7-61): channels R, G, B as f16 / f32 / u32, NONE / RLE / ZIPS /
+    ZIP scanline blocks, data window not at the origin; as an `imagemap` texture (with the 1.05 inverse
+    gamma of spectrum textures) and as the `mapname` of an infinite light (raw values)."""
+    rng = np.random.RandomState(5)
+    H, W = 37, 21                                     # 37 rows: ZIP blocks of 16 + a ragged last block of 5
+    img = (rng.rand(H, W, 3) * 4).astype(np.float32)
+    img[5:9, :, :] = 0.25                             # constant rows: runs for RLE, blocks that really shrink
+    head = ('Camera "perspective" "float fov" [40]\nSampler "halton" "integer pixelsamples" [1]\n'
+            'Film "image" "integer xresolution" [8] "integer yresolution" [8]\nIntegrator "path"\nWorldBegin\n')
+    for comp in (0, 1, 2, 3):
+        for ptype in (1, 2, 0):
+            name = "env_%d_%d.exr" % (comp, ptype)
+            src = np.floor(img * 50) if ptype == 0 else img
+            write_exr(str(tmp_path / name), src, comp, ptype, origin=(3, -2))
+            expect = src.astype(np.float16).astype(np.float32) if ptype == 1 else src.astype(np.float32)
+            s = cpbrt.Scene.parse(head + 'LightSource "infinite" "string mapname" "%s"\nMaterial "matte"\nShape "sphere"\nWorldEnd\n' % name, base_dir=str(tmp_path))
+            d = s.desc
+            tex = d.textures[d.lights[0].tex]
+            assert (tex.kind, tex.channels, tex.width, tex.height) == (cpbrt.abi.TEX_IMAGE, 3, W, H)
+            got = np.ctypeslib.as_array(d.texels, shape=(int(d.n_texels),))[tex.offset:tex.offset + W * H * 3].reshape(H, W, 3)
+            assert np.array_equal(got, expect), (comp, ptype)
+    # spectrum imagemap: same loader, then the inverse gamma of texture_map.rs:41-49
+    write_exr(str(tmp_path / "tex.exr"), img / 4, 3, 1)
+    s = cpbrt.Scene.parse(head + 'Texture "t" "spectrum" "imagemap" "string filename" "tex.exr"\n'
+                          'Material "matte" "texture Kd" "t"\nShape "sphere"\nWorldEnd\n', base_dir=str(tmp_path))
+    d = s.desc
+    tex = d.textures[d.materials[0].tex[0]]
+    v = (img / 4).astype(np.float16).astype(np.float32)
+    expect = np.where(v <= 0.04045, v / 12.92, ((v + 0.055) / 1.05) ** 2.4)
+    got = np.ctypeslib.as_array(d.texels, shape=(int(d.n_texels),))[tex.offset:tex.offset + W * H * 3].reshape(H, W, 3)
+    np.testing.assert_allclose(got, expect, rtol=2e-5, atol=1e-7)
+    # what the reference panics on is an error here: extra channels, unsupported codecs
+    bad = bytearray(open(str(tmp_path / "tex.exr"), "rb").read())
+    i = bad.index(b"compression\0compression\0") + len(b"compression\0compression\0") + 4
+    bad[i] = 4                                        # PIZ
+    open(str(tmp_path / "piz.exr"), "wb").write(bytes(bad))
+    with pytest.raises(cpbrt.CpbrtError, match="PIZ"):
+        cpbrt.Scene.parse(head + 'LightSource "infinite" "string mapname" "piz.exr"\nMaterial "matte"\nShape "sphere"\nWorldEnd\n', base_dir=str(tmp_path))
+    bad = bytearray(open(str(tmp_path / "tex.exr"), "rb").read())
+    i = bad.index(b"chlist\0") + len(b"chlist\0") + 4
+    bad[i] = ord("A")                                 # channel B renamed to A
+    open(str(tmp_path / "alpha.exr"), "wb").write(bytes(bad))
+    with pytest.raises(cpbrt.CpbrtError, match="neither R, G nor B"):
+        cpbrt.Scene.parse(head + 'LightSource "infinite" "string mapname" "alpha.exr"\nMaterial "matte"\nShape "sphere"\nWorldEnd\n', base_dir=str(tmp_path))

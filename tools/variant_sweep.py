@@ -18,13 +18,7 @@ VAR = os.path.join(PKG, "build", "variants")
 
 VARIANTS = {
     "base": [],
-    "loop12": ["-DCPBRT_REFILL_CLOSEST_LOOP=12", "-DCPBRT_REFILL_SHADOW_LOOP=12"],
-    "loop20": ["-DCPBRT_REFILL_CLOSEST_LOOP=20", "-DCPBRT_REFILL_SHADOW_LOOP=20"],
-    "loop24": ["-DCPBRT_REFILL_CLOSEST_LOOP=24", "-DCPBRT_REFILL_SHADOW_LOOP=24"],
-    "loop28": ["-DCPBRT_REFILL_CLOSEST_LOOP=28", "-DCPBRT_REFILL_SHADOW_LOOP=28"],
-    "vote12_cvb6": ["-DCPBRT_REFILL_CLOSEST_VOTE=12", "-DCPBRT_REFILL_SHADOW_VOTE=12", "-DCPBRT_BLOCKS_CLOSEST_VOTE=6"],
-    "vote16_cvb5": ["-DCPBRT_REFILL_CLOSEST_VOTE=16", "-DCPBRT_REFILL_SHADOW_VOTE=16", "-DCPBRT_BLOCKS_CLOSEST_VOTE=5"],
-    "vote8_b7": ["-DCPBRT_BLOCKS_CLOSEST_VOTE=7", "-DCPBRT_BLOCKS_SHADOW_VOTE=7"],
+    "plain": ["-DCPBRT_PLAIN_FAST=1"],
 }
 
 
@@ -60,7 +54,7 @@ def run(names, spp, c4):
                 continue
             env = dict(os.environ, CPBRT_LIB=so)
             rec = dict(variant=name, flags=VARIANTS[name])
-            if not name.startswith("vote"):      # vote* variants only change the big-tree schedule
+            if not name.startswith("vote"):      # vote* variants only change the big-tree schedule, loop* the small-tree one
                 r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--spp", str(spp), "--steps", "2", "--warmup", "2", "--no-cpu-baseline"],
                                    env=env, capture_output=True, text=True, cwd=ROOT)
                 try:
