@@ -171,8 +171,20 @@ struct BSDF {
     CP_DEV bool sample_f(const DevSampler& S, SamplerState& st, V3 wo, V3* wi, Spec* f, float* pdf, bool* is_delta) const {
         float w[2]; w[0] = (float)n_lobes; w[1] = (float)n_deltas;
         int i; float p, remap;
-        distribution_sample_remap<2>(w, 2, sampler_get_1d(S, st), &i, &p, &remap);
         bool has; float ip;
+#if CPBRT_HALTON_PAIR
+        if (NL > 0 && n_lobes > 0) {
+            // the second dimension is used whenever the non-delta group is chosen: both are drawn
+            // together (halton.cuh) and the second is handed back if a delta lobe was picked
+            const P2 uu = sampler_get_2d(S, st);
+            distribution_sample_remap<2>(w, 2, uu.x, &i, &p, &remap);
+            if (i == 0) { P2 u; u.x = remap; u.y = uu.y; has = sample_no_delta_f(wo, u, wi, f, &ip); *is_delta = false; }
+            else { st.dim -= 1; has = sample_delta_f(wo, remap, wi, f, &ip); *is_delta = true; }
+            *pdf = p * ip;
+            return has;
+        }
+#endif
+        distribution_sample_remap<2>(w, 2, sampler_get_1d(S, st), &i, &p, &remap);
         if (i == 0) { P2 u; u.x = remap; u.y = sampler_get_1d(S, st); has = sample_no_delta_f(wo, u, wi, f, &ip); *is_delta = false; }
         else { has = sample_delta_f(wo, remap, wi, f, &ip); *is_delta = true; }
         *pdf = p * ip;

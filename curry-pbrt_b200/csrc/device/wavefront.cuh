@@ -390,7 +390,7 @@ CP_DEV void emit_direct_lighting(const DevScene& sc, const PathArrays& P, uint32
     if (lane_active) {
         uint32_t flags = kPendAny;
         if (sc.n_lights != 0) {
-            const uint32_t li = sampler_get_usize(sc.sampler, st, sc.n_lights);
+            const uint32_t li = sampler_get_usize_then_2d(sc.sampler, st, sc.n_lights);   // every light's sample_li draws exactly one 2-D sample
             const DevLight& light = sc.lights[li];
             const V3 n = sp.n;
             LightSample ls = light_sample_li(sc, light, sp, st);

@@ -18,7 +18,7 @@ VAR = os.path.join(PKG, "build", "variants")
 
 VARIANTS = {
     "base": [],
-    "plain": ["-DCPBRT_PLAIN_FAST=1"],
+    "nopair": ["-DCPBRT_HALTON_PAIR=0"],
 }
 
 
