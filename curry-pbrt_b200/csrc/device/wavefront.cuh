@@ -473,7 +473,13 @@ __global__ void k_shade_terminal(DevScene sc, PathArrays P, Queues Q) {
 // Resident blocks per SM: the matte kernel (NEE + MIS + continuation) spills heavily at the 64
 // registers that 8 blocks allow; 5 blocks (96 registers, 76 B of spills) measured ~5% faster,
 // 4 and 6 no better.  The short mirror / glass kernels keep 8.
-template <int KIND> struct ShadeBlocks { static constexpr int value = KIND == SHADE_MATTE ? 5 : (KIND == SHADE_GENERAL ? 2 : 8); };
+#ifndef CPBRT_BLOCKS_MATTE
+#define CPBRT_BLOCKS_MATTE 5
+#endif
+#ifndef CPBRT_BLOCKS_SPECULAR
+#define CPBRT_BLOCKS_SPECULAR 8
+#endif
+template <int KIND> struct ShadeBlocks { static constexpr int value = KIND == SHADE_MATTE ? CPBRT_BLOCKS_MATTE : (KIND == SHADE_GENERAL ? 2 : CPBRT_BLOCKS_SPECULAR); };
 template <int KIND>
 __global__ void __launch_bounds__(128, ShadeBlocks<KIND>::value) k_shade(DevScene sc, PathArrays P, Queues Q, int next, Totals* totals) {
     typedef typename BsdfFor<KIND>::type B;

@@ -18,7 +18,9 @@ VAR = os.path.join(PKG, "build", "variants")
 
 VARIANTS = {
     "base": [],
-    "nopair": ["-DCPBRT_HALTON_PAIR=0"],
+    "matte4": ["-DCPBRT_BLOCKS_MATTE=4"],
+    "matte6": ["-DCPBRT_BLOCKS_MATTE=6"],
+    "spec6": ["-DCPBRT_BLOCKS_SPECULAR=6"],
 }
 
 
