@@ -214,11 +214,11 @@ def main():
             achieved = bytes_closest * n_closest / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else 0.0
             # DRAM traffic of the kernel from the committed ncu capture (bytes per ms of kernel time x this run's launch time)
             traffic = None
-            tpath = os.path.join(ROOT, "profiles", "r01_s2_traffic.json")
+            tpath = os.path.join(ROOT, "profiles", "r01_s3_traffic.json")
             if os.path.exists(tpath) and st.trace_launches:
                 traffic = json.load(open(tpath))["k_trace_closest"]["dram_bytes_per_ms"] * (trace_ms / st.trace_launches)
             extra["roofline"] = dict(bound="hbm", kernel="k_trace_closest", achieved=achieved, peak=peak, unit="GB/s",
-                                     frac=achieved / peak, traffic=traffic, traffic_unit="bytes per launch (ncu dram__bytes read+write, profiles/r01_s2_traffic.json)",
+                                     frac=achieved / peak, traffic=traffic, traffic_unit="bytes per launch (ncu dram__bytes read+write, profiles/r01_s3_traffic.json)",
                                      peak_source=which,
                                      algorithmic_bytes_per_ray=bytes_closest, rays_per_launch=n_closest / max(1, st.trace_launches),
                                      avg_launch_ms=trace_ms / max(1, st.trace_launches),

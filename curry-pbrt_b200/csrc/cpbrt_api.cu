@@ -770,10 +770,15 @@ int cpbrt_halton(cpbrt_ctx* ctx, const uint32_t* px, const uint32_t* py, const u
     if (!rc && index_out) rc = alloc_upload(ctx, bi, nullptr, n * 8);
     if (!rc && value_out) rc = alloc_upload(ctx, bv, nullptr, n * 4);
     cudaError_t err = cudaSuccess;
+    unsigned long long mismatches = 0;
+    if (!rc) rc = ensure_totals(ctx);
     if (!rc) {
+        unsigned long long* d_mismatch = (unsigned long long*)(ctx->d_totals + 1);
+        err = cudaMemsetAsync(d_mismatch, 0, sizeof(unsigned long long), ctx->stream);
         k_batch_halton<<<grid_for(ctx, 4), 256, 0, ctx->stream>>>(ctx->scene, (const uint32_t*)b[0].p, (const uint32_t*)b[1].p, (const uint32_t*)b[2].p,
-                                                                  (const uint32_t*)b[3].p, n, (unsigned long long*)bi.p, (float*)bv.p);
-        err = cudaGetLastError();
+                                                                  (const uint32_t*)b[3].p, n, (unsigned long long*)bi.p, (float*)bv.p, d_mismatch);
+        if (err == cudaSuccess) err = cudaGetLastError();
+        if (err == cudaSuccess) err = cudaMemcpyAsync(&mismatches, d_mismatch, sizeof mismatches, cudaMemcpyDeviceToHost, ctx->stream);
         if (err == cudaSuccess && index_out) err = cudaMemcpyAsync(index_out, bi.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream);
         if (err == cudaSuccess && value_out) err = cudaMemcpyAsync(value_out, bv.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
         if (err == cudaSuccess) err = cudaStreamSynchronize(ctx->stream);
@@ -782,6 +787,7 @@ int cpbrt_halton(cpbrt_ctx* ctx, const uint32_t* px, const uint32_t* py, const u
     bi.release(); bv.release();
     if (rc) return rc;
     if (err != cudaSuccess) return ctx->fail(CPBRT_ERR_CUDA, "halton: %s", cudaGetErrorString(err));
+    if (mismatches) return ctx->fail(CPBRT_ERR_CUDA, "halton: %llu values differ between the interleaved and the one-at-a-time evaluation", mismatches);
     return CPBRT_OK;
 }
 

@@ -724,13 +724,33 @@ __global__ void __launch_bounds__(128) k_batch_any(DevScene sc, const float4* __
 }
 
 __global__ void k_batch_halton(DevScene sc, const uint32_t* __restrict__ px, const uint32_t* __restrict__ py, const uint32_t* __restrict__ sample,
-                               const uint32_t* __restrict__ dim, uint64_t n, unsigned long long* __restrict__ index_out, float* __restrict__ value_out) {
+                               const uint32_t* __restrict__ dim, uint64_t n, unsigned long long* __restrict__ index_out, float* __restrict__ value_out,
+                               unsigned long long* __restrict__ mismatches) {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         SamplerState st;
         st.index = halton_pixel_index(sc.sampler, px[i], py[i]) + (uint64_t)sample[i] * sc.sampler.stride;
         st.dim = dim[i];
         if (index_out) index_out[i] = st.index;
-        if (value_out) value_out[i] = sampler_get_sample(sc.sampler, st);
+        if (value_out) {
+            const uint32_t d = st.dim;
+            const float v = sampler_get_sample(sc.sampler, st);
+            value_out[i] = v;
+            // The renderer evaluates runs of consecutive dimensions as interleaved chains
+            // (scrambled_radical_inverse_n, halton.cuh).  Every value asked for here is also
+            // produced that way -- as the first of a pair and of a triple, whose other members are
+            // compared with their one-at-a-time values -- so the parity test of this entry point
+            // against the oracle covers the code path the shading kernels actually take.
+            if (d >= 2 && d + 2 < 1000) {
+                float u3[3], u2[2];
+                scrambled_radical_inverse_n<3>(sc.sampler, st.index, d, u3);
+                scrambled_radical_inverse_n<2>(sc.sampler, st.index, d, u2);
+                const float v1 = scrambled_radical_inverse(sc.sampler, st.index, d + 1), v2 = scrambled_radical_inverse(sc.sampler, st.index, d + 2);
+                const bool same = __float_as_uint(u3[0]) == __float_as_uint(v) && __float_as_uint(u2[0]) == __float_as_uint(v) &&
+                                  __float_as_uint(u3[1]) == __float_as_uint(v1) && __float_as_uint(u2[1]) == __float_as_uint(v1) &&
+                                  __float_as_uint(u3[2]) == __float_as_uint(v2);
+                if (!same) atomicAdd(mismatches, 1ull);
+            }
+        }
     }
 }
 

@@ -80,6 +80,10 @@ def edge_case_rays():
 
 
 def test_halton_bit_exact(cornell):
+    """Halton indices and values against the oracle.  cpbrt_halton also evaluates every value the
+    way the shading kernels do -- as the first of an interleaved pair and triple of consecutive
+    dimensions -- and fails if any member differs from its one-at-a-time value, so this covers the
+    renderer's code path too, 64-bit indices included."""
     _, r, w, _ = cornell
     rng = np.random.RandomState(1)
     n = 200000
