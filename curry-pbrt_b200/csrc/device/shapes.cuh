@@ -34,19 +34,25 @@ CP_DEV ShapePoint shape_point_apply(const ShapePoint& s, const float* __restrict
 
 // Per-ray constants of the watertight test (triangle.rs:202-212): they depend on ray.d only,
 // so a ray that meets many untransformed triangles computes them once.
-struct TriRaySetup { int kx, ky, kz; float sx, sy, sz; };
+// kx = kz + 1 and ky = kx + 1 (mod 3): the permutation is the rotation that brings the dominant
+// axis to z, so the axis index alone selects every component (two loop-invariant predicates
+// instead of six index comparisons per primitive test).
+struct TriRaySetup { int kz; float sx, sy, sz; };
+CP_DEV V3 permute(V3 v, const TriRaySetup& s) {
+    const bool z0 = s.kz == 0, z1 = s.kz == 1;
+    return v3(z0 ? v.y : (z1 ? v.z : v.x), z0 ? v.z : (z1 ? v.x : v.y), z0 ? v.x : (z1 ? v.y : v.z));
+}
 CP_DEV TriRaySetup tri_ray_setup(V3 d) {
     TriRaySetup s;
     V3 a = vabs(d);
     int kz = 0; float m = a.x;                 // nalgebra imax: first maximum wins
     if (a.y > m) { m = a.y; kz = 1; }
     if (a.z > m) { kz = 2; }
-    s.kz = kz; s.kx = kz + 1 == 3 ? 0 : kz + 1; s.ky = s.kx + 1 == 3 ? 0 : s.kx + 1;
-    float dx = comp(d, s.kx), dy = comp(d, s.ky), dz = comp(d, s.kz);
-    s.sx = -dx / dz; s.sy = -dy / dz; s.sz = 1.f / dz;
+    s.kz = kz;
+    const V3 dp = permute(d, s);
+    s.sx = -dp.x / dp.z; s.sy = -dp.y / dp.z; s.sz = 1.f / dp.z;
     return s;
 }
-CP_DEV V3 permute(V3 v, const TriRaySetup& s) { return v3(comp(v, s.kx), comp(v, s.ky), comp(v, s.kz)); }
 
 struct TriVerts { V3 p0, p1, p2; };
 
@@ -93,9 +99,9 @@ CP_DEV void tri_barycentrics(const TriVerts& tv, V3 o, V3 d, float b[3]) {
     int kz = 0; float m = a.x;
     if (a.y > m) { m = a.y; kz = 1; }
     if (a.z > m) { kz = 2; }
-    TriRaySetup rs; rs.kz = kz; rs.kx = kz + 1 == 3 ? 0 : kz + 1; rs.ky = rs.kx + 1 == 3 ? 0 : rs.kx + 1;
-    const float dx = comp(d, rs.kx), dy = comp(d, rs.ky), dz = comp(d, rs.kz);
-    const float sx = -dx / dz, sy = -dy / dz;
+    TriRaySetup rs; rs.kz = kz;
+    const V3 dp = permute(d, rs);
+    const float sx = -dp.x / dp.z, sy = -dp.y / dp.z;
     V3 p0t = permute(tv.p0 - o, rs), p1t = permute(tv.p1 - o, rs), p2t = permute(tv.p2 - o, rs);
     p0t.x += sx * p0t.z; p0t.y += sy * p0t.z;
     p1t.x += sx * p1t.z; p1t.y += sy * p1t.z;

@@ -18,9 +18,6 @@ VAR = os.path.join(PKG, "build", "variants")
 
 VARIANTS = {
     "base": [],
-    "matte4": ["-DCPBRT_BLOCKS_MATTE=4"],
-    "matte6": ["-DCPBRT_BLOCKS_MATTE=6"],
-    "spec6": ["-DCPBRT_BLOCKS_SPECULAR=6"],
 }
 
 
