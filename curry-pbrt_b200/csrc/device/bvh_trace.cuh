@@ -78,13 +78,13 @@ struct TaskStack {
 //   refill  idle lanes a warp waits for before it writes results back and fetches new rays
 static constexpr int kTraceBlock = 128;
 #ifndef CPBRT_BLOCKS_CLOSEST_LOOP
-#define CPBRT_BLOCKS_CLOSEST_LOOP 8
+#define CPBRT_BLOCKS_CLOSEST_LOOP 7
 #endif
 #ifndef CPBRT_BLOCKS_CLOSEST_VOTE
 #define CPBRT_BLOCKS_CLOSEST_VOTE 6
 #endif
 #ifndef CPBRT_BLOCKS_SHADOW_LOOP
-#define CPBRT_BLOCKS_SHADOW_LOOP 8
+#define CPBRT_BLOCKS_SHADOW_LOOP 7
 #endif
 #ifndef CPBRT_BLOCKS_SHADOW_VOTE
 #define CPBRT_BLOCKS_SHADOW_VOTE 8

@@ -18,6 +18,12 @@ VAR = os.path.join(PKG, "build", "variants")
 
 VARIANTS = {
     "base": [],
+    # examples of what has been swept (profiles/r01_s3_variant_sweeps.jsonl):
+    "closest_loop_8_blocks": ["-DCPBRT_BLOCKS_CLOSEST_LOOP=8"],
+    "loop_refill_12": ["-DCPBRT_REFILL_CLOSEST_LOOP=12", "-DCPBRT_REFILL_SHADOW_LOOP=12"],
+    "vote_refill_8": ["-DCPBRT_REFILL_CLOSEST_VOTE=8", "-DCPBRT_REFILL_SHADOW_VOTE=8"],
+    "halton_one_by_one": ["-DCPBRT_HALTON_PAIR=0"],
+    "matte_4_blocks": ["-DCPBRT_BLOCKS_MATTE=4"],
 }
 
 
