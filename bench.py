@@ -86,7 +86,18 @@ class ClockSampler(threading.Thread):
         return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons, n=len(self.samples))
 
 
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints its
+    version banner to fd 1 when the communicator is created), so fd 1 is pointed at stderr for the
+    whole run and the JSON line goes to a private copy of the real stdout."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(real, "w")
+
+
 def main():
+    json_out = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -122,12 +133,13 @@ def main():
         n = sum(v["samples"] for v in vals)
         v = n / sec / 1e6
         sample = "whole film %s at %d spp (%d samples) of the 1024 per step" % (list(vals[0]["rect"]), args.cpu_spp, vals[0]["samples"])
-        print(json.dumps(dict(metric="Msamples/s", value=v, unit="Msamples/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+        json_out.write(json.dumps(dict(metric="Msamples/s", value=v, unit="Msamples/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                               ms_per_step=1e3 * sec / len(vals), higher_is_better=True, scaling="strong", vs_baseline=None,
                               dtype="f32", data="synthetic", impl="reference", config=config,
                               mrays_s=sum(x["mrays_s"] * x["seconds"] for x in vals) / sec,
                               cpu_baseline=dict(value=v, unit="Msamples/s", cores=threads, kind="port", sample=sample),
-                              e2e=dict(value=v, unit="Msamples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
+                              e2e=dict(value=v, unit="Msamples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))) + "\n")
+        json_out.flush()
         return 0
 
     import numpy as np
@@ -258,7 +270,8 @@ def main():
                    gpu_launches=launches,
                    device_ms_per_step=dev_ms / args.steps, wall_ms_per_step=wall_ms / args.steps, clocks=clocks.summary())
         out.update(extra)
-        print(json.dumps(out))
+        json_out.write(json.dumps(out) + "\n")
+        json_out.flush()
     if world > 1:
         dist.destroy_process_group()
     return 0
