@@ -145,9 +145,11 @@ def test_plymesh_and_include(cpbrt, tmp_path):
     mesh_text = 'Shape "trianglemesh" "integer indices" [%s] "point P" [%s]\n' % (
         " ".join(str(i) for i in faces.ravel()), " ".join(repr(float(x)) for x in verts.ravel()))
     (tmp_path / "inc.pbrt").write_text('Shape "plymesh" "string filename" "m.ply"\n')
-    a = cpbrt.Scene.parse(head + mesh_text + "WorldEnd\n", base_dir=str(tmp_path)).desc
-    b = cpbrt.Scene.parse(head + 'Shape "plymesh" "string filename" "m.ply"\nWorldEnd\n', base_dir=str(tmp_path)).desc
-    c = cpbrt.Scene.parse(head + 'Include "inc.pbrt"\nWorldEnd\n', base_dir=str(tmp_path)).desc
+    # the Scene objects own the arrays their descriptions point into: keep them alive while comparing
+    scene_a = cpbrt.Scene.parse(head + mesh_text + "WorldEnd\n", base_dir=str(tmp_path))
+    scene_b = cpbrt.Scene.parse(head + 'Shape "plymesh" "string filename" "m.ply"\nWorldEnd\n', base_dir=str(tmp_path))
+    scene_c = cpbrt.Scene.parse(head + 'Include "inc.pbrt"\nWorldEnd\n', base_dir=str(tmp_path))
+    a, b, c = scene_a.desc, scene_b.desc, scene_c.desc
     assert a.n_triangles > 0
     ta = np.ctypeslib.as_array(a.triangles, shape=(int(a.n_triangles),)).view(np.uint8).copy()
     for other in (b, c):
@@ -164,7 +166,8 @@ def test_imported_scene_fixture_matches_reference_file_when_available(cpbrt):
     ref = "/root/reference/scenes/cornel_box.pbrt"
     if not os.path.exists(ref):
         pytest.skip("reference checkout not present (GPU box)")
-    a, b = cpbrt.Scene.load(ref).desc, cpbrt.Scene.load(os.path.join(SCENES, "cornel_box.pbrt")).desc
+    scene_a, scene_b = cpbrt.Scene.load(ref), cpbrt.Scene.load(os.path.join(SCENES, "cornel_box.pbrt"))   # owners of the arrays below
+    a, b = scene_a.desc, scene_b.desc
     assert a.n_primitives == b.n_primitives and a.n_triangles == b.n_triangles
     ta = np.ctypeslib.as_array(a.triangles, shape=(int(a.n_triangles),)).view(np.uint8)
     tb = np.ctypeslib.as_array(b.triangles, shape=(int(b.n_triangles),)).view(np.uint8)
