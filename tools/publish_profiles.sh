@@ -6,6 +6,7 @@ set -e
 TAG=${1:?tag}
 G=gpurun_out
 P=profiles
+grep '^"' $G/${TAG}_launches.csv > $P/${TAG}_launches.csv
 for f in bench.json bench_reference.json configs.jsonl traversal_c4.jsonl bvh_build.jsonl schedule_crossover.jsonl; do cp $G/${TAG}_$f $P/${TAG}_$f; done
 python - "$TAG" <<'PY'
 import json, subprocess, sys
