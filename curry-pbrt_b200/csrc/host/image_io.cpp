@@ -82,8 +82,8 @@ bool read_png_rgb8(const std::string& path, uint32_t* w, uint32_t* h, std::vecto
 // `exr` crate (0.7.4) and copies the channels named R, G and B -- f16, f32 or u32 samples, each
 // converted to f32 -- into an RGB buffer in data-window row order; any other channel name panics
 // there and is an error here.  This reader covers single-part scanline files, uncompressed or with
-// the RLE / ZIPS / ZIP codecs (the byte-level ones; zlib is already linked for PNG).  Tiled, deep and
-// multi-part files and the lossy / wavelet codecs (PIZ, PXR24, B44, DWA) are rejected by name.
+// the lossless RLE / ZIPS / ZIP / PIZ codecs (zlib is already linked for PNG).  Tiled, deep and
+// multi-part files and the lossy codecs (PXR24, B44, DWA) are rejected by name.
 static float half_to_float(uint16_t h) {
     const uint32_t sign = (uint32_t)(h & 0x8000u) << 16;
     uint32_t exp = (h >> 10) & 0x1Fu, man = h & 0x3FFu, bits;
@@ -119,6 +119,190 @@ static void exr_unfilter(std::vector<uint8_t>& t, std::vector<uint8_t>& out) {
     const size_t half = (t.size() + 1) / 2;
     for (size_t i = 0; i < t.size(); ++i) out[i] = (i & 1) ? t[half + i / 2] : t[i / 2];
 }
+
+// ---- PIZ codec (OpenEXR's default for photographs; published format: ImfPizCompressor / ImfHuf / ImfWav) ----
+// A block is: the range [min, max] of non-zero bytes of a 65536-bit "value occurs" bitmap and those
+// bytes, then a canonical-Huffman stream of 16-bit symbols (with a run-length escape symbol).  The
+// symbols are the 2-D Haar-like wavelet coefficients of every channel (per 16-bit half of a 32-bit
+// sample), computed on values that were first mapped through the bitmap's rank table.
+namespace {
+struct PizBits {
+    const uint8_t* in; const uint8_t* end; uint64_t c = 0; int lc = 0;
+    void byte() { c = (c << 8) | (in < end ? *in : 0); ++in; lc += 8; }
+    uint32_t get(int n) { while (lc < n) byte(); lc -= n; return (uint32_t)((c >> lc) & ((1u << n) - 1u)); }
+};
+constexpr int kHufEncSize = (1 << 16) + 1, kHufDecBits = 14, kHufDecSize = 1 << kHufDecBits;
+struct HufDec { int len = 0; uint32_t lit = 0; std::vector<uint32_t> longs; };
+
+bool huf_uncompress(const uint8_t* data, size_t n, std::vector<uint16_t>& out) {
+    if (n == 0) return out.empty();
+    if (n < 20) return false;
+    auto u32 = [&](size_t o) { uint32_t v; memcpy(&v, data + o, 4); return v; };
+    uint32_t im = u32(0); const uint32_t iM = u32(4), n_bits = u32(12);
+    if (im >= (uint32_t)kHufEncSize || iM >= (uint32_t)kHufEncSize) return false;
+    // code lengths, 6 bits each, runs of zeros packed (59..62: 2..5 zeros, 63: 6 + next 8 bits)
+    std::vector<uint64_t> code(kHufEncSize, 0);
+    PizBits tb{data + 20, data + n};
+    for (uint32_t i = im; i <= iM; ++i) {
+        const uint32_t l = tb.get(6);
+        code[i] = l;
+        if (l == 63) { uint32_t z = tb.get(8) + 6; if (i + z > iM + 1) return false; while (z--) code[i++] = 0; --i; }
+        else if (l >= 59) { uint32_t z = l - 59 + 2; if (i + z > iM + 1) return false; while (z--) code[i++] = 0; --i; }
+    }
+    const uint8_t* bits = tb.in;
+    if (bits > data + n) return false;
+    // canonical codes: shorter codes have numerically larger prefixes
+    uint64_t cnt[59] = {0};
+    for (int i = 0; i < kHufEncSize; ++i) { if (code[i] > 58) return false; ++cnt[code[i]]; }
+    uint64_t c = 0;
+    for (int i = 58; i > 0; --i) { const uint64_t nc = (c + cnt[i]) >> 1; cnt[i] = c; c = nc; }
+    for (int i = 0; i < kHufEncSize; ++i) { const uint64_t l = code[i]; if (l > 0) code[i] = l | (cnt[l]++ << 6); }
+    // decoding table indexed by the next 14 bits
+    std::vector<HufDec> dec(kHufDecSize);
+    for (uint32_t i = im; i <= iM; ++i) {
+        const uint64_t cd = code[i] >> 6; const int l = (int)(code[i] & 63);
+        if (l == 0) continue;
+        if (cd >> l) return false;
+        if (l > kHufDecBits) { HufDec& d = dec[cd >> (l - kHufDecBits)]; if (d.len) return false; d.longs.push_back(i); }
+        else { HufDec* d = &dec[cd << (kHufDecBits - l)]; for (uint64_t k = 1ull << (kHufDecBits - l); k > 0; --k, ++d) { if (d->len || !d->longs.empty()) return false; d->len = l; d->lit = i; } }
+    }
+    const size_t want = out.size(); size_t no = 0;
+    PizBits b{bits, data + n};
+    const uint8_t* ie = bits + (n_bits + 7) / 8;
+    if (ie > data + n) return false;
+    auto emit = [&](uint32_t sym) -> bool {
+        if (sym == iM) {                      // run-length escape: repeat the previous symbol `next 8 bits` times
+            if (b.lc < 8) b.byte();
+            b.lc -= 8;
+            uint32_t run = (uint32_t)((b.c >> b.lc) & 0xFF);
+            if (no == 0 || no + run > want) return false;
+            const uint16_t v = out[no - 1];
+            while (run--) out[no++] = v;
+            return true;
+        }
+        if (no >= want) return false;
+        out[no++] = (uint16_t)sym;
+        return true;
+    };
+    while (b.in < ie) {
+        b.byte();
+        while (b.lc >= kHufDecBits) {
+            const HufDec& d = dec[(b.c >> (b.lc - kHufDecBits)) & (kHufDecSize - 1)];
+            if (d.len) { b.lc -= d.len; if (!emit(d.lit)) return false; }
+            else {
+                if (d.longs.empty()) return false;
+                size_t j = 0;
+                for (; j < d.longs.size(); ++j) {
+                    const int l = (int)(code[d.longs[j]] & 63);
+                    while (b.lc < l && b.in < ie) b.byte();
+                    if (b.lc >= l && (code[d.longs[j]] >> 6) == ((b.c >> (b.lc - l)) & ((1ull << l) - 1))) { b.lc -= l; if (!emit(d.longs[j])) return false; break; }
+                }
+                if (j == d.longs.size()) return false;
+            }
+        }
+    }
+    const int pad = (8 - (int)n_bits) & 7;     // the last byte's unused low bits
+    b.c >>= pad; b.lc -= pad;
+    while (b.lc > 0) {
+        const HufDec& d = dec[(b.c << (kHufDecBits - b.lc)) & (kHufDecSize - 1)];
+        if (!d.len) return false;
+        b.lc -= d.len;
+        if (!emit(d.lit)) return false;
+    }
+    return no == want;
+}
+
+inline void wdec14(uint16_t l, uint16_t h, uint16_t& a, uint16_t& b) {
+    const int ls = (int16_t)l, hi = (int16_t)h;
+    const int ai = ls + (hi & 1) + (hi >> 1);
+    a = (uint16_t)(int16_t)ai; b = (uint16_t)(int16_t)(ai - hi);
+}
+inline void wdec16(uint16_t l, uint16_t h, uint16_t& a, uint16_t& b) {
+    const int m = l, d = h;
+    const int bb = (m - (d >> 1)) & 0xFFFF;
+    const int aa = (d + bb - 0x8000) & 0xFFFF;
+    b = (uint16_t)bb; a = (uint16_t)aa;
+}
+// inverse of the hierarchical 2-D wavelet transform over an nx x ny grid with strides ox, oy
+void wav2_decode(uint16_t* in, int nx, int ox, int ny, int oy, uint16_t mx) {
+    const bool w14 = mx < (1 << 14);
+    const int n = nx > ny ? ny : nx;
+    int p = 1, p2;
+    while (p <= n) p <<= 1;
+    p >>= 1; p2 = p; p >>= 1;
+    while (p >= 1) {
+        uint16_t* py = in;
+        uint16_t* const ey = in + (ptrdiff_t)oy * (ny - p2);
+        const ptrdiff_t oy1 = (ptrdiff_t)oy * p, oy2 = (ptrdiff_t)oy * p2, ox1 = (ptrdiff_t)ox * p, ox2 = (ptrdiff_t)ox * p2;
+        uint16_t i00, i01, i10, i11;
+        for (; py <= ey; py += oy2) {
+            uint16_t* px = py;
+            uint16_t* const ex = py + (ptrdiff_t)ox * (nx - p2);
+            for (; px <= ex; px += ox2) {
+                uint16_t *p01 = px + ox1, *p10 = px + oy1, *p11 = p10 + ox1;
+                if (w14) { wdec14(*px, *p10, i00, i10); wdec14(*p01, *p11, i01, i11); wdec14(i00, i01, *px, *p01); wdec14(i10, i11, *p10, *p11); }
+                else { wdec16(*px, *p10, i00, i10); wdec16(*p01, *p11, i01, i11); wdec16(i00, i01, *px, *p01); wdec16(i10, i11, *p10, *p11); }
+            }
+            if (nx & p) {      // odd column
+                uint16_t* p10 = px + oy1;
+                if (w14) wdec14(*px, *p10, i00, *p10); else wdec16(*px, *p10, i00, *p10);
+                *px = i00;
+            }
+        }
+        if (ny & p) {          // odd line
+            uint16_t* px = py;
+            uint16_t* const ex = py + (ptrdiff_t)ox * (nx - p2);
+            for (; px <= ex; px += ox2) {
+                uint16_t* p01 = px + ox1;
+                if (w14) wdec14(*px, *p01, i00, *p01); else wdec16(*px, *p01, i00, *p01);
+                *px = i00;
+            }
+        }
+        p2 = p; p >>= 1;
+    }
+}
+
+// One PIZ block -> the block's bytes in the uncompressed scanline layout.  words[c] = 16-bit words per sample of channel c.
+bool piz_decode_block(const uint8_t* src, size_t size, const std::vector<int>& words, int nx, int ny, std::vector<uint8_t>& raw) {
+    if (size < 4) return false;
+    uint16_t min_nz, max_nz; memcpy(&min_nz, src, 2); memcpy(&max_nz, src + 2, 2);
+    size_t pos = 4;
+    std::vector<uint8_t> bitmap(8192, 0);
+    if (min_nz <= max_nz) {
+        if (max_nz >= 8192 || pos + (size_t)(max_nz - min_nz + 1) > size) return false;
+        memcpy(bitmap.data() + min_nz, src + pos, (size_t)(max_nz - min_nz + 1));
+        pos += (size_t)(max_nz - min_nz + 1);
+    }
+    std::vector<uint16_t> lut(65536, 0);
+    int k = 0;
+    for (int i = 0; i < 65536; ++i) if (i == 0 || (bitmap[i >> 3] & (1 << (i & 7)))) lut[k++] = (uint16_t)i;
+    const uint16_t max_value = (uint16_t)(k - 1);
+    if (pos + 4 > size) return false;
+    int32_t length; memcpy(&length, src + pos, 4); pos += 4;
+    if (length < 0 || pos + (size_t)length > size) return false;
+    size_t total = 0;
+    for (int w : words) total += (size_t)w * nx * ny;
+    std::vector<uint16_t> tmp(total);
+    if (!huf_uncompress(src + pos, (size_t)length, tmp)) return false;
+    size_t off = 0;
+    std::vector<size_t> start(words.size());
+    for (size_t c = 0; c < words.size(); ++c) {
+        start[c] = off;
+        for (int j = 0; j < words[c]; ++j) wav2_decode(tmp.data() + off + j, nx, words[c], ny, nx * words[c], max_value);
+        off += (size_t)words[c] * nx * ny;
+    }
+    for (auto& v : tmp) v = lut[v];
+    raw.resize(total * 2);
+    uint8_t* q = raw.data();
+    for (int y = 0; y < ny; ++y)
+        for (size_t c = 0; c < words.size(); ++c) {
+            const size_t n = (size_t)nx * words[c];
+            memcpy(q, tmp.data() + start[c] + (size_t)y * n, n * 2);
+            q += n * 2;
+        }
+    return true;
+}
+}  // namespace
 
 bool read_exr_rgb(const std::string& path, uint32_t* w, uint32_t* h, std::vector<float>* rgb, std::string* err) {
     std::ifstream f(path, std::ios::binary);
@@ -159,13 +343,13 @@ bool read_exr_rgb(const std::string& path, uint32_t* w, uint32_t* h, std::vector
     }
     if (channels.empty() || compression < 0 || !have_window || win[2] < win[0] || win[3] < win[1]) { *err = "incomplete OpenEXR header: " + path; return false; }
     static const char* codec_names[] = {"NONE", "RLE", "ZIPS", "ZIP", "PIZ", "PXR24", "B44", "B44A", "DWAA", "DWAB"};
-    if (compression > 3) {
-        *err = std::string("OpenEXR compression ") + (compression < 10 ? codec_names[compression] : "?") + " is not supported (NONE, RLE, ZIPS, ZIP are): " + path;
+    if (compression > 4) {
+        *err = std::string("OpenEXR compression ") + (compression < 10 ? codec_names[compression] : "?") + " is not supported (NONE, RLE, ZIPS, ZIP, PIZ are): " + path;
         return false;
     }
     const uint64_t W = (uint64_t)((int64_t)win[2] - win[0] + 1), H = (uint64_t)((int64_t)win[3] - win[1] + 1);
     if (W > (1u << 20) || H > (1u << 20)) { *err = "OpenEXR data window too large: " + path; return false; }
-    const uint32_t lines_per_block = compression == 3 ? 16u : 1u;
+    const uint32_t lines_per_block = compression == 3 ? 16u : (compression == 4 ? 32u : 1u);
     const uint64_t n_blocks = (H + lines_per_block - 1) / lines_per_block;
     size_t line_bytes = 0;
     for (const auto& ch : channels) line_bytes += (ch.type == 1 ? 2 : 4) * (size_t)W;
@@ -196,6 +380,10 @@ bool read_exr_rgb(const std::string& path, uint32_t* w, uint32_t* h, std::vector
             }
             if (tmp.size() != want) { *err = "OpenEXR RLE block has the wrong length: " + path; return false; }
             exr_unfilter(tmp, raw);
+        } else if (compression == 4) {
+            std::vector<int> words;
+            for (const auto& ch : channels) words.push_back(ch.type == 1 ? 1 : 2);
+            if (!piz_decode_block(src, size, words, (int)W, (int)rows, raw) || raw.size() != want) { *err = "OpenEXR PIZ block could not be decoded: " + path; return false; }
         } else {                                     // ZIPS / ZIP: zlib stream
             tmp.assign(want, 0);
             uLongf out_len = want;

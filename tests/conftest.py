@@ -35,6 +35,7 @@ def oracle():
 
 
 SCENES = os.path.join(ROOT, "scenes")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
 def scene_text(name, xres=None, yres=None, spp=None, integrator=None):

@@ -5,7 +5,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import SCENES, scene_text, write_exr
+from conftest import GOLDEN, SCENES, scene_text, write_exr
 
 
 def test_cornell_tables(cpbrt):
@@ -207,16 +207,35 @@ def test_exr_texture_and_environment_map(cpbrt, tmp_path):
     expect = np.where(v <= 0.04045, v / 12.92, ((v + 0.055) / 1.05) ** 2.4)
     got = np.ctypeslib.as_array(d.texels, shape=(int(d.n_texels),))[tex.offset:tex.offset + W * H * 3].reshape(H, W, 3)
     np.testing.assert_allclose(got, expect, rtol=2e-5, atol=1e-7)
-    # what the reference panics on is an error here: extra channels, unsupported codecs
+    # what the reference panics on is an error here (extra channels); lossy codecs are rejected by name
     bad = bytearray(open(str(tmp_path / "tex.exr"), "rb").read())
     i = bad.index(b"compression\0compression\0") + len(b"compression\0compression\0") + 4
-    bad[i] = 4                                        # PIZ
-    open(str(tmp_path / "piz.exr"), "wb").write(bytes(bad))
-    with pytest.raises(cpbrt.CpbrtError, match="PIZ"):
-        cpbrt.Scene.parse(head + 'LightSource "infinite" "string mapname" "piz.exr"\nMaterial "matte"\nShape "sphere"\nWorldEnd\n', base_dir=str(tmp_path))
+    bad[i] = 5                                        # PXR24 (lossy)
+    open(str(tmp_path / "pxr24.exr"), "wb").write(bytes(bad))
+    with pytest.raises(cpbrt.CpbrtError, match="PXR24"):
+        cpbrt.Scene.parse(head + 'LightSource "infinite" "string mapname" "pxr24.exr"\nMaterial "matte"\nShape "sphere"\nWorldEnd\n', base_dir=str(tmp_path))
     bad = bytearray(open(str(tmp_path / "tex.exr"), "rb").read())
     i = bad.index(b"chlist\0") + len(b"chlist\0") + 4
     bad[i] = ord("A")                                 # channel B renamed to A
     open(str(tmp_path / "alpha.exr"), "wb").write(bytes(bad))
     with pytest.raises(cpbrt.CpbrtError, match="neither R, G nor B"):
         cpbrt.Scene.parse(head + 'LightSource "infinite" "string mapname" "alpha.exr"\nMaterial "matte"\nShape "sphere"\nWorldEnd\n', base_dir=str(tmp_path))
+
+
+@pytest.mark.parametrize("name", ["piz_half", "piz_float", "zip_half", "zips_float", "rle_half", "none_float"])
+def test_exr_files_written_by_openexr(cpbrt, name):
+    """Fixtures encoded by the OpenEXR library itself (through OpenCV, tests/golden/make_exr_golden.py), so
+    the reader is checked against an encoder that shares nothing with this repository -- including PIZ
+    (Huffman + wavelet), which the test-suite's own writer does not produce."""
+    src = np.load(os.path.join(GOLDEN, "exr", "exr_source.npz"))["rgb"]
+    head = ('Camera "perspective" "float fov" [40]\nSampler "halton" "integer pixelsamples" [1]\n'
+            'Film "image" "integer xresolution" [8] "integer yresolution" [8]\nIntegrator "path"\nWorldBegin\n')
+    s = cpbrt.Scene.parse(head + 'LightSource "infinite" "string mapname" "%s.exr"\nMaterial "matte"\nShape "sphere"\nWorldEnd\n' % name,
+                          base_dir=os.path.join(GOLDEN, "exr"))
+    d = s.desc
+    tex = d.textures[d.lights[0].tex]
+    H, W, _ = src.shape
+    assert (tex.width, tex.height, tex.channels) == (W, H, 3)
+    got = np.ctypeslib.as_array(d.texels, shape=(int(d.n_texels),))[tex.offset:tex.offset + W * H * 3].reshape(H, W, 3)
+    expect = src.astype(np.float16).astype(np.float32) if name.endswith("half") else src
+    assert np.array_equal(got, expect)
