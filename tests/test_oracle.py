@@ -56,6 +56,34 @@ def test_radical_inverse_against_python(cpbrt, oracle):
             assert np.float32(oracle.lib.orc_radical_inverse(int(x), bi)) == rad_inv(int(x), base)
 
 
+def test_scrambled_radical_inverse_against_exact_arithmetic(cpbrt, oracle, make_scene):
+    """Dimensions >= 2 (halton.rs:56-64): digits of the index in base PRIMS[dim], each replaced through the
+    dimension's block of the permutation table, plus the infinite tail of permuted zero digits.  Recomputed
+    here with Python integers / Fractions (no rounding at all) from the index the oracle reports; the
+    oracle's f32 value must be the exact one to within the rounding of its three f32 operations."""
+    from fractions import Fraction
+    perm = np.zeros(cpbrt.abi.PERM_TABLE_LEN, np.uint16)
+    cpbrt.lib.cpbrt_make_permutation(1, perm.ctypes.data_as(C.POINTER(C.c_uint16)))
+    primes = [p for p in range(2, 8000) if all(p % q for q in range(2, int(p ** 0.5) + 1))][:1000]
+    offsets = np.concatenate([[0], np.cumsum(primes)])
+    w = oracle.OracleWorld(make_scene("cornel_box.pbrt", xres=64, yres=48, spp=4))
+    rng = np.random.RandomState(3)
+    n = 3000
+    px = rng.randint(0, 64, n).astype(np.uint32); py = rng.randint(0, 48, n).astype(np.uint32)
+    sample = rng.randint(0, 1 << 22, n).astype(np.uint32)
+    dim = rng.randint(2, 1000, n).astype(np.uint32)
+    dim[:60] = np.arange(2, 62)
+    idx, val = w.halton(px, py, sample, dim)
+    assert idx.max() > 2 ** 32
+    for i in range(n):
+        b, block = primes[dim[i]], perm[offsets[dim[i]]:offsets[dim[i]] + primes[dim[i]]]
+        x, rev, digits = int(idx[i]), 0, 0
+        while x:
+            rev = rev * b + int(block[x % b]); x //= b; digits += 1
+        exact = (Fraction(rev) + Fraction(int(block[0]), b - 1)) / Fraction(b) ** digits
+        assert abs(Fraction(float(val[i])) - exact) <= exact * Fraction(4, 2 ** 23) + Fraction(1, 2 ** 40), (i, dim[i], float(val[i]), float(exact))
+
+
 def test_permutation_table_is_blockwise_permutation(cpbrt):
     perm = np.zeros(cpbrt.abi.PERM_TABLE_LEN, np.uint16)
     cpbrt.lib.cpbrt_make_permutation(1, perm.ctypes.data_as(C.POINTER(C.c_uint16)))
