@@ -116,6 +116,71 @@ def test_bvh_closest_equals_brute_force(make_scene, oracle):
     assert differ.mean() < 1e-3          # only ties
 
 
+def test_closest_hits_against_float64_geometry(cpbrt, make_scene, oracle):
+    """The oracle's closest hits (watertight f32 triangle test, f64-quadratic sphere under a transform,
+    BVH with the reference's visiting rules) against a formulation that shares nothing with it:
+    Moeller-Trumbore triangles and an analytic sphere, all primitives for every ray, in float64.
+    Rays whose answer depends on rounding (two hits within 1e-4 of each other, a hit within 1e-5
+    of a triangle edge, grazing incidence) are set aside; every other ray must name the same
+    primitive at the same distance."""
+    scene = make_scene("cornel_box.pbrt", xres=32, yres=32, spp=1)
+    d = scene.desc
+    w = oracle.OracleWorld(scene)
+    rays = lcg_rays(20000, (0, 0, -100), (556, 548, 559), seed=23)
+    o, dr = rays[:, 0:3].astype(np.float64), rays[:, 4:7].astype(np.float64)
+    n = len(rays)
+    T = np.full((n, int(d.n_primitives)), np.inf)
+    edge_margin = np.full((n, int(d.n_primitives)), np.inf)
+    for k in range(int(d.n_primitives)):
+        sh = d.primitives[k].shape
+        oo, dd = o, dr
+        x = sh.xform
+        chain = []
+        while x >= 0:
+            chain.append(x); x = d.transforms[x].outer
+        for x in reversed(chain):            # world -> object through the inverse matrices, outermost first
+            mi = np.array(list(d.transforms[x].m_inv), np.float64).reshape(4, 4)
+            oo = oo @ mi[:3, :3].T + mi[:3, 3]; dd = dd @ mi[:3, :3].T
+        if sh.kind == cpbrt.abi.SHAPE_TRIANGLE:
+            tri = np.array([list(v) for v in d.triangles[sh.data].p], np.float64)
+            e1, e2 = tri[1] - tri[0], tri[2] - tri[0]
+            pv = np.cross(dd, e2); det = pv @ e1
+            with np.errstate(divide="ignore", invalid="ignore"):
+                inv = 1.0 / det
+                tv = oo - tri[0]; u = (tv * pv).sum(1) * inv
+                qv = np.cross(tv, e1); v = (dd * qv).sum(1) * inv
+                t = qv @ e2 * inv
+            ok = (np.abs(det) > 1e-9) & (u >= 0) & (v >= 0) & (u + v <= 1) & (t > 1e-6)
+            T[ok, k] = t[ok]
+            cosang = np.abs(det) / (np.linalg.norm(dd, axis=1) * np.linalg.norm(np.cross(e1, e2)))
+            m = np.minimum(np.minimum(np.abs(u), np.abs(v)), np.abs(1 - u - v))
+            m = np.where(cosang < 1e-3, 0.0, m)          # grazing rays count as ambiguous
+            edge_margin[:, k] = np.where(np.isfinite(m), m, 0.0)
+        else:
+            r = float(d.sphere_radius[sh.data])
+            a = (dd * dd).sum(1); b = 2 * (dd * oo).sum(1); c = (oo * oo).sum(1) - r * r
+            disc = b * b - 4 * a * c
+            sq = np.sqrt(np.maximum(disc, 0))
+            t0, t1 = (-b - sq) / (2 * a), (-b + sq) / (2 * a)
+            t = np.where(t0 > 1e-6, t0, t1)
+            ok = (disc > 0) & (t > 1e-6)
+            T[ok, k] = t[ok]
+            edge_margin[:, k] = np.where(disc > 0, sq / np.maximum(np.abs(b), 1e-30), 0.0)   # tangent rays are ambiguous
+    best = T.argmin(1); tb = T[np.arange(n), best]
+    Ts = np.sort(T, 1)
+    hit = np.isfinite(tb)
+    with np.errstate(invalid="ignore"):
+        gap = np.where(np.isfinite(Ts[:, 1]), Ts[:, 1] - Ts[:, 0], np.inf)
+    clear = hit & (gap > 1e-4 * np.maximum(1.0, Ts[:, 0])) & (edge_margin[np.arange(n), best] > 1e-5)
+    # misses must be clear too: no primitive may be missed only by a hair -- inside a closed box nearly every ray hits
+    got = w.trace_closest(rays)
+    assert clear.sum() > 0.7 * n          # the box is open towards the camera: a fifth of the rays leave through the front
+    assert np.array_equal(got["prim"][clear], best[clear].astype(np.uint32))
+    np.testing.assert_allclose(got["t"][clear], tb[clear], rtol=2e-5, atol=1e-4)   # f32 coordinates of magnitude 500
+    miss = ~hit
+    assert np.all(got["prim"][miss & (edge_margin.min(1) > 1e-5)] == 0xFFFFFFFF)
+
+
 def test_any_hit_consistent_with_closest(make_scene, oracle):
     w = oracle.OracleWorld(make_scene("cornel_box.pbrt"))
     rays = _scene_bbox_rays(20000, seed=11)
