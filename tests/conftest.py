@@ -142,3 +142,13 @@ def write_exr(path, img, compression, pixel_type, origin=(0, 0)):
         pos += len(b)
     with open(path, "wb") as f:
         f.write(header + struct.pack("<%dQ" % len(blocks), *offsets) + b"".join(blocks))
+
+
+def furnace_scene_text(integrator, kd, spp=256, res=24):
+    """White furnace: a convex matte sphere inside a constant environment of radiance 1.  No path can
+    bounce twice on a convex body, so the exitant radiance is exactly Kd wherever the sphere covers the
+    pixel and exactly 1 elsewhere, whatever the integrator, the sampling strategy or the MIS weights."""
+    return ('Camera "perspective" "float fov" [40]\nSampler "halton" "integer pixelsamples" [%d]\n'
+            'Film "image" "integer xresolution" [%d] "integer yresolution" [%d]\nIntegrator "%s" "integer maxdepth" [5]\nWorldBegin\n'
+            'LightSource "infinite"\nMaterial "matte" "rgb Kd" [%g %g %g]\nTranslate 0 0 5\nShape "sphere" "float radius" [1.2]\nWorldEnd\n'
+            % (spp, res, res, integrator, kd, kd * 0.5, kd * 0.25))

@@ -10,7 +10,7 @@ import re
 import numpy as np
 import pytest
 
-from conftest import SCENES, lcg_rays, scene_text, write_exr
+from conftest import SCENES, furnace_scene_text, lcg_rays, scene_text, write_exr
 from test_oracle import _synthetic_mesh_scene
 
 pytestmark = pytest.mark.gpu
@@ -520,6 +520,21 @@ def test_hdr_exr_environment_map(cpbrt, oracle, tmp_path):
     bad = (_relerr(g, o).max(axis=2) > 1e-3)
     assert bad.mean() <= 0.02, bad.mean()
     assert abs(gs.rays_any - os_["rays_any"]) <= 2e-3 * os_["rays_any"]
+
+
+@pytest.mark.parametrize("integrator", ["path", "directlighting"])
+def test_white_furnace(cpbrt, integrator):
+    """Analytic answer, no oracle involved: a convex matte sphere in a constant environment of radiance 1
+    shows exactly its Kd (conftest.furnace_scene_text)."""
+    kd = 0.8
+    r = cpbrt.Renderer(0)
+    r.upload(cpbrt.Scene.parse(furnace_scene_text(integrator, kd)))
+    r.build_bvh()
+    film, st = r.render()
+    assert st.nan_dropped == 0
+    np.testing.assert_allclose(film[10:14, 10:14].mean(axis=(0, 1)), [kd, kd * 0.5, kd * 0.25], rtol=2e-3)
+    np.testing.assert_allclose(film[0, 0], [1, 1, 1], rtol=1e-6)
+    r.close()
 
 
 def test_thin_lens_camera(cpbrt, oracle):

@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import SCENES, lcg_rays, scene_text
+from conftest import SCENES, furnace_scene_text, lcg_rays, scene_text
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -114,6 +114,39 @@ def test_bvh_closest_equals_brute_force(make_scene, oracle):
     np.testing.assert_array_equal(a["t"][hit_a], b["t"][hit_a])
     differ = a["prim"] != b["prim"]
     assert differ.mean() < 1e-3          # only ties
+
+
+@pytest.mark.parametrize("xres,yres", [(900, 900), (1600, 900), (300, 700)])
+def test_camera_rays_against_closed_form(make_scene, oracle, xres, yres):
+    """PerspectiveCamera::new builds raster_to_camera as the inverse of perspective * translate * scale * scale
+    (perspective.rs:10-45) and the scene's LookAt supplies camera_to_world.  Written out by hand in float64:
+    d = normalize(right * sx * tan(fov/2) + up * sy * tan(fov/2) + dir) with the screen window [-a, a] x [-1, 1]
+    (or [-1, 1] x [-1/a, 1/a] for a < 1), sx = lerp over x / W, sy = top - y / H * height; origin = the eye."""
+    w = oracle.OracleWorld(make_scene("cornel_box.pbrt", xres=xres, yres=yres, spp=1))
+    a = xres / yres
+    half_w, half_h = (a, 1.0) if a > 1 else (1.0, 1.0 / a)
+    tan_half = np.tan(np.radians(37.5) / 2)
+    rng = np.random.RandomState(9)
+    for fx, fy in [(0.0, 0.0), (xres, yres), (xres / 2, yres / 2)] + [tuple(p) for p in rng.rand(40, 2) * [xres, yres]]:
+        sx = -half_w + fx / xres * 2 * half_w
+        sy = half_h - fy / yres * 2 * half_h
+        d = np.array([sx * tan_half, sy * tan_half, 1.0])       # right = +x, up = +y, dir = +z for this LookAt
+        d /= np.linalg.norm(d)
+        ray = w.camera_ray_at(float(fx), float(fy))
+        np.testing.assert_allclose(ray[0:3], [278.0, 273.0, -800.0], atol=1e-3)
+        np.testing.assert_allclose(ray[4:7], d, atol=2e-5)
+
+
+@pytest.mark.parametrize("integrator", ["path", "directlighting"])
+def test_white_furnace(cpbrt, oracle, integrator):
+    """An analytic answer for the whole estimator (BSDF, cosine sampling, environment sampling and its
+    pdf, MIS weights, Russian roulette, film mean): see furnace_scene_text."""
+    kd = 0.8
+    w = oracle.OracleWorld(cpbrt.Scene.parse(furnace_scene_text(integrator, kd)))
+    film, _, st = w.render()
+    assert st["nan_dropped"] == 0
+    np.testing.assert_allclose(film[10:14, 10:14].mean(axis=(0, 1)), [kd, kd * 0.5, kd * 0.25], rtol=2e-3)
+    np.testing.assert_allclose(film[0, 0], [1, 1, 1], rtol=1e-6)
 
 
 def test_closest_hits_against_float64_geometry(cpbrt, make_scene, oracle):
