@@ -152,3 +152,23 @@ def furnace_scene_text(integrator, kd, spp=256, res=24):
             'Film "image" "integer xresolution" [%d] "integer yresolution" [%d]\nIntegrator "%s" "integer maxdepth" [5]\nWorldBegin\n'
             'LightSource "infinite"\nMaterial "matte" "rgb Kd" [%g %g %g]\nTranslate 0 0 5\nShape "sphere" "float radius" [1.2]\nWorldEnd\n'
             % (spp, res, res, integrator, kd, kd * 0.5, kd * 0.25))
+
+
+def point_light_quad_scene_text(integrator):
+    """A matte square facing the camera at distance 5 with a point light at the eye: the radiance through a
+    pixel at angle a off the axis is Kd / pi * I * cos(a)^3 / 25 (inverse square law at 5 / cos a, cosine
+    at the surface) -- closed form for the delta-light branch of uniform_sample_one_light."""
+    return ('Camera "perspective" "float fov" [20]\nSampler "halton" "integer pixelsamples" [8]\n'
+            'Film "image" "integer xresolution" [33] "integer yresolution" [33]\nIntegrator "%s" "integer maxdepth" [1]\nWorldBegin\n'
+            'LightSource "point" "rgb I" [10 5 2.5] "point from" [0 0 0]\nMaterial "matte" "rgb Kd" [0.5 0.5 0.5]\n'
+            'Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [-0.5 -0.5 5  0.5 -0.5 5  0.5 0.5 5  -0.5 0.5 5]\nWorldEnd\n' % integrator)
+
+
+def point_light_quad_expected():
+    """(mask of pixels well inside the square, expected red channel) for point_light_quad_scene_text."""
+    ys, xs = np.mgrid[0:33, 0:33]
+    t = np.tan(np.radians(10))
+    sx, sy = (-1 + xs / 33 * 2) * t, (1 - ys / 33 * 2) * t
+    cos_a = 1 / np.sqrt(sx * sx + sy * sy + 1)
+    inside = (np.abs(sx * 5) < 0.45) & (np.abs(sy * 5) < 0.45)
+    return inside, 0.5 / np.pi * 10 * cos_a ** 3 / 25
