@@ -172,3 +172,25 @@ def point_light_quad_expected():
     cos_a = 1 / np.sqrt(sx * sx + sy * sy + 1)
     inside = (np.abs(sx * 5) < 0.45) & (np.abs(sy * 5) < 0.45)
     return inside, 0.5 / np.pi * 10 * cos_a ** 3 / 25
+
+
+def area_light_quad_scene_text(integrator, spp=64):
+    """The same matte square lit by a small diffuse emitter (0.2 x 0.2, two triangle lights) on the axis
+    behind the eye, 8 away: irradiance L * A * cos^2 / r^2 (small-source limit, error ~ (0.1 / 8)^2) -- closed
+    form for AreaLight::sample_li, the area -> solid-angle pdf, one-light selection and the MIS weights."""
+    return ('Camera "perspective" "float fov" [20]\nSampler "halton" "integer pixelsamples" [%d]\n'
+            'Film "image" "integer xresolution" [33] "integer yresolution" [33]\nIntegrator "%s" "integer maxdepth" [1]\nWorldBegin\n'
+            'AttributeBegin\nAreaLightSource "diffuse" "rgb L" [50 25 12.5]\nMaterial "matte"\n'
+            'Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [-0.1 -0.1 -3  0.1 -0.1 -3  0.1 0.1 -3  -0.1 0.1 -3]\nAttributeEnd\n'
+            'Material "matte" "rgb Kd" [0.5 0.5 0.5]\n'
+            'Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [-0.5 -0.5 5  0.5 -0.5 5  0.5 0.5 5  -0.5 0.5 5]\nWorldEnd\n'
+            % (spp, integrator))
+
+
+def area_light_quad_expected():
+    ys, xs = np.mgrid[0:33, 0:33]
+    t = np.tan(np.radians(10))
+    x, y = (-1 + xs / 33 * 2) * t * 5, (1 - ys / 33 * 2) * t * 5
+    r2 = x * x + y * y + 64.0
+    inside = (np.abs(x) < 0.42) & (np.abs(y) < 0.42)
+    return inside, 0.5 / np.pi * 50 * 0.04 * (64.0 / r2) / r2

@@ -10,7 +10,7 @@ import re
 import numpy as np
 import pytest
 
-from conftest import SCENES, furnace_scene_text, lcg_rays, point_light_quad_expected, point_light_quad_scene_text, scene_text, write_exr
+from conftest import SCENES, area_light_quad_expected, area_light_quad_scene_text, furnace_scene_text, lcg_rays, point_light_quad_expected, point_light_quad_scene_text, scene_text, write_exr
 from test_oracle import _synthetic_mesh_scene
 
 pytestmark = pytest.mark.gpu
@@ -547,6 +547,19 @@ def test_point_light_inverse_square_closed_form(cpbrt, integrator):
     inside, expect = point_light_quad_expected()
     np.testing.assert_allclose(film[..., 0][inside], expect[inside], rtol=3e-3)
     np.testing.assert_allclose(film[..., 2][inside], expect[inside] / 4, rtol=3e-3)
+    r.close()
+
+
+@pytest.mark.parametrize("integrator", ["path", "directlighting"])
+def test_area_light_small_source_closed_form(cpbrt, integrator):
+    """Closed form, no oracle involved (conftest.area_light_quad_scene_text)."""
+    r = cpbrt.Renderer(0)
+    r.upload(cpbrt.Scene.parse(area_light_quad_scene_text(integrator)))
+    r.build_bvh()
+    film, _ = r.render()
+    inside, expect = area_light_quad_expected()
+    np.testing.assert_allclose(film[..., 0][inside], expect[inside], rtol=3e-3)
+    np.testing.assert_allclose(film[..., 1][inside], expect[inside] / 2, rtol=3e-3)
     r.close()
 
 

@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import SCENES, furnace_scene_text, lcg_rays, point_light_quad_expected, point_light_quad_scene_text, scene_text
+from conftest import SCENES, area_light_quad_expected, area_light_quad_scene_text, furnace_scene_text, lcg_rays, point_light_quad_expected, point_light_quad_scene_text, scene_text
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -157,6 +157,15 @@ def test_point_light_inverse_square_closed_form(cpbrt, oracle, integrator):
     # the film point of a sample drifts by the accumulated jitter (render.rs:26-31), a fraction of a pixel here
     np.testing.assert_allclose(film[..., 0][inside], expect[inside], rtol=3e-3)
     np.testing.assert_allclose(film[..., 1][inside], expect[inside] / 2, rtol=3e-3)
+
+
+@pytest.mark.parametrize("integrator", ["path", "directlighting"])
+def test_area_light_small_source_closed_form(cpbrt, oracle, integrator):
+    w = oracle.OracleWorld(cpbrt.Scene.parse(area_light_quad_scene_text(integrator)))
+    film, _, _ = w.render()
+    inside, expect = area_light_quad_expected()
+    np.testing.assert_allclose(film[..., 0][inside], expect[inside], rtol=3e-3)
+    np.testing.assert_allclose(film[..., 2][inside], expect[inside] / 4, rtol=3e-3)
 
 
 def test_closest_hits_against_float64_geometry(cpbrt, make_scene, oracle):
