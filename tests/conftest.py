@@ -144,6 +144,17 @@ def write_exr(path, img, compression, pixel_type, origin=(0, 0)):
         f.write(header + struct.pack("<%dQ" % len(blocks), *offsets) + b"".join(blocks))
 
 
+def specular_furnace_scene_text(material, spp=256, res=24):
+    """White furnace for the delta lobes: a mirror sphere (Kr = 1) or a glass sphere with Kr = Kt = 1 (the
+    reference's default Kr is 0.5) returns exactly the environment's radiance -- Fresnel reflectance plus
+    transmittance is 1 at every interface, so this checks fresnel_dielectric, refract, the luminance-weighted
+    choice between the two delta lobes and its pmf, and Russian roulette; only paths cut at maxdepth are lost."""
+    mat = 'Material "mirror"' if material == "mirror" else 'Material "glass" "rgb Kr" [1 1 1]'
+    return ('Camera "perspective" "float fov" [40]\nSampler "halton" "integer pixelsamples" [%d]\n'
+            'Film "image" "integer xresolution" [%d] "integer yresolution" [%d]\nIntegrator "path" "integer maxdepth" [12]\nWorldBegin\n'
+            'LightSource "infinite"\n%s\nTranslate 0 0 5\nShape "sphere" "float radius" [1.2]\nWorldEnd\n' % (spp, res, res, mat))
+
+
 def furnace_scene_text(integrator, kd, spp=256, res=24):
     """White furnace: a convex matte sphere inside a constant environment of radiance 1.  No path can
     bounce twice on a convex body, so the exitant radiance is exactly Kd wherever the sphere covers the

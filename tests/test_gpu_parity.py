@@ -10,7 +10,7 @@ import re
 import numpy as np
 import pytest
 
-from conftest import SCENES, area_light_quad_expected, area_light_quad_scene_text, furnace_scene_text, lcg_rays, point_light_quad_expected, point_light_quad_scene_text, scene_text, write_exr
+from conftest import SCENES, area_light_quad_expected, area_light_quad_scene_text, furnace_scene_text, lcg_rays, point_light_quad_expected, point_light_quad_scene_text, scene_text, specular_furnace_scene_text, write_exr
 from test_oracle import _synthetic_mesh_scene
 
 pytestmark = pytest.mark.gpu
@@ -560,6 +560,19 @@ def test_area_light_small_source_closed_form(cpbrt, integrator):
     inside, expect = area_light_quad_expected()
     np.testing.assert_allclose(film[..., 0][inside], expect[inside], rtol=3e-3)
     np.testing.assert_allclose(film[..., 1][inside], expect[inside] / 2, rtol=3e-3)
+    r.close()
+
+
+@pytest.mark.parametrize("material", ["mirror", "glass"])
+def test_specular_white_furnace(cpbrt, material):
+    """Analytic answer, no oracle involved (conftest.specular_furnace_scene_text)."""
+    r = cpbrt.Renderer(0)
+    r.upload(cpbrt.Scene.parse(specular_furnace_scene_text(material)))
+    r.build_bvh()
+    film, st = r.render()
+    assert st.nan_dropped == 0
+    np.testing.assert_allclose(film[10:14, 10:14].mean(axis=(0, 1)), [1, 1, 1], rtol=2e-3)
+    np.testing.assert_allclose(film[7:17, 7:17].mean(axis=(0, 1)), [1, 1, 1], rtol=3e-3)
     r.close()
 
 

@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import SCENES, area_light_quad_expected, area_light_quad_scene_text, furnace_scene_text, lcg_rays, point_light_quad_expected, point_light_quad_scene_text, scene_text
+from conftest import SCENES, area_light_quad_expected, area_light_quad_scene_text, furnace_scene_text, lcg_rays, point_light_quad_expected, point_light_quad_scene_text, scene_text, specular_furnace_scene_text
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -166,6 +166,15 @@ def test_area_light_small_source_closed_form(cpbrt, oracle, integrator):
     inside, expect = area_light_quad_expected()
     np.testing.assert_allclose(film[..., 0][inside], expect[inside], rtol=3e-3)
     np.testing.assert_allclose(film[..., 2][inside], expect[inside] / 4, rtol=3e-3)
+
+
+@pytest.mark.parametrize("material", ["mirror", "glass"])
+def test_specular_white_furnace(cpbrt, oracle, material):
+    w = oracle.OracleWorld(cpbrt.Scene.parse(specular_furnace_scene_text(material)))
+    film, _, st = w.render()
+    assert st["nan_dropped"] == 0
+    np.testing.assert_allclose(film[10:14, 10:14].mean(axis=(0, 1)), [1, 1, 1], rtol=2e-3)
+    np.testing.assert_allclose(film[7:17, 7:17].mean(axis=(0, 1)), [1, 1, 1], rtol=3e-3)
 
 
 def test_closest_hits_against_float64_geometry(cpbrt, make_scene, oracle):
