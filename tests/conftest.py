@@ -205,3 +205,14 @@ def area_light_quad_expected():
     r2 = x * x + y * y + 64.0
     inside = (np.abs(x) < 0.42) & (np.abs(y) < 0.42)
     return inside, 0.5 / np.pi * 50 * 0.04 * (64.0 / r2) / r2
+
+
+def distant_light_quad_scene_text(to):
+    """The matte square under a distant light of radiance (3, 1.5, 0.75) travelling along `to`: Kd / pi * L * cos."""
+    return ('Camera "perspective" "float fov" [20]\nSampler "halton" "integer pixelsamples" [4]\n'
+            'Film "image" "integer xresolution" [33] "integer yresolution" [33]\nIntegrator "path" "integer maxdepth" [1]\nWorldBegin\n'
+            'LightSource "distant" "point from" [0 0 0] "point to" [%s] "rgb L" [3 1.5 0.75]\nMaterial "matte" "rgb Kd" [0.5 0.5 0.5]\n'
+            'Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [-0.5 -0.5 5  0.5 -0.5 5  0.5 0.5 5  -0.5 0.5 5]\nWorldEnd\n' % to)
+
+
+DISTANT_CASES = [("0 0 1", 1.0), ("1 0 1", 0.5 ** 0.5), ("0 -1 1", 0.5 ** 0.5), ("1 1 1", 3 ** -0.5)]

@@ -10,7 +10,7 @@ import re
 import numpy as np
 import pytest
 
-from conftest import SCENES, area_light_quad_expected, area_light_quad_scene_text, furnace_scene_text, lcg_rays, point_light_quad_expected, point_light_quad_scene_text, scene_text, specular_furnace_scene_text, write_exr
+from conftest import DISTANT_CASES, SCENES, area_light_quad_expected, distant_light_quad_scene_text, area_light_quad_scene_text, furnace_scene_text, lcg_rays, point_light_quad_expected, point_light_quad_scene_text, scene_text, specular_furnace_scene_text, write_exr
 from test_oracle import _synthetic_mesh_scene
 
 pytestmark = pytest.mark.gpu
@@ -573,6 +573,17 @@ def test_specular_white_furnace(cpbrt, material):
     assert st.nan_dropped == 0
     np.testing.assert_allclose(film[10:14, 10:14].mean(axis=(0, 1)), [1, 1, 1], rtol=2e-3)
     np.testing.assert_allclose(film[7:17, 7:17].mean(axis=(0, 1)), [1, 1, 1], rtol=3e-3)
+    r.close()
+
+
+@pytest.mark.parametrize("to,cos", DISTANT_CASES)
+def test_distant_light_closed_form(cpbrt, to, cos):
+    """Closed form, no oracle involved (conftest.distant_light_quad_scene_text)."""
+    r = cpbrt.Renderer(0)
+    r.upload(cpbrt.Scene.parse(distant_light_quad_scene_text(to)))
+    r.build_bvh()
+    film, _ = r.render()
+    np.testing.assert_allclose(film[12:21, 12:21].reshape(-1, 3), np.tile(0.5 / np.pi * cos * np.array([3, 1.5, 0.75]), (81, 1)), rtol=2e-6)
     r.close()
 
 

@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import SCENES, area_light_quad_expected, area_light_quad_scene_text, furnace_scene_text, lcg_rays, point_light_quad_expected, point_light_quad_scene_text, scene_text, specular_furnace_scene_text
+from conftest import DISTANT_CASES, SCENES, area_light_quad_expected, distant_light_quad_scene_text, area_light_quad_scene_text, furnace_scene_text, lcg_rays, point_light_quad_expected, point_light_quad_scene_text, scene_text, specular_furnace_scene_text
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -175,6 +175,12 @@ def test_specular_white_furnace(cpbrt, oracle, material):
     assert st["nan_dropped"] == 0
     np.testing.assert_allclose(film[10:14, 10:14].mean(axis=(0, 1)), [1, 1, 1], rtol=2e-3)
     np.testing.assert_allclose(film[7:17, 7:17].mean(axis=(0, 1)), [1, 1, 1], rtol=3e-3)
+
+
+@pytest.mark.parametrize("to,cos", DISTANT_CASES)
+def test_distant_light_closed_form(cpbrt, oracle, to, cos):
+    film, _, _ = oracle.OracleWorld(cpbrt.Scene.parse(distant_light_quad_scene_text(to))).render()
+    np.testing.assert_allclose(film[12:21, 12:21].reshape(-1, 3), np.tile(0.5 / np.pi * cos * np.array([3, 1.5, 0.75]), (81, 1)), rtol=2e-6)
 
 
 def test_closest_hits_against_float64_geometry(cpbrt, make_scene, oracle):
