@@ -216,3 +216,24 @@ def distant_light_quad_scene_text(to):
 
 
 DISTANT_CASES = [("0 0 1", 1.0), ("1 0 1", 0.5 ** 0.5), ("0 -1 1", 0.5 ** 0.5), ("1 1 1", 3 ** -0.5)]
+
+
+def sphere_light_quad_scene_text(integrator, spp=64):
+    """The matte square under a spherical diffuse emitter (radius 0.5, on the axis 8 away): a uniformly emitting
+    sphere gives the irradiance pi * L * (R / d)^2 * cos exactly, so the radiance is Kd * L * R^2 / d^2 * cos --
+    closed form for Sphere::sample_by_point (cone sampling), by_point_pdf and TransformShape around a light."""
+    return ('Camera "perspective" "float fov" [20]\nSampler "halton" "integer pixelsamples" [%d]\n'
+            'Film "image" "integer xresolution" [33] "integer yresolution" [33]\nIntegrator "%s" "integer maxdepth" [1]\nWorldBegin\n'
+            'AttributeBegin\nAreaLightSource "diffuse" "rgb L" [50 25 12.5]\nTranslate 0 0 -3\nShape "sphere" "float radius" [0.5]\nAttributeEnd\n'
+            'Material "matte" "rgb Kd" [0.5 0.5 0.5]\n'
+            'Shape "trianglemesh" "integer indices" [0 1 2 0 2 3] "point P" [-0.5 -0.5 5  0.5 -0.5 5  0.5 0.5 5  -0.5 0.5 5]\nWorldEnd\n'
+            % (spp, integrator))
+
+
+def sphere_light_quad_expected():
+    ys, xs = np.mgrid[0:33, 0:33]
+    t = np.tan(np.radians(10))
+    x, y = (-1 + xs / 33 * 2) * t * 5, (1 - ys / 33 * 2) * t * 5
+    r2 = x * x + y * y + 64.0
+    inside = (np.abs(x) < 0.42) & (np.abs(y) < 0.42)
+    return inside, 0.5 * 50 * 0.25 / r2 * (8 / np.sqrt(r2))

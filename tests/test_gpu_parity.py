@@ -10,7 +10,7 @@ import re
 import numpy as np
 import pytest
 
-from conftest import DISTANT_CASES, SCENES, area_light_quad_expected, distant_light_quad_scene_text, area_light_quad_scene_text, furnace_scene_text, lcg_rays, point_light_quad_expected, point_light_quad_scene_text, scene_text, specular_furnace_scene_text, write_exr
+from conftest import DISTANT_CASES, SCENES, area_light_quad_expected, distant_light_quad_scene_text, area_light_quad_scene_text, furnace_scene_text, lcg_rays, point_light_quad_expected, point_light_quad_scene_text, scene_text, specular_furnace_scene_text, sphere_light_quad_expected, sphere_light_quad_scene_text, write_exr
 from test_oracle import _synthetic_mesh_scene
 
 pytestmark = pytest.mark.gpu
@@ -584,6 +584,19 @@ def test_distant_light_closed_form(cpbrt, to, cos):
     r.build_bvh()
     film, _ = r.render()
     np.testing.assert_allclose(film[12:21, 12:21].reshape(-1, 3), np.tile(0.5 / np.pi * cos * np.array([3, 1.5, 0.75]), (81, 1)), rtol=2e-6)
+    r.close()
+
+
+@pytest.mark.parametrize("integrator", ["path", "directlighting"])
+def test_sphere_light_closed_form(cpbrt, integrator):
+    """Closed form, no oracle involved (conftest.sphere_light_quad_scene_text)."""
+    r = cpbrt.Renderer(0)
+    r.upload(cpbrt.Scene.parse(sphere_light_quad_scene_text(integrator)))
+    r.build_bvh()
+    film, _ = r.render()
+    inside, expect = sphere_light_quad_expected()
+    ratio = film[..., 0][inside] / expect[inside]
+    assert abs(ratio.mean() - 1) < 3e-3 and np.abs(ratio - 1).max() < 3e-2, (ratio.mean(), ratio.min(), ratio.max())
     r.close()
 
 

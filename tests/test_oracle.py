@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import DISTANT_CASES, SCENES, area_light_quad_expected, distant_light_quad_scene_text, area_light_quad_scene_text, furnace_scene_text, lcg_rays, point_light_quad_expected, point_light_quad_scene_text, scene_text, specular_furnace_scene_text
+from conftest import DISTANT_CASES, SCENES, area_light_quad_expected, distant_light_quad_scene_text, area_light_quad_scene_text, furnace_scene_text, lcg_rays, point_light_quad_expected, point_light_quad_scene_text, scene_text, specular_furnace_scene_text, sphere_light_quad_expected, sphere_light_quad_scene_text
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -181,6 +181,15 @@ def test_specular_white_furnace(cpbrt, oracle, material):
 def test_distant_light_closed_form(cpbrt, oracle, to, cos):
     film, _, _ = oracle.OracleWorld(cpbrt.Scene.parse(distant_light_quad_scene_text(to))).render()
     np.testing.assert_allclose(film[12:21, 12:21].reshape(-1, 3), np.tile(0.5 / np.pi * cos * np.array([3, 1.5, 0.75]), (81, 1)), rtol=2e-6)
+
+
+@pytest.mark.parametrize("integrator", ["path", "directlighting"])
+def test_sphere_light_closed_form(cpbrt, oracle, integrator):
+    film, _, _ = oracle.OracleWorld(cpbrt.Scene.parse(sphere_light_quad_scene_text(integrator))).render()
+    inside, expect = sphere_light_quad_expected()
+    ratio = film[..., 0][inside] / expect[inside]
+    assert abs(ratio.mean() - 1) < 3e-3 and np.abs(ratio - 1).max() < 3e-2, (ratio.mean(), ratio.min(), ratio.max())
+    np.testing.assert_allclose(film[..., 2][inside], film[..., 0][inside] / 4, rtol=1e-5)
 
 
 def test_closest_hits_against_float64_geometry(cpbrt, make_scene, oracle):
