@@ -6,6 +6,12 @@
 // un-vendored crates), so this restatement is pinned only by the reference's two unit tests
 // (halton_works, perspective_works) and by values derived from its sources; BVH order, hit
 // ids, shading and film are "parity unpinned" against a real reference run.
+// What the restatement is additionally held to (tests/test_oracle.py), none of it a reference run:
+// an independent brute-force aggregate, exact integer / rational arithmetic for the scrambled
+// radical inverse, float64 Moeller-Trumbore + analytic-sphere geometry over all primitives, the
+// closed form of the camera, and analytic radiometry (white furnace for matte / mirror / glass,
+// point, distant, small-area and spherical emitters) -- these pin its arithmetic and physics, not
+// the reference's quirks.
 //
 // Value types and small math.  Follows src/math/mod.rs, src/geometry/{point,vector,normal}.rs and
 // the nalgebra 0.20 arithmetic they sit on (dot = (x*x'+y*y')+z*z', normalize = v / sqrt(dot),
