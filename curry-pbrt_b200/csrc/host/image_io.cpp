@@ -48,6 +48,10 @@ bool read_png_rgb8(const std::string& path, uint32_t* w, uint32_t* h, std::vecto
     // would be misread there, so they are rejected here instead of silently reinterpreted.
     if (depth != 8 || ctype != 2 || interlace != 0) { *err = "only 8-bit non-interlaced RGB PNG is supported: " + path; return false; }
     const size_t bpp = 3, stride = size_t(W) * bpp;
+    // a corrupted header must not turn into a multi-terabyte allocation: deflate expands at most ~1032x
+    if (W == 0 || H == 0 || W > (1u << 16) || H > (1u << 16) || (stride + 1) * H > idat.size() * 1100 + 4096) {
+        *err = "PNG header and data sizes do not fit together: " + path; return false;
+    }
     std::vector<uint8_t> raw((stride + 1) * H);
     uLongf out_len = raw.size();
     if (uncompress(raw.data(), &out_len, (const Bytef*)idat.data(), idat.size()) != Z_OK || out_len != raw.size()) {
@@ -353,6 +357,8 @@ bool read_exr_rgb(const std::string& path, uint32_t* w, uint32_t* h, std::vector
     const uint64_t n_blocks = (H + lines_per_block - 1) / lines_per_block;
     size_t line_bytes = 0;
     for (const auto& ch : channels) line_bytes += (ch.type == 1 ? 2 : 4) * (size_t)W;
+    // as for PNG: the pixel data cannot be more than ~1100x the file (zlib) -- rejects corrupted windows
+    if ((uint64_t)line_bytes * H > (uint64_t)d.size() * 1100 + 4096 || n_blocks * 8 > d.size()) { *err = "OpenEXR data window does not fit the file: " + path; return false; }
     std::vector<uint64_t> offsets(n_blocks);
     for (auto& o : offsets) o = c.u64();
     if (!c.ok) { *err = "truncated OpenEXR offset table: " + path; return false; }
