@@ -241,7 +241,12 @@ std::vector<Token> lex_text(const std::string& text, const std::string& file_lab
     Lexer lx(text, file_label);
     return lx.run();
 }
+// Include nests through lex_file (lex.rs:98-105).  A file that includes itself, directly or through
+// others, recurses until the stack is gone in the reference; here it is a parse error.
+static thread_local int g_include_depth = 0;
 std::vector<Token> lex_file(const std::string& path) {
+    struct Depth { Depth() { ++g_include_depth; } ~Depth() { --g_include_depth; } } depth;
+    if (g_include_depth > 32) throw ParseError("Include nested deeper than 32 files (a file including itself?): " + path);
     std::string text = read_file(path);
     return lex_text(text, path);
 }
@@ -294,7 +299,14 @@ static Property property_from_tokens(std::deque<Token>& toks) {   // Property::f
     return p;
 }
 
+// Blocks nest by recursion here, in the scene builder and in the reference (BlockSegment::from_lex,
+// SceneParseStack::parse); a file with hundreds of thousands of unclosed *Begin lines would take the
+// stack with it, so the depth is bounded and exceeding it is a parse error.
+static thread_local int g_block_depth = 0;
+static const int kMaxBlockDepth = 512;
 static Segment segment_from_tokens(std::deque<Token>& toks) {   // BlockSegment::from_lex (mod.rs:41-100)
+    struct Depth { Depth() { ++g_block_depth; } ~Depth() { --g_block_depth; } } depth;
+    if (g_block_depth > kMaxBlockDepth) throw ParseError("blocks nested deeper than " + std::to_string(kMaxBlockDepth));
     Token t = std::move(toks.front());
     toks.pop_front();
     Segment seg;

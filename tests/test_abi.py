@@ -53,6 +53,33 @@ def test_parse_errors_are_codes_not_crashes(cpbrt):
         cpbrt.Scene.parse('Camera "perspective" "float fov" [40\n')                 # unpaired [ then EOF word
 
 
+def test_hostile_scene_files_are_codes_not_crashes(cpbrt, tmp_path):
+    """What overflows the stack in the reference (a file including itself, hundreds of thousands of nested
+    blocks) and what would ask for terabytes (image headers that do not fit their file) must come back as an
+    error code: the library lives inside the caller's process."""
+    head = ('Camera "perspective" "float fov" [40]\nSampler "halton" "integer pixelsamples" [1]\n'
+            'Film "image" "integer xresolution" [8] "integer yresolution" [8]\nIntegrator "path"\nWorldBegin\n')
+    (tmp_path / "self.pbrt").write_text('Include "self.pbrt"\n')
+    with pytest.raises(cpbrt.CpbrtError, match="Include nested"):
+        cpbrt.Scene.parse(head + 'Include "self.pbrt"\nWorldEnd\n', base_dir=str(tmp_path))
+    with pytest.raises(cpbrt.CpbrtError, match="nested deeper"):
+        cpbrt.Scene.parse(head + "AttributeBegin\n" * 200000)
+    # 400 levels are fine
+    s = cpbrt.Scene.parse(head + 'LightSource "point"\nMaterial "matte"\n' + "AttributeBegin\n" * 400 + 'Translate 0 0 5\nShape "sphere"\n'
+                          + "AttributeEnd\n" * 400 + "WorldEnd\n")
+    assert s.desc.n_primitives == 1
+    # a PNG whose header claims 60000 x 60000 pixels over a few bytes of data
+    import struct
+    import zlib
+    def chunk(t, b):
+        return struct.pack(">I", len(b)) + t + b + struct.pack(">I", zlib.crc32(t + b))
+    png = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", 60000, 60000, 8, 2, 0, 0, 0)) + chunk(b"IDAT", zlib.compress(b"\0" * 64)) + chunk(b"IEND", b"")
+    (tmp_path / "huge.png").write_bytes(png)
+    with pytest.raises(cpbrt.CpbrtError, match="do not fit"):
+        cpbrt.Scene.parse(head + 'Texture "t" "spectrum" "imagemap" "string filename" "huge.png"\nMaterial "matte" "texture Kd" "t"\nShape "sphere"\nWorldEnd\n',
+                          base_dir=str(tmp_path))
+
+
 def test_write_png_roundtrip(cpbrt, tmp_path):
     from PIL import Image
     film = np.zeros((4, 6, 3), np.float32)
