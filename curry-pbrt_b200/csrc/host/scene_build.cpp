@@ -432,7 +432,7 @@ struct Builder {
         std::ifstream f(path, std::ios::binary);
         if (!f) fail("cannot open ply '" + path + "'");
         std::string line;
-        auto getl = [&]() { std::getline(f, line); };
+        auto getl = [&]() { if (!std::getline(f, line)) fail("ply: truncated header"); };   // a failed read leaves `line` as it was: the property loop would never end
         getl(); if (line != "ply") fail("ply: bad magic");
         getl(); if (line != "format binary_little_endian 1.0") fail("ply: only binary_little_endian 1.0");
         getl(); if (line.compare(0, 14, "element vertex") != 0) fail("ply: expected element vertex");
@@ -451,6 +451,13 @@ struct Builder {
         size_t nf = std::stoull(line.substr(13));
         getl(); if (line != "property list uint8 int vertex_indices") fail("ply: bad face property");
         getl(); if (line != "end_header") fail("ply: expected end_header");
+        {   // the counts come from the file: they must fit what is left of it before anything is allocated
+            const std::streampos here = f.tellg();
+            f.seekg(0, std::ios::end);
+            const uint64_t left = (uint64_t)(f.tellg() - here);
+            f.seekg(here);
+            if (nv > left / 32 || nf > left / 13 || nv * 32 + nf * 13 > left) fail("ply: truncated file");
+        }
         std::vector<float> verts(nv * 3);
         for (size_t i = 0; i < nv; ++i) {
             float rec[8];

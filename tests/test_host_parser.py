@@ -155,8 +155,14 @@ def test_plymesh_and_include(cpbrt, tmp_path):
     for other in (b, c):
         assert other.n_triangles == a.n_triangles and other.n_primitives == a.n_primitives
         assert np.array_equal(np.ctypeslib.as_array(other.triangles, shape=(int(other.n_triangles),)).view(np.uint8), ta)
-    # a truncated file is an error code, not a crash
+    # a header cut off inside its property list, and element counts far beyond the file: error codes, promptly
     data = (tmp_path / "m.ply").read_bytes()
+    (tmp_path / "cut.ply").write_bytes(data[:data.index(b"property float nz")])
+    (tmp_path / "many.ply").write_bytes(data.replace(b"element vertex 40", b"element vertex 4000000000"))
+    for name in ("cut.ply", "many.ply"):
+        with pytest.raises(cpbrt.CpbrtError, match="truncated"):
+            cpbrt.Scene.parse(head + 'Shape "plymesh" "string filename" "%s"\nWorldEnd\n' % name, base_dir=str(tmp_path))
+    # a truncated file is an error code, not a crash
     (tmp_path / "bad.ply").write_bytes(data[:len(data) // 2])
     with pytest.raises(cpbrt.CpbrtError):
         cpbrt.Scene.parse(head + 'Shape "plymesh" "string filename" "bad.ply"\nWorldEnd\n', base_dir=str(tmp_path))
