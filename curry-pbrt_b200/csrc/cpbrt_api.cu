@@ -43,23 +43,29 @@ struct NcclApi {
     int (*Reduce)(const void*, void*, size_t, int, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     bool load(std::string* err) {
         if (handle) return true;
-        handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-        if (!handle) handle = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
-        if (!handle) { *err = std::string("cannot load libnccl: ") + dlerror(); return false; }
-        GetUniqueId = (int (*)(NcclUniqueId*))dlsym(handle, "ncclGetUniqueId");
-        CommInitRank = (int (*)(ncclComm_t*, int, NcclUniqueId, int))dlsym(handle, "ncclCommInitRank");
-        CommDestroy = (int (*)(ncclComm_t))dlsym(handle, "ncclCommDestroy");
-        Reduce = (int (*)(const void*, void*, size_t, int, int, int, ncclComm_t, cudaStream_t))dlsym(handle, "ncclReduce");
-        Broadcast = (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(handle, "ncclBroadcast");
-        GetErrorString = (const char* (*)(int))dlsym(handle, "ncclGetErrorString");
-        if (!GetUniqueId || !CommInitRank || !CommDestroy || !Reduce) { *err = "libnccl lacks a required symbol"; return false; }
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) { *err = std::string("cannot load libnccl: ") + dlerror(); return false; }
+        GetUniqueId = (int (*)(NcclUniqueId*))dlsym(h, "ncclGetUniqueId");
+        CommInitRank = (int (*)(ncclComm_t*, int, NcclUniqueId, int))dlsym(h, "ncclCommInitRank");
+        CommDestroy = (int (*)(ncclComm_t))dlsym(h, "ncclCommDestroy");
+        Reduce = (int (*)(const void*, void*, size_t, int, int, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclReduce");
+        Broadcast = (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclBroadcast");
+        AllReduce = (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclAllReduce");
+        GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+        if (!GetUniqueId || !CommInitRank || !CommDestroy || !Reduce || !Broadcast || !AllReduce) {
+            // the handle is only published once every entry point resolved: a later call fails the same way
+            *err = "libnccl lacks a required symbol"; dlclose(h); return false;
+        }
+        handle = h;
         return true;
     }
 };
 NcclApi g_nccl;
-const int kNcclFloat32 = 7, kNcclUint8 = 1, kNcclSum = 0;
+const int kNcclFloat32 = 7, kNcclUint8 = 1, kNcclInt32 = 2, kNcclSum = 0, kNcclMax = 2;
 
 }  // namespace
 
@@ -71,6 +77,7 @@ struct cpbrt_ctx {
     cudaStream_t aux[2] = {nullptr, nullptr};
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     std::string error;
+    uint64_t h2d_bytes = 0;      // bytes copied host -> device by this context so far (counted where the copies are issued)
 
     // host copy of what the BVH build needs
     bool has_scene = false, has_bvh = false, has_general_materials = false, recursive_direct = false;
@@ -83,7 +90,7 @@ struct cpbrt_ctx {
     std::vector<DevLight> host_lights;
 
     DevScene scene;   // by-value kernel argument
-    DevBuf d_prims, d_prim_uv, d_prim_frame, d_nodes, d_env, d_transforms, d_materials, d_textures, d_texels, d_lights, d_perm, d_primes, d_primsum, d_magic, d_halton_dims, d_halton_inv_pow;
+    DevBuf d_prims, d_prim_uv, d_prim_frame, d_nodes, d_flat, d_env, d_transforms, d_materials, d_textures, d_texels, d_lights, d_perm, d_primes, d_primsum, d_magic, d_halton_dims, d_halton_inv_pow, d_chunk_full, d_chunk_last;
 
     // wavefront state
     uint32_t path_capacity = 0;
@@ -112,13 +119,14 @@ struct cpbrt_ctx {
 namespace {
 
 int alloc_upload(cpbrt_ctx* ctx, DevBuf& b, const void* src, size_t bytes) {
+    const size_t src_bytes = bytes;      // an empty array still gets a 16-byte placeholder, but nothing is read from `src`
     if (bytes == 0) bytes = 16;
     if (b.bytes != bytes) {   // re-uploading a scene of the same shape reuses its buffers
         b.release();
         CU(cudaMalloc(&b.p, bytes));
         b.bytes = bytes;
     }
-    if (src) CU(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (src && src_bytes) { CU(cudaMemcpyAsync(b.p, src, src_bytes, cudaMemcpyHostToDevice, ctx->stream)); ctx->h2d_bytes += src_bytes; }
     else CU(cudaMemsetAsync(b.p, 0, bytes, ctx->stream));
     return 0;
 }
@@ -168,12 +176,18 @@ int grid_for(const cpbrt_ctx* ctx, int blocks_per_sm) { return ctx->sm_count * b
 // descend-then-test loop is ahead on small trees (33-primitive Cornell box: 1.2x).
 // CPBRT_SCHEDULE=vote|loop overrides (used to measure the crossover).
 static constexpr uint32_t kVoteMinPrims = 256;    // measured: equal at 264 primitives, vote +12% at 4k, +23% at 40k, +32% at 1M (tools/schedule_crossover.py)
-bool use_vote(const cpbrt_ctx* ctx) {
+// Scenes of at most kFlatMaxPrims primitives skip the tree walk altogether (flat_trace.cuh).
+// CPBRT_SCHEDULE=flat|loop|vote overrides ("flat" only where the tables exist).
+int trace_schedule(const cpbrt_ctx* ctx) {
     const char* e = getenv("CPBRT_SCHEDULE");
-    if (e && strcmp(e, "vote") == 0) return true;
-    if (e && strcmp(e, "loop") == 0) return false;
-    return ctx->scene.n_prims >= kVoteMinPrims;
+    const bool can_flat = ctx->scene.flat != nullptr;
+    if (e && strcmp(e, "vote") == 0) return SCHED_VOTE;
+    if (e && strcmp(e, "loop") == 0) return SCHED_LOOP;
+    if (e && strcmp(e, "flat") == 0 && can_flat) return SCHED_FLAT;
+    if (can_flat) return SCHED_FLAT;
+    return ctx->scene.n_prims >= kVoteMinPrims ? SCHED_VOTE : SCHED_LOOP;
 }
+size_t flat_bytes(const cpbrt_ctx* ctx) { return flat_smem_bytes(ctx->scene.flat_n, ctx->scene.flat_stride, ctx->scene.flat_pstride); }
 
 }  // namespace
 
@@ -211,8 +225,8 @@ void cpbrt_destroy(cpbrt_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
-    DevBuf* bufs[] = {&ctx->d_prims, &ctx->d_prim_uv, &ctx->d_prim_frame, &ctx->d_nodes, &ctx->d_env, &ctx->d_transforms, &ctx->d_materials, &ctx->d_textures, &ctx->d_texels,
-                      &ctx->d_lights, &ctx->d_perm, &ctx->d_primes, &ctx->d_primsum, &ctx->d_magic, &ctx->d_halton_dims, &ctx->d_halton_inv_pow, &ctx->d_path, &ctx->d_kind, &ctx->d_queues, &ctx->d_counts,
+    DevBuf* bufs[] = {&ctx->d_prims, &ctx->d_prim_uv, &ctx->d_prim_frame, &ctx->d_nodes, &ctx->d_flat, &ctx->d_env, &ctx->d_transforms, &ctx->d_materials, &ctx->d_textures, &ctx->d_texels,
+                      &ctx->d_lights, &ctx->d_perm, &ctx->d_primes, &ctx->d_primsum, &ctx->d_magic, &ctx->d_halton_dims, &ctx->d_halton_inv_pow, &ctx->d_chunk_full, &ctx->d_chunk_last, &ctx->d_path, &ctx->d_kind, &ctx->d_queues, &ctx->d_counts,
                       &ctx->d_pixels, &ctx->d_totals_buf, &ctx->d_film_out};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < 6; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -412,15 +426,43 @@ int cpbrt_upload_scene(cpbrt_ctx* ctx, const cpbrt_scene_desc* d) {
         {
             std::vector<DevHaltonDim> dims(CPBRT_N_PRIMES);
             std::vector<float> inv_pow((size_t)CPBRT_N_PRIMES * kHaltonMaxDigits);
+            // chunk tables (halton.cuh): k digits at a time with B = p^k <= 4096 (tables that stay in L1), or
+            // k = 2 while p^2 still fits the 16-bit entries; larger primes keep the digit loop
+            std::vector<uint16_t> chunk_full; std::vector<uint2> chunk_last;
             for (int i = 0; i < CPBRT_N_PRIMES; ++i) {
-                const float inv_base = 1.f / (float)primes[i];
-                dims[i].magic = magic[i]; dims[i].base = primes[i]; dims[i].primsum = sums[i];
-                dims[i].tail = inv_base * (float)d->sampler.permutation[sums[i]] / (1.f - inv_base);
-                dims[i].pad[0] = dims[i].pad[1] = dims[i].pad[2] = 0;
+                const uint32_t p = primes[i];
+                const float inv_base = 1.f / (float)p;
+                DevHaltonDim& D = dims[i];
+                memset(&D, 0, sizeof D);
+                D.magic = magic[i]; D.base = p; D.primsum = sums[i];
+                D.tail = inv_base * (float)d->sampler.permutation[sums[i]] / (1.f - inv_base);
                 uint64_t pw = 1;
-                for (int c = 0; c < kHaltonMaxDigits; ++c) { inv_pow[(size_t)i * kHaltonMaxDigits + c] = 1.f / (float)pw; pw *= primes[i]; }
+                for (int c = 0; c < kHaltonMaxDigits; ++c) { inv_pow[(size_t)i * kHaltonMaxDigits + c] = 1.f / (float)pw; pw *= p; }
+                uint32_t k = 1, B = p;
+                while ((uint64_t)B * p <= 4096) { B *= p; ++k; }
+                if (k == 1 && (uint64_t)p * p <= 65536) { B = p * p; k = 2; }
+                // a table that is not a permutation of 0..p-1 (the reference would take it) could overflow the 16-bit entries
+                for (uint32_t j = 0; j < p && k > 1; ++j) if (d->sampler.permutation[sums[i] + j] >= p) { k = 1; B = p; }
+                D.chunk_digits = k; D.chunk_base = B; D.chunk_magic = 0xFFFFFFFFFFFFFFFFull / B + 1; D.chunk_off = 0;
+                if (k > 1) {
+                    D.chunk_off = (uint32_t)chunk_full.size();
+                    const uint16_t* perm = d->sampler.permutation + sums[i];
+                    chunk_full.resize(chunk_full.size() + B); chunk_last.resize(chunk_last.size() + B);
+                    for (uint32_t r = 0; r < B; ++r) {
+                        uint32_t full = 0, last = 0, m = 0, pm = 1, x = r;
+                        for (uint32_t j = 0; j < k; ++j) {          // least significant digit first, like the reference loop
+                            const uint32_t digit = x % p; x /= p;
+                            full = full * p + perm[digit];
+                        }
+                        for (x = r; x != 0; x /= p) { last = last * p + perm[x % p]; ++m; pm *= p; }
+                        chunk_full[D.chunk_off + r] = (uint16_t)full;
+                        chunk_last[D.chunk_off + r] = make_uint2(pm, last | (m << 24));
+                    }
+                }
             }
             if (int rc = alloc_upload(ctx, ctx->d_halton_dims, dims.data(), dims.size() * sizeof(DevHaltonDim))) return rc;
+            if (int rc = alloc_upload(ctx, ctx->d_chunk_full, chunk_full.data(), chunk_full.size() * 2)) return rc;
+            if (int rc = alloc_upload(ctx, ctx->d_chunk_last, chunk_last.data(), chunk_last.size() * sizeof(uint2))) return rc;
             if (int rc = alloc_upload(ctx, ctx->d_halton_inv_pow, inv_pow.data(), inv_pow.size() * 4)) return rc;
         }
         DevSampler& sm = S.sampler;
@@ -430,6 +472,7 @@ int cpbrt_upload_scene(cpbrt_ctx* ctx, const cpbrt_scene_desc* d) {
         if (sm.scale[0] != (1ull << sm.exp[0])) return ctx->fail(CPBRT_ERR_BAD_ARG, "sampler.scale[0] must be 2^exp[0]");
         sm.permutation = (const uint16_t*)ctx->d_perm.p; sm.primes = (const uint32_t*)ctx->d_primes.p; sm.primsum = (const uint32_t*)ctx->d_primsum.p; sm.prime_magic = (const uint64_t*)ctx->d_magic.p;
         sm.dims = (const DevHaltonDim*)ctx->d_halton_dims.p; sm.inv_pow = (const float*)ctx->d_halton_inv_pow.p;
+        sm.chunk_full = (const uint16_t*)ctx->d_chunk_full.p; sm.chunk_last = (const uint2*)ctx->d_chunk_last.p;
     }
     S.transforms = (const DevTransform*)ctx->d_transforms.p;
     S.materials = (const DevMaterial*)ctx->d_materials.p;
@@ -638,6 +681,95 @@ int cpbrt_build_bvh(cpbrt_ctx* ctx, uint32_t* prim_order_out, cpbrt_bvh_dump* du
     }
     lap("node layout");
     if (int rc = alloc_upload(ctx, ctx->d_nodes, nodes.empty() ? nullptr : nodes.data(), nodes.size() * sizeof(float4))) return rc;
+    // tiny scenes: tables of the flat search (flat_trace.cuh): each untransformed triangle in the three
+    // component rotations of the watertight test, and every primitive's world bounds
+    S.flat = nullptr; S.flat_n = 0; S.flat_stride = 0; S.flat_items = 0; S.flat_pstride = 0; S.flat_item_mask = 0; S.flat_special_mask = 0;
+    if (n > 0 && n <= (uint32_t)kFlatMaxPrims) {
+        // phase-1 items: an untransformed triangle is paired with the first later one that shares two of its
+        // vertices (bitwise); what is left stays single
+        struct Item { uint32_t a, b; int sa0, sa1, ua, ub; };      // slots; vertex numbers of S0, S1, Ua in a, of Ub in b
+        std::vector<Item> items;
+        std::vector<char> used(n, 0);
+        uint64_t special_mask = 0;
+        auto tri_of = [&](uint32_t slot) -> const cpbrt_triangle* {
+            const cpbrt_primitive& p = ctx->primitives[R.order[slot]];
+            return (p.shape.kind == CPBRT_SHAPE_TRIANGLE && p.shape.xform < 0) ? &ctx->triangles[p.shape.data] : nullptr;
+        };
+        for (uint32_t a = 0; a < n; ++a) {
+            const cpbrt_triangle* ta = tri_of(a);
+            if (!ta) { special_mask |= 1ull << a; continue; }
+            if (used[a]) continue;
+            used[a] = 1;
+            Item it; it.a = a; it.b = 0xFFFFFFFFu; it.sa0 = 0; it.sa1 = 1; it.ua = 2; it.ub = 2;
+            for (uint32_t b = a + 1; b < n && it.b == 0xFFFFFFFFu; ++b) {
+                const cpbrt_triangle* tb = tri_of(b);
+                if (!tb || used[b]) continue;
+                int match_a[3] = {-1, -1, -1}, n_match = 0;      // vertex of b equal to vertex i of a
+                for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j)
+                    if (match_a[i] < 0 && memcmp(ta->p[i], tb->p[j], 12) == 0) { match_a[i] = j; ++n_match; break; }
+                if (n_match != 2) continue;
+                int ua = 0; while (match_a[ua] >= 0) ++ua;
+                const int s0 = (ua + 1) % 3, s1 = (ua + 2) % 3;
+                const int ub = 3 - match_a[s0] - match_a[s1];
+                if (match_a[s0] == match_a[s1]) continue;        // degenerate b
+                it.b = b; it.sa0 = s0; it.sa1 = s1; it.ua = ua; it.ub = ub; used[b] = 1;
+            }
+            items.push_back(it);
+        }
+        if (items.size() <= 32) {
+        const uint32_t n_items = (uint32_t)items.size();
+        uint32_t stride = 3 * n, pstride = 3 * std::max(1u, n_items);
+        while ((stride * 16u) % 128u != 48u) ++stride;          // the three copies start in different shared-memory banks
+        while ((pstride * 16u) % 128u != 48u) ++pstride;
+        const FlatLayout L = flat_layout(n, stride, pstride);
+        std::vector<float4> flat(L.total, make_float4(0, 0, 0, 0));
+        uint8_t* tab = reinterpret_cast<uint8_t*>(&flat[L.tab_off]);
+        uint64_t item_mask = 0;
+        for (uint32_t k = 0; k < n_items; ++k) {
+            const Item& it = items[k];
+            const cpbrt_triangle& ta = *tri_of(it.a);
+            const float* S0 = ta.p[it.sa0]; const float* S1 = ta.p[it.sa1]; const float* Ua = ta.p[it.ua];
+            const float* Ub = it.b != 0xFFFFFFFFu ? tri_of(it.b)->p[it.ub] : Ua;
+            item_mask |= 1ull << (2 * k); tab[2 * k] = (uint8_t)it.a;
+            if (it.b != 0xFFFFFFFFu) { item_mask |= 1ull << (2 * k + 1); tab[2 * k + 1] = (uint8_t)it.b; }
+            for (int c = 0; c < 3; ++c) {      // permute(): (v[kz + 1], v[kz + 2], v[kz]) with kz = c
+                const int kx = (c + 1) % 3, ky = (c + 2) % 3;
+                float4* q = &flat[(size_t)c * pstride + 3ull * k];
+                q[0] = make_float4(S0[kx], S0[ky], S0[c], S1[kx]);
+                q[1] = make_float4(S1[ky], S1[c], Ua[kx], Ua[ky]);
+                q[2] = make_float4(Ua[c], Ub[kx], Ub[ky], Ub[c]);
+            }
+        }
+        for (uint32_t slot = 0; slot < n; ++slot) {
+            if (const cpbrt_triangle* t = tri_of(slot)) {
+                for (int c = 0; c < 3; ++c) {
+                    const int kx = (c + 1) % 3, ky = (c + 2) % 3;
+                    float4* q = &flat[L.tri_off + (size_t)c * stride + 3ull * slot];
+                    q[0] = make_float4(t->p[0][kx], t->p[0][ky], t->p[0][c], t->p[1][kx]);
+                    q[1] = make_float4(t->p[1][ky], t->p[1][c], t->p[2][kx], t->p[2][ky]);
+                    q[2] = make_float4(t->p[2][c], 0.f, 0.f, 0.f);
+                }
+            }
+            const BuildBounds& pb = bounds[R.order[slot]];
+            flat[L.box_off + 2ull * slot] = make_float4(pb.mn[0], pb.mn[1], pb.mn[2], pb.mx[0]);
+            flat[L.box_off + 2ull * slot + 1] = make_float4(pb.mx[1], pb.mx[2], 0.f, 0.f);
+        }
+        if (int rc = alloc_upload(ctx, ctx->d_flat, flat.data(), flat.size() * sizeof(float4))) return rc;
+        S.flat = (const float4*)ctx->d_flat.p; S.flat_n = n; S.flat_stride = stride; S.flat_items = n_items; S.flat_pstride = pstride;
+        S.flat_item_mask = item_mask; S.flat_special_mask = special_mask;
+        }
+        // the margins of the flat search scale with the scene bounds: also needed when the root is a single Leaf
+        const BuildNode& root = R.arena[R.root];
+        if (root.leaf) {
+            for (uint32_t slot = 0; slot < n; ++slot) {
+                const BuildBounds& pb = bounds[R.order[slot]];
+                for (int k = 0; k < 3; ++k) {
+                    S.root_box[k] = slot == 0 ? pb.mn[k] : std::min(S.root_box[k], pb.mn[k]);
+                    S.root_box[3 + k] = slot == 0 ? pb.mx[k] : std::max(S.root_box[3 + k], pb.mx[k]);
+                }
+            }
+        }
+    }
     // BVH slot of each area light's primitive (when exactly one primitive carries the light)
     {
         std::vector<uint32_t> count(ctx->host_lights.size(), 0);
@@ -684,6 +816,7 @@ int cpbrt_trace_closest(cpbrt_ctx* ctx, const cpbrt_ray* rays, uint64_t n, cpbrt
     if (!ctx->has_bvh) return ctx->fail(CPBRT_ERR_BAD_CTX, "cpbrt_trace_closest before cpbrt_build_bvh");
     if ((!rays || !hits_out) && n) return ctx->fail(CPBRT_ERR_BAD_ARG, "null ray / hit buffer");
     if (n >= 0xFFFFFFFFull) return ctx->fail(CPBRT_ERR_UNSUPPORTED, "more than 2^32-1 rays in one batch");
+    if (n == 0) { if (stats) memset(stats, 0, sizeof *stats); return CPBRT_OK; }
     CU(cudaSetDevice(ctx->device));
     if (int rc = ensure_totals(ctx)) return rc;
     CU(cudaMemsetAsync(ctx->d_totals, 0, ctx->d_totals_buf.bytes, ctx->stream));
@@ -698,8 +831,10 @@ int cpbrt_trace_closest(cpbrt_ctx* ctx, const cpbrt_ray* rays, uint64_t n, cpbrt
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0, ctx->stream);
     if (n) {
+        const int sched = trace_schedule(ctx);
         if (count) k_batch_closest<1><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, d_rays, n, d_hits, counters, ctx->d_totals);
-        else if (use_vote(ctx)) k_batch_closest<2><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, d_rays, n, d_hits, counters, ctx->d_totals);
+        else if (sched == SCHED_VOTE) k_batch_closest<2><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, d_rays, n, d_hits, counters, ctx->d_totals);
+        else if (sched == SCHED_FLAT) k_batch_closest<3><<<grid_for(ctx, CPBRT_BLOCKS_FLAT), 128, flat_bytes(ctx), ctx->stream>>>(ctx->scene, d_rays, n, d_hits, counters, ctx->d_totals);
         else k_batch_closest<0><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, d_rays, n, d_hits, counters, ctx->d_totals);
     }
     cudaEventRecord(e1, ctx->stream);
@@ -723,6 +858,7 @@ int cpbrt_trace_any(cpbrt_ctx* ctx, const cpbrt_ray* rays, uint64_t n, uint8_t* 
     if (!ctx->has_bvh) return ctx->fail(CPBRT_ERR_BAD_CTX, "cpbrt_trace_any before cpbrt_build_bvh");
     if ((!rays || !out) && n) return ctx->fail(CPBRT_ERR_BAD_ARG, "null ray / result buffer");
     if (n >= 0xFFFFFFFFull) return ctx->fail(CPBRT_ERR_UNSUPPORTED, "more than 2^32-1 rays in one batch");
+    if (n == 0) { if (stats) memset(stats, 0, sizeof *stats); return CPBRT_OK; }
     CU(cudaSetDevice(ctx->device));
     if (int rc = ensure_totals(ctx)) return rc;
     CU(cudaMemsetAsync(ctx->d_totals, 0, ctx->d_totals_buf.bytes, ctx->stream));
@@ -737,8 +873,10 @@ int cpbrt_trace_any(cpbrt_ctx* ctx, const cpbrt_ray* rays, uint64_t n, uint8_t* 
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0, ctx->stream);
     if (n) {
+        const int sched = trace_schedule(ctx);
         if (count) k_batch_any<1><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, d_rays, n, d_out, counters, ctx->d_totals);
-        else if (use_vote(ctx)) k_batch_any<2><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, d_rays, n, d_out, counters, ctx->d_totals);
+        else if (sched == SCHED_VOTE) k_batch_any<2><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, d_rays, n, d_out, counters, ctx->d_totals);
+        else if (sched == SCHED_FLAT) k_batch_any<3><<<grid_for(ctx, CPBRT_BLOCKS_FLAT), 128, flat_bytes(ctx), ctx->stream>>>(ctx->scene, d_rays, n, d_out, counters, ctx->d_totals);
         else k_batch_any<0><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, d_rays, n, d_out, counters, ctx->d_totals);
     }
     cudaEventRecord(e1, ctx->stream);
@@ -886,8 +1024,10 @@ int cpbrt_render(cpbrt_ctx* ctx, const cpbrt_render_params* params, float* film_
     auto span_end = [&]() { if (prof) cudaEventRecord(spans.back().b, st); };
     cudaEventRecord(e0, st);
     uint64_t launches = 0, trace_launches = 0;
-    const bool vote = use_vote(ctx);
-    const int g_closest = grid_for(ctx, vote ? CPBRT_BLOCKS_CLOSEST_VOTE : CPBRT_BLOCKS_CLOSEST_LOOP), g_shadow = grid_for(ctx, vote ? CPBRT_BLOCKS_SHADOW_VOTE : CPBRT_BLOCKS_SHADOW_LOOP), g_shade = grid_for(ctx, 8), g_pix = grid_for(ctx, 4);
+    const int sched = trace_schedule(ctx);
+    const bool vote = sched == SCHED_VOTE, flat = sched == SCHED_FLAT;
+    const size_t flat_sm = flat ? flat_bytes(ctx) : 0;
+    const int g_closest = grid_for(ctx, flat ? CPBRT_BLOCKS_FLAT : (vote ? CPBRT_BLOCKS_CLOSEST_VOTE : CPBRT_BLOCKS_CLOSEST_LOOP)), g_shadow = grid_for(ctx, flat ? CPBRT_BLOCKS_FLAT : (vote ? CPBRT_BLOCKS_SHADOW_VOTE : CPBRT_BLOCKS_SHADOW_LOOP)), g_shade = grid_for(ctx, 8), g_pix = grid_for(ctx, 4);
     // one thread per pixel where possible: each walks a dependent chain of radical inverses (all of a
     // rank's skipped samples on the first pass), which only many resident warps can hide
     const int g_raygen = (int)std::min<uint64_t>(((uint64_t)npix + 127) / 128, (uint64_t)ctx->sm_count * 16);
@@ -922,14 +1062,16 @@ int cpbrt_render(cpbrt_ctx* ctx, const cpbrt_render_params* params, float* film_
         for (uint32_t it = 0; it < n_iters && !recursive; ++it) {
             const int next = cur ^ 1;
             span_begin(1);
-            if (vote) k_trace_closest<true><<<g_closest, 128, 0, st>>>(S, P, Q, cur, T);
-            else k_trace_closest<false><<<g_closest, 128, 0, st>>>(S, P, Q, cur, T);
+            if (flat) k_trace_closest<SCHED_FLAT><<<g_closest, 128, flat_sm, st>>>(S, P, Q, cur, T);
+            else if (vote) k_trace_closest<SCHED_VOTE><<<g_closest, 128, 0, st>>>(S, P, Q, cur, T);
+            else k_trace_closest<SCHED_LOOP><<<g_closest, 128, 0, st>>>(S, P, Q, cur, T);
             ++trace_launches;
             span_end();
             if (!prof) { cudaEventRecord(eK1, st); cudaStreamWaitEvent(sa, ePrev, 0); }
             span_begin(2);
-            if (vote) k_trace_shadow<true><<<g_shadow, 128, 0, sa>>>(S, P, Q, T);
-            else k_trace_shadow<false><<<g_shadow, 128, 0, sa>>>(S, P, Q, T);
+            if (flat) k_trace_shadow<SCHED_FLAT><<<g_shadow, 128, flat_sm, sa>>>(S, P, Q, T);
+            else if (vote) k_trace_shadow<SCHED_VOTE><<<g_shadow, 128, 0, sa>>>(S, P, Q, T);
+            else k_trace_shadow<SCHED_LOOP><<<g_shadow, 128, 0, sa>>>(S, P, Q, T);
             span_end();
             if (!prof) cudaStreamWaitEvent(sa, eK1, 0);
             k_queue_reset<<<1, 32, 0, sa>>>(Q, cur, 0, T);
@@ -1060,6 +1202,7 @@ int cpbrt_comm_init(cpbrt_ctx* ctx, int n_ranks, int rank, const uint8_t id_byte
     std::string err;
     if (!g_nccl.load(&err)) return ctx->fail(CPBRT_ERR_NCCL, "%s", err.c_str());
     NcclUniqueId id; memcpy(&id, id_bytes, CPBRT_COMM_ID_BYTES);
+    if (ctx->comm) { g_nccl.CommDestroy(ctx->comm); ctx->comm = nullptr; ctx->n_ranks = 1; ctx->rank = 0; }   // re-attaching replaces the old communicator
     int rc = g_nccl.CommInitRank(&ctx->comm, n_ranks, id, rank);
     if (rc != 0) return ctx->fail(CPBRT_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
     ctx->n_ranks = n_ranks; ctx->rank = rank;

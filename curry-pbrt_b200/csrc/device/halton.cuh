@@ -34,80 +34,118 @@ CP_DEV float radical_inverse(uint64_t x, uint32_t base) {
     return inv_base_n * __ull2float_rn(acc);
 }
 
-// scrambled_radical_inverse (halton.rs:56-64).  While the running quotient fits 32 bits the
-// division by the prime is one 64-bit multiply-high with floor(2^64/p)+1, which is exact for
-// x < 2^32 and p < 2^13 (error term x / 2^64 < 1 / p); same quotients, same digits.
-CP_DEV float scrambled_radical_inverse(const DevSampler& S, uint64_t x, uint32_t dim) {
+// scrambled_radical_inverse (halton.rs:56-64): acc = acc * base + perm[digit] over the digits of x,
+// least significant first, then (acc + tail) / base^digits.
+//
+// The digit loop is one dependent chain (divide -> digit -> table look-up -> multiply-add) of 5..14
+// steps per dimension, and a matte bounce draws seven dimensions: 28 % of the shading kernel's
+// instructions (ncu, profiles/r01_s3_ncu_cornell.txt).  k consecutive digits of x are the base-p
+// digits of r = x mod p^k, and what they add to the accumulator,
+//     acc' = acc * p^k + (perm[d0] * p^(k-1) + ... + perm[d(k-1)]),
+// depends on r alone: it is tabulated per dimension (`chunk_full`, B = p^k entries) for every
+// prime whose B fits 16 bits.  The final chunk has only as many digits as the remaining quotient
+// (the reference stops at x == 0, leading zeros belong to `tail`), so it has its own table with the
+// digit count and p^m beside the value (`chunk_last`).  Same integers in acc and the same digit
+// count as the digit-by-digit loop, so the value is bit-identical (cpbrt_halton checks every
+// requested value against the one-digit-at-a-time evaluation on the device, and the parity test
+// against the oracle runs over it).  A 32-bit index now takes at most 3 steps in any dimension.
+// While the running quotient fits 32 bits the division is one 64-bit multiply-high with
+// floor(2^64 / B) + 1, exact for x < 2^32 and B < 2^17.
+struct HaltonChain { uint64_t magic, acc; uint32_t B, kd, off, cnt, xs; };
+
+CP_DEV void halton_chain_begin(const DevSampler& S, uint64_t x, uint32_t dim, HaltonChain& c, float* tail) {
     const float4* rec = reinterpret_cast<const float4*>(S.dims + dim);
     const float4 r0 = __ldg(rec), r1 = __ldg(rec + 1);
-    const uint64_t magic = ((uint64_t)__float_as_uint(r0.y) << 32) | __float_as_uint(r0.x);
-    const uint32_t base = __float_as_uint(r0.z);
-    const uint16_t* __restrict__ pm = S.permutation + __float_as_uint(r0.w);
-    const float tail = r1.x;
-    uint64_t acc = 0; uint32_t count = 0;
-    while ((x >> 32) != 0) { uint64_t q = x / base; uint32_t digit = (uint32_t)(x - q * base); acc = acc * base + __ldg(&pm[digit]); ++count; x = q; }
-    uint32_t xs = (uint32_t)x;
-    while (xs != 0) {
-        const uint32_t q = (uint32_t)__umul64hi((uint64_t)xs, magic);
-        const uint32_t digit = xs - q * base;
-        acc = acc * base + __ldg(&pm[digit]); ++count; xs = q;
+    c.magic = ((uint64_t)__float_as_uint(r0.y) << 32) | __float_as_uint(r0.x);
+    c.B = __float_as_uint(r0.z); c.kd = __float_as_uint(r0.w); c.off = __float_as_uint(r1.x);
+    *tail = r1.w;
+    c.acc = 0; c.cnt = 0;
+    if ((x >> 32) != 0 || c.kd == 1) {
+        // digit by digit: until a 64-bit index fits 32 bits, and all the way for primes without a chunk table
+        const uint32_t base = __float_as_uint(r1.z);
+        const uint16_t* __restrict__ pm = S.permutation + __float_as_uint(r1.y);
+        while ((x >> 32) != 0) { const uint64_t q = x / base; const uint32_t digit = (uint32_t)(x - q * base); c.acc = c.acc * base + __ldg(&pm[digit]); ++c.cnt; x = q; }
+        if (c.kd == 1) {
+            uint32_t xs = (uint32_t)x;
+            while (xs != 0) { const uint32_t q = (uint32_t)__umul64hi((uint64_t)xs, c.magic); c.acc = c.acc * base + __ldg(&pm[xs - q * base]); ++c.cnt; xs = q; }
+            x = 0;
+        }
     }
+    c.xs = (uint32_t)x;
+}
+CP_DEV bool halton_chain_full(const HaltonChain& c) { return c.xs >= c.B; }
+CP_DEV void halton_chain_last(const DevSampler& S, HaltonChain& c) {
+    if (c.xs != 0) {
+        const uint2 e = __ldg(&S.chunk_last[c.off + c.xs]);
+        c.acc = c.acc * e.x + (e.y & 0xFFFFFFu); c.cnt += e.y >> 24; c.xs = 0;
+    }
+}
+CP_DEV float halton_chain_value(const DevSampler& S, const HaltonChain& c, uint32_t dim, float tail) {
     // inv_base_n and the tail of permuted zero digits were evaluated on the host with the same f32 operations
-    const float inv_base_n = __ldg(&S.inv_pow[dim * kHaltonMaxDigits + count]);
-    return inv_base_n * (__ull2float_rn(acc) + tail);
+    return __ldg(&S.inv_pow[dim * kHaltonMaxDigits + c.cnt]) * (__ull2float_rn(c.acc) + tail);
 }
 
-// N consecutive dimensions of the same index at once.  The digit loops of different primes are
-// independent dependency chains (multiply-high -> digit -> table look-up -> accumulate); one at a
-// time each iteration waits out its own latencies, and the shading kernels have too few resident
-// warps to cover them.  Walking N chains in one loop lets each chain's latency hide behind the
-// others' instructions.  Same quotients, digits and accumulators as N calls of
-// scrambled_radical_inverse (matte shading stage: -3.5 % with pairs).
+CP_DEV float scrambled_radical_inverse(const DevSampler& S, uint64_t x, uint32_t dim) {
+    HaltonChain c; float tail;
+    halton_chain_begin(S, x, dim, c, &tail);
+    while (halton_chain_full(c)) {
+        const uint32_t q = (uint32_t)__umul64hi((uint64_t)c.xs, c.magic);
+        c.acc = c.acc * c.B + __ldg(&S.chunk_full[c.off + (c.xs - q * c.B)]); c.cnt += c.kd; c.xs = q;
+    }
+    halton_chain_last(S, c);
+    return halton_chain_value(S, c, dim, tail);
+}
+
+// The reference loop itself, one digit per step: what cpbrt_halton compares the chunked evaluation with.
+CP_DEV float scrambled_radical_inverse_digitwise(const DevSampler& S, uint64_t x, uint32_t dim) {
+    const DevHaltonDim& d = S.dims[dim];
+    const uint32_t base = d.base;
+    const uint16_t* __restrict__ pm = S.permutation + d.primsum;
+    uint64_t acc = 0; uint32_t count = 0;
+    while (x != 0) { const uint64_t q = x / base; acc = acc * base + __ldg(&pm[(uint32_t)(x - q * base)]); ++count; x = q; }
+    return __ldg(&S.inv_pow[dim * kHaltonMaxDigits + count]) * (__ull2float_rn(acc) + d.tail);
+}
+
+// N consecutive dimensions of the same index at once.  The chains of different primes are
+// independent (multiply-high -> remainder -> table look-up -> accumulate); one at a time each step
+// waits out its own latencies, and the shading kernels have too few resident warps to cover them.
+// Walking N chains in one loop lets each chain's latency hide behind the others' instructions.
+// Same quotients, chunks and accumulators as N calls of scrambled_radical_inverse.
 #ifndef CPBRT_HALTON_PAIR
 #define CPBRT_HALTON_PAIR 1
 #endif
 template <int N>
 CP_DEV void scrambled_radical_inverse_n(const DevSampler& S, uint64_t x, uint32_t dim, float* out) {
-    uint64_t magic[N], acc[N]; uint32_t base[N], cnt[N], xs[N], off[N]; float tail[N];
+    HaltonChain c[N]; float tail[N];
 #pragma unroll
-    for (int k = 0; k < N; ++k) {
-        const float4* rec = reinterpret_cast<const float4*>(S.dims + dim + k);
-        const float4 r0 = __ldg(rec), r1 = __ldg(rec + 1);
-        magic[k] = ((uint64_t)__float_as_uint(r0.y) << 32) | __float_as_uint(r0.x);
-        base[k] = __float_as_uint(r0.z); off[k] = __float_as_uint(r0.w); tail[k] = r1.x;
-        acc[k] = 0; cnt[k] = 0;
-    }
-    if ((x >> 32) != 0) {      // the quotients of a 64-bit index differ per prime: each chain on its own until it fits 32 bits
-#pragma unroll
-        for (int k = 0; k < N; ++k) {
-            uint64_t xk = x;
-            while ((xk >> 32) != 0) { const uint64_t q = xk / base[k]; const uint32_t digit = (uint32_t)(xk - q * base[k]); acc[k] = acc[k] * base[k] + __ldg(&S.permutation[off[k] + digit]); ++cnt[k]; xk = q; }
-            xs[k] = (uint32_t)xk;
-        }
-    } else {
-#pragma unroll
-        for (int k = 0; k < N; ++k) xs[k] = (uint32_t)x;
-    }
+    for (int k = 0; k < N; ++k) halton_chain_begin(S, x, dim + k, c[k], &tail[k]);
     for (;;) {
         bool all = true;
 #pragma unroll
-        for (int k = 0; k < N; ++k) all = all && xs[k] != 0;
+        for (int k = 0; k < N; ++k) all = all && halton_chain_full(c[k]);
         if (!all) break;
         uint32_t q[N], pv[N];
 #pragma unroll
-        for (int k = 0; k < N; ++k) q[k] = (uint32_t)__umul64hi((uint64_t)xs[k], magic[k]);
+        for (int k = 0; k < N; ++k) q[k] = (uint32_t)__umul64hi((uint64_t)c[k].xs, c[k].magic);
 #pragma unroll
-        for (int k = 0; k < N; ++k) pv[k] = __ldg(&S.permutation[off[k] + (xs[k] - q[k] * base[k])]);
+        for (int k = 0; k < N; ++k) pv[k] = __ldg(&S.chunk_full[c[k].off + (c[k].xs - q[k] * c[k].B)]);
 #pragma unroll
-        for (int k = 0; k < N; ++k) { acc[k] = acc[k] * base[k] + pv[k]; ++cnt[k]; xs[k] = q[k]; }
+        for (int k = 0; k < N; ++k) { c[k].acc = c[k].acc * c[k].B + pv[k]; c[k].cnt += c[k].kd; c[k].xs = q[k]; }
     }
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-        while (xs[k] != 0) {
-            const uint32_t q = (uint32_t)__umul64hi((uint64_t)xs[k], magic[k]);
-            acc[k] = acc[k] * base[k] + __ldg(&S.permutation[off[k] + (xs[k] - q * base[k])]); ++cnt[k]; xs[k] = q;
+        while (halton_chain_full(c[k])) {
+            const uint32_t q = (uint32_t)__umul64hi((uint64_t)c[k].xs, c[k].magic);
+            c[k].acc = c[k].acc * c[k].B + __ldg(&S.chunk_full[c[k].off + (c[k].xs - q * c[k].B)]); c[k].cnt += c[k].kd; c[k].xs = q;
         }
-        out[k] = __ldg(&S.inv_pow[(dim + k) * kHaltonMaxDigits + cnt[k]]) * (__ull2float_rn(acc[k]) + tail[k]);
+    }
+    uint2 e[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) e[k] = c[k].xs != 0 ? __ldg(&S.chunk_last[c[k].off + c[k].xs]) : make_uint2(1u, 0u);
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        c[k].acc = c[k].acc * e[k].x + (e[k].y & 0xFFFFFFu); c[k].cnt += e[k].y >> 24;
+        out[k] = halton_chain_value(S, c[k], dim + k, tail[k]);
     }
 }
 

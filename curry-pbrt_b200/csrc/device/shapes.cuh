@@ -59,8 +59,8 @@ struct TriVerts { V3 p0, p1, p2; };
 // Triangle::intersect up to the acceptance decision; b[] and *t are the barycentrics and the
 // distance of an accepted hit.  intersect_predicate (triangle.rs:127-192) is the same chain of
 // conditions on the same values.
-CP_DEV bool tri_intersect_core(const TriVerts& tv, V3 o, float t_max, const TriRaySetup& rs, float* t_out, float b[3]) {
-    V3 p0t = permute(tv.p0 - o, rs), p1t = permute(tv.p1 - o, rs), p2t = permute(tv.p2 - o, rs);
+// `p0t`, `p1t`, `p2t` = the vertices relative to the ray origin, already permuted (triangle.rs:202-205).
+CP_DEV bool tri_intersect_permuted(V3 p0t, V3 p1t, V3 p2t, float t_max, const TriRaySetup& rs, float* t_out, float b[3]) {
     p0t.x += rs.sx * p0t.z; p0t.y += rs.sy * p0t.z;
     p1t.x += rs.sx * p1t.z; p1t.y += rs.sy * p1t.z;
     p2t.x += rs.sx * p2t.z; p2t.y += rs.sy * p2t.z;
@@ -89,6 +89,9 @@ CP_DEV bool tri_intersect_core(const TriVerts& tv, V3 o, float t_max, const TriR
     *t_out = t;
     if (b) { b[0] = e0 * inv_det; b[1] = e1 * inv_det; b[2] = e2 * inv_det; }
     return true;
+}
+CP_DEV bool tri_intersect_core(const TriVerts& tv, V3 o, float t_max, const TriRaySetup& rs, float* t_out, float b[3]) {
+    return tri_intersect_permuted(permute(tv.p0 - o, rs), permute(tv.p1 - o, rs), permute(tv.p2 - o, rs), t_max, rs, t_out, b);
 }
 
 // Barycentrics of a hit that the acceptance test above has already accepted: the same e0, e1, e2 and

@@ -16,6 +16,7 @@
 // ever write the same field of the same path in one kernel.
 #pragma once
 #include "bvh_trace.cuh"
+#include "flat_trace.cuh"
 #include "shading.cuh"
 #include "bsdf_general.cuh"
 #include "direct_recursive.cuh"
@@ -190,10 +191,12 @@ __global__ void k_raygen(DevScene sc, PixelArrays px, PathArrays P, Queues Q, ui
 // entries one by one (bvh_trace.cuh, trace_persistent).
 struct ClosestItem { uint32_t pid; uint32_t is_mis; float w_o, w_d; };   // w_* = the .w of the ray's two float4
 
-// VOTE selects the warp schedule of the traversal (bvh_trace.cuh): vote-scheduled steps for big
-// trees, the descend-then-test loop for small ones.
-template <bool VOTE>
-__global__ void __launch_bounds__(kTraceBlock, VOTE ? CPBRT_BLOCKS_CLOSEST_VOTE : CPBRT_BLOCKS_CLOSEST_LOOP) k_trace_closest(DevScene sc, PathArrays P, Queues Q, int cur, Totals* totals) {
+// SCHED selects how the closest hit is found: SCHED_VOTE = vote-scheduled tree walk for big trees,
+// SCHED_LOOP = descend-then-test loop for small ones (bvh_trace.cuh), SCHED_FLAT = no tree walk at
+// all for scenes of at most kFlatMaxPrims primitives (flat_trace.cuh).
+enum TraceSchedule : int { SCHED_LOOP = 0, SCHED_VOTE = 1, SCHED_FLAT = 2 };
+template <int SCHED>
+__global__ void __launch_bounds__(kTraceBlock, SCHED == SCHED_VOTE ? CPBRT_BLOCKS_CLOSEST_VOTE : (SCHED == SCHED_FLAT ? CPBRT_BLOCKS_FLAT : CPBRT_BLOCKS_CLOSEST_LOOP)) k_trace_closest(DevScene sc, PathArrays P, Queues Q, int cur, Totals* totals) {
     const uint32_t n = Q.counts[kCntClosest0 + cur];
     uint32_t overflow = 0;
     const uint32_t* __restrict__ queue = Q.closest[cur];
@@ -245,7 +248,8 @@ __global__ void __launch_bounds__(kTraceBlock, VOTE ? CPBRT_BLOCKS_CLOSEST_VOTE 
         }
         if (kind >= 0) P.shade_kind[pid] = (uint8_t)kind;
     };
-    if (VOTE) closest_persistent<ClosestItem>(sc, n, &Q.counts[kCntWorkClosest], &overflow, fetch, finish);
+    if (SCHED == SCHED_VOTE) closest_persistent<ClosestItem>(sc, n, &Q.counts[kCntWorkClosest], &overflow, fetch, finish);
+    else if (SCHED == SCHED_FLAT) closest_flat<ClosestItem>(sc, n, &overflow, fetch, finish);
     else closest_persistent_loop<ClosestItem>(sc, n, &Q.counts[kCntWorkClosest], &overflow, fetch, finish);
     if (overflow) atomicAdd(&totals->overflow, 1ull);
 }
@@ -309,8 +313,8 @@ __global__ void __launch_bounds__(256) k_classify(PathArrays P, Queues Q, uint32
 }
 
 // Shadow-ray stage: VisibilityTester::unoccluded (light/mod.rs:112-114).
-template <bool VOTE>
-__global__ void __launch_bounds__(kTraceBlock, VOTE ? CPBRT_BLOCKS_SHADOW_VOTE : CPBRT_BLOCKS_SHADOW_LOOP) k_trace_shadow(DevScene sc, PathArrays P, Queues Q, Totals* totals) {
+template <int SCHED>
+__global__ void __launch_bounds__(kTraceBlock, SCHED == SCHED_VOTE ? CPBRT_BLOCKS_SHADOW_VOTE : (SCHED == SCHED_FLAT ? CPBRT_BLOCKS_FLAT : CPBRT_BLOCKS_SHADOW_LOOP)) k_trace_shadow(DevScene sc, PathArrays P, Queues Q, Totals* totals) {
     const uint32_t n = Q.counts[kCntShadow];
     uint32_t overflow = 0;
     auto fetch = [&](uint32_t i, Ray* ray, uint32_t* pid) {
@@ -321,7 +325,8 @@ __global__ void __launch_bounds__(kTraceBlock, VOTE ? CPBRT_BLOCKS_SHADOW_VOTE :
     auto finish = [&](bool done, uint32_t pid, const Ray&, uint32_t slot, float) {
         if (done && slot != 0xFFFFFFFFu) P.nee_light[pid] = make_float4(0.f, 0.f, 0.f, 0.f);
     };
-    if (VOTE) any_persistent<uint32_t>(sc, n, &Q.counts[kCntWorkShadow], &overflow, fetch, finish);
+    if (SCHED == SCHED_VOTE) any_persistent<uint32_t>(sc, n, &Q.counts[kCntWorkShadow], &overflow, fetch, finish);
+    else if (SCHED == SCHED_FLAT) any_flat<uint32_t>(sc, n, &overflow, fetch, finish);
     else any_persistent_loop<uint32_t>(sc, n, &Q.counts[kCntWorkShadow], &overflow, fetch, finish);
     if (overflow) atomicAdd(&totals->overflow, 1ull);
 }
@@ -674,9 +679,9 @@ __global__ void k_film_resolve_srgb8(DevScene sc, const float4* __restrict__ sum
 // Batch entry points used by the parity tests and the traversal benchmark.
 // counters: [0] Parent visits, [1] primitive tests, [2] work cursor (zeroed by the caller)
 // MODE: 0 = two-phase traversal, loop-scheduled; 1 = reference-order traversal with visit counters;
-//       2 = two-phase traversal, vote-scheduled
+//       2 = two-phase traversal, vote-scheduled; 3 = flat search (tiny scenes)
 template <int MODE>
-__global__ void __launch_bounds__(kTraceBlock, MODE == 2 ? CPBRT_BLOCKS_CLOSEST_VOTE : 1) k_batch_closest(DevScene sc, const float4* __restrict__ rays, uint64_t n, float4* __restrict__ hits,
+__global__ void __launch_bounds__(kTraceBlock, MODE == 2 ? CPBRT_BLOCKS_CLOSEST_VOTE : (MODE == 3 ? CPBRT_BLOCKS_FLAT : 1)) k_batch_closest(DevScene sc, const float4* __restrict__ rays, uint64_t n, float4* __restrict__ hits,
                                                        unsigned long long* counters, Totals* totals) {
     uint32_t overflow = 0;
     TraceStats ts; ts.parent_visits = 0; ts.prim_tests = 0;
@@ -699,6 +704,7 @@ __global__ void __launch_bounds__(kTraceBlock, MODE == 2 ? CPBRT_BLOCKS_CLOSEST_
     // otherwise the two-phase traversal the renderer uses.  Both must return the same hits.
     if (MODE == 1) trace_persistent<false, true, uint32_t>(sc, (uint32_t)n, (uint32_t*)&counters[2], &ts, &overflow, fetch, finish);
     else if (MODE == 2) closest_persistent<uint32_t>(sc, (uint32_t)n, (uint32_t*)&counters[2], &overflow, fetch, finish);
+    else if (MODE == 3) closest_flat<uint32_t>(sc, (uint32_t)n, &overflow, fetch, finish);
     else closest_persistent_loop<uint32_t>(sc, (uint32_t)n, (uint32_t*)&counters[2], &overflow, fetch, finish);
     if (MODE == 1) { atomicAdd(&counters[0], (unsigned long long)ts.parent_visits); atomicAdd(&counters[1], (unsigned long long)ts.prim_tests); }
     if (overflow) atomicAdd(&totals->overflow, 1ull);
@@ -718,6 +724,7 @@ __global__ void __launch_bounds__(128) k_batch_any(DevScene sc, const float4* __
     };
     if (MODE == 1) trace_persistent<true, true, uint32_t>(sc, (uint32_t)n, (uint32_t*)&counters[2], &ts, &overflow, fetch, finish);
     else if (MODE == 2) any_persistent<uint32_t>(sc, (uint32_t)n, (uint32_t*)&counters[2], &overflow, fetch, finish);
+    else if (MODE == 3) any_flat<uint32_t>(sc, (uint32_t)n, &overflow, fetch, finish);
     else any_persistent_loop<uint32_t>(sc, (uint32_t)n, (uint32_t*)&counters[2], &overflow, fetch, finish);
     if (MODE == 1) { atomicAdd(&counters[0], (unsigned long long)ts.parent_visits); atomicAdd(&counters[1], (unsigned long long)ts.prim_tests); }
     if (overflow) atomicAdd(&totals->overflow, 1ull);
@@ -735,17 +742,18 @@ __global__ void k_batch_halton(DevScene sc, const uint32_t* __restrict__ px, con
             const uint32_t d = st.dim;
             const float v = sampler_get_sample(sc.sampler, st);
             value_out[i] = v;
-            // The renderer evaluates runs of consecutive dimensions as interleaved chains
-            // (scrambled_radical_inverse_n, halton.cuh).  Every value asked for here is also
-            // produced that way -- as the first of a pair and of a triple, whose other members are
-            // compared with their one-at-a-time values -- so the parity test of this entry point
+            // The renderer evaluates runs of consecutive dimensions as interleaved chains over chunk
+            // tables (scrambled_radical_inverse_n, halton.cuh).  Every value asked for here is also
+            // produced that way -- as the first of a pair and of a triple -- and all of them are compared
+            // with the reference's own digit-by-digit loop, so the parity test of this entry point
             // against the oracle covers the code path the shading kernels actually take.
             if (d >= 2 && d + 2 < 1000) {
                 float u3[3], u2[2];
                 scrambled_radical_inverse_n<3>(sc.sampler, st.index, d, u3);
                 scrambled_radical_inverse_n<2>(sc.sampler, st.index, d, u2);
-                const float v1 = scrambled_radical_inverse(sc.sampler, st.index, d + 1), v2 = scrambled_radical_inverse(sc.sampler, st.index, d + 2);
-                const bool same = __float_as_uint(u3[0]) == __float_as_uint(v) && __float_as_uint(u2[0]) == __float_as_uint(v) &&
+                const float v0 = scrambled_radical_inverse_digitwise(sc.sampler, st.index, d);
+                const float v1 = scrambled_radical_inverse_digitwise(sc.sampler, st.index, d + 1), v2 = scrambled_radical_inverse_digitwise(sc.sampler, st.index, d + 2);
+                const bool same = __float_as_uint(v0) == __float_as_uint(v) && __float_as_uint(u3[0]) == __float_as_uint(v) && __float_as_uint(u2[0]) == __float_as_uint(v) &&
                                   __float_as_uint(u3[1]) == __float_as_uint(v1) && __float_as_uint(u2[1]) == __float_as_uint(v1) &&
                                   __float_as_uint(u3[2]) == __float_as_uint(v2);
                 if (!same) atomicAdd(mismatches, 1ull);

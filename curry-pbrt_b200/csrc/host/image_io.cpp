@@ -39,6 +39,7 @@ bool read_png_rgb8(const std::string& path, uint32_t* w, uint32_t* h, std::vecto
         std::string typ(d.data() + pos + 4, 4);
         if (pos + 12 + len > d.size()) { *err = "truncated PNG: " + path; return false; }
         const uint8_t* body = p + 8;
+        if (typ == "IHDR" && len != 13) { *err = "bad PNG IHDR length: " + path; return false; }
         if (typ == "IHDR") { W = be32(body); H = be32(body + 4); depth = body[8]; ctype = body[9]; interlace = body[12]; }
         else if (typ == "IDAT") idat.append((const char*)body, len);
         else if (typ == "IEND") break;
@@ -107,7 +108,7 @@ static float half_to_float(uint16_t h) {
 namespace {
 struct ExrCursor {
     const uint8_t* p; size_t n, pos = 0; bool ok = true;
-    bool need(size_t k) { if (pos + k > n) ok = false; return ok; }
+    bool need(size_t k) { if (k > n || pos > n - k) ok = false; return ok; }   // no wrap-around for hostile offsets
     uint8_t u8() { return need(1) ? p[pos++] : 0; }
     uint32_t u32() { if (!need(4)) return 0; uint32_t v; memcpy(&v, p + pos, 4); pos += 4; return v; }   // little-endian host
     uint64_t u64() { if (!need(8)) return 0; uint64_t v; memcpy(&v, p + pos, 8); pos += 8; return v; }
@@ -365,6 +366,7 @@ bool read_exr_rgb(const std::string& path, uint32_t* w, uint32_t* h, std::vector
     rgb->assign((size_t)W * H * 3, 0.f);
     std::vector<uint8_t> tmp, raw;
     for (uint64_t b = 0; b < n_blocks; ++b) {
+        if (offsets[b] >= c.n) { *err = "bad OpenEXR chunk offset: " + path; return false; }
         ExrCursor k{c.p, c.n, (size_t)offsets[b]};
         const int32_t y0 = (int32_t)k.u32();
         const uint32_t size = k.u32();
