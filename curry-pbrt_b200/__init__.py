@@ -96,6 +96,10 @@ class Scene:
             pass
 
 
+def _count_flag(count):
+    return 4 if count == "own" else (2 if count else 0)
+
+
 class Renderer:
     """One GPU context: upload, BVH build (Aggregate::build) and the device entry points."""
 
@@ -142,11 +146,13 @@ class Renderer:
         return order, nodes
 
     def trace_closest(self, rays, count=False):
+        """count=True: reference-order traversal with its visit counters; count="own": the shipped
+        traversal counting its own node steps / primitive tests (include/cpbrt.h, CPBRT_TRACE_COUNT*)."""
         rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
         hits = np.zeros((rays.shape[0], 4), np.float32)
         stats = abi.Stats()
         self._check(lib.cpbrt_trace_closest(self._ctx, rays.ctypes.data, rays.shape[0], hits.ctypes.data,
-                                            2 if count else 0, C.byref(stats)))
+                                            _count_flag(count), C.byref(stats)))
         out = dict(t=hits[:, 0].copy(), prim=hits[:, 1].view(np.uint32).copy(), u=hits[:, 2].copy(), v=hits[:, 3].copy())
         return (out, stats) if count else out
 
@@ -155,18 +161,18 @@ class Renderer:
         out = np.zeros(rays.shape[0], np.uint8)
         stats = abi.Stats()
         self._check(lib.cpbrt_trace_any(self._ctx, rays.ctypes.data, rays.shape[0], out.ctypes.data,
-                                        2 if count else 0, C.byref(stats)))
+                                        _count_flag(count), C.byref(stats)))
         return (out, stats) if count else out
 
     def trace_closest_device(self, rays_ptr, n, hits_ptr, count=False):
         """Batch already resident in HBM (device pointers); returns Stats (ms_trace = kernel time)."""
         stats = abi.Stats()
-        self._check(lib.cpbrt_trace_closest(self._ctx, C.c_void_p(rays_ptr), n, C.c_void_p(hits_ptr), 1 | (2 if count else 0), C.byref(stats)))
+        self._check(lib.cpbrt_trace_closest(self._ctx, C.c_void_p(rays_ptr), n, C.c_void_p(hits_ptr), 1 | _count_flag(count), C.byref(stats)))
         return stats
 
     def trace_any_device(self, rays_ptr, n, out_ptr, count=False):
         stats = abi.Stats()
-        self._check(lib.cpbrt_trace_any(self._ctx, C.c_void_p(rays_ptr), n, C.c_void_p(out_ptr), 1 | (2 if count else 0), C.byref(stats)))
+        self._check(lib.cpbrt_trace_any(self._ctx, C.c_void_p(rays_ptr), n, C.c_void_p(out_ptr), 1 | _count_flag(count), C.byref(stats)))
         return stats
 
     def halton(self, px, py, sample, dim):
@@ -206,6 +212,10 @@ class Renderer:
     def bvh_gpu_levels(self):
         """Levels of the last cpbrt_build_bvh that ran on the device (0: pure host build)."""
         return int(lib.cpbrt_bvh_gpu_levels(self._ctx))
+
+    def h2d_bytes(self):
+        """Bytes this context has copied host -> device so far (counted where the copies are issued)."""
+        return int(lib.cpbrt_h2d_bytes(self._ctx))
 
     def read_bandwidth(self, nbytes, repeats=20):
         """GB/s of a read-only streaming kernel over a device buffer (roofline denominators)."""

@@ -139,6 +139,7 @@ DEVICE_SYMBOLS = {
     "cpbrt_camera_rays": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_int]),
     "cpbrt_render": (C.c_int, [C.c_void_p, C.POINTER(RenderParams), C.c_void_p, C.POINTER(Stats)]),
     "cpbrt_bvh_gpu_levels": (C.c_int, [C.c_void_p]),
+    "cpbrt_h2d_bytes": (C.c_uint64, [C.c_void_p]),
     "cpbrt_measure_read_bandwidth": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(C.c_double)]),
     "cpbrt_comm_unique_id": (C.c_int, [C.c_void_p]),
     "cpbrt_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),

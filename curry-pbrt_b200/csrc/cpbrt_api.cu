@@ -90,7 +90,7 @@ struct cpbrt_ctx {
     std::vector<DevLight> host_lights;
 
     DevScene scene;   // by-value kernel argument
-    DevBuf d_prims, d_prim_uv, d_prim_frame, d_nodes, d_flat, d_env, d_transforms, d_materials, d_textures, d_texels, d_lights, d_perm, d_primes, d_primsum, d_magic, d_halton_dims, d_halton_inv_pow, d_chunk_full, d_chunk_last;
+    DevBuf d_prims, d_prim_uv, d_prim_frame, d_nodes, d_flat, d_env, d_transforms, d_materials, d_textures, d_texels, d_lights, d_perm, d_primes, d_primsum, d_magic, d_halton_dims, d_halton_inv_pow;
 
     // wavefront state
     uint32_t path_capacity = 0;
@@ -226,7 +226,7 @@ void cpbrt_destroy(cpbrt_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     DevBuf* bufs[] = {&ctx->d_prims, &ctx->d_prim_uv, &ctx->d_prim_frame, &ctx->d_nodes, &ctx->d_flat, &ctx->d_env, &ctx->d_transforms, &ctx->d_materials, &ctx->d_textures, &ctx->d_texels,
-                      &ctx->d_lights, &ctx->d_perm, &ctx->d_primes, &ctx->d_primsum, &ctx->d_magic, &ctx->d_halton_dims, &ctx->d_halton_inv_pow, &ctx->d_chunk_full, &ctx->d_chunk_last, &ctx->d_path, &ctx->d_kind, &ctx->d_queues, &ctx->d_counts,
+                      &ctx->d_lights, &ctx->d_perm, &ctx->d_primes, &ctx->d_primsum, &ctx->d_magic, &ctx->d_halton_dims, &ctx->d_halton_inv_pow, &ctx->d_path, &ctx->d_kind, &ctx->d_queues, &ctx->d_counts,
                       &ctx->d_pixels, &ctx->d_totals_buf, &ctx->d_film_out};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < 6; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -426,43 +426,15 @@ int cpbrt_upload_scene(cpbrt_ctx* ctx, const cpbrt_scene_desc* d) {
         {
             std::vector<DevHaltonDim> dims(CPBRT_N_PRIMES);
             std::vector<float> inv_pow((size_t)CPBRT_N_PRIMES * kHaltonMaxDigits);
-            // chunk tables (halton.cuh): k digits at a time with B = p^k <= 4096 (tables that stay in L1), or
-            // k = 2 while p^2 still fits the 16-bit entries; larger primes keep the digit loop
-            std::vector<uint16_t> chunk_full; std::vector<uint2> chunk_last;
             for (int i = 0; i < CPBRT_N_PRIMES; ++i) {
-                const uint32_t p = primes[i];
-                const float inv_base = 1.f / (float)p;
-                DevHaltonDim& D = dims[i];
-                memset(&D, 0, sizeof D);
-                D.magic = magic[i]; D.base = p; D.primsum = sums[i];
-                D.tail = inv_base * (float)d->sampler.permutation[sums[i]] / (1.f - inv_base);
+                const float inv_base = 1.f / (float)primes[i];
+                dims[i].magic = magic[i]; dims[i].base = primes[i]; dims[i].primsum = sums[i];
+                dims[i].tail = inv_base * (float)d->sampler.permutation[sums[i]] / (1.f - inv_base);
+                dims[i].pad[0] = dims[i].pad[1] = dims[i].pad[2] = 0;
                 uint64_t pw = 1;
-                for (int c = 0; c < kHaltonMaxDigits; ++c) { inv_pow[(size_t)i * kHaltonMaxDigits + c] = 1.f / (float)pw; pw *= p; }
-                uint32_t k = 1, B = p;
-                while ((uint64_t)B * p <= 4096) { B *= p; ++k; }
-                if (k == 1 && (uint64_t)p * p <= 65536) { B = p * p; k = 2; }
-                // a table that is not a permutation of 0..p-1 (the reference would take it) could overflow the 16-bit entries
-                for (uint32_t j = 0; j < p && k > 1; ++j) if (d->sampler.permutation[sums[i] + j] >= p) { k = 1; B = p; }
-                D.chunk_digits = k; D.chunk_base = B; D.chunk_magic = 0xFFFFFFFFFFFFFFFFull / B + 1; D.chunk_off = 0;
-                if (k > 1) {
-                    D.chunk_off = (uint32_t)chunk_full.size();
-                    const uint16_t* perm = d->sampler.permutation + sums[i];
-                    chunk_full.resize(chunk_full.size() + B); chunk_last.resize(chunk_last.size() + B);
-                    for (uint32_t r = 0; r < B; ++r) {
-                        uint32_t full = 0, last = 0, m = 0, pm = 1, x = r;
-                        for (uint32_t j = 0; j < k; ++j) {          // least significant digit first, like the reference loop
-                            const uint32_t digit = x % p; x /= p;
-                            full = full * p + perm[digit];
-                        }
-                        for (x = r; x != 0; x /= p) { last = last * p + perm[x % p]; ++m; pm *= p; }
-                        chunk_full[D.chunk_off + r] = (uint16_t)full;
-                        chunk_last[D.chunk_off + r] = make_uint2(pm, last | (m << 24));
-                    }
-                }
+                for (int c = 0; c < kHaltonMaxDigits; ++c) { inv_pow[(size_t)i * kHaltonMaxDigits + c] = 1.f / (float)pw; pw *= primes[i]; }
             }
             if (int rc = alloc_upload(ctx, ctx->d_halton_dims, dims.data(), dims.size() * sizeof(DevHaltonDim))) return rc;
-            if (int rc = alloc_upload(ctx, ctx->d_chunk_full, chunk_full.data(), chunk_full.size() * 2)) return rc;
-            if (int rc = alloc_upload(ctx, ctx->d_chunk_last, chunk_last.data(), chunk_last.size() * sizeof(uint2))) return rc;
             if (int rc = alloc_upload(ctx, ctx->d_halton_inv_pow, inv_pow.data(), inv_pow.size() * 4)) return rc;
         }
         DevSampler& sm = S.sampler;
@@ -472,7 +444,6 @@ int cpbrt_upload_scene(cpbrt_ctx* ctx, const cpbrt_scene_desc* d) {
         if (sm.scale[0] != (1ull << sm.exp[0])) return ctx->fail(CPBRT_ERR_BAD_ARG, "sampler.scale[0] must be 2^exp[0]");
         sm.permutation = (const uint16_t*)ctx->d_perm.p; sm.primes = (const uint32_t*)ctx->d_primes.p; sm.primsum = (const uint32_t*)ctx->d_primsum.p; sm.prime_magic = (const uint64_t*)ctx->d_magic.p;
         sm.dims = (const DevHaltonDim*)ctx->d_halton_dims.p; sm.inv_pow = (const float*)ctx->d_halton_inv_pow.p;
-        sm.chunk_full = (const uint16_t*)ctx->d_chunk_full.p; sm.chunk_last = (const uint2*)ctx->d_chunk_last.p;
     }
     S.transforms = (const DevTransform*)ctx->d_transforms.p;
     S.materials = (const DevMaterial*)ctx->d_materials.p;
@@ -490,7 +461,7 @@ int cpbrt_upload_scene(cpbrt_ctx* ctx, const cpbrt_scene_desc* d) {
 // other ranks receive the finished arrays over NVLink (ncclBroadcast) instead of repeating the same
 // build on the same host cores: eight ranks share one CPU, and the host part of a 10-million-primitive
 // build would otherwise run eight times at an eighth of the threads.
-struct BvhShareHeader { uint32_t n_prims, n_nodes, root_ref, root_cnt, any_uv, pad[3]; float root_box[6]; float pad2[2]; };
+struct BvhShareHeader { uint32_t n_prims, n_nodes, root_ref, root_cnt, any_uv, status, pad[2]; float root_box[6]; float pad2[2]; };
 static bool share_bvh(const cpbrt_ctx* ctx, uint32_t n) {
     if (!ctx->comm || ctx->n_ranks <= 1 || !g_nccl.Broadcast) return false;
     const char* e = getenv("CPBRT_BVH_SHARE");
@@ -502,32 +473,60 @@ static int bcast(cpbrt_ctx* ctx, void* buf, size_t bytes) {
     if (rc != 0) return ctx->fail(CPBRT_ERR_NCCL, "ncclBroadcast: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
     return 0;
 }
-// both sides: header first (sizes), then the arrays, all on the context's stream
-static int exchange_bvh(cpbrt_ctx* ctx, uint32_t n, bool any_uv, const uint32_t* order_host, uint32_t* prim_order_out) {
+// Both sides: header first (sizes + rank 0's status), then every rank's own status is agreed on with one
+// all-reduce, and only if ALL ranks are fine do the array broadcasts follow.  A rank-local failure (rank 0's
+// build, a mismatching scene, an allocation, a bad argument) therefore ends the call with an error on every
+// rank after the same two collectives -- nobody is left waiting inside a broadcast.  `local_rc` is what this
+// rank already knows to be wrong (its error text is in ctx->error).  Collectives that fail themselves
+// (NCCL errors) leave the communicator unusable in any case.
+static int exchange_bvh(cpbrt_ctx* ctx, uint32_t n, int local_rc, bool any_uv, const uint32_t* order_host, uint32_t* prim_order_out) {
     DevScene& S = ctx->scene;
     const bool root = ctx->rank == 0;
     DevBuf d_hdr, d_order;
     BvhShareHeader h; memset(&h, 0, sizeof h);
-    if (root) { h.n_prims = n; h.n_nodes = S.n_nodes; h.root_ref = S.root_ref; h.root_cnt = S.root_cnt; h.any_uv = any_uv ? 1u : 0u; memcpy(h.root_box, S.root_box, sizeof h.root_box); }
-    if (int rc = alloc_upload(ctx, d_hdr, root ? &h : nullptr, sizeof h)) return rc;
-    int rc = bcast(ctx, d_hdr.p, sizeof h);
-    if (!rc && !root) {
+    if (root) { h.n_prims = n; h.n_nodes = S.n_nodes; h.root_ref = S.root_ref; h.root_cnt = S.root_cnt; h.any_uv = any_uv ? 1u : 0u; h.status = local_rc ? 1u : 0u; memcpy(h.root_box, S.root_box, sizeof h.root_box); }
+    const std::string first_error = local_rc ? ctx->error : std::string();
+    auto cleanup = [&]() { d_hdr.release(); d_order.release(); };
+    // the header buffer carries one extra int32 pair for the status all-reduce
+    struct { BvhShareHeader h; int32_t flag[4]; } up; up.h = h; up.flag[0] = up.flag[1] = up.flag[2] = up.flag[3] = 0;
+    if (int rc = alloc_upload(ctx, d_hdr, &up, sizeof up)) { cleanup(); return rc; }      // cannot even talk: peers see the NCCL time-out / abort
+    if (int rc = bcast(ctx, d_hdr.p, sizeof h)) { cleanup(); return rc; }
+    int status = local_rc;
+    if (!root) {
         cudaError_t e = cudaMemcpyAsync(&h, d_hdr.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) rc = ctx->fail(CPBRT_ERR_CUDA, "bvh header: %s", cudaGetErrorString(e));
-        else if (h.n_prims != n) rc = ctx->fail(CPBRT_ERR_BAD_ARG, "rank 0 built a BVH over %u primitives, this rank uploaded %u", h.n_prims, n);
-        if (!rc) {
+        if (e != cudaSuccess) status = status ? status : ctx->fail(CPBRT_ERR_CUDA, "bvh header: %s", cudaGetErrorString(e));
+        else if (h.status != 0) status = status ? status : ctx->fail(CPBRT_ERR_BAD_ARG, "rank 0 could not build the shared BVH");
+        else if (h.n_prims != n) status = status ? status : ctx->fail(CPBRT_ERR_BAD_ARG, "rank 0 built a BVH over %u primitives, this rank uploaded %u", h.n_prims, n);
+        if (!status) {
             S.n_nodes = h.n_nodes; S.root_ref = h.root_ref; S.root_cnt = h.root_cnt; memcpy(S.root_box, h.root_box, sizeof h.root_box);
             any_uv = h.any_uv != 0;
-            rc = alloc_upload(ctx, ctx->d_prims, nullptr, 3ull * n * sizeof(float4));
-            if (!rc) rc = alloc_upload(ctx, ctx->d_prim_uv, nullptr, any_uv ? 6ull * n * 4 : 0);
-            if (!rc) rc = alloc_upload(ctx, ctx->d_prim_frame, nullptr, 3ull * n * sizeof(float4));
-            if (!rc) rc = alloc_upload(ctx, ctx->d_nodes, nullptr, 4ull * h.n_nodes * sizeof(float4));
-            if (!rc) rc = alloc_upload(ctx, ctx->d_lights, ctx->host_lights.data(), ctx->host_lights.size() * sizeof(DevLight));
+            status = alloc_upload(ctx, ctx->d_prims, nullptr, 3ull * n * sizeof(float4));
+            if (!status) status = alloc_upload(ctx, ctx->d_prim_uv, nullptr, any_uv ? 6ull * n * 4 : 0);
+            if (!status) status = alloc_upload(ctx, ctx->d_prim_frame, nullptr, 3ull * n * sizeof(float4));
+            if (!status) status = alloc_upload(ctx, ctx->d_nodes, nullptr, 4ull * h.n_nodes * sizeof(float4));
+            if (!status) status = alloc_upload(ctx, ctx->d_lights, ctx->host_lights.data(), ctx->host_lights.size() * sizeof(DevLight));
         }
     }
-    if (!rc) rc = alloc_upload(ctx, d_order, root ? order_host : nullptr, (size_t)n * 4);
-    if (!rc) rc = bcast(ctx, ctx->d_prims.p, 3ull * n * sizeof(float4));
+    if (!status) status = alloc_upload(ctx, d_order, root ? order_host : nullptr, (size_t)n * 4);
+    // agreement: max over ranks of "something is wrong here"
+    {
+        int32_t* flag = reinterpret_cast<int32_t*>((char*)d_hdr.p + sizeof(BvhShareHeader));
+        const int32_t mine = status ? 1 : 0;
+        int32_t all = 1;
+        cudaError_t e = cudaMemcpyAsync(flag, &mine, 4, cudaMemcpyHostToDevice, ctx->stream);
+        int nrc = e == cudaSuccess ? g_nccl.AllReduce(flag, flag + 1, 1, kNcclInt32, kNcclMax, ctx->comm, ctx->stream) : 0;
+        if (e == cudaSuccess && nrc == 0) e = cudaMemcpyAsync(&all, flag + 1, 4, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess && nrc == 0) e = cudaStreamSynchronize(ctx->stream);
+        if (nrc != 0) { cleanup(); return ctx->fail(CPBRT_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "error"); }
+        if (e != cudaSuccess) { cleanup(); return ctx->fail(CPBRT_ERR_CUDA, "bvh exchange: %s", cudaGetErrorString(e)); }
+        if (all != 0) {
+            cleanup();
+            if (status) { if (!first_error.empty()) ctx->error = first_error; return status; }
+            return ctx->fail(CPBRT_ERR_BAD_ARG, "the shared BVH build failed on another rank");
+        }
+    }
+    int rc = bcast(ctx, ctx->d_prims.p, 3ull * n * sizeof(float4));
     if (!rc && any_uv) rc = bcast(ctx, ctx->d_prim_uv.p, 6ull * n * 4);
     if (!rc) rc = bcast(ctx, ctx->d_prim_frame.p, 3ull * n * sizeof(float4));
     if (!rc) rc = bcast(ctx, ctx->d_nodes.p, 4ull * S.n_nodes * sizeof(float4));
@@ -539,7 +538,7 @@ static int exchange_bvh(cpbrt_ctx* ctx, uint32_t n, bool any_uv, const uint32_t*
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) rc = ctx->fail(CPBRT_ERR_CUDA, "bvh exchange: %s", cudaGetErrorString(e));
     }
-    d_hdr.release(); d_order.release();
+    cleanup();
     if (!rc && !root) {
         S.prims = (const float4*)ctx->d_prims.p;
         S.prim_uv = any_uv ? (const float*)ctx->d_prim_uv.p : nullptr;
@@ -550,19 +549,8 @@ static int exchange_bvh(cpbrt_ctx* ctx, uint32_t n, bool any_uv, const uint32_t*
     return rc;
 }
 
-int cpbrt_build_bvh(cpbrt_ctx* ctx, uint32_t* prim_order_out, cpbrt_bvh_dump* dump) {
-    if (!ctx) return CPBRT_ERR_BAD_CTX;
-    if (!ctx->has_scene) return ctx->fail(CPBRT_ERR_BAD_CTX, "cpbrt_build_bvh before cpbrt_upload_scene");
-    CU(cudaSetDevice(ctx->device));
-    const uint32_t n = (uint32_t)ctx->primitives.size();
-    const bool shared = share_bvh(ctx, n);
-    if (shared && ctx->rank != 0) {
-        if (dump) return ctx->fail(CPBRT_ERR_BAD_ARG, "the node dump of a shared build is only available on rank 0");
-        ctx->bvh = BvhBuildResult(); ctx->bvh_gpu_levels = 0;
-        if (int rc = exchange_bvh(ctx, n, false, nullptr, prim_order_out)) return rc;
-        ctx->has_bvh = true;
-        return CPBRT_OK;
-    }
+// The build proper: SAH tree (device top levels + host subtrees, or host only), device layout, uploads.
+static int build_bvh_local(cpbrt_ctx* ctx, uint32_t n, bool* any_uv_out) {
     const bool timing = getenv("CPBRT_TIMING") != nullptr;
     auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     double t_mark = now();
@@ -787,11 +775,32 @@ int cpbrt_build_bvh(cpbrt_ctx* ctx, uint32_t* prim_order_out, cpbrt_bvh_dump* du
     S.prim_frame = n ? (const float4*)ctx->d_prim_frame.p : nullptr;
     S.nodes = (const float4*)ctx->d_nodes.p;
     CU(cudaStreamSynchronize(ctx->stream));
-    if (shared) { if (int rc = exchange_bvh(ctx, n, any_uv, R.order.data(), nullptr)) return rc; lap("broadcast to the other ranks"); }
-    ctx->has_bvh = true;
-
     lap("uploads");
-    if (!export_bvh(R, prim_order_out, dump))
+    *any_uv_out = any_uv;
+    return CPBRT_OK;
+}
+
+int cpbrt_build_bvh(cpbrt_ctx* ctx, uint32_t* prim_order_out, cpbrt_bvh_dump* dump) {
+    if (!ctx) return CPBRT_ERR_BAD_CTX;
+    if (!ctx->has_scene) return ctx->fail(CPBRT_ERR_BAD_CTX, "cpbrt_build_bvh before cpbrt_upload_scene");
+    CU(cudaSetDevice(ctx->device));
+    ctx->has_bvh = false;
+    const uint32_t n = (uint32_t)ctx->primitives.size();
+    const bool shared = share_bvh(ctx, n);
+    const bool builds = !shared || ctx->rank == 0;
+    // every argument / local check happens BEFORE the first collective, and whatever goes wrong on this rank is
+    // carried into the exchange as a status instead of an early return (the peers would wait forever)
+    int local_rc = 0; bool any_uv = false;
+    if (builds) local_rc = build_bvh_local(ctx, n, &any_uv);
+    else {
+        ctx->bvh = BvhBuildResult(); ctx->bvh_gpu_levels = 0;
+        if (dump) local_rc = ctx->fail(CPBRT_ERR_BAD_ARG, "the node dump of a shared build is only available on rank 0");
+    }
+    if (shared) {
+        if (int rc = exchange_bvh(ctx, n, local_rc, any_uv, builds && !local_rc ? ctx->bvh.order.data() : nullptr, prim_order_out)) return rc;
+    } else if (local_rc) return local_rc;
+    ctx->has_bvh = true;
+    if (builds && !export_bvh(ctx->bvh, prim_order_out, dump))
         return ctx->fail(CPBRT_ERR_BAD_ARG, "bvh dump capacity %llu < %llu nodes", (unsigned long long)dump->capacity, (unsigned long long)dump->n_nodes);
     return CPBRT_OK;
 }
@@ -807,11 +816,12 @@ static int ensure_totals(cpbrt_ctx* ctx) {
 static int check_overflow(cpbrt_ctx* ctx, const Totals& t) {
     if (t.overflow) return ctx->fail(CPBRT_ERR_UNSUPPORTED, "BVH deeper than the %d-entry traversal stack", kStackSize);
     if (t.bsdf_overflow) return ctx->fail(CPBRT_ERR_UNSUPPORTED, "a material expands to more than %d lobes of one kind", kMaxLobes);
+    if (t.replay_mismatch) return ctx->fail(CPBRT_ERR_CUDA, "film-point replay: %llu table-driven radical inverses differ from the digit loop", t.replay_mismatch);
     return 0;
 }
 
 int cpbrt_trace_closest(cpbrt_ctx* ctx, const cpbrt_ray* rays, uint64_t n, cpbrt_hit* hits_out, int flags, cpbrt_stats* stats) {
-    const int on_device = flags & CPBRT_TRACE_ON_DEVICE; const bool count = (flags & CPBRT_TRACE_COUNT) != 0;
+    const int on_device = flags & CPBRT_TRACE_ON_DEVICE; const bool count = (flags & CPBRT_TRACE_COUNT) != 0, count_own = (flags & CPBRT_TRACE_COUNT_OWN) != 0;
     if (!ctx) return CPBRT_ERR_BAD_CTX;
     if (!ctx->has_bvh) return ctx->fail(CPBRT_ERR_BAD_CTX, "cpbrt_trace_closest before cpbrt_build_bvh");
     if ((!rays || !hits_out) && n) return ctx->fail(CPBRT_ERR_BAD_ARG, "null ray / hit buffer");
@@ -832,7 +842,9 @@ int cpbrt_trace_closest(cpbrt_ctx* ctx, const cpbrt_ray* rays, uint64_t n, cpbrt
     cudaEventRecord(e0, ctx->stream);
     if (n) {
         const int sched = trace_schedule(ctx);
-        if (count) k_batch_closest<1><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, d_rays, n, d_hits, counters, ctx->d_totals);
+        if (count_own && sched == SCHED_VOTE) k_batch_closest<4><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, d_rays, n, d_hits, counters, ctx->d_totals);
+        else if (count_own && sched == SCHED_LOOP) k_batch_closest<5><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, d_rays, n, d_hits, counters, ctx->d_totals);
+        else if (count) k_batch_closest<1><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, d_rays, n, d_hits, counters, ctx->d_totals);
         else if (sched == SCHED_VOTE) k_batch_closest<2><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, d_rays, n, d_hits, counters, ctx->d_totals);
         else if (sched == SCHED_FLAT) k_batch_closest<3><<<grid_for(ctx, CPBRT_BLOCKS_FLAT), 128, flat_bytes(ctx), ctx->stream>>>(ctx->scene, d_rays, n, d_hits, counters, ctx->d_totals);
         else k_batch_closest<0><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, d_rays, n, d_hits, counters, ctx->d_totals);
@@ -853,7 +865,7 @@ int cpbrt_trace_closest(cpbrt_ctx* ctx, const cpbrt_ray* rays, uint64_t n, cpbrt
 }
 
 int cpbrt_trace_any(cpbrt_ctx* ctx, const cpbrt_ray* rays, uint64_t n, uint8_t* out, int flags, cpbrt_stats* stats) {
-    const int on_device = flags & CPBRT_TRACE_ON_DEVICE; const bool count = (flags & CPBRT_TRACE_COUNT) != 0;
+    const int on_device = flags & CPBRT_TRACE_ON_DEVICE; const bool count = (flags & CPBRT_TRACE_COUNT) != 0, count_own = (flags & CPBRT_TRACE_COUNT_OWN) != 0;
     if (!ctx) return CPBRT_ERR_BAD_CTX;
     if (!ctx->has_bvh) return ctx->fail(CPBRT_ERR_BAD_CTX, "cpbrt_trace_any before cpbrt_build_bvh");
     if ((!rays || !out) && n) return ctx->fail(CPBRT_ERR_BAD_ARG, "null ray / result buffer");
@@ -874,7 +886,9 @@ int cpbrt_trace_any(cpbrt_ctx* ctx, const cpbrt_ray* rays, uint64_t n, uint8_t* 
     cudaEventRecord(e0, ctx->stream);
     if (n) {
         const int sched = trace_schedule(ctx);
-        if (count) k_batch_any<1><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, d_rays, n, d_out, counters, ctx->d_totals);
+        if (count_own && sched == SCHED_VOTE) k_batch_any<4><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, d_rays, n, d_out, counters, ctx->d_totals);
+        else if (count_own && sched == SCHED_LOOP) k_batch_any<5><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, d_rays, n, d_out, counters, ctx->d_totals);
+        else if (count) k_batch_any<1><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, d_rays, n, d_out, counters, ctx->d_totals);
         else if (sched == SCHED_VOTE) k_batch_any<2><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, d_rays, n, d_out, counters, ctx->d_totals);
         else if (sched == SCHED_FLAT) k_batch_any<3><<<grid_for(ctx, CPBRT_BLOCKS_FLAT), 128, flat_bytes(ctx), ctx->stream>>>(ctx->scene, d_rays, n, d_out, counters, ctx->d_totals);
         else k_batch_any<0><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, d_rays, n, d_out, counters, ctx->d_totals);
@@ -955,6 +969,7 @@ static int ensure_wavefront(cpbrt_ctx* ctx, uint32_t n_paths) {
     char* pp = (char*)ctx->d_pixels.p;
     ctx->PX.base_index = (uint2*)pp; ctx->PX.film_point = (float2*)(pp + (size_t)npix * 8); ctx->PX.sum = (float4*)(pp + (size_t)npix * 16);
     if (ctx->path_capacity < n_paths) {
+        ctx->path_capacity = 0;      // stays 0 if any allocation below fails: the next call starts over instead of trusting freed buffers
         if (int rc = alloc_upload(ctx, ctx->d_path, nullptr, kPathBytes * n_paths)) return rc;
         if (int rc = alloc_upload(ctx, ctx->d_kind, nullptr, (size_t)n_paths + 4)) return rc;   // k_classify reads whole 32-bit words
         CU(cudaMemsetAsync(ctx->d_kind.p, 0xFF, (size_t)n_paths + 4, ctx->stream));
@@ -1015,12 +1030,18 @@ int cpbrt_render(cpbrt_ctx* ctx, const cpbrt_render_params* params, float* film_
     CU(cudaMemsetAsync(T, 0, sizeof(Totals), st));
     CU(cudaMemsetAsync(Q.counts, 0, 64 * 4, st));
 
-    cudaEvent_t e0, e1, e2; cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
+    // every event of this call lives in one bag that destroys them on ANY way out (error returns included)
+    struct EventBag {
+        std::vector<cudaEvent_t> all;
+        cudaEvent_t make() { cudaEvent_t e = nullptr; cudaEventCreate(&e); all.push_back(e); return e; }
+        ~EventBag() { for (cudaEvent_t e : all) if (e) cudaEventDestroy(e); }
+    } events;
+    cudaEvent_t e0 = events.make(), e1 = events.make(), e2 = events.make();
     // optional per-stage timing: event pairs around each stage, read back after the final sync
     struct Span { cudaEvent_t a, b; int stage; };   // 0 raygen/film, 1 trace closest, 2 trace shadow, 3 shade
     std::vector<Span> spans;
     const bool prof = rp.profile_stages != 0;
-    auto span_begin = [&](int stage) { if (prof) { Span s; cudaEventCreate(&s.a); cudaEventCreate(&s.b); s.stage = stage; cudaEventRecord(s.a, st); spans.push_back(s); } };
+    auto span_begin = [&](int stage) { if (prof) { Span s; s.a = events.make(); s.b = events.make(); s.stage = stage; cudaEventRecord(s.a, st); spans.push_back(s); } };
     auto span_end = [&]() { if (prof) cudaEventRecord(spans.back().b, st); };
     cudaEventRecord(e0, st);
     uint64_t launches = 0, trace_launches = 0;
@@ -1041,7 +1062,8 @@ int cpbrt_render(cpbrt_ctx* ctx, const cpbrt_render_params* params, float* film_
         const uint32_t skip = first_pass ? k0 : 0;
         first_pass = false;
         span_begin(0);
-        k_raygen<<<g_raygen, 128, 0, st>>>(S, PX, P, Q, k0, Sn, skip); ++launches;
+        if (skip) { k_film_replay<<<g_pix, 256, 0, st>>>(S, PX, 0, skip, T); ++launches; }
+        k_raygen<<<g_raygen, 128, 0, st>>>(S, PX, P, Q, k0, Sn, 0); ++launches;
         span_end();
         int cur = 0;
         if (recursive) {
@@ -1065,31 +1087,31 @@ int cpbrt_render(cpbrt_ctx* ctx, const cpbrt_render_params* params, float* film_
             if (flat) k_trace_closest<SCHED_FLAT><<<g_closest, 128, flat_sm, st>>>(S, P, Q, cur, T);
             else if (vote) k_trace_closest<SCHED_VOTE><<<g_closest, 128, 0, st>>>(S, P, Q, cur, T);
             else k_trace_closest<SCHED_LOOP><<<g_closest, 128, 0, st>>>(S, P, Q, cur, T);
-            ++trace_launches;
+            ++trace_launches; ++launches;
             span_end();
             if (!prof) { cudaEventRecord(eK1, st); cudaStreamWaitEvent(sa, ePrev, 0); }
             span_begin(2);
             if (flat) k_trace_shadow<SCHED_FLAT><<<g_shadow, 128, flat_sm, sa>>>(S, P, Q, T);
             else if (vote) k_trace_shadow<SCHED_VOTE><<<g_shadow, 128, 0, sa>>>(S, P, Q, T);
             else k_trace_shadow<SCHED_LOOP><<<g_shadow, 128, 0, sa>>>(S, P, Q, T);
+            ++launches;
             span_end();
             if (!prof) cudaStreamWaitEvent(sa, eK1, 0);
-            k_queue_reset<<<1, 32, 0, sa>>>(Q, cur, 0, T);
+            k_queue_reset<<<1, 32, 0, sa>>>(Q, cur, 0, T); ++launches;
             if (!prof) cudaEventRecord(eK3, sa);
             span_begin(3);
             k_classify<<<g_pix, 256, 0, st>>>(P, Q, Sn * npix); ++launches;
             if (!prof) { cudaEventRecord(eK4, st); cudaStreamWaitEvent(sb, eK4, 0); cudaStreamWaitEvent(sb, eK3, 0); }
-            k_shade_terminal<<<g_shade, 128, 0, sb>>>(S, P, Q);
-            k_shade<SHADE_MIRROR><<<g_shade, 128, 0, sb>>>(S, P, Q, next, T);
-            k_shade<SHADE_GLASS><<<g_shade, 128, 0, sb>>>(S, P, Q, next, T);
+            k_shade_terminal<<<g_shade, 128, 0, sb>>>(S, P, Q); ++launches;
+            k_shade<SHADE_MIRROR><<<g_shade, 128, 0, sb>>>(S, P, Q, next, T); ++launches;
+            k_shade<SHADE_GLASS><<<g_shade, 128, 0, sb>>>(S, P, Q, next, T); ++launches;
             if (ctx->has_general_materials) { k_shade<SHADE_GENERAL><<<grid_for(ctx, ShadeBlocks<SHADE_GENERAL>::value), 128, 0, sb>>>(S, P, Q, next, T); ++launches; }
             if (!prof) { cudaEventRecord(eS, sb); cudaStreamWaitEvent(st, eK3, 0); }
-            k_shade<SHADE_MATTE><<<grid_for(ctx, ShadeBlocks<SHADE_MATTE>::value), 128, 0, st>>>(S, P, Q, next, T);
+            k_shade<SHADE_MATTE><<<grid_for(ctx, ShadeBlocks<SHADE_MATTE>::value), 128, 0, st>>>(S, P, Q, next, T); ++launches;
             span_end();
             if (!prof) cudaStreamWaitEvent(st, eS, 0);
-            k_queue_reset<<<1, 32, 0, st>>>(Q, cur, 1, T);
+            k_queue_reset<<<1, 32, 0, st>>>(Q, cur, 1, T); ++launches;
             if (!prof) cudaEventRecord(ePrev, st);
-            launches += 8;
             cur = next;
         }
         span_begin(0);
@@ -1098,11 +1120,7 @@ int cpbrt_render(cpbrt_ctx* ctx, const cpbrt_render_params* params, float* film_
     }
     cudaEventRecord(e1, st);
     cudaError_t err = cudaGetLastError();
-    if (err != cudaSuccess) {
-        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
-        for (auto& sp : spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
-        return ctx->fail(CPBRT_ERR_CUDA, "render launch: %s", cudaGetErrorString(err));
-    }
+    if (err != cudaSuccess) return ctx->fail(CPBRT_ERR_CUDA, "render launch: %s", cudaGetErrorString(err));
 
     // film: single GPU -> resolve straight into the output.  With a communicator every GPU
     // writes its raw {sum, count} accumulator, one ncclReduce sums them on rank 0, and the
@@ -1138,13 +1156,11 @@ int cpbrt_render(cpbrt_ctx* ctx, const cpbrt_render_params* params, float* film_
     if (err == cudaSuccess) err = cudaStreamSynchronize(st);
     float ms_render = 0.f, ms_film = 0.f;
     if (err == cudaSuccess) { cudaEventElapsedTime(&ms_render, e0, e1); cudaEventElapsedTime(&ms_film, e1, e2); }
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
     double ms_stage[4] = {0, 0, 0, 0};
     for (auto& sp : spans) {
         float ms = 0.f;
         if (err == cudaSuccess) cudaEventElapsedTime(&ms, sp.a, sp.b);
         ms_stage[sp.stage] += ms;
-        cudaEventDestroy(sp.a); cudaEventDestroy(sp.b);
     }
     if (err != cudaSuccess) return ctx->fail(CPBRT_ERR_CUDA, "render: %s", cudaGetErrorString(err));
     if (stats) {
@@ -1162,6 +1178,8 @@ int cpbrt_render(cpbrt_ctx* ctx, const cpbrt_render_params* params, float* film_
 }
 
 int cpbrt_bvh_gpu_levels(const cpbrt_ctx* ctx) { return ctx ? ctx->bvh_gpu_levels : 0; }
+
+uint64_t cpbrt_h2d_bytes(const cpbrt_ctx* ctx) { return ctx ? ctx->h2d_bytes : 0; }
 
 int cpbrt_measure_read_bandwidth(cpbrt_ctx* ctx, uint64_t bytes, uint32_t repeats, double* gb_per_s) {
     if (!ctx) return CPBRT_ERR_BAD_CTX;

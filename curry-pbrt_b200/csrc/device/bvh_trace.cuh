@@ -384,8 +384,10 @@ enum TraceMode : int { MODE_SEARCH = 0, MODE_REPLAY = 1 };
 // Persistent-warp closest hit (two-phase), loop-scheduled: every lane descends to its next leaf,
 // then every lane tests that leaf.  The better schedule for small trees and coherent rays (a few
 // node steps per leaf, little to wait for); see closest_persistent below for the other one.
-template <class User, class Fetch, class Finish>
-__device__ void closest_persistent_loop(const DevScene& sc, uint32_t n_items, uint32_t* work_counter, uint32_t* overflow, Fetch fetch, Finish finish) {
+// COUNT: node steps (64-byte Parent fetches) and primitive tests (48-byte records) of THIS traversal are
+// added to *st -- the kernel's own work, for the roofline (the reference-order counters live in bvh_closest).
+template <class User, bool COUNT = false, class Fetch, class Finish>
+__device__ void closest_persistent_loop(const DevScene& sc, uint32_t n_items, uint32_t* work_counter, uint32_t* overflow, Fetch fetch, Finish finish, TraceStats* st = nullptr) {
     const int lane = threadIdx.x & 31;
     Ray ray; ray.o = v3(0.f, 0.f, 0.f); ray.d = v3(0.f, 0.f, 1.f); ray.t_max = 0.f;
     RayBoxSetup bs = ray_box_setup(ray);
@@ -440,6 +442,7 @@ __device__ void closest_persistent_loop(const DevScene& sc, uint32_t n_items, ui
             const float key = __uint_as_float(task.y);
             if (mode == MODE_SEARCH ? (key > t_cut) : !(key < ray.t_max)) { task = stack.pop(); continue; }
             const ChildTests c = expand_node2(sc, task.x, bs);
+            if (COUNT) ++st->parent_visits;
             if (mode == MODE_SEARCH) {
                 // near-first; a child is entered if the reference could reach it (its own
                 // predicate, against the initial t_max) and the tight interval meets [0, t_cut]
@@ -489,6 +492,7 @@ __device__ void closest_persistent_loop(const DevScene& sc, uint32_t n_items, ui
                 const uint32_t first = task.x & ~kLeafBit, end = first + task.y;
                 for (uint32_t s = first; s < end; ++s) {
                     const PrimRecord pr = load_prim(sc, s);
+                    if (COUNT) ++st->prim_tests;
                     float t;
                     if (mode == MODE_SEARCH) {
                         Ray probe = ray; probe.t_max = fminf(t_init, t_cut);
@@ -529,8 +533,8 @@ __device__ void closest_persistent_loop(const DevScene& sc, uint32_t n_items, ui
 // Persistent-warp any hit, loop-scheduled.  The result is a pure existence test against a constant t_max, so
 // the visiting order is free: nearer child first, reference predicate (required for parity)
 // plus the tight interval (prunes what the reference's loose test lets through).
-template <class User, class Fetch, class Finish>
-__device__ void any_persistent_loop(const DevScene& sc, uint32_t n_items, uint32_t* work_counter, uint32_t* overflow, Fetch fetch, Finish finish) {
+template <class User, bool COUNT = false, class Fetch, class Finish>
+__device__ void any_persistent_loop(const DevScene& sc, uint32_t n_items, uint32_t* work_counter, uint32_t* overflow, Fetch fetch, Finish finish, TraceStats* st = nullptr) {
     const int lane = threadIdx.x & 31;
     Ray ray; ray.o = v3(0.f, 0.f, 0.f); ray.d = v3(0.f, 0.f, 1.f); ray.t_max = 0.f;
     RayBoxSetup bs = ray_box_setup(ray);
@@ -569,6 +573,7 @@ __device__ void any_persistent_loop(const DevScene& sc, uint32_t n_items, uint32
         if (__all_sync(0xFFFFFFFFu, !have_ray)) break;
         while (have_ray && !(task.x & kLeafBit)) {
             const ChildTests c = expand_node2(sc, task.x, bs);
+            if (COUNT) ++st->parent_visits;
             bool go[2]; float key[2];
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
@@ -591,6 +596,7 @@ __device__ void any_persistent_loop(const DevScene& sc, uint32_t n_items, uint32
                 const uint32_t first = task.x & ~kLeafBit, end = first + task.y;
                 for (uint32_t s = first; s < end && !hit; ++s) {
                     const PrimRecord pr = load_prim(sc, s);
+                    if (COUNT) ++st->prim_tests;
                     float t;
                     if (prim_intersect_t(sc, pr, ray, ts, &t)) hit = true;
                 }
@@ -616,8 +622,8 @@ __device__ void any_persistent_loop(const DevScene& sc, uint32_t n_items, uint32
 // written back, and their lanes refilled, in groups of CPBRT_REFILL_* lanes.
 //   lane state   EMPTY (have_ray = false) | ACTIVE (task is a Parent or a leaf cursor) | DONE (task = kDone)
 //   leaf cursor  x = kLeafBit | next slot, y = primitives left
-template <class User, class Fetch, class Finish>
-__device__ void closest_persistent(const DevScene& sc, uint32_t n_items, uint32_t* work_counter, uint32_t* overflow, Fetch fetch, Finish finish) {
+template <class User, bool COUNT = false, class Fetch, class Finish>
+__device__ void closest_persistent(const DevScene& sc, uint32_t n_items, uint32_t* work_counter, uint32_t* overflow, Fetch fetch, Finish finish, TraceStats* st = nullptr) {
     const int lane = threadIdx.x & 31;
     Ray ray; ray.o = v3(0.f, 0.f, 0.f); ray.d = v3(0.f, 0.f, 1.f); ray.t_max = 0.f;
     RayBoxSetup bs = ray_box_setup(ray);
@@ -694,6 +700,7 @@ __device__ void closest_persistent(const DevScene& sc, uint32_t n_items, uint32_
                 if (mode == MODE_SEARCH ? (key > t_cut) : !(key < ray.t_max)) { task = stack.pop(); }
                 else {
                     const ChildTests c = expand_node2(sc, task.x, bs);
+            if (COUNT) ++st->parent_visits;
                     if (mode == MODE_SEARCH) {
                         // near-first; a child is entered if the reference could reach it (its own
                         // predicate, against the initial t_max) and the tight interval meets [0, t_cut]
@@ -742,6 +749,7 @@ __device__ void closest_persistent(const DevScene& sc, uint32_t n_items, uint32_
             if (want_prim) {
                 const uint32_t s = task.x & ~kLeafBit;
                 const PrimRecord pr = load_prim(sc, s);
+                    if (COUNT) ++st->prim_tests;
                 float t;
                 if (mode == MODE_SEARCH) {
                     Ray probe = ray; probe.t_max = fminf(t_init, t_cut);
@@ -764,8 +772,8 @@ __device__ void closest_persistent(const DevScene& sc, uint32_t n_items, uint32_
 // existence test against a constant t_max, so the visiting order is free: nearer child first,
 // reference predicate (required for parity) plus the tight interval (prunes what the reference's
 // loose test lets through).
-template <class User, class Fetch, class Finish>
-__device__ void any_persistent(const DevScene& sc, uint32_t n_items, uint32_t* work_counter, uint32_t* overflow, Fetch fetch, Finish finish) {
+template <class User, bool COUNT = false, class Fetch, class Finish>
+__device__ void any_persistent(const DevScene& sc, uint32_t n_items, uint32_t* work_counter, uint32_t* overflow, Fetch fetch, Finish finish, TraceStats* st = nullptr) {
     const int lane = threadIdx.x & 31;
     Ray ray; ray.o = v3(0.f, 0.f, 0.f); ray.d = v3(0.f, 0.f, 1.f); ray.t_max = 0.f;
     RayBoxSetup bs = ray_box_setup(ray);
@@ -816,6 +824,7 @@ __device__ void any_persistent(const DevScene& sc, uint32_t n_items, uint32_t* w
         if (__popc(m_node) >= __popc(m_prim)) {
             if (want_node) {
                 const ChildTests c = expand_node2(sc, task.x, bs);
+            if (COUNT) ++st->parent_visits;
                 bool go[2]; float key[2];
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
@@ -835,6 +844,7 @@ __device__ void any_persistent(const DevScene& sc, uint32_t n_items, uint32_t* w
         } else {
             if (want_prim) {
                 const PrimRecord pr = load_prim(sc, task.x & ~kLeafBit);
+                if (COUNT) ++st->prim_tests;
                 float t;
                 if (prim_intersect_t(sc, pr, ray, ts, &t)) { hit = true; task = make_uint2(kDone, 0u); }
                 else {

@@ -77,7 +77,8 @@ CP_DEV V3 apply_point(const float* __restrict__ m, V3 p) {
     float r1 = ((m[4] * p.x + m[5] * p.y) + m[6] * p.z) + m[7] * 1.f;
     float r2 = ((m[8] * p.x + m[9] * p.y) + m[10] * p.z) + m[11] * 1.f;
     float r3 = ((m[12] * p.x + m[13] * p.y) + m[14] * p.z) + m[15] * 1.f;
-    if (r3 != 0.f) return v3(r0 / r3, r1 / r3, r2 / r3);
+    // x / 1 == x bit for bit: affine matrices (every Translate / Scale / Rotate / LookAt) skip the three IEEE divisions
+    if (r3 != 0.f && r3 != 1.f) return v3(r0 / r3, r1 / r3, r2 / r3);
     return v3(r0, r1, r2);
 }
 CP_DEV V3 apply_vector(const float* __restrict__ m, V3 v) {

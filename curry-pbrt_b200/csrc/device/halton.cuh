@@ -34,118 +34,80 @@ CP_DEV float radical_inverse(uint64_t x, uint32_t base) {
     return inv_base_n * __ull2float_rn(acc);
 }
 
-// scrambled_radical_inverse (halton.rs:56-64): acc = acc * base + perm[digit] over the digits of x,
-// least significant first, then (acc + tail) / base^digits.
-//
-// The digit loop is one dependent chain (divide -> digit -> table look-up -> multiply-add) of 5..14
-// steps per dimension, and a matte bounce draws seven dimensions: 28 % of the shading kernel's
-// instructions (ncu, profiles/r01_s3_ncu_cornell.txt).  k consecutive digits of x are the base-p
-// digits of r = x mod p^k, and what they add to the accumulator,
-//     acc' = acc * p^k + (perm[d0] * p^(k-1) + ... + perm[d(k-1)]),
-// depends on r alone: it is tabulated per dimension (`chunk_full`, B = p^k entries) for every
-// prime whose B fits 16 bits.  The final chunk has only as many digits as the remaining quotient
-// (the reference stops at x == 0, leading zeros belong to `tail`), so it has its own table with the
-// digit count and p^m beside the value (`chunk_last`).  Same integers in acc and the same digit
-// count as the digit-by-digit loop, so the value is bit-identical (cpbrt_halton checks every
-// requested value against the one-digit-at-a-time evaluation on the device, and the parity test
-// against the oracle runs over it).  A 32-bit index now takes at most 3 steps in any dimension.
-// While the running quotient fits 32 bits the division is one 64-bit multiply-high with
-// floor(2^64 / B) + 1, exact for x < 2^32 and B < 2^17.
-struct HaltonChain { uint64_t magic, acc; uint32_t B, kd, off, cnt, xs; };
-
-CP_DEV void halton_chain_begin(const DevSampler& S, uint64_t x, uint32_t dim, HaltonChain& c, float* tail) {
+// scrambled_radical_inverse (halton.rs:56-64).  While the running quotient fits 32 bits the
+// division by the prime is one 64-bit multiply-high with floor(2^64/p)+1, which is exact for
+// x < 2^32 and p < 2^13 (error term x / 2^64 < 1 / p); same quotients, same digits.
+CP_DEV float scrambled_radical_inverse(const DevSampler& S, uint64_t x, uint32_t dim) {
     const float4* rec = reinterpret_cast<const float4*>(S.dims + dim);
     const float4 r0 = __ldg(rec), r1 = __ldg(rec + 1);
-    c.magic = ((uint64_t)__float_as_uint(r0.y) << 32) | __float_as_uint(r0.x);
-    c.B = __float_as_uint(r0.z); c.kd = __float_as_uint(r0.w); c.off = __float_as_uint(r1.x);
-    *tail = r1.w;
-    c.acc = 0; c.cnt = 0;
-    if ((x >> 32) != 0 || c.kd == 1) {
-        // digit by digit: until a 64-bit index fits 32 bits, and all the way for primes without a chunk table
-        const uint32_t base = __float_as_uint(r1.z);
-        const uint16_t* __restrict__ pm = S.permutation + __float_as_uint(r1.y);
-        while ((x >> 32) != 0) { const uint64_t q = x / base; const uint32_t digit = (uint32_t)(x - q * base); c.acc = c.acc * base + __ldg(&pm[digit]); ++c.cnt; x = q; }
-        if (c.kd == 1) {
-            uint32_t xs = (uint32_t)x;
-            while (xs != 0) { const uint32_t q = (uint32_t)__umul64hi((uint64_t)xs, c.magic); c.acc = c.acc * base + __ldg(&pm[xs - q * base]); ++c.cnt; xs = q; }
-            x = 0;
-        }
-    }
-    c.xs = (uint32_t)x;
-}
-CP_DEV bool halton_chain_full(const HaltonChain& c) { return c.xs >= c.B; }
-CP_DEV void halton_chain_last(const DevSampler& S, HaltonChain& c) {
-    if (c.xs != 0) {
-        const uint2 e = __ldg(&S.chunk_last[c.off + c.xs]);
-        c.acc = c.acc * e.x + (e.y & 0xFFFFFFu); c.cnt += e.y >> 24; c.xs = 0;
-    }
-}
-CP_DEV float halton_chain_value(const DevSampler& S, const HaltonChain& c, uint32_t dim, float tail) {
-    // inv_base_n and the tail of permuted zero digits were evaluated on the host with the same f32 operations
-    return __ldg(&S.inv_pow[dim * kHaltonMaxDigits + c.cnt]) * (__ull2float_rn(c.acc) + tail);
-}
-
-CP_DEV float scrambled_radical_inverse(const DevSampler& S, uint64_t x, uint32_t dim) {
-    HaltonChain c; float tail;
-    halton_chain_begin(S, x, dim, c, &tail);
-    while (halton_chain_full(c)) {
-        const uint32_t q = (uint32_t)__umul64hi((uint64_t)c.xs, c.magic);
-        c.acc = c.acc * c.B + __ldg(&S.chunk_full[c.off + (c.xs - q * c.B)]); c.cnt += c.kd; c.xs = q;
-    }
-    halton_chain_last(S, c);
-    return halton_chain_value(S, c, dim, tail);
-}
-
-// The reference loop itself, one digit per step: what cpbrt_halton compares the chunked evaluation with.
-CP_DEV float scrambled_radical_inverse_digitwise(const DevSampler& S, uint64_t x, uint32_t dim) {
-    const DevHaltonDim& d = S.dims[dim];
-    const uint32_t base = d.base;
-    const uint16_t* __restrict__ pm = S.permutation + d.primsum;
+    const uint64_t magic = ((uint64_t)__float_as_uint(r0.y) << 32) | __float_as_uint(r0.x);
+    const uint32_t base = __float_as_uint(r0.z);
+    const uint16_t* __restrict__ pm = S.permutation + __float_as_uint(r0.w);
+    const float tail = r1.x;
     uint64_t acc = 0; uint32_t count = 0;
-    while (x != 0) { const uint64_t q = x / base; acc = acc * base + __ldg(&pm[(uint32_t)(x - q * base)]); ++count; x = q; }
-    return __ldg(&S.inv_pow[dim * kHaltonMaxDigits + count]) * (__ull2float_rn(acc) + d.tail);
+    while ((x >> 32) != 0) { uint64_t q = x / base; uint32_t digit = (uint32_t)(x - q * base); acc = acc * base + __ldg(&pm[digit]); ++count; x = q; }
+    uint32_t xs = (uint32_t)x;
+    while (xs != 0) {
+        const uint32_t q = (uint32_t)__umul64hi((uint64_t)xs, magic);
+        const uint32_t digit = xs - q * base;
+        acc = acc * base + __ldg(&pm[digit]); ++count; xs = q;
+    }
+    // inv_base_n and the tail of permuted zero digits were evaluated on the host with the same f32 operations
+    const float inv_base_n = __ldg(&S.inv_pow[dim * kHaltonMaxDigits + count]);
+    return inv_base_n * (__ull2float_rn(acc) + tail);
 }
 
-// N consecutive dimensions of the same index at once.  The chains of different primes are
-// independent (multiply-high -> remainder -> table look-up -> accumulate); one at a time each step
-// waits out its own latencies, and the shading kernels have too few resident warps to cover them.
-// Walking N chains in one loop lets each chain's latency hide behind the others' instructions.
-// Same quotients, chunks and accumulators as N calls of scrambled_radical_inverse.
+// N consecutive dimensions of the same index at once.  The digit loops of different primes are
+// independent dependency chains (multiply-high -> digit -> table look-up -> accumulate); one at a
+// time each iteration waits out its own latencies, and the shading kernels have too few resident
+// warps to cover them.  Walking N chains in one loop lets each chain's latency hide behind the
+// others' instructions.  Same quotients, digits and accumulators as N calls of
+// scrambled_radical_inverse (matte shading stage: -3.5 % with pairs).
 #ifndef CPBRT_HALTON_PAIR
 #define CPBRT_HALTON_PAIR 1
 #endif
 template <int N>
 CP_DEV void scrambled_radical_inverse_n(const DevSampler& S, uint64_t x, uint32_t dim, float* out) {
-    HaltonChain c[N]; float tail[N];
+    uint64_t magic[N], acc[N]; uint32_t base[N], cnt[N], xs[N], off[N]; float tail[N];
 #pragma unroll
-    for (int k = 0; k < N; ++k) halton_chain_begin(S, x, dim + k, c[k], &tail[k]);
+    for (int k = 0; k < N; ++k) {
+        const float4* rec = reinterpret_cast<const float4*>(S.dims + dim + k);
+        const float4 r0 = __ldg(rec), r1 = __ldg(rec + 1);
+        magic[k] = ((uint64_t)__float_as_uint(r0.y) << 32) | __float_as_uint(r0.x);
+        base[k] = __float_as_uint(r0.z); off[k] = __float_as_uint(r0.w); tail[k] = r1.x;
+        acc[k] = 0; cnt[k] = 0;
+    }
+    if ((x >> 32) != 0) {      // the quotients of a 64-bit index differ per prime: each chain on its own until it fits 32 bits
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            uint64_t xk = x;
+            while ((xk >> 32) != 0) { const uint64_t q = xk / base[k]; const uint32_t digit = (uint32_t)(xk - q * base[k]); acc[k] = acc[k] * base[k] + __ldg(&S.permutation[off[k] + digit]); ++cnt[k]; xk = q; }
+            xs[k] = (uint32_t)xk;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < N; ++k) xs[k] = (uint32_t)x;
+    }
     for (;;) {
         bool all = true;
 #pragma unroll
-        for (int k = 0; k < N; ++k) all = all && halton_chain_full(c[k]);
+        for (int k = 0; k < N; ++k) all = all && xs[k] != 0;
         if (!all) break;
         uint32_t q[N], pv[N];
 #pragma unroll
-        for (int k = 0; k < N; ++k) q[k] = (uint32_t)__umul64hi((uint64_t)c[k].xs, c[k].magic);
+        for (int k = 0; k < N; ++k) q[k] = (uint32_t)__umul64hi((uint64_t)xs[k], magic[k]);
 #pragma unroll
-        for (int k = 0; k < N; ++k) pv[k] = __ldg(&S.chunk_full[c[k].off + (c[k].xs - q[k] * c[k].B)]);
+        for (int k = 0; k < N; ++k) pv[k] = __ldg(&S.permutation[off[k] + (xs[k] - q[k] * base[k])]);
 #pragma unroll
-        for (int k = 0; k < N; ++k) { c[k].acc = c[k].acc * c[k].B + pv[k]; c[k].cnt += c[k].kd; c[k].xs = q[k]; }
+        for (int k = 0; k < N; ++k) { acc[k] = acc[k] * base[k] + pv[k]; ++cnt[k]; xs[k] = q[k]; }
     }
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-        while (halton_chain_full(c[k])) {
-            const uint32_t q = (uint32_t)__umul64hi((uint64_t)c[k].xs, c[k].magic);
-            c[k].acc = c[k].acc * c[k].B + __ldg(&S.chunk_full[c[k].off + (c[k].xs - q * c[k].B)]); c[k].cnt += c[k].kd; c[k].xs = q;
+        while (xs[k] != 0) {
+            const uint32_t q = (uint32_t)__umul64hi((uint64_t)xs[k], magic[k]);
+            acc[k] = acc[k] * base[k] + __ldg(&S.permutation[off[k] + (xs[k] - q * base[k])]); ++cnt[k]; xs[k] = q;
         }
-    }
-    uint2 e[N];
-#pragma unroll
-    for (int k = 0; k < N; ++k) e[k] = c[k].xs != 0 ? __ldg(&S.chunk_last[c[k].off + c[k].xs]) : make_uint2(1u, 0u);
-#pragma unroll
-    for (int k = 0; k < N; ++k) {
-        c[k].acc = c[k].acc * e[k].x + (e[k].y & 0xFFFFFFu); c[k].cnt += e[k].y >> 24;
-        out[k] = halton_chain_value(S, c[k], dim + k, tail[k]);
+        out[k] = __ldg(&S.inv_pow[(dim + k) * kHaltonMaxDigits + cnt[k]]) * (__ull2float_rn(acc[k]) + tail[k]);
     }
 }
 
@@ -163,6 +125,15 @@ CP_DEV uint64_t halton_pixel_index(const DevSampler& S, uint32_t px, uint32_t py
     return idx % S.stride;
 }
 
+// Dimensions >= 1000 (a path ~120 bounces long): the reference draws rand::random() from the thread's
+// generator (halton.rs:131), which no implementation can reproduce.  A counter-based generator keyed
+// on (index, dimension) keeps such draws independent and uniform (a constant would bias roulette and
+// light selection on very long paths) and repeatable; the oracle uses the same function.
+CP_DEV float halton_overflow_sample(uint64_t index, uint32_t dim) {
+    uint64_t z = index * 0x9E3779B97F4A7C15ull + (uint64_t)dim * 0xD1B54A32D192ED03ull + 0x632BE59BD9B4E019ull;   // splitmix64 finaliser
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
+    return (float)(uint32_t)(z >> 40) * (1.f / 16777216.f);      // 24 bits: exact in f32, < 1
+}
 // get_sample (halton.rs:124-136)
 CP_DEV float sampler_get_sample(const DevSampler& S, SamplerState& st) {
     float r;
@@ -170,7 +141,7 @@ CP_DEV float sampler_get_sample(const DevSampler& S, SamplerState& st) {
     if (st.dim == 0) r = radical_inverse(st.index / S.scale[0], 2u);
     else if (st.dim == 1) r = radical_inverse(st.index / S.scale[1], 3u);
     else if (st.dim < 1000) r = scrambled_radical_inverse(S, st.index, st.dim);
-    else r = 0.5f;   // reference draws rand::random() here; unreachable for sane max_depth
+    else r = halton_overflow_sample(st.index, st.dim);   // reference: rand::random(), not reproducible by design
     ++st.dim;
     return r;
 }
@@ -183,6 +154,46 @@ CP_DEV P2 halton_film_sample(uint64_t q0, uint64_t q1) {
     p.x = a >= 1.f ? 1.f : a; p.y = b >= 1.f ? 1.f : b;
     return p;
 }
+// ---- radical_inverse(x, 3) without the digit loop -------------------------------------------------
+// A rank of a sample-partitioned render starts in the middle of the sample range and first has to
+// replay the film-point drift of every sample before it (render.rs:26-31): two radical inverses per
+// pixel and skipped sample, ~900 x 810 000 x 2 for the last of eight ranks.  The base-2 one is a bit
+// reversal; the base-3 one walks 13 digits.  Here the reversed digit string comes from a table of
+// reversed 7-digit chunks (3^7 = 2187 entries, built in shared memory by the block itself):
+//     x = c0 + 2187 * c1  (x < 3^14)   ->   R = rev7(c0) * 2187 + rev7(c1)      (14 digits, reversed)
+//     acc = R / 3^(14 - count)         exact, done as a multiplication by the inverse of 3^j modulo 2^32
+// with count = number of base-3 digits of x.  Same integer acc, same count, same two f32 operations
+// as radical_inverse (halton.rs:36-47, 65-70): bit-identical, and k_film_replay re-checks a sample
+// of its values against the digit loop on every run.
+struct Rev3Tables { uint16_t rev7[2187]; uint32_t pow3[16]; uint32_t inv3mod[16]; float inv_pw[16]; };
+CP_DEV void rev3_tables_fill(Rev3Tables& t) {
+    for (uint32_t c = threadIdx.x; c < 2187u; c += blockDim.x) {
+        uint32_t x = c, r = 0;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) { r = r * 3u + x % 3u; x /= 3u; }
+        t.rev7[c] = (uint16_t)r;
+    }
+    if (threadIdx.x < 16) {
+        uint32_t pw = 1, inv = 1;
+        for (uint32_t j = 0; j < threadIdx.x; ++j) { pw *= 3u; inv *= 0xAAAAAAABu; }      // 3 * 0xAAAAAAAB == 1 (mod 2^32)
+        t.pow3[threadIdx.x] = pw; t.inv3mod[threadIdx.x] = inv; t.inv_pw[threadIdx.x] = 1.f / __ull2float_rn((unsigned long long)pw);
+    }
+    __syncthreads();
+}
+CP_DEV float radical_inverse3_fast(const Rev3Tables& t, uint64_t x64) {
+    if (x64 >= 4782969ull) return radical_inverse(x64, 3u);      // 3^14 and beyond: the digit loop
+    const uint32_t x = (uint32_t)x64;
+    if (x == 0) return 0.f;
+    uint32_t c = x >= t.pow3[8] ? 8u : 0u;                       // c = number of digits - 1
+    if (x >= t.pow3[c + 4]) c += 4;
+    if (x >= t.pow3[c + 2]) c += 2;
+    if (x >= t.pow3[c + 1]) c += 1;
+    const uint32_t c1 = x / 2187u, c0 = x - c1 * 2187u;
+    const uint32_t R = (uint32_t)t.rev7[c0] * 2187u + t.rev7[c1];
+    const uint32_t acc = R * t.inv3mod[13u - c];
+    return t.inv_pw[c + 1] * __ull2float_rn((unsigned long long)acc);
+}
+
 // get_1d (sampler/mod.rs:10-17): the clamp constant 0.9999999999999 is 1.0 in f32
 CP_DEV float sampler_get_1d(const DevSampler& S, SamplerState& st) { float r = sampler_get_sample(S, st); return r >= 1.f ? 1.f : r; }
 CP_DEV P2 sampler_get_2d(const DevSampler& S, SamplerState& st) {

@@ -55,20 +55,13 @@ struct DevCamera {
     float lens_radius, focal_distance;
 };
 
-// one 48-byte record per Halton dimension (three 16-byte loads): everything scrambled_radical_inverse needs.
-// Digits are consumed in CHUNKS of `chunk_digits` at a time wherever the chunk base B = base^chunk_digits
-// still has a table (halton.cuh): `chunk_full[chunk_off + r]` holds the chunk_digits permuted digits of r
-// already combined, `chunk_last[chunk_off + r]` the same for the final, shorter chunk (r has fewer digits).
+// one 32-byte record per Halton dimension (two 16-byte loads): everything scrambled_radical_inverse needs
 struct DevHaltonDim {
-    uint64_t chunk_magic;   // floor(2^64 / B) + 1: x / B == umul64hi(x, chunk_magic) exactly for x < 2^32
-    uint32_t chunk_base;    // B = base^chunk_digits (<= 65536); == base when chunk_digits == 1
-    uint32_t chunk_digits;
-    uint32_t chunk_off;     // first entry of this dimension in chunk_full / chunk_last (unused when chunk_digits == 1)
-    uint32_t primsum;       // offset of the dimension's permutation block
-    uint32_t base;          // PRIMS[d]
-    float tail;             // inv_base * perm(0) / (1 - inv_base), evaluated on the host in f32 (halton.rs:61-63)
-    uint64_t magic;         // floor(2^64 / base) + 1
-    uint32_t pad[2];
+    uint64_t magic;      // floor(2^64 / base) + 1: x / base == umul64hi(x, magic) exactly for x < 2^32
+    uint32_t base;       // PRIMS[d]
+    uint32_t primsum;    // offset of the dimension's permutation block
+    float tail;          // inv_base * perm(0) / (1 - inv_base), evaluated on the host in f32 (halton.rs:61-63)
+    uint32_t pad[3];
 };
 static constexpr int kHaltonMaxDigits = 32;   // base >= 5 from dimension 2 on: at most 28 digits in 64 bits
 
@@ -83,8 +76,6 @@ struct DevSampler {
     const uint32_t* primsum;
     const uint64_t* prime_magic;     // floor(2^64 / p) + 1: x / p == umul64hi(x, magic) exactly for x < 2^32
     const DevHaltonDim* dims;        // the same per-dimension data gathered in one record
-    const uint16_t* chunk_full;      // see DevHaltonDim
-    const uint2* chunk_last;         // {base^m, value | m << 24} for a final chunk of m digits
     const float* inv_pow;            // [dim][digit count] = 1 / (base^count as f32)
 };
 

@@ -77,7 +77,7 @@ struct Queues {
 static constexpr int kCntClosest0 = 0, kCntShadow = 2, kCntShade0 = 3, kCntN = 3 + SHADE_KINDS;
 static constexpr int kCntWorkClosest = kCntN, kCntWorkShadow = kCntN + 1;   // work-distribution cursors of the persistent trace kernels
 // 64-bit totals that live after the counters: rays_closest, rays_any, nan_dropped, stack_overflow
-struct Totals { unsigned long long rays_closest, rays_any, nan_dropped, overflow, elided_closest, bsdf_overflow; };
+struct Totals { unsigned long long rays_closest, rays_any, nan_dropped, overflow, elided_closest, bsdf_overflow, replay_mismatch; };
 
 struct PixelArrays {
     uint2* base_index;   // Halton index of sample 0 (set_pixel)
@@ -144,6 +144,31 @@ CP_DEV Ray camera_generate_ray(const DevScene& sc, P2 film, SamplerState& st) {
     }
     if (cam.has_camera_to_world) { ray.o = apply_point(cam.camera_to_world, ray.o); ray.d = apply_vector(cam.camera_to_world, ray.d); }
     return ray;
+}
+
+// Film-point drift of samples [k_begin, k_end) that this GPU does not render (sample partitioning):
+// only dimensions 0 and 1 are evaluated for them, with the table-driven base-3 inverse of halton.cuh.
+// Every 61st (pixel, sample) is also evaluated with the digit loop; a difference is counted in
+// totals->replay_mismatch and fails the render.
+__global__ void __launch_bounds__(256) k_film_replay(DevScene sc, PixelArrays px, uint32_t k_begin, uint32_t k_end, Totals* totals) {
+    __shared__ Rev3Tables tab;
+    rev3_tables_fill(tab);
+    const uint32_t npix = sc.width * sc.height;
+    uint32_t bad = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x) {
+        const uint2 bi = px.base_index[i];
+        const uint64_t base = ((uint64_t)bi.y << 32) | bi.x;
+        float2 fp = px.film_point[i];
+        const uint64_t q0_base = base >> sc.sampler.exp[0], q1_base = base / sc.sampler.scale[1];
+        for (uint32_t k = k_begin; k < k_end; ++k) {
+            const uint64_t q0 = q0_base + (uint64_t)k * sc.sampler.scale[1], q1 = q1_base + (uint64_t)k * sc.sampler.scale[0];
+            const float a = radical_inverse(q0, 2u), b = radical_inverse3_fast(tab, q1);
+            if ((i + k) % 61u == 0u && __float_as_uint(b) != __float_as_uint(radical_inverse(q1, 3u))) ++bad;
+            fp.x += (a >= 1.f ? 1.f : a) - 0.5f; fp.y += (b >= 1.f ? 1.f : b) - 0.5f;           // render.rs:30-31
+        }
+        px.film_point[i] = fp;
+    }
+    if (bad) atomicAdd(&totals->replay_mismatch, (unsigned long long)bad);
 }
 
 // One thread per pixel; samples [k0, k0 + S) of that pixel go to paths s * npix + pixel.
@@ -679,7 +704,8 @@ __global__ void k_film_resolve_srgb8(DevScene sc, const float4* __restrict__ sum
 // Batch entry points used by the parity tests and the traversal benchmark.
 // counters: [0] Parent visits, [1] primitive tests, [2] work cursor (zeroed by the caller)
 // MODE: 0 = two-phase traversal, loop-scheduled; 1 = reference-order traversal with visit counters;
-//       2 = two-phase traversal, vote-scheduled; 3 = flat search (tiny scenes)
+//       2 = two-phase traversal, vote-scheduled; 3 = flat search (tiny scenes);
+//       4 / 5 = modes 2 / 0 counting their OWN node steps and primitive tests (roofline of the shipped kernels)
 template <int MODE>
 __global__ void __launch_bounds__(kTraceBlock, MODE == 2 ? CPBRT_BLOCKS_CLOSEST_VOTE : (MODE == 3 ? CPBRT_BLOCKS_FLAT : 1)) k_batch_closest(DevScene sc, const float4* __restrict__ rays, uint64_t n, float4* __restrict__ hits,
                                                        unsigned long long* counters, Totals* totals) {
@@ -705,8 +731,10 @@ __global__ void __launch_bounds__(kTraceBlock, MODE == 2 ? CPBRT_BLOCKS_CLOSEST_
     if (MODE == 1) trace_persistent<false, true, uint32_t>(sc, (uint32_t)n, (uint32_t*)&counters[2], &ts, &overflow, fetch, finish);
     else if (MODE == 2) closest_persistent<uint32_t>(sc, (uint32_t)n, (uint32_t*)&counters[2], &overflow, fetch, finish);
     else if (MODE == 3) closest_flat<uint32_t>(sc, (uint32_t)n, &overflow, fetch, finish);
+    else if (MODE == 4) closest_persistent<uint32_t, true>(sc, (uint32_t)n, (uint32_t*)&counters[2], &overflow, fetch, finish, &ts);
+    else if (MODE == 5) closest_persistent_loop<uint32_t, true>(sc, (uint32_t)n, (uint32_t*)&counters[2], &overflow, fetch, finish, &ts);
     else closest_persistent_loop<uint32_t>(sc, (uint32_t)n, (uint32_t*)&counters[2], &overflow, fetch, finish);
-    if (MODE == 1) { atomicAdd(&counters[0], (unsigned long long)ts.parent_visits); atomicAdd(&counters[1], (unsigned long long)ts.prim_tests); }
+    if (MODE == 1 || MODE >= 4) { atomicAdd(&counters[0], (unsigned long long)ts.parent_visits); atomicAdd(&counters[1], (unsigned long long)ts.prim_tests); }
     if (overflow) atomicAdd(&totals->overflow, 1ull);
 }
 template <int MODE>
@@ -725,8 +753,10 @@ __global__ void __launch_bounds__(128) k_batch_any(DevScene sc, const float4* __
     if (MODE == 1) trace_persistent<true, true, uint32_t>(sc, (uint32_t)n, (uint32_t*)&counters[2], &ts, &overflow, fetch, finish);
     else if (MODE == 2) any_persistent<uint32_t>(sc, (uint32_t)n, (uint32_t*)&counters[2], &overflow, fetch, finish);
     else if (MODE == 3) any_flat<uint32_t>(sc, (uint32_t)n, &overflow, fetch, finish);
+    else if (MODE == 4) any_persistent<uint32_t, true>(sc, (uint32_t)n, (uint32_t*)&counters[2], &overflow, fetch, finish, &ts);
+    else if (MODE == 5) any_persistent_loop<uint32_t, true>(sc, (uint32_t)n, (uint32_t*)&counters[2], &overflow, fetch, finish, &ts);
     else any_persistent_loop<uint32_t>(sc, (uint32_t)n, (uint32_t*)&counters[2], &overflow, fetch, finish);
-    if (MODE == 1) { atomicAdd(&counters[0], (unsigned long long)ts.parent_visits); atomicAdd(&counters[1], (unsigned long long)ts.prim_tests); }
+    if (MODE == 1 || MODE >= 4) { atomicAdd(&counters[0], (unsigned long long)ts.parent_visits); atomicAdd(&counters[1], (unsigned long long)ts.prim_tests); }
     if (overflow) atomicAdd(&totals->overflow, 1ull);
 }
 
@@ -742,18 +772,17 @@ __global__ void k_batch_halton(DevScene sc, const uint32_t* __restrict__ px, con
             const uint32_t d = st.dim;
             const float v = sampler_get_sample(sc.sampler, st);
             value_out[i] = v;
-            // The renderer evaluates runs of consecutive dimensions as interleaved chains over chunk
-            // tables (scrambled_radical_inverse_n, halton.cuh).  Every value asked for here is also
-            // produced that way -- as the first of a pair and of a triple -- and all of them are compared
-            // with the reference's own digit-by-digit loop, so the parity test of this entry point
+            // The renderer evaluates runs of consecutive dimensions as interleaved chains
+            // (scrambled_radical_inverse_n, halton.cuh).  Every value asked for here is also
+            // produced that way -- as the first of a pair and of a triple, whose other members are
+            // compared with their one-at-a-time values -- so the parity test of this entry point
             // against the oracle covers the code path the shading kernels actually take.
             if (d >= 2 && d + 2 < 1000) {
                 float u3[3], u2[2];
                 scrambled_radical_inverse_n<3>(sc.sampler, st.index, d, u3);
                 scrambled_radical_inverse_n<2>(sc.sampler, st.index, d, u2);
-                const float v0 = scrambled_radical_inverse_digitwise(sc.sampler, st.index, d);
-                const float v1 = scrambled_radical_inverse_digitwise(sc.sampler, st.index, d + 1), v2 = scrambled_radical_inverse_digitwise(sc.sampler, st.index, d + 2);
-                const bool same = __float_as_uint(v0) == __float_as_uint(v) && __float_as_uint(u3[0]) == __float_as_uint(v) && __float_as_uint(u2[0]) == __float_as_uint(v) &&
+                const float v1 = scrambled_radical_inverse(sc.sampler, st.index, d + 1), v2 = scrambled_radical_inverse(sc.sampler, st.index, d + 2);
+                const bool same = __float_as_uint(u3[0]) == __float_as_uint(v) && __float_as_uint(u2[0]) == __float_as_uint(v) &&
                                   __float_as_uint(u3[1]) == __float_as_uint(v1) && __float_as_uint(u2[1]) == __float_as_uint(v1) &&
                                   __float_as_uint(u3[2]) == __float_as_uint(v2);
                 if (!same) atomicAdd(mismatches, 1ull);

@@ -358,17 +358,6 @@ struct Builder {
                 idx.push_back((uint64_t)(int64_t)b.i);
             }
             add_mesh(idx, pf.data(), nv, &r);
-        } else if (n == "heightfield_lcg") {
-            // EXTENSION (not in the reference): the synthetic height-field mesh of benchmark
-            // configs C4 / C5, generated in place instead of being spelled out as a
-            // multi-hundred-megabyte trianglemesh.  Equivalent to a `trianglemesh` with
-            // (nx+1)*(nz+1) vertices and 2*nx*nz triangles; see heightfield_mesh() below.
-            uint64_t nx = 0, nz = 0, seed = 20260418;
-            if (!get_usize_prop(ps, "nx", &nx) || !get_usize_prop(ps, "nz", &nz) || nx == 0 || nz == 0) fail("heightfield_lcg needs integer nx, nz");
-            get_usize_prop(ps, "seed", &seed);
-            float height = 40.f, xmax = 556.f, zmax = 559.f;
-            get_float_prop(ps, "height", &height); get_float_prop(ps, "xmax", &xmax); get_float_prop(ps, "zmax", &zmax);
-            heightfield_mesh(nx, nz, seed, height, xmax, zmax, &r);
         } else if (n == "plymesh") {
             std::string fn, file;
             if (!get_string_prop(ps, "filename", &fn, &file)) fail("plymesh needs 'filename'");
@@ -395,39 +384,6 @@ struct Builder {
             out->push_back({CPBRT_SHAPE_TRIANGLE, (uint32_t)sd->triangles.size() - 1, -1});
         }
     }
-    // Height field y = height * noise(x, z): a 65x65 lattice of LCG values (state <- state *
-    // 6364136223846793005 + 1442695040888963407, value = top 24 bits / 2^24, row-major in z then x)
-    // interpolated bilinearly; vertices row-major in z; each quad (i, j) gives triangles
-    // (v, v+1, v+nx+2) and (v+nx+2, v+nx+1, v) with v = j*(nx+1)+i.
-    void heightfield_mesh(uint64_t nx, uint64_t nz, uint64_t seed, float height, float xmax, float zmax, std::vector<HShape>* out) {
-        const int L = 64;
-        std::vector<float> lat((L + 1) * (L + 1));
-        uint64_t x = seed;
-        for (auto& v : lat) { x = x * 6364136223846793005ull + 1442695040888963407ull; v = (float)(x >> 40) / 16777216.f; }
-        const size_t nv = (nx + 1) * (nz + 1);
-        std::vector<float> P(nv * 3);
-        for (uint64_t j = 0; j <= nz; ++j)
-            for (uint64_t i = 0; i <= nx; ++i) {
-                const float u = (float)i / (float)nx * (float)L, w = (float)j / (float)nz * (float)L;
-                int iu = (int)u, iw = (int)w;
-                if (iu >= L) iu = L - 1;
-                if (iw >= L) iw = L - 1;
-                const float fu = u - (float)iu, fw = w - (float)iw;
-                const float a = lat[iw * (L + 1) + iu], b = lat[iw * (L + 1) + iu + 1], c = lat[(iw + 1) * (L + 1) + iu], d = lat[(iw + 1) * (L + 1) + iu + 1];
-                const float n0 = a + (b - a) * fu, n1 = c + (d - c) * fu;
-                float* p = &P[(j * (nx + 1) + i) * 3];
-                p[0] = xmax * ((float)i / (float)nx); p[1] = height * (n0 + (n1 - n0) * fw); p[2] = zmax * ((float)j / (float)nz);
-            }
-        std::vector<uint64_t> idx; idx.reserve(nx * nz * 6);
-        for (uint64_t j = 0; j < nz; ++j)
-            for (uint64_t i = 0; i < nx; ++i) {
-                const uint64_t v = j * (nx + 1) + i;
-                const uint64_t q[6] = {v, v + 1, v + nx + 2, v + nx + 2, v + nx + 1, v};
-                idx.insert(idx.end(), q, q + 6);
-            }
-        add_mesh(idx, P.data(), nv, out);
-    }
-    // PlyParser (plymesh.rs:14-131): binary little-endian, float x y z nx ny nz u v, uint8+int faces
     void load_ply(const std::string& path, std::vector<HShape>* out) {
         std::ifstream f(path, std::ios::binary);
         if (!f) fail("cannot open ply '" + path + "'");
@@ -458,21 +414,19 @@ struct Builder {
             f.seekg(here);
             if (nv > left / 32 || nf > left / 13 || nv * 32 + nf * 13 > left) fail("ply: truncated file");
         }
-        std::vector<float> verts(nv * 3);
-        for (size_t i = 0; i < nv; ++i) {
-            float rec[8];
-            f.read((char*)rec, sizeof rec);
-            verts[i * 3] = rec[0]; verts[i * 3 + 1] = rec[1]; verts[i * 3 + 2] = rec[2];
-        }
-        std::vector<uint64_t> idx; idx.reserve(nf * 3);
-        for (size_t i = 0; i < nf; ++i) {
-            uint8_t cnt; int32_t v[3];
-            f.read((char*)&cnt, 1);
-            if (cnt != 3) fail("ply: only triangles");
-            f.read((char*)v, 12);
-            for (int k = 0; k < 3; ++k) idx.push_back((uint64_t)(int64_t)v[k]);
-        }
+        // one read for the whole body (a 10-million-triangle mesh is ~300 MB: record-by-record stream reads took seconds)
+        std::vector<char> body(nv * 32 + nf * 13);
+        f.read(body.data(), (std::streamsize)body.size());
         if (!f) fail("ply: truncated file");
+        std::vector<float> verts(nv * 3);
+        for (size_t i = 0; i < nv; ++i) memcpy(&verts[i * 3], &body[i * 32], 12);     // x y z; normals and uvs are not kept (plymesh.rs:82-131)
+        std::vector<uint64_t> idx(nf * 3);
+        const char* fp = body.data() + nv * 32;
+        for (size_t i = 0; i < nf; ++i) {
+            if ((uint8_t)fp[i * 13] != 3) fail("ply: only triangles");
+            int32_t v[3]; memcpy(v, fp + i * 13 + 1, 12);
+            for (int k = 0; k < 3; ++k) idx[i * 3 + k] = (uint64_t)(int64_t)v[k];
+        }
         add_mesh(idx, verts.data(), nv, out);
     }
 

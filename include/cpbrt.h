@@ -263,6 +263,11 @@ int cpbrt_build_bvh(cpbrt_ctx* ctx, uint32_t* prim_order_out, cpbrt_bvh_dump* no
  * stats_out (nullable) receives the kernel's device time and, with COUNT, the counters. */
 #define CPBRT_TRACE_ON_DEVICE 1
 #define CPBRT_TRACE_COUNT 2
+/* CPBRT_TRACE_COUNT_OWN = run the SHIPPED traversal (the schedule cpbrt_render uses for this scene) and count its own
+ * node steps (one 64-byte Parent record each) and primitive tests (one 48-byte record each) into
+ * trace_parent_visits / trace_prim_tests: the work the kernel really does, for its roofline.  Tree walks only
+ * (scenes of more than 64 primitives); wins over CPBRT_TRACE_COUNT when both are set. */
+#define CPBRT_TRACE_COUNT_OWN 4
 int cpbrt_trace_closest(cpbrt_ctx* ctx, const cpbrt_ray* rays, uint64_t n, cpbrt_hit* hits_out,
                         int flags, cpbrt_stats* stats_out);
 int cpbrt_trace_any(cpbrt_ctx* ctx, const cpbrt_ray* rays, uint64_t n, uint8_t* occluded_out,
@@ -287,6 +292,10 @@ int cpbrt_render(cpbrt_ctx* ctx, const cpbrt_render_params* params, float* film_
  * Scenes of >= 131072 primitives build the top of the tree (segments of >= 256 primitives) on the GPU and
  * finish the small subtrees on the host threads; the result is identical either way (bvh.rs:24-124). */
 int cpbrt_bvh_gpu_levels(const cpbrt_ctx* ctx);
+
+/* Bytes this context has copied host -> device since cpbrt_create (counted where the copies are issued):
+ * scene arrays, sampler tables, BVH layout, ray batches.  Bookkeeping for the end-to-end measurement. */
+uint64_t cpbrt_h2d_bytes(const cpbrt_ctx* ctx);
 
 /* Roofline denominators: read bandwidth of a zero-filled device buffer of `bytes` bytes
  * streamed `repeats` times by a read-only kernel (16-byte loads).  64 MB stays resident in the 126 MB

@@ -94,7 +94,13 @@ struct Sampler {   // HaltonSampler (halton.rs:71-79) behind the Sampler trait (
         Float r;
         if (dim < 2) r = radical_inverse(index / cfg->scale[dim], dim);
         else if (dim < 1000) r = scrambled_radical_inverse(index, dim, cfg->permutation);
-        else r = 0.5f;   // reference: rand::random(); unreachable with max_depth <= ~100
+        else {
+            // reference: rand::random() (halton.rs:131), not reproducible by design; a counter-based draw keyed on
+            // (index, dimension), the same function as the device path (halton.cuh, halton_overflow_sample)
+            uint64_t z = index * 0x9E3779B97F4A7C15ull + (uint64_t)dim * 0xD1B54A32D192ED03ull + 0x632BE59BD9B4E019ull;
+            z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
+            r = (Float)(uint32_t)(z >> 40) * (1.f / 16777216.f);
+        }
         ++dim;
         return r;
     }

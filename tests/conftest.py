@@ -53,6 +53,17 @@ def scene_text(name, xres=None, yres=None, spp=None, integrator=None):
     return text
 
 
+def c3_text(scene_text=None):
+    """BASELINE config C3: the Cornell box with box-texture.png as the Kd of its white surfaces, 1920x1080, 1024 spp."""
+    text = globals()["scene_text"]("cornel_box.pbrt", xres=1920, yres=1080, spp=1024)
+    text = text.replace('WorldBegin\n', 'WorldBegin\nTexture "boxtex" "spectrum" "imagemap" "string filename" "box-texture.png"\n', 1)
+    parts = text.split('Material "matte"\n"spectrum Kd"')
+    head = 'Material "matte"\n"spectrum Kd"'.join(parts[:4])
+    rest = parts[4]
+    rest = rest[rest.index(']') + 1:]
+    return head + 'Material "matte" "texture Kd" "boxtex"' + rest
+
+
 @pytest.fixture(scope="session")
 def make_scene(cpbrt):
     def _make(name, **kw):

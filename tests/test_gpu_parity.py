@@ -692,7 +692,7 @@ def test_c4_million_triangles(cpbrt, oracle):
     full size; the oracle traces a subset of the rays, the device all of them."""
     import importlib
     syn = importlib.import_module("curry-pbrt_b200.synthetic")
-    scene = cpbrt.Scene.parse(syn.heightfield_scene(1000, 500, 480, 270, 1))
+    scene = syn.load_heightfield(cpbrt, 1000, 500, 480, 270, 1)
     assert scene.desc.n_primitives == 1000008
     r = cpbrt.Renderer(0); r.upload(scene)
     order = r.build_bvh()

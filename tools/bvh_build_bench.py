@@ -20,7 +20,7 @@ def main():
     syn = importlib.import_module("curry-pbrt_b200.synthetic")
     for size in args.sizes.split(","):
         nx, nz = (int(v) for v in size.split("x"))
-        scene = cpbrt.Scene.parse(syn.heightfield_scene(nx, nz, 64, 64, 1))
+        scene = syn.load_heightfield(cpbrt, nx, nz, 64, 64, 1)
         r = cpbrt.Renderer(0); r.upload(scene)
         row = dict(size=size, primitives=int(scene.desc.n_primitives), host_threads=os.cpu_count())
         os.environ["CPBRT_BVH_BUILD"] = "host"

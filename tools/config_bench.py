@@ -27,16 +27,6 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
-def c3_text(scene_text):
-    text = scene_text("cornel_box.pbrt", xres=1920, yres=1080, spp=1024)
-    text = text.replace('WorldBegin\n', 'WorldBegin\nTexture "boxtex" "spectrum" "imagemap" "string filename" "box-texture.png"\n', 1)
-    parts = text.split('Material "matte"\n"spectrum Kd"')
-    head = 'Material "matte"\n"spectrum Kd"'.join(parts[:4])
-    rest = parts[4]
-    rest = rest[rest.index(']') + 1:]
-    return head + 'Material "matte" "texture Kd" "boxtex"' + rest
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="C1,C2,C3,C4")
@@ -47,7 +37,7 @@ def main():
     import numpy as np
     import __graft_entry__
     cpbrt = __graft_entry__.build()
-    from conftest import SCENES, scene_text
+    from conftest import SCENES, c3_text, scene_text
     syn = importlib.import_module("curry-pbrt_b200.synthetic")
 
     def make(name):
@@ -60,7 +50,8 @@ def main():
         cfg = dict(syn.CONFIGS[name])
         if name == "C5":
             cfg["spp"] = args.c5_spp
-        return cpbrt.Scene.parse(syn.heightfield_scene(**cfg)), "height field %d x %d quads, %dx%d path d5" % (cfg["nx"], cfg["nz"], cfg["xres"], cfg["yres"])
+        syn.write_heightfield_files(syn.default_dir(), **cfg)      # the mesh file is an input: written before the parse is timed
+        return syn.load_heightfield(cpbrt, **cfg), "height field %d x %d quads as .pbrt + binary .ply (plymesh), %dx%d path d5" % (cfg["nx"], cfg["nz"], cfg["xres"], cfg["yres"])
 
     for name in args.configs.split(","):
         t0 = time.perf_counter()

@@ -36,7 +36,10 @@ def main():
         torch.cuda.synchronize()
 
     barrier(); t0 = time.perf_counter()
-    scene = cpbrt.Scene.parse(syn.heightfield_scene(**cfg))
+    if rank == 0:
+        syn.write_heightfield_files(syn.default_dir(), **cfg)      # one writer; the others find the files
+    barrier()
+    scene = syn.load_heightfield(cpbrt, **cfg)
     barrier(); t_parse = time.perf_counter() - t0
     r = cpbrt.Renderer(local)
     r.upload(scene)

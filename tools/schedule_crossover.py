@@ -21,7 +21,7 @@ def main():
     from conftest import lcg_rays
     for size in args.sizes.split(","):
         nx, nz = (int(v) for v in size.split("x"))
-        scene = cpbrt.Scene.parse(syn.heightfield_scene(nx, nz, 960, 540, 16))
+        scene = syn.load_heightfield(cpbrt, nx, nz, 960, 540, 16)
         r = cpbrt.Renderer(0); r.upload(scene); r.build_bvh()
         rnd = lcg_rays(1 << args.rays, (0, 0, 0), (556, 548, 559), seed=7)
         sh = lcg_rays(1 << args.rays, (0, 0, 0), (556, 548, 559), seed=13)

@@ -37,7 +37,7 @@ def main():
     syn = importlib.import_module("curry-pbrt_b200.synthetic")
     from conftest import lcg_rays
     cfg = dict(syn.CONFIGS[args.config]); cfg["spp"] = 1
-    scene = cpbrt.Scene.parse(syn.heightfield_scene(**cfg))
+    scene = syn.load_heightfield(cpbrt, **cfg)
     r = cpbrt.Renderer(0)
     t0 = time.time(); r.upload(scene); r.build_bvh(); build_s = time.time() - t0
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
