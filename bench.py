@@ -56,6 +56,67 @@ def run_cpu_baseline(cpbrt, spp_sample, threads, count_visits):
                 stats=st, rect=rect, spp=spp_sample)
 
 
+def traversal_roofline(cpbrt, cornell_renderer):
+    """Roofline of the BVH traversal on the traversal-bound configuration C4 (1,000,008 triangles, written as
+    .pbrt + binary PLY and parsed like any scene): 2^22 random rays resident in HBM through the SHIPPED
+    closest-hit kernel (vote-scheduled two-phase walk), timed with CUDA events on the library's stream.
+
+    achieved = the kernel's OWN work, counted by the same kernel in its counting variant on the same rays:
+               node steps x 64 B (one Parent record) + primitive tests x 48 B (one record) + 48 B ray in / hit out
+    peak     = this GPU's L2 read bandwidth, measured in the same run by a streaming kernel over 64 MB
+               (the 94 MB of nodes + triangles live in the 126 MB L2; DRAM traffic is a few % of peak)
+    The reference's own visit counts (far-first, loose boxes) are 2-3x larger and are reported as
+    work_avoided_vs_reference, not as a fraction of anything."""
+    import importlib
+    import numpy as np
+    import torch
+    from conftest import lcg_rays
+    syn = importlib.import_module("curry-pbrt_b200.synthetic")
+    cfg = dict(syn.CONFIGS["C4"]); cfg["spp"] = 1
+    timing = {}
+    scene = syn.load_heightfield(cpbrt, timing=timing, **cfg)
+    r = cpbrt.Renderer(torch.cuda.current_device())
+    t0 = time.perf_counter(); r.upload(scene); r.build_bvh(); build_s = time.perf_counter() - t0
+    l2_gbs = r.read_bandwidth(64 << 20, 50)
+    n = 1 << 22
+    rays = torch.from_numpy(lcg_rays(n, (0, 0, 0), (556, 548, 559), seed=7)).cuda()
+    hits = torch.zeros(n * 4, dtype=torch.float32, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    own = r.trace_closest_device(rays.data_ptr(), n, hits.data_ptr(), count="own")
+    ref = r.trace_closest_device(rays.data_ptr(), n, hits.data_ptr(), count=True)
+    ms = []
+    for i in range(6):
+        flush.fill_(i); torch.cuda.synchronize()            # L2 flushed before every launch
+        st = r.trace_closest_device(rays.data_ptr(), n, hits.data_ptr())
+        if i:
+            ms.append(st.ms_trace)
+    ms_avg = sum(ms) / len(ms)
+    own_bytes = 64.0 * own.trace_parent_visits + 48.0 * own.trace_prim_tests + 48.0 * n
+    ref_bytes = 32.0 * ref.trace_parent_visits + 48.0 * ref.trace_prim_tests + 48.0 * n
+    achieved = own_bytes / (ms_avg * 1e-3) / 1e9
+    ncu = None
+    npath = os.path.join(ROOT, "profiles", "r02_ncu_c4_traversal.json")
+    if os.path.exists(npath):
+        ncu = json.load(open(npath))
+    out = dict(bound="l2", kernel="k_batch_closest<vote> (the closest-hit traversal cpbrt_render uses for scenes of >= 256 primitives)",
+               workload="C4: 1,000,008 triangles (.pbrt + binary PLY), 2^22 random rays (LCG seed 7) resident in HBM, L2 flushed before every launch",
+               achieved=achieved, peak=l2_gbs, unit="GB/s", frac=achieved / l2_gbs,
+               peak_source="measured in this run: read-only streaming kernel over 64 MB (cpbrt_measure_read_bandwidth)",
+               avg_launch_ms=ms_avg, launches_timed=len(ms), grays_s=n / (ms_avg * 1e-3) / 1e9,
+               own_node_steps_per_ray=own.trace_parent_visits / n, own_prim_tests_per_ray=own.trace_prim_tests / n,
+               algorithmic_bytes_per_ray=own_bytes / n,
+               work_avoided_vs_reference=dict(reference_parent_visits_per_ray=ref.trace_parent_visits / n, reference_prim_tests_per_ray=ref.trace_prim_tests / n,
+                                              reference_bytes_per_ray=ref_bytes / n, ratio=ref_bytes / own_bytes),
+               traffic=(ncu or {}).get("lts_bytes_per_launch"), traffic_unit="lts__t_bytes per launch of the same kernel on 2^20 of these rays (ncu --set full, profiles/r02_ncu_c4_traversal.json); null = no capture of this build",
+               issue=(ncu or {}).get("issue"),
+               hbm_peak_gbs=(json.load(open(PEAKS))["hbm_gbs"] if os.path.exists(PEAKS) else FALLBACK_HBM_GBS),
+               scene_load=dict(ply_write_s=timing.get("write_s"), parse_s=timing.get("parse_s"), upload_and_bvh_build_s=build_s),
+               note="the kernel is instruction-issue bound (divergent tree walk); see DESIGN.md 5 for the issue-slot figures from the same capture. "
+                    "The Cornell box of this bench line has 33 primitives and is traced without a tree walk (flat search from shared memory): no memory roofline applies there.")
+    r.close()
+    return out
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks + throttle reasons while the timed region runs (B200_PROFILING.md)."""
 
@@ -83,7 +144,9 @@ class ClockSampler(threading.Thread):
         mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for s in self.samples for i in range(4) if len(s) >= 7 and s[3 + i].lower().startswith("active")})
-        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons, n=len(self.samples))
+        pw = sorted(float(s[2]) for s in self.samples if len(s) > 2 and s[2].replace(".", "").isdigit())
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_min_mhz=sm[0] if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                    power_w_median=pw[len(pw) // 2] if pw else None, power_w_max=pw[-1] if pw else None, n=len(self.samples))
 
 
 def _claim_stdout():
@@ -117,7 +180,7 @@ def main():
     cpbrt = __graft_entry__.build()
     config = dict(workload="scenes/cornel_box.pbrt 900x900 path maxdepth=5 halton %d spp" % args.spp, spp=args.spp,
                   film=[900, 900], primitives=33, partition="sample-index" if world > 1 else "none",
-                  l2_policy="working set exceeds L2: every pass rewrites ~3.6 GB of path state (20 spp x 810k pixels x 224 B) "
+                  l2_policy="working set exceeds L2: every pass rewrites ~5.8 GB of path state (32 spp x 810k pixels x 224 B) "
                             "plus its queues, against 126 MB of L2; no flush needed")
 
     if args.impl == "reference":
@@ -183,8 +246,10 @@ def main():
     barrier()
     t0 = time.perf_counter()
     dev_ms, launches, rays_c, rays_a, rays_ct = 0.0, 0, 0, 0, 0
+    step_ms_list = []
     for _ in range(args.steps):
         st = step()
+        step_ms_list.append(round(st.ms_total, 2))
         dev_ms += st.ms_total; launches += st.kernel_launches; rays_c += st.rays_closest; rays_a += st.rays_any; rays_ct += st.rays_closest_traced
     barrier()
     wall = time.perf_counter() - t0
@@ -203,8 +268,49 @@ def main():
     step_ms = max(dev_ms, wall_ms) / args.steps
     value = samples / args.steps / (step_ms * 1e-3) / 1e6
 
-    # ---- stage profile + e2e + roofline + CPU baseline on rank 0 / N == 1 ---------------------
     extra = {}
+    # ---- e2e: the call a user makes, host buffers in and out, at N GPUs ---------------------------
+    # every step: cpbrt_upload_scene (H2D of the scene + Halton tables) + cpbrt_build_bvh +
+    # cpbrt_render into a host film on rank 0 (D2H); barrier-to-barrier wall time, max over ranks
+    # the host film is pinned memory (the read-back is then one DMA, not a staged copy through a bounce buffer)
+    host_film = None
+    if rank == 0:
+        pinned = torch.empty((H, W, 3), dtype=torch.float32).pin_memory()
+        host_film = pinned.numpy()
+    e2e_steps = max(1, args.steps)
+    for _ in range(2):          # warm-up of the upload / build path (first-use allocations)
+        r.upload(scene); r.build_bvh()
+    h2d_before = r.h2d_bytes()
+    phase = [0.0, 0.0, 0.0]
+    e2e_each, e2e_dev = [], []
+    clocks2 = ClockSampler(local_rank)
+    if rank == 0:
+        clocks2.start()
+    barrier()
+    t1 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ta = time.perf_counter(); r.upload(scene)
+        tb = time.perf_counter(); r.build_bvh()
+        tc = time.perf_counter(); _, est = r.render(film=host_film) if rank == 0 else r.render()
+        td = time.perf_counter()
+        phase[0] += tb - ta; phase[1] += tc - tb; phase[2] += td - tc
+        e2e_each.append(round(1e3 * (td - ta), 2)); e2e_dev.append(round(est.ms_total, 2))
+    barrier()
+    e2e_wall = time.perf_counter() - t1
+    clocks2.stop_flag.set()
+    e2e_t = torch.tensor([e2e_wall], dtype=torch.float64, device="cuda")
+    h2d = torch.tensor([float(r.h2d_bytes() - h2d_before)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(h2d, op=dist.ReduceOp.SUM)
+    e2e_s = float(e2e_t[0]) / e2e_steps
+    extra["e2e"] = dict(value=W * H * args.spp / e2e_s / 1e6, unit="Msamples/s", h2d_bytes_per_step=int(float(h2d[0]) / e2e_steps),
+                        d2h_bytes_per_step=W * H * 3 * 4, ms_per_step=e2e_s * 1e3, steps=e2e_steps, rank0_ms_of_each_step=e2e_each, rank0_device_ms_of_each_step=e2e_dev, clocks=clocks2.summary() if rank == 0 else None,
+                        rank0_ms_per_step=dict(upload_scene=1e3 * phase[0] / e2e_steps, build_bvh=1e3 * phase[1] / e2e_steps, render_and_readback=1e3 * phase[2] / e2e_steps),
+                        note="scene upload + BVH build + render + film read-back into pinned host memory per step, every rank uploads its own replica; "
+                             "h2d bytes are counted by the library where the copies are issued (cpbrt_h2d_bytes), summed over ranks")
+
+    # ---- stage profile + e2e + roofline + CPU baseline on rank 0 / N == 1 ---------------------
     if world == 1:
         st = step(profile=True)
         trace_ms = st.ms_trace_closest
@@ -219,47 +325,19 @@ def main():
             extra["cpu_baseline"] = dict(value=cb["msamples_s"], unit="Msamples/s", cores=cores, kind="port", mrays_s=cb["mrays_s"],
                                          sample="whole film %s at %d spp (%d samples) of the 1024, C++ restatement of the reference CPU path"
                                                 % (list(cb["rect"]), cb["spp"], cb["samples"]))
-            peak = FALLBACK_HBM_GBS; which = "fallback"
-            if os.path.exists(PEAKS):
-                peak = float(json.load(open(PEAKS))["hbm_gbs"]); which = "measured"
-            n_closest = st.rays_closest_traced   # rays that went through the traversal kernel
-            achieved = bytes_closest * n_closest / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else 0.0
-            # DRAM traffic of the kernel from the committed ncu capture (bytes per ms of kernel time x this run's launch time)
-            traffic = None
-            tpath = os.path.join(ROOT, "profiles", "r01_s3_traffic.json")
-            if os.path.exists(tpath) and st.trace_launches:
-                traffic = json.load(open(tpath))["k_trace_closest"]["dram_bytes_per_ms"] * (trace_ms / st.trace_launches)
-            extra["roofline"] = dict(bound="hbm", kernel="k_trace_closest", achieved=achieved, peak=peak, unit="GB/s",
-                                     frac=achieved / peak, traffic=traffic, traffic_unit="bytes per launch (ncu dram__bytes read+write, profiles/r01_s3_traffic.json)",
-                                     peak_source=which,
-                                     algorithmic_bytes_per_ray=bytes_closest, rays_per_launch=n_closest / max(1, st.trace_launches),
-                                     avg_launch_ms=trace_ms / max(1, st.trace_launches),
-                                     note="33-primitive scene: the BVH lives in L1/L2, so this is not an HBM-bound kernel; "
-                                          "see DESIGN.md and profiles/ for the 1M-triangle traversal roofline")
-    # ---- e2e: the call a user makes, host buffers in and out, at N GPUs ---------------------------
-    # every step: cpbrt_upload_scene (H2D of the scene + Halton tables) + cpbrt_build_bvh +
-    # cpbrt_render into a host film on rank 0 (D2H); barrier-to-barrier wall time, max over ranks
-    d = scene.desc
-    h2d = (int(d.n_primitives) * 24 + int(d.n_triangles) * 60 + int(d.n_spheres) * 4 + int(d.n_transforms) * 144 +
-           int(d.n_materials) * 48 + int(d.n_textures) * 40 + int(d.n_texels) * 4 + int(d.n_lights) * 48 +
-           cpbrt.abi.PERM_TABLE_LEN * 2 + 8000)
-    host_film = np.zeros((H, W, 3), np.float32) if rank == 0 else None
-    e2e_steps = max(1, min(args.steps, 2))
-    barrier()
-    t1 = time.perf_counter()
-    for _ in range(e2e_steps):
-        r.upload(scene)
-        r.build_bvh()
-        r.render(film=host_film) if rank == 0 else r.render()
-    barrier()
-    e2e_t = torch.tensor([time.perf_counter() - t1], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_s = float(e2e_t[0]) / e2e_steps
-    extra["e2e"] = dict(value=W * H * args.spp / e2e_s / 1e6, unit="Msamples/s", h2d_bytes_per_step=h2d * world,
-                        d2h_bytes_per_step=W * H * 3 * 4, ms_per_step=e2e_s * 1e3,
-                        note="scene upload + BVH build + render + film read-back per step, every rank uploads its own replica")
-
+            extra["reference_visit_bytes_per_ray_cornell"] = bytes_closest      # SURVEY 8d figure (the REFERENCE's far-first loose-box walk), kept for context
+        extra["roofline"] = traversal_roofline(cpbrt, r)
+        # the stage that dominates THIS workload (Cornell box): shading, bound by path-state traffic and latency.
+        # Algorithmic bytes per shaded hit = the 32-byte state records a bounce must read (ray, throughput, sampler
+        # state, pending direct-lighting terms) and write (new ray, throughput, state, shadow ray, two direct-lighting
+        # records, MIS ray) + queue entries: 4 x 32 + 7 x 32 + 16 = 368 B.
+        hbm = float(json.load(open(PEAKS))["hbm_gbs"]) if os.path.exists(PEAKS) else FALLBACK_HBM_GBS
+        shade_bytes = 368.0 * st.shade_items
+        extra["roofline_shading_stage"] = dict(bound="hbm", kernel="k_classify + k_shade<*> (all launches of the profiled step)",
+                                               achieved=shade_bytes / (st.ms_shade * 1e-3) / 1e9, peak=hbm, unit="GB/s",
+                                               frac=shade_bytes / (st.ms_shade * 1e-3) / 1e9 / hbm, bytes_per_shaded_hit=368, shaded_hits=int(st.shade_items),
+                                               stage_ms=st.ms_shade, peak_source="MEASURED_PEAKS.json hbm_gbs" if os.path.exists(PEAKS) else "fallback",
+                                               note="latency-bound at 20 resident warps per SM (96 registers): 46 % issue-active, DRAM 27 % of peak (ncu, profiles/)")
     if rank == 0:
         out = dict(metric="Msamples/s", value=value, unit="Msamples/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                    ms_per_step=step_ms, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32", data="synthetic",
@@ -268,7 +346,8 @@ def main():
                    rays_note="mrays_s counts the Scene::intersect / intersect_predicate calls of the reference whose result is used; "
                              "mrays_traced_s only those that needed a BVH traversal here (DESIGN.md 4.2)",
                    gpu_launches=launches,
-                   device_ms_per_step=dev_ms / args.steps, wall_ms_per_step=wall_ms / args.steps, clocks=clocks.summary())
+                   device_ms_per_step=dev_ms / args.steps, wall_ms_per_step=wall_ms / args.steps, rank0_device_ms_of_each_step=step_ms_list,
+                   clocks=clocks.summary())
         out.update(extra)
         json_out.write(json.dumps(out) + "\n")
         json_out.flush()

@@ -108,7 +108,7 @@ class Stats(C.Structure):
                 ("ms_raygen_film", C.c_double), ("ms_reduce", C.c_double),
                 ("trace_parent_visits", C.c_uint64), ("trace_prim_tests", C.c_uint64),
                 ("trace_launches", C.c_uint64), ("ms_trace_closest", C.c_double), ("ms_trace_shadow", C.c_double),
-                ("rays_closest_traced", C.c_uint64)]
+                ("rays_closest_traced", C.c_uint64), ("shade_items", C.c_uint64)]
 
 
 # name -> (restype, argtypes); every symbol include/cpbrt.h declares

@@ -72,10 +72,7 @@ const int kNcclFloat32 = 7, kNcclUint8 = 1, kNcclInt32 = 2, kNcclSum = 0, kNcclM
 struct cpbrt_ctx {
     int device = 0;
     int sm_count = 148;
-    cudaStream_t stream = nullptr;
-    // two auxiliary streams + a handful of timing-less events: independent stages of a bounce overlap (cpbrt_render)
-    cudaStream_t aux[2] = {nullptr, nullptr};
-    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t stream = nullptr;      // control stream: uploads, builds, batch entry points, start / end of a render
     std::string error;
     uint64_t h2d_bytes = 0;      // bytes copied host -> device by this context so far (counted where the copies are issued)
 
@@ -92,10 +89,20 @@ struct cpbrt_ctx {
     DevScene scene;   // by-value kernel argument
     DevBuf d_prims, d_prim_uv, d_prim_frame, d_nodes, d_flat, d_env, d_transforms, d_materials, d_textures, d_texels, d_lights, d_perm, d_primes, d_primsum, d_magic, d_halton_dims, d_halton_inv_pow;
 
-    // wavefront state
-    uint32_t path_capacity = 0;
-    DevBuf d_path, d_kind, d_queues, d_counts, d_pixels;
-    PathArrays P; Queues Q; PixelArrays PX;
+    // wavefront state: up to kMaxLanes independent pipelines ("lanes"), each with its own path state, queues,
+    // streams and events, so that consecutive passes of a render overlap on the GPU (cpbrt_render)
+    struct WaveLane {
+        uint32_t capacity = 0;
+        DevBuf d_path, d_kind, d_queues, d_counts;
+        PathArrays P; Queues Q;
+        cudaStream_t s[3] = {nullptr, nullptr, nullptr};        // main + two auxiliary streams of a bounce
+        cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+        cudaEvent_t raygen_done = nullptr, film_done = nullptr; // order of the per-pixel state across lanes
+    };
+    static constexpr int kMaxLanes = 2;
+    WaveLane lanes[kMaxLanes];
+    DevBuf d_pixels;
+    PixelArrays PX;
     Totals* d_totals = nullptr;
     DevBuf d_totals_buf, d_film_out;
 
@@ -213,8 +220,12 @@ int cpbrt_create(cpbrt_ctx** out, int device_id) {
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device_id);
     e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e); delete ctx; return CPBRT_ERR_CUDA; }
-    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking);
-    for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming);
+    for (auto& lane : ctx->lanes) {
+        for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&lane.s[i], cudaStreamNonBlocking);
+        for (int i = 0; i < 5 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&lane.ev[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&lane.raygen_done, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&lane.film_done, cudaEventDisableTiming);
+    }
     if (e != cudaSuccess) { g_create_error = std::string("cudaStreamCreate / cudaEventCreate: ") + cudaGetErrorString(e); cpbrt_destroy(ctx); return CPBRT_ERR_CUDA; }
     memset(&ctx->scene, 0, sizeof ctx->scene);
     *out = ctx;
@@ -226,11 +237,16 @@ void cpbrt_destroy(cpbrt_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     DevBuf* bufs[] = {&ctx->d_prims, &ctx->d_prim_uv, &ctx->d_prim_frame, &ctx->d_nodes, &ctx->d_flat, &ctx->d_env, &ctx->d_transforms, &ctx->d_materials, &ctx->d_textures, &ctx->d_texels,
-                      &ctx->d_lights, &ctx->d_perm, &ctx->d_primes, &ctx->d_primsum, &ctx->d_magic, &ctx->d_halton_dims, &ctx->d_halton_inv_pow, &ctx->d_path, &ctx->d_kind, &ctx->d_queues, &ctx->d_counts,
+                      &ctx->d_lights, &ctx->d_perm, &ctx->d_primes, &ctx->d_primsum, &ctx->d_magic, &ctx->d_halton_dims, &ctx->d_halton_inv_pow,
                       &ctx->d_pixels, &ctx->d_totals_buf, &ctx->d_film_out};
     for (DevBuf* b : bufs) b->release();
-    for (int i = 0; i < 6; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
-    for (int i = 0; i < 2; ++i) if (ctx->aux[i]) cudaStreamDestroy(ctx->aux[i]);
+    for (auto& lane : ctx->lanes) {
+        lane.d_path.release(); lane.d_kind.release(); lane.d_queues.release(); lane.d_counts.release();
+        for (cudaEvent_t ev : lane.ev) if (ev) cudaEventDestroy(ev);
+        if (lane.raygen_done) cudaEventDestroy(lane.raygen_done);
+        if (lane.film_done) cudaEventDestroy(lane.film_done);
+        for (cudaStream_t st : lane.s) if (st) cudaStreamDestroy(st);
+    }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -961,38 +977,41 @@ int cpbrt_camera_rays(cpbrt_ctx* ctx, uint32_t sample, cpbrt_ray* rays_out, int 
 }
 
 // ---- wavefront state ---------------------------------------------------------------------------
-static int ensure_wavefront(cpbrt_ctx* ctx, uint32_t n_paths) {
+static int ensure_wavefront(cpbrt_ctx* ctx, uint32_t n_paths, int n_lanes) {
     const uint32_t npix = ctx->scene.width * ctx->scene.height;
     if (ctx->d_pixels.bytes < (size_t)npix * 32) {
         if (int rc = alloc_upload(ctx, ctx->d_pixels, nullptr, (size_t)npix * 32)) return rc;
     }
     char* pp = (char*)ctx->d_pixels.p;
     ctx->PX.base_index = (uint2*)pp; ctx->PX.film_point = (float2*)(pp + (size_t)npix * 8); ctx->PX.sum = (float4*)(pp + (size_t)npix * 16);
-    if (ctx->path_capacity < n_paths) {
-        ctx->path_capacity = 0;      // stays 0 if any allocation below fails: the next call starts over instead of trusting freed buffers
-        if (int rc = alloc_upload(ctx, ctx->d_path, nullptr, kPathBytes * n_paths)) return rc;
-        if (int rc = alloc_upload(ctx, ctx->d_kind, nullptr, (size_t)n_paths + 4)) return rc;   // k_classify reads whole 32-bit words
-        CU(cudaMemsetAsync(ctx->d_kind.p, 0xFF, (size_t)n_paths + 4, ctx->stream));
-        ctx->P.shade_kind = (uint8_t*)ctx->d_kind.p;
-        // a path can have a MIS ray and a continuation ray queued at once: 2 entries per path
-        if (int rc = alloc_upload(ctx, ctx->d_queues, nullptr, (size_t)n_paths * 4 * (5 + SHADE_KINDS))) return rc;
-        ctx->path_capacity = n_paths;
-        char* p = (char*)ctx->d_path.p;
-        const size_t rec = (size_t)n_paths * 32;
-        PathArrays& P = ctx->P;
-        P.ray_o.base = (float4*)p; P.ray_d.base = (float4*)p + 1; P.hit_t.base = p; p += rec;
-        P.beta.base = (float4*)p; P.L.base = (float4*)p + 1; p += rec;
-        P.sh_o.base = (float4*)p; P.sh_d.base = (float4*)p + 1; p += rec;
-        P.mis_o.base = (float4*)p; P.mis_d.base = (float4*)p + 1; p += rec;
-        P.mis_A.base = (float4*)p; P.mis_p.base = (float4*)p + 1; p += rec;
-        P.nee_light.base = (float4*)p; P.nee_bsdf.base = (float4*)p + 1; p += rec;
-        P.beta_prev.base = (float4*)p; P.smp_index.base = p; P.smp_dim.base = p; P.hit_slot.base = p;
-        uint32_t* q = (uint32_t*)ctx->d_queues.p;
-        ctx->Q.closest[0] = q; q += 2 * (size_t)n_paths; ctx->Q.closest[1] = q; q += 2 * (size_t)n_paths; ctx->Q.shadow = q; q += n_paths;
-        for (int k = 0; k < SHADE_KINDS; ++k) { ctx->Q.shade[k] = q; q += n_paths; }
+    for (int li = 0; li < n_lanes; ++li) {
+        cpbrt_ctx::WaveLane& L = ctx->lanes[li];
+        if (L.capacity < n_paths) {
+            L.capacity = 0;      // stays 0 if any allocation below fails: the next call starts over instead of trusting freed buffers
+            if (int rc = alloc_upload(ctx, L.d_path, nullptr, kPathBytes * n_paths)) return rc;
+            if (int rc = alloc_upload(ctx, L.d_kind, nullptr, (size_t)n_paths + 4)) return rc;   // k_classify reads whole 32-bit words
+            CU(cudaMemsetAsync(L.d_kind.p, 0xFF, (size_t)n_paths + 4, ctx->stream));
+            L.P.shade_kind = (uint8_t*)L.d_kind.p;
+            // a path can have a MIS ray and a continuation ray queued at once: 2 entries per path
+            if (int rc = alloc_upload(ctx, L.d_queues, nullptr, (size_t)n_paths * 4 * (5 + SHADE_KINDS))) return rc;
+            L.capacity = n_paths;
+            char* p = (char*)L.d_path.p;
+            const size_t rec = (size_t)n_paths * 32;
+            PathArrays& P = L.P;
+            P.ray_o.base = (float4*)p; P.ray_d.base = (float4*)p + 1; P.hit_t.base = p; p += rec;
+            P.beta.base = (float4*)p; P.L.base = (float4*)p + 1; p += rec;
+            P.sh_o.base = (float4*)p; P.sh_d.base = (float4*)p + 1; p += rec;
+            P.mis_o.base = (float4*)p; P.mis_d.base = (float4*)p + 1; p += rec;
+            P.mis_A.base = (float4*)p; P.mis_p.base = (float4*)p + 1; p += rec;
+            P.nee_light.base = (float4*)p; P.nee_bsdf.base = (float4*)p + 1; p += rec;
+            P.beta_prev.base = (float4*)p; P.smp_index.base = p; P.smp_dim.base = p; P.hit_slot.base = p;
+            uint32_t* q = (uint32_t*)L.d_queues.p;
+            L.Q.closest[0] = q; q += 2 * (size_t)n_paths; L.Q.closest[1] = q; q += 2 * (size_t)n_paths; L.Q.shadow = q; q += n_paths;
+            for (int k = 0; k < SHADE_KINDS; ++k) { L.Q.shade[k] = q; q += n_paths; }
+        }
+        if (!L.d_counts.p) { if (int rc = alloc_upload(ctx, L.d_counts, nullptr, 64 * 4)) return rc; }
+        L.Q.counts = (uint32_t*)L.d_counts.p;
     }
-    if (!ctx->d_counts.p) { if (int rc = alloc_upload(ctx, ctx->d_counts, nullptr, 64 * 4)) return rc; }
-    ctx->Q.counts = (uint32_t*)ctx->d_counts.p;
     return ensure_totals(ctx);
 }
 
@@ -1023,12 +1042,22 @@ int cpbrt_render(cpbrt_ctx* ctx, const cpbrt_render_params* params, float* film_
     // measured 1 % ahead of 20, 4 % ahead of 8)
     if (spass == 0) { spass = (32u << 20) / npix; if (spass < 1) spass = 1; if (spass > 32) spass = 32; }
     if ((uint64_t)spass * npix >= 0x7FFFFFFFull) return ctx->fail(CPBRT_ERR_UNSUPPORTED, "film too large for one pass");
-    if (int rc = ensure_wavefront(ctx, spass * npix)) return rc;
-    const PathArrays P = ctx->P; const Queues Q = ctx->Q; const PixelArrays PX = ctx->PX;
+    // Two lanes: consecutive passes run as independent pipelines on their own streams and overlap on the GPU.
+    // The stages of a pass stress different things -- the traversal kernels saturate the math pipes, the shading
+    // kernels wait on memory at 20 resident warps per SM -- so one pass's shading fills the issue slots the other
+    // pass's traversal leaves, and the tails / launch gaps of one hide behind the other.  What couples two passes
+    // is the per-pixel state only: the film-point drift (k_raygen) and the sample-ordered sums (k_film) are chained
+    // across lanes with events, everything else is private to a lane.  profile_stages, the recursive direct-lighting
+    // kernel and single-pass renders use one lane on the control stream.  CPBRT_LANES=1|2 overrides.
+    const uint32_t n_passes = (s_end - s_begin + spass - 1) / spass;
+    int n_lanes = (rp.profile_stages || (ctx->recursive_direct && !rp.first_hit_only) || n_passes < 2) ? 1 : cpbrt_ctx::kMaxLanes;
+    if (const char* e = getenv("CPBRT_LANES")) n_lanes = std::max(1, std::min(n_lanes, atoi(e)));
+    if (int rc = ensure_wavefront(ctx, spass * npix, n_lanes)) return rc;
+    const PixelArrays PX = ctx->PX;
     Totals* T = ctx->d_totals;
     cudaStream_t st = ctx->stream;
     CU(cudaMemsetAsync(T, 0, sizeof(Totals), st));
-    CU(cudaMemsetAsync(Q.counts, 0, 64 * 4, st));
+    for (int li = 0; li < n_lanes; ++li) CU(cudaMemsetAsync(ctx->lanes[li].Q.counts, 0, 64 * 4, st));
 
     // every event of this call lives in one bag that destroys them on ANY way out (error returns included)
     struct EventBag {
@@ -1041,7 +1070,7 @@ int cpbrt_render(cpbrt_ctx* ctx, const cpbrt_render_params* params, float* film_
     struct Span { cudaEvent_t a, b; int stage; };   // 0 raygen/film, 1 trace closest, 2 trace shadow, 3 shade
     std::vector<Span> spans;
     const bool prof = rp.profile_stages != 0;
-    auto span_begin = [&](int stage) { if (prof) { Span s; s.a = events.make(); s.b = events.make(); s.stage = stage; cudaEventRecord(s.a, st); spans.push_back(s); } };
+    auto span_begin = [&](int stage) { if (prof) { Span s; s.a = events.make(); s.b = events.make(); s.stage = stage; cudaEventRecord(s.a, st); spans.push_back(s); } };      // prof => one lane on `st`
     auto span_end = [&]() { if (prof) cudaEventRecord(spans.back().b, st); };
     cudaEventRecord(e0, st);
     uint64_t launches = 0, trace_launches = 0;
@@ -1055,41 +1084,51 @@ int cpbrt_render(cpbrt_ctx* ctx, const cpbrt_render_params* params, float* film_
     k_pixel_setup<<<g_pix, 256, 0, st>>>(S, PX); ++launches;
     const uint32_t n_iters = S.integrator == CPBRT_INTEGRATOR_PATH ? S.max_depth + 1 : 2;
     const bool recursive = ctx->recursive_direct && !rp.first_hit_only;
-    bool first_pass = true;
-    for (uint32_t k0 = s_begin; k0 < s_end; k0 += spass) {
+    const bool multi = n_lanes > 1;
+    cudaEvent_t e_start = events.make();
+    if (multi) cudaEventRecord(e_start, st);       // pixel set-up done: the lanes may start
+    uint32_t pass_index = 0;
+    for (uint32_t k0 = s_begin; k0 < s_end; k0 += spass, ++pass_index) {
         const uint32_t Sn = std::min(spass, s_end - k0);
+        cpbrt_ctx::WaveLane& lane = ctx->lanes[pass_index % n_lanes];
+        const cpbrt_ctx::WaveLane* prev_lane = (multi && pass_index > 0) ? &ctx->lanes[(pass_index - 1) % n_lanes] : nullptr;
+        const PathArrays P = lane.P; const Queues Q = lane.Q;
+        // the pass's main stream; with one lane everything stays on the control stream
+        cudaStream_t sm = multi ? lane.s[0] : st;
+        if (multi && pass_index < (uint32_t)n_lanes) cudaStreamWaitEvent(sm, e_start, 0);
         // a rank that starts in the middle of the sample range first replays the film-point drift
-        const uint32_t skip = first_pass ? k0 : 0;
-        first_pass = false;
+        const uint32_t skip = pass_index == 0 ? k0 : 0;
         span_begin(0);
-        if (skip) { k_film_replay<<<g_pix, 256, 0, st>>>(S, PX, 0, skip, T); ++launches; }
-        k_raygen<<<g_raygen, 128, 0, st>>>(S, PX, P, Q, k0, Sn, 0); ++launches;
+        if (prev_lane) cudaStreamWaitEvent(sm, prev_lane->raygen_done, 0);      // film_point: sample order
+        if (skip) { k_film_replay<<<g_pix, 256, 0, sm>>>(S, PX, 0, skip, T); ++launches; }
+        k_raygen<<<g_raygen, 128, 0, sm>>>(S, PX, P, Q, k0, Sn, 0); ++launches;
+        if (multi) cudaEventRecord(lane.raygen_done, sm);
         span_end();
         int cur = 0;
         if (recursive) {
             span_begin(3);
-            k_direct_recursive<<<grid_for(ctx, 8), 64, 0, st>>>(S, P, Sn * npix, T); ++launches;
+            k_direct_recursive<<<grid_for(ctx, 8), 64, 0, sm>>>(S, P, Sn * npix, T); ++launches;
             span_end();
         }
         // One bounce = closest-hit stage (K1), shadow stage (K2), queue bookkeeping (K3), classify (K4),
         // the per-kind shading kernels (K5..) and their bookkeeping (K9).  K1 and K2 are independent, K4
         // only needs K1, and the shading kernels of different kinds touch different paths: they are put
         // on three streams so that the short, poorly filled kernels (terminal / mirror / glass / classify,
-        // ~8 % of a bounce when run back to back) and the tails of the persistent trace kernels overlap
-        // with the long ones.  `st` is the join point.  With profile_stages the bounce runs back to back
+        // ~8 % of a bounce when run back to back) and the tails of the trace kernels overlap
+        // with the long ones.  `sm` is the join point.  With profile_stages the bounce runs back to back
         // on one stream so that the per-stage times mean something.
-        cudaStream_t sa = prof ? st : ctx->aux[0], sb = prof ? st : ctx->aux[1];
-        cudaEvent_t eK1 = ctx->ev[0], eK3 = ctx->ev[1], eK4 = ctx->ev[2], eS = ctx->ev[3], ePrev = ctx->ev[4];
-        if (!prof && !recursive) cudaEventRecord(ePrev, st);          // after raygen
+        cudaStream_t sa = prof ? sm : lane.s[1], sb = prof ? sm : lane.s[2];
+        cudaEvent_t eK1 = lane.ev[0], eK3 = lane.ev[1], eK4 = lane.ev[2], eS = lane.ev[3], ePrev = lane.ev[4];
+        if (!prof && !recursive) cudaEventRecord(ePrev, sm);          // after raygen
         for (uint32_t it = 0; it < n_iters && !recursive; ++it) {
             const int next = cur ^ 1;
             span_begin(1);
-            if (flat) k_trace_closest<SCHED_FLAT><<<g_closest, 128, flat_sm, st>>>(S, P, Q, cur, T);
-            else if (vote) k_trace_closest<SCHED_VOTE><<<g_closest, 128, 0, st>>>(S, P, Q, cur, T);
-            else k_trace_closest<SCHED_LOOP><<<g_closest, 128, 0, st>>>(S, P, Q, cur, T);
+            if (flat) k_trace_closest<SCHED_FLAT><<<g_closest, 128, flat_sm, sm>>>(S, P, Q, cur, T);
+            else if (vote) k_trace_closest<SCHED_VOTE><<<g_closest, 128, 0, sm>>>(S, P, Q, cur, T);
+            else k_trace_closest<SCHED_LOOP><<<g_closest, 128, 0, sm>>>(S, P, Q, cur, T);
             ++trace_launches; ++launches;
             span_end();
-            if (!prof) { cudaEventRecord(eK1, st); cudaStreamWaitEvent(sa, ePrev, 0); }
+            if (!prof) { cudaEventRecord(eK1, sm); cudaStreamWaitEvent(sa, ePrev, 0); }
             span_begin(2);
             if (flat) k_trace_shadow<SCHED_FLAT><<<g_shadow, 128, flat_sm, sa>>>(S, P, Q, T);
             else if (vote) k_trace_shadow<SCHED_VOTE><<<g_shadow, 128, 0, sa>>>(S, P, Q, T);
@@ -1100,24 +1139,28 @@ int cpbrt_render(cpbrt_ctx* ctx, const cpbrt_render_params* params, float* film_
             k_queue_reset<<<1, 32, 0, sa>>>(Q, cur, 0, T); ++launches;
             if (!prof) cudaEventRecord(eK3, sa);
             span_begin(3);
-            k_classify<<<g_pix, 256, 0, st>>>(P, Q, Sn * npix); ++launches;
-            if (!prof) { cudaEventRecord(eK4, st); cudaStreamWaitEvent(sb, eK4, 0); cudaStreamWaitEvent(sb, eK3, 0); }
+            k_classify<<<g_pix, 256, 0, sm>>>(P, Q, Sn * npix); ++launches;
+            if (!prof) { cudaEventRecord(eK4, sm); cudaStreamWaitEvent(sb, eK4, 0); cudaStreamWaitEvent(sb, eK3, 0); }
             k_shade_terminal<<<g_shade, 128, 0, sb>>>(S, P, Q); ++launches;
             k_shade<SHADE_MIRROR><<<g_shade, 128, 0, sb>>>(S, P, Q, next, T); ++launches;
             k_shade<SHADE_GLASS><<<g_shade, 128, 0, sb>>>(S, P, Q, next, T); ++launches;
             if (ctx->has_general_materials) { k_shade<SHADE_GENERAL><<<grid_for(ctx, ShadeBlocks<SHADE_GENERAL>::value), 128, 0, sb>>>(S, P, Q, next, T); ++launches; }
-            if (!prof) { cudaEventRecord(eS, sb); cudaStreamWaitEvent(st, eK3, 0); }
-            k_shade<SHADE_MATTE><<<grid_for(ctx, ShadeBlocks<SHADE_MATTE>::value), 128, 0, st>>>(S, P, Q, next, T); ++launches;
+            if (!prof) { cudaEventRecord(eS, sb); cudaStreamWaitEvent(sm, eK3, 0); }
+            k_shade<SHADE_MATTE><<<grid_for(ctx, ShadeBlocks<SHADE_MATTE>::value), 128, 0, sm>>>(S, P, Q, next, T); ++launches;
             span_end();
-            if (!prof) cudaStreamWaitEvent(st, eS, 0);
-            k_queue_reset<<<1, 32, 0, st>>>(Q, cur, 1, T); ++launches;
-            if (!prof) cudaEventRecord(ePrev, st);
+            if (!prof) cudaStreamWaitEvent(sm, eS, 0);
+            k_queue_reset<<<1, 32, 0, sm>>>(Q, cur, 1, T); ++launches;
+            if (!prof) cudaEventRecord(ePrev, sm);
             cur = next;
         }
         span_begin(0);
-        k_film<<<g_pix, 128, 0, st>>>(S, PX, P, Sn, T); ++launches;
+        if (prev_lane) cudaStreamWaitEvent(sm, prev_lane->film_done, 0);        // per-pixel sums: sample order
+        k_film<<<g_pix, 128, 0, sm>>>(S, PX, P, Sn, T); ++launches;
+        if (multi) cudaEventRecord(lane.film_done, sm);
         span_end();
     }
+    // join: the last pass's k_film waited for the one before it, and so on down the chain
+    if (multi && pass_index > 0) cudaStreamWaitEvent(st, ctx->lanes[(pass_index - 1) % n_lanes].film_done, 0);
     cudaEventRecord(e1, st);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return ctx->fail(CPBRT_ERR_CUDA, "render launch: %s", cudaGetErrorString(err));
@@ -1133,7 +1176,7 @@ int cpbrt_render(cpbrt_ctx* ctx, const cpbrt_render_params* params, float* film_
     }
     if (ctx->comm) {
         // the path-state buffer is idle now: first npix*16 bytes = contribution, next = reduce target
-        float* contrib = (float*)ctx->d_path.p;
+        float* contrib = (float*)ctx->lanes[0].d_path.p;
         float* red = contrib + (size_t)npix * 4;
         k_film_resolve<<<g_pix, 256, 0, st>>>(S, PX.sum, contrib, 0); ++launches;
         int nrc = g_nccl.Reduce(contrib, red, (size_t)npix * 4, kNcclFloat32, kNcclSum, 0, ctx->comm, st);
@@ -1167,7 +1210,7 @@ int cpbrt_render(cpbrt_ctx* ctx, const cpbrt_render_params* params, float* film_
         memset(stats, 0, sizeof *stats);
         stats->camera_samples = (uint64_t)npix * (s_end - s_begin);
         stats->rays_closest = t.rays_closest + t.elided_closest; stats->rays_closest_traced = t.rays_closest; stats->rays_any = t.rays_any; stats->nan_dropped = t.nan_dropped;
-        stats->kernel_launches = launches; stats->ms_total = ms_render + ms_film;
+        stats->kernel_launches = launches; stats->ms_total = ms_render + ms_film; stats->shade_items = t.shade_items;
         stats->ms_reduce = ctx->comm ? ms_film : 0.0; stats->ms_raygen_film = ms_film;
         if (prof) {
             stats->ms_raygen_film = ms_stage[0] + ms_film; stats->ms_trace_closest = ms_stage[1]; stats->ms_trace_shadow = ms_stage[2];

@@ -180,9 +180,7 @@ CP_DEV void rev3_tables_fill(Rev3Tables& t) {
     }
     __syncthreads();
 }
-CP_DEV float radical_inverse3_fast(const Rev3Tables& t, uint64_t x64) {
-    if (x64 >= 4782969ull) return radical_inverse(x64, 3u);      // 3^14 and beyond: the digit loop
-    const uint32_t x = (uint32_t)x64;
+CP_DEV float radical_inverse3_fast32(const Rev3Tables& t, uint32_t x) {      // x < 3^14
     if (x == 0) return 0.f;
     uint32_t c = x >= t.pow3[8] ? 8u : 0u;                       // c = number of digits - 1
     if (x >= t.pow3[c + 4]) c += 4;
@@ -191,7 +189,18 @@ CP_DEV float radical_inverse3_fast(const Rev3Tables& t, uint64_t x64) {
     const uint32_t c1 = x / 2187u, c0 = x - c1 * 2187u;
     const uint32_t R = (uint32_t)t.rev7[c0] * 2187u + t.rev7[c1];
     const uint32_t acc = R * t.inv3mod[13u - c];
-    return t.inv_pw[c + 1] * __ull2float_rn((unsigned long long)acc);
+    return t.inv_pw[c + 1] * __uint2float_rn(acc);               // acc < 2^32: the same value __ull2float_rn gives
+}
+CP_DEV float radical_inverse3_fast(const Rev3Tables& t, uint64_t x64) {
+    if (x64 >= 4782969ull) return radical_inverse(x64, 3u);      // 3^14 and beyond: the digit loop
+    return radical_inverse3_fast32(t, (uint32_t)x64);
+}
+// radical_inverse(x, 2) for x < 2^32: bit reversal; 1 / 2^c is built from its exponent (exact, as the division is)
+CP_DEV float radical_inverse2_fast32(uint32_t x) {
+    if (x == 0) return 0.f;
+    const uint32_t c = 32u - (uint32_t)__clz((int)x);
+    const uint32_t acc = __brev(x) >> (32u - c);
+    return __uint_as_float((127u - c) << 23) * __uint2float_rn(acc);
 }
 
 // get_1d (sampler/mod.rs:10-17): the clamp constant 0.9999999999999 is 1.0 in f32

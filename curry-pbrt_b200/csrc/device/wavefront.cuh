@@ -77,7 +77,7 @@ struct Queues {
 static constexpr int kCntClosest0 = 0, kCntShadow = 2, kCntShade0 = 3, kCntN = 3 + SHADE_KINDS;
 static constexpr int kCntWorkClosest = kCntN, kCntWorkShadow = kCntN + 1;   // work-distribution cursors of the persistent trace kernels
 // 64-bit totals that live after the counters: rays_closest, rays_any, nan_dropped, stack_overflow
-struct Totals { unsigned long long rays_closest, rays_any, nan_dropped, overflow, elided_closest, bsdf_overflow, replay_mismatch; };
+struct Totals { unsigned long long rays_closest, rays_any, nan_dropped, overflow, elided_closest, bsdf_overflow, replay_mismatch, shade_items; };
 
 struct PixelArrays {
     uint2* base_index;   // Halton index of sample 0 (set_pixel)
@@ -148,7 +148,7 @@ CP_DEV Ray camera_generate_ray(const DevScene& sc, P2 film, SamplerState& st) {
 
 // Film-point drift of samples [k_begin, k_end) that this GPU does not render (sample partitioning):
 // only dimensions 0 and 1 are evaluated for them, with the table-driven base-3 inverse of halton.cuh.
-// Every 61st (pixel, sample) is also evaluated with the digit loop; a difference is counted in
+// Every 61st sample of a block's pixels is also evaluated with the digit loop; a difference is counted in
 // totals->replay_mismatch and fails the render.
 __global__ void __launch_bounds__(256) k_film_replay(DevScene sc, PixelArrays px, uint32_t k_begin, uint32_t k_end, Totals* totals) {
     __shared__ Rev3Tables tab;
@@ -160,11 +160,26 @@ __global__ void __launch_bounds__(256) k_film_replay(DevScene sc, PixelArrays px
         const uint64_t base = ((uint64_t)bi.y << 32) | bi.x;
         float2 fp = px.film_point[i];
         const uint64_t q0_base = base >> sc.sampler.exp[0], q1_base = base / sc.sampler.scale[1];
-        for (uint32_t k = k_begin; k < k_end; ++k) {
-            const uint64_t q0 = q0_base + (uint64_t)k * sc.sampler.scale[1], q1 = q1_base + (uint64_t)k * sc.sampler.scale[0];
-            const float a = radical_inverse(q0, 2u), b = radical_inverse3_fast(tab, q1);
-            if ((i + k) % 61u == 0u && __float_as_uint(b) != __float_as_uint(radical_inverse(q1, 3u))) ++bad;
-            fp.x += (a >= 1.f ? 1.f : a) - 0.5f; fp.y += (b >= 1.f ? 1.f : b) - 0.5f;           // render.rs:30-31
+        // both quotients advance by a constant per sample; when they stay below 2^32 / 3^14 over the whole range
+        // (every film up to a few thousand pixels a side at a few thousand spp) the loop runs on 32-bit integers
+        const uint64_t q0_last = q0_base + (uint64_t)k_end * sc.sampler.scale[1], q1_last = q1_base + (uint64_t)k_end * sc.sampler.scale[0];
+        if (q0_last < 0xFFFFFFFFull && q1_last < 4782969ull) {
+            uint32_t q0 = (uint32_t)(q0_base + (uint64_t)k_begin * sc.sampler.scale[1]), q1 = (uint32_t)(q1_base + (uint64_t)k_begin * sc.sampler.scale[0]);
+            const uint32_t d0 = (uint32_t)sc.sampler.scale[1], d1 = (uint32_t)sc.sampler.scale[0];
+            uint32_t check = (blockIdx.x + k_begin) % 61u;      // warp-uniform: a lane-dependent phase would send every warp through the digit loops on almost every sample
+            for (uint32_t k = k_begin; k < k_end; ++k, q0 += d0, q1 += d1) {
+                const float a = radical_inverse2_fast32(q0), b = radical_inverse3_fast32(tab, q1);
+                if (check == 0u && (__float_as_uint(b) != __float_as_uint(radical_inverse(q1, 3u)) || __float_as_uint(a) != __float_as_uint(radical_inverse(q0, 2u)))) ++bad;
+                check = check == 60u ? 0u : check + 1u;
+                fp.x += (a >= 1.f ? 1.f : a) - 0.5f; fp.y += (b >= 1.f ? 1.f : b) - 0.5f;           // render.rs:30-31
+            }
+        } else {
+            for (uint32_t k = k_begin; k < k_end; ++k) {
+                const uint64_t q0 = q0_base + (uint64_t)k * sc.sampler.scale[1], q1 = q1_base + (uint64_t)k * sc.sampler.scale[0];
+                const float a = radical_inverse(q0, 2u), b = radical_inverse3_fast(tab, q1);
+                if ((blockIdx.x + k) % 61u == 0u && __float_as_uint(b) != __float_as_uint(radical_inverse(q1, 3u))) ++bad;
+                fp.x += (a >= 1.f ? 1.f : a) - 0.5f; fp.y += (b >= 1.f ? 1.f : b) - 0.5f;           // render.rs:30-31
+            }
         }
         px.film_point[i] = fp;
     }
@@ -360,15 +375,16 @@ __global__ void __launch_bounds__(kTraceBlock, SCHED == SCHED_VOTE ? CPBRT_BLOCK
 // empty those queues; `which` 0 = after trace, 1 = after shade.
 __global__ void k_queue_reset(Queues Q, int cur, int which, Totals* totals) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    // atomics: two lanes (cpbrt_render) run this kernel concurrently on the same totals
     if (which == 0) {
-        totals->rays_closest += Q.counts[kCntClosest0 + cur];
-        totals->rays_any += Q.counts[kCntShadow];
+        atomicAdd(&totals->rays_closest, (unsigned long long)Q.counts[kCntClosest0 + cur]);
+        atomicAdd(&totals->rays_any, (unsigned long long)Q.counts[kCntShadow]);
         Q.counts[kCntClosest0 + cur] = 0;
         Q.counts[kCntShadow] = 0;
         Q.counts[kCntWorkClosest] = 0;
         Q.counts[kCntWorkShadow] = 0;
     } else {
-        for (int k = 0; k < SHADE_KINDS; ++k) Q.counts[kCntShade0 + k] = 0;
+        for (int k = 0; k < SHADE_KINDS; ++k) { atomicAdd(&totals->shade_items, (unsigned long long)Q.counts[kCntShade0 + k]); Q.counts[kCntShade0 + k] = 0; }
     }
 }
 

@@ -71,11 +71,11 @@ int cpbrt_scene_set_integrator(cpbrt_scene* scene, uint32_t integrator, uint32_t
 void cpbrt_make_permutation(uint64_t seed, uint16_t* out) { make_permutation(seed, out); }
 
 // Sample-index share of a rank (see curry-pbrt_b200/partition.py for the reasoning): boundaries
-// b_k = round(spp * (1 - q^k) / (1 - q^n)), q = 1 - 1/160, in IEEE double with this exact operation order.
+// b_k = round(spp * (1 - q^k) / (1 - q^n)), q = 1 - 1/420, in IEEE double with this exact operation order.
 static uint32_t share_boundary(uint32_t spp, int k, int n_ranks) {
     if (k <= 0) return 0;
     if (k >= n_ranks) return spp;
-    const double q = 1.0 - 1.0 / 160.0;
+    const double q = 1.0 - 1.0 / 420.0;
     double qk = 1.0, qn = 1.0;
     for (int i = 0; i < n_ranks; ++i) { qn *= q; if (i < k) qk *= q; }
     const double b = (double)spp * ((1.0 - qk) / (1.0 - qn)) + 0.5;

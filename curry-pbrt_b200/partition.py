@@ -10,7 +10,7 @@ rendering n_g samples plus replaying the s_g before them takes the same time on 
 Pure integer / IEEE-double logic, importable without the CUDA library.
 """
 
-REPLAY_COST = 1.0 / 160.0     # measured on the Cornell box: 9 ms to replay 896 samples, 1.62 ms to render one
+REPLAY_COST = 1.0 / 420.0     # measured on the Cornell box (round 2): 2.06 ms to replay 899 samples (k_film_replay), 0.97 ms to render one
 
 
 def _boundary(spp, k, n_ranks):

@@ -238,6 +238,7 @@ typedef struct cpbrt_stats {
     double   ms_trace_shadow;
     uint64_t rays_closest_traced;   /* closest-hit queries that needed a BVH traversal: MIS rays that miss their
                                        light's primitive and last-depth non-specular rays are answered without one */
+    uint64_t shade_items;           /* hits handed to the shading stage, all bounces and material kinds (terminal hits included) */
 } cpbrt_stats;
 
 /* ------------------------------------------------------------------------------------------

@@ -74,4 +74,4 @@ def test_sample_share_matches_library_rule(cpbrt):
             assert all(x + 1 >= y for x, y in zip(sizes, sizes[1:]))      # shrinking, up to rounding
             if spp >= 16 * world:
                 assert min(sizes) >= 1 and max(sizes) - min(sizes) <= 1 + spp // (10 * world)
-    assert part.sample_share(1024, 0, 8) == (0, 131) and part.sample_share(1024, 7, 8)[1] == 1024
+    assert part.sample_share(1024, 0, 8) == (0, 129) and part.sample_share(1024, 7, 8) == (897, 1024)
