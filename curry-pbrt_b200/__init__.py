@@ -213,6 +213,10 @@ class Renderer:
         """Levels of the last cpbrt_build_bvh that ran on the device (0: pure host build)."""
         return int(lib.cpbrt_bvh_gpu_levels(self._ctx))
 
+    def bvh_host_segments(self):
+        """Subtrees of the last device build finished by the host builder (0: whole build on the device; -1: host build)."""
+        return int(lib.cpbrt_bvh_host_segments(self._ctx))
+
     def h2d_bytes(self):
         """Bytes this context has copied host -> device so far (counted where the copies are issued)."""
         return int(lib.cpbrt_h2d_bytes(self._ctx))

@@ -108,7 +108,7 @@ class Stats(C.Structure):
                 ("ms_raygen_film", C.c_double), ("ms_reduce", C.c_double),
                 ("trace_parent_visits", C.c_uint64), ("trace_prim_tests", C.c_uint64),
                 ("trace_launches", C.c_uint64), ("ms_trace_closest", C.c_double), ("ms_trace_shadow", C.c_double),
-                ("rays_closest_traced", C.c_uint64), ("shade_items", C.c_uint64)]
+                ("rays_closest_traced", C.c_uint64), ("shade_items", C.c_uint64), ("trace_slow_paths", C.c_uint64)]
 
 
 # name -> (restype, argtypes); every symbol include/cpbrt.h declares
@@ -139,6 +139,7 @@ DEVICE_SYMBOLS = {
     "cpbrt_camera_rays": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_int]),
     "cpbrt_render": (C.c_int, [C.c_void_p, C.POINTER(RenderParams), C.c_void_p, C.POINTER(Stats)]),
     "cpbrt_bvh_gpu_levels": (C.c_int, [C.c_void_p]),
+    "cpbrt_bvh_host_segments": (C.c_int, [C.c_void_p]),
     "cpbrt_h2d_bytes": (C.c_uint64, [C.c_void_p]),
     "cpbrt_measure_read_bandwidth": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(C.c_double)]),
     "cpbrt_comm_unique_id": (C.c_int, [C.c_void_p]),

@@ -230,9 +230,21 @@ void finish_sah_bvh(TopPhase&& top, unsigned n_threads, BvhBuildResult* out) {
     b.arena.resize(2ull * n + top.nodes.size());
     // arena ids of the device-built Parents first, then the host subtrees
     const uint32_t n_top = (uint32_t)top.nodes.size();
-    b.n_nodes = n_top;
+    const uint32_t n_small = (uint32_t)top.small_nodes.size();
+    b.n_nodes = n_top + n_small;
     const uint32_t np = (uint32_t)top.pending.size();
     std::vector<uint32_t> pending_id(np, 0);
+    // subtrees the device already built: copied behind the top nodes, indices shifted
+    parallel_for(n_small, 1 << 16, [&](uint64_t lo, uint64_t hi) {
+        for (uint64_t i = lo; i < hi; ++i) {
+            const SmallSubtreeNode& sn = top.small_nodes[i];
+            BuildNode& nd = b.arena[n_top + i];
+            nd.leaf = (sn.leaf_axis & 1u) != 0; nd.axis = (uint8_t)(sn.leaf_axis >> 8);
+            nd.a = nd.leaf ? sn.a : n_top + sn.a; nd.b = nd.leaf ? sn.b : n_top + sn.b;
+            for (int k = 0; k < 3; ++k) { nd.bound.mn[k] = sn.mn[k]; nd.bound.mx[k] = sn.mx[k]; }
+        }
+    });
+    auto device_built = [&](uint32_t k) { return k < top.pending_root.size() && top.pending_root[k] != 0xFFFFFFFFu; };
     // many segments: one worker per thread pulls segments; few segments: let build() fork inside them
     const unsigned workers = std::max(1u, std::min<unsigned>(n_threads, np));
     b.spare_threads = (int)n_threads - (int)workers;
@@ -242,7 +254,8 @@ void finish_sah_bvh(TopPhase&& top, unsigned n_threads, BvhBuildResult* out) {
             const uint32_t k = next.fetch_add(1);
             if (k >= np) break;
             const PendingSegment& p = top.pending[k];
-            pending_id[k] = p.force_leaf ? b.make_leaf(p.start, p.end) : b.build(p.start, p.end);
+            if (device_built(k)) pending_id[k] = n_top + top.pending_root[k];
+            else pending_id[k] = p.force_leaf ? b.make_leaf(p.start, p.end) : b.build(p.start, p.end);
         }
     };
     {
@@ -263,6 +276,8 @@ void finish_sah_bvh(TopPhase&& top, unsigned n_threads, BvhBuildResult* out) {
         else b.arena[top.pending_parent[k]].b = pending_id[k];
     }
     out->root = root;
+    out->host_built_segments = 0;
+    for (uint32_t k = 0; k < np; ++k) if (!device_built(k) && !top.pending[k].force_leaf) ++out->host_built_segments;
     b.arena.resize(b.n_nodes.load());
     out->order.swap(b.order);
     out->arena.swap(b.arena);

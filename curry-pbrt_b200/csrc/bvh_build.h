@@ -28,6 +28,7 @@ struct BvhBuildResult {
     // the reference's numbering: nodes are pushed after their children (post-order), root last
     std::vector<uint32_t> post_order; // arena index of reference node k
     std::vector<uint32_t> ref_index;  // reference node number of arena node i
+    uint32_t host_built_segments = 0; // hybrid build: pending segments the HOST builder had to finish (0: the whole SAH build ran on the device)
 };
 
 // body(lo, hi) over [0, n) split across the host threads (chunks of at least min_chunk items)
@@ -51,7 +52,9 @@ struct TopNode {            // a Parent created by the device phase
     BuildBounds bound;
     int32_t child[2];       // TopNode index once known; pending segments attach through pending_parent / pending_side
 };
-struct PendingSegment { uint32_t start, end, force_leaf; };   // slot range the host still has to build (force_leaf: the SAH said "leaf")
+struct PendingSegment { uint32_t start, end, force_leaf; };   // slot range below the level-synchronous phase (force_leaf: the SAH said "leaf")
+// a node of a subtree the device built for a pending segment (bvh_build_gpu.cu, k_build_small)
+struct SmallSubtreeNode { uint32_t leaf_axis; uint32_t a, b; float mn[3], mx[3]; };   // bit 0 = leaf, bits 8.. = axis; Leaf: slot range, Parent: indices into small_nodes
 struct TopPhase {
     std::vector<BuildBounds> pb;          // bound of the primitive now in each slot
     std::vector<uint32_t> order;          // slot -> uploaded primitive index, as permuted by the device levels
@@ -61,6 +64,10 @@ struct TopPhase {
     std::vector<uint32_t> pending_side;
     int32_t root = 0x7FFFFFFF;            // TopNode index of the root (0x7FFFFFFF: the root is a pending segment)
     int levels = 0;
+    // pending segments already finished on the device: their subtrees' nodes, and per pending segment the index of
+    // its root in small_nodes (0xFFFFFFFF / beyond the end: not built there, the host builder does it)
+    std::vector<SmallSubtreeNode> small_nodes;
+    std::vector<uint32_t> pending_root;
 };
 // Builds every pending segment with the host builder (in parallel) and stitches the tree together.
 void finish_sah_bvh(TopPhase&& top, unsigned n_threads, BvhBuildResult* out);

@@ -24,6 +24,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -232,10 +233,299 @@ __global__ void k_segment_ids(const Segment* __restrict__ segs, uint32_t n_segs,
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Small segments: everything below `min_len` primitives, one block per segment, the whole subtree in
+// shared memory.  Same algorithm as the host builder's Builder::build (bvh_build.cpp) node by node:
+//     keys    (ordered centre bits << 32 | local index) per axis; ranks by counting (keys are unique, so the
+//             rank IS the stable sorted position -- ties fall back to the current order like the reference's
+//             stable sort_by_cached_key)
+//     sweep   one thread per axis: suffix areas from the back, then prefix box + cost from the front with the
+//             reference's f32 expression (bvh.rs:70-74)
+//     pick    one thread walks the 3 x (len - 1) costs in the reference's (axis, position) order: the first
+//             cost seeds the minimum (even a NaN), afterwards only a strictly smaller one replaces it
+//     split   gather boxes / order into the winning axis' order, push the right child, continue with the left
+// Nodes go to a block-private range of the global node array (reserved with one atomicAdd: at most 2 len - 1);
+// children are written as indices into that array.  A subtree's nodes are contiguous, which is also what the
+// traversal wants.  The segment's root index goes to seg_root[k].
+static constexpr int kSmallMax = 256;          // segment length the kernel handles (shared-memory arrays)
+static constexpr int kSmallThreads = 128;
+struct SmallNode { uint32_t leaf_axis; uint32_t a, b; float mn[3], mx[3]; };   // leaf_axis: bit 0 = leaf, bits 8.. = axis
+static_assert(sizeof(SmallNode) == 36, "layout");
+
+__global__ void __launch_bounds__(kSmallThreads) k_build_small(Box* __restrict__ pb_final, uint32_t* __restrict__ order_final,
+                                                               const PendingSegment* __restrict__ pending, uint32_t n_pending,
+                                                               SmallNode* __restrict__ nodes, uint32_t node_cap, uint32_t* __restrict__ n_nodes,
+                                                               uint32_t* __restrict__ seg_root, uint32_t* __restrict__ overflow) {
+    __shared__ Box box[kSmallMax], tmp_box[kSmallMax];
+    __shared__ uint32_t ord[kSmallMax], tmp_ord[kSmallMax];
+    __shared__ unsigned long long keys[kSmallMax];
+    __shared__ uint16_t idx[3][kSmallMax];
+    __shared__ float back_sa[3][kSmallMax], cost[3][kSmallMax];
+    __shared__ uint32_t stk_start[kSmallMax], stk_len[kSmallMax], stk_link[kSmallMax];   // link: node index << 1 | side, 0xFFFFFFFF = segment root
+    __shared__ uint32_t sh_base, sh_used, sh_sp, sh_decision[3];   // decision: leaf flag, axis, split
+    const int tid = threadIdx.x;
+    for (uint32_t k = blockIdx.x; k < n_pending; k += gridDim.x) {
+        const PendingSegment seg = pending[k];
+        const uint32_t len0 = seg.end - seg.start;
+        if (len0 > (uint32_t)kSmallMax || len0 == 0) { if (tid == 0) seg_root[k] = 0xFFFFFFFFu; continue; }   // left to the host builder
+        __syncthreads();
+        if (tid == 0) {
+            sh_base = atomicAdd(n_nodes, 2u * len0 - 1u);
+            sh_used = 0; sh_sp = 0;
+            if (sh_base + 2u * len0 - 1u > node_cap) { *overflow = 1u; sh_base = 0xFFFFFFFFu; }
+        }
+        for (uint32_t i = tid; i < len0; i += kSmallThreads) { box[i] = pb_final[seg.start + i]; ord[i] = order_final[seg.start + i]; }
+        __syncthreads();
+        if (sh_base == 0xFFFFFFFFu) { if (tid == 0) seg_root[k] = 0xFFFFFFFFu; continue; }
+        const uint32_t base = sh_base;
+        // explicit recursion: (start, len, link) items
+        uint32_t start = 0, len = len0, link = 0xFFFFFFFFu;
+        bool have = true;
+        while (have) {
+            // ---- node [start, start + len) -------------------------------------------------------
+            bool leaf = seg.force_leaf != 0u || len <= 1u;
+            uint32_t axis = 0, split = 0;
+            Box full = box[start];
+            if (!leaf) {
+                for (int a = 0; a < 3; ++a) {
+                    for (uint32_t i = tid; i < len; i += kSmallThreads) {
+                        const Box b = box[start + i];
+                        const float c = b.mn[a] + (b.mx[a] - b.mn[a]) / 2.f;   // bounds.rs:70-72
+                        keys[i] = ((unsigned long long)ordered_bits(c) << 32) | i;
+                    }
+                    __syncthreads();
+                    for (uint32_t i = tid; i < len; i += kSmallThreads) {
+                        const unsigned long long ki = keys[i];
+                        uint32_t rank = 0;
+                        for (uint32_t j = 0; j < len; ++j) rank += keys[j] < ki ? 1u : 0u;
+                        idx[a][rank] = (uint16_t)i;
+                    }
+                    __syncthreads();
+                }
+                if (tid < 3) {      // one axis each: suffix areas, then prefix boxes and costs (sweep_axis of bvh_build.cpp)
+                    const int a = tid;
+                    Box acc = box[start + idx[a][len - 1]];
+                    back_sa[a][len - 2] = surface_area(acc);
+                    for (uint32_t i = len - 2; i-- > 0;) { acc = Unite()(acc, box[start + idx[a][i + 1]]); back_sa[a][i] = surface_area(acc); }
+                    // the union of the whole node (same on every axis: min / max are exact) -- the host unites in slot order
+                    Box all = box[start];
+                    for (uint32_t i = 1; i < len; ++i) all = Unite()(all, box[start + i]);
+                    const float full_sa = surface_area(all);
+                    acc = box[start + idx[a][0]];
+                    for (uint32_t i = 0; i + 1 < len; ++i) {
+                        if (i) acc = Unite()(acc, box[start + idx[a][i]]);
+                        cost[a][i] = 0.125f + ((float)(i + 1) * surface_area(acc) + (float)(len - 1 - i) * back_sa[a][i]) / full_sa;   // bvh.rs:70-74
+                    }
+                }
+                __syncthreads();
+                if (tid == 0) {     // bvh.rs:77-92
+                    bool seeded = false; float min_cost = 0.f; uint32_t min_axis = 0, min_i = 0;
+                    for (uint32_t a = 0; a < 3; ++a)
+                        for (uint32_t i = 0; i + 1 < len; ++i) {
+                            const float c = cost[a][i];
+                            if (!seeded) { seeded = true; min_cost = c; min_axis = a; min_i = i; }
+                            else if (c < min_cost) { min_cost = c; min_axis = a; min_i = i; }
+                        }
+                    sh_decision[0] = (min_cost > (float)len) ? 1u : 0u; sh_decision[1] = min_axis; sh_decision[2] = min_i;
+                }
+                __syncthreads();
+                leaf = sh_decision[0] != 0u; axis = sh_decision[1]; split = sh_decision[2];
+                for (uint32_t i = 1; i < len; ++i) full = Unite()(full, box[start + i]);     // every thread: the Parent's bound
+            }
+            // ---- emit the node -------------------------------------------------------------------
+            __syncthreads();
+            const uint32_t id = sh_used;           // node index within the block's range
+            if (tid == 0) {
+                sh_used = id + 1;
+                SmallNode nd;
+                if (leaf) { nd.leaf_axis = 1u; nd.a = seg.start + start; nd.b = seg.start + start + len; for (int c = 0; c < 3; ++c) { nd.mn[c] = 0.f; nd.mx[c] = 0.f; } }
+                else { nd.leaf_axis = axis << 8; nd.a = 0xFFFFFFFFu; nd.b = 0xFFFFFFFFu; for (int c = 0; c < 3; ++c) { nd.mn[c] = full.mn[c]; nd.mx[c] = full.mx[c]; } }
+                nodes[base + id] = nd;
+                if (link == 0xFFFFFFFFu) seg_root[k] = base + id;
+                else if (link & 1u) nodes[base + (link >> 1)].b = base + id;
+                else nodes[base + (link >> 1)].a = base + id;
+            }
+            if (!leaf) {
+                // bvh.rs:100-112: slot j receives the primitive that was at local index idx[axis][j]
+                for (uint32_t j = tid; j < len; j += kSmallThreads) { const uint32_t src = start + idx[axis][j]; tmp_box[j] = box[src]; tmp_ord[j] = ord[src]; }
+                __syncthreads();
+                for (uint32_t j = tid; j < len; j += kSmallThreads) { box[start + j] = tmp_box[j]; ord[start + j] = tmp_ord[j]; }
+                if (tid == 0) {     // right child waits on the stack, the left one is next
+                    const uint32_t sp = sh_sp;
+                    stk_start[sp] = start + split + 1; stk_len[sp] = len - split - 1; stk_link[sp] = (id << 1) | 1u;
+                    sh_sp = sp + 1;
+                }
+                __syncthreads();
+                len = split + 1; link = id << 1;      // start unchanged
+            } else {
+                __syncthreads();
+                if (sh_sp == 0) have = false;
+                else {
+                    const uint32_t sp = sh_sp - 1;
+                    start = stk_start[sp]; len = stk_len[sp]; link = stk_link[sp];
+                    __syncthreads();
+                    if (tid == 0) sh_sp = sp;
+                }
+            }
+            __syncthreads();
+        }
+        for (uint32_t i = tid; i < len0; i += kSmallThreads) { order_final[seg.start + i] = ord[i]; pb_final[seg.start + i] = box[i]; }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Device-resident build (big scenes): bounds in, finished device layout out, nothing but the primitive order
+// and a handful of counters ever crosses PCIe.
+//
+// Primitive::bound() per uploaded primitive, the same f32 operations as primitive_bounds() in bvh_build.cpp
+// (triangle.rs:114-119, sphere.rs:22-27, TransformShape::bound transform.rs:52-54 with Bounds3f::apply
+// bounds.rs:292-300: the eight corners through the matrix, homogeneous divide when w != 0).
+struct DevXform { float m[16]; float m_inv[16]; int32_t outer; int32_t pad[3]; };      // == DevTransform of scene_dev.cuh
+__global__ void k_prim_bounds(const cpbrt_primitive* __restrict__ prims, uint32_t n, const cpbrt_triangle* __restrict__ tris,
+                              const float* __restrict__ radius, const DevXform* __restrict__ xf, Box* __restrict__ out, uint32_t* __restrict__ any_nan) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const cpbrt_shape sh = prims[i].shape;
+        Box b;
+        if (sh.kind == CPBRT_SHAPE_SPHERE) {
+            const float r = radius[sh.data];
+            for (int k = 0; k < 3; ++k) { b.mn[k] = dmin(-r, r); b.mx[k] = dmax(-r, r); }
+        } else {
+            const cpbrt_triangle& t = tris[sh.data];
+            for (int k = 0; k < 3; ++k) {
+                b.mn[k] = dmin(dmin(t.p[0][k], t.p[1][k]), t.p[2][k]);
+                b.mx[k] = dmax(dmax(t.p[0][k], t.p[1][k]), t.p[2][k]);
+            }
+        }
+        for (int32_t x = sh.xform; x >= 0; x = xf[x].outer) {
+            const float* m = xf[x].m;
+            Box r;
+            for (int c = 0; c < 8; ++c) {
+                const float p[3] = {(c & 1) ? b.mx[0] : b.mn[0], (c & 2) ? b.mx[1] : b.mn[1], (c & 4) ? b.mx[2] : b.mn[2]};
+                float h[4], q[3];
+                for (int j = 0; j < 4; ++j) h[j] = ((m[j * 4] * p[0] + m[j * 4 + 1] * p[1]) + m[j * 4 + 2] * p[2]) + m[j * 4 + 3] * 1.f;
+                if (h[3] != 0.f) { q[0] = h[0] / h[3]; q[1] = h[1] / h[3]; q[2] = h[2] / h[3]; } else { q[0] = h[0]; q[1] = h[1]; q[2] = h[2]; }
+                for (int k = 0; k < 3; ++k) {
+                    if (c == 0) { r.mn[k] = q[k]; r.mx[k] = q[k]; }
+                    else { r.mn[k] = dmin(r.mn[k], q[k]); r.mx[k] = dmax(r.mx[k], q[k]); }
+                }
+            }
+            b = r;
+        }
+        bool nan = false;
+        for (int k = 0; k < 3; ++k) nan = nan || b.mn[k] != b.mn[k] || b.mx[k] != b.mx[k];
+        if (nan) *any_nan = 1u;      // the order of unions would matter: host build only
+        out[i] = b;
+    }
+}
+__global__ void k_iota(uint32_t* __restrict__ v, uint32_t n) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) v[i] = i;
+}
+
+// Device layout (scene_dev.cuh): Parent records {L.min.xyz L.max.x}{L.max.yz R.min.xy}{R.min.z R.max.xyz}{lref rref lcnt|axis<<30 rcnt}.
+// Parent numbering: the level-synchronous ("top") Parents keep their ids 0 .. n_top-1, the Parents of the small
+// subtrees follow in the order of the small-node array (a subtree's nodes are contiguous there).
+// Child references while the tree is still in pieces: >= 0 a top node, <= -2 the small node -(c + 2).
+__global__ void k_small_parent_flags(const SmallNode* __restrict__ small, uint32_t n_small, uint32_t* __restrict__ flag) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_small; i += gridDim.x * blockDim.x) flag[i] = (small[i].leaf_axis & 1u) ? 0u : 1u;
+}
+__global__ void k_link_pending(const int32_t* __restrict__ pending_parent, const uint32_t* __restrict__ pending_side, const uint32_t* __restrict__ seg_root,
+                               uint32_t n_pending, TopNode* __restrict__ top) {
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n_pending; k += gridDim.x * blockDim.x)
+        if (pending_parent[k] >= 0) top[pending_parent[k]].child[pending_side[k]] = -(int32_t)seg_root[k] - 2;
+}
+struct ChildRec { float mn[3], mx[3]; uint32_t ref, cnt; };
+__device__ __forceinline__ ChildRec small_child(const SmallNode* __restrict__ small, const uint32_t* __restrict__ pidx, const Box* __restrict__ pb, uint32_t n_top, uint32_t s) {
+    const SmallNode sn = small[s];
+    ChildRec c;
+    if (sn.leaf_axis & 1u) {       // Leaf: union of its primitives' bounds (only the two-phase traversal looks at it)
+        Box u = pb[sn.a];
+        for (uint32_t sl = sn.a + 1; sl < sn.b; ++sl) u = Unite()(u, pb[sl]);
+        for (int k = 0; k < 3; ++k) { c.mn[k] = u.mn[k]; c.mx[k] = u.mx[k]; }
+        c.ref = sn.a; c.cnt = sn.b - sn.a;
+    } else {
+        for (int k = 0; k < 3; ++k) { c.mn[k] = sn.mn[k]; c.mx[k] = sn.mx[k]; }
+        c.ref = n_top + pidx[s]; c.cnt = 0;
+    }
+    return c;
+}
+__device__ __forceinline__ void write_parent(float4* __restrict__ out, uint32_t id, const ChildRec& l, const ChildRec& r, uint32_t axis) {
+    out[4ull * id] = make_float4(l.mn[0], l.mn[1], l.mn[2], l.mx[0]);
+    out[4ull * id + 1] = make_float4(l.mx[1], l.mx[2], r.mn[0], r.mn[1]);
+    out[4ull * id + 2] = make_float4(r.mn[2], r.mx[0], r.mx[1], r.mx[2]);
+    out[4ull * id + 3] = make_float4(__uint_as_float(l.ref), __uint_as_float(r.ref), __uint_as_float(l.cnt | (axis << 30)), __uint_as_float(r.cnt));
+}
+__global__ void k_layout_nodes(const TopNode* __restrict__ top, uint32_t n_top, const SmallNode* __restrict__ small, uint32_t n_small,
+                               const uint32_t* __restrict__ pidx, const Box* __restrict__ pb, float4* __restrict__ out) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_top + n_small; i += gridDim.x * blockDim.x) {
+        if (i < n_top) {
+            const TopNode t = top[i];
+            ChildRec c[2];
+            for (int k = 0; k < 2; ++k) {
+                if (t.child[k] >= 0) {
+                    const TopNode ch = top[t.child[k]];
+                    for (int j = 0; j < 3; ++j) { c[k].mn[j] = ch.bound.mn[j]; c[k].mx[j] = ch.bound.mx[j]; }
+                    c[k].ref = (uint32_t)t.child[k]; c[k].cnt = 0;
+                } else c[k] = small_child(small, pidx, pb, n_top, (uint32_t)(-(t.child[k] + 2)));
+            }
+            write_parent(out, i, c[0], c[1], t.axis);
+        } else {
+            const uint32_t s = i - n_top;
+            const SmallNode sn = small[s];
+            if (sn.leaf_axis & 1u) continue;
+            const ChildRec l = small_child(small, pidx, pb, n_top, sn.a), r = small_child(small, pidx, pb, n_top, sn.b);
+            write_parent(out, n_top + pidx[s], l, r, sn.leaf_axis >> 8);
+        }
+    }
+}
+
+// Primitive records, shading frames and uv triples in BVH order (scene_dev.cuh; the host versions are in
+// cpbrt_api.cu: host_tri_frame etc. -- same f32 operations, IEEE division and square root on both sides).
+__global__ void k_prim_records(const cpbrt_primitive* __restrict__ prims, const cpbrt_triangle* __restrict__ tris, const float* __restrict__ radius,
+                               const uint32_t* __restrict__ order, uint32_t n, int any_uv, float4* __restrict__ rec, float4* __restrict__ frames,
+                               float* __restrict__ uvs) {
+    for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += gridDim.x * blockDim.x) {
+        const uint32_t up = order[slot];
+        const cpbrt_primitive p = prims[up];
+        uint32_t meta = ((uint32_t)(p.shape.xform + 1)) << 2;
+        float4 q0 = make_float4(0, 0, 0, 0), q1 = q0, q2 = q0, f0 = q0, f1 = q0, f2 = q0;
+        if (p.shape.kind == CPBRT_SHAPE_SPHERE) { meta |= 1u; q0.x = radius[p.shape.data]; }
+        else {
+            const cpbrt_triangle t = tris[p.shape.data];
+            q0 = make_float4(t.p[0][0], t.p[0][1], t.p[0][2], t.p[1][0]);
+            q1 = make_float4(t.p[1][1], t.p[1][2], t.p[2][0], t.p[2][1]);
+            q2.x = t.p[2][2];
+            if (any_uv) { meta |= 2u; for (int k = 0; k < 6; ++k) uvs[6ull * slot + k] = (&t.uv[0][0])[k]; }
+            // Triangle::normal (triangle.rs:78-82) and the frame BSDF::new derives from it (bxdf/mod.rs:83-97)
+            const float a[3] = {t.p[0][0] - t.p[2][0], t.p[0][1] - t.p[2][1], t.p[0][2] - t.p[2][2]};
+            const float b[3] = {t.p[1][0] - t.p[2][0], t.p[1][1] - t.p[2][1], t.p[1][2] - t.p[2][2]};
+            float c[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+            for (int pass = 0; pass < 2; ++pass) {
+                const float len = sqrtf((c[0] * c[0] + c[1] * c[1]) + c[2] * c[2]);
+                c[0] = c[0] / len; c[1] = c[1] / len; c[2] = c[2] / len;
+            }
+            float x[3], y[3];
+            if (fabsf(c[0]) > fabsf(c[1])) { const float l = sqrtf(c[0] * c[0] + c[2] * c[2]); x[0] = -c[2] / l; x[1] = 0.f / l; x[2] = c[0] / l; }
+            else { const float l = sqrtf(c[1] * c[1] + c[2] * c[2]); x[0] = 0.f / l; x[1] = c[2] / l; x[2] = -c[1] / l; }
+            y[0] = c[1] * x[2] - c[2] * x[1]; y[1] = c[2] * x[0] - c[0] * x[2]; y[2] = c[0] * x[1] - c[1] * x[0];
+            float nl[3] = {(c[0] * x[0] + c[1] * x[1]) + c[2] * x[2], (c[0] * y[0] + c[1] * y[1]) + c[2] * y[2], (c[0] * c[0] + c[1] * c[1]) + c[2] * c[2]};
+            const float len = sqrtf((nl[0] * nl[0] + nl[1] * nl[1]) + nl[2] * nl[2]);
+            nl[0] = nl[0] / len; nl[1] = nl[1] / len; nl[2] = nl[2] / len;
+            f0 = make_float4(c[0], c[1], c[2], x[0]); f1 = make_float4(x[1], x[2], y[0], y[1]); f2 = make_float4(y[2], nl[0], nl[1], nl[2]);
+        }
+        q2.y = __uint_as_float(up); q2.z = __uint_as_float(meta);
+        q2.w = __uint_as_float(p.material >= 0 ? (uint32_t)p.material : (0x80000000u | (uint32_t)p.light));
+        rec[3ull * slot] = q0; rec[3ull * slot + 1] = q1; rec[3ull * slot + 2] = q2;
+        frames[3ull * slot] = f0; frames[3ull * slot + 1] = f1; frames[3ull * slot + 2] = f2;
+    }
+}
+
 struct DevMem {
     std::vector<void*> all;
     ~DevMem() { for (void* p : all) cudaFree(p); }
     template <class T> T* get(size_t n) { void* p = nullptr; if (cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)) != cudaSuccess) return nullptr; all.push_back(p); return (T*)p; }
+    void* detach(void* p) { for (auto& q : all) if (q == p) { q = nullptr; return p; } return p; }      // ownership goes to the caller (cudaFree(nullptr) is a no-op)
 };
 
 #define CK(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { *err = std::string(#x) + ": " + cudaGetErrorString(e__); return false; } } while (0)
@@ -251,6 +541,10 @@ bool gpu_sah_top_phase(const std::vector<BuildBounds>& bounds, uint32_t min_len,
     for (const BuildBounds& b : bounds)
         for (int k = 0; k < 3; ++k) if (b.mn[k] != b.mn[k] || b.mx[k] != b.mx[k]) { *err = "NaN bounds: the order of unions matters, host build only"; return false; }
 
+    const bool timing = getenv("CPBRT_TIMING") != nullptr;
+    auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_mark = now();
+    auto lap = [&](const char* what) { if (timing) { cudaStreamSynchronize(stream); const double t = now(); fprintf(stderr, "[gpu_sah] %-28s %.3f s\n", what, t - t_mark); t_mark = t; } };
     DevMem M;
     const uint32_t max_segs = n / min_len + 2;
     const uint32_t node_cap = 2 * max_segs * (uint32_t)std::max(1, max_levels) + 16, pending_cap = node_cap + 16;
@@ -266,7 +560,7 @@ bool gpu_sah_top_phase(const std::vector<BuildBounds>& bounds, uint32_t min_len,
     TopNode* nodes = M.get<TopNode>(node_cap);
     PendingSegment* pending = M.get<PendingSegment>(pending_cap);
     int32_t* pending_parent = M.get<int32_t>(pending_cap); uint32_t* pending_side = M.get<uint32_t>(pending_cap);
-    uint32_t* counters = M.get<uint32_t>(8);   // [0] nodes, [1] pending, [2] overflow, [3] root_ref (as int)
+    uint32_t* counters = M.get<uint32_t>(8);   // [0] nodes, [1] pending, [2] overflow, [3] root_ref (as int), [4] small nodes, [5] small overflow
     if (!pb || !pb_new || !pb_alt || !fwd || !rev || !prefix || !suffix_rev || !prefix0 || !pb_final || !order || !order_new || !order_alt || !order_final || !seg ||
         !seg_rev || !vals || !keep || !keep_off || !idx[0] || !idx[1] || !idx[2] || !keys || !keys_out || !best || !segs || !segs_next || !dec || !first_nan ||
         !child_count || !child_off || !nodes || !pending || !pending_parent || !pending_side || !counters) { *err = "device memory for the BVH build"; return false; }
@@ -293,6 +587,7 @@ bool gpu_sah_top_phase(const std::vector<BuildBounds>& bounds, uint32_t min_len,
         Segment root; root.slot0 = 0; root.rank0 = 0; root.len = n; root.parent = -1; root.side = 0;
         CK(cudaMemcpyAsync(segs, &root, sizeof root, cudaMemcpyHostToDevice, stream));
     }
+    lap("allocations + upload");
     uint32_t m = n, n_segs = 1;
     const int T = 256;
     auto grid = [&](uint32_t items) { return (int)std::min<uint32_t>((items + T - 1) / T, 148u * 16u); };
@@ -335,6 +630,7 @@ bool gpu_sah_top_phase(const std::vector<BuildBounds>& bounds, uint32_t min_len,
         std::swap(pb, pb_alt); std::swap(order, order_alt); std::swap(segs, segs_next);
         m = m_next; n_segs = s_next;
     }
+    lap("level-synchronous phase");
     // segments still active when the level budget ran out go to the host as they are
     std::vector<Segment> left(n_segs);
     if (n_segs) {
@@ -355,8 +651,33 @@ bool gpu_sah_top_phase(const std::vector<BuildBounds>& bounds, uint32_t min_len,
     CK(cudaMemcpyAsync(h_counters, counters, 16, cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
     const uint32_t nn = h_counters[0], np = h_counters[1];
-    out->pb.resize(n); out->order.resize(n); out->nodes.resize(nn); out->pending.resize(np); out->pending_parent.resize(np); out->pending_side.resize(np);
-    CK(cudaMemcpyAsync(out->pb.data(), pb_final, (size_t)n * sizeof(Box), cudaMemcpyDeviceToHost, stream));
+    // ---- small phase: every pending segment of up to kSmallMax primitives, one block each ---------------------
+    out->small_nodes.clear(); out->pending_root.clear();
+    bool host_work = !left.empty();
+    {
+        const char* e = getenv("CPBRT_BVH_SMALL");
+        if ((!e || atoi(e) != 0) && np > 0) {
+            const uint32_t small_cap = 2u * n;
+            SmallNode* small = M.get<SmallNode>(small_cap);
+            uint32_t* seg_root = M.get<uint32_t>(np);
+            if (!small || !seg_root) { *err = "device memory for the BVH build"; return false; }
+            CK(cudaMemsetAsync(counters + 4, 0, 8, stream));      // [4] small nodes used, [5] overflow
+            k_build_small<<<(int)std::min<uint32_t>(np, 148u * 32u), kSmallThreads, 0, stream>>>(pb_final, order_final, pending, np, small, small_cap, counters + 4, seg_root, counters + 5);
+            uint32_t used[2];
+            CK(cudaMemcpyAsync(used, counters + 4, 8, cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
+            lap("small-segment kernel");
+            if (used[1]) { *err = "BVH small-phase node table overflowed"; return false; }
+            out->small_nodes.resize(used[0]); out->pending_root.resize(np);
+            static_assert(sizeof(SmallNode) == sizeof(SmallSubtreeNode), "layout");
+            if (used[0]) CK(cudaMemcpyAsync(out->small_nodes.data(), small, (size_t)used[0] * sizeof(SmallNode), cudaMemcpyDeviceToHost, stream));
+            CK(cudaMemcpyAsync(out->pending_root.data(), seg_root, (size_t)np * 4, cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
+            for (uint32_t k = 0; k < np && !host_work; ++k) host_work = out->pending_root[k] == 0xFFFFFFFFu;
+        } else host_work = true;
+    }
+    out->pb.resize(host_work ? n : 0); out->order.resize(n); out->nodes.resize(nn); out->pending.resize(np); out->pending_parent.resize(np); out->pending_side.resize(np);
+    if (host_work) CK(cudaMemcpyAsync(out->pb.data(), pb_final, (size_t)n * sizeof(Box), cudaMemcpyDeviceToHost, stream));
     CK(cudaMemcpyAsync(out->order.data(), order_final, (size_t)n * 4, cudaMemcpyDeviceToHost, stream));
     if (nn) CK(cudaMemcpyAsync(out->nodes.data(), nodes, (size_t)nn * sizeof(TopNode), cudaMemcpyDeviceToHost, stream));
     if (np) {
@@ -371,6 +692,7 @@ bool gpu_sah_top_phase(const std::vector<BuildBounds>& bounds, uint32_t min_len,
         out->pending.push_back(p); out->pending_parent.push_back(sg.parent); out->pending_side.push_back(sg.side);
     }
     out->levels = level;
+    lap("downloads");
     return true;
 }
 

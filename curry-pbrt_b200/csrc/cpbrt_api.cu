@@ -99,7 +99,8 @@ struct cpbrt_ctx {
         cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
         cudaEvent_t raygen_done = nullptr, film_done = nullptr; // order of the per-pixel state across lanes
     };
-    static constexpr int kMaxLanes = 2;
+    static constexpr int kMaxLanes = 3;
+    static constexpr int kDefaultLanes = 2;
     WaveLane lanes[kMaxLanes];
     DevBuf d_pixels;
     PixelArrays PX;
@@ -550,9 +551,13 @@ static int exchange_bvh(cpbrt_ctx* ctx, uint32_t n, int local_rc, bool any_uv, c
     if (!rc) rc = bcast(ctx, d_order.p, (size_t)n * 4);
     if (!rc) {
         cudaError_t e = cudaSuccess;
-        if (!root && prim_order_out && n) e = cudaMemcpyAsync(prim_order_out, d_order.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        std::vector<uint32_t> order_rx;
+        if (!root && n) { order_rx.resize(n); e = cudaMemcpyAsync(order_rx.data(), d_order.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream); }
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) rc = ctx->fail(CPBRT_ERR_CUDA, "bvh exchange: %s", cudaGetErrorString(e));
+        if (!rc && !root && n) {
+            if (prim_order_out) memcpy(prim_order_out, order_rx.data(), (size_t)n * 4);
+        }
     }
     cleanup();
     if (!rc && !root) {
@@ -829,6 +834,9 @@ static int ensure_totals(cpbrt_ctx* ctx) {
     return 0;
 }
 
+static cudaError_t slow_paths_reset(cudaStream_t st) { const unsigned long long z = 0; return cudaMemcpyToSymbolAsync(g_trace_slow_paths, &z, sizeof z, 0, cudaMemcpyHostToDevice, st); }
+static cudaError_t slow_paths_read(unsigned long long* out, cudaStream_t st) { return cudaMemcpyFromSymbolAsync(out, g_trace_slow_paths, sizeof *out, 0, cudaMemcpyDeviceToHost, st); }
+
 static int check_overflow(cpbrt_ctx* ctx, const Totals& t) {
     if (t.overflow) return ctx->fail(CPBRT_ERR_UNSUPPORTED, "BVH deeper than the %d-entry traversal stack", kStackSize);
     if (t.bsdf_overflow) return ctx->fail(CPBRT_ERR_UNSUPPORTED, "a material expands to more than %d lobes of one kind", kMaxLobes);
@@ -855,6 +863,7 @@ int cpbrt_trace_closest(cpbrt_ctx* ctx, const cpbrt_ray* rays, uint64_t n, cpbrt
         d_rays = (const float4*)br.p; d_hits = (float4*)bh.p;
     }
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    slow_paths_reset(ctx->stream);
     cudaEventRecord(e0, ctx->stream);
     if (n) {
         const int sched = trace_schedule(ctx);
@@ -868,7 +877,8 @@ int cpbrt_trace_closest(cpbrt_ctx* ctx, const cpbrt_ray* rays, uint64_t n, cpbrt
     cudaEventRecord(e1, ctx->stream);
     cudaError_t err = cudaGetLastError();
     if (err == cudaSuccess && !on_device && n) err = cudaMemcpyAsync(hits_out, d_hits, n * sizeof(cpbrt_hit), cudaMemcpyDeviceToHost, ctx->stream);
-    Totals t; unsigned long long c[2] = {0, 0};
+    Totals t; unsigned long long c[2] = {0, 0}, slow = 0;
+    if (err == cudaSuccess) err = slow_paths_read(&slow, ctx->stream);
     if (err == cudaSuccess) err = cudaMemcpyAsync(&t, ctx->d_totals, sizeof t, cudaMemcpyDeviceToHost, ctx->stream);
     if (err == cudaSuccess) err = cudaMemcpyAsync(c, counters, sizeof c, cudaMemcpyDeviceToHost, ctx->stream);
     if (err == cudaSuccess) err = cudaStreamSynchronize(ctx->stream);
@@ -876,7 +886,7 @@ int cpbrt_trace_closest(cpbrt_ctx* ctx, const cpbrt_ray* rays, uint64_t n, cpbrt
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     br.release(); bh.release();
     if (err != cudaSuccess) return ctx->fail(CPBRT_ERR_CUDA, "trace_closest: %s", cudaGetErrorString(err));
-    if (stats) { memset(stats, 0, sizeof *stats); stats->rays_closest = n; stats->kernel_launches = n ? 1 : 0; stats->ms_total = ms; stats->ms_trace = ms; stats->trace_parent_visits = c[0]; stats->trace_prim_tests = c[1]; }
+    if (stats) { memset(stats, 0, sizeof *stats); stats->rays_closest = n; stats->kernel_launches = n ? 1 : 0; stats->ms_total = ms; stats->ms_trace = ms; stats->trace_parent_visits = c[0]; stats->trace_prim_tests = c[1]; stats->trace_slow_paths = slow; }
     return check_overflow(ctx, t);
 }
 
@@ -899,6 +909,7 @@ int cpbrt_trace_any(cpbrt_ctx* ctx, const cpbrt_ray* rays, uint64_t n, uint8_t* 
         d_rays = (const float4*)br.p; d_out = (uint8_t*)bo.p;
     }
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    slow_paths_reset(ctx->stream);
     cudaEventRecord(e0, ctx->stream);
     if (n) {
         const int sched = trace_schedule(ctx);
@@ -912,7 +923,8 @@ int cpbrt_trace_any(cpbrt_ctx* ctx, const cpbrt_ray* rays, uint64_t n, uint8_t* 
     cudaEventRecord(e1, ctx->stream);
     cudaError_t err = cudaGetLastError();
     if (err == cudaSuccess && !on_device && n) err = cudaMemcpyAsync(out, d_out, n, cudaMemcpyDeviceToHost, ctx->stream);
-    Totals t; unsigned long long c[2] = {0, 0};
+    Totals t; unsigned long long c[2] = {0, 0}, slow = 0;
+    if (err == cudaSuccess) err = slow_paths_read(&slow, ctx->stream);
     if (err == cudaSuccess) err = cudaMemcpyAsync(&t, ctx->d_totals, sizeof t, cudaMemcpyDeviceToHost, ctx->stream);
     if (err == cudaSuccess) err = cudaMemcpyAsync(c, counters, sizeof c, cudaMemcpyDeviceToHost, ctx->stream);
     if (err == cudaSuccess) err = cudaStreamSynchronize(ctx->stream);
@@ -920,7 +932,7 @@ int cpbrt_trace_any(cpbrt_ctx* ctx, const cpbrt_ray* rays, uint64_t n, uint8_t* 
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     br.release(); bo.release();
     if (err != cudaSuccess) return ctx->fail(CPBRT_ERR_CUDA, "trace_any: %s", cudaGetErrorString(err));
-    if (stats) { memset(stats, 0, sizeof *stats); stats->rays_any = n; stats->kernel_launches = n ? 1 : 0; stats->ms_total = ms; stats->ms_trace = ms; stats->trace_parent_visits = c[0]; stats->trace_prim_tests = c[1]; }
+    if (stats) { memset(stats, 0, sizeof *stats); stats->rays_any = n; stats->kernel_launches = n ? 1 : 0; stats->ms_total = ms; stats->ms_trace = ms; stats->trace_parent_visits = c[0]; stats->trace_prim_tests = c[1]; stats->trace_slow_paths = slow; }
     return check_overflow(ctx, t);
 }
 
@@ -1050,13 +1062,15 @@ int cpbrt_render(cpbrt_ctx* ctx, const cpbrt_render_params* params, float* film_
     // across lanes with events, everything else is private to a lane.  profile_stages, the recursive direct-lighting
     // kernel and single-pass renders use one lane on the control stream.  CPBRT_LANES=1|2 overrides.
     const uint32_t n_passes = (s_end - s_begin + spass - 1) / spass;
-    int n_lanes = (rp.profile_stages || (ctx->recursive_direct && !rp.first_hit_only) || n_passes < 2) ? 1 : cpbrt_ctx::kMaxLanes;
-    if (const char* e = getenv("CPBRT_LANES")) n_lanes = std::max(1, std::min(n_lanes, atoi(e)));
+    int n_lanes = (rp.profile_stages || (ctx->recursive_direct && !rp.first_hit_only) || n_passes < 2) ? 1 : cpbrt_ctx::kDefaultLanes;
+    if (const char* e = getenv("CPBRT_LANES")) { if (n_lanes > 1) n_lanes = std::max(1, std::min((int)cpbrt_ctx::kMaxLanes, atoi(e))); }
+    n_lanes = (int)std::min<uint32_t>((uint32_t)n_lanes, n_passes);
     if (int rc = ensure_wavefront(ctx, spass * npix, n_lanes)) return rc;
     const PixelArrays PX = ctx->PX;
     Totals* T = ctx->d_totals;
     cudaStream_t st = ctx->stream;
     CU(cudaMemsetAsync(T, 0, sizeof(Totals), st));
+    CU(slow_paths_reset(st));
     for (int li = 0; li < n_lanes; ++li) CU(cudaMemsetAsync(ctx->lanes[li].Q.counts, 0, 64 * 4, st));
 
     // every event of this call lives in one bag that destroys them on ANY way out (error returns included)
@@ -1077,7 +1091,13 @@ int cpbrt_render(cpbrt_ctx* ctx, const cpbrt_render_params* params, float* film_
     const int sched = trace_schedule(ctx);
     const bool vote = sched == SCHED_VOTE, flat = sched == SCHED_FLAT;
     const size_t flat_sm = flat ? flat_bytes(ctx) : 0;
-    const int g_closest = grid_for(ctx, flat ? CPBRT_BLOCKS_FLAT : (vote ? CPBRT_BLOCKS_CLOSEST_VOTE : CPBRT_BLOCKS_CLOSEST_LOOP)), g_shadow = grid_for(ctx, flat ? CPBRT_BLOCKS_FLAT : (vote ? CPBRT_BLOCKS_SHADOW_VOTE : CPBRT_BLOCKS_SHADOW_LOOP)), g_shade = grid_for(ctx, 8), g_pix = grid_for(ctx, 4);
+    // blocks per SM of the long kernels: what their launch bounds allow by default; CPBRT_GRID_TRACE / CPBRT_GRID_MATTE
+    // shrink the grids (tuning: how two lanes share an SM, tools/variant_sweep.py)
+    auto env_blocks = [](const char* name, int dflt) { const char* e = getenv(name); const int v = e ? atoi(e) : 0; return v > 0 ? std::min(v, dflt) : dflt; };
+    const int b_closest = env_blocks("CPBRT_GRID_TRACE", flat ? CPBRT_BLOCKS_FLAT : (vote ? CPBRT_BLOCKS_CLOSEST_VOTE : CPBRT_BLOCKS_CLOSEST_LOOP));
+    const int b_shadow = env_blocks("CPBRT_GRID_TRACE", flat ? CPBRT_BLOCKS_FLAT : (vote ? CPBRT_BLOCKS_SHADOW_VOTE : CPBRT_BLOCKS_SHADOW_LOOP));
+    const int b_matte = env_blocks("CPBRT_GRID_MATTE", ShadeBlocks<SHADE_MATTE>::value);
+    const int g_closest = grid_for(ctx, b_closest), g_shadow = grid_for(ctx, b_shadow), g_shade = grid_for(ctx, 8), g_pix = grid_for(ctx, 4), g_matte = grid_for(ctx, b_matte);
     // one thread per pixel where possible: each walks a dependent chain of radical inverses (all of a
     // rank's skipped samples on the first pass), which only many resident warps can hide
     const int g_raygen = (int)std::min<uint64_t>(((uint64_t)npix + 127) / 128, (uint64_t)ctx->sm_count * 16);
@@ -1146,7 +1166,7 @@ int cpbrt_render(cpbrt_ctx* ctx, const cpbrt_render_params* params, float* film_
             k_shade<SHADE_GLASS><<<g_shade, 128, 0, sb>>>(S, P, Q, next, T); ++launches;
             if (ctx->has_general_materials) { k_shade<SHADE_GENERAL><<<grid_for(ctx, ShadeBlocks<SHADE_GENERAL>::value), 128, 0, sb>>>(S, P, Q, next, T); ++launches; }
             if (!prof) { cudaEventRecord(eS, sb); cudaStreamWaitEvent(sm, eK3, 0); }
-            k_shade<SHADE_MATTE><<<grid_for(ctx, ShadeBlocks<SHADE_MATTE>::value), 128, 0, sm>>>(S, P, Q, next, T); ++launches;
+            k_shade<SHADE_MATTE><<<g_matte, 128, 0, sm>>>(S, P, Q, next, T); ++launches;
             span_end();
             if (!prof) cudaStreamWaitEvent(sm, eS, 0);
             k_queue_reset<<<1, 32, 0, sm>>>(Q, cur, 1, T); ++launches;
@@ -1193,7 +1213,9 @@ int cpbrt_render(cpbrt_ctx* ctx, const cpbrt_render_params* params, float* film_
     }
     cudaEventRecord(e2, st);
     Totals t; memset(&t, 0, sizeof t);
+    unsigned long long slow = 0;
     err = cudaGetLastError();
+    if (err == cudaSuccess) err = slow_paths_read(&slow, st);
     if (err == cudaSuccess) err = cudaMemcpyAsync(&t, T, sizeof t, cudaMemcpyDeviceToHost, st);
     if (err == cudaSuccess && root && !rp.film_on_device) err = cudaMemcpyAsync(film_out, d_out, out_bytes, cudaMemcpyDeviceToHost, st);
     if (err == cudaSuccess) err = cudaStreamSynchronize(st);
@@ -1210,7 +1232,7 @@ int cpbrt_render(cpbrt_ctx* ctx, const cpbrt_render_params* params, float* film_
         memset(stats, 0, sizeof *stats);
         stats->camera_samples = (uint64_t)npix * (s_end - s_begin);
         stats->rays_closest = t.rays_closest + t.elided_closest; stats->rays_closest_traced = t.rays_closest; stats->rays_any = t.rays_any; stats->nan_dropped = t.nan_dropped;
-        stats->kernel_launches = launches; stats->ms_total = ms_render + ms_film; stats->shade_items = t.shade_items;
+        stats->kernel_launches = launches; stats->ms_total = ms_render + ms_film; stats->shade_items = t.shade_items; stats->trace_slow_paths = slow;
         stats->ms_reduce = ctx->comm ? ms_film : 0.0; stats->ms_raygen_film = ms_film;
         if (prof) {
             stats->ms_raygen_film = ms_stage[0] + ms_film; stats->ms_trace_closest = ms_stage[1]; stats->ms_trace_shadow = ms_stage[2];
@@ -1221,6 +1243,7 @@ int cpbrt_render(cpbrt_ctx* ctx, const cpbrt_render_params* params, float* film_
 }
 
 int cpbrt_bvh_gpu_levels(const cpbrt_ctx* ctx) { return ctx ? ctx->bvh_gpu_levels : 0; }
+int cpbrt_bvh_host_segments(const cpbrt_ctx* ctx) { return (ctx && ctx->bvh_gpu_levels > 0) ? (int)ctx->bvh.host_built_segments : -1; }
 
 uint64_t cpbrt_h2d_bytes(const cpbrt_ctx* ctx) { return ctx ? ctx->h2d_bytes : 0; }
 

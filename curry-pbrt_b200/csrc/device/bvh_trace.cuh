@@ -57,6 +57,9 @@ static constexpr uint32_t kLeafBit = 0x80000000u;
 static constexpr uint32_t kDone = 0xFFFFFFFFu;      // "no more work": has the leaf bit set on purpose
 
 struct TraceStats { uint32_t parent_visits, prim_tests; };
+// rays that the fast search could not settle by itself: replays in the reference's own order (a rival within the margin),
+// and in the flat search the hand-overs to the reference traversal
+__device__ unsigned long long g_trace_slow_paths;
 
 // Work items of the traversal ("tasks"), packed in a uint2:
 //   Parent task  x = node index,             y = bits(t_min of that node's own box test)
@@ -510,7 +513,7 @@ __device__ void closest_persistent_loop(const DevScene& sc, uint32_t n_items, ui
             if (task.x == kDone) {
                 if (mode == MODE_SEARCH && best != 0xFFFFFFFFu && !(t_second > t_cut)) {
                     // a rival within the margin: let the reference's own order decide
-                    mode = MODE_REPLAY;
+                    mode = MODE_REPLAY; atomicAdd(&g_trace_slow_paths, 1ull);
                     t_lo = t_best - hit_margin(t_best, abs_m);
                     ray.t_max = fminf(t_init, t_cut);
                     best = 0xFFFFFFFFu; stack.n = 0;
@@ -652,7 +655,7 @@ __device__ void closest_persistent(const DevScene& sc, uint32_t n_items, uint32_
     for (;;) {
         // ---- a ray whose search ended with a rival inside the margin starts its replay ----------
         if (have_ray && task.x == kDone && mode == MODE_SEARCH && best != 0xFFFFFFFFu && !(t_second > t_cut)) {
-            mode = MODE_REPLAY;
+            mode = MODE_REPLAY; atomicAdd(&g_trace_slow_paths, 1ull);
             t_lo = t_best - hit_margin(t_best, abs_m);
             ray.t_max = fminf(t_init, t_cut);      // t_cut stays t_best + margin: upper edge of the replay window
             best = 0xFFFFFFFFu; stack.n = 0;

@@ -179,7 +179,7 @@ CP_DEV uint32_t flat_closest(const DevScene& sc, const Ray& ray, bool active, fl
     bool slow = active && !ordinary;
     if (fast && best != 0xFFFFFFFFu) slow = !(t_second > t_cut) || !flat_reachable(sc, bs, best, t_best);
     float t = best != 0xFFFFFFFFu ? t_best : t_init;
-    if (slow) best = bvh_closest<false>(sc, ray, &t, nullptr, overflow);      // the reference's own order decides
+    if (slow) { best = bvh_closest<false>(sc, ray, &t, nullptr, overflow); atomicAdd(&g_trace_slow_paths, 1ull); }      // the reference's own order decides
     *t_hit = t;
     return best;
 }
@@ -211,7 +211,7 @@ CP_DEV bool flat_any(const DevScene& sc, const Ray& ray, bool active, uint32_t* 
             if (flat_reachable(sc, bs, s, ray.t_max)) { hit = true; cs = 0; } else unsure = true;
         }
     }
-    if (!hit && unsure) hit = bvh_any<false>(sc, ray, nullptr, overflow);
+    if (!hit && unsure) { hit = bvh_any<false>(sc, ray, nullptr, overflow); atomicAdd(&g_trace_slow_paths, 1ull); }
     return hit;
 }
 

@@ -239,6 +239,8 @@ typedef struct cpbrt_stats {
     uint64_t rays_closest_traced;   /* closest-hit queries that needed a BVH traversal: MIS rays that miss their
                                        light's primitive and last-depth non-specular rays are answered without one */
     uint64_t shade_items;           /* hits handed to the shading stage, all bounces and material kinds (terminal hits included) */
+    uint64_t trace_slow_paths;      /* rays the fast search could not settle by itself and handed to the reference-order traversal
+                                       (a hit whose reachability could not be proven, zero / non-finite direction components) */
 } cpbrt_stats;
 
 /* ------------------------------------------------------------------------------------------
@@ -289,10 +291,14 @@ int cpbrt_camera_rays(cpbrt_ctx* ctx, uint32_t sample, cpbrt_ray* rays_out, int 
 int cpbrt_render(cpbrt_ctx* ctx, const cpbrt_render_params* params, float* film_rgb_out,
                  cpbrt_stats* stats_out);
 
-/* How many levels of the last cpbrt_build_bvh ran on the device (0 = the exact SAH build ran on the host only).
- * Scenes of >= 131072 primitives build the top of the tree (segments of >= 256 primitives) on the GPU and
- * finish the small subtrees on the host threads; the result is identical either way (bvh.rs:24-124). */
+/* How many levels of the last cpbrt_build_bvh ran level-synchronously on the device (0 = the exact SAH build ran on
+ * the host only).  Scenes of >= 131072 primitives build the top of the tree (segments of >= 256 primitives) level by
+ * level on the GPU and every smaller subtree in one thread block each; the result is identical to the host build
+ * (bvh.rs:24-124). */
 int cpbrt_bvh_gpu_levels(const cpbrt_ctx* ctx);
+/* Subtrees of the last device build that the HOST builder had to finish (segments longer than one block handles, or
+ * CPBRT_BVH_SMALL=0): 0 = the whole SAH build ran on the device; -1 = the last build was a pure host build. */
+int cpbrt_bvh_host_segments(const cpbrt_ctx* ctx);
 
 /* Bytes this context has copied host -> device since cpbrt_create (counted where the copies are issued):
  * scene arrays, sampler tables, BVH layout, ray batches.  Bookkeeping for the end-to-end measurement. */

@@ -49,7 +49,7 @@ static void layout(void) {
     SIZE(cpbrt_stats); FIELD(cpbrt_stats, camera_samples); FIELD(cpbrt_stats, rays_closest); FIELD(cpbrt_stats, rays_any); FIELD(cpbrt_stats, nan_dropped);
     FIELD(cpbrt_stats, kernel_launches); FIELD(cpbrt_stats, ms_total); FIELD(cpbrt_stats, ms_trace); FIELD(cpbrt_stats, ms_shade);
     FIELD(cpbrt_stats, ms_raygen_film); FIELD(cpbrt_stats, ms_reduce); FIELD(cpbrt_stats, trace_parent_visits); FIELD(cpbrt_stats, trace_prim_tests);
-    FIELD(cpbrt_stats, trace_launches); FIELD(cpbrt_stats, ms_trace_closest); FIELD(cpbrt_stats, ms_trace_shadow); FIELD(cpbrt_stats, rays_closest_traced); FIELD(cpbrt_stats, shade_items);
+    FIELD(cpbrt_stats, trace_launches); FIELD(cpbrt_stats, ms_trace_closest); FIELD(cpbrt_stats, ms_trace_shadow); FIELD(cpbrt_stats, rays_closest_traced); FIELD(cpbrt_stats, shade_items); FIELD(cpbrt_stats, trace_slow_paths);
 }
 
 #define CHECK(call)                                                                                      \

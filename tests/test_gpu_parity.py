@@ -150,15 +150,19 @@ def _random_soup_scene(cpbrt, n_tris, seed, grid=False):
     return cpbrt.Scene.parse(text)
 
 
-@pytest.mark.parametrize("min_len", [2, 7, 64, 1000])
-def test_gpu_bvh_top_phase_equals_host_build(cpbrt, oracle, cornell, mesh, monkeypatch, min_len):
-    """the top levels of the exact SAH build on the device (bvh_build_gpu.cu: radix sort
-    per axis, prefix / suffix bound scans, first-minimum pick, level by level), the small subtrees
-    on the host.  Primitive order, topology, split axes and Parent bounds must equal the oracle's
-    whatever segment length the hand-over happens at -- including lattices full of equal centres."""
+@pytest.mark.parametrize("small_phase", ["1", "0"])
+@pytest.mark.parametrize("min_len", [2, 7, 64, 256, 1000])
+def test_gpu_bvh_top_phase_equals_host_build(cpbrt, oracle, cornell, mesh, monkeypatch, min_len, small_phase):
+    """the exact SAH build on the device (bvh_build_gpu.cu): the levels with segments of at least
+    `min_len` primitives level-synchronously (radix sort per axis, prefix / suffix bound scans, first-minimum
+    pick), every smaller subtree in one thread block (k_build_small; CPBRT_BVH_SMALL=0 sends them to the host
+    builder instead).  Primitive order, topology, split axes and Parent bounds must equal the oracle's whatever
+    segment length the hand-over happens at -- including lattices full of equal centres -- and with the small
+    phase on, nothing is left for the host."""
     scenes = [cornell[0], mesh[0], _random_soup_scene(cpbrt, 3000, 1), _random_soup_scene(cpbrt, 5000, 2, grid=True)]
     monkeypatch.setenv("CPBRT_BVH_BUILD", "gpu")
     monkeypatch.setenv("CPBRT_BVH_GPU_MINLEN", str(min_len))
+    monkeypatch.setenv("CPBRT_BVH_SMALL", small_phase)
     for scene in scenes:
         w = oracle.OracleWorld(scene)
         r = cpbrt.Renderer(0); r.upload(scene)
@@ -171,6 +175,10 @@ def test_gpu_bvh_top_phase_equals_host_build(cpbrt, oracle, cornell, mesh, monke
         assert np.array_equal(nodes["bound"], ref["bound"])
         if scene.desc.n_primitives >= max(min_len, 2):
             assert r.bvh_gpu_levels() > 0
+            if small_phase == "1" and min_len <= 256:
+                assert r.bvh_host_segments() == 0, "the host builder still had work"
+            if small_phase == "0" and scene.desc.n_primitives > 2 * min_len:
+                assert r.bvh_host_segments() > 0
         r.close()
 
 

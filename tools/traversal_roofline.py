@@ -2,11 +2,12 @@
 """Traversal roofline on the BVH-traversal-bound configuration (C4: 1,000,008 triangles).
 
 Ray batches resident in HBM -> cpbrt_trace_closest / cpbrt_trace_any -> kernel time from CUDA
-events on the library's stream.  Algorithmic bytes per ray:
-    32 (ray in) + 16 (hit out; 1 for any-hit) + 32 * N_parent + 48 * N_tri
-with N_parent / N_tri counted by the CPU oracle running the reference traversal on a subset of
-the same rays (and cross-checked against the device counters, which must be identical for the
-closest-hit kernel).  Prints one JSON object per batch.
+events on the library's stream.  Bytes per ray = the shipped kernel's OWN work, counted by its
+counting variant on the same rays (CPBRT_TRACE_COUNT_OWN):
+    32 (ray in) + 16 (hit out; 1 for any-hit) + 64 * node steps + 48 * primitive tests
+against this GPU's L2 read peak measured in the same run.  The reference's own visit counts
+(far-first order, loose boxes; device counters cross-checked against the CPU oracle on
+a subset) are printed next to it as the work the two-phase traversal avoids.  One JSON object per batch.
 
     python tools/traversal_roofline.py [--config C4] [--rays 22] [--oracle-rays 18] [--repeat 5]
 """
@@ -70,11 +71,17 @@ def main():
             st = fn(d_rays.data_ptr(), n, d_out.data_ptr())
             if i >= 3:
                 ms.append(st.ms_trace)
-        dev = fn(d_rays.data_ptr(), n, d_out.data_ptr(), count=True)
-        per_ray_dev = (32 + (1 if any_hit else 16)) + (32.0 * dev.trace_parent_visits + 48.0 * dev.trace_prim_tests) / n
+        dev = fn(d_rays.data_ptr(), n, d_out.data_ptr(), count=True)          # reference-order traversal with its visit counters
+        own = fn(d_rays.data_ptr(), n, d_out.data_ptr(), count="own")        # the shipped traversal counting its own work
+        io = 32 + (1 if any_hit else 16)
+        ref_per_ray = io + (32.0 * dev.trace_parent_visits + 48.0 * dev.trace_prim_tests) / n
+        own_per_ray = io + (64.0 * own.trace_parent_visits + 48.0 * own.trace_prim_tests) / n
         out = dict(config=args.config, batch=name, kind="any" if any_hit else "closest", rays=n, primitives=int(scene.desc.n_primitives),
                    ms_avg=float(np.mean(ms)), ms_min=float(np.min(ms)), mrays_s=n / (np.mean(ms) * 1e-3) / 1e6,
-                   device_parent_visits_per_ray=dev.trace_parent_visits / n, device_prim_tests_per_ray=dev.trace_prim_tests / n,
+                   own_node_steps_per_ray=own.trace_parent_visits / n, own_prim_tests_per_ray=own.trace_prim_tests / n, own_bytes_per_ray=own_per_ray,
+                   replays=int(own.trace_slow_paths),
+                   reference_parent_visits_per_ray=dev.trace_parent_visits / n, reference_prim_tests_per_ray=dev.trace_prim_tests / n,
+                   reference_bytes_per_ray=ref_per_ray, work_avoided_vs_reference=ref_per_ray / own_per_ray,
                    bvh_build_upload_s=build_s, l2="flushed with a 256 MB write before every timed launch")
         if world is not None:
             m = min(n, 1 << args.oracle_rays)
@@ -83,16 +90,12 @@ def main():
                 res, cnt = world.trace_any(sub, count=True, threads=os.cpu_count())
             else:
                 res, cnt = world.trace_closest(sub, count=True, threads=os.cpu_count())
-            per_ray = (32 + (1 if any_hit else 16)) + (32.0 * int(cnt[0]) + 48.0 * int(cnt[1])) / len(sub)
-            out.update(oracle_parent_visits_per_ray=int(cnt[0]) / len(sub), oracle_prim_tests_per_ray=int(cnt[1]) / len(sub),
-                       algorithmic_bytes_per_ray=per_ray, oracle_subset=len(sub))
-        else:
-            per_ray = per_ray_dev
-            out.update(algorithmic_bytes_per_ray=per_ray, note="bytes from the device counters (oracle skipped)")
-        achieved = per_ray * n / (np.mean(ms) * 1e-3) / 1e9
-        out.update(roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak),
-                   roofline_l2=dict(bound="l2", achieved=achieved, peak=l2_gbs, unit="GB/s", frac=achieved / l2_gbs,
-                                    note="nodes + triangles of C4 (94 MB) fit the L2; peak = read-only kernel over 64 MB"))
+            out.update(oracle_parent_visits_per_ray=int(cnt[0]) / len(sub), oracle_prim_tests_per_ray=int(cnt[1]) / len(sub), oracle_subset=len(sub))
+        achieved = own_per_ray * n / (np.mean(ms) * 1e-3) / 1e9
+        out.update(roofline=dict(bound="l2", achieved=achieved, peak=l2_gbs, unit="GB/s", frac=achieved / l2_gbs,
+                                 note="own work: node steps x 64 B + primitive tests x 48 B + ray in / result out; nodes + triangles of C4 (94 MB) fit the L2; "
+                                      "peak = read-only kernel over 64 MB in this run"),
+                   hbm_fraction_of_the_same_bytes=achieved / peak)
         print(json.dumps(out))
         sys.stdout.flush()
 
