@@ -217,6 +217,19 @@ class Renderer:
         """Subtrees of the last device build finished by the host builder (0: whole build on the device; -1: host build)."""
         return int(lib.cpbrt_bvh_host_segments(self._ctx))
 
+    def bvh_device_layout(self):
+        """The traversal layout in device memory after build_bvh (cpbrt_bvh_device_layout): dict with
+        nodes[n_nodes, 16] float32, records[n, 12], frames[n, 12], uv[n, 6] or None, resident (bool)."""
+        n_nodes, resident = C.c_uint64(), C.c_int()
+        self._check(lib.cpbrt_bvh_device_layout(self._ctx, 0, C.byref(n_nodes), None, None, None, None, C.byref(resident)))
+        n = int(self.n_primitives)
+        nodes = np.zeros((n_nodes.value, 16), np.float32)
+        records, frames, uv = np.zeros((n, 12), np.float32), np.zeros((n, 12), np.float32), np.zeros((n, 6), np.float32)
+        rc = lib.cpbrt_bvh_device_layout(self._ctx, n_nodes.value, None, nodes.ctypes.data, records.ctypes.data, frames.ctypes.data,
+                                         uv.ctypes.data, None)
+        self._check(min(rc, 0))
+        return dict(nodes=nodes, records=records, frames=frames, uv=uv if rc == 1 else None, resident=bool(resident.value))
+
     def h2d_bytes(self):
         """Bytes this context has copied host -> device so far (counted where the copies are issued)."""
         return int(lib.cpbrt_h2d_bytes(self._ctx))

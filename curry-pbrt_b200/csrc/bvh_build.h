@@ -69,6 +69,24 @@ struct TopPhase {
     std::vector<SmallSubtreeNode> small_nodes;
     std::vector<uint32_t> pending_root;
 };
+// The whole build on the device (bvh_build_gpu.cu, gpu_sah_build_resident): host scene arrays in, device traversal
+// layout out (scene_dev.cuh: 64-byte Parent records, 48-byte primitive records, shading frames, uv triples).
+struct ResidentBuildInput {
+    const cpbrt_primitive* prims; uint32_t n_prims;
+    const cpbrt_triangle* tris; uint32_t n_tris;
+    const float* radius; uint32_t n_spheres;
+    const void* d_transforms;         // DevTransform array already on the device
+    bool any_uv;
+};
+struct ResidentBuildOutput {
+    void* d_base = nullptr; size_t bytes = 0;        // ONE cudaMalloc'ed block, owned by the caller; the four arrays below are pieces of it
+    void *d_nodes = nullptr, *d_records = nullptr, *d_frames = nullptr, *d_uv = nullptr;
+    uint32_t n_nodes = 0;
+    float root_box[6] = {0, 0, 0, 0, 0, 0};
+    std::vector<uint32_t> order;      // slot -> uploaded primitive index
+    int levels = 0;
+    uint64_t h2d_bytes = 0;
+};
 // Builds every pending segment with the host builder (in parallel) and stitches the tree together.
 void finish_sah_bvh(TopPhase&& top, unsigned n_threads, BvhBuildResult* out);
 

@@ -268,6 +268,18 @@ __global__ void __launch_bounds__(kSmallThreads) k_build_small(Box* __restrict__
     for (uint32_t k = blockIdx.x; k < n_pending; k += gridDim.x) {
         const PendingSegment seg = pending[k];
         const uint32_t len0 = seg.end - seg.start;
+        if (seg.force_leaf != 0u && len0 > 0) {      // the SAH said "leaf" upstairs: one node, whatever the length
+            if (tid == 0) {
+                const uint32_t at = atomicAdd(n_nodes, 1u);
+                if (at + 1u > node_cap) { *overflow = 1u; seg_root[k] = 0xFFFFFFFFu; }
+                else {
+                    SmallNode nd; nd.leaf_axis = 1u; nd.a = seg.start; nd.b = seg.end;
+                    for (int c = 0; c < 3; ++c) { nd.mn[c] = 0.f; nd.mx[c] = 0.f; }
+                    nodes[at] = nd; seg_root[k] = at;
+                }
+            }
+            continue;
+        }
         if (len0 > (uint32_t)kSmallMax || len0 == 0) { if (tid == 0) seg_root[k] = 0xFFFFFFFFu; continue; }   // left to the host builder
         __syncthreads();
         if (tid == 0) {
@@ -521,46 +533,92 @@ __global__ void k_prim_records(const cpbrt_primitive* __restrict__ prims, const 
     }
 }
 
+// Device scratch of one build: one slab (a single cudaMalloc -- dozens of separate multi-hundred-megabyte
+// allocations cost anything between 15 and 500 ms on the same box) handed out in 256-byte aligned pieces;
+// whatever does not fit falls back to its own allocation.
 struct DevMem {
     std::vector<void*> all;
-    ~DevMem() { for (void* p : all) cudaFree(p); }
-    template <class T> T* get(size_t n) { void* p = nullptr; if (cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)) != cudaSuccess) return nullptr; all.push_back(p); return (T*)p; }
-    void* detach(void* p) { for (auto& q : all) if (q == p) { q = nullptr; return p; } return p; }      // ownership goes to the caller (cudaFree(nullptr) is a no-op)
+    char* slab = nullptr; size_t slab_bytes = 0, used = 0;
+    ~DevMem() { for (void* p : all) cudaFree(p); cudaFree(slab); }
+    bool reserve(size_t bytes) {
+        if (slab) return true;
+        if (cudaMalloc((void**)&slab, bytes) != cudaSuccess) { cudaGetLastError(); slab = nullptr; return false; }
+        slab_bytes = bytes; used = 0;
+        return true;
+    }
+    template <class T> T* get(size_t n) {
+        const size_t bytes = (std::max<size_t>(n, 1) * sizeof(T) + 255) & ~(size_t)255;
+        if (slab && used + bytes <= slab_bytes) { T* p = (T*)(slab + used); used += bytes; return p; }
+        void* p = nullptr;
+        if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
+        all.push_back(p);
+        return (T*)p;
+    }
 };
 
 #define CK(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { *err = std::string(#x) + ": " + cudaGetErrorString(e__); return false; } } while (0)
 
-}  // namespace
-
-bool gpu_sah_top_phase(const std::vector<BuildBounds>& bounds, uint32_t min_len, int max_levels, cudaStream_t stream, TopPhase* out, std::string* err) {
-    const uint32_t n = (uint32_t)bounds.size();
-    out->pb.clear(); out->order.clear(); out->nodes.clear(); out->pending.clear(); out->pending_parent.clear(); out->pending_side.clear();
-    out->root = 0x7FFFFFFF; out->levels = 0;
-    if (n < 2 || n < min_len || n >= 0x3FFFFFFFu) { *err = "nothing to do on the device"; return false; }
-    if (min_len < 2) min_len = 2;
-    for (const BuildBounds& b : bounds)
-        for (int k = 0; k < 3; ++k) if (b.mn[k] != b.mn[k] || b.mx[k] != b.mx[k]) { *err = "NaN bounds: the order of unions matters, host build only"; return false; }
-
-    const bool timing = getenv("CPBRT_TIMING") != nullptr;
-    auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    double t_mark = now();
-    auto lap = [&](const char* what) { if (timing) { cudaStreamSynchronize(stream); const double t = now(); fprintf(stderr, "[gpu_sah] %-28s %.3f s\n", what, t - t_mark); t_mark = t; } };
+// ------------------------------------------------------------------------------------------------
+// One build's device working set.  run() performs the level-synchronous phase and the small-segment phase and
+// leaves everything on the device; the two front ends below either download the pieces for the host stitcher
+// (gpu_sah_top_phase: node dumps, tests) or finish the traversal layout on the device (gpu_sah_build_resident).
+struct DeviceSah {
     DevMem M;
+    cudaStream_t stream = nullptr;
+    uint32_t n = 0, min_len = 2;
+    int max_levels = 48;
+    bool timing = false;
+    double t_mark = 0.0;
+    // results (device)
+    Box* pb_final = nullptr; uint32_t* order_final = nullptr;
+    TopNode* nodes = nullptr; PendingSegment* pending = nullptr; int32_t* pending_parent = nullptr; uint32_t* pending_side = nullptr;
+    uint32_t* counters = nullptr;      // [0] nodes, [1] pending, [2] overflow, [3] root_ref (as int), [4] small nodes, [5] small overflow
+    SmallNode* small = nullptr; uint32_t* seg_root = nullptr;
+    Box* pb_in = nullptr;              // primitive bounds in upload order: filled by the caller before run()
+    // results (host)
+    uint32_t nn = 0, np = 0, n_small = 0;
+    int levels = 0; int32_t root = 0x7FFFFFFF;
+    std::vector<Segment> left;         // segments still active when the level budget ran out
+    bool small_ran = false;
+
+    static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+    void lap(const char* what) { if (timing) { cudaStreamSynchronize(stream); const double t = now(); fprintf(stderr, "[gpu_sah] %-28s %.3f s\n", what, t - t_mark); t_mark = t; } }
+    bool init(uint32_t n_, uint32_t min_len_, int max_levels_, cudaStream_t st, std::string* err, size_t extra_bytes = 0) {
+        n = n_; min_len = std::max(2u, min_len_); max_levels = max_levels_; stream = st;
+        timing = getenv("CPBRT_TIMING") != nullptr; t_mark = now();
+        if (n < 2 || n < min_len || n >= 0x3FFFFFFFu) { *err = "nothing to do on the device"; return false; }
+        // 9 box arrays, 12 index arrays, 2 key arrays, CUB scratch and the per-segment tables; extra_bytes: what the
+        // front end keeps next to them (the uploaded scene arrays of the resident build)
+        M.reserve((size_t)n * (9 * sizeof(Box) + 12 * 4 + 2 * 8 + 8) + extra_bytes + (64u << 20));
+        pb_in = M.get<Box>(n);
+        if (!pb_in) { *err = "device memory for the BVH build"; return false; }
+        return true;
+    }
+    bool run(bool small_phase, std::string* err);
+};
+
+bool DeviceSah::run(bool small_phase, std::string* err) {
     const uint32_t max_segs = n / min_len + 2;
     const uint32_t node_cap = 2 * max_segs * (uint32_t)std::max(1, max_levels) + 16, pending_cap = node_cap + 16;
-    Box *pb = M.get<Box>(n), *pb_new = M.get<Box>(n), *pb_alt = M.get<Box>(n), *fwd = M.get<Box>(n), *rev = M.get<Box>(n), *prefix = M.get<Box>(n),
-        *suffix_rev = M.get<Box>(n), *prefix0 = M.get<Box>(n), *pb_final = M.get<Box>(n);
-    uint32_t *order = M.get<uint32_t>(n), *order_new = M.get<uint32_t>(n), *order_alt = M.get<uint32_t>(n), *order_final = M.get<uint32_t>(n), *seg = M.get<uint32_t>(n),
+    // fwd, rev and prefix are one piece: after the level-synchronous phase the small-subtree nodes live there
+    // (2 n nodes of 36 bytes = 3 n boxes of 24 bytes)
+    static_assert(2 * sizeof(SmallNode) == 3 * sizeof(Box), "the small nodes reuse three box arrays");
+    Box* scan3 = M.get<Box>(3ull * n + 32);
+    Box *pb = pb_in, *pb_new = M.get<Box>(n), *pb_alt = M.get<Box>(n), *fwd = scan3, *rev = scan3 ? scan3 + n : nullptr, *prefix = scan3 ? scan3 + 2ull * n : nullptr,
+        *suffix_rev = M.get<Box>(n), *prefix0 = M.get<Box>(n);
+    pb_final = M.get<Box>(n);
+    uint32_t *order = M.get<uint32_t>(n), *order_new = M.get<uint32_t>(n), *order_alt = M.get<uint32_t>(n), *seg = M.get<uint32_t>(n),
              *seg_rev = M.get<uint32_t>(n), *vals = M.get<uint32_t>(n), *keep = M.get<uint32_t>(n + 1), *keep_off = M.get<uint32_t>(n + 1);
+    order_final = M.get<uint32_t>(n);
     uint32_t* idx[3] = {M.get<uint32_t>(n), M.get<uint32_t>(n), M.get<uint32_t>(n)};
     unsigned long long *keys = M.get<unsigned long long>(n), *keys_out = M.get<unsigned long long>(n), *best = M.get<unsigned long long>(max_segs);
     Segment *segs = M.get<Segment>(max_segs), *segs_next = M.get<Segment>(max_segs);
     Decision* dec = M.get<Decision>(max_segs);
     uint32_t *first_nan = M.get<uint32_t>(max_segs), *child_count = M.get<uint32_t>(max_segs + 1), *child_off = M.get<uint32_t>(max_segs + 1);
-    TopNode* nodes = M.get<TopNode>(node_cap);
-    PendingSegment* pending = M.get<PendingSegment>(pending_cap);
-    int32_t* pending_parent = M.get<int32_t>(pending_cap); uint32_t* pending_side = M.get<uint32_t>(pending_cap);
-    uint32_t* counters = M.get<uint32_t>(8);   // [0] nodes, [1] pending, [2] overflow, [3] root_ref (as int), [4] small nodes, [5] small overflow
+    nodes = M.get<TopNode>(node_cap);
+    pending = M.get<PendingSegment>(pending_cap);
+    pending_parent = M.get<int32_t>(pending_cap); pending_side = M.get<uint32_t>(pending_cap);
+    counters = M.get<uint32_t>(8);
     if (!pb || !pb_new || !pb_alt || !fwd || !rev || !prefix || !suffix_rev || !prefix0 || !pb_final || !order || !order_new || !order_alt || !order_final || !seg ||
         !seg_rev || !vals || !keep || !keep_off || !idx[0] || !idx[1] || !idx[2] || !keys || !keys_out || !best || !segs || !segs_next || !dec || !first_nan ||
         !child_count || !child_off || !nodes || !pending || !pending_parent || !pending_side || !counters) { *err = "device memory for the BVH build"; return false; }
@@ -573,24 +631,19 @@ bool gpu_sah_top_phase(const std::vector<BuildBounds>& bounds, uint32_t min_len,
     void* tmp = M.get<char>(tmp_bytes);
     if (!tmp) { *err = "device memory for the BVH build"; return false; }
 
-    CK(cudaMemcpyAsync(pb, bounds.data(), (size_t)n * sizeof(Box), cudaMemcpyHostToDevice, stream));
-    {
-        std::vector<uint32_t> iota(n);
-        for (uint32_t i = 0; i < n; ++i) iota[i] = i;
-        CK(cudaMemcpyAsync(order, iota.data(), (size_t)n * 4, cudaMemcpyHostToDevice, stream));
-        CK(cudaStreamSynchronize(stream));
-    }
+    const int T = 256;
+    auto grid = [&](uint32_t items) { return (int)std::min<uint32_t>((items + T - 1) / T, 148u * 16u); };
+    k_iota<<<grid(n), T, 0, stream>>>(order, n);
     CK(cudaMemsetAsync(counters, 0, 8 * 4, stream));
     {
         int32_t none = 0x7FFFFFFF;
         CK(cudaMemcpyAsync(counters + 3, &none, 4, cudaMemcpyHostToDevice, stream));
-        Segment root; root.slot0 = 0; root.rank0 = 0; root.len = n; root.parent = -1; root.side = 0;
-        CK(cudaMemcpyAsync(segs, &root, sizeof root, cudaMemcpyHostToDevice, stream));
+        Segment root_seg; root_seg.slot0 = 0; root_seg.rank0 = 0; root_seg.len = n; root_seg.parent = -1; root_seg.side = 0;
+        CK(cudaMemcpyAsync(segs, &root_seg, sizeof root_seg, cudaMemcpyHostToDevice, stream));
+        CK(cudaStreamSynchronize(stream));      // the two sources above are locals
     }
-    lap("allocations + upload");
+    lap("allocations + setup");
     uint32_t m = n, n_segs = 1;
-    const int T = 256;
-    auto grid = [&](uint32_t items) { return (int)std::min<uint32_t>((items + T - 1) / T, 148u * 16u); };
     int level = 0;
     for (; level < max_levels && n_segs > 0; ++level) {
         k_segment_ids<<<grid(m), T, 0, stream>>>(segs, n_segs, seg);
@@ -630,69 +683,163 @@ bool gpu_sah_top_phase(const std::vector<BuildBounds>& bounds, uint32_t min_len,
         std::swap(pb, pb_alt); std::swap(order, order_alt); std::swap(segs, segs_next);
         m = m_next; n_segs = s_next;
     }
+    levels = level;
     lap("level-synchronous phase");
     // segments still active when the level budget ran out go to the host as they are
-    std::vector<Segment> left(n_segs);
+    left.assign(n_segs, Segment());
     if (n_segs) {
         CK(cudaMemcpyAsync(left.data(), segs, (size_t)n_segs * sizeof(Segment), cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
         // their primitives are in the working arrays: move them to their final slots
-        std::vector<Box> hb(m); std::vector<uint32_t> ho(m);
-        CK(cudaMemcpyAsync(hb.data(), pb, (size_t)m * sizeof(Box), cudaMemcpyDeviceToHost, stream));
-        CK(cudaMemcpyAsync(ho.data(), order, (size_t)m * 4, cudaMemcpyDeviceToHost, stream));
-        CK(cudaStreamSynchronize(stream));
         for (const Segment& sg : left) {
-            CK(cudaMemcpyAsync(pb_final + sg.slot0, hb.data() + sg.rank0, (size_t)sg.len * sizeof(Box), cudaMemcpyHostToDevice, stream));
-            CK(cudaMemcpyAsync(order_final + sg.slot0, ho.data() + sg.rank0, (size_t)sg.len * 4, cudaMemcpyHostToDevice, stream));
+            CK(cudaMemcpyAsync(pb_final + sg.slot0, pb + sg.rank0, (size_t)sg.len * sizeof(Box), cudaMemcpyDeviceToDevice, stream));
+            CK(cudaMemcpyAsync(order_final + sg.slot0, order + sg.rank0, (size_t)sg.len * 4, cudaMemcpyDeviceToDevice, stream));
         }
-        CK(cudaStreamSynchronize(stream));
     }
     uint32_t h_counters[4];
     CK(cudaMemcpyAsync(h_counters, counters, 16, cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
-    const uint32_t nn = h_counters[0], np = h_counters[1];
+    nn = h_counters[0]; np = h_counters[1]; root = (int32_t)h_counters[3];
     // ---- small phase: every pending segment of up to kSmallMax primitives, one block each ---------------------
+    small_ran = false; n_small = 0;
+    if (small_phase && np > 0) {
+        const uint32_t small_cap = 2u * n;
+        small = reinterpret_cast<SmallNode*>(scan3);
+        seg_root = M.get<uint32_t>(np);
+        if (!small || !seg_root) { *err = "device memory for the BVH build"; return false; }
+        CK(cudaMemsetAsync(counters + 4, 0, 8, stream));
+        // a block reserves 2 len - 1 nodes and may use fewer (multi-primitive Leaves): what stays unused reads as a Leaf
+        CK(cudaMemsetAsync(small, 0xFF, (size_t)small_cap * sizeof(SmallNode), stream));
+        k_build_small<<<(int)std::min<uint32_t>(np, 148u * 32u), kSmallThreads, 0, stream>>>(pb_final, order_final, pending, np, small, small_cap, counters + 4, seg_root, counters + 5);
+        uint32_t used[2];
+        CK(cudaMemcpyAsync(used, counters + 4, 8, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        lap("small-segment kernel");
+        if (used[1]) { *err = "BVH small-phase node table overflowed"; return false; }
+        n_small = used[0]; small_ran = true;
+    }
+    return true;
+}
+
+}  // namespace
+
+bool gpu_sah_top_phase(const std::vector<BuildBounds>& bounds, uint32_t min_len, int max_levels, cudaStream_t stream, TopPhase* out, std::string* err) {
+    const uint32_t n = (uint32_t)bounds.size();
+    out->pb.clear(); out->order.clear(); out->nodes.clear(); out->pending.clear(); out->pending_parent.clear(); out->pending_side.clear();
     out->small_nodes.clear(); out->pending_root.clear();
-    bool host_work = !left.empty();
-    {
-        const char* e = getenv("CPBRT_BVH_SMALL");
-        if ((!e || atoi(e) != 0) && np > 0) {
-            const uint32_t small_cap = 2u * n;
-            SmallNode* small = M.get<SmallNode>(small_cap);
-            uint32_t* seg_root = M.get<uint32_t>(np);
-            if (!small || !seg_root) { *err = "device memory for the BVH build"; return false; }
-            CK(cudaMemsetAsync(counters + 4, 0, 8, stream));      // [4] small nodes used, [5] overflow
-            k_build_small<<<(int)std::min<uint32_t>(np, 148u * 32u), kSmallThreads, 0, stream>>>(pb_final, order_final, pending, np, small, small_cap, counters + 4, seg_root, counters + 5);
-            uint32_t used[2];
-            CK(cudaMemcpyAsync(used, counters + 4, 8, cudaMemcpyDeviceToHost, stream));
-            CK(cudaStreamSynchronize(stream));
-            lap("small-segment kernel");
-            if (used[1]) { *err = "BVH small-phase node table overflowed"; return false; }
-            out->small_nodes.resize(used[0]); out->pending_root.resize(np);
-            static_assert(sizeof(SmallNode) == sizeof(SmallSubtreeNode), "layout");
-            if (used[0]) CK(cudaMemcpyAsync(out->small_nodes.data(), small, (size_t)used[0] * sizeof(SmallNode), cudaMemcpyDeviceToHost, stream));
-            CK(cudaMemcpyAsync(out->pending_root.data(), seg_root, (size_t)np * 4, cudaMemcpyDeviceToHost, stream));
-            CK(cudaStreamSynchronize(stream));
-            for (uint32_t k = 0; k < np && !host_work; ++k) host_work = out->pending_root[k] == 0xFFFFFFFFu;
-        } else host_work = true;
+    out->root = 0x7FFFFFFF; out->levels = 0;
+    for (const BuildBounds& b : bounds)
+        for (int k = 0; k < 3; ++k) if (b.mn[k] != b.mn[k] || b.mx[k] != b.mx[k]) { *err = "NaN bounds: the order of unions matters, host build only"; return false; }
+    DeviceSah D;
+    if (!D.init(n, min_len, max_levels, stream, err)) return false;
+    CK(cudaMemcpyAsync(D.pb_in, bounds.data(), (size_t)n * sizeof(Box), cudaMemcpyHostToDevice, stream));
+    const char* e = getenv("CPBRT_BVH_SMALL");
+    if (!D.run(!e || atoi(e) != 0, err)) return false;
+    const uint32_t nn = D.nn, np = D.np;
+    bool host_work = !D.left.empty() || !D.small_ran;
+    if (D.small_ran) {
+        out->small_nodes.resize(D.n_small); out->pending_root.resize(np);
+        static_assert(sizeof(SmallNode) == sizeof(SmallSubtreeNode), "layout");
+        if (D.n_small) CK(cudaMemcpyAsync(out->small_nodes.data(), D.small, (size_t)D.n_small * sizeof(SmallNode), cudaMemcpyDeviceToHost, stream));
+        CK(cudaMemcpyAsync(out->pending_root.data(), D.seg_root, (size_t)np * 4, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        for (uint32_t k = 0; k < np && !host_work; ++k) host_work = out->pending_root[k] == 0xFFFFFFFFu;
     }
     out->pb.resize(host_work ? n : 0); out->order.resize(n); out->nodes.resize(nn); out->pending.resize(np); out->pending_parent.resize(np); out->pending_side.resize(np);
-    if (host_work) CK(cudaMemcpyAsync(out->pb.data(), pb_final, (size_t)n * sizeof(Box), cudaMemcpyDeviceToHost, stream));
-    CK(cudaMemcpyAsync(out->order.data(), order_final, (size_t)n * 4, cudaMemcpyDeviceToHost, stream));
-    if (nn) CK(cudaMemcpyAsync(out->nodes.data(), nodes, (size_t)nn * sizeof(TopNode), cudaMemcpyDeviceToHost, stream));
+    if (host_work) CK(cudaMemcpyAsync(out->pb.data(), D.pb_final, (size_t)n * sizeof(Box), cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(out->order.data(), D.order_final, (size_t)n * 4, cudaMemcpyDeviceToHost, stream));
+    if (nn) CK(cudaMemcpyAsync(out->nodes.data(), D.nodes, (size_t)nn * sizeof(TopNode), cudaMemcpyDeviceToHost, stream));
     if (np) {
-        CK(cudaMemcpyAsync(out->pending.data(), pending, (size_t)np * sizeof(PendingSegment), cudaMemcpyDeviceToHost, stream));
-        CK(cudaMemcpyAsync(out->pending_parent.data(), pending_parent, (size_t)np * 4, cudaMemcpyDeviceToHost, stream));
-        CK(cudaMemcpyAsync(out->pending_side.data(), pending_side, (size_t)np * 4, cudaMemcpyDeviceToHost, stream));
+        CK(cudaMemcpyAsync(out->pending.data(), D.pending, (size_t)np * sizeof(PendingSegment), cudaMemcpyDeviceToHost, stream));
+        CK(cudaMemcpyAsync(out->pending_parent.data(), D.pending_parent, (size_t)np * 4, cudaMemcpyDeviceToHost, stream));
+        CK(cudaMemcpyAsync(out->pending_side.data(), D.pending_side, (size_t)np * 4, cudaMemcpyDeviceToHost, stream));
     }
     CK(cudaStreamSynchronize(stream));
-    out->root = (int32_t)h_counters[3];
-    for (const Segment& sg : left) {
+    out->root = D.root;
+    for (const Segment& sg : D.left) {
         PendingSegment p; p.start = sg.slot0; p.end = sg.slot0 + sg.len; p.force_leaf = 0;
         out->pending.push_back(p); out->pending_parent.push_back(sg.parent); out->pending_side.push_back(sg.side);
     }
-    out->levels = level;
-    lap("downloads");
+    out->levels = D.levels;
+    D.lap("downloads");
+    return true;
+}
+
+// The whole build on the device: bounds, SAH tree, traversal layout, primitive records.  Only the primitive order
+// (4 bytes per primitive) comes back.  Returns false (with *err) whenever the device cannot finish by itself -- NaN
+// bounds, a subtree the block kernel does not take, a root that is a Leaf -- and the caller falls back to the
+// hybrid path, which produces the same tree.
+bool gpu_sah_build_resident(const ResidentBuildInput& in, uint32_t min_len, int max_levels, cudaStream_t stream, ResidentBuildOutput* out, std::string* err) {
+    const uint32_t n = in.n_prims;
+    DeviceSah D;
+    if (!D.init(n, min_len, max_levels, stream, err, (size_t)n * sizeof(cpbrt_primitive) + (size_t)in.n_tris * sizeof(cpbrt_triangle) + (size_t)in.n_spheres * 4)) return false;
+    const int T = 256;
+    auto grid = [&](uint32_t items) { return (int)std::min<uint32_t>((items + T - 1) / T, 148u * 16u); };
+    cpbrt_primitive* d_prims_in = D.M.get<cpbrt_primitive>(n);
+    cpbrt_triangle* d_tris = D.M.get<cpbrt_triangle>(in.n_tris);
+    float* d_radius = D.M.get<float>(in.n_spheres);
+    uint32_t* d_flag = D.M.get<uint32_t>(1);
+    if (!d_prims_in || !d_tris || !d_radius || !d_flag) { *err = "device memory for the BVH build"; return false; }
+    CK(cudaMemcpyAsync(d_prims_in, in.prims, (size_t)n * sizeof(cpbrt_primitive), cudaMemcpyHostToDevice, stream));
+    if (in.n_tris) CK(cudaMemcpyAsync(d_tris, in.tris, (size_t)in.n_tris * sizeof(cpbrt_triangle), cudaMemcpyHostToDevice, stream));
+    if (in.n_spheres) CK(cudaMemcpyAsync(d_radius, in.radius, (size_t)in.n_spheres * 4, cudaMemcpyHostToDevice, stream));
+    out->h2d_bytes = (uint64_t)n * sizeof(cpbrt_primitive) + (uint64_t)in.n_tris * sizeof(cpbrt_triangle) + (uint64_t)in.n_spheres * 4;
+    CK(cudaMemsetAsync(d_flag, 0, 4, stream));
+    k_prim_bounds<<<grid(n), T, 0, stream>>>(d_prims_in, n, d_tris, d_radius, (const DevXform*)in.d_transforms, D.pb_in, d_flag);
+    uint32_t any_nan = 0;
+    CK(cudaMemcpyAsync(&any_nan, d_flag, 4, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    D.lap("scene upload + bounds");
+    if (any_nan) { *err = "NaN bounds: the order of unions matters, host build only"; return false; }
+    if (!D.run(true, err)) return false;
+    if (!D.left.empty()) { *err = "level budget exhausted"; return false; }
+    if (D.root != 0 || D.nn == 0) { *err = "the root is a Leaf"; return false; }       // the traversal wants the root Parent at index 0
+    const uint32_t np = D.np, n_top = D.nn, n_small = D.n_small;
+    if (!D.small_ran && np) { *err = "small phase did not run"; return false; }
+    // every pending segment must have been taken by the block kernel
+    {
+        std::vector<uint32_t> roots(np);
+        if (np) CK(cudaMemcpyAsync(roots.data(), D.seg_root, (size_t)np * 4, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        for (uint32_t k = 0; k < np; ++k) if (roots[k] == 0xFFFFFFFFu) { *err = "a subtree was left to the host builder"; return false; }
+    }
+    // Parent numbers of the small subtrees
+    uint32_t* pflag = D.M.get<uint32_t>(n_small + 1);
+    uint32_t* pidx = D.M.get<uint32_t>(n_small + 1);
+    if (!pflag || !pidx) { *err = "device memory for the BVH build"; return false; }
+    size_t need = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, need, pflag, pidx, (int)n_small + 1, stream);
+    void* tmp = D.M.get<char>(need);
+    if (!tmp) { *err = "device memory for the BVH build"; return false; }
+    CK(cudaMemsetAsync(pflag + n_small, 0, 4, stream));
+    if (n_small) k_small_parent_flags<<<grid(n_small), T, 0, stream>>>(D.small, n_small, pflag);
+    CK(cub::DeviceScan::ExclusiveSum(tmp, need, pflag, pidx, (int)n_small + 1, stream));
+    uint32_t n_small_parents = 0;
+    CK(cudaMemcpyAsync(&n_small_parents, pidx + n_small, 4, cudaMemcpyDeviceToHost, stream));
+    TopNode root_node;
+    CK(cudaMemcpyAsync(&root_node, D.nodes, sizeof root_node, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    const uint32_t n_nodes = n_top + n_small_parents;
+    // outputs: one allocation {Parents | records | frames | uv}, owned by the caller from here on
+    const size_t off_rec = (size_t)n_nodes * 64, off_frames = off_rec + (size_t)n * 48, off_uv = off_frames + (size_t)n * 48;
+    const size_t out_bytes = off_uv + (in.any_uv ? (size_t)n * 24 : 0);
+    char* o_base = nullptr;
+    if (cudaMalloc((void**)&o_base, out_bytes) != cudaSuccess) { cudaGetLastError(); *err = "device memory for the BVH layout"; return false; }
+    void *o_nodes = o_base, *o_rec = o_base + off_rec, *o_frames = o_base + off_frames, *o_uv = in.any_uv ? o_base + off_uv : nullptr;
+    auto drop = [&]() { cudaFree(o_base); };
+    if (np) k_link_pending<<<grid(np), T, 0, stream>>>(D.pending_parent, D.pending_side, D.seg_root, np, D.nodes);
+    k_layout_nodes<<<grid(n_top + n_small), T, 0, stream>>>(D.nodes, n_top, D.small, n_small, pidx, D.pb_final, (float4*)o_nodes);
+    k_prim_records<<<grid(n), T, 0, stream>>>(d_prims_in, d_tris, d_radius, D.order_final, n, in.any_uv ? 1 : 0, (float4*)o_rec, (float4*)o_frames, (float*)o_uv);
+    out->order.resize(n);
+    cudaError_t e = cudaMemcpyAsync(out->order.data(), D.order_final, (size_t)n * 4, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) { drop(); *err = std::string("BVH layout: ") + cudaGetErrorString(e); return false; }
+    out->d_base = o_base; out->bytes = out_bytes;
+    out->d_nodes = o_nodes; out->d_records = o_rec; out->d_frames = o_frames; out->d_uv = o_uv;
+    out->n_nodes = n_nodes; out->levels = D.levels;
+    for (int k = 0; k < 3; ++k) { out->root_box[k] = root_node.bound.mn[k]; out->root_box[3 + k] = root_node.bound.mx[k]; }
+    D.lap("layout + records + order");
     return true;
 }
 

@@ -5,6 +5,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
@@ -20,6 +21,7 @@
 namespace cpbrt {
 // bvh_build_gpu.cu: the levels of the SAH build whose segments hold at least `min_len` primitives
 bool gpu_sah_top_phase(const std::vector<BuildBounds>& bounds, uint32_t min_len, int max_levels, cudaStream_t stream, TopPhase* out, std::string* err);
+bool gpu_sah_build_resident(const ResidentBuildInput& in, uint32_t min_len, int max_levels, cudaStream_t stream, ResidentBuildOutput* out, std::string* err);
 }
 using namespace cpbrt;
 
@@ -29,7 +31,9 @@ thread_local std::string g_create_error;
 
 struct DevBuf {
     void* p = nullptr; size_t bytes = 0;
-    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    bool view = false;      // a piece of another allocation (the resident BVH build's block): nothing to free
+    void release() { if (p && !view) cudaFree(p); p = nullptr; bytes = 0; view = false; }
+    void set_view(void* q, size_t b) { release(); p = q; bytes = b; view = q != nullptr; }
 };
 
 // ---- NCCL through dlopen: the library is only needed when a communicator is attached -------
@@ -84,9 +88,11 @@ struct cpbrt_ctx {
     std::vector<cpbrt_transform> transforms;
     BvhBuildResult bvh;
     int bvh_gpu_levels = 0;   // levels of the last BVH build that ran on the device
+    bool bvh_resident = false; // the last build never left the device (no host arena: ctx->bvh holds the order only)
     std::vector<DevLight> host_lights;
 
     DevScene scene;   // by-value kernel argument
+    DevBuf d_bvh_block;       // the resident build's single output allocation; d_prims / d_prim_uv / d_prim_frame / d_nodes are views into it then
     DevBuf d_prims, d_prim_uv, d_prim_frame, d_nodes, d_flat, d_env, d_transforms, d_materials, d_textures, d_texels, d_lights, d_perm, d_primes, d_primsum, d_magic, d_halton_dims, d_halton_inv_pow;
 
     // wavefront state: up to kMaxLanes independent pipelines ("lanes"), each with its own path state, queues,
@@ -129,7 +135,7 @@ namespace {
 int alloc_upload(cpbrt_ctx* ctx, DevBuf& b, const void* src, size_t bytes) {
     const size_t src_bytes = bytes;      // an empty array still gets a 16-byte placeholder, but nothing is read from `src`
     if (bytes == 0) bytes = 16;
-    if (b.bytes != bytes) {   // re-uploading a scene of the same shape reuses its buffers
+    if (b.bytes != bytes || b.view) {   // re-uploading a scene of the same shape reuses its buffers
         b.release();
         CU(cudaMalloc(&b.p, bytes));
         b.bytes = bytes;
@@ -237,7 +243,7 @@ void cpbrt_destroy(cpbrt_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
-    DevBuf* bufs[] = {&ctx->d_prims, &ctx->d_prim_uv, &ctx->d_prim_frame, &ctx->d_nodes, &ctx->d_flat, &ctx->d_env, &ctx->d_transforms, &ctx->d_materials, &ctx->d_textures, &ctx->d_texels,
+    DevBuf* bufs[] = {&ctx->d_bvh_block, &ctx->d_prims, &ctx->d_prim_uv, &ctx->d_prim_frame, &ctx->d_nodes, &ctx->d_flat, &ctx->d_env, &ctx->d_transforms, &ctx->d_materials, &ctx->d_textures, &ctx->d_texels,
                       &ctx->d_lights, &ctx->d_perm, &ctx->d_primes, &ctx->d_primsum, &ctx->d_magic, &ctx->d_halton_dims, &ctx->d_halton_inv_pow,
                       &ctx->d_pixels, &ctx->d_totals_buf, &ctx->d_film_out};
     for (DevBuf* b : bufs) b->release();
@@ -570,50 +576,115 @@ static int exchange_bvh(cpbrt_ctx* ctx, uint32_t n, int local_rc, bool any_uv, c
     return rc;
 }
 
-// The build proper: SAH tree (device top levels + host subtrees, or host only), device layout, uploads.
-static int build_bvh_local(cpbrt_ctx* ctx, uint32_t n, bool* any_uv_out) {
+// BVH slot of each area light's primitive (when exactly one primitive carries the light)
+static int assign_light_slots(cpbrt_ctx* ctx, const std::vector<uint32_t>& order) {
+    const uint32_t n = (uint32_t)order.size();
+    const size_t nl = ctx->host_lights.size();
+    std::vector<std::atomic<uint32_t>> count(nl), slot_of(nl);
+    for (size_t i = 0; i < nl; ++i) { count[i].store(0); slot_of[i].store(0xFFFFFFFFu); }
+    parallel_for(n, 1 << 16, [&](uint64_t lo, uint64_t hi) {
+        for (uint32_t slot = (uint32_t)lo; slot < (uint32_t)hi; ++slot) {
+            const cpbrt_primitive& p = ctx->primitives[order[slot]];
+            if (p.light >= 0) { slot_of[p.light].store(slot); count[p.light].fetch_add(1); }
+        }
+    });
+    for (size_t i = 0; i < nl; ++i) ctx->host_lights[i].slot = count[i].load() == 1 ? slot_of[i].load() : 0xFFFFFFFFu;
+    if (int rc = alloc_upload(ctx, ctx->d_lights, ctx->host_lights.data(), nl * sizeof(DevLight))) return rc;
+    ctx->scene.lights = (const DevLight*)ctx->d_lights.p;
+    return 0;
+}
+
+// The build proper: SAH tree, device layout, uploads.  Three ways to the same tree (bvh.rs:24-124):
+//   resident  big scenes, no node dump asked for: bounds, SAH levels, small subtrees, traversal layout and primitive
+//             records all on the device (bvh_build_gpu.cu); the host only gets the primitive order back
+//   hybrid    the same device phases, pieces downloaded and stitched into the host arena (node dumps, tests;
+//             CPBRT_BVH_SMALL=0 additionally leaves the small subtrees to the host builder)
+//   host      small scenes, NaN bounds, CPBRT_BVH_BUILD=host
+static int build_bvh_local(cpbrt_ctx* ctx, uint32_t n, bool* any_uv_out, bool want_dump) {
     const bool timing = getenv("CPBRT_TIMING") != nullptr;
     auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     double t_mark = now();
     auto lap = [&](const char* what) { if (timing) { const double t = now(); fprintf(stderr, "[cpbrt_build_bvh] %-28s %.3f s\n", what, t - t_mark); t_mark = t; } };
+    DevScene& S = ctx->scene;
+    // CPBRT_BVH_BUILD=host|gpu and CPBRT_BVH_GPU_MINLEN override the defaults (tests use both).
+    const char* how = getenv("CPBRT_BVH_BUILD");
+    const char* ml = getenv("CPBRT_BVH_GPU_MINLEN");
+    const uint32_t min_len = ml ? (uint32_t)std::max(2, atoi(ml)) : 256u;   // measured flat between 16 and 1024 (tools/bvh_build_bench.py)
+    bool on_gpu = (how ? strcmp(how, "gpu") == 0 : n >= (1u << 17)) && n >= min_len && n >= 2;
+    ctx->bvh_gpu_levels = 0; ctx->bvh_resident = false;
+    bool any_uv = false;
+    {
+        std::atomic<bool> found(false);
+        parallel_for(n, 1 << 16, [&](uint64_t lo, uint64_t hi) {
+            for (uint64_t i = lo; i < hi && !found.load(std::memory_order_relaxed); ++i) {
+                const cpbrt_primitive& p = ctx->primitives[i];
+                if (p.shape.kind != CPBRT_SHAPE_TRIANGLE) continue;
+                const cpbrt_triangle& t = ctx->triangles[p.shape.data];
+                if (!(t.uv[0][0] == 0.f && t.uv[0][1] == 0.f && t.uv[1][0] == 1.f && t.uv[1][1] == 0.f && t.uv[2][0] == 1.f && t.uv[2][1] == 1.f)) found.store(true);
+            }
+        });
+        any_uv = found.load();
+    }
+    {
+        const char* e = getenv("CPBRT_BVH_RESIDENT");
+        if (on_gpu && !want_dump && (!e || atoi(e) != 0) && n > (uint32_t)kFlatMaxPrims) {
+            ResidentBuildInput in;
+            in.prims = ctx->primitives.data(); in.n_prims = n;
+            in.tris = ctx->triangles.data(); in.n_tris = (uint32_t)ctx->triangles.size();
+            in.radius = ctx->sphere_radius.data(); in.n_spheres = (uint32_t)ctx->sphere_radius.size();
+            in.d_transforms = ctx->d_transforms.p; in.any_uv = any_uv;
+            ResidentBuildOutput out; std::string why;
+            if (gpu_sah_build_resident(in, min_len, 48, ctx->stream, &out, &why)) {
+                lap("device build");
+                ctx->h2d_bytes += out.h2d_bytes;
+                ctx->d_prims.release(); ctx->d_prim_frame.release(); ctx->d_prim_uv.release(); ctx->d_nodes.release();
+                ctx->d_bvh_block.release(); ctx->d_bvh_block.p = out.d_base; ctx->d_bvh_block.bytes = out.bytes;
+                ctx->d_prims.set_view(out.d_records, 48ull * n);
+                ctx->d_prim_frame.set_view(out.d_frames, 48ull * n);
+                ctx->d_prim_uv.set_view(out.d_uv, any_uv ? 24ull * n : 0);
+                ctx->d_nodes.set_view(out.d_nodes, 64ull * out.n_nodes);
+                ctx->bvh = BvhBuildResult(); ctx->bvh.order.swap(out.order);
+                ctx->bvh_gpu_levels = out.levels; ctx->bvh_resident = true;
+                S.n_nodes = out.n_nodes; S.root_ref = 0; S.root_cnt = 0; memcpy(S.root_box, out.root_box, sizeof S.root_box);
+                S.flat = nullptr; S.flat_n = 0; S.flat_stride = 0; S.flat_items = 0; S.flat_pstride = 0; S.flat_item_mask = 0; S.flat_special_mask = 0;
+                if (int rc = assign_light_slots(ctx, ctx->bvh.order)) return rc;
+                S.prims = (const float4*)ctx->d_prims.p;
+                S.prim_uv = any_uv ? (const float*)ctx->d_prim_uv.p : nullptr;
+                S.prim_frame = (const float4*)ctx->d_prim_frame.p;
+                S.nodes = (const float4*)ctx->d_nodes.p;
+                CU(cudaStreamSynchronize(ctx->stream));
+                lap("light slots");
+                *any_uv_out = any_uv;
+                return CPBRT_OK;
+            }
+            if (timing) fprintf(stderr, "[cpbrt_build_bvh] resident build declined: %s\n", why.c_str());
+            cudaGetLastError();
+        }
+    }
+    // what a previous resident build left behind goes first: the four arrays are about to be uploaded afresh
+    if (ctx->d_bvh_block.p) { ctx->d_prims.release(); ctx->d_prim_frame.release(); ctx->d_prim_uv.release(); ctx->d_nodes.release(); ctx->d_bvh_block.release(); }
     std::vector<BuildBounds> bounds;
     primitive_bounds(ctx->primitives.data(), n, ctx->triangles.data(), ctx->sphere_radius.data(), ctx->transforms.data(), &bounds);
-    // Big scenes: the top of the tree (segments of >= min_len primitives) is built on the device, the
-    // host builder finishes the many small subtrees in parallel; same order and topology either way.
-    // CPBRT_BVH_BUILD=host|gpu and CPBRT_BVH_GPU_MINLEN override the defaults (tests use both).
     {
-        const char* how = getenv("CPBRT_BVH_BUILD");
-        const char* ml = getenv("CPBRT_BVH_GPU_MINLEN");
-        const uint32_t min_len = ml ? (uint32_t)std::max(2, atoi(ml)) : 256u;   // measured flat between 16 and 1024 (tools/bvh_build_bench.py)
-        bool on_gpu = how ? strcmp(how, "gpu") == 0 : n >= (1u << 17);
-        ctx->bvh_gpu_levels = 0;
-        if (on_gpu && n >= min_len && n >= 2) {
+        if (on_gpu) {
             TopPhase top; std::string why;
             lap("primitive bounds");
             if (gpu_sah_top_phase(bounds, min_len, 48, ctx->stream, &top, &why)) {
-                lap("device top levels");
+                lap("device phases");
                 ctx->bvh_gpu_levels = top.levels;
                 finish_sah_bvh(std::move(top), 0, &ctx->bvh);
-                lap("host subtrees");
+                lap("host stitching");
             } else {
                 cudaGetLastError();
                 on_gpu = false;
             }
-        } else on_gpu = false;
+        }
         if (!on_gpu) { build_sah_bvh(bounds, 0, &ctx->bvh); lap("host build"); }
     }
     const BvhBuildResult& R = ctx->bvh;
 
     // primitive records in BVH order
     std::vector<float4> prims(3ull * n);
-    bool any_uv = false;
-    for (uint32_t i = 0; i < n && !any_uv; ++i) {
-        const cpbrt_primitive& p = ctx->primitives[i];
-        if (p.shape.kind == CPBRT_SHAPE_TRIANGLE) {
-            const cpbrt_triangle& t = ctx->triangles[p.shape.data];
-            any_uv = !(t.uv[0][0] == 0.f && t.uv[0][1] == 0.f && t.uv[1][0] == 1.f && t.uv[1][1] == 0.f && t.uv[2][0] == 1.f && t.uv[2][1] == 1.f);
-        }
-    }
     std::vector<float> uvs(any_uv ? 6ull * n : 0);
     std::vector<float4> frames(3ull * n);
     parallel_for(n, 1 << 16, [&](uint64_t slot_lo, uint64_t slot_hi) {
@@ -642,7 +713,6 @@ static int build_bvh_local(cpbrt_ctx* ctx, uint32_t n, bool* any_uv_out) {
     if (int rc = alloc_upload(ctx, ctx->d_prim_frame, frames.data(), frames.size() * sizeof(float4))) return rc;
 
     // Parent nodes in depth-first order, far... the device layout (see scene_dev.cuh)
-    DevScene& S = ctx->scene;
     S.n_nodes = 0; S.root_ref = 0; S.root_cnt = 0; memset(S.root_box, 0, sizeof S.root_box);
     std::vector<float4> nodes;
     if (n > 0) {
@@ -779,18 +849,7 @@ static int build_bvh_local(cpbrt_ctx* ctx, uint32_t n, bool* any_uv_out) {
             }
         }
     }
-    // BVH slot of each area light's primitive (when exactly one primitive carries the light)
-    {
-        std::vector<uint32_t> count(ctx->host_lights.size(), 0);
-        for (auto& l : ctx->host_lights) l.slot = 0xFFFFFFFFu;
-        for (uint32_t slot = 0; slot < n; ++slot) {
-            const cpbrt_primitive& p = ctx->primitives[R.order[slot]];
-            if (p.light >= 0) { ctx->host_lights[p.light].slot = slot; ++count[p.light]; }
-        }
-        for (size_t i = 0; i < count.size(); ++i) if (count[i] != 1) ctx->host_lights[i].slot = 0xFFFFFFFFu;
-        if (int rc = alloc_upload(ctx, ctx->d_lights, ctx->host_lights.data(), ctx->host_lights.size() * sizeof(DevLight))) return rc;
-        S.lights = (const DevLight*)ctx->d_lights.p;
-    }
+    if (int rc = assign_light_slots(ctx, R.order)) return rc;
     S.prims = (const float4*)ctx->d_prims.p;
     S.prim_uv = any_uv ? (const float*)ctx->d_prim_uv.p : nullptr;
     S.prim_frame = n ? (const float4*)ctx->d_prim_frame.p : nullptr;
@@ -812,7 +871,7 @@ int cpbrt_build_bvh(cpbrt_ctx* ctx, uint32_t* prim_order_out, cpbrt_bvh_dump* du
     // every argument / local check happens BEFORE the first collective, and whatever goes wrong on this rank is
     // carried into the exchange as a status instead of an early return (the peers would wait forever)
     int local_rc = 0; bool any_uv = false;
-    if (builds) local_rc = build_bvh_local(ctx, n, &any_uv);
+    if (builds) local_rc = build_bvh_local(ctx, n, &any_uv, dump != nullptr);
     else {
         ctx->bvh = BvhBuildResult(); ctx->bvh_gpu_levels = 0;
         if (dump) local_rc = ctx->fail(CPBRT_ERR_BAD_ARG, "the node dump of a shared build is only available on rank 0");
@@ -1243,6 +1302,23 @@ int cpbrt_render(cpbrt_ctx* ctx, const cpbrt_render_params* params, float* film_
 }
 
 int cpbrt_bvh_gpu_levels(const cpbrt_ctx* ctx) { return ctx ? ctx->bvh_gpu_levels : 0; }
+
+int cpbrt_bvh_device_layout(cpbrt_ctx* ctx, uint64_t node_capacity, uint64_t* n_nodes_out, float* nodes_out, float* records_out, float* frames_out, float* uv_out, int* resident_out) {
+    if (!ctx) return CPBRT_ERR_BAD_CTX;
+    if (!ctx->has_bvh) return ctx->fail(CPBRT_ERR_BAD_CTX, "cpbrt_bvh_device_layout before cpbrt_build_bvh");
+    CU(cudaSetDevice(ctx->device));
+    const DevScene& S = ctx->scene;
+    const uint64_t n = ctx->primitives.size();
+    if (n_nodes_out) *n_nodes_out = S.n_nodes;
+    if (resident_out) *resident_out = ctx->bvh_resident ? 1 : 0;
+    if (nodes_out && node_capacity < S.n_nodes) return ctx->fail(CPBRT_ERR_BAD_ARG, "node capacity %llu < %u Parents", (unsigned long long)node_capacity, S.n_nodes);
+    if (nodes_out && S.n_nodes) CU(cudaMemcpyAsync(nodes_out, S.nodes, 64ull * S.n_nodes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (records_out && n) CU(cudaMemcpyAsync(records_out, S.prims, 48ull * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (frames_out && n) CU(cudaMemcpyAsync(frames_out, S.prim_frame, 48ull * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (uv_out && n && S.prim_uv) CU(cudaMemcpyAsync(uv_out, S.prim_uv, 24ull * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return S.prim_uv ? 1 : 0;
+}
 int cpbrt_bvh_host_segments(const cpbrt_ctx* ctx) { return (ctx && ctx->bvh_gpu_levels > 0) ? (int)ctx->bvh.host_built_segments : -1; }
 
 uint64_t cpbrt_h2d_bytes(const cpbrt_ctx* ctx) { return ctx ? ctx->h2d_bytes : 0; }

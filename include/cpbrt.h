@@ -300,6 +300,21 @@ int cpbrt_bvh_gpu_levels(const cpbrt_ctx* ctx);
  * CPBRT_BVH_SMALL=0): 0 = the whole SAH build ran on the device; -1 = the last build was a pure host build. */
 int cpbrt_bvh_host_segments(const cpbrt_ctx* ctx);
 
+/* Tests / debugging: the traversal layout as it sits in device memory after cpbrt_build_bvh, copied to the host.
+ *   nodes_out    16 floats per Parent: {L.min.xyz L.max.x}{L.max.yz R.min.xy}{R.min.z R.max.xyz}
+ *                {left ref, right ref, left count | axis << 30, right count} (the last four are uint32 bit patterns;
+ *                count 0 = the ref is a Parent index, otherwise a Leaf of `count` primitives starting at slot `ref`;
+ *                a Leaf's box is the union of its primitives' bounds).  Parent 0 is the root.
+ *   records_out  12 floats per primitive in BVH order (triangle vertices or sphere radius, upload index, meta, source)
+ *   frames_out   12 floats per primitive (unit normal and the shading frame BSDF::new derives from it)
+ *   uv_out       6 floats per primitive, only written when the scene carries non-default uv (return value 1)
+ * Any output may be NULL; *n_nodes_out receives the Parent count (call once with NULL arrays to size them),
+ * *resident_out 1 when the last build ran on the device from bounds to layout.  Parents are numbered differently by
+ * the device and the host builders (same tree): compare by walking from Parent 0.
+ * Returns 0 / 1 (uv present) or a negative CPBRT_ERR_*. */
+int cpbrt_bvh_device_layout(cpbrt_ctx* ctx, uint64_t node_capacity, uint64_t* n_nodes_out, float* nodes_out,
+                            float* records_out, float* frames_out, float* uv_out, int* resident_out);
+
 /* Bytes this context has copied host -> device since cpbrt_create (counted where the copies are issued):
  * scene arrays, sampler tables, BVH layout, ray batches.  Bookkeeping for the end-to-end measurement. */
 uint64_t cpbrt_h2d_bytes(const cpbrt_ctx* ctx);

@@ -150,6 +150,81 @@ def _random_soup_scene(cpbrt, n_tris, seed, grid=False):
     return cpbrt.Scene.parse(text)
 
 
+def _canonical_layout(nodes):
+    """The device Parent records walked breadth-first from Parent 0, children left before right: a numbering-free
+    description of the tree (boxes, split axes, Leaf slot ranges) -- builders that number Parents differently
+    must agree on it bit for bit."""
+    w = nodes.view(np.uint32)
+    frontier = np.zeros(1, np.int64) if len(nodes) else np.zeros(0, np.int64)
+    boxes, axes, leaves, visited = [], [], [], 0
+    while len(frontier):
+        rows = w[frontier]
+        visited += len(frontier)
+        lref, rref, lw, rcnt = rows[:, 12], rows[:, 13], rows[:, 14], rows[:, 15]
+        lcnt, axis = lw & 0x3FFFFFFF, lw >> 30
+        boxes.append(rows[:, :12]); axes.append(axis)
+        refs = np.stack([lref, rref], 1).ravel(); cnts = np.stack([lcnt, rcnt], 1).ravel()
+        leaves.append(np.stack([np.where(cnts > 0, refs, 0xFFFFFFFF), cnts], 1))
+        frontier = refs[cnts == 0].astype(np.int64)
+    assert visited == len(nodes), "unreachable or shared Parents"
+    return np.concatenate(boxes), np.concatenate(axes), np.concatenate(leaves)
+
+
+def _sphere_cloud_scene(cpbrt, n, seed):
+    """Transformed spheres and triangles mixed: Primitive::bound through TransformShape on the device."""
+    rng = np.random.default_rng(seed)
+    parts = ['Camera "perspective" "float fov" [50]\nSampler "halton" "integer pixelsamples" [1]\n'
+             'Film "image" "integer xresolution" [32] "integer yresolution" [32]\nIntegrator "path"\nWorldBegin\n'
+             'AttributeBegin\nAreaLightSource "diffuse" "rgb L" [5 5 5]\nTranslate 0 4 6\nShape "sphere" "float radius" [0.5]\nAttributeEnd\nMaterial "matte"\n']
+    for i in range(n):
+        x, y, z = (rng.random(3) * [8, 6, 8] + [-4, -3, 3]).tolist()
+        if i % 3 == 0:
+            parts.append('AttributeBegin\nTranslate %r %r %r\nRotate %r 0 1 0\nScale 1 %r 1\nShape "sphere" "float radius" [%r]\nAttributeEnd\n' % (x, y, z, float(rng.random() * 90), float(0.5 + rng.random()), float(0.05 + 0.1 * rng.random())))
+        else:
+            P = (np.array([x, y, z]) + rng.normal(scale=0.15, size=(3, 3))).astype(np.float32)
+            parts.append('Shape "trianglemesh" "integer indices" [0 1 2] "point P" [%s]\n' % " ".join(repr(float(v)) for v in P.ravel()))
+    parts.append('WorldEnd\n')
+    return cpbrt.Scene.parse("".join(parts))
+
+
+@pytest.mark.parametrize("min_len", [2, 7, 64, 256])
+def test_device_resident_build_equals_host_layout(cpbrt, oracle, mesh, monkeypatch, min_len):
+    """SURVEY 8f.2, finished: without a node dump, big scenes are built on the device from primitive bounds to the
+    traversal layout (bvh_build_gpu.cu, gpu_sah_build_resident) and only the primitive order comes back.  The
+    layout in device memory -- Parent boxes, axes, Leaf ranges walked from the root, the 48-byte primitive
+    records, shading frames, uv -- must equal the one the host builder + host layout code produce (which
+    test_bvh_order_and_nodes_bit_exact ties to the oracle), and the order must equal the oracle's."""
+    scenes = [mesh[0], _random_soup_scene(cpbrt, 3000, 1), _random_soup_scene(cpbrt, 5000, 2, grid=True), _sphere_cloud_scene(cpbrt, 900, 3)]
+    monkeypatch.setenv("CPBRT_BVH_GPU_MINLEN", str(min_len))
+    for scene in scenes:
+        monkeypatch.setenv("CPBRT_BVH_BUILD", "host")
+        h = cpbrt.Renderer(0); h.upload(scene); order_h = h.build_bvh(); lay_h = h.bvh_device_layout()
+        assert not lay_h["resident"]
+        monkeypatch.setenv("CPBRT_BVH_BUILD", "gpu")
+        r = cpbrt.Renderer(0); r.upload(scene); order_r = r.build_bvh(); lay_r = r.bvh_device_layout()
+        assert lay_r["resident"], "the device-resident build declined"
+        assert r.bvh_host_segments() == 0
+        assert np.array_equal(order_r, order_h)
+        assert np.array_equal(order_r, oracle.OracleWorld(scene).bvh_order())
+        assert lay_r["nodes"].shape == lay_h["nodes"].shape
+        for a, b, what in zip(_canonical_layout(lay_r["nodes"]), _canonical_layout(lay_h["nodes"]), ("boxes", "axes", "leaves")):
+            assert np.array_equal(a, b), what
+        for k in ("records", "frames"):
+            assert np.array_equal(lay_r[k].view(np.uint32), lay_h[k].view(np.uint32)), k
+        assert (lay_r["uv"] is None) == (lay_h["uv"] is None)
+        if lay_r["uv"] is not None:
+            assert np.array_equal(lay_r["uv"].view(np.uint32), lay_h["uv"].view(np.uint32))
+        fr, _ = r.render(); fh, _ = h.render()
+        assert np.array_equal(fr.view(np.uint32), fh.view(np.uint32))
+        # asking for the node dump afterwards still works (hybrid path) and agrees
+        _, nodes = r.build_bvh(want_nodes=True)
+        assert not r.bvh_device_layout()["resident"]
+        _, nodes_h = h.build_bvh(want_nodes=True)
+        for k in ("is_leaf", "axis", "a", "b", "bound"):
+            assert np.array_equal(nodes[k], nodes_h[k]), k
+        r.close(); h.close()
+
+
 @pytest.mark.parametrize("small_phase", ["1", "0"])
 @pytest.mark.parametrize("min_len", [2, 7, 64, 256, 1000])
 def test_gpu_bvh_top_phase_equals_host_build(cpbrt, oracle, cornell, mesh, monkeypatch, min_len, small_phase):
@@ -345,6 +420,28 @@ def test_full_path_image(cornell, mesh):
         assert gs.rays_closest_traced < gs.rays_closest
         assert abs(gs.rays_any - os_["rays_any"]) <= 2e-3 * os_["rays_any"]
         assert gs.nan_dropped == os_["nan_dropped"]
+
+
+def test_stream_schedules_are_race_free(cpbrt, make_scene, monkeypatch):
+    """compute-sanitizer is closed on this GPU pool, so the stream schedule is checked by its results: the bounce
+    loop overlaps stages on three streams per lane and up to three pass lanes on their own streams; the profiled
+    schedule runs the same kernels back to back on one stream.  Every combination -- lanes 1 / 2 / 3, flat / loop /
+    vote traversal, pass sizes that leave a ragged last pass -- must give the serial schedule's film bit for bit,
+    five times in a row (a missed event dependency shows up as a differing or non-repeating film)."""
+    scene = make_scene("cornel_box.pbrt", xres=96, yres=96, spp=7)
+    r = cpbrt.Renderer(0); r.upload(scene); r.build_bvh()
+    for sched in ("flat", "loop", "vote"):
+        monkeypatch.setenv("CPBRT_SCHEDULE", sched)
+        monkeypatch.setenv("CPBRT_LANES", "1")
+        serial, st = r.render(profile_stages=True, samples_per_pass=2)
+        assert st.kernel_launches > 0
+        for lanes in ("1", "2", "3"):
+            monkeypatch.setenv("CPBRT_LANES", lanes)
+            for spass in (1, 2, 3):
+                for rep in range(5 if spass == 2 else 1):
+                    film, _ = r.render(samples_per_pass=spass)
+                    assert np.array_equal(film.view(np.uint32), serial.view(np.uint32)), (sched, lanes, spass, rep)
+    r.close()
 
 
 def test_directlighting_scene(spheres):

@@ -1,6 +1,8 @@
 #!/usr/bin/env python3
-"""Exact SAH build time, host-only vs device top levels + host finish (cpbrt_build_bvh), on the
-synthetic height fields.  One JSON line per size; both builds must give the same primitive order.
+"""Exact SAH build time (cpbrt_build_bvh) on the synthetic height fields: host only, the device phases with the
+pieces stitched on the host (CPBRT_BVH_RESIDENT=0), and the device-resident build (bounds to traversal layout on the
+GPU, only the primitive order comes back).  One JSON line per size; all builds must give the same primitive order
+and the resident and host layouts must describe the same tree.
 
     python tools/bvh_build_bench.py [--sizes 1000x500,2500x2000] [--min-lens 4096]
 """
@@ -30,7 +32,15 @@ def main():
             os.environ["CPBRT_BVH_GPU_MINLEN"] = ml
             r.build_bvh()          # warm-up (CUB first-use, allocations)
             t0 = time.perf_counter(); order = r.build_bvh(); dt = time.perf_counter() - t0
-            row["gpu_minlen_%s" % ml] = dict(seconds=dt, device_levels=r.bvh_gpu_levels(), same_order=bool(np.array_equal(order, ref)))
+            resident = r.bvh_device_layout()["resident"] if int(scene.desc.n_primitives) <= 2000000 else None
+            row["gpu_minlen_%s" % ml] = dict(seconds=dt, device_levels=r.bvh_gpu_levels(), host_segments=r.bvh_host_segments(), resident=resident,
+                                             same_order=bool(np.array_equal(order, ref)))
+            os.environ["CPBRT_BVH_RESIDENT"] = "0"
+            r.build_bvh()
+            t0 = time.perf_counter(); order = r.build_bvh(); dt = time.perf_counter() - t0
+            row["gpu_minlen_%s_hybrid" % ml] = dict(seconds=dt, device_levels=r.bvh_gpu_levels(), host_segments=r.bvh_host_segments(),
+                                                    same_order=bool(np.array_equal(order, ref)))
+            os.environ.pop("CPBRT_BVH_RESIDENT")
         os.environ.pop("CPBRT_BVH_BUILD", None); os.environ.pop("CPBRT_BVH_GPU_MINLEN", None)
         print(json.dumps(row), flush=True)
         r.close()
