@@ -192,13 +192,22 @@ int grid_for(const cpbrt_ctx* ctx, int blocks_per_sm) { return ctx->sm_count * b
 static constexpr uint32_t kVoteMinPrims = 256;    // measured: equal at 264 primitives, vote +12% at 4k, +23% at 40k, +32% at 1M (tools/schedule_crossover.py)
 // Scenes of at most kFlatMaxPrims primitives skip the tree walk altogether (flat_trace.cuh).
 // CPBRT_SCHEDULE=flat|loop|vote overrides ("flat" only where the tables exist).
+// Tiny scenes: SCHED_FUSED additionally traces shadow and continuation rays inside the shading kernels (cpbrt_render
+// only; the batch entry points treat it as SCHED_FLAT).  Measured and NOT the default: same film bit for bit, but the
+// Cornell box drops from 829 to 685-735 Msamples/s (profiles/r02_fused_sweep.txt) -- the searches run at the warp's
+// full instruction count whenever any lane has a ray, while the queues hand the separate trace kernels full warps.
+// CPBRT_SCHEDULE=flat|fused|loop|vote overrides.
+#ifndef CPBRT_DEFAULT_TINY_SCHEDULE
+#define CPBRT_DEFAULT_TINY_SCHEDULE SCHED_FLAT
+#endif
 int trace_schedule(const cpbrt_ctx* ctx) {
     const char* e = getenv("CPBRT_SCHEDULE");
     const bool can_flat = ctx->scene.flat != nullptr;
     if (e && strcmp(e, "vote") == 0) return SCHED_VOTE;
     if (e && strcmp(e, "loop") == 0) return SCHED_LOOP;
     if (e && strcmp(e, "flat") == 0 && can_flat) return SCHED_FLAT;
-    if (can_flat) return SCHED_FLAT;
+    if (e && strcmp(e, "fused") == 0 && can_flat) return SCHED_FUSED;
+    if (can_flat) return CPBRT_DEFAULT_TINY_SCHEDULE;
     return ctx->scene.n_prims >= kVoteMinPrims ? SCHED_VOTE : SCHED_LOOP;
 }
 size_t flat_bytes(const cpbrt_ctx* ctx) { return flat_smem_bytes(ctx->scene.flat_n, ctx->scene.flat_stride, ctx->scene.flat_pstride); }
@@ -441,22 +450,51 @@ int cpbrt_upload_scene(cpbrt_ctx* ctx, const cpbrt_scene_desc* d) {
         std::vector<uint64_t> magic(CPBRT_N_PRIMES);
         for (int i = 0; i < CPBRT_N_PRIMES; ++i) magic[i] = 0xFFFFFFFFFFFFFFFFull / primes[i] + 1;   // floor(2^64/p)+1 (p never divides 2^64)
         if (int rc = alloc_upload(ctx, ctx->d_magic, magic.data(), magic.size() * 8)) return rc;
-        if (int rc = alloc_upload(ctx, ctx->d_perm, d->sampler.permutation, (size_t)CPBRT_PERM_TABLE_LEN * 2)) return rc;
         // Per-dimension constants of scrambled_radical_inverse (halton.rs:56-64), evaluated once here with the
         // reference's f32 operations instead of per sample on the device:
         //   tail[d]       = inv_base * perm_d(0) / (1 - inv_base)        (the infinite tail of permuted zero digits)
         //   inv_pow[d][c] = 1 / (base^c as f32)                           (usize pow, wrapping like release Rust)
+        // and the digit-group tables (scene_dev.cuh, DevHaltonDim): behind the caller's permutation table, for every
+        // dimension whose base^2 still fits kHaltonGroupMax, the permuted-and-reversed strings of 1, 2, ... g digits.
         {
+            uint32_t group_max = 1024;      // measured: tools/variant_sweep.py / DESIGN.md 4.2
+            if (const char* e = getenv("CPBRT_HALTON_GROUP")) group_max = (uint32_t)std::max(2, std::min(65536, atoi(e)));
+            std::vector<uint16_t> table;        // what follows the caller's CPBRT_PERM_TABLE_LEN entries on the device
+            const uint32_t table0 = CPBRT_PERM_TABLE_LEN;
             std::vector<DevHaltonDim> dims(CPBRT_N_PRIMES);
             std::vector<float> inv_pow((size_t)CPBRT_N_PRIMES * kHaltonMaxDigits);
             for (int i = 0; i < CPBRT_N_PRIMES; ++i) {
-                const float inv_base = 1.f / (float)primes[i];
-                dims[i].magic = magic[i]; dims[i].base = primes[i]; dims[i].primsum = sums[i];
+                const uint32_t b = primes[i];
+                const float inv_base = 1.f / (float)b;
+                memset(&dims[i], 0, sizeof dims[i]);
+                dims[i].magic = magic[i]; dims[i].base = b; dims[i].primsum = sums[i];
                 dims[i].tail = inv_base * (float)d->sampler.permutation[sums[i]] / (1.f - inv_base);
-                dims[i].pad[0] = dims[i].pad[1] = dims[i].pad[2] = 0;
+                uint32_t g = 1, G = b;
+                while ((uint64_t)G * b <= group_max) { G *= b; ++g; }
+                dims[i].group = G; dims[i].group_digits = g; dims[i].group_magic = 0xFFFFFFFFFFFFFFFFull / G + 1;
+                if (g == 1) { dims[i].group_off = sums[i]; dims[i].full_off = sums[i]; }
+                else {
+                    dims[i].group_off = table0 + (uint32_t)table.size();
+                    uint32_t pw = 1;
+                    for (uint32_t j = 1; j <= g; ++j) {
+                        pw *= b;
+                        if (j == g) dims[i].full_off = table0 + (uint32_t)table.size();
+                        for (uint32_t x = 0; x < pw; ++x) {
+                            uint32_t v = 0, t = x;
+                            for (uint32_t c = 0; c < j; ++c) { v = v * b + d->sampler.permutation[sums[i] + t % b]; t /= b; }
+                            table.push_back((uint16_t)v);
+                        }
+                    }
+                }
                 uint64_t pw = 1;
                 for (int c = 0; c < kHaltonMaxDigits; ++c) { inv_pow[(size_t)i * kHaltonMaxDigits + c] = 1.f / (float)pw; pw *= primes[i]; }
             }
+            // the caller's table goes up as it is (7 MB: no host copy), the group tables behind it
+            const size_t perm_bytes = (size_t)table0 * 2, total_bytes = perm_bytes + table.size() * 2;
+            if (ctx->d_perm.bytes != total_bytes) { ctx->d_perm.release(); CU(cudaMalloc(&ctx->d_perm.p, total_bytes)); ctx->d_perm.bytes = total_bytes; }
+            CU(cudaMemcpyAsync(ctx->d_perm.p, d->sampler.permutation, perm_bytes, cudaMemcpyHostToDevice, ctx->stream));
+            if (!table.empty()) CU(cudaMemcpyAsync((char*)ctx->d_perm.p + perm_bytes, table.data(), table.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
+            ctx->h2d_bytes += total_bytes;
             if (int rc = alloc_upload(ctx, ctx->d_halton_dims, dims.data(), dims.size() * sizeof(DevHaltonDim))) return rc;
             if (int rc = alloc_upload(ctx, ctx->d_halton_inv_pow, inv_pow.data(), inv_pow.size() * 4)) return rc;
         }
@@ -925,7 +963,7 @@ int cpbrt_trace_closest(cpbrt_ctx* ctx, const cpbrt_ray* rays, uint64_t n, cpbrt
     slow_paths_reset(ctx->stream);
     cudaEventRecord(e0, ctx->stream);
     if (n) {
-        const int sched = trace_schedule(ctx);
+        const int sched = trace_schedule(ctx) == SCHED_FUSED ? SCHED_FLAT : trace_schedule(ctx);
         if (count_own && sched == SCHED_VOTE) k_batch_closest<4><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, d_rays, n, d_hits, counters, ctx->d_totals);
         else if (count_own && sched == SCHED_LOOP) k_batch_closest<5><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, d_rays, n, d_hits, counters, ctx->d_totals);
         else if (count) k_batch_closest<1><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, d_rays, n, d_hits, counters, ctx->d_totals);
@@ -971,7 +1009,7 @@ int cpbrt_trace_any(cpbrt_ctx* ctx, const cpbrt_ray* rays, uint64_t n, uint8_t* 
     slow_paths_reset(ctx->stream);
     cudaEventRecord(e0, ctx->stream);
     if (n) {
-        const int sched = trace_schedule(ctx);
+        const int sched = trace_schedule(ctx) == SCHED_FUSED ? SCHED_FLAT : trace_schedule(ctx);
         if (count_own && sched == SCHED_VOTE) k_batch_any<4><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, d_rays, n, d_out, counters, ctx->d_totals);
         else if (count_own && sched == SCHED_LOOP) k_batch_any<5><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, d_rays, n, d_out, counters, ctx->d_totals);
         else if (count) k_batch_any<1><<<grid_for(ctx, 8), 128, 0, ctx->stream>>>(ctx->scene, d_rays, n, d_out, counters, ctx->d_totals);
@@ -1075,7 +1113,7 @@ static int ensure_wavefront(cpbrt_ctx* ctx, uint32_t n_paths, int n_lanes) {
             P.mis_o.base = (float4*)p; P.mis_d.base = (float4*)p + 1; p += rec;
             P.mis_A.base = (float4*)p; P.mis_p.base = (float4*)p + 1; p += rec;
             P.nee_light.base = (float4*)p; P.nee_bsdf.base = (float4*)p + 1; p += rec;
-            P.beta_prev.base = (float4*)p; P.smp_index.base = p; P.smp_dim.base = p; P.hit_slot.base = p;
+            P.beta_prev.base = (float4*)p; P.state2.base = (float4*)p + 1; P.smp_index.base = p; P.smp_dim.base = p; P.hit_slot.base = p;
             uint32_t* q = (uint32_t*)L.d_queues.p;
             L.Q.closest[0] = q; q += 2 * (size_t)n_paths; L.Q.closest[1] = q; q += 2 * (size_t)n_paths; L.Q.shadow = q; q += n_paths;
             for (int k = 0; k < SHADE_KINDS; ++k) { L.Q.shade[k] = q; q += n_paths; }
@@ -1148,7 +1186,8 @@ int cpbrt_render(cpbrt_ctx* ctx, const cpbrt_render_params* params, float* film_
     cudaEventRecord(e0, st);
     uint64_t launches = 0, trace_launches = 0;
     const int sched = trace_schedule(ctx);
-    const bool vote = sched == SCHED_VOTE, flat = sched == SCHED_FLAT;
+    const bool fused = sched == SCHED_FUSED && !(ctx->recursive_direct && !rp.first_hit_only);
+    const bool vote = sched == SCHED_VOTE, flat = sched == SCHED_FLAT || sched == SCHED_FUSED;
     const size_t flat_sm = flat ? flat_bytes(ctx) : 0;
     // blocks per SM of the long kernels: what their launch bounds allow by default; CPBRT_GRID_TRACE / CPBRT_GRID_MATTE
     // shrink the grids (tuning: how two lanes share an SM, tools/variant_sweep.py)
@@ -1208,12 +1247,14 @@ int cpbrt_render(cpbrt_ctx* ctx, const cpbrt_render_params* params, float* film_
             ++trace_launches; ++launches;
             span_end();
             if (!prof) { cudaEventRecord(eK1, sm); cudaStreamWaitEvent(sa, ePrev, 0); }
-            span_begin(2);
-            if (flat) k_trace_shadow<SCHED_FLAT><<<g_shadow, 128, flat_sm, sa>>>(S, P, Q, T);
-            else if (vote) k_trace_shadow<SCHED_VOTE><<<g_shadow, 128, 0, sa>>>(S, P, Q, T);
-            else k_trace_shadow<SCHED_LOOP><<<g_shadow, 128, 0, sa>>>(S, P, Q, T);
-            ++launches;
-            span_end();
+            if (!fused) {      // fused: shadow rays are traced inside the shading kernels
+                span_begin(2);
+                if (flat) k_trace_shadow<SCHED_FLAT><<<g_shadow, 128, flat_sm, sa>>>(S, P, Q, T);
+                else if (vote) k_trace_shadow<SCHED_VOTE><<<g_shadow, 128, 0, sa>>>(S, P, Q, T);
+                else k_trace_shadow<SCHED_LOOP><<<g_shadow, 128, 0, sa>>>(S, P, Q, T);
+                ++launches;
+                span_end();
+            }
             if (!prof) cudaStreamWaitEvent(sa, eK1, 0);
             k_queue_reset<<<1, 32, 0, sa>>>(Q, cur, 0, T); ++launches;
             if (!prof) cudaEventRecord(eK3, sa);
@@ -1221,11 +1262,18 @@ int cpbrt_render(cpbrt_ctx* ctx, const cpbrt_render_params* params, float* film_
             k_classify<<<g_pix, 256, 0, sm>>>(P, Q, Sn * npix); ++launches;
             if (!prof) { cudaEventRecord(eK4, sm); cudaStreamWaitEvent(sb, eK4, 0); cudaStreamWaitEvent(sb, eK3, 0); }
             k_shade_terminal<<<g_shade, 128, 0, sb>>>(S, P, Q); ++launches;
-            k_shade<SHADE_MIRROR><<<g_shade, 128, 0, sb>>>(S, P, Q, next, T); ++launches;
-            k_shade<SHADE_GLASS><<<g_shade, 128, 0, sb>>>(S, P, Q, next, T); ++launches;
-            if (ctx->has_general_materials) { k_shade<SHADE_GENERAL><<<grid_for(ctx, ShadeBlocks<SHADE_GENERAL>::value), 128, 0, sb>>>(S, P, Q, next, T); ++launches; }
+            if (fused) {
+                k_shade<SHADE_MIRROR, true><<<grid_for(ctx, ShadeBlocksFused<SHADE_MIRROR>::value), 128, flat_sm, sb>>>(S, P, Q, next, T); ++launches;
+                k_shade<SHADE_GLASS, true><<<grid_for(ctx, ShadeBlocksFused<SHADE_GLASS>::value), 128, flat_sm, sb>>>(S, P, Q, next, T); ++launches;
+                if (ctx->has_general_materials) { k_shade<SHADE_GENERAL, true><<<grid_for(ctx, ShadeBlocksFused<SHADE_GENERAL>::value), 128, flat_sm, sb>>>(S, P, Q, next, T); ++launches; }
+            } else {
+                k_shade<SHADE_MIRROR, false><<<g_shade, 128, 0, sb>>>(S, P, Q, next, T); ++launches;
+                k_shade<SHADE_GLASS, false><<<g_shade, 128, 0, sb>>>(S, P, Q, next, T); ++launches;
+                if (ctx->has_general_materials) { k_shade<SHADE_GENERAL, false><<<grid_for(ctx, ShadeBlocks<SHADE_GENERAL>::value), 128, 0, sb>>>(S, P, Q, next, T); ++launches; }
+            }
             if (!prof) { cudaEventRecord(eS, sb); cudaStreamWaitEvent(sm, eK3, 0); }
-            k_shade<SHADE_MATTE><<<g_matte, 128, 0, sm>>>(S, P, Q, next, T); ++launches;
+            if (fused) { k_shade<SHADE_MATTE, true><<<grid_for(ctx, env_blocks("CPBRT_GRID_MATTE", ShadeBlocksFused<SHADE_MATTE>::value)), 128, flat_sm, sm>>>(S, P, Q, next, T); ++launches; }
+            else { k_shade<SHADE_MATTE, false><<<g_matte, 128, 0, sm>>>(S, P, Q, next, T); ++launches; }
             span_end();
             if (!prof) cudaStreamWaitEvent(sm, eS, 0);
             k_queue_reset<<<1, 32, 0, sm>>>(Q, cur, 1, T); ++launches;

@@ -34,32 +34,44 @@ CP_DEV float radical_inverse(uint64_t x, uint32_t base) {
     return inv_base_n * __ull2float_rn(acc);
 }
 
-// scrambled_radical_inverse (halton.rs:56-64).  While the running quotient fits 32 bits the
-// division by the prime is one 64-bit multiply-high with floor(2^64/p)+1, which is exact for
-// x < 2^32 and p < 2^13 (error term x / 2^64 < 1 / p); same quotients, same digits.
+// scrambled_radical_inverse (halton.rs:56-64).  The reference peels one digit per round:
+//     reversed = reversed * base + perm[a % base];  a /= base;      while a != 0
+// Here, once the running quotient fits 32 bits, a round takes a whole GROUP of g digits (DevHaltonDim): with
+// G = base^g, reversed * G + T_g[a % G] is what g of the reference's rounds produce when all g digits are still to
+// come (a >= G), T_g[r] being the g digits of r permuted and reversed.  The last, partial group (a < G: j <= g digits
+// left) uses the table of j-digit strings.  Divisions by G are one 64-bit multiply-high with floor(2^64/G)+1,
+// exact for a < 2^32.  Same integer accumulator and digit count as the reference (cpbrt_halton's parity test
+// against the oracle, which keeps the one-digit loop, covers 200 000 values incl. indices beyond 2^32).
+CP_DEV void halton_finish_chain(const DevSampler& S, const float4 r0, const float4 r1, const float4 r2, uint32_t xs, uint64_t& acc, uint32_t& cnt) {
+    const uint32_t G = __float_as_uint(r1.y), gd = __float_as_uint(r2.z), full_off = __float_as_uint(r2.y);
+    const uint64_t gm = ((uint64_t)__float_as_uint(r1.w) << 32) | __float_as_uint(r1.z);
+    while (xs >= G) {
+        const uint32_t q = (uint32_t)__umul64hi((uint64_t)xs, gm);
+        acc = acc * G + __ldg(&S.permutation[full_off + (xs - q * G)]); cnt += gd; xs = q;
+    }
+    if (xs != 0) {
+        const uint32_t base = __float_as_uint(r0.z);
+        uint32_t j = 1, pw = base, o = __float_as_uint(r2.x);
+        while (xs >= pw) { o += pw; ++j; pw *= base; }
+        acc = acc * pw + __ldg(&S.permutation[o + xs]); cnt += j;
+    }
+}
 CP_DEV float scrambled_radical_inverse(const DevSampler& S, uint64_t x, uint32_t dim) {
     const float4* rec = reinterpret_cast<const float4*>(S.dims + dim);
-    const float4 r0 = __ldg(rec), r1 = __ldg(rec + 1);
-    const uint64_t magic = ((uint64_t)__float_as_uint(r0.y) << 32) | __float_as_uint(r0.x);
+    const float4 r0 = __ldg(rec), r1 = __ldg(rec + 1), r2 = __ldg(rec + 2);
     const uint32_t base = __float_as_uint(r0.z);
     const uint16_t* __restrict__ pm = S.permutation + __float_as_uint(r0.w);
-    const float tail = r1.x;
     uint64_t acc = 0; uint32_t count = 0;
     while ((x >> 32) != 0) { uint64_t q = x / base; uint32_t digit = (uint32_t)(x - q * base); acc = acc * base + __ldg(&pm[digit]); ++count; x = q; }
-    uint32_t xs = (uint32_t)x;
-    while (xs != 0) {
-        const uint32_t q = (uint32_t)__umul64hi((uint64_t)xs, magic);
-        const uint32_t digit = xs - q * base;
-        acc = acc * base + __ldg(&pm[digit]); ++count; xs = q;
-    }
+    halton_finish_chain(S, r0, r1, r2, (uint32_t)x, acc, count);
     // inv_base_n and the tail of permuted zero digits were evaluated on the host with the same f32 operations
     const float inv_base_n = __ldg(&S.inv_pow[dim * kHaltonMaxDigits + count]);
-    return inv_base_n * (__ull2float_rn(acc) + tail);
+    return inv_base_n * (__ull2float_rn(acc) + r1.x);
 }
 
 // N consecutive dimensions of the same index at once.  The digit loops of different primes are
-// independent dependency chains (multiply-high -> digit -> table look-up -> accumulate); one at a
-// time each iteration waits out its own latencies, and the shading kernels have too few resident
+// independent dependency chains (multiply-high -> digits -> table look-up -> accumulate); one at a
+// time each round waits out its own latencies, and the shading kernels have too few resident
 // warps to cover them.  Walking N chains in one loop lets each chain's latency hide behind the
 // others' instructions.  Same quotients, digits and accumulators as N calls of
 // scrambled_radical_inverse (matte shading stage: -3.5 % with pairs).
@@ -68,46 +80,50 @@ CP_DEV float scrambled_radical_inverse(const DevSampler& S, uint64_t x, uint32_t
 #endif
 template <int N>
 CP_DEV void scrambled_radical_inverse_n(const DevSampler& S, uint64_t x, uint32_t dim, float* out) {
-    uint64_t magic[N], acc[N]; uint32_t base[N], cnt[N], xs[N], off[N]; float tail[N];
+    uint64_t gm[N], acc[N]; uint32_t G[N], fo[N], xs[N], cnt[N];
 #pragma unroll
     for (int k = 0; k < N; ++k) {
         const float4* rec = reinterpret_cast<const float4*>(S.dims + dim + k);
-        const float4 r0 = __ldg(rec), r1 = __ldg(rec + 1);
-        magic[k] = ((uint64_t)__float_as_uint(r0.y) << 32) | __float_as_uint(r0.x);
-        base[k] = __float_as_uint(r0.z); off[k] = __float_as_uint(r0.w); tail[k] = r1.x;
+        const float4 r1 = __ldg(rec + 1), r2 = __ldg(rec + 2);
+        G[k] = __float_as_uint(r1.y); gm[k] = ((uint64_t)__float_as_uint(r1.w) << 32) | __float_as_uint(r1.z);
+        fo[k] = __float_as_uint(r2.y);
         acc[k] = 0; cnt[k] = 0;
     }
     if ((x >> 32) != 0) {      // the quotients of a 64-bit index differ per prime: each chain on its own until it fits 32 bits
 #pragma unroll
         for (int k = 0; k < N; ++k) {
+            const float4 r0 = __ldg(reinterpret_cast<const float4*>(S.dims + dim + k));
+            const uint32_t base = __float_as_uint(r0.z), off = __float_as_uint(r0.w);
             uint64_t xk = x;
-            while ((xk >> 32) != 0) { const uint64_t q = xk / base[k]; const uint32_t digit = (uint32_t)(xk - q * base[k]); acc[k] = acc[k] * base[k] + __ldg(&S.permutation[off[k] + digit]); ++cnt[k]; xk = q; }
+            while ((xk >> 32) != 0) { const uint64_t q = xk / base; const uint32_t digit = (uint32_t)(xk - q * base); acc[k] = acc[k] * base + __ldg(&S.permutation[off + digit]); ++cnt[k]; xk = q; }
             xs[k] = (uint32_t)xk;
         }
     } else {
 #pragma unroll
         for (int k = 0; k < N; ++k) xs[k] = (uint32_t)x;
     }
+    uint32_t rounds = 0;       // full groups taken by every chain in lock step
     for (;;) {
         bool all = true;
 #pragma unroll
-        for (int k = 0; k < N; ++k) all = all && xs[k] != 0;
+        for (int k = 0; k < N; ++k) all = all && xs[k] >= G[k];
         if (!all) break;
         uint32_t q[N], pv[N];
 #pragma unroll
-        for (int k = 0; k < N; ++k) q[k] = (uint32_t)__umul64hi((uint64_t)xs[k], magic[k]);
+        for (int k = 0; k < N; ++k) q[k] = (uint32_t)__umul64hi((uint64_t)xs[k], gm[k]);
 #pragma unroll
-        for (int k = 0; k < N; ++k) pv[k] = __ldg(&S.permutation[off[k] + (xs[k] - q[k] * base[k])]);
+        for (int k = 0; k < N; ++k) pv[k] = __ldg(&S.permutation[fo[k] + (xs[k] - q[k] * G[k])]);
 #pragma unroll
-        for (int k = 0; k < N; ++k) { acc[k] = acc[k] * base[k] + pv[k]; ++cnt[k]; xs[k] = q[k]; }
+        for (int k = 0; k < N; ++k) { acc[k] = acc[k] * G[k] + pv[k]; xs[k] = q[k]; }
+        ++rounds;
     }
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-        while (xs[k] != 0) {
-            const uint32_t q = (uint32_t)__umul64hi((uint64_t)xs[k], magic[k]);
-            acc[k] = acc[k] * base[k] + __ldg(&S.permutation[off[k] + (xs[k] - q * base[k])]); ++cnt[k]; xs[k] = q;
-        }
-        out[k] = __ldg(&S.inv_pow[(dim + k) * kHaltonMaxDigits + cnt[k]]) * (__ull2float_rn(acc[k]) + tail[k]);
+        const float4* rec = reinterpret_cast<const float4*>(S.dims + dim + k);
+        const float4 r0 = __ldg(rec), r1 = __ldg(rec + 1), r2 = __ldg(rec + 2);
+        cnt[k] += rounds * __float_as_uint(r2.z);
+        halton_finish_chain(S, r0, r1, r2, xs[k], acc[k], cnt[k]);
+        out[k] = __ldg(&S.inv_pow[(dim + k) * kHaltonMaxDigits + cnt[k]]) * (__ull2float_rn(acc[k]) + r1.x);
     }
 }
 

@@ -55,14 +55,23 @@ struct DevCamera {
     float lens_radius, focal_distance;
 };
 
-// one 32-byte record per Halton dimension (two 16-byte loads): everything scrambled_radical_inverse needs
+// one 48-byte record per Halton dimension (three 16-byte loads): everything scrambled_radical_inverse needs.
+// Digits are consumed in GROUPS of `group_digits` (as many as keep base^digits <= kHaltonGroupMax): one division by
+// `group` = base^group_digits and one look-up in a table of already reversed and permuted digit strings replace
+// group_digits rounds of divide / look up / multiply-add.  Integer arithmetic, so the accumulator is the same.
 struct DevHaltonDim {
-    uint64_t magic;      // floor(2^64 / base) + 1: x / base == umul64hi(x, magic) exactly for x < 2^32
-    uint32_t base;       // PRIMS[d]
-    uint32_t primsum;    // offset of the dimension's permutation block
-    float tail;          // inv_base * perm(0) / (1 - inv_base), evaluated on the host in f32 (halton.rs:61-63)
-    uint32_t pad[3];
+    uint64_t magic;        // floor(2^64 / base) + 1: x / base == umul64hi(x, magic) exactly for x < 2^32
+    uint32_t base;         // PRIMS[d]
+    uint32_t primsum;      // offset of the dimension's permutation block (single digits)
+    float tail;            // inv_base * perm(0) / (1 - inv_base), evaluated on the host in f32 (halton.rs:61-63)
+    uint32_t group;        // base^group_digits
+    uint64_t group_magic;  // floor(2^64 / group) + 1
+    uint32_t group_off;    // tables of 1, 2, ... group_digits digits one after the other (sizes base, base^2, ...), in DevSampler::permutation
+    uint32_t full_off;     // where the last of them (group_digits digits: the full-group table) starts
+    uint32_t group_digits;
+    uint32_t pad;
 };
+static_assert(sizeof(DevHaltonDim) == 48, "three 16-byte loads");
 static constexpr int kHaltonMaxDigits = 32;   // base >= 5 from dimension 2 on: at most 28 digits in 64 bits
 
 struct DevSampler {
@@ -71,7 +80,7 @@ struct DevSampler {
     uint64_t scale[2];
     uint64_t mult_inverse[2];
     uint64_t stride;                 // scale[0] * scale[1]
-    const uint16_t* permutation;     // digit permutations, block of prime k at primsum[k]
+    const uint16_t* permutation;     // digit permutations, block of prime k at primsum[k]; behind them the digit-group tables (DevHaltonDim)
     const uint32_t* primes;          // first 1000 primes
     const uint32_t* primsum;
     const uint64_t* prime_magic;     // floor(2^64 / p) + 1: x / p == umul64hi(x, magic) exactly for x < 2^32

@@ -60,6 +60,7 @@ struct PathArrays {
     F4Field nee_light, nee_bsdf;
     // StateRec  {beta_prev.rgb, bits(pending flags)}{Halton index u64, next dimension, hit slot}
     F4Field beta_prev; ScalarField<uint2, 16> smp_index; ScalarField<uint32_t, 24> smp_dim; ScalarField<uint32_t, 28> hit_slot;
+    F4Field state2;      // the second float4 of StateRec as a whole: {index lo, index hi, dimension, hit slot}
     // which shading queue the path's latest hit belongs to (kShadeNone = nothing to shade);
     // written by the closest-hit stage, consumed (and reset) by k_classify
     uint8_t* shade_kind;
@@ -226,6 +227,19 @@ __global__ void k_raygen(DevScene sc, PixelArrays px, PathArrays P, Queues Q, ui
     if (blockIdx.x == 0 && threadIdx.x == 0) Q.counts[kCntClosest0] = S * npix;
 }
 
+// which shading queue a continuation ray's closest hit goes to (`bounce` = the ray's own bounce number)
+CP_DEV int shade_kind_of_hit(const DevScene& sc, uint32_t slot, uint32_t bounce) {
+    int kind = SHADE_TERMINAL;
+    if (slot != 0xFFFFFFFFu) {
+        const uint32_t src = __float_as_uint(__ldg(&sc.prims[3ull * slot + 2].w));
+        if (!(src & kSourceLight) && !(sc.integrator == 0 && bounce >= sc.max_depth)) {
+            const uint32_t mt = sc.materials[src].type;
+            kind = mt == 0 ? SHADE_MATTE : (mt == 1 ? SHADE_MIRROR : (mt == 2 ? SHADE_GLASS : SHADE_GENERAL));
+        }
+    }
+    return kind;
+}
+
 // ------------------------------------------------------------------------------------------
 // Closest-hit stage.  `cur` selects the input queue.  Persistent warps: lanes pull queue
 // entries one by one (bvh_trace.cuh, trace_persistent).
@@ -234,7 +248,7 @@ struct ClosestItem { uint32_t pid; uint32_t is_mis; float w_o, w_d; };   // w_* 
 // SCHED selects how the closest hit is found: SCHED_VOTE = vote-scheduled tree walk for big trees,
 // SCHED_LOOP = descend-then-test loop for small ones (bvh_trace.cuh), SCHED_FLAT = no tree walk at
 // all for scenes of at most kFlatMaxPrims primitives (flat_trace.cuh).
-enum TraceSchedule : int { SCHED_LOOP = 0, SCHED_VOTE = 1, SCHED_FLAT = 2 };
+enum TraceSchedule : int { SCHED_LOOP = 0, SCHED_VOTE = 1, SCHED_FLAT = 2, SCHED_FUSED = 3 };     // SCHED_FUSED: flat search inside the shading kernels (k_shade<KIND, true>)
 template <int SCHED>
 __global__ void __launch_bounds__(kTraceBlock, SCHED == SCHED_VOTE ? CPBRT_BLOCKS_CLOSEST_VOTE : (SCHED == SCHED_FLAT ? CPBRT_BLOCKS_FLAT : CPBRT_BLOCKS_CLOSEST_LOOP)) k_trace_closest(DevScene sc, PathArrays P, Queues Q, int cur, Totals* totals) {
     const uint32_t n = Q.counts[kCntClosest0 + cur];
@@ -275,15 +289,7 @@ __global__ void __launch_bounds__(kTraceBlock, SCHED == SCHED_VOTE ? CPBRT_BLOCK
                 P.nee_bsdf[pid] = mk4(ld, 0.f);
             } else {
                 P.hit_t[pid] = t; P.hit_slot[pid] = slot;
-                kind = SHADE_TERMINAL;
-                if (slot != 0xFFFFFFFFu) {
-                    const uint32_t src = __float_as_uint(__ldg(&sc.prims[3ull * slot + 2].w));
-                    const uint32_t bounce = __float_as_uint(it.w_d) & 0xFFu;
-                    if (!(src & kSourceLight) && !(sc.integrator == 0 && bounce >= sc.max_depth)) {
-                        const uint32_t mt = sc.materials[src].type;
-                        kind = mt == 0 ? SHADE_MATTE : (mt == 1 ? SHADE_MIRROR : (mt == 2 ? SHADE_GLASS : SHADE_GENERAL));
-                    }
-                }
+                kind = shade_kind_of_hit(sc, slot, __float_as_uint(it.w_d) & 0xFFu);
             }
         }
         if (kind >= 0) P.shade_kind[pid] = (uint8_t)kind;
@@ -428,10 +434,11 @@ CP_DEV void build_bsdf(const DevScene& sc, uint32_t mat, const ShapePoint& sp, t
 // uniform_sample_one_light (integrator/mod.rs:13-97) up to the point where its two rays are
 // needed: the light term is stored assuming visibility (the shadow stage zeroes it), the BSDF
 // term is finished by the closest-hit stage.  Returns the pending flags.
-template <class B>
+struct ShadowOut { Ray ray; Spec ld; };      // FUSED: the shadow ray and the light term it guards stay in registers
+template <bool FUSED, class B>
 CP_DEV void emit_direct_lighting(const DevScene& sc, const PathArrays& P, uint32_t pid, bool lane_active,
                                  const ShapePoint& sp, const B& bsdf, V3 wo, SamplerState& st, Spec beta, bool* want_shadow_out, bool* want_mis_out,
-                                 uint32_t* elided) {
+                                 uint32_t* elided, ShadowOut* sh) {
     bool want_shadow = false, want_mis = false;
     if (lane_active) {
         uint32_t flags = kPendAny;
@@ -446,9 +453,12 @@ CP_DEV void emit_direct_lighting(const DevScene& sc, const PathArrays& P, uint32
                     Spec ld;
                     if (light_is_delta(light)) ld = ls.li * f * fabsf(dot(n, ls.wi)) / ls.pdf;
                     else ld = ls.li * f * fabsf(dot(n, ls.wi)) * power_heuristic(ls.pdf, f_pdf) / ls.pdf;
-                    P.sh_o[pid] = mk4(ls.vis.o, ls.vis.t_max);
-                    P.sh_d[pid] = mk4(ls.vis.d, 0.f);
-                    P.nee_light[pid] = mk4(ld, 0.f);
+                    if constexpr (FUSED) { sh->ray = ls.vis; sh->ld = ld; }
+                    else {
+                        P.sh_o[pid] = mk4(ls.vis.o, ls.vis.t_max);
+                        P.sh_d[pid] = mk4(ls.vis.d, 0.f);
+                        P.nee_light[pid] = mk4(ld, 0.f);
+                    }
                     flags |= kPendLight;
                     want_shadow = true;
                 }
@@ -468,9 +478,10 @@ CP_DEV void emit_direct_lighting(const DevScene& sc, const PathArrays& P, uint32
                         float t_l;
                         may_hit_light = prim_intersect_t(sc, load_prim(sc, light.slot), probe, tri_ray_setup(wi), &t_l);
                     }
-                    P.nee_bsdf[pid] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    flags |= kPendMis;
+                    // an elided MIS ray contributes exactly 0 (no pending bit: l + 0 == l); a queued one has its
+                    // term written by the closest-hit stage before anything reads it
                     if (may_hit_light) {
+                        flags |= kPendMis;
                         Spec le = spec3(light.L[0], light.L[1], light.L[2]);
                         float le_pdf = 0.f;
                         if (light.type == 3) { P2 uv; le = infinite_le(sc, light, wi, &uv); le_pdf = infinite_out_scene_pdf(sc, light, uv); }
@@ -526,12 +537,27 @@ __global__ void k_shade_terminal(DevScene sc, PathArrays P, Queues Q) {
 #define CPBRT_BLOCKS_SPECULAR 8
 #endif
 template <int KIND> struct ShadeBlocks { static constexpr int value = KIND == SHADE_MATTE ? CPBRT_BLOCKS_MATTE : (KIND == SHADE_GENERAL ? 2 : CPBRT_BLOCKS_SPECULAR); };
-template <int KIND>
-__global__ void __launch_bounds__(128, ShadeBlocks<KIND>::value) k_shade(DevScene sc, PathArrays P, Queues Q, int next, Totals* totals) {
+// FUSED (tiny scenes, SCHED_FUSED): the shadow ray and the continuation ray this hit produces are traced right
+// here with the flat search of flat_trace.cuh instead of going through a queue to k_trace_shadow / k_trace_closest
+// and back: no ShadowRec / queue round trips, and the warps that are busy with the (ILP-rich, shared-memory) search
+// fill the issue slots that the warps waiting on path-state loads leave empty.  Only the rare MIS rays that can hit
+// their light's primitive still go through the closest-hit queue.  Same arithmetic per ray, so the film is
+// bit-identical to the other schedules (tests/test_gpu_parity.py::test_stream_schedules_are_race_free).
+#ifndef CPBRT_BLOCKS_MATTE_FUSED
+#define CPBRT_BLOCKS_MATTE_FUSED 5
+#endif
+#ifndef CPBRT_BLOCKS_SPECULAR_FUSED
+#define CPBRT_BLOCKS_SPECULAR_FUSED 6
+#endif
+template <int KIND> struct ShadeBlocksFused { static constexpr int value = KIND == SHADE_MATTE ? CPBRT_BLOCKS_MATTE_FUSED : (KIND == SHADE_GENERAL ? 2 : CPBRT_BLOCKS_SPECULAR_FUSED); };
+template <int KIND, bool FUSED>
+__global__ void __launch_bounds__(128, FUSED ? ShadeBlocksFused<KIND>::value : ShadeBlocks<KIND>::value) k_shade(DevScene sc, PathArrays P, Queues Q, int next, Totals* totals) {
     typedef typename BsdfFor<KIND>::type B;
+    if constexpr (FUSED) flat_load(sc);
     const uint32_t n = Q.counts[kCntShade0 + KIND];
     const uint32_t n_round = (n + 31u) & ~31u;
     uint32_t elided = 0;   // closest-hit queries answered without a traversal (see below)
+    uint32_t n_shadow = 0, n_cont = 0, overflow = 0;      // FUSED: rays traced in this kernel
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
         const bool active = i < n;
         uint32_t pid = 0;
@@ -570,10 +596,14 @@ __global__ void __launch_bounds__(128, ShadeBlocks<KIND>::value) k_shade(DevScen
         // the direct-lighting integrator does not (direct_light.rs:25)
         const bool do_nee = active && (sc.integrator != 0 || bsdf.n_lobes != 0);
         bool want_shadow, want_mis;
-        emit_direct_lighting(sc, P, pid, do_nee, sp, bsdf, wo, st, sc.integrator == 0 ? beta : spec(1.f), &want_shadow, &want_mis, &elided);
+        ShadowOut sh;
+        if constexpr (FUSED) { sh.ray.o = v3(0.f, 0.f, 0.f); sh.ray.d = v3(0.25f, 0.5f, 1.f); sh.ray.t_max = 0.f; sh.ld = spec(0.f); }
+        emit_direct_lighting<FUSED>(sc, P, pid, do_nee, sp, bsdf, wo, st, sc.integrator == 0 ? beta : spec(1.f), &want_shadow, &want_mis, &elided, &sh);
         // A purely non-specular BSDF at depth max_depth - 1 cannot continue usefully (see below),
         // so its sample_f / Russian-roulette draws are not evaluated at all.
         const bool last_useless = (BsdfFor<KIND>::type::kNoDelta) && bounce + 1u >= sc.max_depth;
+        Ray cray; cray.o = v3(0.f, 0.f, 0.f); cray.d = v3(0.25f, 0.5f, 1.f); cray.t_max = 0.f;      // FUSED: the continuation ray (a harmless one on idle lanes)
+        uint32_t cflags = 0;
         if (active && sc.integrator == 0 && !last_useless) {
             V3 wi; Spec f; float f_pdf; bool is_delta;
             if (bsdf.sample_f(sc.sampler, st, wo, &wi, &f, &f_pdf, &is_delta) && f_pdf != 0.f) {
@@ -590,17 +620,41 @@ __global__ void __launch_bounds__(128, ShadeBlocks<KIND>::value) k_shade(DevScen
                 // at `bounce >= max_depth` (path.rs:21-33).  It is neither generated nor counted.
                 if (cont && bounce + 1u >= sc.max_depth && !is_delta) cont = false;
                 if (cont) {
-                    P.ray_o[pid] = mk4(o, 0.f);
-                    P.ray_d[pid] = mk4(wi, __uint_as_float((bounce + 1u) | (is_delta ? kFlagSpecular : 0u)));
+                    cflags = (bounce + 1u) | (is_delta ? kFlagSpecular : 0u);
                     P.beta[pid] = mk4(beta, 0.f);
-                    P.smp_index[pid] = make_uint2((uint32_t)st.index, (uint32_t)(st.index >> 32));
-                    P.smp_dim[pid] = st.dim;
+                    if constexpr (FUSED) { cray.o = o; cray.d = wi; cray.t_max = kFloatMax; }
+                    else {
+                        P.ray_o[pid] = mk4(o, 0.f);
+                        P.ray_d[pid] = mk4(wi, __uint_as_float(cflags));
+                        P.smp_index[pid] = make_uint2((uint32_t)st.index, (uint32_t)(st.index >> 32));
+                        P.smp_dim[pid] = st.dim;
+                    }
                 }
             }
         }
         if (active) P.L[pid] = mk4(L, 0.f);
-        // the MIS ray and the continuation ray go to the same queue: one reservation for both
-        {
+        if constexpr (FUSED) {
+            // shadow ray: VisibilityTester::unoccluded (light/mod.rs:112-114); the light term survives only if nothing is hit
+            if (__any_sync(0xFFFFFFFFu, want_shadow)) {
+                const bool occluded = flat_any(sc, sh.ray, want_shadow, &overflow);
+                if (want_shadow) { P.nee_light[pid] = occluded ? make_float4(0.f, 0.f, 0.f, 0.f) : mk4(sh.ld, 0.f); ++n_shadow; }
+            }
+            // continuation ray: Scene::intersect (scene.rs:20-22) and the routing of its hit, as k_trace_closest does it
+            if (__any_sync(0xFFFFFFFFu, cont)) {
+                float t;
+                const uint32_t slot = flat_closest(sc, cray, cont, &t, &overflow);
+                if (cont) {
+                    P.ray_o[pid] = mk4(cray.o, t);
+                    P.ray_d[pid] = mk4(cray.d, __uint_as_float(cflags));
+                    P.state2[pid] = make_float4(__uint_as_float((uint32_t)st.index), __uint_as_float((uint32_t)(st.index >> 32)), __uint_as_float(st.dim), __uint_as_float(slot));
+                    P.shade_kind[pid] = (uint8_t)shade_kind_of_hit(sc, slot, cflags & 0xFFu);
+                    ++n_cont;
+                }
+            }
+            // the rare MIS ray that can hit its light's primitive still goes through the closest-hit queue
+            queue_push(Q.closest[next], &Q.counts[kCntClosest0 + next], want_mis, pid | kMisRayBit);
+        } else {
+            // the MIS ray and the continuation ray go to the same queue: one reservation for both
             const unsigned mm = __ballot_sync(0xFFFFFFFFu, want_mis), mc = __ballot_sync(0xFFFFFFFFu, cont), ms = __ballot_sync(0xFFFFFFFFu, want_shadow);
             if (mm | mc | ms) {
                 const int lane = threadIdx.x & 31;
@@ -620,6 +674,14 @@ __global__ void __launch_bounds__(128, ShadeBlocks<KIND>::value) k_shade(DevScen
     // warp-reduced count of elided closest-hit queries (they still count as answered rays)
     for (int off = 16; off > 0; off >>= 1) elided += __shfl_down_sync(0xFFFFFFFFu, elided, off);
     if ((threadIdx.x & 31) == 0 && elided) atomicAdd(&totals->elided_closest, (unsigned long long)elided);
+    if constexpr (FUSED) {
+        for (int off = 16; off > 0; off >>= 1) { n_shadow += __shfl_down_sync(0xFFFFFFFFu, n_shadow, off); n_cont += __shfl_down_sync(0xFFFFFFFFu, n_cont, off); }
+        if ((threadIdx.x & 31) == 0) {
+            if (n_shadow) atomicAdd(&totals->rays_any, (unsigned long long)n_shadow);
+            if (n_cont) atomicAdd(&totals->rays_closest, (unsigned long long)n_cont);
+        }
+        if (overflow) atomicAdd(&totals->overflow, 1ull);
+    }
 }
 
 // directlighting with recursion over delta lobes (direct_recursive.cuh): one thread per camera

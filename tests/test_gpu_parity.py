@@ -426,15 +426,21 @@ def test_stream_schedules_are_race_free(cpbrt, make_scene, monkeypatch):
     """compute-sanitizer is closed on this GPU pool, so the stream schedule is checked by its results: the bounce
     loop overlaps stages on three streams per lane and up to three pass lanes on their own streams; the profiled
     schedule runs the same kernels back to back on one stream.  Every combination -- lanes 1 / 2 / 3, flat / loop /
-    vote traversal, pass sizes that leave a ragged last pass -- must give the serial schedule's film bit for bit,
+    vote traversal and the fused shade-and-trace kernels, pass sizes that leave a ragged last pass -- must give the serial schedule's film bit for bit,
     five times in a row (a missed event dependency shows up as a differing or non-repeating film)."""
     scene = make_scene("cornel_box.pbrt", xres=96, yres=96, spp=7)
     r = cpbrt.Renderer(0); r.upload(scene); r.build_bvh()
-    for sched in ("flat", "loop", "vote"):
+    first = None
+    for sched in ("flat", "fused", "loop", "vote"):
         monkeypatch.setenv("CPBRT_SCHEDULE", sched)
         monkeypatch.setenv("CPBRT_LANES", "1")
         serial, st = r.render(profile_stages=True, samples_per_pass=2)
         assert st.kernel_launches > 0
+        # the schedules differ in HOW a ray's hit is found, never in the hit: same film, same ray counts
+        if first is None:
+            first = (serial, st.rays_closest, st.rays_any, st.rays_closest_traced)
+        assert np.array_equal(serial.view(np.uint32), first[0].view(np.uint32)), sched
+        assert (st.rays_closest, st.rays_any, st.rays_closest_traced) == first[1:], sched
         for lanes in ("1", "2", "3"):
             monkeypatch.setenv("CPBRT_LANES", lanes)
             for spass in (1, 2, 3):

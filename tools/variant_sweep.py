@@ -24,6 +24,9 @@ VARIANTS = {
     "vote_refill_8": ["-DCPBRT_REFILL_CLOSEST_VOTE=8", "-DCPBRT_REFILL_SHADOW_VOTE=8"],
     "halton_one_by_one": ["-DCPBRT_HALTON_PAIR=0"],
     "matte_4_blocks": ["-DCPBRT_BLOCKS_MATTE=4"],
+    "fused_matte_4": ["-DCPBRT_BLOCKS_MATTE_FUSED=4"],
+    "fused_matte_3": ["-DCPBRT_BLOCKS_MATTE_FUSED=3"],
+    "fused_matte_6": ["-DCPBRT_BLOCKS_MATTE_FUSED=6"],
 }
 
 
