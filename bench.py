@@ -107,7 +107,11 @@ def traversal_roofline(cpbrt, cornell_renderer):
                algorithmic_bytes_per_ray=own_bytes / n,
                work_avoided_vs_reference=dict(reference_parent_visits_per_ray=ref.trace_parent_visits / n, reference_prim_tests_per_ray=ref.trace_prim_tests / n,
                                               reference_bytes_per_ray=ref_bytes / n, ratio=ref_bytes / own_bytes),
-               traffic=(ncu or {}).get("lts_bytes_per_launch"), traffic_unit="lts__t_bytes per launch of the same kernel on 2^20 of these rays (ncu --set full, profiles/r02_ncu_c4_traversal.json); null = no capture of this build",
+               traffic=(ncu or {}).get("dram_bytes_per_launch"), traffic_l2=(ncu or {}).get("lts_bytes_per_launch"),
+               traffic_rays_per_launch=(ncu or {}).get("rays_per_launch"),
+               traffic_unit="bytes per launch of the same kernel on the same ray batch, from one ncu --set full capture (profiles/r02_ncu_c4_traversal.json): "
+                            "traffic = dram__bytes_read.sum + dram__bytes_write.sum, traffic_l2 = lts__t_bytes.sum; compare traffic_l2 with "
+                            "algorithmic_bytes_per_ray x traffic_rays_per_launch (the tree lives in L2, DRAM only sees it once per launch)",
                issue=(ncu or {}).get("issue"),
                hbm_peak_gbs=(json.load(open(PEAKS))["hbm_gbs"] if os.path.exists(PEAKS) else FALLBACK_HBM_GBS),
                scene_load=dict(ply_write_s=timing.get("write_s"), parse_s=timing.get("parse_s"), upload_and_bvh_build_s=build_s),
