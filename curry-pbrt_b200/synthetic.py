@@ -103,8 +103,17 @@ def write_heightfield_files(directory, nx, nz, xres, yres, spp, seed=20260418, i
     if not os.path.exists(os.path.join(directory, ply)):
         write_ply(os.path.join(directory, ply), heightfield_vertices(nx, nz, seed), heightfield_faces(nx, nz))
     pbrt = os.path.join(directory, "heightfield_%dx%d_%d_%dx%d_%dspp_%s%d.pbrt" % (nx, nz, seed, xres, yres, spp, integrator, max_depth))
-    with open(pbrt, "w") as f:
-        f.write(heightfield_scene_text(ply, xres, yres, spp, integrator, max_depth))
+    text = heightfield_scene_text(ply, xres, yres, spp, integrator, max_depth)
+    try:
+        with open(pbrt) as f:
+            if f.read() == text:
+                return pbrt          # several ranks of one box call this at once: never truncate a file a neighbour is reading
+    except OSError:
+        pass
+    tmp = pbrt + ".tmp.%d" % os.getpid()
+    with open(tmp, "w") as f:
+        f.write(text)
+    os.replace(tmp, pbrt)
     return pbrt
 
 

@@ -59,6 +59,30 @@ def main():
         print("shared-build check: same order on all ranks=%s, max rel err=%.3g, film identical to the replicated-build run=%s -> %s" % (
             same_order.item() == 1.0, err2.max(), np.array_equal(film2.view(np.uint32), film.view(np.uint32)), "OK" if ok2 else "FAIL"))
     ok = ok and ok2
+    # third phase: the same hand-over when rank 0's build never left the device (device-resident SAH build: the
+    # broadcast arrays are pieces of one device allocation there) -- a height field, device build forced
+    from test_oracle import _synthetic_mesh_scene
+    mesh = cpbrt.Scene.parse(_synthetic_mesh_scene(120, 100, res=64))
+    os.environ["CPBRT_BVH_BUILD"] = "gpu"
+    r3 = cpbrt.Renderer(local); r3.upload(mesh)
+    idt3 = torch.zeros(cpbrt.abi.COMM_ID_BYTES, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt3.copy_(torch.tensor(list(cpbrt.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt3, 0)
+    r3.comm_init(world, rank, bytes(idt3.cpu().tolist()))
+    order3 = r3.build_bvh()
+    resident = r3.bvh_device_layout()["resident"] if rank == 0 else True
+    film3, _ = r3.render()
+    os.environ.pop("CPBRT_BVH_SHARE"); os.environ["CPBRT_BVH_BUILD"] = "host"
+    ok3 = True
+    if rank == 0:
+        s3 = cpbrt.Renderer(local); s3.upload(mesh); order_host = s3.build_bvh(); ref3, _ = s3.render()
+        err3 = np.abs(film3 - ref3) / (np.abs(ref3) + 1e-3)
+        ok3 = bool(resident) and np.array_equal(order3, order_host) and bool(err3.max() < 1e-4)
+        print("resident shared-build check: resident=%s, order equals the host build=%s, max rel err=%.3g -> %s" % (
+            resident, np.array_equal(order3, order_host), err3.max(), "OK" if ok3 else "FAIL"))
+    os.environ.pop("CPBRT_BVH_BUILD")
+    ok = ok and ok3
     dist.barrier()
     dist.destroy_process_group()
     return 0 if ok else 1
