@@ -1149,7 +1149,17 @@ int cpbrt_render(cpbrt_ctx* ctx, const cpbrt_render_params* params, float* film_
     // up to 32 spp and ~32 M paths per pass (7 GB of path state + 1.3 GB of queues, of 180 GB): long
     // stages amortise the launch gaps and the thinning later bounces (Cornell 900x900: 32 spp per pass
     // measured 1 % ahead of 20, 4 % ahead of 8)
-    if (spass == 0) { spass = (32u << 20) / npix; if (spass < 1) spass = 1; if (spass > 32) spass = 32; }
+    if (spass == 0) {
+        spass = (32u << 20) / npix; if (spass < 1) spass = 1; if (spass > 32) spass = 32;
+        // equal passes instead of a ragged last one: a rank's share of a partitioned render is rarely a multiple of 32
+        // (131 samples = 4 x 32 + 3 would pay a whole pass of launches for 3 samples; it becomes 33 + 33 + 33 + 32)
+        const uint32_t n_samples = s_end - s_begin;
+        if (n_samples > 0) {
+            const uint32_t n_eq = std::max(1u, (n_samples + spass / 2) / spass);
+            const uint32_t even = (n_samples + n_eq - 1) / n_eq;
+            if (even <= spass + spass / 4 && (uint64_t)even * npix < 0x7FFFFFFFull) spass = even;
+        }
+    }
     if ((uint64_t)spass * npix >= 0x7FFFFFFFull) return ctx->fail(CPBRT_ERR_UNSUPPORTED, "film too large for one pass");
     // Two lanes: consecutive passes run as independent pipelines on their own streams and overlap on the GPU.
     // The stages of a pass stress different things -- the traversal kernels saturate the math pipes, the shading
@@ -1192,8 +1202,8 @@ int cpbrt_render(cpbrt_ctx* ctx, const cpbrt_render_params* params, float* film_
     // blocks per SM of the long kernels: what their launch bounds allow by default; CPBRT_GRID_TRACE / CPBRT_GRID_MATTE
     // shrink the grids (tuning: how two lanes share an SM, tools/variant_sweep.py)
     auto env_blocks = [](const char* name, int dflt) { const char* e = getenv(name); const int v = e ? atoi(e) : 0; return v > 0 ? std::min(v, dflt) : dflt; };
-    const int b_closest = env_blocks("CPBRT_GRID_TRACE", flat ? CPBRT_BLOCKS_FLAT : (vote ? CPBRT_BLOCKS_CLOSEST_VOTE : CPBRT_BLOCKS_CLOSEST_LOOP));
-    const int b_shadow = env_blocks("CPBRT_GRID_TRACE", flat ? CPBRT_BLOCKS_FLAT : (vote ? CPBRT_BLOCKS_SHADOW_VOTE : CPBRT_BLOCKS_SHADOW_LOOP));
+    const int b_closest = env_blocks("CPBRT_GRID_TRACE", flat ? CPBRT_BLOCKS_FLAT_CLOSEST : (vote ? CPBRT_BLOCKS_CLOSEST_VOTE : CPBRT_BLOCKS_CLOSEST_LOOP));
+    const int b_shadow = env_blocks("CPBRT_GRID_TRACE", flat ? CPBRT_BLOCKS_FLAT_SHADOW : (vote ? CPBRT_BLOCKS_SHADOW_VOTE : CPBRT_BLOCKS_SHADOW_LOOP));
     const int b_matte = env_blocks("CPBRT_GRID_MATTE", ShadeBlocks<SHADE_MATTE>::value);
     const int g_closest = grid_for(ctx, b_closest), g_shadow = grid_for(ctx, b_shadow), g_shade = grid_for(ctx, 8), g_pix = grid_for(ctx, 4), g_matte = grid_for(ctx, b_matte);
     // one thread per pixel where possible: each walks a dependent chain of radical inverses (all of a

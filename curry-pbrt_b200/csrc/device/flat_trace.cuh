@@ -31,8 +31,19 @@
 namespace cpbrt {
 
 static constexpr int kFlatMaxPrims = 64;
+// resident blocks per SM of the flat kernels (launch bounds = register budget); the batch entry points use CPBRT_BLOCKS_FLAT
 #ifndef CPBRT_BLOCKS_FLAT
 #define CPBRT_BLOCKS_FLAT 8
+#endif
+// The render's own kernels: 5 / 6 blocks (87 / 77 registers, no spills) instead of 8 (64 registers, ~100 B of
+// spills).  Alone the kernels are only 3-4 % faster that way, but two pass lanes run at once (cpbrt_render) and a
+// grid that does not claim the whole register file lets the other lane's shading blocks move in next to it:
+// Cornell box 841 -> 888 Msamples/s together with 6 matte blocks (profiles/r02_block_count_sweep.txt).
+#ifndef CPBRT_BLOCKS_FLAT_CLOSEST
+#define CPBRT_BLOCKS_FLAT_CLOSEST 5
+#endif
+#ifndef CPBRT_BLOCKS_FLAT_SHADOW
+#define CPBRT_BLOCKS_FLAT_SHADOW 6
 #endif
 
 // Tables in shared memory (copied from DevScene::flat at kernel start), float4 units:

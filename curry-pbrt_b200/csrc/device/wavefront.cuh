@@ -250,7 +250,7 @@ struct ClosestItem { uint32_t pid; uint32_t is_mis; float w_o, w_d; };   // w_* 
 // all for scenes of at most kFlatMaxPrims primitives (flat_trace.cuh).
 enum TraceSchedule : int { SCHED_LOOP = 0, SCHED_VOTE = 1, SCHED_FLAT = 2, SCHED_FUSED = 3 };     // SCHED_FUSED: flat search inside the shading kernels (k_shade<KIND, true>)
 template <int SCHED>
-__global__ void __launch_bounds__(kTraceBlock, SCHED == SCHED_VOTE ? CPBRT_BLOCKS_CLOSEST_VOTE : (SCHED == SCHED_FLAT ? CPBRT_BLOCKS_FLAT : CPBRT_BLOCKS_CLOSEST_LOOP)) k_trace_closest(DevScene sc, PathArrays P, Queues Q, int cur, Totals* totals) {
+__global__ void __launch_bounds__(kTraceBlock, SCHED == SCHED_VOTE ? CPBRT_BLOCKS_CLOSEST_VOTE : (SCHED == SCHED_FLAT ? CPBRT_BLOCKS_FLAT_CLOSEST : CPBRT_BLOCKS_CLOSEST_LOOP)) k_trace_closest(DevScene sc, PathArrays P, Queues Q, int cur, Totals* totals) {
     const uint32_t n = Q.counts[kCntClosest0 + cur];
     uint32_t overflow = 0;
     const uint32_t* __restrict__ queue = Q.closest[cur];
@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(256) k_classify(PathArrays P, Queues Q, uint32
 
 // Shadow-ray stage: VisibilityTester::unoccluded (light/mod.rs:112-114).
 template <int SCHED>
-__global__ void __launch_bounds__(kTraceBlock, SCHED == SCHED_VOTE ? CPBRT_BLOCKS_SHADOW_VOTE : (SCHED == SCHED_FLAT ? CPBRT_BLOCKS_FLAT : CPBRT_BLOCKS_SHADOW_LOOP)) k_trace_shadow(DevScene sc, PathArrays P, Queues Q, Totals* totals) {
+__global__ void __launch_bounds__(kTraceBlock, SCHED == SCHED_VOTE ? CPBRT_BLOCKS_SHADOW_VOTE : (SCHED == SCHED_FLAT ? CPBRT_BLOCKS_FLAT_SHADOW : CPBRT_BLOCKS_SHADOW_LOOP)) k_trace_shadow(DevScene sc, PathArrays P, Queues Q, Totals* totals) {
     const uint32_t n = Q.counts[kCntShadow];
     uint32_t overflow = 0;
     auto fetch = [&](uint32_t i, Ray* ray, uint32_t* pid) {
@@ -527,11 +527,12 @@ __global__ void k_shade_terminal(DevScene sc, PathArrays P, Queues Q) {
     }
 }
 
-// Resident blocks per SM: the matte kernel (NEE + MIS + continuation) spills heavily at the 64
-// registers that 8 blocks allow; 5 blocks (96 registers, 76 B of spills) measured ~5% faster,
-// 4 and 6 no better.  The short mirror / glass kernels keep 8.
+// Resident blocks per SM: the matte kernel (NEE + MIS + continuation) wants ~100 registers.  Round 1: 5 blocks
+// (96 registers, 88 B of spills) measured 5 % ahead of 8 blocks (64 registers, 366 B of spills).  Round 2, with the
+// radiance store moved up (3 registers freed through the whole direct-lighting section) and two pass lanes sharing
+// the SMs: 6 blocks (80 registers) are ahead, 7 and 4 are not (profiles/r02_block_count_sweep.txt).
 #ifndef CPBRT_BLOCKS_MATTE
-#define CPBRT_BLOCKS_MATTE 5
+#define CPBRT_BLOCKS_MATTE 6
 #endif
 #ifndef CPBRT_BLOCKS_SPECULAR
 #define CPBRT_BLOCKS_SPECULAR 8
@@ -591,6 +592,7 @@ __global__ void __launch_bounds__(128, FUSED ? ShadeBlocksFused<KIND>::value : S
                 wo = -normalize(ray.d);
             }
             bsdf.set_wo(wo);
+            P.L[pid] = mk4(L, 0.f);      // final for this bounce: the direct-lighting terms below stay pending until the next one
         }
         // direct lighting: the path integrator skips it for all-delta BSDFs (path.rs:37),
         // the direct-lighting integrator does not (direct_light.rs:25)
@@ -632,7 +634,6 @@ __global__ void __launch_bounds__(128, FUSED ? ShadeBlocksFused<KIND>::value : S
                 }
             }
         }
-        if (active) P.L[pid] = mk4(L, 0.f);
         if constexpr (FUSED) {
             // shadow ray: VisibilityTester::unoccluded (light/mod.rs:112-114); the light term survives only if nothing is hit
             if (__any_sync(0xFFFFFFFFu, want_shadow)) {

@@ -24,6 +24,27 @@ VARIANTS = {
     "vote_refill_8": ["-DCPBRT_REFILL_CLOSEST_VOTE=8", "-DCPBRT_REFILL_SHADOW_VOTE=8"],
     "halton_one_by_one": ["-DCPBRT_HALTON_PAIR=0"],
     "matte_4_blocks": ["-DCPBRT_BLOCKS_MATTE=4"],
+    "vote_c5_s6": ["-DCPBRT_BLOCKS_CLOSEST_VOTE=5", "-DCPBRT_BLOCKS_SHADOW_VOTE=6"],
+    "vote_c5_s8": ["-DCPBRT_BLOCKS_CLOSEST_VOTE=5"],
+    "vote_c6_s6": ["-DCPBRT_BLOCKS_SHADOW_VOTE=6"],
+    "vote_c4_s6": ["-DCPBRT_BLOCKS_CLOSEST_VOTE=4", "-DCPBRT_BLOCKS_SHADOW_VOTE=6"],
+    "vote_c7_s8": ["-DCPBRT_BLOCKS_CLOSEST_VOTE=7"],
+    "sp7": ["-DCPBRT_BLOCKS_SPECULAR=7"],
+    "sp6": ["-DCPBRT_BLOCKS_SPECULAR=6"],
+    "c5_s6_m6": ["-DCPBRT_BLOCKS_FLAT_CLOSEST=5", "-DCPBRT_BLOCKS_FLAT_SHADOW=6", "-DCPBRT_BLOCKS_MATTE=6"],
+    "c5_s6_m7": ["-DCPBRT_BLOCKS_FLAT_CLOSEST=5", "-DCPBRT_BLOCKS_FLAT_SHADOW=6", "-DCPBRT_BLOCKS_MATTE=7"],
+    "c5_s5_m7": ["-DCPBRT_BLOCKS_FLAT_CLOSEST=5", "-DCPBRT_BLOCKS_FLAT_SHADOW=5", "-DCPBRT_BLOCKS_MATTE=7"],
+    "c5_s4_m6": ["-DCPBRT_BLOCKS_FLAT_CLOSEST=5", "-DCPBRT_BLOCKS_FLAT_SHADOW=4", "-DCPBRT_BLOCKS_MATTE=6"],
+    "c5_s5_m6_sp5": ["-DCPBRT_BLOCKS_FLAT_CLOSEST=5", "-DCPBRT_BLOCKS_FLAT_SHADOW=5", "-DCPBRT_BLOCKS_MATTE=6", "-DCPBRT_BLOCKS_SPECULAR=5"],
+    "c5_s7_m6": ["-DCPBRT_BLOCKS_FLAT_CLOSEST=5", "-DCPBRT_BLOCKS_FLAT_SHADOW=7", "-DCPBRT_BLOCKS_MATTE=6"],
+    "flat_5_blocks": ["-DCPBRT_BLOCKS_FLAT=5"],
+    "flat_4_blocks": ["-DCPBRT_BLOCKS_FLAT=4"],
+    "flat_6_matte_6": ["-DCPBRT_BLOCKS_FLAT=6", "-DCPBRT_BLOCKS_MATTE=6"],
+    "flat_5_matte_6": ["-DCPBRT_BLOCKS_FLAT=5", "-DCPBRT_BLOCKS_MATTE=6"],
+    "flat_7_blocks": ["-DCPBRT_BLOCKS_FLAT=7"],
+    "flat_6_blocks": ["-DCPBRT_BLOCKS_FLAT=6"],
+    "matte_6_blocks": ["-DCPBRT_BLOCKS_MATTE=6"],
+    "specular_6_blocks": ["-DCPBRT_BLOCKS_SPECULAR=6"],
     "fused_matte_4": ["-DCPBRT_BLOCKS_MATTE_FUSED=4"],
     "fused_matte_3": ["-DCPBRT_BLOCKS_MATTE_FUSED=3"],
     "fused_matte_6": ["-DCPBRT_BLOCKS_MATTE_FUSED=6"],
