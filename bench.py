@@ -341,7 +341,7 @@ def main():
                                                achieved=shade_bytes / (st.ms_shade * 1e-3) / 1e9, peak=hbm, unit="GB/s",
                                                frac=shade_bytes / (st.ms_shade * 1e-3) / 1e9 / hbm, bytes_per_shaded_hit=368, shaded_hits=int(st.shade_items),
                                                stage_ms=st.ms_shade, peak_source="MEASURED_PEAKS.json hbm_gbs" if os.path.exists(PEAKS) else "fallback",
-                                               note="latency-bound at 20 resident warps per SM (96 registers): 46 % issue-active, DRAM 27 % of peak (ncu, profiles/)")
+                                               note="latency-bound: the matte kernel issues on 44 % of cycles at 24 resident warps per SM (80 registers), DRAM 30 % of peak (ncu, profiles/r02_final_ncu_cornell.txt)")
     if rank == 0:
         out = dict(metric="Msamples/s", value=value, unit="Msamples/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                    ms_per_step=step_ms, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32", data="synthetic",

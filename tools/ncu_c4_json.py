@@ -24,7 +24,7 @@ def main():
     # the first captured launches belong to the camera-ray batch when the capture starts early: keep the launches of the last batch of equal grid
     n = len(sel)
     avg = lambda k: sum(val(r, k) for r in sel) / n
-    j = dict(source="%s (ncu --set full --clock-control none, tools/traversal_roofline.py --rays %d --no-oracle --repeat 1), summary in profiles/r02_s_ncu_c4.txt" % (os.path.basename(rep), log2_rays),
+    j = dict(source="%s (ncu --set full --clock-control none, tools/traversal_roofline.py --rays %d --no-oracle --repeat 1), summary in profiles/r02_final_ncu_c4.txt" % (os.path.basename(rep), log2_rays),
              kernel="k_batch_closest<2>", rays_per_launch=1 << log2_rays, launches=n,
              gpu_time_ms=avg("gpu__time_duration.sum"),
              dram_bytes_per_launch=avg("dram__bytes_read.sum") + avg("dram__bytes_write.sum"),

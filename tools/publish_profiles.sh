@@ -7,7 +7,7 @@ TAG=${1:?tag}
 G=gpurun_out
 P=profiles
 grep '^"' $G/${TAG}_launches.csv > $P/${TAG}_launches.csv
-for f in bench.json bench_reference.json configs.jsonl traversal_c4.jsonl bvh_build.jsonl schedule_crossover.jsonl; do cp $G/${TAG}_$f $P/${TAG}_$f; done
+for f in bench.json bench_reference.json configs.jsonl traversal_c4.jsonl; do cp $G/${TAG}_$f $P/${TAG}_$f; done
 python - "$TAG" <<'PY'
 import json, subprocess, sys
 tag = sys.argv[1]
@@ -40,12 +40,12 @@ json.dump({"source": "profiles/%s_ncu_cornell.txt (ncu --set full, bench.py --sp
                                "note": "almost all of it is path-state records (ray / MIS records read, hit and shading-kind bytes written); the 33-primitive BVH itself stays in L1"}},
           open('profiles/%s_traffic.json' % tag, 'w'), indent=1)
 PY
-(echo "# ncu --set full --clock-control none --import-source on, Cornell box, one 32-spp pass (bench.py --spp 32), launches 9-15 of the trace / shade kernels (second bounce)"
+(echo "# ncu --set full --clock-control none --import-source on, Cornell box, one 32-spp pass (bench.py --spp 32), launches 14-20 of the trace / classify / shade kernels (second bounce of the timed pass)"
  python tools/ncu_summary.py $G/${TAG}_cornell.ncu-rep
- echo; echo "# hot CUDA source lines, k_trace_closest<loop schedule>"; python tools/ncu_hot_lines.py $G/${TAG}_cornell.ncu-rep "k_trace_closest" 16
- echo; echo "# hot CUDA source lines, k_shade<matte>"; python tools/ncu_hot_lines.py $G/${TAG}_cornell.ncu-rep "k_shade<\(int\)1>" 16) > $P/${TAG}_ncu_cornell.txt 2>&1
-(echo "# ncu --set full --clock-control none --import-source on, C4 (1,000,008 triangles), tools/traversal_roofline.py --rays 20 --no-oracle --repeat 1"
- echo "# k_batch_closest<2> = vote-scheduled two-phase traversal on the random-ray batch (1,048,576 rays, 3 launches); <1> = reference-order counting traversal of the same batch; k_batch_any<2> = shadow-ray batch"
+ echo; echo "# hot CUDA source lines, k_trace_closest<flat search>"; python tools/ncu_hot_lines.py $G/${TAG}_cornell.ncu-rep "k_trace_closest" 16
+ echo; echo "# hot CUDA source lines, k_shade<matte>"; python tools/ncu_hot_lines.py $G/${TAG}_cornell.ncu-rep "k_shade<\(int\)1" 16) > $P/${TAG}_ncu_cornell.txt 2>&1
+(echo "# ncu --set full --clock-control none --import-source on, C4 (1,000,008 triangles), tools/traversal_roofline.py --rays 22 --no-oracle --repeat 1"
+ echo "# k_batch_closest<2> = vote-scheduled two-phase traversal on the random-ray batch (4,194,304 rays); <1> = reference-order counting traversal of the same batch; k_batch_any<2> = shadow-ray batch"
  python tools/ncu_summary.py $G/${TAG}_c4.ncu-rep
  echo; echo "# hot CUDA source lines, k_batch_closest<2>"; python tools/ncu_hot_lines.py $G/${TAG}_c4.ncu-rep "k_batch_closest<\(int\)2>" 16) > $P/${TAG}_ncu_c4.txt 2>&1
 ls -la $P/${TAG}_*
