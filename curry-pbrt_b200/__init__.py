@@ -230,6 +230,13 @@ class Renderer:
         self._check(min(rc, 0))
         return dict(nodes=nodes, records=records, frames=frames, uv=uv if rc == 1 else None, resident=bool(resident.value))
 
+    def check_failures(self):
+        """(checked_build, violations, first_site): bounds violations counted by a -DCPBRT_CHECKED build of the library."""
+        n, site = C.c_uint64(), C.c_uint32()
+        rc = lib.cpbrt_check_failures(self._ctx, C.byref(n), C.byref(site))
+        self._check(min(rc, 0))
+        return bool(rc), int(n.value), int(site.value)
+
     def h2d_bytes(self):
         """Bytes this context has copied host -> device so far (counted where the copies are issued)."""
         return int(lib.cpbrt_h2d_bytes(self._ctx))

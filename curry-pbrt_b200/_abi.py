@@ -140,6 +140,7 @@ DEVICE_SYMBOLS = {
     "cpbrt_render": (C.c_int, [C.c_void_p, C.POINTER(RenderParams), C.c_void_p, C.POINTER(Stats)]),
     "cpbrt_bvh_gpu_levels": (C.c_int, [C.c_void_p]),
     "cpbrt_bvh_host_segments": (C.c_int, [C.c_void_p]),
+    "cpbrt_check_failures": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
     "cpbrt_bvh_device_layout": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),
     "cpbrt_h2d_bytes": (C.c_uint64, [C.c_void_p]),
     "cpbrt_measure_read_bandwidth": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(C.c_double)]),

@@ -13,6 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libcpbrt.so")
+OUT_CHECKED = os.path.join(HERE, "libcpbrt_checked.so")      # same library with device-side bounds checks (tests/test_gpu_parity.py::test_checked_build...)
 OBJ = os.path.join(HERE, "build")
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -51,9 +52,9 @@ def _unit_deps(src):
     return deps
 
 
-def _compile_cuda(src, obj, verbose):
-    r = subprocess.run([NVCC] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj], capture_output=True, text=True)
-    with open(os.path.join(OBJ, src.replace("/", "_") + ".ptxas.log"), "w") as f:
+def _compile_cuda(src, obj, verbose, extra=()):
+    r = subprocess.run([NVCC] + NVCC_FLAGS + list(extra) + ["-c", os.path.join(CSRC, src), "-o", obj], capture_output=True, text=True)
+    with open(os.path.join(OBJ, os.path.basename(obj)[:-2] + ".ptxas.log"), "w") as f:
         f.write(r.stderr)
     if r.returncode != 0:
         sys.stderr.write(r.stderr)
@@ -91,11 +92,11 @@ def build(force=False, verbose=False):
     flags = " ".join(NVCC_FLAGS + HOST_CXX)
     want = _fingerprint(_deps(), flags)
     stamp = os.path.join(OBJ, "libcpbrt.stamp")
-    if not force and os.path.exists(OUT) and _read(stamp) == want:
+    if not force and os.path.exists(OUT) and os.path.exists(OUT_CHECKED) and _read(stamp) == want:
         return OUT
     with open(os.path.join(OBJ, ".lock"), "w") as lock:
         fcntl.flock(lock, fcntl.LOCK_EX)
-        if not force and os.path.exists(OUT) and _read(stamp) == want:
+        if not force and os.path.exists(OUT) and os.path.exists(OUT_CHECKED) and _read(stamp) == want:
             return OUT
         objs = []
         # CUDA translation units in parallel threads (nvcc is a subprocess), each only when its inputs changed
@@ -108,6 +109,11 @@ def build(force=False, verbose=False):
                 if force or not os.path.exists(o) or _read(o + ".stamp") != unit:
                     jobs.append((pool.submit(_compile_cuda, src, o, verbose), o, unit))
                 objs.append(o)
+            # the bounds-checked twin of the render translation unit (dmath.cuh CP_CHECK) -> libcpbrt_checked.so
+            co = os.path.join(OBJ, "cpbrt_api_checked.o")
+            cunit = _fingerprint(_unit_deps("cpbrt_api.cu"), flags + " checked")
+            if force or not os.path.exists(co) or _read(co + ".stamp") != cunit:
+                jobs.append((pool.submit(_compile_cuda, "cpbrt_api.cu", co, verbose, ["-DCPBRT_CHECKED"]), co, cunit))
             for src in HOST_SOURCES:
                 o = os.path.join(OBJ, src.replace("/", "_") + ".o")
                 subprocess.check_call(HOST_CXX + ["-c", os.path.join(CSRC, src), "-o", o])
@@ -119,6 +125,10 @@ def build(force=False, verbose=False):
         tmp = OUT + ".tmp.%d" % os.getpid()
         subprocess.check_call([NVCC, "-shared", "-o", tmp] + objs + ["-lz", "-ldl", "-lpthread", "-cudart", "static"])
         os.replace(tmp, OUT)
+        cobjs = [co if o.endswith("cpbrt_api.cu.o") else o for o in objs]
+        tmp = OUT_CHECKED + ".tmp.%d" % os.getpid()
+        subprocess.check_call([NVCC, "-shared", "-o", tmp] + cobjs + ["-lz", "-ldl", "-lpthread", "-cudart", "static"])
+        os.replace(tmp, OUT_CHECKED)
         with open(stamp, "w") as f:
             f.write(want)
     return OUT

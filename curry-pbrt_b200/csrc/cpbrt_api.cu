@@ -495,6 +495,7 @@ int cpbrt_upload_scene(cpbrt_ctx* ctx, const cpbrt_scene_desc* d) {
             CU(cudaMemcpyAsync(ctx->d_perm.p, d->sampler.permutation, perm_bytes, cudaMemcpyHostToDevice, ctx->stream));
             if (!table.empty()) CU(cudaMemcpyAsync((char*)ctx->d_perm.p + perm_bytes, table.data(), table.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
             ctx->h2d_bytes += total_bytes;
+            S.sampler.table_len = (uint32_t)(total_bytes / 2);
             if (int rc = alloc_upload(ctx, ctx->d_halton_dims, dims.data(), dims.size() * sizeof(DevHaltonDim))) return rc;
             if (int rc = alloc_upload(ctx, ctx->d_halton_inv_pow, inv_pow.data(), inv_pow.size() * 4)) return rc;
         }
@@ -506,6 +507,7 @@ int cpbrt_upload_scene(cpbrt_ctx* ctx, const cpbrt_scene_desc* d) {
         sm.permutation = (const uint16_t*)ctx->d_perm.p; sm.primes = (const uint32_t*)ctx->d_primes.p; sm.primsum = (const uint32_t*)ctx->d_primsum.p; sm.prime_magic = (const uint64_t*)ctx->d_magic.p;
         sm.dims = (const DevHaltonDim*)ctx->d_halton_dims.p; sm.inv_pow = (const float*)ctx->d_halton_inv_pow.p;
     }
+    S.n_materials = d->n_materials; S.n_textures = d->n_textures; S.n_transforms = d->n_transforms;
     S.transforms = (const DevTransform*)ctx->d_transforms.p;
     S.materials = (const DevMaterial*)ctx->d_materials.p;
     S.textures = (const DevTexture*)ctx->d_textures.p;
@@ -1114,6 +1116,14 @@ static int ensure_wavefront(cpbrt_ctx* ctx, uint32_t n_paths, int n_lanes) {
             P.mis_A.base = (float4*)p; P.mis_p.base = (float4*)p + 1; p += rec;
             P.nee_light.base = (float4*)p; P.nee_bsdf.base = (float4*)p + 1; p += rec;
             P.beta_prev.base = (float4*)p; P.state2.base = (float4*)p + 1; P.smp_index.base = p; P.smp_dim.base = p; P.hit_slot.base = p;
+#ifdef CPBRT_CHECKED
+            {
+                const uint32_t cap = n_paths;
+                P.ray_o.cap = P.ray_d.cap = P.hit_t.cap = P.beta.cap = P.L.cap = P.sh_o.cap = P.sh_d.cap = P.mis_o.cap = P.mis_d.cap = P.mis_A.cap = P.mis_p.cap =
+                    P.nee_light.cap = P.nee_bsdf.cap = P.beta_prev.cap = P.state2.cap = P.smp_index.cap = P.smp_dim.cap = P.hit_slot.cap = cap;
+                L.Q.n_paths = n_paths;
+            }
+#endif
             uint32_t* q = (uint32_t*)L.d_queues.p;
             L.Q.closest[0] = q; q += 2 * (size_t)n_paths; L.Q.closest[1] = q; q += 2 * (size_t)n_paths; L.Q.shadow = q; q += n_paths;
             for (int k = 0; k < SHADE_KINDS; ++k) { L.Q.shade[k] = q; q += n_paths; }
@@ -1360,6 +1370,30 @@ int cpbrt_render(cpbrt_ctx* ctx, const cpbrt_render_params* params, float* film_
 }
 
 int cpbrt_bvh_gpu_levels(const cpbrt_ctx* ctx) { return ctx ? ctx->bvh_gpu_levels : 0; }
+
+#ifdef CPBRT_CHECKED
+// CPBRT_CHECK_SELFTEST=1: one deliberate out-of-range access through the checked accessor, to show that a violation
+// is counted and reported (site 101) and does not touch memory it should not
+__global__ void k_check_selftest(F4Field f) { if (threadIdx.x == 0) { float4 v = f[f.cap + 7u]; if (v.x == 123456.f) f[0] = v; } }
+#endif
+int cpbrt_check_failures(cpbrt_ctx* ctx, uint64_t* n_failures_out, uint32_t* first_site_out) {
+    if (!ctx) return CPBRT_ERR_BAD_CTX;
+#ifdef CPBRT_CHECKED
+    CU(cudaSetDevice(ctx->device));
+    if (getenv("CPBRT_CHECK_SELFTEST") && ctx->lanes[0].capacity) { k_check_selftest<<<1, 32, 0, ctx->stream>>>(ctx->lanes[0].P.ray_o); }
+    unsigned long long n = 0; unsigned int site = 0;
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpyFromSymbol(&n, g_check_failures, sizeof n));
+    CU(cudaMemcpyFromSymbol(&site, g_check_first_site, sizeof site));
+    if (n_failures_out) *n_failures_out = n;
+    if (first_site_out) *first_site_out = site;
+    return 1;
+#else
+    if (n_failures_out) *n_failures_out = 0;
+    if (first_site_out) *first_site_out = 0;
+    return 0;
+#endif
+}
 
 int cpbrt_bvh_device_layout(cpbrt_ctx* ctx, uint64_t node_capacity, uint64_t* n_nodes_out, float* nodes_out, float* records_out, float* frames_out, float* uv_out, int* resident_out) {
     if (!ctx) return CPBRT_ERR_BAD_CTX;

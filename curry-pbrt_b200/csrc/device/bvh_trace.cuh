@@ -110,6 +110,7 @@ struct NodeChildren { uint32_t ref[2], cnt[2]; bool ok[2]; float tmin[2]; uint32
 // Reads one Parent node (64 B) and runs the t_max-independent part of both children's box tests.
 template <bool COUNT>
 CP_DEV NodeChildren expand_node(const DevScene& sc, uint32_t node, const RayBoxSetup& bs, TraceStats* st) {
+    CP_CHECK(node < sc.n_nodes, 301);
     const float4* np = sc.nodes + 4ull * node;
     const float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2), q3 = __ldg(np + 3);
     NodeChildren c;
@@ -357,6 +358,7 @@ CP_DEV void slab_tests(const RayBoxSetup& s, float mnx, float mny, float mnz, fl
 }
 
 CP_DEV ChildTests expand_node2(const DevScene& sc, uint32_t node, const RayBoxSetup& bs) {
+    CP_CHECK(node < sc.n_nodes, 301);
     const float4* np = sc.nodes + 4ull * node;
     const float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2), q3 = __ldg(np + 3);
     ChildTests c;

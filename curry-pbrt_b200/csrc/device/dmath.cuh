@@ -14,6 +14,19 @@ namespace cpbrt {
 
 #define CP_DEV __device__ __forceinline__
 
+// Checked build (-DCPBRT_CHECKED, tools/variant_sweep.py "checked"): every index into the path state, the queues,
+// the primitive / node / light / material arrays and the sampler tables is compared with its bound; a violation is
+// counted (and the first site remembered) instead of trapping, so that a whole workload runs to its end and the
+// count is read back with cpbrt_check_failures.  compute-sanitizer is closed on the GPU pool this was developed on;
+// this is the bounds-checking half of what memcheck would have given.  Costs nothing in the normal build.
+#ifdef CPBRT_CHECKED
+__device__ unsigned long long g_check_failures;
+__device__ unsigned int g_check_first_site;
+#define CP_CHECK(cond, site) do { if (!(cond)) { if (atomicAdd(&g_check_failures, 1ull) == 0ull) g_check_first_site = (unsigned int)(site); } } while (0)
+#else
+#define CP_CHECK(cond, site) do { } while (0)
+#endif
+
 static constexpr float kMachineEpsilon = 1.1920929e-07f * 0.5f;   // src/def.rs:4
 static constexpr float kInvPi = 0.31830988618379067154f;          // src/math/mod.rs:213
 static constexpr float kPi = 3.14159265358979323846f;             // src/math/mod.rs:216

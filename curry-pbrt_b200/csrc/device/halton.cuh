@@ -34,6 +34,8 @@ CP_DEV float radical_inverse(uint64_t x, uint32_t base) {
     return inv_base_n * __ull2float_rn(acc);
 }
 
+CP_DEV uint32_t halton_table(const DevSampler& S, uint32_t i) { CP_CHECK(i < S.table_len, 401); return __ldg(&S.permutation[i]); }
+
 // scrambled_radical_inverse (halton.rs:56-64).  The reference peels one digit per round:
 //     reversed = reversed * base + perm[a % base];  a /= base;      while a != 0
 // Here, once the running quotient fits 32 bits, a round takes a whole GROUP of g digits (DevHaltonDim): with
@@ -47,13 +49,13 @@ CP_DEV void halton_finish_chain(const DevSampler& S, const float4 r0, const floa
     const uint64_t gm = ((uint64_t)__float_as_uint(r1.w) << 32) | __float_as_uint(r1.z);
     while (xs >= G) {
         const uint32_t q = (uint32_t)__umul64hi((uint64_t)xs, gm);
-        acc = acc * G + __ldg(&S.permutation[full_off + (xs - q * G)]); cnt += gd; xs = q;
+        acc = acc * G + halton_table(S, full_off + (xs - q * G)); cnt += gd; xs = q;
     }
     if (xs != 0) {
         const uint32_t base = __float_as_uint(r0.z);
         uint32_t j = 1, pw = base, o = __float_as_uint(r2.x);
         while (xs >= pw) { o += pw; ++j; pw *= base; }
-        acc = acc * pw + __ldg(&S.permutation[o + xs]); cnt += j;
+        acc = acc * pw + halton_table(S, o + xs); cnt += j;
     }
 }
 CP_DEV float scrambled_radical_inverse(const DevSampler& S, uint64_t x, uint32_t dim) {
@@ -95,7 +97,7 @@ CP_DEV void scrambled_radical_inverse_n(const DevSampler& S, uint64_t x, uint32_
             const float4 r0 = __ldg(reinterpret_cast<const float4*>(S.dims + dim + k));
             const uint32_t base = __float_as_uint(r0.z), off = __float_as_uint(r0.w);
             uint64_t xk = x;
-            while ((xk >> 32) != 0) { const uint64_t q = xk / base; const uint32_t digit = (uint32_t)(xk - q * base); acc[k] = acc[k] * base + __ldg(&S.permutation[off + digit]); ++cnt[k]; xk = q; }
+            while ((xk >> 32) != 0) { const uint64_t q = xk / base; const uint32_t digit = (uint32_t)(xk - q * base); acc[k] = acc[k] * base + halton_table(S, off + digit); ++cnt[k]; xk = q; }
             xs[k] = (uint32_t)xk;
         }
     } else {
@@ -112,7 +114,7 @@ CP_DEV void scrambled_radical_inverse_n(const DevSampler& S, uint64_t x, uint32_
 #pragma unroll
         for (int k = 0; k < N; ++k) q[k] = (uint32_t)__umul64hi((uint64_t)xs[k], gm[k]);
 #pragma unroll
-        for (int k = 0; k < N; ++k) pv[k] = __ldg(&S.permutation[fo[k] + (xs[k] - q[k] * G[k])]);
+        for (int k = 0; k < N; ++k) pv[k] = halton_table(S, fo[k] + (xs[k] - q[k] * G[k]));
 #pragma unroll
         for (int k = 0; k < N; ++k) { acc[k] = acc[k] * G[k] + pv[k]; xs[k] = q[k]; }
         ++rounds;

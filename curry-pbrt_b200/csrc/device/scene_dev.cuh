@@ -86,6 +86,7 @@ struct DevSampler {
     const uint64_t* prime_magic;     // floor(2^64 / p) + 1: x / p == umul64hi(x, magic) exactly for x < 2^32
     const DevHaltonDim* dims;        // the same per-dimension data gathered in one record
     const float* inv_pow;            // [dim][digit count] = 1 / (base^count as f32)
+    uint32_t table_len;              // entries behind `permutation` (permutation blocks + digit-group tables)
 };
 
 struct DevScene {
@@ -114,7 +115,7 @@ struct DevScene {
     const float* texels;
     const DevLight* lights;
     const float* env;           // distribution tables of the infinite lights
-    uint32_t n_lights;
+    uint32_t n_lights, n_materials, n_textures, n_transforms;
     uint32_t integrator, max_depth;
     uint32_t width, height;
     DevCamera camera;

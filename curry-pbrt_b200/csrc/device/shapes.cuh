@@ -184,13 +184,14 @@ CP_DEV Ray ray_to_object(const DevScene& sc, int32_t xform, Ray r) {
     return r;
 }
 CP_DEV ShapePoint shape_point_to_world(const DevScene& sc, int32_t xform, ShapePoint s) {
-    for (int32_t x = xform; x >= 0; x = sc.transforms[x].outer) s = shape_point_apply(s, sc.transforms[x].m, sc.transforms[x].m_inv);
+    for (int32_t x = xform; x >= 0; x = sc.transforms[x].outer) { CP_CHECK((uint32_t)x < sc.n_transforms, 202); s = shape_point_apply(s, sc.transforms[x].m, sc.transforms[x].m_inv); }
     return s;
 }
 
 struct PrimRecord { float4 q0, q1, q2; };
 CP_DEV PrimRecord load_prim(const DevScene& sc, uint32_t slot) {
     PrimRecord r;
+    CP_CHECK(slot < sc.n_prims, 201);
     const float4* p = sc.prims + 3ull * slot;
     r.q0 = __ldg(p); r.q1 = __ldg(p + 1); r.q2 = __ldg(p + 2);
     return r;

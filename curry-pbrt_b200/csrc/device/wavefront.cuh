@@ -38,12 +38,22 @@ static constexpr uint32_t kMisRayBit = 0x80000000u;    // queue entry: path id |
 // ones.  The accessors below keep the per-field view (`P.ray_o[pid]`).
 struct F4Field {   // one float4 of a 32-byte record
     float4* base;
+#ifdef CPBRT_CHECKED
+    uint32_t cap;
+    CP_DEV float4& operator[](uint32_t i) const { CP_CHECK(i < cap, 101); return base[2ull * (i < cap ? i : 0u)]; }
+#else
     CP_DEV float4& operator[](uint32_t i) const { return base[2ull * i]; }
+#endif
 };
 template <class T, int OFFSET>
 struct ScalarField {   // a 4- or 8-byte member at byte OFFSET of a 32-byte record
     char* base;
+#ifdef CPBRT_CHECKED
+    uint32_t cap;
+    CP_DEV T& operator[](uint32_t i) const { CP_CHECK(i < cap, 102); return *reinterpret_cast<T*>(base + 32ull * (i < cap ? i : 0u) + OFFSET); }
+#else
     CP_DEV T& operator[](uint32_t i) const { return *reinterpret_cast<T*>(base + 32ull * i + OFFSET); }
+#endif
 };
 struct PathArrays {
     // RayRec    {o.xyz, hit_t}{d.xyz, bits(bounce | specular flag)}   continuation ray + its hit distance
@@ -74,7 +84,15 @@ struct Queues {
     uint32_t* shade[SHADE_KINDS];
     // counters: [0],[1] closest; [2] shadow; [3..3+SHADE_KINDS) shade; then totals
     uint32_t* counts;
+#ifdef CPBRT_CHECKED
+    uint32_t n_paths;         // capacities: closest 2 * n_paths, shadow and every shade queue n_paths
+#endif
 };
+#ifdef CPBRT_CHECKED
+#define CP_CHECK_QUEUE(Q, pos, mult, site) CP_CHECK((uint64_t)(pos) < (uint64_t)(mult) * (Q).n_paths, site)
+#else
+#define CP_CHECK_QUEUE(Q, pos, mult, site) do { } while (0)
+#endif
 static constexpr int kCntClosest0 = 0, kCntShadow = 2, kCntShade0 = 3, kCntN = 3 + SHADE_KINDS;
 static constexpr int kCntWorkClosest = kCntN, kCntWorkShadow = kCntN + 1;   // work-distribution cursors of the persistent trace kernels
 // 64-bit totals that live after the counters: rays_closest, rays_any, nan_dropped, stack_overflow
@@ -87,7 +105,7 @@ struct PixelArrays {
 };
 
 // warp-aggregated queue push: every lane calls it, `want` says whether it has an item
-CP_DEV void queue_push(uint32_t* q, uint32_t* count, bool want, uint32_t item) {
+CP_DEV void queue_push(uint32_t* q, uint32_t* count, bool want, uint32_t item, uint32_t cap = 0xFFFFFFFFu) {
     const unsigned mask = __ballot_sync(0xFFFFFFFFu, want);
     if (mask == 0) return;
     const int lane = threadIdx.x & 31;
@@ -95,7 +113,9 @@ CP_DEV void queue_push(uint32_t* q, uint32_t* count, bool want, uint32_t item) {
     uint32_t base = 0;
     if (lane == leader) base = atomicAdd(count, (uint32_t)__popc(mask));
     base = __shfl_sync(0xFFFFFFFFu, base, leader);
-    if (want) q[base + __popc(mask & ((1u << lane) - 1u))] = item;
+    const uint32_t pos = base + __popc(mask & ((1u << lane) - 1u));
+    CP_CHECK(!want || pos < cap, 103); (void)cap;
+    if (want) q[pos] = item;
 }
 CP_DEV V3 f4_xyz(float4 v) { return v3(v.x, v.y, v.z); }
 CP_DEV Spec f4_rgb(float4 v) { return spec3(v.x, v.y, v.z); }
@@ -220,6 +240,7 @@ __global__ void k_raygen(DevScene sc, PixelArrays px, PathArrays P, Queues Q, ui
             P.smp_index[pid] = make_uint2((uint32_t)st.index, (uint32_t)(st.index >> 32));
             P.smp_dim[pid] = st.dim;
             P.beta_prev[pid] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0u));
+            CP_CHECK_QUEUE(Q, pid, 2, 104);
             Q.closest[0][pid] = pid;
         }
         px.film_point[i] = fp;
@@ -233,6 +254,7 @@ CP_DEV int shade_kind_of_hit(const DevScene& sc, uint32_t slot, uint32_t bounce)
     if (slot != 0xFFFFFFFFu) {
         const uint32_t src = __float_as_uint(__ldg(&sc.prims[3ull * slot + 2].w));
         if (!(src & kSourceLight) && !(sc.integrator == 0 && bounce >= sc.max_depth)) {
+            CP_CHECK(src < sc.n_materials, 112);
             const uint32_t mt = sc.materials[src].type;
             kind = mt == 0 ? SHADE_MATTE : (mt == 1 ? SHADE_MIRROR : (mt == 2 ? SHADE_GLASS : SHADE_GENERAL));
         }
@@ -255,6 +277,7 @@ __global__ void __launch_bounds__(kTraceBlock, SCHED == SCHED_VOTE ? CPBRT_BLOCK
     uint32_t overflow = 0;
     const uint32_t* __restrict__ queue = Q.closest[cur];
     auto fetch = [&](uint32_t i, Ray* ray, ClosestItem* it) {
+        CP_CHECK_QUEUE(Q, i, 2, 110);
         const uint32_t e = queue[i];
         it->pid = e & ~kMisRayBit; it->is_mis = (e & kMisRayBit) ? 1u : 0u;
         const float4 ro = it->is_mis ? P.mis_o[it->pid] : P.ray_o[it->pid];
@@ -351,7 +374,7 @@ __global__ void __launch_bounds__(256) k_classify(PathArrays P, Queues Q, uint32
                 uint32_t pos = warp_base[warp][k] + before[k];
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                    if (((w >> (8 * j)) & 0xFFu) == (uint32_t)k) Q.shade[k][pos++] = 4u * q + j;
+                    if (((w >> (8 * j)) & 0xFFu) == (uint32_t)k) { CP_CHECK_QUEUE(Q, pos, 1, 105); Q.shade[k][pos++] = 4u * q + j; }
             }
         }
         __syncthreads();      // warp_tot / warp_base are reused by the next trip
@@ -364,6 +387,7 @@ __global__ void __launch_bounds__(kTraceBlock, SCHED == SCHED_VOTE ? CPBRT_BLOCK
     const uint32_t n = Q.counts[kCntShadow];
     uint32_t overflow = 0;
     auto fetch = [&](uint32_t i, Ray* ray, uint32_t* pid) {
+        CP_CHECK_QUEUE(Q, i, 1, 111);
         *pid = Q.shadow[i];
         const float4 so = P.sh_o[*pid], sd = P.sh_d[*pid];
         ray->o = f4_xyz(so); ray->d = f4_xyz(sd); ray->t_max = so.w;
@@ -444,6 +468,7 @@ CP_DEV void emit_direct_lighting(const DevScene& sc, const PathArrays& P, uint32
         uint32_t flags = kPendAny;
         if (sc.n_lights != 0) {
             const uint32_t li = sampler_get_usize_then_2d(sc.sampler, st, sc.n_lights);   // every light's sample_li draws exactly one 2-D sample
+            CP_CHECK(li < sc.n_lights, 109);
             const DevLight& light = sc.lights[li];
             const V3 n = sp.n;
             LightSample ls = light_sample_li(sc, light, sp, st);
@@ -568,6 +593,7 @@ __global__ void __launch_bounds__(128, FUSED ? ShadeBlocksFused<KIND>::value : S
         uint32_t bounce = 0, flags = 0;
         float4 rd = make_float4(0.f, 0.f, 0.f, 0.f);
         if (active) {
+            CP_CHECK_QUEUE(Q, i, 1, 108);
             pid = Q.shade[KIND][i];
             L = resolve_pending(sc, P, pid, f4_rgb(P.L[pid]));
             const float4 ro = P.ray_o[pid];
@@ -666,6 +692,7 @@ __global__ void __launch_bounds__(128, FUSED ? ShadeBlocksFused<KIND>::value : S
                 }
                 bc = __shfl_sync(0xFFFFFFFFu, bc, 0); bsh = __shfl_sync(0xFFFFFFFFu, bsh, 0);
                 const unsigned below = (1u << lane) - 1u;
+                CP_CHECK_QUEUE(Q, bc + __popc(mm) + __popc(mc), 2, 106); CP_CHECK_QUEUE(Q, bsh + __popc(ms), 1, 107);
                 if (want_mis) Q.closest[next][bc + __popc(mm & below)] = pid | kMisRayBit;
                 if (cont) Q.closest[next][bc + __popc(mm) + __popc(mc & below)] = pid;
                 if (want_shadow) Q.shadow[bsh + __popc(ms & below)] = pid;

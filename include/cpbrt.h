@@ -315,6 +315,12 @@ int cpbrt_bvh_host_segments(const cpbrt_ctx* ctx);
 int cpbrt_bvh_device_layout(cpbrt_ctx* ctx, uint64_t node_capacity, uint64_t* n_nodes_out, float* nodes_out,
                             float* records_out, float* frames_out, float* uv_out, int* resident_out);
 
+/* Checked build only (libcpbrt compiled with -DCPBRT_CHECKED: every index into the path state, the queues, the
+ * primitive / node / light / material arrays and the sampler tables is compared with its bound on the device):
+ * number of violations since the library was loaded and the site code of the first one.  Returns 1 from a checked
+ * build, 0 from a normal one (outputs zeroed), negative CPBRT_ERR_* on failure. */
+int cpbrt_check_failures(cpbrt_ctx* ctx, uint64_t* n_failures_out, uint32_t* first_site_out);
+
 /* Bytes this context has copied host -> device since cpbrt_create (counted where the copies are issued):
  * scene arrays, sampler tables, BVH layout, ray batches.  Bookkeeping for the end-to-end measurement. */
 uint64_t cpbrt_h2d_bytes(const cpbrt_ctx* ctx);

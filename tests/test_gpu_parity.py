@@ -827,6 +827,24 @@ def test_c4_million_triangles(cpbrt, oracle):
     assert hit.mean() > 0.4 and full["prim"][hit].max() < 1000008 and (full["t"][hit] > 0).all()
 
 
+def test_checked_build_runs_every_kernel_without_a_bounds_violation():
+    """compute-sanitizer is closed on this GPU pool.  The library's own checked build (libcpbrt_checked.so: every index
+    into the path state, the queues, the primitive / node / light / material arrays and the sampler tables compared
+    with its bound on the device, csrc/device/dmath.cuh CP_CHECK) runs the every-kernel workload of
+    tools/sanitize_workload.py -- all four traversal schedules, one and two lanes, the film-point replay, general
+    materials, both integrators, the device SAH build -- and must count no violation; the checker itself is
+    exercised with one deliberate out-of-range access that must be counted."""
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = os.path.join(root, "curry-pbrt_b200", "libcpbrt_checked.so")
+    assert os.path.exists(lib), "build() did not produce the checked library"
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "sanitize_workload.py")], env=dict(os.environ, CPBRT_LIB=lib),
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+    assert "checked build: True; bounds violations: 0" in out.stdout, out.stdout[-2000:]
+    assert "1 violation(s) counted, site 101" in out.stdout, out.stdout[-2000:]
+
+
 def test_two_gpu_sample_partition_and_nccl_reduce():
     """Needs 2 GPUs on the box (skipped on the 1-GPU test box): torchrun x2 -> tools/check_multi_gpu.py."""
     import subprocess, sys, os, torch

@@ -3,6 +3,12 @@
 
     compute-sanitizer --tool memcheck|initcheck|synccheck|racecheck python tools/sanitize_workload.py
 
+or, where compute-sanitizer is not available (it is closed on the GPU pool this was developed on), for the
+library's own checked build (device-side bounds checks, include/cpbrt.h cpbrt_check_failures):
+
+    python tools/variant_sweep.py build checked
+    CPBRT_LIB=curry-pbrt_b200/build/variants/libcpbrt_checked.so python tools/sanitize_workload.py
+
 Cornell box 48 x 48 (matte, mirror, glass; flat search, then the loop and vote tree walks forced with
 CPBRT_SCHEDULE), one lane and two lanes (several passes: the three-stream bounce schedule and the
 cross-lane event chain), a sample range that starts in the middle (film-point replay), the general
@@ -29,11 +35,13 @@ def main():
         r = cpbrt.Renderer(0); r.upload(scene); r.build_bvh()
         film, st = r.render(**kw)
         assert np.isfinite(film).all()
-        print("%-44s mean %.6f launches %d rays %d" % (tag, float(film.mean()), st.kernel_launches, st.rays_closest + st.rays_any), flush=True)
+        checked, bad, site = r.check_failures()
+        print("%-44s mean %.6f launches %d rays %d%s" % (tag, float(film.mean()), st.kernel_launches, st.rays_closest + st.rays_any,
+                                                       "  bounds violations so far: %d (first site %d)" % (bad, site) if checked else ""), flush=True)
         return r
 
     cornell = cpbrt.Scene.parse(scene_text("cornel_box.pbrt", xres=48, yres=48, spp=6), base_dir=SCENES)
-    for sched in ("flat", "loop", "vote"):
+    for sched in ("flat", "fused", "loop", "vote"):
         os.environ["CPBRT_SCHEDULE"] = sched
         for lanes in ("1", "2"):
             os.environ["CPBRT_LANES"] = lanes
@@ -56,7 +64,19 @@ def main():
     run("directlighting over delta lobes", cpbrt.Scene.parse(scene_text("cornel_box.pbrt", xres=32, yres=32, spp=2, integrator=("directlighting", 4)), base_dir=SCENES)).close()
     os.environ["CPBRT_BVH_BUILD"] = "gpu"; os.environ["CPBRT_BVH_GPU_MINLEN"] = "64"
     run("height field 60 x 50, device SAH levels", cpbrt.Scene.parse(_synthetic_mesh_scene(60, 50, res=48))).close()
-    print("sanitize workload done", flush=True)
+    r = cpbrt.Renderer(0); r.upload(cornell); r.build_bvh(); r.render()
+    checked, bad, site = r.check_failures()
+    if checked and not bad:      # the checker itself: one deliberate violation must be counted, with its site
+        os.environ["CPBRT_CHECK_SELFTEST"] = "1"
+        _, bad2, site2 = r.check_failures()
+        os.environ.pop("CPBRT_CHECK_SELFTEST")
+        print("self-test of the checker: %d violation(s) counted, site %d (expected 1, site 101)" % (bad2, site2), flush=True)
+        if (bad2, site2) != (1, 101):
+            sys.exit(2)
+    r.close()
+    print("sanitize workload done; checked build: %s; bounds violations: %d%s" % (checked, bad, " (first site %d)" % site if bad else ""), flush=True)
+    if checked and bad:
+        sys.exit(1)
 
 
 if __name__ == "__main__":

@@ -18,6 +18,7 @@ VAR = os.path.join(PKG, "build", "variants")
 
 VARIANTS = {
     "base": [],
+    "checked": ["-DCPBRT_CHECKED"],      # device-side bounds checks (dmath.cuh CP_CHECK); run tools/sanitize_workload.py with CPBRT_LIB set to it
     # examples of what has been swept (profiles/r01_s3_variant_sweeps.jsonl):
     "closest_loop_8_blocks": ["-DCPBRT_BLOCKS_CLOSEST_LOOP=8"],
     "loop_refill_12": ["-DCPBRT_REFILL_CLOSEST_LOOP=12", "-DCPBRT_REFILL_SHADOW_LOOP=12"],
