@@ -854,4 +854,4 @@ def test_two_gpu_sample_partition_and_nccl_reduce():
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                           "--master-port", "29533", os.path.join(root, "tools", "check_multi_gpu.py")], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
-    assert "multi-gpu check" in out.stdout and "shared-build check" in out.stdout and "resident shared-build check" in out.stdout and out.stdout.count("-> OK") == 3, out.stdout[-2000:]
+    assert "multi-gpu check" in out.stdout and "shared-build check" in out.stdout and "resident shared-build check" in out.stdout and "mismatched-scene check" in out.stdout and out.stdout.count("-> OK") == 4, out.stdout[-2000:]

@@ -83,6 +83,30 @@ def main():
             resident, np.array_equal(order3, order_host), err3.max(), "OK" if ok3 else "FAIL"))
     os.environ.pop("CPBRT_BVH_BUILD")
     ok = ok and ok3
+    # fourth phase: ranks that disagree about the scene (rank 0: the Cornell box, the others: sphere.pbrt) must ALL come
+    # back from the shared build with an error -- nobody may be left waiting inside a broadcast -- and the same
+    # contexts must still work afterwards with the right scene
+    os.environ["CPBRT_BVH_SHARE"] = "1"
+    other = cpbrt.Scene.parse(scene_text("sphere.pbrt", xres=160, yres=120, spp=16), base_dir=SCENES)
+    r4 = cpbrt.Renderer(local); r4.upload(scene if rank == 0 else other)
+    idt4 = torch.zeros(cpbrt.abi.COMM_ID_BYTES, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt4.copy_(torch.tensor(list(cpbrt.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt4, 0)
+    r4.comm_init(world, rank, bytes(idt4.cpu().tolist()))
+    failed = 0.0
+    try:
+        r4.build_bvh()
+    except cpbrt.CpbrtError:
+        failed = 1.0
+    all_failed = torch.tensor([failed], device="cuda"); dist.all_reduce(all_failed, op=dist.ReduceOp.MIN)
+    r4.upload(scene); r4.build_bvh(); film4, _ = r4.render()
+    os.environ.pop("CPBRT_BVH_SHARE")
+    if rank == 0:
+        ok4 = all_failed.item() == 1.0 and np.array_equal(film4.view(np.uint32), film.view(np.uint32))
+        print("mismatched-scene check: every rank got an error=%s, contexts usable afterwards and film identical=%s -> %s" % (
+            all_failed.item() == 1.0, np.array_equal(film4.view(np.uint32), film.view(np.uint32)), "OK" if ok4 else "FAIL"))
+        ok = ok and ok4
     dist.barrier()
     dist.destroy_process_group()
     return 0 if ok else 1
