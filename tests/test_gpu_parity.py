@@ -15,6 +15,21 @@ from test_oracle import _synthetic_mesh_scene
 
 pytestmark = pytest.mark.gpu
 
+
+def _bounded(name, value, limit):
+    """assert value <= limit; with CPBRT_OBSERVE=<file> the observed value is appended there, which is how the limits
+    below were set.  Observed on B200 (tests/golden/observed_image_differences.txt): at most ONE pixel of a test image
+    (6.9e-5 of 14 400) differs from the oracle by more than 1e-3 relative -- first-hit shading and sphere.pbrt, where an
+    ulp-level libm difference flips a discrete decision on a silhouette -- and no pixel at all in the path-traced,
+    textured, general-material, environment-map, thin-lens and recursive direct-lighting images; the image RMSE stays
+    below 1e-4 absolute everywhere.  Limits: 5e-4 of the pixels (a handful of flipped decisions), RMSE 1e-3 of the mean."""
+    import os
+    path = os.environ.get("CPBRT_OBSERVE")
+    if path:
+        with open(path, "a") as f:
+            f.write("%s %.6g %.6g\n" % (name, float(value), float(limit)))
+    assert value <= limit, (name, value, limit)
+
 NO_HIT = 0xFFFFFFFF
 
 
@@ -400,7 +415,7 @@ def test_first_hit_shading(cornell, spheres, mesh):
         o, _, os_ = w.render(integrator=1, max_depth=0)
         assert gs.rays_closest == os_["rays_closest"] or abs(gs.rays_closest - os_["rays_closest"]) <= 1e-4 * os_["rays_closest"]
         bad = (_relerr(g, o).max(axis=2) > 1e-3)
-        assert bad.mean() <= 1e-3, bad.mean()
+        _bounded("first_hit_shading", bad.mean(), 5e-4)
         assert np.isfinite(g).all() and g.mean() > 1e-3
 
 
@@ -410,10 +425,10 @@ def test_full_path_image(cornell, mesh):
         g, gs = r.render()
         o, _, os_ = w.render()
         bad = (_relerr(g, o).max(axis=2) > 1e-3)
-        assert bad.mean() <= 0.01, bad.mean()
+        _bounded("full_path", bad.mean(), 5e-4)
         # image-level: RMSE far inside the MC noise band (the noise itself is ~0.1-0.3 of the mean at 8 spp)
         rmse = float(np.sqrt(np.mean((g - o) ** 2)))
-        assert rmse <= 0.02 * float(o.mean()) + 1e-4, rmse
+        _bounded("full_path_rmse", (rmse - 1e-4) / float(o.mean()), 1e-3)
         # the device neither generates nor counts the reference's last, result-less ray of a path
         expect = os_["rays_closest"] - os_["rays_unused_last"]
         assert os_["rays_unused_last"] > 0 and abs(gs.rays_closest - expect) <= 2e-3 * expect
@@ -456,7 +471,7 @@ def test_directlighting_scene(spheres):
     g, gs = r.render()
     o, _, os_ = w.render()
     bad = (_relerr(g, o).max(axis=2) > 1e-3)
-    assert bad.mean() <= 2e-3, bad.mean()
+    _bounded("directlighting_spheres", bad.mean(), 5e-4)
     assert gs.rays_any == os_["rays_any"] or abs(gs.rays_any - os_["rays_any"]) <= 1e-3 * os_["rays_any"]
 
 
@@ -482,7 +497,7 @@ def test_queues_at_full_capacity(cpbrt, oracle, make_scene):
     r = cpbrt.Renderer(0); r.upload(scene); r.build_bvh()
     g, _ = r.render(samples_per_pass=4)
     o, _, _ = oracle.OracleWorld(scene).render()
-    assert (_relerr(g, o).max(axis=2) > 1e-3).mean() <= 0.01
+    _bounded("mis_and_continuation_queue", (_relerr(g, o).max(axis=2) > 1e-3).mean(), 5e-4)
 
 
 def test_textured_matte(cpbrt, oracle):
@@ -503,7 +518,7 @@ def test_textured_matte(cpbrt, oracle):
     g, _ = r.render()
     o, _, _ = w.render()
     bad = (_relerr(g, o).max(axis=2) > 1e-3)
-    assert bad.mean() <= 0.01, bad.mean()
+    _bounded("textured_matte", bad.mean(), 5e-4)
 
 
 def test_device_film_output_stage(cornell):
@@ -576,9 +591,9 @@ def test_general_materials(cpbrt, oracle, name):
     o, _, os_ = w.render()
     assert np.isfinite(g).all()
     bad = (_relerr(g, o).max(axis=2) > 1e-3)
-    assert bad.mean() <= 0.02, (name, bad.mean())
+    _bounded("general_material_" + name, bad.mean(), 5e-4)
     rmse = float(np.sqrt(np.mean((g - o) ** 2)))
-    assert rmse <= 0.03 * float(o.mean()) + 1e-4, (name, rmse)
+    _bounded("general_material_rmse_" + name, (rmse - 1e-4) / float(o.mean()), 1e-3)
     assert gs.nan_dropped == os_["nan_dropped"]
     # first-hit shading of the same scene
     g1, _ = r.render(first_hit_only=True)
@@ -605,9 +620,9 @@ def test_infinite_area_light(cpbrt, oracle, envmap, integrator):
     o, _, os_ = w.render()
     assert np.isfinite(g).all() and o.mean() > 0.05
     bad = (_relerr(g, o).max(axis=2) > 1e-3)
-    assert bad.mean() <= 0.02, bad.mean()
+    _bounded("infinite_area_light", bad.mean(), 5e-4)
     rmse = float(np.sqrt(np.mean((g - o) ** 2)))
-    assert rmse <= 0.03 * float(o.mean()) + 1e-4, rmse
+    _bounded("infinite_area_light_rmse", (rmse - 1e-4) / float(o.mean()), 1e-3)
     assert abs(gs.rays_any - os_["rays_any"]) <= 2e-3 * os_["rays_any"]
 
 
@@ -629,7 +644,7 @@ def test_hdr_exr_environment_map(cpbrt, oracle, tmp_path):
     o, _, os_ = w.render()
     assert np.isfinite(g).all() and o.mean() > 0.05
     bad = (_relerr(g, o).max(axis=2) > 1e-3)
-    assert bad.mean() <= 0.02, bad.mean()
+    _bounded("exr_environment_map", bad.mean(), 5e-4)
     assert abs(gs.rays_any - os_["rays_any"]) <= 2e-3 * os_["rays_any"]
 
 
@@ -729,7 +744,7 @@ def test_thin_lens_camera(cpbrt, oracle):
         assert np.abs(a[:, 0:2] - b[0, 0:2]).max() > 1.0      # origins really are spread over the lens
     g, _ = r.render()
     o, _, _ = w.render()
-    assert (_relerr(g, o).max(axis=2) > 1e-3).mean() <= 0.01
+    _bounded("thin_lens", (_relerr(g, o).max(axis=2) > 1e-3).mean(), 5e-4)
 
 
 @pytest.mark.parametrize("material", [None, "uber", "mix"])
@@ -748,7 +763,7 @@ def test_directlighting_recursion_over_delta_lobes(cpbrt, oracle, material):
     g, gs = r.render()
     o, _, os_ = w.render()
     bad = (_relerr(g, o).max(axis=2) > 1e-3)
-    assert bad.mean() <= 5e-3, bad.mean()
+    _bounded("direct_recursion_" + str(material), bad.mean(), 5e-4)
     assert abs(gs.rays_closest - os_["rays_closest"]) <= 1e-3 * os_["rays_closest"]
     assert abs(gs.rays_any - os_["rays_any"]) <= 1e-3 * os_["rays_any"]
     # the tree really branches: more closest-hit queries than camera samples + MIS rays of a depth-1 render
