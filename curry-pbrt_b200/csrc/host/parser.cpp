@@ -110,6 +110,73 @@ static bool parse_f32(const std::string& w, float* out) {
     return end && *end == 0;
 }
 
+// Numbers are almost all of a big scene file (a million-triangle `trianglemesh` literal is 4.5 million of them), so
+// the common shape -- [-]digits[.digits][e[+-]digits] -- is read straight from the text, without a std::string, a
+// Token or strtof per number:
+//   * all digits, fits i32                       -> Integer, as parse_i32
+//   * mantissa <= 2^53 and |decimal exponent| <= 22 -> one IEEE double operation m * 10^e or m / 10^e (both operands
+//     exact, so the double is the correctly rounded value), then double -> float.  The two roundings can only differ
+//     from one correct rounding to f32 when the double lands EXACTLY on the midpoint of two neighbouring floats (its
+//     low 29 mantissa bits are 0x10000000): those, subnormal / overflowing magnitudes and everything else that is not
+//     the common shape take the strtof path (parse_f32) as before.
+// Same values bit for bit (tests/lexer_number_check.cpp compares millions of literals with strtof); returns
+// 0 = not a number, 1 = Integer, 2 = Float.
+int parse_number(const char* b, size_t n, int32_t* iv, float* fv) {
+    static const double p10[23] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+    size_t k = 0;
+    bool neg = false;
+    if (k < n && (b[k] == '-' || b[k] == '+')) { neg = b[k] == '-'; ++k; }
+    uint64_t m = 0; int sig = 0, int_digits = 0, frac_digits = 0; int dropped = 0; bool inexact = false;
+    auto take = [&](char c) {
+        if (sig < 19) { m = m * 10 + (uint64_t)(c - '0'); if (m) ++sig; }
+        else { ++dropped; if (c != '0') inexact = true; }
+    };
+    while (k < n && b[k] >= '0' && b[k] <= '9') { take(b[k]); ++k; ++int_digits; }
+    const size_t after_int = k;
+    bool is_int = int_digits > 0 && k == n;
+    if (is_int) {
+        // parse_i32: no overflow
+        if (sig <= 10 && dropped == 0 && m <= (neg ? 2147483648ull : 2147483647ull)) { *iv = neg ? (int32_t)(-(int64_t)m) : (int32_t)m; return 1; }
+    }
+    int dropped_int = dropped;
+    if (k < n && b[k] == '.') { ++k; while (k < n && b[k] >= '0' && b[k] <= '9') { take(b[k]); ++k; ++frac_digits; } }
+    (void)after_int;
+    if (int_digits + frac_digits == 0) goto slow;
+    {
+        int e10 = 0;
+        if (k < n && (b[k] == 'e' || b[k] == 'E')) {
+            ++k;
+            bool eneg = false;
+            if (k < n && (b[k] == '+' || b[k] == '-')) { eneg = b[k] == '-'; ++k; }
+            int ed = 0, ev = 0;
+            while (k < n && b[k] >= '0' && b[k] <= '9') { if (ev < 100000) ev = ev * 10 + (b[k] - '0'); ++k; ++ed; }
+            if (ed == 0) return 0;
+            e10 = eneg ? -ev : ev;
+        }
+        if (k != n) goto slow;
+        // digits beyond the 19th were dropped: those before the point scale the value, any non-zero one makes it inexact
+        const int frac_kept = frac_digits - (dropped - dropped_int);
+        e10 += dropped_int - frac_kept;
+        if (inexact) goto slow;
+        if (m == 0) { *fv = neg ? -0.f : 0.f; return 2; }
+        if (m > (1ull << 53) || e10 < -22 || e10 > 22) goto slow;
+        const double d = e10 >= 0 ? (double)m * p10[e10] : (double)m / p10[-e10];
+        if (!(d >= 1e-30 && d <= 1e30)) goto slow;
+        uint64_t bits; memcpy(&bits, &d, 8);
+        const uint32_t low = (uint32_t)(bits & 0x1FFFFFFFu);
+        if (low >= 0x0FFFFFFFu && low <= 0x10000001u) goto slow;
+        const float f = (float)d;
+        *fv = neg ? -f : f;
+        return 2;
+    }
+slow: {
+        const std::string w(b, n);
+        if (parse_i32(w, iv)) return 1;
+        if (parse_f32(w, fv)) return 2;
+        return 0;
+    }
+}
+
 namespace {
 struct Lexer {
     const std::string& s;
@@ -134,10 +201,12 @@ struct Lexer {
     }
     // word (lex.rs:55-61)
     bool word(size_t* end) const {
-        size_t p = s.find_first_of(" \n\t]\r", index + 1);
-        if (p == std::string::npos) return false;
-        *end = p;
-        return true;
+        const char* d = s.data();
+        for (size_t p = index + 1, n = s.size(); p < n; ++p) {
+            const char ch = d[p];
+            if (ch == ' ' || ch == '\n' || ch == '\t' || ch == ']' || ch == '\r') { *end = p; return true; }
+        }
+        return false;
     }
     // Between '[' and ']' the reference pushes ordinary tokens and drains them into
     // Token::Array at ']' (lex.rs:127-155); we append the reduced BasicType directly, which is
@@ -187,6 +256,16 @@ struct Lexer {
             else if (c == '[') {
                 if (in_array) fail("nested '['");
                 in_array = true; cur_array.clear(); arr_line = line; arr_col = column;
+                // one allocation for the array instead of a dozen doublings (a mesh literal holds millions of
+                // elements): elements are separated by white space, so the separators up to ']' bound their number
+                if (const void* close = memchr(s.data() + index, ']', s.size() - index)) {
+                    const char* b = s.data() + index + 1; const char* e = (const char*)close;
+                    if (e - b > 4096) {
+                        size_t seps = 0;
+                        for (const char* q = b; q < e; ++q) seps += (*q == ' ' || *q == '\n' || *q == '\t' || *q == '\r') ? 1u : 0u;
+                        cur_array.reserve(seps + 1);
+                    }
+                }
                 ++column; ++index;
             }
             else if (c == ']') {
@@ -219,12 +298,16 @@ struct Lexer {
             else if (c == '-' || (c >= '0' && c <= '9')) {
                 size_t end;
                 if (!word(&end)) break;
-                std::string w = s.substr(index, end - index);
-                Token t;
-                if (parse_i32(w, &t.i)) t.kind = Token::Integer;
-                else if (parse_f32(w, &t.f)) t.kind = Token::Float;
-                else fail("Cant parse number \"" + w + "\"");
-                push(std::move(t));
+                int32_t iv = 0; float fv = 0.f;
+                const int kind = parse_number(s.data() + index, end - index, &iv, &fv);
+                if (kind == 0) fail("Cant parse number \"" + s.substr(index, end - index) + "\"");
+                if (in_array) {      // the bulk: no Token in between
+                    Basic b; b.kind = kind == 1 ? Basic::Int : Basic::Flt; b.i = iv; b.f = fv;
+                    cur_array.push_back(b);
+                } else {
+                    Token t; t.kind = kind == 1 ? Token::Integer : Token::Float; t.i = iv; t.f = fv;
+                    push(std::move(t));
+                }
                 column += end - index;
                 index = end;
             }

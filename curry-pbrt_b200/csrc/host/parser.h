@@ -42,6 +42,9 @@ struct Token {
     uint32_t line = 0, column = 0;
 };
 
+// One numeric literal of the scene text (parser.cpp): 0 = not a number, 1 = Integer (*iv), 2 = Float (*fv).
+int parse_number(const char* begin, size_t n, int32_t* iv, float* fv);
+
 // parse_lex (lex.rs:202-205).  `text` may be given directly (file is then only a label).
 std::vector<Token> lex_file(const std::string& path);
 std::vector<Token> lex_text(const std::string& text, const std::string& file_label);

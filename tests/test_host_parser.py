@@ -245,3 +245,19 @@ def test_exr_files_written_by_openexr(cpbrt, name):
     got = np.ctypeslib.as_array(d.texels, shape=(int(d.n_texels),))[tex.offset:tex.offset + W * H * 3].reshape(H, W, 3)
     expect = src.astype(np.float16).astype(np.float32) if name.endswith("half") else src
     assert np.array_equal(got, expect)
+
+
+def test_lexer_number_fast_path_equals_strtof(cpbrt, tmp_path):
+    """The scene lexer reads the common numeric literals without strtof (csrc/host/parser.cpp, parse_number: integer
+    grammar, or one exact double operation + a midpoint guard, strtof for everything else).  tests/lexer_number_check.cpp
+    compares it with strtof / the i32 grammar on 600 000 literals of every shape a scene file holds -- "%.9g" and
+    "%.17g" floats over the whole f32 range, indices, exponents, 20-digit mantissas, exact midpoints of two floats,
+    negative zeros, leading zeros -- bit for bit."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "curry-pbrt_b200")
+    exe = str(tmp_path / "lexer_number_check")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", os.path.join(root, "tests", "lexer_number_check.cpp"), "-o", exe,
+                           "-L", pkg, "-l:libcpbrt.so", "-Wl,-rpath," + pkg, "-lm"])
+    out = subprocess.run([exe, "600000"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and " 0 mismatches" in out.stdout, out.stdout[-2000:]
