@@ -261,3 +261,30 @@ def test_lexer_number_fast_path_equals_strtof(cpbrt, tmp_path):
                            "-L", pkg, "-l:libcpbrt.so", "-Wl,-rpath," + pkg, "-lm"])
     out = subprocess.run([exe, "600000"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and " 0 mismatches" in out.stdout, out.stdout[-2000:]
+
+
+def test_cornell_triangles_against_an_independent_reader(cpbrt):
+    """The host parser and scene builder are shared by the product and by the oracle's input, so an error there would
+    cancel in every parity test.  This reads the triangles of scenes/cornel_box.pbrt with a reader that shares nothing
+    with csrc/host (a regular expression over the text + numpy): every `trianglemesh` block in file order, one triangle
+    per index triple with the vertices in index order (triangle.rs:30-36) -- the object "ball_and_box" is instanced
+    right after its definition, so file order is push order (scene.rs:84-140) -- and compares them with the flattened
+    scene description vertex for vertex, bit for bit; the 32 + 1 primitives must all survive the camera clipper."""
+    import re
+    text = open(os.path.join(SCENES, "cornel_box.pbrt")).read()
+    text = re.sub(r"#[^\n]*", "", text)
+    want = []
+    for m in re.finditer(r'Shape\s+"trianglemesh"\s+"integer indices"\s*\[([^\]]*)\]\s*"point P"\s*\[([^\]]*)\]', text):
+        idx = np.array(m.group(1).split(), np.int64).reshape(-1, 3)
+        pts = np.array(m.group(2).split(), np.float32).reshape(-1, 3)
+        want.append(pts[idx])                       # [n_tris, 3 vertices, xyz]
+    want = np.concatenate(want)
+    assert want.shape == (32, 3, 3)
+    s = cpbrt.Scene.load(os.path.join(SCENES, "cornel_box.pbrt"))
+    d = s.desc
+    tri_prims = [d.primitives[i] for i in range(d.n_primitives) if d.primitives[i].shape.kind == cpbrt.abi.SHAPE_TRIANGLE]
+    got = np.array([[[d.triangles[p.shape.data].p[v][c] for c in range(3)] for v in range(3)] for p in tri_prims], np.float32)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert all(p.shape.xform == -1 for p in tri_prims)            # no transform is in force where the meshes are declared
+    # the first two triangles are the light quad: emissive primitives, one AreaLight each (scene.rs:91-95)
+    assert [p.light for p in tri_prims[:2]] == [0, 1] and all(p.light == -1 for p in tri_prims[2:])
