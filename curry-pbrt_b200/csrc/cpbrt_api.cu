@@ -180,7 +180,6 @@ void host_tri_frame(const float p[9], float4 out[3]) {
     out[2] = make_float4(y[2], nl[0], nl[1], nl[2]);
 }
 
-uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 
 int grid_for(const cpbrt_ctx* ctx, int blocks_per_sm) { return ctx->sm_count * blocks_per_sm; }

@@ -132,7 +132,6 @@ int parse_number(const char* b, size_t n, int32_t* iv, float* fv) {
         else { ++dropped; if (c != '0') inexact = true; }
     };
     while (k < n && b[k] >= '0' && b[k] <= '9') { take(b[k]); ++k; ++int_digits; }
-    const size_t after_int = k;
     bool is_int = int_digits > 0 && k == n;
     if (is_int) {
         // parse_i32: no overflow
@@ -140,7 +139,6 @@ int parse_number(const char* b, size_t n, int32_t* iv, float* fv) {
     }
     int dropped_int = dropped;
     if (k < n && b[k] == '.') { ++k; while (k < n && b[k] >= '0' && b[k] <= '9') { take(b[k]); ++k; ++frac_digits; } }
-    (void)after_int;
     if (int_digits + frac_digits == 0) goto slow;
     {
         int e10 = 0;
