@@ -18,7 +18,10 @@ VAR = os.path.join(PKG, "build", "variants")
 
 VARIANTS = {
     "base": [],
-    "checked": ["-DCPBRT_CHECKED"],      # device-side bounds checks (dmath.cuh CP_CHECK); run tools/sanitize_workload.py with CPBRT_LIB set to it
+    "checked": ["-DCPBRT_CHECKED"],
+    "shade_64_threads": ["-DCPBRT_SHADE_THREADS=64"],
+    "shade_32_threads": ["-DCPBRT_SHADE_THREADS=32"],
+    "shade_256_threads": ["-DCPBRT_SHADE_THREADS=256"],      # device-side bounds checks (dmath.cuh CP_CHECK); run tools/sanitize_workload.py with CPBRT_LIB set to it
     # examples of what has been swept (profiles/r01_s3_variant_sweeps.jsonl):
     "closest_loop_8_blocks": ["-DCPBRT_BLOCKS_CLOSEST_LOOP=8"],
     "loop_refill_12": ["-DCPBRT_REFILL_CLOSEST_LOOP=12", "-DCPBRT_REFILL_SHADOW_LOOP=12"],
@@ -57,7 +60,7 @@ def build(names):
     import build as B
     B.build()
     os.makedirs(VAR, exist_ok=True)
-    others = [os.path.join(B.OBJ, f) for f in os.listdir(B.OBJ) if f.endswith(".o") and f != "cpbrt_api.cu.o"]
+    others = [os.path.join(B.OBJ, f) for f in os.listdir(B.OBJ) if f.endswith(".o") and f not in ("cpbrt_api.cu.o", "cpbrt_api_checked.o")]
     procs = []
     for name in names:
         obj = os.path.join(VAR, "cpbrt_api_%s.o" % name)
