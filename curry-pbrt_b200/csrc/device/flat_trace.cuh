@@ -46,6 +46,13 @@ static constexpr int kFlatMaxPrims = 64;
 #define CPBRT_BLOCKS_FLAT_SHADOW 6
 #endif
 
+#ifndef CPBRT_FLAT_UNROLL
+// Items per trip of the edge phase.  Alone the trace kernels are 1-3 % faster unrolled by 4, but the frame -- two pass
+// lanes, this kernel sharing the SMs and their instruction caches with the 300 KB matte kernel -- is 1.7 % faster
+// with the rolled loop (888 -> 903 Msamples/s, repeatable to 0.1 %; 2 and 8 are worse: profiles/r02_block_count_sweep.txt).
+#define CPBRT_FLAT_UNROLL 1
+#endif
+static constexpr int kFlatUnroll = CPBRT_FLAT_UNROLL;
 // Tables in shared memory (copied from DevScene::flat at kernel start), float4 units:
 //   pairs  [c * pstride + 3 * k + 0..2]        item k of phase 1 for a ray whose dominant axis is c (components
 //                                              rotated like permute() of shapes.cuh): two triangles that share an
@@ -97,7 +104,7 @@ CP_DEV uint64_t flat_edge_candidates(const DevScene& sc, uint32_t kz, V3 op, flo
         if (lo < sc.flat_items) {
             const uint32_t cnt = sc.flat_items - lo < 16u ? sc.flat_items - lo : 16u;
             uint32_t bit = 1u, mm = 0u;
-#pragma unroll 4
+#pragma unroll kFlatUnroll
             for (uint32_t k = 0; k < cnt; ++k) {
                 const float4 a = flat_smem[base + 3u * (lo + k)], b = flat_smem[base + 3u * (lo + k) + 1u], c = flat_smem[base + 3u * (lo + k) + 2u];
                 // sheared x, y of the four vertices (the z components do not enter the edge functions)

@@ -19,6 +19,9 @@ VAR = os.path.join(PKG, "build", "variants")
 VARIANTS = {
     "base": [],
     "checked": ["-DCPBRT_CHECKED"],
+    "flat_unroll_2": ["-DCPBRT_FLAT_UNROLL=2"],
+    "flat_unroll_4": ["-DCPBRT_FLAT_UNROLL=4"],
+    "flat_unroll_8": ["-DCPBRT_FLAT_UNROLL=8"],
     "shade_64_threads": ["-DCPBRT_SHADE_THREADS=64"],
     "shade_32_threads": ["-DCPBRT_SHADE_THREADS=32"],
     "shade_256_threads": ["-DCPBRT_SHADE_THREADS=256"],      # device-side bounds checks (dmath.cuh CP_CHECK); run tools/sanitize_workload.py with CPBRT_LIB set to it
