@@ -5,6 +5,7 @@
 // src/scene/texture_map.rs:17-51, src/geometry/shape/mod.rs:198-216), flattened into the
 // index-based arrays of cpbrt_scene_desc.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <fstream>
@@ -12,6 +13,7 @@
 #include <memory>
 
 #include "scene_host.h"
+#include "../bvh_build.h"      // parallel_for
 
 namespace cpbrt_host {
 
@@ -369,20 +371,24 @@ struct Builder {
     }
     // create_triangles (triangle.rs:30-36): one Triangle per index triple; uvs default
     void add_mesh(const std::vector<uint64_t>& idx, const float* p, size_t nv, std::vector<HShape>* out) {
-        size_t nt = idx.size() / 3;
-        sd->triangles.reserve(sd->triangles.size() + nt);
-        out->reserve(out->size() + nt);
-        for (size_t t = 0; t < nt; ++t) {
-            cpbrt_triangle tri;
-            for (int k = 0; k < 3; ++k) {
-                uint64_t v = idx[t * 3 + k];
-                if (v >= nv) fail("trianglemesh: vertex index out of range");
-                tri.p[k][0] = p[v * 3]; tri.p[k][1] = p[v * 3 + 1]; tri.p[k][2] = p[v * 3 + 2];
+        const size_t nt = idx.size() / 3, t0 = sd->triangles.size(), s0 = out->size();
+        sd->triangles.resize(t0 + nt);
+        out->resize(s0 + nt);
+        std::atomic<bool> bad(false);
+        cpbrt::parallel_for(nt, 1 << 15, [&](uint64_t lo, uint64_t hi) {
+            for (uint64_t t = lo; t < hi; ++t) {
+                cpbrt_triangle tri;
+                for (int k = 0; k < 3; ++k) {
+                    const uint64_t v = idx[t * 3 + k];
+                    if (v >= nv) { bad.store(true); return; }
+                    tri.p[k][0] = p[v * 3]; tri.p[k][1] = p[v * 3 + 1]; tri.p[k][2] = p[v * 3 + 2];
+                }
+                tri.uv[0][0] = 0.f; tri.uv[0][1] = 0.f; tri.uv[1][0] = 1.f; tri.uv[1][1] = 0.f; tri.uv[2][0] = 1.f; tri.uv[2][1] = 1.f;
+                sd->triangles[t0 + t] = tri;
+                (*out)[s0 + t] = HShape{CPBRT_SHAPE_TRIANGLE, (uint32_t)(t0 + t), -1};
             }
-            tri.uv[0][0] = 0.f; tri.uv[0][1] = 0.f; tri.uv[1][0] = 1.f; tri.uv[1][1] = 0.f; tri.uv[2][0] = 1.f; tri.uv[2][1] = 1.f;
-            sd->triangles.push_back(tri);
-            out->push_back({CPBRT_SHAPE_TRIANGLE, (uint32_t)sd->triangles.size() - 1, -1});
-        }
+        });
+        if (bad.load()) fail("trianglemesh: vertex index out of range");
     }
     void load_ply(const std::string& path, std::vector<HShape>* out) {
         std::ifstream f(path, std::ios::binary);
@@ -419,14 +425,20 @@ struct Builder {
         f.read(body.data(), (std::streamsize)body.size());
         if (!f) fail("ply: truncated file");
         std::vector<float> verts(nv * 3);
-        for (size_t i = 0; i < nv; ++i) memcpy(&verts[i * 3], &body[i * 32], 12);     // x y z; normals and uvs are not kept (plymesh.rs:82-131)
+        cpbrt::parallel_for(nv, 1 << 16, [&](uint64_t lo, uint64_t hi) {
+            for (uint64_t i = lo; i < hi; ++i) memcpy(&verts[i * 3], &body[i * 32], 12);     // x y z; normals and uvs are not kept (plymesh.rs:82-131)
+        });
         std::vector<uint64_t> idx(nf * 3);
         const char* fp = body.data() + nv * 32;
-        for (size_t i = 0; i < nf; ++i) {
-            if ((uint8_t)fp[i * 13] != 3) fail("ply: only triangles");
-            int32_t v[3]; memcpy(v, fp + i * 13 + 1, 12);
-            for (int k = 0; k < 3; ++k) idx[i * 3 + k] = (uint64_t)(int64_t)v[k];
-        }
+        std::atomic<bool> not_tri(false);
+        cpbrt::parallel_for(nf, 1 << 16, [&](uint64_t lo, uint64_t hi) {
+            for (uint64_t i = lo; i < hi; ++i) {
+                if ((uint8_t)fp[i * 13] != 3) { not_tri.store(true); return; }
+                int32_t v[3]; memcpy(v, fp + i * 13 + 1, 12);
+                for (int k = 0; k < 3; ++k) idx[i * 3 + k] = (uint64_t)(int64_t)v[k];
+            }
+        });
+        if (not_tri.load()) fail("ply: only triangles");
         add_mesh(idx, verts.data(), nv, out);
     }
 
@@ -442,11 +454,19 @@ struct Builder {
     }
     // TransformCamera::clip + PerspectiveCamera::clip (camera/mod.rs:58-63, perspective.rs:54-78)
     bool clip(const HPrimitive& p) const {
-        if (p.material < 0) return false;
+        const int r = clip_status(p);
+        if (r == 2) fail("clipper: point at w == 0 (the reference panics here)");
+        return r == 1;
+    }
+    // 0 = kept, 1 = clipped, 2 = a corner projects to w == 0.  Const and allocation-free after its first call on a
+    // thread, so the primitives of a big mesh are tested in parallel (parse, "Shape").
+    int clip_status(const HPrimitive& p) const {
+        if (p.material < 0) return 0;
         B3 b = base_bound(p.shape);
         // chain links from innermost outwards; the outermost link is the TransformShape the
         // clipper composes with world->camera (shape_apply, shape/mod.rs:86-91)
-        std::vector<int32_t> chain;
+        static thread_local std::vector<int32_t> chain;
+        chain.clear();
         for (int32_t x = p.shape.xform; x >= 0; x = sd->transforms[x].outer) chain.push_back(x);
         if (cam.has_world) {
             Xf w2c = cam.stored.inverse();
@@ -462,11 +482,11 @@ struct Builder {
             V3 pt = (corner % 2 == 0) ? b.mn : b.mx;   // Index<usize> for Bounds: index % 2 (bounds.rs:162-169)
             bool ok = true;
             V3 r = apply_point(c2r, pt, &ok);
-            if (!ok) fail("clipper: point at w == 0 (the reference panics here)");
+            if (!ok) return 2;
             bool clipped = r.z < 0.f || r.x >= cam.res_x || r.x < 0.f || r.y >= cam.res_y || r.y < 0.f;
-            if (!clipped) return false;
+            if (!clipped) return 0;
         }
-        return true;
+        return 1;
     }
     void add_primitive(const HPrimitive& p, bool use_clipper) {
         if (use_clipper && clip(p)) { ++sd->n_clipped; return; }
@@ -511,8 +531,26 @@ struct Builder {
                 int32_t rec = add_transform(st.transform);
                 for (auto& s : shapes) s.xform = rec;
             }
-            for (auto& s : shapes) {
+            // a mesh of a million triangles: the clipper (two matrix products and sixteen point transforms per
+            // primitive) runs on all host threads, the primitives are then pushed in order as before
+            std::vector<uint8_t> clip_flag;
+            if (shapes.size() >= 65536 && !st.has_area_light && !st.has_object_name && st.material >= 0) {
+                clip_flag.resize(shapes.size());
+                cpbrt::parallel_for(shapes.size(), 1 << 14, [&](uint64_t lo, uint64_t hi) {
+                    for (uint64_t i = lo; i < hi; ++i) clip_flag[i] = (uint8_t)clip_status(HPrimitive{shapes[i], st.material, -1});
+                });
+                for (uint8_t f : clip_flag) if (f == 2) fail("clipper: point at w == 0 (the reference panics here)");
+                sd->primitives.reserve(sd->primitives.size() + shapes.size());
+            }
+            for (size_t si = 0; si < shapes.size(); ++si) {
+                auto& s = shapes[si];
                 HPrimitive p{s, -1, -1};
+                if (!clip_flag.empty()) {
+                    if (clip_flag[si]) { ++sd->n_clipped; continue; }
+                    p.material = st.material;
+                    add_primitive(p, false);
+                    continue;
+                }
                 if (st.has_area_light) {
                     cpbrt_light l{};
                     l.type = CPBRT_LIGHT_AREA;

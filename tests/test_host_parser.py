@@ -288,3 +288,33 @@ def test_cornell_triangles_against_an_independent_reader(cpbrt):
     assert all(p.shape.xform == -1 for p in tri_prims)            # no transform is in force where the meshes are declared
     # the first two triangles are the light quad: emissive primitives, one AreaLight each (scene.rs:91-95)
     assert [p.light for p in tri_prims[:2]] == [0, 1] and all(p.light == -1 for p in tri_prims[2:])
+
+
+def test_big_mesh_parallel_clipper_equals_sequential(cpbrt):
+    """Meshes of >= 65 536 triangles run the camera clipper (perspective.rs:54-78) on all host threads and create
+    their triangles in parallel (csrc/host/scene_build.cpp); smaller ones take the sequential path.  The same 80 000
+    triangles -- a strip far wider than the view, so that many are clipped -- as ONE mesh and as four meshes of
+    20 000 must give the same primitives in the same order."""
+    rng = np.random.default_rng(5)
+    n = 80000
+    c = np.stack([rng.uniform(-40, 40, n), rng.uniform(-3, 3, n), rng.uniform(-2, 30, n)], 1).astype(np.float32)
+    tris = (c[:, None, :] + rng.normal(scale=0.05, size=(n, 3, 3))).astype(np.float32)
+    head = ('Camera "perspective" "float fov" [40]\nSampler "halton" "integer pixelsamples" [1]\n'
+            'Film "image" "integer xresolution" [64] "integer yresolution" [48]\nIntegrator "path"\nWorldBegin\nMaterial "matte"\n')
+
+    def mesh(t):
+        return 'Shape "trianglemesh" "integer indices" [%s] "point P" [%s]\n' % (
+            " ".join(str(i) for i in range(3 * len(t))), " ".join(repr(float(v)) for v in t.ravel()))
+    one = cpbrt.Scene.parse(head + mesh(tris) + "WorldEnd\n")
+    four = cpbrt.Scene.parse(head + "".join(mesh(tris[k:k + 20000]) for k in range(0, n, 20000)) + "WorldEnd\n")
+    a, b = one.desc, four.desc
+    assert a.n_primitives == b.n_primitives and 0 < a.n_primitives < n          # the clipper dropped some, kept some
+    assert a.n_triangles == b.n_triangles == n
+
+    def kept(d):
+        idx = np.array([d.primitives[i].shape.data for i in range(d.n_primitives)])
+        pts = np.ctypeslib.as_array(C.cast(d.triangles, C.POINTER(C.c_float)), shape=(d.n_triangles, 15))
+        return idx, pts[idx, :9].copy()
+    import ctypes as C
+    ia, pa = kept(a); ib, pb = kept(b)
+    assert np.array_equal(ia, ib) and np.array_equal(pa.view(np.uint32), pb.view(np.uint32))
