@@ -274,7 +274,24 @@ int cpbrt_upload_scene(cpbrt_ctx* ctx, const cpbrt_scene_desc* d) {
     if (d->n_primitives >= 0x40000000ull) return ctx->fail(CPBRT_ERR_UNSUPPORTED, "more than 2^30 primitives");
     if (!d->sampler.permutation) return ctx->fail(CPBRT_ERR_BAD_ARG, "sampler.permutation is null");
     // validation: every index must be in range; unsupported features fail loudly
-    for (uint64_t i = 0; i < d->n_primitives; ++i) {
+    // (big scenes: all host threads look for the first bad primitive, its message is then produced by the serial checks)
+    uint64_t first_check = 0, last_check = d->n_primitives;
+    if (d->n_primitives >= (1u << 18)) {
+        std::atomic<uint64_t> first_bad(d->n_primitives);
+        parallel_for(d->n_primitives, 1 << 16, [&](uint64_t lo, uint64_t hi) {
+            for (uint64_t i = lo; i < hi && i < first_bad.load(std::memory_order_relaxed); ++i) {
+                const cpbrt_primitive& p = d->primitives[i];
+                const bool bad = p.shape.kind > CPBRT_SHAPE_SPHERE ||
+                                 (p.shape.kind == CPBRT_SHAPE_TRIANGLE ? p.shape.data >= d->n_triangles : p.shape.data >= d->n_spheres) ||
+                                 p.shape.xform >= (int32_t)d->n_transforms || (p.material < 0) == (p.light < 0) ||
+                                 p.material >= (int32_t)d->n_materials || p.light >= (int32_t)d->n_lights;
+                if (bad) { uint64_t cur = first_bad.load(); while (i < cur && !first_bad.compare_exchange_weak(cur, i)) {} break; }
+            }
+        });
+        first_check = first_bad.load();
+        last_check = std::min<uint64_t>(d->n_primitives, first_check + 1);      // nothing to re-check when all passed
+    }
+    for (uint64_t i = first_check; i < last_check; ++i) {
         const cpbrt_primitive& p = d->primitives[i];
         if (p.shape.kind > CPBRT_SHAPE_SPHERE) return ctx->fail(CPBRT_ERR_BAD_ARG, "primitive %llu: bad shape kind", (unsigned long long)i);
         if (p.shape.kind == CPBRT_SHAPE_TRIANGLE ? p.shape.data >= d->n_triangles : p.shape.data >= d->n_spheres)

@@ -813,6 +813,34 @@ def test_unsupported_features_fail_loudly(cpbrt):
         r.render()            # no scene / BVH yet
 
 
+def test_scene_validation_names_the_first_bad_primitive(cpbrt):
+    """cpbrt_upload_scene checks every index of the scene description before anything reaches the device; scenes of
+    >= 262 144 primitives are scanned by all host threads, and the error must still be the one of the FIRST bad
+    primitive, as the serial scan of small scenes reports it."""
+    scene = cpbrt.Scene.parse(_synthetic_mesh_scene(400, 400, res=32))
+    d = scene.desc
+    n = int(d.n_primitives)
+    assert n >= (1 << 18)
+    r = cpbrt.Renderer(0)
+    r.upload(scene)                                        # fine as parsed
+    saved = {}
+    for k in (n - 5, 200001, 77):                          # later ones first: the lowest index must win every time
+        saved[k] = d.primitives[k].material
+        d.primitives[k].material = 1 << 20
+        with pytest.raises(cpbrt.CpbrtError, match="primitive %d: source out of range" % min(saved)) as e:
+            r.upload(scene)
+        assert e.value.code == cpbrt.abi.ERR_BAD_ARG
+    for k, v in saved.items():
+        d.primitives[k].material = v
+    keep = d.primitives[n // 2].shape.data
+    d.primitives[n // 2].shape.data = 0x7FFFFFFF
+    with pytest.raises(cpbrt.CpbrtError, match="primitive %d: shape data index out of range" % (n // 2)):
+        r.upload(scene)
+    d.primitives[n // 2].shape.data = keep
+    r.upload(scene)                                        # and fine again
+    r.close()
+
+
 def test_c4_million_triangles(cpbrt, oracle):
     """Config C4's geometry (1,000,008 primitives): BVH primitive order and first-hit ids at
     full size; the oracle traces a subset of the rays, the device all of them."""
