@@ -122,6 +122,7 @@ HOST_SYMBOLS = {
     "cpbrt_scene_set_spp": (C.c_int, [C.c_void_p, C.c_uint32]),
     "cpbrt_scene_set_integrator": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
     "cpbrt_make_permutation": (None, [C.c_uint64, C.POINTER(C.c_uint16)]),
+    "cpbrt_host_halton_grouped": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "cpbrt_sample_share": (None, [C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "cpbrt_write_png": (C.c_int, [C.c_char_p, C.POINTER(C.c_float), C.c_uint32, C.c_uint32]),
     "cpbrt_render_from_file": (C.c_int, [C.c_char_p, C.c_int]),

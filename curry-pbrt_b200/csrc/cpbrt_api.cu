@@ -16,6 +16,7 @@
 
 #include "../../include/cpbrt.h"
 #include "bvh_build.h"
+#include "host/scene_host.h"      // build_halton_groups
 #include "device/wavefront.cuh"
 
 namespace cpbrt {
@@ -477,6 +478,8 @@ int cpbrt_upload_scene(cpbrt_ctx* ctx, const cpbrt_scene_desc* d) {
             if (const char* e = getenv("CPBRT_HALTON_GROUP")) group_max = (uint32_t)std::max(2, std::min(65536, atoi(e)));
             std::vector<uint16_t> table;        // what follows the caller's CPBRT_PERM_TABLE_LEN entries on the device
             const uint32_t table0 = CPBRT_PERM_TABLE_LEN;
+            std::vector<cpbrt_host::HaltonGroupDim> groups;
+            cpbrt_host::build_halton_groups(d->sampler.permutation, group_max, &groups, &table);      // host/halton_tables.cpp
             std::vector<DevHaltonDim> dims(CPBRT_N_PRIMES);
             std::vector<float> inv_pow((size_t)CPBRT_N_PRIMES * kHaltonMaxDigits);
             for (int i = 0; i < CPBRT_N_PRIMES; ++i) {
@@ -485,26 +488,12 @@ int cpbrt_upload_scene(cpbrt_ctx* ctx, const cpbrt_scene_desc* d) {
                 memset(&dims[i], 0, sizeof dims[i]);
                 dims[i].magic = magic[i]; dims[i].base = b; dims[i].primsum = sums[i];
                 dims[i].tail = inv_base * (float)d->sampler.permutation[sums[i]] / (1.f - inv_base);
-                uint32_t g = 1, G = b;
-                while ((uint64_t)G * b <= group_max) { G *= b; ++g; }
-                dims[i].group = G; dims[i].group_digits = g; dims[i].group_magic = 0xFFFFFFFFFFFFFFFFull / G + 1;
-                if (g == 1) { dims[i].group_off = sums[i]; dims[i].full_off = sums[i]; }
-                else {
-                    dims[i].group_off = table0 + (uint32_t)table.size();
-                    uint32_t pw = 1;
-                    for (uint32_t j = 1; j <= g; ++j) {
-                        pw *= b;
-                        if (j == g) dims[i].full_off = table0 + (uint32_t)table.size();
-                        for (uint32_t x = 0; x < pw; ++x) {
-                            uint32_t v = 0, t = x;
-                            for (uint32_t c = 0; c < j; ++c) { v = v * b + d->sampler.permutation[sums[i] + t % b]; t /= b; }
-                            table.push_back((uint16_t)v);
-                        }
-                    }
-                }
+                dims[i].group = groups[i].group; dims[i].group_digits = groups[i].group_digits; dims[i].group_magic = groups[i].group_magic;
+                dims[i].group_off = groups[i].group_off; dims[i].full_off = groups[i].full_off;
                 uint64_t pw = 1;
                 for (int c = 0; c < kHaltonMaxDigits; ++c) { inv_pow[(size_t)i * kHaltonMaxDigits + c] = 1.f / (float)pw; pw *= primes[i]; }
             }
+            (void)table0;
             // the caller's table goes up as it is (7 MB: no host copy), the group tables behind it
             const size_t perm_bytes = (size_t)table0 * 2, total_bytes = perm_bytes + table.size() * 2;
             if (ctx->d_perm.bytes != total_bytes) { ctx->d_perm.release(); CU(cudaMalloc(&ctx->d_perm.p, total_bytes)); ctx->d_perm.bytes = total_bytes; }

@@ -79,4 +79,55 @@ void make_permutation(uint64_t seed, uint16_t* out) {
     }
 }
 
+// Digit-group tables of scrambled_radical_inverse (csrc/device/halton.cuh, DevHaltonDim): for every dimension whose
+// base^2 still fits `group_max`, the permuted-and-reversed strings of 1, 2, ... g digits (g = the most digits with
+// base^g <= group_max), appended behind the caller's CPBRT_PERM_TABLE_LEN single-digit entries.  T_j[x] for
+// x < base^j is what j rounds of `reversed = reversed * base + perm[a % base]; a /= base` produce from reversed = 0.
+void build_halton_groups(const uint16_t* permutation, uint32_t group_max, std::vector<HaltonGroupDim>* dims, std::vector<uint16_t>* extra) {
+    const uint32_t* primes = primes_1000();
+    const uint32_t* sums = prime_sums_1000();
+    dims->assign(CPBRT_N_PRIMES, HaltonGroupDim());
+    extra->clear();
+    const uint32_t table0 = CPBRT_PERM_TABLE_LEN;
+    for (int i = 0; i < CPBRT_N_PRIMES; ++i) {
+        const uint32_t b = primes[i];
+        HaltonGroupDim& d = (*dims)[i];
+        uint32_t g = 1, G = b;
+        while ((uint64_t)G * b <= group_max) { G *= b; ++g; }
+        d.base = b; d.group = G; d.group_digits = g; d.group_magic = 0xFFFFFFFFFFFFFFFFull / G + 1;
+        if (g == 1) { d.group_off = sums[i]; d.full_off = sums[i]; continue; }
+        d.group_off = table0 + (uint32_t)extra->size();
+        uint32_t pw = 1;
+        for (uint32_t j = 1; j <= g; ++j) {
+            pw *= b;
+            if (j == g) d.full_off = table0 + (uint32_t)extra->size();
+            for (uint32_t x = 0; x < pw; ++x) {
+                uint32_t v = 0, t = x;
+                for (uint32_t c = 0; c < j; ++c) { v = v * b + permutation[sums[i] + t % b]; t /= b; }
+                extra->push_back((uint16_t)v);
+            }
+        }
+    }
+}
+
+// The device's evaluation order on the host (tests): one digit at a time while the quotient needs 64 bits, whole
+// groups while it is at least `group`, the partial last group from the table of its digit count.
+void halton_grouped_reference(const uint16_t* permutation, const HaltonGroupDim& d, const std::vector<uint16_t>& extra, uint32_t primsum,
+                              uint64_t index, uint64_t* acc_out, uint32_t* digits_out) {
+    auto table = [&](uint32_t i) -> uint64_t { return i < (uint32_t)CPBRT_PERM_TABLE_LEN ? permutation[i] : extra[i - CPBRT_PERM_TABLE_LEN]; };
+    uint64_t acc = 0, x = index; uint32_t cnt = 0;
+    while ((x >> 32) != 0) { const uint64_t q = x / d.base; acc = acc * d.base + permutation[primsum + (uint32_t)(x - q * d.base)]; ++cnt; x = q; }
+    uint32_t xs = (uint32_t)x;
+    while (xs >= d.group) {
+        const uint32_t q = (uint32_t)(((unsigned __int128)xs * d.group_magic) >> 64);      // the device's __umul64hi
+        acc = acc * d.group + table(d.full_off + (xs - q * d.group)); cnt += d.group_digits; xs = q;
+    }
+    if (xs != 0) {
+        uint32_t j = 1, pw = d.base, o = d.group_off;
+        while (xs >= pw) { o += pw; ++j; pw *= d.base; }
+        acc = acc * pw + table(o + xs); cnt += j;
+    }
+    *acc_out = acc; *digits_out = cnt;
+}
+
 }  // namespace cpbrt_host

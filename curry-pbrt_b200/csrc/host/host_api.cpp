@@ -70,6 +70,19 @@ int cpbrt_scene_set_integrator(cpbrt_scene* scene, uint32_t integrator, uint32_t
 
 void cpbrt_make_permutation(uint64_t seed, uint16_t* out) { make_permutation(seed, out); }
 
+int cpbrt_host_halton_grouped(const uint16_t* permutation, uint32_t group_max, const uint64_t* index, const uint32_t* dim, uint64_t n,
+                              uint64_t* acc_out, uint32_t* digits_out) {
+    if (!permutation || !index || !dim || !acc_out || !digits_out || group_max < 2 || group_max > 65536) { g_host_error = "cpbrt_host_halton_grouped: bad argument"; return CPBRT_ERR_BAD_ARG; }
+    std::vector<HaltonGroupDim> dims; std::vector<uint16_t> extra;
+    build_halton_groups(permutation, group_max, &dims, &extra);
+    const uint32_t* sums = prime_sums_1000();
+    for (uint64_t i = 0; i < n; ++i) {
+        if (dim[i] >= (uint32_t)CPBRT_N_PRIMES) { g_host_error = "cpbrt_host_halton_grouped: dimension out of range"; return CPBRT_ERR_BAD_ARG; }
+        halton_grouped_reference(permutation, dims[dim[i]], extra, sums[dim[i]], index[i], &acc_out[i], &digits_out[i]);
+    }
+    return CPBRT_OK;
+}
+
 // Sample-index share of a rank (see curry-pbrt_b200/partition.py for the reasoning): boundaries
 // b_k = round(spp * (1 - q^k) / (1 - q^n)), q = 1 - 1/420, in IEEE double with this exact operation order.
 static uint32_t share_boundary(uint32_t spp, int k, int n_ranks) {

@@ -24,6 +24,11 @@ const uint32_t* primes_1000();        // PRIMS   (halton.rs:141-203: the first 1
 const uint32_t* prime_sums_1000();    // PRIMSUM (halton.rs:205-214)
 void make_permutation(uint64_t seed, uint16_t* out);
 void halton_sampler_params(uint32_t spp, uint32_t xres, uint32_t yres, cpbrt_sampler* out);   // HaltonSampler::new
+// digit-group tables of the device's scrambled_radical_inverse (halton_tables.cpp)
+struct HaltonGroupDim { uint32_t base = 0, group = 0, group_digits = 0, group_off = 0, full_off = 0; uint64_t group_magic = 0; };
+void build_halton_groups(const uint16_t* permutation, uint32_t group_max, std::vector<HaltonGroupDim>* dims, std::vector<uint16_t>* extra);
+void halton_grouped_reference(const uint16_t* permutation, const HaltonGroupDim& d, const std::vector<uint16_t>& extra, uint32_t primsum,
+                              uint64_t index, uint64_t* acc_out, uint32_t* digits_out);
 
 struct SceneData {
     std::vector<cpbrt_primitive> primitives;

@@ -366,6 +366,13 @@ int cpbrt_host_build_bvh(const cpbrt_scene_desc* desc, uint32_t* prim_order_out,
  * 1442695040888963407); stands in for the reference's thread_rng shuffle (halton.rs:216-231). */
 void cpbrt_make_permutation(uint64_t seed, uint16_t* out /* CPBRT_PERM_TABLE_LEN */);
 
+/* Tests: the digit-GROUP evaluation of scrambled_radical_inverse that the device uses (csrc/device/halton.cuh:
+ * several digits per division and table look-up, tables built by the host for `group_max` = the largest base^digits
+ * of a group, 2 .. 65536), run on the host for n (index, dimension) pairs: the integer accumulator ("reversed",
+ * halton.rs:56-64, wrapping in 64 bits) and the digit count.  Must equal the one-digit loop for every group_max. */
+int cpbrt_host_halton_grouped(const uint16_t* permutation, uint32_t group_max, const uint64_t* index, const uint32_t* dim, uint64_t n,
+                              uint64_t* acc_out, uint32_t* digits_out);
+
 /* The contiguous range [*begin, *end) of sample indices rank `rank` of `n_ranks` renders when cpbrt_render is
  * called without an explicit range.  The shares tile [0, spp) and shrink slightly with the rank: a rank that
  * starts at sample s first replays the film-point drift of the s samples before it (src/render.rs:26-31). */

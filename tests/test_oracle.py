@@ -84,6 +84,41 @@ def test_scrambled_radical_inverse_against_exact_arithmetic(cpbrt, oracle, make_
         assert abs(Fraction(float(val[i])) - exact) <= exact * Fraction(4, 2 ** 23) + Fraction(1, 2 ** 40), (i, dim[i], float(val[i]), float(exact))
 
 
+@pytest.mark.parametrize("group_max", [2, 25, 128, 1024, 4096, 65536])
+def test_halton_digit_groups_equal_the_digit_loop(cpbrt, group_max):
+    """The device takes several digits of scrambled_radical_inverse per round (one division by base^g and one
+    look-up in a table of permuted-and-reversed g-digit strings, csrc/device/halton.cuh).  The tables are built on
+    the host (csrc/host/halton_tables.cpp) and the same evaluation order runs on the host through
+    cpbrt_host_halton_grouped: its integer accumulator and digit count must equal the reference's one-digit loop
+    (halton.rs:56-64), recomputed here with Python integers, for every group size -- indices up to 2^40 (the 64-bit
+    prefix), indices just below and above powers of the base (partial last groups of every length), dimension 2
+    (base 5: 4-5 digits per group) to 999."""
+    perm = np.zeros(cpbrt.abi.PERM_TABLE_LEN, np.uint16)
+    cpbrt.lib.cpbrt_make_permutation(7, perm.ctypes.data_as(C.POINTER(C.c_uint16)))
+    primes = [p for p in range(2, 8000) if all(p % q for q in range(2, int(p ** 0.5) + 1))][:1000]
+    offsets = np.concatenate([[0], np.cumsum(primes)])
+    rng = np.random.default_rng(group_max)
+    n = 6000
+    dim = rng.integers(2, 1000, n).astype(np.uint32)
+    dim[:400] = np.arange(400) % 40 + 2                       # the small bases, where groups are longest
+    index = rng.integers(0, 1 << 40, n, dtype=np.uint64)
+    index[:1500] = rng.integers(0, 1 << 31, 1500, dtype=np.uint64)      # what a 900 x 900 x 1024-spp render draws
+    for k in range(1500, 2500):                               # b^j - 1, b^j, b^j + 1
+        b = primes[dim[k]]
+        j = int(rng.integers(1, 14))
+        index[k] = max(0, min(b ** j + int(rng.integers(-1, 2)), (1 << 63) - 1))
+    index[2500:2520] = np.arange(20)                          # tiny indices, zero included
+    acc = np.zeros(n, np.uint64); digits = np.zeros(n, np.uint32)
+    rc = cpbrt.lib.cpbrt_host_halton_grouped(perm.ctypes.data, group_max, index.ctypes.data, dim.ctypes.data, n, acc.ctypes.data, digits.ctypes.data)
+    assert rc == 0
+    for i in range(n):
+        b, block = primes[dim[i]], perm[offsets[dim[i]]:offsets[dim[i]] + primes[dim[i]]]
+        x, rev, cnt = int(index[i]), 0, 0
+        while x:
+            rev = (rev * b + int(block[x % b])) % (1 << 64); x //= b; cnt += 1
+        assert (int(acc[i]), int(digits[i])) == (rev, cnt), (i, int(index[i]), int(dim[i]))
+
+
 def test_permutation_table_is_blockwise_permutation(cpbrt):
     perm = np.zeros(cpbrt.abi.PERM_TABLE_LEN, np.uint16)
     cpbrt.lib.cpbrt_make_permutation(1, perm.ctypes.data_as(C.POINTER(C.c_uint16)))
