@@ -138,6 +138,18 @@ int main(int argc, char** argv) {
     CHECK(cpbrt_trace_any(ctx, rays, 3, occ, 0, NULL));
     EXPECT(occ[0] == 1 && occ[1] == 1 && occ[2] == 0);
 
+    {   /* the traversal layout as it sits in device memory: two primitives -> one Parent with two Leaf children, or none */
+        uint64_t n_nodes = 99; int resident = 7;
+        float nodes[16], records[24], frames[24];
+        EXPECT(cpbrt_bvh_device_layout(ctx, 0, &n_nodes, NULL, NULL, NULL, NULL, &resident) >= 0);
+        EXPECT(n_nodes <= 1 && resident == 0);               /* a two-primitive scene is built on the host */
+        EXPECT(cpbrt_bvh_device_layout(ctx, 1, NULL, nodes, records, frames, NULL, NULL) >= 0);
+        EXPECT(records[0] == d.triangles[order[0]].p[0][0] && records[12] == d.triangles[order[1]].p[0][0]);
+        EXPECT(cpbrt_bvh_gpu_levels(ctx) == 0 && cpbrt_bvh_host_segments(ctx) == -1);
+        uint64_t bad = 5; uint32_t site = 5;
+        EXPECT(cpbrt_check_failures(ctx, &bad, &site) == 0 && bad == 0 && site == 0);      /* the normal library: no checks compiled in */
+    }
+
     uint32_t px = 5, py = 7, sample = 3, dim = 2;
     uint64_t index = 0; float value = -1.f;
     CHECK(cpbrt_halton(ctx, &px, &py, &sample, &dim, 1, &index, &value));
