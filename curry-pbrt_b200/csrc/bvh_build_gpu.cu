@@ -348,6 +348,7 @@ __global__ void __launch_bounds__(kSmallThreads) k_build_small(Box* __restrict__
             // ---- emit the node -------------------------------------------------------------------
             __syncthreads();
             const uint32_t id = sh_used;           // node index within the block's range
+            __syncthreads();                       // every thread has read it before thread 0 advances it
             if (tid == 0) {
                 sh_used = id + 1;
                 SmallNode nd;
