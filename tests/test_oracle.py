@@ -358,6 +358,66 @@ def test_product_bvh_builder_matches_oracle_on_mesh(cpbrt, oracle):
     assert (leaf_sizes == 2).sum() > 100 and leaf_sizes.max() <= 4
 
 
+def _triangle_soup_scene(tris):
+    """One trianglemesh of independent triangles (n, 3, 3) plus the usual light quad."""
+    tris = np.asarray(tris, np.float32)
+    n = tris.shape[0]
+    return ('LookAt 278 273 -800 278 273 0 0 1 0\nCamera "perspective" "float fov" [37.5]\nSampler "halton" "integer pixelsamples" [2]\n'
+            'Film "image" "integer xresolution" [32] "integer yresolution" [32]\nIntegrator "path" "integer maxdepth" [5]\nWorldBegin\n'
+            'AttributeBegin\nAreaLightSource "diffuse" "rgb L" [17 12 4]\nShape "trianglemesh" "integer indices" [0 1 2 2 3 0] '
+            '"point P" [343 548.7 227 343 548.7 332 213 548.7 332 213 548.7 227]\nAttributeEnd\n'
+            'Material "matte" "rgb Kd" [0.5 0.5 0.5]\nShape "trianglemesh" "integer indices" [%s] "point P" [%s]\nWorldEnd\n'
+            % (" ".join(map(str, range(3 * n))), " ".join("%.9g" % v for v in tris.ravel())))
+
+
+def _sah_numpy():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("sah_numpy", os.path.join(os.path.dirname(__file__), "..", "oracle", "sah_numpy.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _sah_cases():
+    rng = np.random.RandomState(11)
+    soup = rng.rand(700, 1, 3) * 500 + (rng.rand(700, 3, 3) - 0.5) * rng.choice([0.5, 8.0, 120.0], (700, 1, 1))
+    same = np.tile(np.array([[[1, 1, 1], [2, 1, 1], [1, 2, 1]]], np.float32), (9, 1, 1))             # identical boxes: every cost ties
+    flat = np.tile(np.array([[[0, 0, 0], [1, 0, 0], [0, 0, 1]]], np.float32), (12, 1, 1))                # cost 12.125 > 12: one leaf of 12
+    line = np.zeros((17, 3, 3), np.float32); line[:, :, 1] = np.arange(17, dtype=np.float32)[:, None]     # zero-area parents: every cost is NaN, the first candidate is taken
+    signed = rng.rand(64, 3, 3).astype(np.float32) - 0.5; signed[::4, :, 0] = 0.0; signed[1::4, :, 0] = -0.0   # +0 / -0 centres
+    return [("mesh 24x17", None, _synthetic_mesh_scene(24, 17, seed=5)), ("mesh 3x70", None, _synthetic_mesh_scene(3, 70, seed=9)),
+            ("soup", soup, None), ("identical", same, None), ("degenerate plane", flat, None), ("points on a line", line, None),
+            ("signed zeros", signed, None)]
+
+
+@pytest.mark.parametrize("case", range(7))
+def test_bvh_build_against_independent_numpy_restatement(cpbrt, oracle, case):
+    """a8, second pin: oracle/sah_numpy.py restates bvh.rs:24-124 in numpy float32 from the Rust alone
+    (own bounds, own sort, the swap loop literally).  Primitive order, node numbering, split axes,
+    child links and parent bounds of the C++ oracle and of the product's host builder must equal it
+    bit for bit -- on ties, NaN / infinite costs (zero-area parents) and signed-zero keys too."""
+    name, tris, text = _sah_cases()[case]
+    scene = cpbrt.Scene.parse(text if text is not None else _triangle_soup_scene(tris))
+    d = scene.desc
+    n = int(d.n_primitives)
+    assert all(d.primitives[i].shape.kind == cpbrt.abi.SHAPE_TRIANGLE for i in range(n)), name
+    P = np.array([[list(d.triangles[d.primitives[i].shape.data].p[k]) for k in range(3)] for i in range(n)], np.float32)
+    sah = _sah_numpy()
+    tree = sah.build(*sah.triangle_bounds(P))
+    w = oracle.OracleWorld(scene)
+    ref = w.bvh_nodes()
+    assert np.array_equal(tree.order, w.bvh_order()), name
+    assert tree.root == ref["root"] and len(tree.a) == len(ref["a"]), name
+    for k in ("is_leaf", "a", "b"):
+        assert np.array_equal(np.array(getattr(tree, k), np.int64), ref[k].astype(np.int64)), (name, k)
+    parents = np.array(tree.is_leaf) == 0
+    assert np.array_equal(np.array(tree.axis)[parents], ref["axis"][parents]), name
+    assert np.array_equal(np.array(tree.bound, np.float32)[parents].view(np.uint32), ref["bound"][parents].view(np.uint32)), name
+    order = np.zeros(n, np.uint32)
+    assert cpbrt.lib.cpbrt_host_build_bvh(scene.desc_ptr, order.ctypes.data_as(C.POINTER(C.c_uint32)), None) == 0
+    assert np.array_equal(order, tree.order), name
+
+
 def test_render_is_deterministic_and_thread_count_independent(make_scene, oracle):
     scene = make_scene("cornel_box.pbrt", xres=40, yres=40, spp=2)
     w = oracle.OracleWorld(scene)
