@@ -1,0 +1,179 @@
+"""ORACLE -- TEST INFRASTRUCTURE ONLY.
+
+A second, independent restatement of the reference's BVH search and triangle test, scalar
+np.float32 arithmetic written directly from the Rust (shares nothing with oracle/oracle.cpp).
+Slow by design (a few hundred rays per second): the tests run it over a few thousand rays and hold
+the C++ oracle -- and through it the device kernels -- to the same primitive and the same bits of t.
+
+  RayIntersectCache::from          src/geometry/ray.rs (inverse_d, is_positive_d = d >= 0)
+  Bounds3f::intersect_component    src/geometry/bounds.rs:306-311   far slab widened by 1 + 2*gamma(3)
+  intersect_predicate_cached       src/geometry/bounds.rs:312-323   the interval is *widened* axis by
+                                   axis (min of the mins, max of the maxes) -- the reference's loose test
+  intersect_through_bound          src/aggregate/bvh.rs:151-191     far child first (by the split axis
+                                   and the sign of d), a Leaf updates t_max on every hit, later hits win
+  intersect_predicate_through_bound  bvh.rs:125-150                 left then right, first hit ends it
+  Triangle::intersect              src/geometry/shape/triangle.rs:194-262 (and :127-192, the predicate)
+  gamma(n)                         src/math/mod.rs:76-79, MACHINE_EPSILON = f32::EPSILON / 2 (def.rs:4)
+  min / max                        src/math/mod.rs:36-49 (`rhs < lhs ? rhs : lhs`)
+
+The tree comes from oracle/sah_numpy.py (`SahTree`); `tris` are the (n, 3, 3) float32 vertices in
+upload order."""
+import numpy as np
+
+F = np.float32
+_EPS = F(np.finfo(np.float32).eps) * F(0.5)
+
+
+def gamma(n):
+    ne = F(n) * _EPS
+    return ne / (F(1) - ne)
+
+
+_G2, _G3, _G5 = gamma(2), gamma(3), gamma(5)
+_WIDEN = F(1) + F(2) * _G3
+
+
+def _min(lhs, rhs):
+    return rhs if rhs < lhs else lhs
+
+
+def _max(lhs, rhs):
+    return rhs if rhs > lhs else lhs
+
+
+class _Ray:
+    def __init__(self, o, d, t_max):
+        self.o = [F(x) for x in o]
+        self.d = [F(x) for x in d]
+        self.t_max = F(t_max)
+        self.inv = [F(1) / x for x in self.d]
+        self.pos = [1 if x >= 0 else 0 for x in self.d]
+        self.neg = [1 - p for p in self.pos]
+
+
+def _slab(bound, ray):
+    """bound = (lo[3], hi[3]) as lists of np.float32."""
+    def component(c):
+        return ((bound[ray.neg[c]][c] - ray.o[c]) * ray.inv[c],
+                (bound[ray.pos[c]][c] - ray.o[c]) * ray.inv[c] * _WIDEN)
+    t_min, t_max = component(0)
+    for c in (1, 2):
+        n_min, n_max = component(c)
+        if t_min > n_max or n_min > t_max:
+            return False
+        t_min = _min(t_min, n_min)
+        t_max = _max(t_max, n_max)
+    return bool(t_min < ray.t_max and t_max > 0)
+
+
+def _imax_abs(v):
+    a = [abs(x) for x in v]
+    best, idx = a[0], 0
+    for i in (1, 2):
+        if a[i] > best:
+            best, idx = a[i], i
+    return idx
+
+
+def triangle_intersect(p, ray):
+    """Returns t (np.float32) or None.  `Triangle::intersect` and `intersect_predicate` accept and
+    reject exactly the same rays (the same sequence up to the barycentrics)."""
+    o = ray.o
+    pt = [[p[k][c] - o[c] for c in range(3)] for k in range(3)]
+    kz = _imax_abs(ray.d)
+    kx = 0 if kz + 1 == 3 else kz + 1
+    ky = 0 if kx + 1 == 3 else kx + 1
+    d = [ray.d[kx], ray.d[ky], ray.d[kz]]
+    pt = [[q[kx], q[ky], q[kz]] for q in pt]
+    sx = -d[0] / d[2]
+    sy = -d[1] / d[2]
+    sz = F(1) / d[2]
+    for q in pt:
+        q[0] = q[0] + sx * q[2]
+        q[1] = q[1] + sy * q[2]
+    p0, p1, p2 = pt
+    e0 = p1[0] * p2[1] - p1[1] * p2[0]
+    e1 = p2[0] * p0[1] - p2[1] * p0[0]
+    e2 = p0[0] * p1[1] - p0[1] * p1[0]
+    if (e0 < 0 or e1 < 0 or e2 < 0) and (e0 > 0 or e1 > 0 or e2 > 0):
+        return None
+    det = e0 + e1 + e2
+    if det == 0:
+        return None
+    for q in pt:
+        q[2] = q[2] * sz
+    t_scaled = e0 * p0[2] + e1 * p1[2] + e2 * p2[2]
+    if (det < 0 and (t_scaled >= 0 or t_scaled < ray.t_max * det)) or \
+       (det > 0 and (t_scaled <= 0 or t_scaled > ray.t_max * det)):
+        return None
+    inv_det = F(1) / det
+    t = t_scaled * inv_det
+    max_zt = max(abs(p0[2]), abs(p1[2]), abs(p2[2]))
+    delta_z = _G3 * max_zt
+    max_xt = max(abs(p0[0]), abs(p1[0]), abs(p2[0]))
+    max_yt = max(abs(p0[1]), abs(p1[1]), abs(p2[1]))
+    delta_x = _G5 * (max_xt + max_zt)
+    delta_y = _G5 * (max_yt + max_zt)
+    delta_e = F(2) * (_G2 * max_xt * max_yt + delta_y * max_xt + delta_x * max_yt)
+    max_e = max(abs(e0), abs(e1), abs(e2))
+    delta_t = F(3) * (_G3 * max_e * max_zt + delta_e * max_zt + delta_z * max_e) * abs(inv_det)
+    if t <= delta_t:
+        return None
+    return t
+
+
+class Searcher:
+    def __init__(self, tree, tris):
+        tris = np.asarray(tris, F)
+        self.tree = tree
+        self.order = [int(i) for i in tree.order]
+        self.prims = [[[F(x) for x in v] for v in tris[i]] for i in self.order]   # BVH slot -> vertices
+        self.bounds = [([F(x) for x in b[:3]], [F(x) for x in b[3:]]) for b in tree.bound]
+        self.visits = 0
+        self.tests = 0
+
+    def closest(self, o, d, t_max=np.finfo(np.float32).max):
+        """(upload index of the primitive hit, t) or (None, None)."""
+        import sys
+        sys.setrecursionlimit(max(sys.getrecursionlimit(), 4 * len(self.order) + 1000))
+        with np.errstate(all="ignore"):
+            ray = _Ray(o, d, t_max)
+            slot = self._closest(self.tree.root, ray)
+        return (None, None) if slot is None else (self.order[slot], ray.t_max)
+
+    def _closest(self, node, ray):
+        t = self.tree
+        result = None
+        if t.is_leaf[node]:
+            for slot in range(t.a[node], t.b[node]):
+                self.tests += 1
+                hit = triangle_intersect(self.prims[slot], ray)
+                if hit is not None:
+                    ray.t_max = hit
+                    result = slot
+            return result
+        self.visits += 1
+        if _slab(self.bounds[node], ray):
+            left, right = (t.a[node], t.b[node]) if ray.pos[t.axis[node]] == 1 else (t.b[node], t.a[node])
+            r = self._closest(right, ray)
+            if r is not None:
+                result = r
+            r = self._closest(left, ray)
+            if r is not None:
+                result = r
+        return result
+
+    def any_hit(self, o, d, t_max=np.finfo(np.float32).max):
+        with np.errstate(all="ignore"):
+            return self._any(self.tree.root, _Ray(o, d, t_max))
+
+    def _any(self, node, ray):
+        t = self.tree
+        if t.is_leaf[node]:
+            for slot in range(t.a[node], t.b[node]):
+                self.tests += 1
+                if triangle_intersect(self.prims[slot], ray) is not None:
+                    return True
+            return False
+        self.visits += 1
+        return _slab(self.bounds[node], ray) and (self._any(t.a[node], ray) or self._any(t.b[node], ray))

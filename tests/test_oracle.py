@@ -370,14 +370,6 @@ def _triangle_soup_scene(tris):
             % (" ".join(map(str, range(3 * n))), " ".join("%.9g" % v for v in tris.ravel())))
 
 
-def _sah_numpy():
-    import importlib.util
-    spec = importlib.util.spec_from_file_location("sah_numpy", os.path.join(os.path.dirname(__file__), "..", "oracle", "sah_numpy.py"))
-    mod = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(mod)
-    return mod
-
-
 def _sah_cases():
     rng = np.random.RandomState(11)
     soup = rng.rand(700, 1, 3) * 500 + (rng.rand(700, 3, 3) - 0.5) * rng.choice([0.5, 8.0, 120.0], (700, 1, 1))
@@ -402,7 +394,7 @@ def test_bvh_build_against_independent_numpy_restatement(cpbrt, oracle, case):
     n = int(d.n_primitives)
     assert all(d.primitives[i].shape.kind == cpbrt.abi.SHAPE_TRIANGLE for i in range(n)), name
     P = np.array([[list(d.triangles[d.primitives[i].shape.data].p[k]) for k in range(3)] for i in range(n)], np.float32)
-    sah = _sah_numpy()
+    sah = _load_oracle_py("sah_numpy")
     tree = sah.build(*sah.triangle_bounds(P))
     w = oracle.OracleWorld(scene)
     ref = w.bvh_nodes()
@@ -416,6 +408,61 @@ def test_bvh_build_against_independent_numpy_restatement(cpbrt, oracle, case):
     order = np.zeros(n, np.uint32)
     assert cpbrt.lib.cpbrt_host_build_bvh(scene.desc_ptr, order.ctypes.data_as(C.POINTER(C.c_uint32)), None) == 0
     assert np.array_equal(order, tree.order), name
+
+
+def _load_oracle_py(name):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(name, os.path.join(os.path.dirname(__file__), "..", "oracle", name + ".py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.parametrize("case", [0, 2])
+def test_bvh_search_against_independent_numpy_restatement(cpbrt, oracle, case):
+    """a9-a12, second pin: oracle/trace_numpy.py restates the far-first search, the loose slab test and the
+    watertight triangle test in scalar np.float32 from the Rust alone.  On random rays, camera rays and rays
+    aimed exactly at shared vertices and edge midpoints, the C++ oracle must report the same primitive, the
+    same bits of t, the same occlusion answer -- and the same number of Parent visits and primitive tests,
+    i.e. the same walk."""
+    name, tris, text = _sah_cases()[case]
+    scene = cpbrt.Scene.parse(text if text is not None else _triangle_soup_scene(tris))
+    d = scene.desc
+    n = int(d.n_primitives)
+    P = np.array([[list(d.triangles[d.primitives[i].shape.data].p[k]) for k in range(3)] for i in range(n)], np.float32)
+    sah, trace = _load_oracle_py("sah_numpy"), _load_oracle_py("trace_numpy")
+    search = trace.Searcher(sah.build(*sah.triangle_bounds(P)), P)
+    lo, hi = P.reshape(-1, 3).min(0), P.reshape(-1, 3).max(0)
+    rays = [lcg_rays(1200, lo, hi, seed=21 + case)]
+    w = oracle.OracleWorld(scene)
+    rays.append(w.camera_rays(0)[::2][:400])
+    rng = np.random.RandomState(4 + case)
+    pick = rng.randint(0, n, 300)
+    eye = np.array([278, 900, -300], np.float32)
+    aimed = np.zeros((600, 8), np.float32)
+    aimed[:, 0:3] = eye; aimed[:, 3] = np.finfo(np.float32).max
+    aimed[:300, 4:7] = P[pick, rng.randint(0, 3, 300)] - eye                                # through a vertex
+    aimed[300:, 4:7] = (P[pick, 0] + P[pick, 1]) * np.float32(0.5) - eye                        # through an edge midpoint
+    rays.append(aimed)
+    rays = np.concatenate(rays)
+    ref, ref_count = w.trace_closest(rays, count=True, threads=1)
+    prim = np.full(len(rays), 0xFFFFFFFF, np.uint32); t = np.zeros(len(rays), np.float32)
+    for i, r in enumerate(rays):
+        hit, th = search.closest(r[0:3], r[4:7], r[3])
+        if hit is not None:
+            prim[i], t[i] = hit, th
+    assert (prim != 0xFFFFFFFF).sum() > len(rays) // 3, name
+    assert np.array_equal(prim, ref["prim"]), name
+    assert np.array_equal(t.view(np.uint32), ref["t"].view(np.uint32)), name
+    assert (search.visits, search.tests) == (int(ref_count[0]), int(ref_count[1])), name
+    # occlusion: segments from the hit points back towards the eye (shortened), plus the raw rays
+    seg = rays.copy(); seg[:, 3] = np.where(prim != 0xFFFFFFFF, t * np.float32(1.5), np.float32(50.0))
+    both = np.concatenate([rays[:400], seg[::2]])
+    search.visits = search.tests = 0
+    occluded = np.array([search.any_hit(r[0:3], r[4:7], r[3]) for r in both], np.uint8)
+    ref_any, any_count = w.trace_any(both, count=True, threads=1)
+    assert np.array_equal(occluded, ref_any), name
+    assert (search.visits, search.tests) == (int(any_count[0]), int(any_count[1])), name
 
 
 def test_render_is_deterministic_and_thread_count_independent(make_scene, oracle):
