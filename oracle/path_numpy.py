@@ -1,0 +1,390 @@
+"""ORACLE -- TEST INFRASTRUCTURE ONLY.
+
+A second, independent restatement of the reference's render loop and path integrator for scenes
+of matte triangles under diffuse area lights (the Cornell box without its glass ball and mirror),
+in scalar np.float32 written directly from the Rust; it shares nothing with oracle/oracle.cpp.
+The tests render a few hundred paths with it and hold the C++ oracle to the same image and the same
+ray counts.  What it takes from outside, as inputs:
+  * the flattened scene (triangles, Kd, emitted radiance) -- `cpbrt_scene_desc`;
+  * the Halton value of (pixel, sample, dimension) and the raster -> camera-ray map, from callables
+    (the sampler and the camera are pinned on their own: exact-arithmetic radical inverses, the
+    reference's two unit tests, the closed-form camera);
+  * the BVH and its search: oracle/sah_numpy.py, oracle/trace_numpy.py.
+
+  render loop, film-point drift, NaN drop, mean   src/render.rs:20-44, src/film.rs:11-18
+  Sampler::get_1d / get_2d / get_usize            src/sampler/mod.rs:10-36
+  PathIntegrator::li                              src/integrator/path.rs:13-66
+  uniform_sample_one_light                        src/integrator/mod.rs:13-97
+  AreaLight::sample_li / le / pdf                 src/light/area.rs:17-51
+  VisibilityTester, Ray::from_to                  src/light/mod.rs:100-115, src/geometry/ray.rs:30-36
+  Shape::default_sample_by_point / by_point_pdf   src/geometry/shape/mod.rs:23-53
+  Triangle::sample / area / normal / interpolate  src/geometry/shape/triangle.rs:76-126,255-261
+  ShapePoint::point_offset_by_error               src/geometry/shape/mod.rs:117-124
+  MatteMaterial, LambertianReflection, BxDF       src/material/matte.rs, bxdf/lambertian.rs, bxdf/mod.rs:17-44
+  BSDF::{new, sample_f, sample_no_delta_f, no_delta_f_pdf, *_to_*}   src/material/bxdf/mod.rs:74-222
+  Distribution1D::{from, sample_remap}            src/math/distribution.rs:16-56
+  coordinate_system, cosine / concentric / triangle sampling, power_heuristic   src/math/mod.rs
+  RGBSpectrum::y                                  src/spectrum/rgb_spectrum.rs:82-84
+
+Vector arithmetic follows nalgebra for 3-vectors: dot = (x*x' + y*y') + z*z', norm = sqrt(dot),
+normalize divides each component by the norm."""
+import math
+
+import numpy as np
+
+F = np.float32
+ZERO, ONE, HALF = F(0), F(1), F(0.5)
+PI = F(3.14159265358979323846)          # src/math/mod.rs:216
+INV_PI = F(0.31830988618379067154)      # src/math/mod.rs:213
+_EPS = F(np.finfo(np.float32).eps) * HALF
+
+
+def _libm_f32(name):
+    """f32::cos / f32::sin compile to calls of the platform's cosf / sinf; numpy's float32 kernels are
+    SIMD approximations that differ from them in the last bit now and then."""
+    import ctypes
+    import ctypes.util
+    fn = getattr(ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6"), name)
+    fn.restype = ctypes.c_float
+    fn.argtypes = [ctypes.c_float]
+    return lambda x: F(fn(float(x)))
+
+
+_cosf, _sinf = _libm_f32("cosf"), _libm_f32("sinf")
+
+
+def gamma(n):
+    ne = F(n) * _EPS
+    return ne / (ONE - ne)
+
+
+# ---- 3-vectors as lists of np.float32 --------------------------------------------------------
+def add(a, b): return [a[0] + b[0], a[1] + b[1], a[2] + b[2]]
+def sub(a, b): return [a[0] - b[0], a[1] - b[1], a[2] - b[2]]
+def mul(a, b): return [a[0] * b[0], a[1] * b[1], a[2] * b[2]]
+def scale(a, s): return [a[0] * s, a[1] * s, a[2] * s]
+def unscale(a, s): return [a[0] / s, a[1] / s, a[2] / s]
+def neg(a): return [-a[0], -a[1], -a[2]]
+def vabs(a): return [abs(a[0]), abs(a[1]), abs(a[2])]
+def dot(a, b): return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]
+def norm2(a): return dot(a, a)
+def normalize(a): return unscale(a, np.sqrt(norm2(a)))
+def cross(a, b): return [a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]]
+def has_nan(a): return bool(np.isnan(a[0]) or np.isnan(a[1]) or np.isnan(a[2]))
+def lum(s): return F(0.212671) * s[0] + F(0.715160) * s[1] + F(0.072169) * s[2]
+
+
+def _min(lhs, rhs): return rhs if rhs < lhs else lhs
+def _max(lhs, rhs): return rhs if rhs > lhs else lhs
+
+
+def power_heuristic(f, g):
+    return (f * f) / (f * f + g * g)
+
+
+def coordinate_system(z):
+    if abs(z[0]) > abs(z[1]):
+        x = unscale([-z[2], ZERO, z[0]], np.sqrt(z[0] * z[0] + z[2] * z[2]))
+    else:
+        x = unscale([ZERO, z[2], -z[1]], np.sqrt(z[1] * z[1] + z[2] * z[2]))
+    return x, cross(z, x)
+
+
+def concentric_sample_disk(u):
+    ux, uy = F(2) * u[0] - ONE, F(2) * u[1] - ONE
+    if ux == 0 or uy == 0:
+        return ZERO, ZERO
+    if abs(ux) > abs(uy):
+        r, theta = ux, (PI / F(4)) * (uy / ux)
+    else:
+        r, theta = uy, (PI / F(2)) - (PI / F(4)) * (ux / uy)
+    return r * _cosf(theta), r * _sinf(theta)
+
+
+def cosine_sample_hemisphere(u):
+    dx, dy = concentric_sample_disk(u)
+    z = np.sqrt(ONE - (dx * dx + dy * dy))
+    return [dx, dy, z], z * INV_PI
+
+
+def sample_usize_remap(u, length):
+    f = u * F(length)
+    tr = np.trunc(f)
+    return min(int(tr), length - 1), f - tr
+
+
+def distribution_sample_remap(f, u):
+    """Distribution1D::from(f).sample_remap(u) -> (index, pdf, remap)."""
+    n = F(len(f))
+    cdf = []
+    for x in f:
+        cdf.append((cdf[-1] if cdf else ZERO) + F(x) / n)
+    f_sum = cdf[-1]
+    pdf = []
+    for i in range(len(f)):
+        cdf[i] = cdf[i] / f_sum
+        pdf.append(F(f[i]) / (n * f_sum))
+    for i, c in enumerate(cdf):
+        if u <= c:
+            return i, pdf[i], (c - u) / pdf[i]
+    return len(f) - 1, pdf[-1], ONE
+
+
+# ---- sampler front (src/sampler/mod.rs) ------------------------------------------------------
+class PixelSampler:
+    """`value(dim)` is HaltonSampler::get_sample for the current (pixel, sample)."""
+
+    def __init__(self, value):
+        self.value = value
+        self.dim = 0
+
+    def get_sample(self):
+        r = self.value(self.dim)
+        self.dim += 1
+        return r
+
+    def get_1d(self):
+        r = self.get_sample()
+        return F(0.9999999999999) if r >= 1 else r
+
+    def get_2d(self):
+        x = self.get_1d()
+        return [x, self.get_1d()]
+
+    def get_usize(self, mx):
+        f = self.get_sample() * F(mx)
+        r = int(np.trunc(f))
+        return mx - 1 if r == mx else r
+
+
+# ---- geometry --------------------------------------------------------------------------------
+class ShapePoint:
+    def __init__(self, p, n, p_error):
+        self.p, self.n, self.p_error = p, n, p_error
+
+    def offset_by_error(self, w):
+        d = dot(vabs(self.n), self.p_error)
+        offset = scale(self.n, d)
+        if dot(w, self.n) < 0:
+            offset = neg(offset)
+        return add(self.p, offset)
+
+
+class Triangle:
+    def __init__(self, p):
+        self.p = [[F(x) for x in v] for v in p]
+
+    def normal(self):
+        p0, p1, p2 = self.p
+        return normalize(normalize(cross(sub(p0, p2), sub(p1, p2))))     # .normalize(), then Normal3f::from normalizes again (normal.rs:8-12)
+
+    def area(self):
+        p0, p1, p2 = self.p
+        return HALF * np.sqrt(norm2(cross(sub(p1, p0), sub(p2, p0))))
+
+    def interpolate(self, b0, b1, b2):
+        p0, p1, p2 = self.p
+        return add(add(scale(p0, b0), scale(p1, b1)), scale(p2, b2))
+
+    def abs_sum(self, b0, b1, b2):
+        p0, p1, p2 = self.p
+        return add(add(vabs(scale(p0, b0)), vabs(scale(p1, b1))), vabs(scale(p2, b2)))
+
+    def hit_point(self, b):
+        return ShapePoint(self.interpolate(*b), self.normal(), scale(self.abs_sum(*b), gamma(7)))
+
+    def sample(self, sampler):
+        u = sampler.get_2d()
+        su0 = np.sqrt(u[0])
+        b0, b1 = ONE - su0, u[1] * su0
+        b2 = ONE - b0 - b1
+        return ShapePoint(self.interpolate(b0, b1, b2), self.normal(), scale(self.abs_sum(b0, b1, b2), gamma(6))), ONE / self.area()
+
+    def sample_by_point(self, point, sampler):
+        sp, pdf = self.sample(sampler)
+        wi = sub(sp.p, point)
+        if norm2(wi) == 0:
+            return sp, ZERO
+        pdf = pdf * norm2(wi) / -dot(normalize(wi), sp.n)
+        if np.isnan(pdf) or np.isinf(pdf):
+            return sp, ZERO
+        return sp, pdf
+
+    def by_point_pdf(self, point, sp):
+        d = sub(point, sp.p)
+        d2 = norm2(d)
+        dist = np.sqrt(d2)
+        pdf = d2 / (abs(dot(unscale(d, dist), sp.n)) * self.area())
+        return ZERO if (np.isnan(pdf) or np.isinf(pdf)) else pdf
+
+
+class MatteBSDF:
+    """BSDF::new(n, n) + one LambertianReflection(kd)."""
+
+    def __init__(self, n, kd):
+        self.sn = n
+        self.snx, self.sny = coordinate_system(n)
+        self.n = normalize([dot(n, self.snx), dot(n, self.sny), dot(n, self.sn)])
+        self.kd = kd
+
+    def local_to_world(self, w):
+        x, y, z = self.snx, self.sny, self.sn
+        return normalize([x[0] * w[0] + y[0] * w[1] + z[0] * w[2],
+                          x[1] * w[0] + y[1] * w[1] + z[1] * w[2],
+                          x[2] * w[0] + y[2] * w[1] + z[2] * w[2]])
+
+    def world_to_local(self, w):
+        return normalize([dot(w, self.snx), dot(w, self.sny), dot(w, self.sn)])
+
+    def f(self):
+        return scale(self.kd, INV_PI)
+
+    def sample_no_delta_f(self, wo, u):
+        index, remap = sample_usize_remap(u[0], 1)
+        wo_local = self.world_to_local(wo)
+        wi, pdf = cosine_sample_hemisphere([remap, u[1]])
+        if wo_local[2] < 0:
+            wi[2] = wi[2] * F(-1)
+        return self.local_to_world(wi), self.f(), pdf / F(1)
+
+    def no_delta_f_pdf(self, wo, wi):
+        wo, wi = self.world_to_local(wo), self.world_to_local(wi)
+        if not (dot(wo, self.n) * dot(wi, self.n) > 0):
+            return None, ZERO / F(0)        # no transmissive lobe: pdf 0 / len 0 = NaN, f None
+        return add([ZERO, ZERO, ZERO], self.f()), (ZERO + wi[2] * INV_PI) / F(1)
+
+    def sample_f(self, wo, sampler):
+        i, pdf, remap = distribution_sample_remap([1, 0], sampler.get_1d())
+        assert i == 0
+        wi, f, internal = self.sample_no_delta_f(wo, [remap, sampler.get_1d()])
+        return wi, f, pdf * internal, False
+
+
+# ---- the scene -------------------------------------------------------------------------------
+class Scene:
+    def __init__(self, desc, abi, sah, trace):
+        n = int(desc.n_primitives)
+        self.tris, self.kd, self.light_of = [], [], []
+        verts = np.zeros((n, 3, 3), np.float32)
+        for i in range(n):
+            pr = desc.primitives[i]
+            assert pr.shape.kind == abi.SHAPE_TRIANGLE and pr.shape.xform < 0
+            verts[i] = [[desc.triangles[pr.shape.data].p[k][c] for c in range(3)] for k in range(3)]
+            self.tris.append(Triangle(verts[i]))
+            self.light_of.append(int(pr.light))
+            if pr.material >= 0:
+                m = desc.materials[pr.material]
+                assert m.type == 0 and desc.textures[m.tex[0]].kind == 0 and desc.textures[m.tex[1]].value[0] == 0.0
+                self.kd.append([F(x) for x in desc.textures[m.tex[0]].value])
+            else:
+                self.kd.append(None)
+        self.lights = []
+        for k in range(int(desc.n_lights)):
+            lt = desc.lights[k]
+            assert lt.type == 0 and lt.shape.kind == abi.SHAPE_TRIANGLE and lt.shape.xform < 0
+            prim = [i for i in range(n) if self.light_of[i] == k]
+            assert len(prim) == 1
+            self.lights.append((self.tris[prim[0]], [F(x) for x in lt.L]))
+        self.search = trace.Searcher(sah.build(*sah.triangle_bounds(verts)), verts)
+        self.max_depth = int(desc.max_depth)
+        self.rays_closest = 0
+        self.rays_any = 0
+
+    def intersect(self, o, d, t_max=np.finfo(np.float32).max):
+        self.rays_closest += 1
+        prim, _ = self.search.closest(o, d, t_max)
+        if prim is None:
+            return None, None
+        return prim, self.tris[prim].hit_point(self.search.hit_b)
+
+    def occluded(self, o, d, t_max):
+        self.rays_any += 1
+        return self.search.any_hit(o, d, t_max)
+
+
+def uniform_sample_one_light(scene, sp, bsdf, wo, sampler):
+    l = [ZERO, ZERO, ZERO]
+    n = sp.n
+    nl = len(scene.lights)
+    if nl:
+        chosen = sampler.get_usize(nl)
+        shape, le = scene.lights[chosen]
+        # sample the light
+        lp, li_pdf = shape.sample_by_point(sp.p, sampler)
+        if not (norm2(sub(lp.p, sp.p)) == 0 or li_pdf == 0):
+            wi = normalize(sub(lp.p, sp.p))
+            frm = sp.offset_by_error(sub(lp.p, sp.p))
+            to = lp.offset_by_error(sub(frm, lp.p))
+            if li_pdf != 0:
+                f, f_pdf = bsdf.no_delta_f_pdf(wo, wi)
+                if f is not None and f_pdf != 0:
+                    if not scene.occluded(frm, sub(to, frm), ONE - F(0.00001)):
+                        ld = unscale(scale(scale(mul(le, f), abs(dot(n, wi))), power_heuristic(li_pdf, f_pdf)), li_pdf)
+                        l = add(l, ld)
+        # sample the BSDF
+        wi, f, f_pdf = bsdf.sample_no_delta_f(wo, sampler.get_2d())
+        if f_pdf != 0:
+            ld = [ZERO, ZERO, ZERO]
+            prim, hit = scene.intersect(sp.offset_by_error(wi), wi)
+            if prim is not None and scene.light_of[prim] == chosen:
+                li_pdf = shape.by_point_pdf(sp.p, hit)
+                if li_pdf != 0:
+                    ld = unscale(scale(scale(mul(le, f), abs(dot(n, wi))), power_heuristic(f_pdf, li_pdf)), f_pdf)
+            l = add(l, ld)
+    return scale(l, F(nl))
+
+
+def path_li(scene, o, d, sampler):
+    l = [ZERO, ZERO, ZERO]
+    beta = [ONE, ONE, ONE]
+    bounce = 0
+    specular_bounce = False
+    while True:
+        prim, sp = scene.intersect(o, d)
+        if bounce == 0 or specular_bounce:
+            if prim is not None and scene.light_of[prim] >= 0:
+                l = add(l, mul(beta, scene.lights[scene.light_of[prim]][1]))
+        if prim is None or bounce >= scene.max_depth or scene.kd[prim] is None:
+            break
+        bsdf = MatteBSDF(sp.n, scene.kd[prim])
+        wo = neg(d)
+        l = add(l, mul(beta, uniform_sample_one_light(scene, sp, bsdf, wo, sampler)))
+        wi, f, f_pdf, is_delta = bsdf.sample_f(wo, sampler)
+        if f_pdf == 0:
+            break
+        beta = mul(beta, unscale(scale(f, abs(dot(wi, sp.n))), f_pdf))
+        o, d = sp.offset_by_error(wi), wi
+        specular_bounce = is_delta
+        if bounce > 3:
+            q = _max(F(0.05), ONE - lum(beta))
+            if sampler.get_1d() < q:
+                break
+            beta = unscale(beta, ONE - q)
+        bounce += 1
+    return l
+
+
+def render(scene, width, height, spp, halton_value, camera_ray_at, rect=None):
+    """film[h, w, 3] over rect = (x0, y0, x1, y1); halton_value(x, y, sample) -> callable dim -> f32;
+    camera_ray_at(fx, fy) -> (o[3], d[3])."""
+    x0, y0, x1, y1 = rect or (0, 0, width, height)
+    film = np.zeros((height, width, 3), np.float32)
+    with np.errstate(all="ignore"):
+        for y in range(y0, y1):
+            for x in range(x0, x1):
+                fx, fy = F(x), F(y)
+                kept = []
+                for s in range(spp):
+                    sampler = PixelSampler(halton_value(x, y, s))
+                    u = sampler.get_2d()
+                    off = [u[0] - HALF, u[1] - HALF]
+                    fx, fy = fx + off[0], fy + off[1]
+                    o, d = camera_ray_at(fx, fy)
+                    li = path_li(scene, [F(v) for v in o], [F(v) for v in d], sampler)
+                    if not has_nan(li):
+                        kept.append(li)
+                total = [ZERO, ZERO, ZERO]
+                for li in kept:
+                    total = add(total, li)
+                film[y, x] = unscale(total, F(len(kept)))
+    return film

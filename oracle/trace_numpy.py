@@ -75,9 +75,10 @@ def _imax_abs(v):
     return idx
 
 
-def triangle_intersect(p, ray):
-    """Returns t (np.float32) or None.  `Triangle::intersect` and `intersect_predicate` accept and
-    reject exactly the same rays (the same sequence up to the barycentrics)."""
+def triangle_intersect(p, ray, barycentrics=None):
+    """Returns t (np.float32) or None; `barycentrics` (a list) receives b0, b1, b2 = e * inv_det.
+    `Triangle::intersect` and `intersect_predicate` accept and reject exactly the same rays (the
+    same sequence up to the barycentrics)."""
     o = ray.o
     pt = [[p[k][c] - o[c] for c in range(3)] for k in range(3)]
     kz = _imax_abs(ray.d)
@@ -119,6 +120,8 @@ def triangle_intersect(p, ray):
     delta_t = F(3) * (_G3 * max_e * max_zt + delta_e * max_zt + delta_z * max_e) * abs(inv_det)
     if t <= delta_t:
         return None
+    if barycentrics is not None:
+        barycentrics[:] = [e0 * inv_det, e1 * inv_det, e2 * inv_det]
     return t
 
 
@@ -131,6 +134,7 @@ class Searcher:
         self.bounds = [([F(x) for x in b[:3]], [F(x) for x in b[3:]]) for b in tree.bound]
         self.visits = 0
         self.tests = 0
+        self.hit_b = None      # barycentrics of the last accepted hit of the current closest() call
 
     def closest(self, o, d, t_max=np.finfo(np.float32).max):
         """(upload index of the primitive hit, t) or (None, None)."""
@@ -147,10 +151,12 @@ class Searcher:
         if t.is_leaf[node]:
             for slot in range(t.a[node], t.b[node]):
                 self.tests += 1
-                hit = triangle_intersect(self.prims[slot], ray)
+                b = []
+                hit = triangle_intersect(self.prims[slot], ray, b)
                 if hit is not None:
                     ray.t_max = hit
                     result = slot
+                    self.hit_b = b
             return result
         self.visits += 1
         if _slab(self.bounds[node], ray):
