@@ -218,14 +218,74 @@ class Triangle:
         return ZERO if (np.isnan(pdf) or np.isinf(pdf)) else pdf
 
 
-class MatteBSDF:
-    """BSDF::new(n, n) + one LambertianReflection(kd)."""
+def fresnel_dielectric(eta_a, eta_b, cos_i):
+    """FresnelDielectric{eta_i: eta_a, eta_t: eta_b}.evaluate (specular.rs:25-45)."""
+    eta_i, eta_t = (eta_a, eta_b) if cos_i > 0 else (eta_b, eta_a)
+    cos_i = abs(cos_i)
+    sin_i = np.sqrt(ONE - cos_i * cos_i)
+    sin_t = sin_i * eta_i / eta_t
+    if sin_t >= 1:
+        return ONE
+    cos_t = np.sqrt(ONE - sin_t * sin_t)
+    t0, t1 = eta_t * cos_i, eta_i * cos_t
+    r_perl = (t0 - t1) / (t0 + t1)
+    t0, t1 = eta_i * cos_i, eta_t * cos_t
+    r_perp = (t0 - t1) / (t0 + t1)
+    return (r_perl * r_perl + r_perp * r_perp) / F(2)
 
-    def __init__(self, n, kd):
+
+def refract(wo, n, eta):
+    cos_o = dot(wo, n)
+    sin2_o = ONE - cos_o * cos_o
+    sin2_i = sin2_o * eta * eta
+    if sin2_i > 1:
+        return None
+    cos_i = np.sqrt(_max(ONE - sin2_i, ZERO))
+    return add(scale(neg(wo), eta), scale(n, eta * cos_o - cos_i))
+
+
+class SpecularReflection:
+    def __init__(self, r, eta=None):
+        self.r, self.eta = r, eta            # eta None = FresnelNoOp, else FresnelDielectric(1, eta)
+
+    def sample_f(self, wo):
+        wi = [-wo[0], -wo[1], wo[2]]
+        cos_i = wi[2]
+        fr = ONE if self.eta is None else fresnel_dielectric(ONE, self.eta, cos_i)
+        if fr == 0:
+            return None
+        return wi, unscale(scale(self.r, fr), abs(cos_i))
+
+
+class SpecularTransmission:
+    def __init__(self, t, eta_a, eta_b):
+        self.t, self.eta_a, self.eta_b = t, eta_a, eta_b
+
+    def sample_f(self, wo):
+        eta_i, eta_t = (self.eta_a, self.eta_b) if wo[2] > 0 else (self.eta_b, self.eta_a)
+        eta = eta_i / eta_t
+        wi = refract(wo, normalize([ZERO, ZERO, np.copysign(ONE, wo[2])]), eta)
+        if wi is None:
+            return None
+        ft = ONE - fresnel_dielectric(self.eta_a, self.eta_b, wi[2])
+        if ft == 0:
+            return None
+        return wi, unscale(scale(self.t, ft), abs(wi[2]))
+
+
+class BSDF:
+    """BSDF::new(n, n) with `kd` (a LambertianReflection, or None) and a list of delta lobes."""
+
+    def __init__(self, n, kd=None, deltas=()):
         self.sn = n
         self.snx, self.sny = coordinate_system(n)
         self.n = normalize([dot(n, self.snx), dot(n, self.sny), dot(n, self.sn)])
         self.kd = kd
+        self.n_bxdfs = 0 if kd is None else 1
+        self.deltas = list(deltas)
+
+    def is_all_delta(self):
+        return self.n_bxdfs == 0
 
     def local_to_world(self, w):
         x, y, z = self.snx, self.sny, self.sn
@@ -240,6 +300,8 @@ class MatteBSDF:
         return scale(self.kd, INV_PI)
 
     def sample_no_delta_f(self, wo, u):
+        if self.n_bxdfs == 0:
+            return [ZERO, ZERO, ZERO], None, ZERO
         index, remap = sample_usize_remap(u[0], 1)
         wo_local = self.world_to_local(wo)
         wi, pdf = cosine_sample_hemisphere([remap, u[1]])
@@ -247,24 +309,50 @@ class MatteBSDF:
             wi[2] = wi[2] * F(-1)
         return self.local_to_world(wi), self.f(), pdf / F(1)
 
+    def sample_delta_f(self, wo, u):
+        wo_local = self.world_to_local(wo)
+        if not self.deltas:
+            return [ZERO, ZERO, ZERO], None, ZERO
+        wi_f = [r for r in (lobe.sample_f(wo_local) for lobe in self.deltas) if r is not None]
+        assert wi_f, "the reference panics here (Distribution1D::from of an empty table)"
+        i, pdf, _ = distribution_sample_remap([lum(f) for _, f in wi_f], u)
+        wi_local, f = wi_f[i]
+        return self.local_to_world(wi_local), f, pdf
+
     def no_delta_f_pdf(self, wo, wi):
+        if self.n_bxdfs == 0:
+            return None, ZERO
         wo, wi = self.world_to_local(wo), self.world_to_local(wi)
         if not (dot(wo, self.n) * dot(wi, self.n) > 0):
             return None, ZERO / F(0)        # no transmissive lobe: pdf 0 / len 0 = NaN, f None
         return add([ZERO, ZERO, ZERO], self.f()), (ZERO + wi[2] * INV_PI) / F(1)
 
     def sample_f(self, wo, sampler):
-        i, pdf, remap = distribution_sample_remap([1, 0], sampler.get_1d())
-        assert i == 0
-        wi, f, internal = self.sample_no_delta_f(wo, [remap, sampler.get_1d()])
-        return wi, f, pdf * internal, False
+        i, pdf, remap = distribution_sample_remap([self.n_bxdfs, len(self.deltas)], sampler.get_1d())
+        if i == 0:
+            wi, f, internal = self.sample_no_delta_f(wo, [remap, sampler.get_1d()])
+            return wi, f, pdf * internal, False
+        wi, f, internal = self.sample_delta_f(wo, remap)
+        return wi, f, pdf * internal, True
+
+
+MAT_MATTE, MAT_MIRROR, MAT_GLASS = 0, 1, 2
+
+
+def make_bsdf(material, n):
+    kind, a, b, eta = material
+    if kind == MAT_MATTE:
+        return BSDF(n, kd=a)
+    if kind == MAT_MIRROR:
+        return BSDF(n, deltas=[SpecularReflection(a)])
+    return BSDF(n, deltas=[SpecularReflection(a, eta), SpecularTransmission(b, ONE, eta)])
 
 
 # ---- the scene -------------------------------------------------------------------------------
 class Scene:
     def __init__(self, desc, abi, sah, trace):
         n = int(desc.n_primitives)
-        self.tris, self.kd, self.light_of = [], [], []
+        self.tris, self.material, self.light_of = [], [], []
         verts = np.zeros((n, 3, 3), np.float32)
         for i in range(n):
             pr = desc.primitives[i]
@@ -272,12 +360,7 @@ class Scene:
             verts[i] = [[desc.triangles[pr.shape.data].p[k][c] for c in range(3)] for k in range(3)]
             self.tris.append(Triangle(verts[i]))
             self.light_of.append(int(pr.light))
-            if pr.material >= 0:
-                m = desc.materials[pr.material]
-                assert m.type == 0 and desc.textures[m.tex[0]].kind == 0 and desc.textures[m.tex[1]].value[0] == 0.0
-                self.kd.append([F(x) for x in desc.textures[m.tex[0]].value])
-            else:
-                self.kd.append(None)
+            self.material.append(self._material(desc, pr.material) if pr.material >= 0 else None)
         self.lights = []
         for k in range(int(desc.n_lights)):
             lt = desc.lights[k]
@@ -289,6 +372,21 @@ class Scene:
         self.max_depth = int(desc.max_depth)
         self.rays_closest = 0
         self.rays_any = 0
+
+    @staticmethod
+    def _material(desc, index):
+        m = desc.materials[index]
+        def tex(slot):
+            t = desc.textures[m.tex[slot]]
+            assert t.kind == 0, "constant textures only"
+            return [F(x) for x in t.value]
+        if m.type == MAT_MATTE:
+            assert tex(1)[0] == 0, "sigma = 0 (LambertianReflection) only"
+            return MAT_MATTE, tex(0), None, None
+        if m.type == MAT_MIRROR:
+            return MAT_MIRROR, tex(0), None, None
+        assert m.type == MAT_GLASS
+        return MAT_GLASS, tex(0), tex(1), tex(2)[0]
 
     def intersect(self, o, d, t_max=np.finfo(np.float32).max):
         self.rays_closest += 1
@@ -344,13 +442,14 @@ def path_li(scene, o, d, sampler):
         if bounce == 0 or specular_bounce:
             if prim is not None and scene.light_of[prim] >= 0:
                 l = add(l, mul(beta, scene.lights[scene.light_of[prim]][1]))
-        if prim is None or bounce >= scene.max_depth or scene.kd[prim] is None:
+        if prim is None or bounce >= scene.max_depth or scene.material[prim] is None:
             break
-        bsdf = MatteBSDF(sp.n, scene.kd[prim])
+        bsdf = make_bsdf(scene.material[prim], sp.n)
         wo = neg(d)
-        l = add(l, mul(beta, uniform_sample_one_light(scene, sp, bsdf, wo, sampler)))
+        if not bsdf.is_all_delta():
+            l = add(l, mul(beta, uniform_sample_one_light(scene, sp, bsdf, wo, sampler)))
         wi, f, f_pdf, is_delta = bsdf.sample_f(wo, sampler)
-        if f_pdf == 0:
+        if f is None or f_pdf == 0:
             break
         beta = mul(beta, unscale(scale(f, abs(dot(wi, sp.n))), f_pdf))
         o, d = sp.offset_by_error(wi), wi

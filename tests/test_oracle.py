@@ -465,22 +465,32 @@ def test_bvh_search_against_independent_numpy_restatement(cpbrt, oracle, case):
     assert (search.visits, search.tests) == (int(any_count[0]), int(any_count[1])), name
 
 
-def _matte_cornell_text(**kw):
-    """The Cornell box with the glass ball taken out and the mirror block made matte: 32 matte / emissive triangles."""
+def _triangle_cornell_text(variant, **kw):
+    """The Cornell box with the glass ball taken out (32 triangles).  "matte": the mirror block made matte too;
+    "specular": the mirror block kept and the short block made of glass."""
     text = scene_text("cornel_box.pbrt", **kw)
     ball = 'Translate 188 247.5 176.5\nMaterial "glass"\nShape "sphere" "float radius" [82.5]\n'
-    assert ball in text and 'Material "mirror"' in text
-    return text.replace(ball, "").replace('Material "mirror"', 'Material "matte"')
+    short_block = 'ObjectBegin "ball_and_box"\nMaterial "matte"'
+    assert ball in text and 'Material "mirror"' in text and short_block in text
+    text = text.replace(ball, "")
+    if variant == "matte":
+        return text.replace('Material "mirror"', 'Material "matte"')
+    return text.replace(short_block, 'ObjectBegin "ball_and_box"\nMaterial "glass"')
 
 
-def test_path_integrator_against_independent_numpy_restatement(cpbrt, oracle):
+@pytest.mark.parametrize("variant", ["matte", "specular"])
+def test_path_integrator_against_independent_numpy_restatement(cpbrt, oracle, variant):
     """a1, a3, a5, a7, a16, a18, second pin: oracle/path_numpy.py restates the render loop (film-point drift, NaN drop,
     mean), the sampler front, PathIntegrator::li, uniform_sample_one_light with both MIS branches, the area light, the
-    triangle sampling, the matte BSDF and Russian roulette in scalar np.float32 from the Rust alone, over the numpy BVH.
+    triangle sampling, the matte BSDF, the mirror and glass delta lobes (Fresnel, refraction, the luminance-weighted
+    choice between them, emission seen through specular bounces) and Russian roulette in scalar np.float32 from the
+    Rust alone, over the numpy BVH.
     Every pixel of the C++ oracle's image must equal it bit for bit, at every path depth, with the same ray counts.
     (Its first run differed in 3 of 576 pixels by one ulp: the new reading had missed that Normal3f::from normalises
     an already normalised vector -- the C++ oracle had it.)"""
-    scene = cpbrt.Scene.parse(_matte_cornell_text(xres=22, yres=22, spp=3), base_dir=SCENES)
+    scene = cpbrt.Scene.parse(_triangle_cornell_text(variant, xres=22, yres=22, spp=3), base_dir=SCENES)
+    kinds = {int(scene.desc.materials[scene.desc.primitives[i].material].type) for i in range(int(scene.desc.n_primitives)) if scene.desc.primitives[i].material >= 0}
+    assert kinds == ({0} if variant == "matte" else {0, 1, 2})
     sah, trace, path = (_load_oracle_py(n) for n in ("sah_numpy", "trace_numpy", "path_numpy"))
     w = oracle.OracleWorld(scene)
     mine = path.Scene(scene.desc, cpbrt.abi, sah, trace)
