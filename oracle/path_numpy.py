@@ -14,6 +14,7 @@ ray counts.  What it takes from outside, as inputs:
   render loop, film-point drift, NaN drop, mean   src/render.rs:20-44, src/film.rs:11-18
   Sampler::get_1d / get_2d / get_usize            src/sampler/mod.rs:10-36
   PathIntegrator::li                              src/integrator/path.rs:13-66
+  DirectLightIntegrator::li_depth                 src/integrator/direct_light.rs:12-41
   uniform_sample_one_light                        src/integrator/mod.rs:13-97
   AreaLight::sample_li / le / pdf                 src/light/area.rs:17-51
   VisibilityTester, Ray::from_to                  src/light/mod.rs:100-115, src/geometry/ray.rs:30-36
@@ -353,12 +354,20 @@ class Scene:
     def __init__(self, desc, abi, sah, trace):
         n = int(desc.n_primitives)
         self.tris, self.material, self.light_of = [], [], []
-        verts = np.zeros((n, 3, 3), np.float32)
+        prims = []
         for i in range(n):
             pr = desc.primitives[i]
-            assert pr.shape.kind == abi.SHAPE_TRIANGLE and pr.shape.xform < 0
-            verts[i] = [[desc.triangles[pr.shape.data].p[k][c] for c in range(3)] for k in range(3)]
-            self.tris.append(Triangle(verts[i]))
+            if pr.shape.kind == abi.SHAPE_TRIANGLE:
+                assert pr.shape.xform < 0
+                verts = [[desc.triangles[pr.shape.data].p[k][c] for c in range(3)] for k in range(3)]
+                prims.append(trace.TrianglePrim(verts))
+                self.tris.append(Triangle(verts))
+            else:
+                assert pr.shape.kind == abi.SHAPE_SPHERE and pr.shape.xform >= 0 and pr.light < 0
+                t = desc.transforms[pr.shape.xform]
+                assert t.outer < 0
+                prims.append(trace.SpherePrim(desc.sphere_radius[pr.shape.data], list(t.m), list(t.m_inv)))
+                self.tris.append(None)
             self.light_of.append(int(pr.light))
             self.material.append(self._material(desc, pr.material) if pr.material >= 0 else None)
         self.lights = []
@@ -368,7 +377,10 @@ class Scene:
             prim = [i for i in range(n) if self.light_of[i] == k]
             assert len(prim) == 1
             self.lights.append((self.tris[prim[0]], [F(x) for x in lt.L]))
-        self.search = trace.Searcher(sah.build(*sah.triangle_bounds(verts)), verts)
+        bounds = [q.bounds() for q in prims]
+        lo = np.array([b[0] for b in bounds], np.float32)
+        hi = np.array([b[1] for b in bounds], np.float32)
+        self.search = trace.Searcher(sah.build(lo, hi), prims)
         self.max_depth = int(desc.max_depth)
         self.rays_closest = 0
         self.rays_any = 0
@@ -393,6 +405,8 @@ class Scene:
         prim, _ = self.search.closest(o, d, t_max)
         if prim is None:
             return None, None
+        if self.tris[prim] is None:
+            return prim, ShapePoint(*self.search.hit_b)
         return prim, self.tris[prim].hit_point(self.search.hit_b)
 
     def occluded(self, o, d, t_max):
@@ -421,7 +435,7 @@ def uniform_sample_one_light(scene, sp, bsdf, wo, sampler):
                         l = add(l, ld)
         # sample the BSDF
         wi, f, f_pdf = bsdf.sample_no_delta_f(wo, sampler.get_2d())
-        if f_pdf != 0:
+        if f is not None and f_pdf != 0:
             ld = [ZERO, ZERO, ZERO]
             prim, hit = scene.intersect(sp.offset_by_error(wi), wi)
             if prim is not None and scene.light_of[prim] == chosen:
@@ -463,7 +477,31 @@ def path_li(scene, o, d, sampler):
     return l
 
 
-def render(scene, width, height, spp, halton_value, camera_ray_at, rect=None):
+def direct_li(scene, o, d, sampler, depth=0):
+    """DirectLightIntegrator::li_depth (direct_light.rs:12-41): one-light estimate at the hit, then the recursion
+    over every delta lobe.  uniform_sample_one_light runs (and draws its five numbers) on all-delta surfaces too."""
+    l = [ZERO, ZERO, ZERO]
+    prim, sp = scene.intersect(o, d)
+    if prim is None:
+        return l
+    if scene.material[prim] is None:
+        return add(l, scene.lights[scene.light_of[prim]][1])
+    bsdf = make_bsdf(scene.material[prim], sp.n)
+    wo = neg(normalize(d))
+    l = add(l, uniform_sample_one_light(scene, sp, bsdf, wo, sampler))
+    if depth + 1 < scene.max_depth:
+        wo_local = bsdf.world_to_local(wo)
+        for lobe in bsdf.deltas:
+            r = lobe.sample_f(wo_local)
+            if r is None:
+                continue
+            wi, s_ = bsdf.local_to_world(r[0]), r[1]
+            inner = direct_li(scene, sp.offset_by_error(wi), wi, sampler, depth + 1)
+            l = add(l, scale(mul(inner, s_), abs(dot(sp.n, wi))))
+    return l
+
+
+def render(scene, width, height, spp, halton_value, camera_ray_at, rect=None, integrator="path"):
     """film[h, w, 3] over rect = (x0, y0, x1, y1); halton_value(x, y, sample) -> callable dim -> f32;
     camera_ray_at(fx, fy) -> (o[3], d[3])."""
     x0, y0, x1, y1 = rect or (0, 0, width, height)
@@ -479,7 +517,7 @@ def render(scene, width, height, spp, halton_value, camera_ray_at, rect=None):
                     off = [u[0] - HALF, u[1] - HALF]
                     fx, fy = fx + off[0], fy + off[1]
                     o, d = camera_ray_at(fx, fy)
-                    li = path_li(scene, [F(v) for v in o], [F(v) for v in d], sampler)
+                    li = (path_li if integrator == "path" else direct_li)(scene, [F(v) for v in o], [F(v) for v in d], sampler)
                     if not has_nan(li):
                         kept.append(li)
                 total = [ZERO, ZERO, ZERO]

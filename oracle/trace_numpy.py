@@ -16,8 +16,16 @@ the C++ oracle -- and through it the device kernels -- to the same primitive and
   gamma(n)                         src/math/mod.rs:76-79, MACHINE_EPSILON = f32::EPSILON / 2 (def.rs:4)
   min / max                        src/math/mod.rs:36-49 (`rhs < lhs ? rhs : lhs`)
 
+  Sphere::intersect, solve_quadratic  src/geometry/shape/sphere.rs:29-53,114-136 (f64 quadratic, p rescaled
+                                   onto the sphere, normal normalised twice, p_error = gamma(5)|p|)
+  TransformShape::{bound,intersect} src/geometry/shape/transform.rs:52-59: the ray goes through the inverse, the
+                                   hit through ShapePoint::apply (shape/mod.rs:135-160: p_error is REPLACED by
+                                   gamma(3) * (|m_i0 p'_x| + |m_i1 p'_y| + |m_i2 p'_z| + m_i3) of the transformed p')
+  Point3f / Vector3f / Normal3f::apply  src/geometry/{point,vector,normal}.rs; nalgebra's matrix * vector adds the
+                                   columns in order: ((m_i0 x + m_i1 y) + m_i2 z) + m_i3 w
+
 The tree comes from oracle/sah_numpy.py (`SahTree`); `tris` are the (n, 3, 3) float32 vertices in
-upload order."""
+upload order, or a list of `TrianglePrim` / `SpherePrim`."""
 import numpy as np
 
 F = np.float32
@@ -125,16 +133,131 @@ def triangle_intersect(p, ray, barycentrics=None):
     return t
 
 
+def mat_rows(m16):
+    return [[F(m16[r * 4 + c]) for c in range(4)] for r in range(4)]
+
+
+def mat_vec(m, v):
+    return [((m[i][0] * v[0] + m[i][1] * v[1]) + m[i][2] * v[2]) + m[i][3] * v[3] for i in range(len(m))]
+
+
+def mat_mul(a, b):
+    """nalgebra gemm: each column of the product is a gemv."""
+    cols = [[sum_in_order([a[i][k] * b[k][j] for k in range(len(b))]) for i in range(len(a))] for j in range(len(b[0]))]
+    return [[cols[j][i] for j in range(len(cols))] for i in range(len(a))]
+
+
+def sum_in_order(terms):
+    acc = terms[0]
+    for t in terms[1:]:
+        acc = acc + t
+    return acc
+
+
+def apply_point(m, p):
+    h = mat_vec(m, [p[0], p[1], p[2], F(1)])
+    return [h[0] / h[3], h[1] / h[3], h[2] / h[3]]          # Point3::from_homogeneous
+
+
+def apply_vector(m, v):
+    return mat_vec(m, [v[0], v[1], v[2], F(0)])[:3]
+
+
+def normal_matrix(m_inv):
+    """Matrix3x4::identity() * (m_inv.transpose() * Matrix4x3::identity())  (normal.rs:33-36)."""
+    eye34 = [[F(1 if r == c else 0) for c in range(4)] for r in range(3)]
+    eye43 = [[F(1 if r == c else 0) for c in range(3)] for r in range(4)]
+    transposed = [[m_inv[c][r] for c in range(4)] for r in range(4)]
+    return mat_mul(eye34, mat_mul(transposed, eye43))
+
+
+def transformed_bounds(lo, hi, m):
+    """Bounds3f::apply (bounds.rs:292-300): the union of the eight transformed corners."""
+    box = (lo, hi)
+    corners = [apply_point(m, [box[(i >> c) & 1][c] for c in range(3)]) for i in range(8)]
+    out_lo, out_hi = list(corners[0]), list(corners[0])
+    for q in corners[1:]:
+        for c in range(3):
+            out_lo[c] = _min(out_lo[c], q[c])
+            out_hi[c] = _max(out_hi[c], q[c])
+    return out_lo, out_hi
+
+
+class TrianglePrim:
+    def __init__(self, verts):
+        self.p = [[F(x) for x in v] for v in verts]
+
+    def bounds(self):
+        return [min(v[c] for v in self.p) for c in range(3)], [max(v[c] for v in self.p) for c in range(3)]
+
+    def intersect(self, ray):
+        """(t, barycentrics) or None."""
+        b = []
+        t = triangle_intersect(self.p, ray, b)
+        return None if t is None else (t, b)
+
+
+class SpherePrim:
+    """TransformShape{Sphere{radius}, transform} -- one wrapper, as `Shape "sphere"` under a CTM yields."""
+
+    def __init__(self, radius, m16, m_inv16):
+        self.radius = F(radius)
+        self.m, self.m_inv = mat_rows(m16), mat_rows(m_inv16)
+        self.m3 = normal_matrix(self.m_inv)
+
+    def bounds(self):
+        r = self.radius
+        lo, hi = [-r, -r, -r], [r, r, r]
+        return transformed_bounds([_min(lo[c], hi[c]) for c in range(3)], [_max(lo[c], hi[c]) for c in range(3)], self.m)
+
+    def intersect(self, ray):
+        """(t, (p, n, p_error)) in world space, or None."""
+        o, d = apply_point(self.m_inv, ray.o), apply_vector(self.m_inv, ray.d)
+        a = (d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]
+        b = F(2) * ((d[0] * o[0] + d[1] * o[1]) + d[2] * o[2])
+        c = ((o[0] * o[0] + o[1] * o[1]) + o[2] * o[2]) - self.radius * self.radius
+        a, b, c = np.float64(a), np.float64(b), np.float64(c)
+        discrim = b * b - np.float64(4) * a * c
+        if discrim < 0:
+            return None
+        root = np.sqrt(discrim)
+        q = np.float64(-0.5) * (b - root) if b < 0 else np.float64(-0.5) * (b + root)
+        t0, t1 = q / a, c / q
+        if t0 > t1:
+            t0, t1 = t1, t0
+        t0, t1 = F(t0), F(t1)
+        if t0 > ray.t_max or t1 < 0:
+            return None
+        t = t1 if t0 < 0 else t0
+        if t > ray.t_max:
+            return None
+        p = [o[k] + d[k] * t for k in range(3)]
+        k = self.radius / np.sqrt((p[0] * p[0] + p[1] * p[1]) + p[2] * p[2])
+        p = [x * k for x in p]
+
+        def normalize(v):
+            length = np.sqrt((v[0] * v[0] + v[1] * v[1]) + v[2] * v[2])
+            return [x / length for x in v]
+        n = normalize(normalize(p))
+        # ShapeIntersect::apply(transform): the object-space p_error (gamma(5)|p|) is dropped
+        pw = apply_point(self.m, p)
+        nw = [(self.m3[i][0] * n[0] + self.m3[i][1] * n[1]) + self.m3[i][2] * n[2] for i in range(3)]
+        m = self.m
+        g3 = gamma(3)
+        err = [g3 * (((abs(m[i][0] * pw[0]) + abs(m[i][1] * pw[1])) + abs(m[i][2] * pw[2])) + m[i][3]) for i in range(3)]
+        return t, (pw, nw, err)
+
+
 class Searcher:
     def __init__(self, tree, tris):
-        tris = np.asarray(tris, F)
+        prims = tris if isinstance(tris, list) else [TrianglePrim(v) for v in np.asarray(tris, F)]
         self.tree = tree
         self.order = [int(i) for i in tree.order]
-        self.prims = [[[F(x) for x in v] for v in tris[i]] for i in self.order]   # BVH slot -> vertices
+        self.prims = [prims[i] for i in self.order]   # BVH slot -> primitive
         self.bounds = [([F(x) for x in b[:3]], [F(x) for x in b[3:]]) for b in tree.bound]
         self.visits = 0
         self.tests = 0
-        self.hit_b = None      # barycentrics of the last accepted hit of the current closest() call
+        self.hit_b = None      # barycentrics (triangle) or (p, n, p_error) (sphere) of the last accepted hit of the current closest() call
 
     def closest(self, o, d, t_max=np.finfo(np.float32).max):
         """(upload index of the primitive hit, t) or (None, None)."""
@@ -151,12 +274,11 @@ class Searcher:
         if t.is_leaf[node]:
             for slot in range(t.a[node], t.b[node]):
                 self.tests += 1
-                b = []
-                hit = triangle_intersect(self.prims[slot], ray, b)
+                hit = self.prims[slot].intersect(ray)
                 if hit is not None:
-                    ray.t_max = hit
+                    ray.t_max = hit[0]
                     result = slot
-                    self.hit_b = b
+                    self.hit_b = hit[1]
             return result
         self.visits += 1
         if _slab(self.bounds[node], ray):
@@ -178,7 +300,7 @@ class Searcher:
         if t.is_leaf[node]:
             for slot in range(t.a[node], t.b[node]):
                 self.tests += 1
-                if triangle_intersect(self.prims[slot], ray) is not None:
+                if self.prims[slot].intersect(ray) is not None:
                     return True
             return False
         self.visits += 1

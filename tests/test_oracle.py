@@ -466,9 +466,12 @@ def test_bvh_search_against_independent_numpy_restatement(cpbrt, oracle, case):
 
 
 def _triangle_cornell_text(variant, **kw):
-    """The Cornell box with the glass ball taken out (32 triangles).  "matte": the mirror block made matte too;
-    "specular": the mirror block kept and the short block made of glass."""
+    """"full": scenes/cornel_box.pbrt as it is (the headline scene: 32 triangles, a glass ball under a Translate, a
+    mirror block).  Otherwise the ball is taken out; "matte": the mirror block made matte too; "specular": the mirror
+    block kept and the short block made of glass."""
     text = scene_text("cornel_box.pbrt", **kw)
+    if variant == "full":
+        return text
     ball = 'Translate 188 247.5 176.5\nMaterial "glass"\nShape "sphere" "float radius" [82.5]\n'
     short_block = 'ObjectBegin "ball_and_box"\nMaterial "matte"'
     assert ball in text and 'Material "mirror"' in text and short_block in text
@@ -478,19 +481,21 @@ def _triangle_cornell_text(variant, **kw):
     return text.replace(short_block, 'ObjectBegin "ball_and_box"\nMaterial "glass"')
 
 
-@pytest.mark.parametrize("variant", ["matte", "specular"])
+@pytest.mark.parametrize("variant", ["matte", "specular", "full"])
 def test_path_integrator_against_independent_numpy_restatement(cpbrt, oracle, variant):
     """a1, a3, a5, a7, a16, a18, second pin: oracle/path_numpy.py restates the render loop (film-point drift, NaN drop,
     mean), the sampler front, PathIntegrator::li, uniform_sample_one_light with both MIS branches, the area light, the
     triangle sampling, the matte BSDF, the mirror and glass delta lobes (Fresnel, refraction, the luminance-weighted
-    choice between them, emission seen through specular bounces) and Russian roulette in scalar np.float32 from the
-    Rust alone, over the numpy BVH.
+    choice between them, emission seen through specular bounces), the sphere under a TransformShape (f64 quadratic,
+    the hit carried back through ShapePoint::apply with its replaced error bound) and Russian roulette in scalar
+    np.float32 from the Rust alone, over the numpy BVH.
     Every pixel of the C++ oracle's image must equal it bit for bit, at every path depth, with the same ray counts.
     (Its first run differed in 3 of 576 pixels by one ulp: the new reading had missed that Normal3f::from normalises
     an already normalised vector -- the C++ oracle had it.)"""
     scene = cpbrt.Scene.parse(_triangle_cornell_text(variant, xres=22, yres=22, spp=3), base_dir=SCENES)
     kinds = {int(scene.desc.materials[scene.desc.primitives[i].material].type) for i in range(int(scene.desc.n_primitives)) if scene.desc.primitives[i].material >= 0}
     assert kinds == ({0} if variant == "matte" else {0, 1, 2})
+    assert int(scene.desc.n_spheres) == (1 if variant == "full" else 0)
     sah, trace, path = (_load_oracle_py(n) for n in ("sah_numpy", "trace_numpy", "path_numpy"))
     w = oracle.OracleWorld(scene)
     mine = path.Scene(scene.desc, cpbrt.abi, sah, trace)
@@ -513,6 +518,31 @@ def test_path_integrator_against_independent_numpy_restatement(cpbrt, oracle, va
         assert (film > 0).any() and np.isfinite(film).all()
         assert (mine.rays_closest, mine.rays_any) == (st["rays_closest"], st["rays_any"]), depth
         assert np.array_equal(film.view(np.uint32), ref.view(np.uint32)), depth
+
+
+def test_directlighting_against_independent_numpy_restatement(cpbrt, oracle):
+    """a6, second pin: DirectLightIntegrator::li_depth of oracle/path_numpy.py (the one-light estimate run on all-delta
+    surfaces too, the recursion over every delta lobe of the mirror block and the glass ball) on the unmodified
+    Cornell box: bit-equal image, equal ray counts."""
+    scene = cpbrt.Scene.parse(scene_text("cornel_box.pbrt", xres=22, yres=22, spp=3, integrator=("directlighting", 5)), base_dir=SCENES)
+    sah, trace, path = (_load_oracle_py(n) for n in ("sah_numpy", "trace_numpy", "path_numpy"))
+    w = oracle.OracleWorld(scene)
+    mine = path.Scene(scene.desc, cpbrt.abi, sah, trace)
+
+    def halton_value(x, y, s):
+        dims = np.arange(256, dtype=np.uint32)
+        _, v = w.halton(np.full(256, x, np.uint32), np.full(256, y, np.uint32), np.full(256, s, np.uint32), dims)
+        return lambda dim: v[dim]
+
+    def camera_ray_at(fx, fy):
+        r = w.camera_ray_at(fx, fy)
+        return r[0:3], r[4:7]
+
+    film = path.render(mine, 22, 22, 3, halton_value, camera_ray_at, integrator="directlighting")
+    ref, _, st = w.render()
+    assert (film > 0).any() and np.isfinite(film).all()
+    assert (mine.rays_closest, mine.rays_any) == (st["rays_closest"], st["rays_any"])
+    assert np.array_equal(film.view(np.uint32), ref.view(np.uint32))
 
 
 def test_render_is_deterministic_and_thread_count_independent(make_scene, oracle):
