@@ -481,6 +481,65 @@ def _triangle_cornell_text(variant, **kw):
     return text.replace(short_block, 'ObjectBegin "ball_and_box"\nMaterial "glass"')
 
 
+def _independent_front(scene):
+    """halton_value / camera_ray_at for oracle/path_numpy.render from oracle/front_numpy.py: nothing of the C++ oracle."""
+    front = _load_oracle_py("front_numpy")
+    d = scene.desc
+    perm = np.ctypeslib.as_array(d.sampler.permutation, shape=(cpbrt_perm_len(),))
+    cam = front.PerspectiveCamera(list(d.camera.raster_to_camera), list(d.camera.camera_to_world) if d.camera.has_camera_to_world else None)
+    assert not d.camera.has_lens
+
+    def halton_value(x, y, s):
+        smp = front.HaltonSampler(int(d.sampler.spp), (int(d.film_width), int(d.film_height)), perm)
+        smp.set_pixel(x, y)
+        for _ in range(s):
+            smp.next_sample()
+
+        def value(dim):
+            smp.dim = dim
+            return smp.get_sample()
+        return value
+    return halton_value, cam.generate_ray
+
+
+def cpbrt_perm_len():
+    return 3682913      # CPBRT_PERM_TABLE_LEN: the sum of the first 1000 primes
+
+
+@pytest.mark.parametrize("size", [(900, 900, 1024), (1920, 1080, 1024), (9, 4, 16)])
+def test_sampler_and_camera_against_independent_numpy_restatement(cpbrt, oracle, size):
+    """a2-a4, second pin: oracle/front_numpy.py (Python integers + np.float32 from halton.rs / perspective.rs alone):
+    sampler set-up including the wrapped Bezout coefficient, pixel indices, radical inverses of dimensions 0..999 at
+    the BASELINE film sizes, and camera rays under the LookAt transform -- all bit-equal to the C++ oracle."""
+    width, height, spp = size
+    scene = cpbrt.Scene.parse(scene_text("cornel_box.pbrt", xres=width, yres=height, spp=spp), base_dir=SCENES)
+    d = scene.desc
+    front = _load_oracle_py("front_numpy")
+    w = oracle.OracleWorld(scene)
+    smp = front.HaltonSampler(spp, (width, height), np.ctypeslib.as_array(d.sampler.permutation, shape=(cpbrt_perm_len(),)))
+    assert (smp.scale, smp.exp, smp.mult_inverse) == (list(d.sampler.scale), list(d.sampler.exp), list(d.sampler.mult_inverse))
+    rng = np.random.RandomState(1)
+    dims = np.arange(0, 1000, 7, dtype=np.uint32)
+    for _ in range(25):
+        x, y, k = int(rng.randint(width)), int(rng.randint(height)), int(rng.randint(spp))
+        smp.set_pixel(x, y)
+        for _j in range(k):
+            smp.next_sample()
+        idx, val = w.halton(np.full(len(dims), x, np.uint32), np.full(len(dims), y, np.uint32), np.full(len(dims), k, np.uint32), dims)
+        assert int(idx[0]) == smp.index
+        mine = []
+        for dim in dims:
+            smp.dim = int(dim)
+            mine.append(smp.get_sample())
+        assert np.array_equal(np.array(mine, np.float32).view(np.uint32), val.view(np.uint32))
+    halton_value, camera_ray_at = _independent_front(scene)
+    for _ in range(200):
+        fx, fy = np.float32(rng.rand() * width), np.float32(rng.rand() * height)
+        o, dd = camera_ray_at(fx, fy)
+        r = w.camera_ray_at(fx, fy)
+        assert np.array_equal(np.array(o + dd, np.float32).view(np.uint32), np.concatenate([r[0:3], r[4:7]]).view(np.uint32))
+
+
 @pytest.mark.parametrize("variant", ["matte", "specular", "full"])
 def test_path_integrator_against_independent_numpy_restatement(cpbrt, oracle, variant):
     """a1, a3, a5, a7, a16, a18, second pin: oracle/path_numpy.py restates the render loop (film-point drift, NaN drop,
@@ -510,6 +569,8 @@ def test_path_integrator_against_independent_numpy_restatement(cpbrt, oracle, va
         r = w.camera_ray_at(fx, fy)
         return r[0:3], r[4:7]
 
+    if variant == "full":      # scene description in, image out: nothing of the C++ oracle on this side
+        halton_value, camera_ray_at = _independent_front(scene)
     for depth, rect in ((5, None), (2, (3, 9, 19, 13)), (0, (0, 0, 22, 4))):
         mine.max_depth = depth
         mine.rays_closest = mine.rays_any = 0

@@ -1,5 +1,6 @@
 """Whole-image comparison of the C++ oracle with the independent numpy restatement
-(oracle/{sah,trace,path}_numpy.py) on scenes/cornel_box.pbrt.  CPU only, slow (about 400 paths/s).
+(oracle/{front,sah,trace,path}_numpy.py: sampler, camera, BVH, search, integrator -- nothing of the C++
+oracle on that side) on scenes/cornel_box.pbrt.  CPU only, slow (about 400 paths/s).
 
     python tools/independent_restatement_check.py WIDTH HEIGHT SPP [MAXDEPTH] > profiles/...json
 """
@@ -30,20 +31,28 @@ def load(name):
 def main():
     width, height, spp = (int(v) for v in sys.argv[1:4])
     depth = int(sys.argv[4]) if len(sys.argv) > 4 else 5
-    sah, trace, path = load("sah_numpy"), load("trace_numpy"), load("path_numpy")
+    sah, trace, path, front = load("sah_numpy"), load("trace_numpy"), load("path_numpy"), load("front_numpy")
     scene = cpbrt.Scene.parse(scene_text("cornel_box.pbrt", xres=width, yres=height, spp=spp), base_dir=SCENES)
     world = oracle_api.OracleWorld(scene)
     mine = path.Scene(scene.desc, cpbrt.abi, sah, trace)
     mine.max_depth = depth
 
-    def halton_value(x, y, s):
-        dims = np.arange(128, dtype=np.uint32)
-        _, v = world.halton(np.full(128, x, np.uint32), np.full(128, y, np.uint32), np.full(128, s, np.uint32), dims)
-        return lambda dim: v[dim]
+    d = scene.desc
+    perm = np.ctypeslib.as_array(d.sampler.permutation, shape=(3682913,))
+    cam = front.PerspectiveCamera(list(d.camera.raster_to_camera), list(d.camera.camera_to_world) if d.camera.has_camera_to_world else None)
 
-    def camera_ray_at(fx, fy):
-        r = world.camera_ray_at(fx, fy)
-        return r[0:3], r[4:7]
+    def halton_value(x, y, s):
+        smp = front.HaltonSampler(spp, (width, height), perm)
+        smp.set_pixel(x, y)
+        for _ in range(s):
+            smp.next_sample()
+
+        def value(dim):
+            smp.dim = dim
+            return smp.get_sample()
+        return value
+
+    camera_ray_at = cam.generate_ray
 
     t0 = time.time()
     film = path.render(mine, width, height, spp, halton_value, camera_ray_at)
