@@ -350,6 +350,98 @@ def make_bsdf(material, n):
 
 
 # ---- the scene -------------------------------------------------------------------------------
+class SphereLightShape:
+    """TransformShape{Sphere} as a light's shape: sample_by_point / by_point_pdf go through the inverse transform
+    (transform.rs:60-70), Sphere::sample_by_point is the cone sampling of sphere.rs:66-99 (outside the sphere)."""
+
+    def __init__(self, prim, trace):
+        self.prim, self.trace = prim, trace
+
+    def _to_world(self, p, n):
+        t, q = self.trace, self.prim
+        pw = t.apply_point(q.m, p)
+        nw = [(q.m3[i][0] * n[0] + q.m3[i][1] * n[1]) + q.m3[i][2] * n[2] for i in range(3)]
+        g3 = gamma(3)
+        err = [g3 * (((abs(q.m[i][0] * pw[0]) + abs(q.m[i][1] * pw[1])) + abs(q.m[i][2] * pw[2])) + q.m[i][3]) for i in range(3)]
+        return ShapePoint(pw, nw, err)
+
+    def sample_by_point(self, point, sampler):
+        r = self.prim.radius
+        point = self.trace.apply_point(self.prim.m_inv, point)
+        d2 = norm2(point)
+        r2 = r * r
+        assert d2 > r2, "shading point inside the emitter: default_sample_by_point, not restated"
+        dist = np.sqrt(d2)
+        z = unscale(point, dist)
+        x, y = coordinate_system(z)
+        u = sampler.get_2d()
+        sin_max2 = r2 / d2
+        cos_max = np.sqrt(_max(ONE - sin_max2, ZERO))
+        cos_t = (ONE - u[0]) + u[0] * cos_max
+        sin_t = np.sqrt(_max(ONE - cos_t * cos_t, ZERO))
+        phi = u[1] * F(2) * PI
+        ds = dist * cos_t - np.sqrt(_max(r2 - d2 * sin_t * sin_t, ZERO))
+        cos_a = (d2 + r2 - ds * ds) / (F(2) * dist * r)
+        sin_a = np.sqrt(_max(ONE - cos_a * cos_a, ZERO))
+        d = add(add(scale(z, cos_a), scale(x, sin_a * _cosf(phi))), scale(y, sin_a * _sinf(phi)))
+        n = normalize(d)
+        p = scale(d, r)
+        return self._to_world(p, n), ONE / (F(2) * PI * (ONE - cos_max))
+
+    def by_point_pdf(self, point, sp):
+        r = self.prim.radius
+        point = self.trace.apply_point(self.prim.m_inv, point)
+        d2 = norm2(point)
+        assert not d2 < r * r
+        cos_max = np.sqrt(ONE - r * r / d2)
+        return ONE / (F(2) * PI * (ONE - cos_max))
+
+
+class AreaLight:
+    is_delta = False
+
+    def __init__(self, shape, le):
+        self.shape, self.le = shape, le
+
+    def sample_li(self, scene, sp, sampler):
+        """(wi, li, pdf, shadow ray) or None."""
+        lp, pdf = self.shape.sample_by_point(sp.p, sampler)
+        if norm2(sub(lp.p, sp.p)) == 0 or pdf == 0:
+            return None
+        frm = sp.offset_by_error(sub(lp.p, sp.p))
+        to = lp.offset_by_error(sub(frm, lp.p))
+        return normalize(sub(lp.p, sp.p)), self.le, pdf, (frm, sub(to, frm), ONE - F(0.00001))
+
+
+class PointLight:
+    """DeltaLight adaptor (light/mod.rs:80-98: two numbers drawn and dropped, pdf 1) over PointLight (point.rs)."""
+    is_delta = True
+
+    def __init__(self, p, i):
+        self.p, self.i = p, i
+
+    def sample_li(self, scene, sp, sampler):
+        sampler.get_2d()
+        wi = sub(self.p, sp.p)
+        li = unscale(self.i, norm2(wi))
+        to = ShapePoint(self.p, normalize(neg(wi)), [ZERO, ZERO, ZERO])
+        frm = sp.offset_by_error(sub(to.p, sp.p))
+        end = to.offset_by_error(sub(frm, to.p))
+        return normalize(wi), li, ONE, (frm, sub(end, frm), ONE - F(0.00001))
+
+
+class DistantLight:
+    is_delta = True
+
+    def __init__(self, w, i):
+        self.w, self.i = w, i
+
+    def sample_li(self, scene, sp, sampler):
+        sampler.get_2d()
+        d = neg(self.w)
+        return d, self.i, ONE, (sp.offset_by_error(d), d, F(np.finfo(np.float32).max))
+
+
 class Scene:
     def __init__(self, desc, abi, sah, trace):
         n = int(desc.n_primitives)
@@ -363,7 +455,7 @@ class Scene:
                 prims.append(trace.TrianglePrim(verts))
                 self.tris.append(Triangle(verts))
             else:
-                assert pr.shape.kind == abi.SHAPE_SPHERE and pr.shape.xform >= 0 and pr.light < 0
+                assert pr.shape.kind == abi.SHAPE_SPHERE and pr.shape.xform >= 0
                 t = desc.transforms[pr.shape.xform]
                 assert t.outer < 0
                 prims.append(trace.SpherePrim(desc.sphere_radius[pr.shape.data], list(t.m), list(t.m_inv)))
@@ -373,10 +465,16 @@ class Scene:
         self.lights = []
         for k in range(int(desc.n_lights)):
             lt = desc.lights[k]
-            assert lt.type == 0 and lt.shape.kind == abi.SHAPE_TRIANGLE and lt.shape.xform < 0
-            prim = [i for i in range(n) if self.light_of[i] == k]
-            assert len(prim) == 1
-            self.lights.append((self.tris[prim[0]], [F(x) for x in lt.L]))
+            if lt.type == 1:
+                self.lights.append(PointLight([F(x) for x in lt.v], [F(x) for x in lt.L]))
+            elif lt.type == 2:
+                self.lights.append(DistantLight([F(x) for x in lt.v], [F(x) for x in lt.L]))
+            else:
+                assert lt.type == 0, "infinite area lights are not restated"
+                prim = [i for i in range(n) if self.light_of[i] == k]
+                assert len(prim) == 1
+                shape = self.tris[prim[0]] if self.tris[prim[0]] is not None else SphereLightShape(prims[prim[0]], trace)
+                self.lights.append(AreaLight(shape, [F(x) for x in lt.L]))
         bounds = [q.bounds() for q in prims]
         lo = np.array([b[0] for b in bounds], np.float32)
         hi = np.array([b[1] for b in bounds], np.float32)
@@ -420,29 +518,30 @@ def uniform_sample_one_light(scene, sp, bsdf, wo, sampler):
     nl = len(scene.lights)
     if nl:
         chosen = sampler.get_usize(nl)
-        shape, le = scene.lights[chosen]
+        light = scene.lights[chosen]
         # sample the light
-        lp, li_pdf = shape.sample_by_point(sp.p, sampler)
-        if not (norm2(sub(lp.p, sp.p)) == 0 or li_pdf == 0):
-            wi = normalize(sub(lp.p, sp.p))
-            frm = sp.offset_by_error(sub(lp.p, sp.p))
-            to = lp.offset_by_error(sub(frm, lp.p))
+        sample = light.sample_li(scene, sp, sampler)
+        if sample is not None:
+            wi, li, li_pdf, shadow = sample
             if li_pdf != 0:
                 f, f_pdf = bsdf.no_delta_f_pdf(wo, wi)
                 if f is not None and f_pdf != 0:
-                    if not scene.occluded(frm, sub(to, frm), ONE - F(0.00001)):
-                        ld = unscale(scale(scale(mul(le, f), abs(dot(n, wi))), power_heuristic(li_pdf, f_pdf)), li_pdf)
-                        l = add(l, ld)
-        # sample the BSDF
-        wi, f, f_pdf = bsdf.sample_no_delta_f(wo, sampler.get_2d())
-        if f is not None and f_pdf != 0:
-            ld = [ZERO, ZERO, ZERO]
-            prim, hit = scene.intersect(sp.offset_by_error(wi), wi)
-            if prim is not None and scene.light_of[prim] == chosen:
-                li_pdf = shape.by_point_pdf(sp.p, hit)
-                if li_pdf != 0:
-                    ld = unscale(scale(scale(mul(le, f), abs(dot(n, wi))), power_heuristic(f_pdf, li_pdf)), f_pdf)
-            l = add(l, ld)
+                    if not scene.occluded(*shadow):
+                        ld = scale(mul(li, f), abs(dot(n, wi)))
+                        if not light.is_delta:
+                            ld = scale(ld, power_heuristic(li_pdf, f_pdf))
+                        l = add(l, unscale(ld, li_pdf))
+        if not light.is_delta:
+            # sample the BSDF
+            wi, f, f_pdf = bsdf.sample_no_delta_f(wo, sampler.get_2d())
+            if f is not None and f_pdf != 0:
+                ld = [ZERO, ZERO, ZERO]
+                prim, hit = scene.intersect(sp.offset_by_error(wi), wi)
+                if prim is not None and scene.light_of[prim] == chosen:
+                    li_pdf = light.shape.by_point_pdf(sp.p, hit)
+                    if li_pdf != 0:
+                        ld = unscale(scale(scale(mul(light.le, f), abs(dot(n, wi))), power_heuristic(f_pdf, li_pdf)), f_pdf)
+                l = add(l, ld)
     return scale(l, F(nl))
 
 
@@ -455,7 +554,7 @@ def path_li(scene, o, d, sampler):
         prim, sp = scene.intersect(o, d)
         if bounce == 0 or specular_bounce:
             if prim is not None and scene.light_of[prim] >= 0:
-                l = add(l, mul(beta, scene.lights[scene.light_of[prim]][1]))
+                l = add(l, mul(beta, scene.lights[scene.light_of[prim]].le))
         if prim is None or bounce >= scene.max_depth or scene.material[prim] is None:
             break
         bsdf = make_bsdf(scene.material[prim], sp.n)
@@ -485,7 +584,7 @@ def direct_li(scene, o, d, sampler, depth=0):
     if prim is None:
         return l
     if scene.material[prim] is None:
-        return add(l, scene.lights[scene.light_of[prim]][1])
+        return add(l, scene.lights[scene.light_of[prim]].le)
     bsdf = make_bsdf(scene.material[prim], sp.n)
     wo = neg(normalize(d))
     l = add(l, uniform_sample_one_light(scene, sp, bsdf, wo, sampler))

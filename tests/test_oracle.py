@@ -606,6 +606,24 @@ def test_directlighting_against_independent_numpy_restatement(cpbrt, oracle):
     assert np.array_equal(film.view(np.uint32), ref.view(np.uint32))
 
 
+def test_sphere_scene_against_independent_numpy_restatement(cpbrt, oracle):
+    """BASELINE config C2 (scenes/sphere.pbrt: matte spheres under Translate, a point light, a distant light, a
+    spherical emitter sampled by its cone, directlighting, a translated camera) through oracle/{front,sah,trace,path}_numpy.py
+    alone: bit-equal to the C++ oracle, equal ray counts."""
+    scene = cpbrt.Scene.parse(scene_text("sphere.pbrt", xres=48, yres=27, spp=3), base_dir=SCENES)
+    assert [int(scene.desc.lights[k].type) for k in range(int(scene.desc.n_lights))] == [1, 0, 2]
+    sah, trace, path = (_load_oracle_py(n) for n in ("sah_numpy", "trace_numpy", "path_numpy"))
+    w = oracle.OracleWorld(scene)
+    mine = path.Scene(scene.desc, cpbrt.abi, sah, trace)
+    assert np.array_equal(mine.search.tree.order, w.bvh_order())
+    halton_value, camera_ray_at = _independent_front(scene)
+    film = path.render(mine, 48, 27, 3, halton_value, camera_ray_at, integrator="directlighting")
+    ref, _, st = w.render()
+    assert (film > 0).any() and np.isfinite(film).all()
+    assert (mine.rays_closest, mine.rays_any) == (st["rays_closest"], st["rays_any"])
+    assert np.array_equal(film.view(np.uint32), ref.view(np.uint32))
+
+
 def test_render_is_deterministic_and_thread_count_independent(make_scene, oracle):
     scene = make_scene("cornel_box.pbrt", xres=40, yres=40, spp=2)
     w = oracle.OracleWorld(scene)
