@@ -22,6 +22,10 @@ ray counts.  What it takes from outside, as inputs:
   Triangle::sample / area / normal / interpolate  src/geometry/shape/triangle.rs:76-126,255-261
   ShapePoint::point_offset_by_error               src/geometry/shape/mod.rs:117-124
   MatteMaterial, LambertianReflection, BxDF       src/material/matte.rs, bxdf/lambertian.rs, bxdf/mod.rs:17-44
+  MirrorMaterial, GlassMaterial, specular lobes   src/material/{mirror,glass}.rs, bxdf/specular.rs, math/mod.rs:202-211 (refract)
+  ConstantTexture, ImageTexture::evaluate         src/texture/{constant,image}.rs (nearest texel, v flipped)
+  PointLight, DistantLight, DeltaLight adaptor    src/light/{point,distant}.rs, light/mod.rs:76-98
+  Sphere::{sample_by_point,by_point_pdf}          src/geometry/shape/sphere.rs:66-109 (cone sampling, outside the sphere)
   BSDF::{new, sample_f, sample_no_delta_f, no_delta_f_pdf, *_to_*}   src/material/bxdf/mod.rs:74-222
   Distribution1D::{from, sample_remap}            src/math/distribution.rs:16-56
   coordinate_system, cosine / concentric / triangle sampling, power_heuristic   src/math/mod.rs
@@ -160,8 +164,8 @@ class PixelSampler:
 
 # ---- geometry --------------------------------------------------------------------------------
 class ShapePoint:
-    def __init__(self, p, n, p_error):
-        self.p, self.n, self.p_error = p, n, p_error
+    def __init__(self, p, n, p_error, uv=None):
+        self.p, self.n, self.p_error, self.uv = p, n, p_error, uv      # uv None: never looked at (constant textures)
 
     def offset_by_error(self, w):
         d = dot(vabs(self.n), self.p_error)
@@ -172,8 +176,9 @@ class ShapePoint:
 
 
 class Triangle:
-    def __init__(self, p):
+    def __init__(self, p, uv=None):
         self.p = [[F(x) for x in v] for v in p]
+        self.uv = [[F(0), F(0)], [F(1), F(0)], [F(1), F(1)]] if uv is None else [[F(x) for x in v] for v in uv]
 
     def normal(self):
         p0, p1, p2 = self.p
@@ -192,7 +197,9 @@ class Triangle:
         return add(add(vabs(scale(p0, b0)), vabs(scale(p1, b1))), vabs(scale(p2, b2)))
 
     def hit_point(self, b):
-        return ShapePoint(self.interpolate(*b), self.normal(), scale(self.abs_sum(*b), gamma(7)))
+        uv0, uv1, uv2 = self.uv
+        uv = [(b[0] * uv0[c] + b[1] * uv1[c]) + b[2] * uv2[c] for c in range(2)]
+        return ShapePoint(self.interpolate(*b), self.normal(), scale(self.abs_sum(*b), gamma(7)), uv)
 
     def sample(self, sampler):
         u = sampler.get_2d()
@@ -340,13 +347,42 @@ class BSDF:
 MAT_MATTE, MAT_MIRROR, MAT_GLASS = 0, 1, 2
 
 
-def make_bsdf(material, n):
+def make_bsdf(material, sp):
     kind, a, b, eta = material
+    n = sp.n
     if kind == MAT_MATTE:
-        return BSDF(n, kd=a)
+        assert b(sp.uv)[0] == 0, "sigma = 0 (LambertianReflection) only"
+        return BSDF(n, kd=a(sp.uv))
     if kind == MAT_MIRROR:
-        return BSDF(n, deltas=[SpecularReflection(a)])
-    return BSDF(n, deltas=[SpecularReflection(a, eta), SpecularTransmission(b, ONE, eta)])
+        return BSDF(n, deltas=[SpecularReflection(a(sp.uv))])
+    index = eta(sp.uv)[0]
+    return BSDF(n, deltas=[SpecularReflection(a(sp.uv), index), SpecularTransmission(b(sp.uv), ONE, index)])
+
+
+def f32_to_usize(f):
+    """`f as usize`: truncates, saturates, NaN -> 0."""
+    if np.isnan(f) or f <= 0:
+        return 0
+    return min(int(f), (1 << 64) - 1)
+
+
+def texture(desc, index):
+    """Texture::evaluate as a callable of uv: constant (texture/constant.rs) or nearest image texel
+    (ImageTexture::evaluate, texture/image.rs:92-101; texels as the host decoded them)."""
+    t = desc.textures[index]
+    if t.kind == 0:
+        value = [F(x) for x in t.value]
+        return lambda uv: value
+    width, height, channels, offset = int(t.width), int(t.height), int(t.channels), int(t.offset)
+    texels = np.ctypeslib.as_array(desc.texels, shape=(int(desc.n_texels),))
+
+    def evaluate(uv):
+        u, v = uv[0], ONE - uv[1]
+        i = min(f32_to_usize(u * F(width)), width - 1)
+        j = min(f32_to_usize(v * F(height)), height - 1)
+        at = offset + (j * width + i) * channels
+        return [F(x) for x in texels[at:at + channels]]
+    return evaluate
 
 
 # ---- the scene -------------------------------------------------------------------------------
@@ -453,7 +489,7 @@ class Scene:
                 assert pr.shape.xform < 0
                 verts = [[desc.triangles[pr.shape.data].p[k][c] for c in range(3)] for k in range(3)]
                 prims.append(trace.TrianglePrim(verts))
-                self.tris.append(Triangle(verts))
+                self.tris.append(Triangle(verts, [[desc.triangles[pr.shape.data].uv[k][c] for c in range(2)] for k in range(3)]))
             else:
                 assert pr.shape.kind == abi.SHAPE_SPHERE and pr.shape.xform >= 0
                 t = desc.transforms[pr.shape.xform]
@@ -486,17 +522,12 @@ class Scene:
     @staticmethod
     def _material(desc, index):
         m = desc.materials[index]
-        def tex(slot):
-            t = desc.textures[m.tex[slot]]
-            assert t.kind == 0, "constant textures only"
-            return [F(x) for x in t.value]
         if m.type == MAT_MATTE:
-            assert tex(1)[0] == 0, "sigma = 0 (LambertianReflection) only"
-            return MAT_MATTE, tex(0), None, None
+            return MAT_MATTE, texture(desc, m.tex[0]), texture(desc, m.tex[1]), None
         if m.type == MAT_MIRROR:
-            return MAT_MIRROR, tex(0), None, None
+            return MAT_MIRROR, texture(desc, m.tex[0]), None, None
         assert m.type == MAT_GLASS
-        return MAT_GLASS, tex(0), tex(1), tex(2)[0]
+        return MAT_GLASS, texture(desc, m.tex[0]), texture(desc, m.tex[1]), texture(desc, m.tex[2])
 
     def intersect(self, o, d, t_max=np.finfo(np.float32).max):
         self.rays_closest += 1
@@ -557,7 +588,7 @@ def path_li(scene, o, d, sampler):
                 l = add(l, mul(beta, scene.lights[scene.light_of[prim]].le))
         if prim is None or bounce >= scene.max_depth or scene.material[prim] is None:
             break
-        bsdf = make_bsdf(scene.material[prim], sp.n)
+        bsdf = make_bsdf(scene.material[prim], sp)
         wo = neg(d)
         if not bsdf.is_all_delta():
             l = add(l, mul(beta, uniform_sample_one_light(scene, sp, bsdf, wo, sampler)))
@@ -585,7 +616,7 @@ def direct_li(scene, o, d, sampler, depth=0):
         return l
     if scene.material[prim] is None:
         return add(l, scene.lights[scene.light_of[prim]].le)
-    bsdf = make_bsdf(scene.material[prim], sp.n)
+    bsdf = make_bsdf(scene.material[prim], sp)
     wo = neg(normalize(d))
     l = add(l, uniform_sample_one_light(scene, sp, bsdf, wo, sampler))
     if depth + 1 < scene.max_depth:

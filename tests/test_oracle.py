@@ -624,6 +624,36 @@ def test_sphere_scene_against_independent_numpy_restatement(cpbrt, oracle):
     assert np.array_equal(film.view(np.uint32), ref.view(np.uint32))
 
 
+@pytest.mark.parametrize("config", ["C3", "C4"])
+def test_textured_and_mesh_scenes_against_independent_numpy_restatement(cpbrt, oracle, config):
+    """BASELINE configs C3 (the Cornell box with box-texture.png as Kd: nearest-texel look-up through the per-triangle
+    uv) and C4 in small (a height-field trianglemesh under the light quad: two-primitive leaves, massive key ties in
+    the build) through oracle/{front,sah,trace,path}_numpy.py alone: bit-equal to the C++ oracle, equal ray counts."""
+    from conftest import c3_text
+    if config == "C3":
+        text = c3_text()
+        for key, old, new in (("xresolution", 1920, 40), ("yresolution", 1080, 24), ("pixelsamples", 1024, 2)):
+            assert '"integer %s" [%d]' % (key, old) in text
+            text = text.replace('"integer %s" [%d]' % (key, old), '"integer %s" [%d]' % (key, new))
+        width, height, spp = 40, 24, 2
+    else:
+        text, (width, height, spp) = _synthetic_mesh_scene(14, 11, seed=8, res=20), (20, 20, 2)
+    scene = cpbrt.Scene.parse(text, base_dir=SCENES)
+    assert (int(scene.desc.film_width), int(scene.desc.film_height), int(scene.desc.sampler.spp)) == (width, height, spp)
+    if config == "C3":
+        assert any(int(scene.desc.textures[k].kind) == 1 for k in range(int(scene.desc.n_textures)))
+    sah, trace, path = (_load_oracle_py(n) for n in ("sah_numpy", "trace_numpy", "path_numpy"))
+    w = oracle.OracleWorld(scene)
+    mine = path.Scene(scene.desc, cpbrt.abi, sah, trace)
+    assert np.array_equal(mine.search.tree.order, w.bvh_order())
+    halton_value, camera_ray_at = _independent_front(scene)
+    film = path.render(mine, width, height, spp, halton_value, camera_ray_at)
+    ref, _, st = w.render()
+    assert (film > 0).any() and np.isfinite(film).all()
+    assert (mine.rays_closest, mine.rays_any) == (st["rays_closest"], st["rays_any"])
+    assert np.array_equal(film.view(np.uint32), ref.view(np.uint32))
+
+
 def test_render_is_deterministic_and_thread_count_independent(make_scene, oracle):
     scene = make_scene("cornel_box.pbrt", xres=40, yres=40, spp=2)
     w = oracle.OracleWorld(scene)
