@@ -11,7 +11,11 @@
 // radical inverse, float64 Moeller-Trumbore + analytic-sphere geometry over all primitives, the
 // closed form of the camera, and analytic radiometry (white furnace for matte / mirror / glass,
 // point, distant, small-area and spherical emitters) -- these pin its arithmetic and physics, not
-// the reference's quirks.
+// the reference's quirks.  The quirks are held by a second, independent reading of the Rust:
+// oracle/{front,sah,trace,path}_numpy.py (Python integers + scalar np.float32, nothing shared with
+// this file) against which this restatement is bit-equal in every pixel, BVH node, hit, t and
+// visit count on the four file-based BASELINE scenes (tests/test_oracle.py,
+// *_against_independent_numpy_restatement).  Two readings that agree are still not a reference run.
 //
 // Value types and small math.  Follows src/math/mod.rs, src/geometry/{point,vector,normal}.rs and
 // the nalgebra 0.20 arithmetic they sit on (dot = (x*x'+y*y')+z*z', normalize = v / sqrt(dot),
