@@ -55,7 +55,7 @@ def _libm_f32(name):
     return lambda x: F(fn(float(x)))
 
 
-_cosf, _sinf = _libm_f32("cosf"), _libm_f32("sinf")
+_cosf, _sinf, _logf = _libm_f32("cosf"), _libm_f32("sinf"), _libm_f32("logf")
 
 
 def gamma(n):
@@ -281,19 +281,260 @@ class SpecularTransmission:
         return wi, unscale(scale(self.t, ft), abs(wi[2]))
 
 
-class BSDF:
-    """BSDF::new(n, n) with `kd` (a LambertianReflection, or None) and a list of delta lobes."""
+# shading-frame trigonometry (math/mod.rs:152-201)
+def cos2_theta(w): return w[2] * w[2]
+def sin2_theta(w): return _max(ONE - cos2_theta(w), ZERO)
+def sin_theta(w): return np.sqrt(sin2_theta(w))
+def tan_theta(w): return sin_theta(w) / w[2]
+def tan2_theta(w): return sin2_theta(w) / cos2_theta(w)
 
-    def __init__(self, n, kd=None, deltas=()):
+
+def clamp(t, lo, hi):
+    return lo if t < lo else (hi if t > hi else t)
+
+
+def cos_phi(w):
+    st = sin_theta(w)
+    return ONE if st == 0 else clamp(w[0] / st, F(-1), ONE)
+
+
+def sin_phi(w):
+    st = sin_theta(w)
+    return ZERO if st == 0 else clamp(w[1] / st, F(-1), ONE)
+
+
+def cos_delta_phi(wa, wb):
+    return clamp((wa[0] * wb[0] + wa[1] * wb[1]) / np.sqrt((wa[0] * wa[0] + wa[1] * wa[1]) * (wb[0] * wb[0] + wb[1] * wb[1])), F(-1), ONE)
+
+
+def is_black(s):
+    return bool(s[0] == 0 and s[1] == 0 and s[2] == 0)
+
+
+class Lobe:
+    """BxDF defaults (bxdf/mod.rs:17-44): cosine sampling flipped by the lobe's side, pdf = wi.z / pi (signed)."""
+    transmit = False
+
+    def sample_f(self, wo, u):
+        wi, pdf = cosine_sample_hemisphere(u)
+        if (not self.transmit and wo[2] < 0) or (self.transmit and wo[2] > 0):
+            wi[2] = wi[2] * F(-1)
+        return wi, self.f(wo, wi), pdf
+
+    def pdf(self, wo, wi):
+        return wi[2] * INV_PI
+
+
+class Lambertian(Lobe):
+    def __init__(self, r, transmit=False):
+        self.r, self.transmit = r, transmit
+
+    def f(self, wo, wi):
+        return scale(self.r, INV_PI)
+
+
+class OrenNayar(Lobe):
+    def __init__(self, r, sigma):
+        sigma = sigma * (PI / F(180))                  # f32::to_radians
+        sigma2 = sigma * sigma
+        self.r = r
+        self.a = ONE - (sigma2 / (F(2) * (sigma + F(0.33))))
+        self.b = F(0.45) * sigma2 / (sigma2 + F(0.09))
+
+    def f(self, wo, wi):
+        if wi[2] < wo[2]:
+            sin_alpha, tan_beta = sin_theta(wi), tan_theta(wo)
+        else:
+            sin_alpha, tan_beta = sin_theta(wo), tan_theta(wi)
+        return scale(self.r, (self.a + self.b * _max(ZERO, cos_delta_phi(wi, wo)) * sin_alpha * tan_beta) / PI)
+
+
+class TrowbridgeReitz:
+    def __init__(self, ax, ay):
+        self.ax, self.ay = ax, ay
+
+    @staticmethod
+    def roughness_to_alpha(rough):
+        rough = _max(rough, F(1e-3))
+        x = _logf(rough)
+        x2 = x * x
+        return F(1.62142) + F(0.819955) * x + F(0.1734) * x2 + F(0.0171201) * x * x2 + F(0.000640711) * x2 * x2
+
+    def d(self, wh):
+        t2 = tan2_theta(wh)
+        if np.isnan(t2) or np.isinf(t2):
+            return ZERO
+        c2 = cos2_theta(wh)
+        c4 = c2 * c2
+        cp, sp_ = cos_phi(wh), sin_phi(wh)
+        e = ((cp * cp) / (self.ax * self.ax) + (sp_ * sp_) / (self.ay * self.ay)) * t2
+        return ONE / (PI * self.ax * self.ay * c4 * (ONE + e) * (ONE + e))
+
+    def lam(self, w):
+        att = abs(tan_theta(w))
+        if np.isnan(att) or np.isinf(att):
+            return ZERO
+        cp, sp_ = cos_phi(w), sin_phi(w)
+        alpha = np.sqrt((cp * cp) * self.ax * self.ax + (sp_ * sp_) * self.ay * self.ay)
+        at = alpha * att
+        return (F(-1) + np.sqrt(ONE + at * at)) / F(2)
+
+    def g(self, wo, wi):
+        return ONE / (ONE + self.lam(wo) + self.lam(wi))
+
+    def g1(self, w):
+        return ONE / (ONE + self.lam(w))
+
+    def sample_wh(self, wo, u):
+        flip = wo[2] < 0
+        wi = neg(wo) if flip else list(wo)
+        ws = [self.ax * wi[0], self.ay * wi[1], wi[2]]
+        cos_i = ws[2]
+        if cos_i > F(0.9999):
+            r = np.sqrt(u[0] / (ONE - u[0]))
+            phi = F(6.28318530718) * u[1]
+            sx, sy = r * _cosf(phi), r * _sinf(phi)
+        else:
+            sin_t = np.sqrt(_max(ZERO, ONE - cos_i * cos_i))
+            tan_t = sin_t / cos_i
+            a = ONE / tan_t
+            g1 = F(2) / (ONE + np.sqrt(ONE + ONE / (a * a)))
+            A = F(2) * u[0] / g1 - ONE
+            tmp = ONE / (A * A - ONE)
+            if tmp > F(1e10):
+                tmp = F(1e10)
+            B = tan_t
+            D = np.sqrt(_max(B * B * tmp * tmp - (A * A - B * B) * tmp, ZERO))
+            sx1, sx2 = B * tmp - D, B * tmp + D
+            sx = sx1 if (A < 0 or sx2 > ONE / tan_t) else sx2
+            if u[1] > HALF:
+                S, u2 = ONE, F(2) * (u[1] - HALF)
+            else:
+                S, u2 = F(-1), F(2) * (HALF - u[1])
+            z = (u2 * (u2 * (u2 * F(0.27385) - F(0.73369)) + F(0.46341))) / (u2 * (u2 * (u2 * F(0.093073) + F(0.309420)) - ONE) + F(0.597999))
+            sy = S * z * np.sqrt(ONE + sx * sx)
+        tmp = cos_phi(ws) * sx - sin_phi(ws) * sy
+        sy = sin_phi(ws) * sx + cos_phi(ws) * sy
+        sx = tmp
+        sx = sx * self.ax
+        sy = sy * self.ay
+        wh = normalize([-sx, -sy, ONE])
+        if flip:
+            wh = neg(wh)
+        return wh, self.d(wh) * self.g1(wo) * abs(dot(wo, wh)) / abs(wo[2])
+
+
+_NONE3 = [ZERO, ZERO, ZERO]
+
+
+class MicrofacetReflection(Lobe):
+    """pdf() is the trait default wi.z / pi: the reference does not override it (bxdf/microfacet.rs)."""
+
+    def __init__(self, r, dist, eta):
+        self.r, self.dist, self.eta = r, dist, eta            # FresnelDielectric(1, eta)
+
+    def f(self, wo, wi):
+        cos_o, cos_i = abs(wo[2]), abs(wi[2])
+        wi, wo = normalize(wi), normalize(wo)
+        wh = add(wi, wo)
+        if (wh[0] == 0 and wh[1] == 0 and wh[2] == 0) or cos_o == 0 or cos_i == 0:
+            return None
+        wh = normalize(wh)
+        fr = fresnel_dielectric(ONE, self.eta, dot(wi, neg(wh) if wh[2] < 0 else wh))
+        return unscale(scale(scale(scale(self.r, self.dist.d(wh)), self.dist.g(wo, wi)), fr), F(4) * cos_o * cos_i)
+
+    def sample_f(self, wo, u):
+        if wo[2] == 0:
+            return list(_NONE3), None, ZERO
+        wh, pdf = self.dist.sample_wh(wo, u)
+        if dot(wo, wh) < 0:
+            return list(_NONE3), None, ZERO
+        wi = add(neg(wo), scale(wh, F(2) * dot(wo, wh)))
+        if wi[2] * wo[2] < 0:
+            return list(_NONE3), None, ZERO
+        return wi, self.f(wo, wi), pdf / (F(4) * dot(wo, wh))
+
+
+class MicrofacetTransmission(Lobe):
+    transmit = True
+
+    def __init__(self, t, dist, eta_a, eta_b):
+        self.t, self.dist, self.eta_a, self.eta_b = t, dist, eta_a, eta_b
+
+    def f(self, wo, wi):
+        if wo[2] * wi[2] > 0:
+            return None
+        cos_o, cos_i = wo[2], wi[2]
+        if cos_i == 0 or cos_o == 0:
+            return None
+        eta = self.eta_b / self.eta_a if wo[2] > 0 else self.eta_a / self.eta_b
+        wh = normalize(add(wo, scale(wi, eta)))
+        if wh[2] < 0:
+            wh = neg(wh)
+        sd = dot(wo, wh) + eta * dot(wi, wh)
+        fr = fresnel_dielectric(self.eta_a, self.eta_b, dot(wo, wh))
+        factor = ONE / eta
+        k = abs(self.dist.d(wh) * self.dist.g(wo, wi) * eta * eta * abs(dot(wi, wh)) * abs(dot(wo, wh)) * factor * factor
+                / (cos_i * cos_o * sd * sd))
+        return scale(mul([ONE - fr, ONE - fr, ONE - fr], self.t), k)
+
+    def sample_f(self, wo, u):
+        if wo[2] == 0:
+            return list(_NONE3), None, ZERO
+        wh, pdf = self.dist.sample_wh(wo, u)
+        if dot(wo, wh) < 0:
+            return list(_NONE3), None, ZERO
+        if wo[2] > 0:
+            eta_i, eta_o = self.eta_a / self.eta_b, self.eta_b / self.eta_a
+        else:
+            eta_i, eta_o = self.eta_b / self.eta_a, self.eta_a / self.eta_b
+        wi = refract(wo, normalize(wh), eta_i)
+        if wi is None:
+            return list(_NONE3), None, ZERO
+        sd = dot(wo, wh) + eta_o * dot(wi, wh)
+        dwh_dwi = abs(eta_o * eta_o * dot(wi, wh)) / (sd * sd)
+        return wi, self.f(wo, wi), pdf * dwh_dwi
+
+
+class Scaled(Lobe):
+    """ScaledBxDF (bxdf/mod.rs:46-66)."""
+
+    def __init__(self, inner, s):
+        self.inner, self.s, self.transmit = inner, s, inner.transmit
+
+    def f(self, wo, wi):
+        f = self.inner.f(wo, wi)
+        return None if f is None else mul(f, self.s)
+
+    def sample_f(self, wo, u):
+        wi, f, pdf = self.inner.sample_f(wo, u)
+        return wi, (None if f is None else mul(f, self.s)), pdf
+
+    def pdf(self, wo, wi):
+        return self.inner.pdf(wo, wi)
+
+
+class ScaledDelta:
+    def __init__(self, inner, s):
+        self.inner, self.s = inner, s
+
+    def sample_f(self, wo):
+        r = self.inner.sample_f(wo)
+        return None if r is None else (r[0], mul(r[1], self.s))
+
+
+class BSDF:
+    """BSDF::new(n, n) (bxdf/mod.rs:74-96) with its lobes in insertion order."""
+
+    def __init__(self, n, lobes=(), deltas=()):
         self.sn = n
         self.snx, self.sny = coordinate_system(n)
         self.n = normalize([dot(n, self.snx), dot(n, self.sny), dot(n, self.sn)])
-        self.kd = kd
-        self.n_bxdfs = 0 if kd is None else 1
+        self.lobes = list(lobes)
         self.deltas = list(deltas)
 
     def is_all_delta(self):
-        return self.n_bxdfs == 0
+        return not self.lobes
 
     def local_to_world(self, w):
         x, y, z = self.snx, self.sny, self.sn
@@ -304,23 +545,17 @@ class BSDF:
     def world_to_local(self, w):
         return normalize([dot(w, self.snx), dot(w, self.sny), dot(w, self.sn)])
 
-    def f(self):
-        return scale(self.kd, INV_PI)
-
     def sample_no_delta_f(self, wo, u):
-        if self.n_bxdfs == 0:
-            return [ZERO, ZERO, ZERO], None, ZERO
-        index, remap = sample_usize_remap(u[0], 1)
-        wo_local = self.world_to_local(wo)
-        wi, pdf = cosine_sample_hemisphere([remap, u[1]])
-        if wo_local[2] < 0:
-            wi[2] = wi[2] * F(-1)
-        return self.local_to_world(wi), self.f(), pdf / F(1)
+        if not self.lobes:
+            return list(_NONE3), None, ZERO
+        index, remap = sample_usize_remap(u[0], len(self.lobes))
+        wi_local, f, pdf = self.lobes[index].sample_f(self.world_to_local(wo), [remap, u[1]])
+        return self.local_to_world(wi_local), f, pdf / F(len(self.lobes))
 
     def sample_delta_f(self, wo, u):
         wo_local = self.world_to_local(wo)
         if not self.deltas:
-            return [ZERO, ZERO, ZERO], None, ZERO
+            return list(_NONE3), None, ZERO
         wi_f = [r for r in (lobe.sample_f(wo_local) for lobe in self.deltas) if r is not None]
         assert wi_f, "the reference panics here (Distribution1D::from of an empty table)"
         i, pdf, _ = distribution_sample_remap([lum(f) for _, f in wi_f], u)
@@ -328,35 +563,104 @@ class BSDF:
         return self.local_to_world(wi_local), f, pdf
 
     def no_delta_f_pdf(self, wo, wi):
-        if self.n_bxdfs == 0:
+        if not self.lobes:
             return None, ZERO
         wo, wi = self.world_to_local(wo), self.world_to_local(wi)
-        if not (dot(wo, self.n) * dot(wi, self.n) > 0):
-            return None, ZERO / F(0)        # no transmissive lobe: pdf 0 / len 0 = NaN, f None
-        return add([ZERO, ZERO, ZERO], self.f()), (ZERO + wi[2] * INV_PI) / F(1)
+        reflect = dot(wo, self.n) * dot(wi, self.n) > 0
+        side = [lobe for lobe in self.lobes if lobe.transmit != reflect]
+        f, pdf = None, ZERO
+        for lobe in side:
+            this_f = lobe.f(wo, wi)
+            if this_f is not None:
+                f = add(f if f is not None else list(_NONE3), this_f)
+                pdf = pdf + lobe.pdf(wo, wi)
+        return f, pdf / F(len(side))
 
     def sample_f(self, wo, sampler):
-        i, pdf, remap = distribution_sample_remap([self.n_bxdfs, len(self.deltas)], sampler.get_1d())
+        i, pdf, remap = distribution_sample_remap([len(self.lobes), len(self.deltas)], sampler.get_1d())
         if i == 0:
             wi, f, internal = self.sample_no_delta_f(wo, [remap, sampler.get_1d()])
             return wi, f, pdf * internal, False
         wi, f, internal = self.sample_delta_f(wo, remap)
         return wi, f, pdf * internal, True
 
+    def mix(self, rhs, s1):
+        s2 = [ONE - s1[0], ONE - s1[1], ONE - s1[2]]
+        if is_black(s1):
+            return rhs
+        if is_black(s2):
+            return self
+        self.lobes = [Scaled(x, s1) for x in self.lobes] + [Scaled(x, s2) for x in rhs.lobes]
+        self.deltas = [ScaledDelta(x, s1) for x in self.deltas] + [ScaledDelta(x, s2) for x in rhs.deltas]
+        return self
 
-MAT_MATTE, MAT_MIRROR, MAT_GLASS = 0, 1, 2
+
+MAT_MATTE, MAT_MIRROR, MAT_GLASS, MAT_PLASTIC, MAT_UBER, MAT_TRANSLUCENT, MAT_MIX = range(7)
 
 
 def make_bsdf(material, sp):
-    kind, a, b, eta = material
-    n = sp.n
+    """Material::compute_scattering_functions (material/{matte,mirror,glass,plastic,uber,translucent,mix}.rs)."""
+    kind, tex, sub = material
+    n, uv = sp.n, sp.uv
+    if kind == MAT_MIX:
+        return make_bsdf(sub[0], sp).mix(make_bsdf(sub[1], sp), tex[0](uv))
+    bsdf = BSDF(n)
     if kind == MAT_MATTE:
-        assert b(sp.uv)[0] == 0, "sigma = 0 (LambertianReflection) only"
-        return BSDF(n, kd=a(sp.uv))
-    if kind == MAT_MIRROR:
-        return BSDF(n, deltas=[SpecularReflection(a(sp.uv))])
-    index = eta(sp.uv)[0]
-    return BSDF(n, deltas=[SpecularReflection(a(sp.uv), index), SpecularTransmission(b(sp.uv), ONE, index)])
+        kd, sigma = tex[0](uv), clamp(tex[1](uv)[0], ZERO, F(90))
+        bsdf.lobes.append(Lambertian(kd) if sigma == 0 else OrenNayar(kd, sigma))
+    elif kind == MAT_MIRROR:
+        bsdf.deltas.append(SpecularReflection(tex[0](uv)))
+    elif kind == MAT_GLASS:
+        index = tex[2](uv)[0]
+        bsdf.deltas += [SpecularReflection(tex[0](uv), index), SpecularTransmission(tex[1](uv), ONE, index)]
+    elif kind == MAT_PLASTIC:
+        kd, ks = tex[0](uv), tex[1](uv)
+        if not is_black(kd):
+            bsdf.lobes.append(Lambertian(kd))
+        if not is_black(ks):
+            rough = TrowbridgeReitz.roughness_to_alpha(tex[2](uv)[0])
+            bsdf.lobes.append(MicrofacetReflection(ks, TrowbridgeReitz(rough, rough), F(1.5)))
+    elif kind == MAT_UBER:
+        eta, opacity = tex[7](uv)[0], tex[8](uv)
+        t = [ONE - opacity[0], ONE - opacity[1], ONE - opacity[2]]
+        if not is_black(t):
+            bsdf.deltas.append(SpecularTransmission(t, ONE, ONE))
+        kd = mul(opacity, tex[0](uv))
+        if not is_black(kd):
+            bsdf.lobes.append(Lambertian(kd))
+        ks = mul(opacity, tex[1](uv))
+        if not is_black(ks):
+            ru = tex[5](uv)[0] if tex[5] is not None else tex[4](uv)[0]
+            rv = tex[6](uv)[0] if tex[6] is not None else ru
+            ru, rv = TrowbridgeReitz.roughness_to_alpha(ru), TrowbridgeReitz.roughness_to_alpha(rv)
+            bsdf.lobes.append(MicrofacetReflection(ks, TrowbridgeReitz(ru, rv), eta))
+        kr = mul(opacity, tex[2](uv))
+        if not is_black(kr):
+            bsdf.deltas.append(SpecularReflection(kr, eta))
+        kt = mul(opacity, tex[3](uv))
+        if not is_black(kt):
+            bsdf.deltas.append(SpecularTransmission(kt, ONE, eta))
+    else:
+        assert kind == MAT_TRANSLUCENT
+        eta = F(1.5)
+        r, t = tex[3](uv), tex[4](uv)
+        if is_black(r) and is_black(t):
+            return bsdf
+        kd = tex[0](uv)
+        if not is_black(kd):
+            if not is_black(r):
+                bsdf.lobes.append(Lambertian(mul(r, kd)))
+            if not is_black(t):
+                bsdf.lobes.append(Lambertian(mul(t, kd), transmit=True))
+        ks = tex[1](uv)
+        if not is_black(ks):
+            rough = TrowbridgeReitz.roughness_to_alpha(tex[2](uv)[0])
+            dist = TrowbridgeReitz(rough, rough)
+            if not is_black(r):
+                bsdf.lobes.append(MicrofacetReflection(mul(r, ks), dist, eta))
+            if not is_black(t):
+                bsdf.lobes.append(MicrofacetTransmission(mul(t, ks), dist, ONE, eta))
+    return bsdf
 
 
 def f32_to_usize(f):
@@ -522,12 +826,8 @@ class Scene:
     @staticmethod
     def _material(desc, index):
         m = desc.materials[index]
-        if m.type == MAT_MATTE:
-            return MAT_MATTE, texture(desc, m.tex[0]), texture(desc, m.tex[1]), None
-        if m.type == MAT_MIRROR:
-            return MAT_MIRROR, texture(desc, m.tex[0]), None, None
-        assert m.type == MAT_GLASS
-        return MAT_GLASS, texture(desc, m.tex[0]), texture(desc, m.tex[1]), texture(desc, m.tex[2])
+        sub = tuple(Scene._material(desc, m.sub[k]) for k in range(2)) if m.type == MAT_MIX else None
+        return int(m.type), [texture(desc, t) if t >= 0 else None for t in m.tex], sub
 
     def intersect(self, o, d, t_max=np.finfo(np.float32).max):
         self.rays_closest += 1

@@ -654,6 +654,25 @@ def test_textured_and_mesh_scenes_against_independent_numpy_restatement(cpbrt, o
     assert np.array_equal(film.view(np.uint32), ref.view(np.uint32))
 
 
+@pytest.mark.parametrize("name", ["mix", "mix_black_amount", "plastic", "plastic_rough", "translucent", "uber"])
+def test_general_materials_against_independent_numpy_restatement(cpbrt, oracle, name):
+    """f1, second pin: plastic / uber / translucent / mix, Trowbridge-Reitz sampling and evaluation, microfacet reflection
+    and transmission (with the trait-default pdf the reference leaves in place), Lambertian transmission, Oren-Nayar,
+    BSDF::mix with its scaled lobes -- oracle/path_numpy.py against the C++ oracle on the Cornell box with its white
+    surfaces replaced: bit-equal image, equal ray counts."""
+    from test_gpu_parity import GENERAL_MATERIALS, _cornell_with_white_material
+    scene = cpbrt.Scene.parse(_cornell_with_white_material(GENERAL_MATERIALS[name], xres=18, yres=18, spp=2), base_dir=SCENES)
+    sah, trace, path = (_load_oracle_py(n) for n in ("sah_numpy", "trace_numpy", "path_numpy"))
+    w = oracle.OracleWorld(scene)
+    mine = path.Scene(scene.desc, cpbrt.abi, sah, trace)
+    halton_value, camera_ray_at = _independent_front(scene)
+    film = path.render(mine, 18, 18, 2, halton_value, camera_ray_at)
+    ref, _, st = w.render()
+    assert (film > 0).any() and st["nan_dropped"] == 0
+    assert (mine.rays_closest, mine.rays_any) == (st["rays_closest"], st["rays_any"])
+    assert np.array_equal(film.view(np.uint32), ref.view(np.uint32))
+
+
 def test_render_is_deterministic_and_thread_count_independent(make_scene, oracle):
     scene = make_scene("cornel_box.pbrt", xres=40, yres=40, spp=2)
     w = oracle.OracleWorld(scene)
