@@ -149,17 +149,54 @@ def _apply_point(m, p):
     return [h[0] / h[3], h[1] / h[3], h[2] / h[3]]
 
 
-class PerspectiveCamera:
-    """raster_to_camera and camera_to_world as the host built them (4x4, row-major); no lens."""
+def _libm(name):
+    import ctypes
+    import ctypes.util
+    fn = getattr(ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6"), name)
+    fn.restype = ctypes.c_float
+    fn.argtypes = [ctypes.c_float]
+    return lambda x: F(fn(float(x)))
 
-    def __init__(self, raster_to_camera16, camera_to_world16=None):
+
+_cosf, _sinf = _libm("cosf"), _libm("sinf")
+_PI = F(3.14159265358979323846)
+
+
+def _concentric_sample_disk(u):
+    """src/math/mod.rs:98-110."""
+    ux, uy = F(2) * u[0] - F(1), F(2) * u[1] - F(1)
+    if ux == 0 or uy == 0:
+        return F(0), F(0)
+    if abs(ux) > abs(uy):
+        r, theta = ux, (_PI / F(4)) * (uy / ux)
+    else:
+        r, theta = uy, (_PI / F(2)) - (_PI / F(4)) * (ux / uy)
+    return r * _cosf(theta), r * _sinf(theta)
+
+
+class PerspectiveCamera:
+    """TransformCamera{LensCamera{PerspectiveCamera}}: raster_to_camera and camera_to_world as the host built them
+    (4x4, row-major); with a lens (camera/lens.rs:24-33) generate_ray draws two numbers from `sampler`."""
+
+    def __init__(self, raster_to_camera16, camera_to_world16=None, lens_radius=None, focal_distance=None):
         self.raster_to_camera = _rows(raster_to_camera16)
         self.camera_to_world = None if camera_to_world16 is None else _rows(camera_to_world16)
+        self.lens_radius = None if lens_radius is None else F(lens_radius)
+        self.focal_distance = None if focal_distance is None else F(focal_distance)
 
-    def generate_ray(self, fx, fy):
+    def generate_ray(self, fx, fy, sampler=None):
         c = _apply_point(self.raster_to_camera, [F(fx), F(fy), F(0)])
         length = np.sqrt((c[0] * c[0] + c[1] * c[1]) + c[2] * c[2])
         o, d = [F(0), F(0), F(0)], [c[0] / length, c[1] / length, c[2] / length]
+        if self.lens_radius is not None:
+            lx, ly = _concentric_sample_disk(sampler.get_2d())
+            lx, ly = self.lens_radius * lx, self.lens_radius * ly
+            ft = self.focal_distance / d[2]
+            focus = [o[k] + d[k] * ft for k in range(3)]
+            o = [lx, ly, F(0)]
+            v = [focus[k] - o[k] for k in range(3)]
+            length = np.sqrt((v[0] * v[0] + v[1] * v[1]) + v[2] * v[2])
+            d = [v[0] / length, v[1] / length, v[2] / length]
         if self.camera_to_world is not None:
             o = _apply_point(self.camera_to_world, o)
             d = _mat_vec(self.camera_to_world, [d[0], d[1], d[2], F(0)])[:3]

@@ -931,9 +931,9 @@ def direct_li(scene, o, d, sampler, depth=0):
     return l
 
 
-def render(scene, width, height, spp, halton_value, camera_ray_at, rect=None, integrator="path"):
+def render(scene, width, height, spp, halton_value, camera_ray_at, rect=None, integrator="path", camera_draws=False):
     """film[h, w, 3] over rect = (x0, y0, x1, y1); halton_value(x, y, sample) -> callable dim -> f32;
-    camera_ray_at(fx, fy) -> (o[3], d[3])."""
+    camera_ray_at(fx, fy) -> (o[3], d[3]); with camera_draws (a thin lens) it is called as (fx, fy, sampler)."""
     x0, y0, x1, y1 = rect or (0, 0, width, height)
     film = np.zeros((height, width, 3), np.float32)
     with np.errstate(all="ignore"):
@@ -946,7 +946,7 @@ def render(scene, width, height, spp, halton_value, camera_ray_at, rect=None, in
                     u = sampler.get_2d()
                     off = [u[0] - HALF, u[1] - HALF]
                     fx, fy = fx + off[0], fy + off[1]
-                    o, d = camera_ray_at(fx, fy)
+                    o, d = camera_ray_at(fx, fy, sampler) if camera_draws else camera_ray_at(fx, fy)
                     li = (path_li if integrator == "path" else direct_li)(scene, [F(v) for v in o], [F(v) for v in d], sampler)
                     if not has_nan(li):
                         kept.append(li)

@@ -486,8 +486,8 @@ def _independent_front(scene):
     front = _load_oracle_py("front_numpy")
     d = scene.desc
     perm = np.ctypeslib.as_array(d.sampler.permutation, shape=(cpbrt_perm_len(),))
-    cam = front.PerspectiveCamera(list(d.camera.raster_to_camera), list(d.camera.camera_to_world) if d.camera.has_camera_to_world else None)
-    assert not d.camera.has_lens
+    cam = front.PerspectiveCamera(list(d.camera.raster_to_camera), list(d.camera.camera_to_world) if d.camera.has_camera_to_world else None,
+                                  d.camera.lens_radius if d.camera.has_lens else None, d.camera.focal_distance if d.camera.has_lens else None)
 
     def halton_value(x, y, s):
         smp = front.HaltonSampler(int(d.sampler.spp), (int(d.film_width), int(d.film_height)), perm)
@@ -669,6 +669,23 @@ def test_general_materials_against_independent_numpy_restatement(cpbrt, oracle, 
     film = path.render(mine, 18, 18, 2, halton_value, camera_ray_at)
     ref, _, st = w.render()
     assert (film > 0).any() and st["nan_dropped"] == 0
+    assert (mine.rays_closest, mine.rays_any) == (st["rays_closest"], st["rays_any"])
+    assert np.array_equal(film.view(np.uint32), ref.view(np.uint32))
+
+
+def test_thin_lens_against_independent_numpy_restatement(cpbrt, oracle):
+    """f4, second pin: LensCamera::generate_ray (two numbers drawn after the film offset, lens point on the concentric
+    disk, refocused through the focal plane, then the camera transform) on the Cornell box: bit-equal image."""
+    text = scene_text("cornel_box.pbrt", xres=20, yres=20, spp=3)
+    assert '"float fov"' in text
+    scene = cpbrt.Scene.parse(text.replace('"float fov"', '"float lensradius" [12] "float focaldistance" [900] "float fov"', 1), base_dir=SCENES)
+    assert scene.desc.camera.has_lens
+    sah, trace, path = (_load_oracle_py(n) for n in ("sah_numpy", "trace_numpy", "path_numpy"))
+    w = oracle.OracleWorld(scene)
+    mine = path.Scene(scene.desc, cpbrt.abi, sah, trace)
+    halton_value, camera_ray_at = _independent_front(scene)
+    film = path.render(mine, 20, 20, 3, halton_value, camera_ray_at, camera_draws=True)
+    ref, _, st = w.render()
     assert (mine.rays_closest, mine.rays_any) == (st["rays_closest"], st["rays_any"])
     assert np.array_equal(film.view(np.uint32), ref.view(np.uint32))
 
