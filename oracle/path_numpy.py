@@ -25,6 +25,7 @@ ray counts.  What it takes from outside, as inputs:
   MirrorMaterial, GlassMaterial, specular lobes   src/material/{mirror,glass}.rs, bxdf/specular.rs, math/mod.rs:202-211 (refract)
   ConstantTexture, ImageTexture::evaluate         src/texture/{constant,image}.rs (nearest texel, v flipped)
   PointLight, DistantLight, DeltaLight adaptor    src/light/{point,distant}.rs, light/mod.rs:76-98
+  InfiniteAreaLight, Distribution2D               src/light/infinite_area.rs, math/distribution.rs:69-139, math/mod.rs:136-152
   Sphere::{sample_by_point,by_point_pdf}          src/geometry/shape/sphere.rs:66-109 (cone sampling, outside the sphere)
   BSDF::{new, sample_f, sample_no_delta_f, no_delta_f_pdf, *_to_*}   src/material/bxdf/mod.rs:74-222
   Distribution1D::{from, sample_remap}            src/math/distribution.rs:16-56
@@ -55,7 +56,16 @@ def _libm_f32(name):
     return lambda x: F(fn(float(x)))
 
 
-_cosf, _sinf, _logf = _libm_f32("cosf"), _libm_f32("sinf"), _libm_f32("logf")
+_cosf, _sinf, _logf, _acosf = _libm_f32("cosf"), _libm_f32("sinf"), _libm_f32("logf"), _libm_f32("acosf")
+
+
+def _atan2f(y, x):
+    import ctypes
+    import ctypes.util
+    fn = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6").atan2f
+    fn.restype = ctypes.c_float
+    fn.argtypes = [ctypes.c_float, ctypes.c_float]
+    return F(fn(float(y), float(x)))
 
 
 def gamma(n):
@@ -782,6 +792,96 @@ class DistantLight:
         return d, self.i, ONE, (sp.offset_by_error(d), d, F(np.finfo(np.float32).max))
 
 
+class Distribution1D:
+    """math/distribution.rs:16-67; the running sum is sequential f32 (np.cumsum accumulates in order)."""
+
+    def __init__(self, f):
+        f = np.asarray(f, np.float32)
+        self.n = F(len(f))
+        cdf = np.cumsum(f / self.n, dtype=np.float32)
+        self.f_sum = cdf[-1]
+        self.cdf = cdf / self.f_sum
+        self.pdf = f / (self.n * self.f_sum)
+
+    def sample_remap(self, u):
+        i = int(np.searchsorted(self.cdf, u, side="left"))       # first i with u <= cdf[i]
+        if i >= len(self.cdf) or not (u <= self.cdf[i]):
+            return len(self.pdf) - 1, self.pdf[-1], ONE
+        return i, self.pdf[i], (self.cdf[i] - u) / self.pdf[i]
+
+    def sample_continuous(self, u):
+        i, pdf, remap = self.sample_remap(u)
+        return i, pdf * self.n, (F(i) + remap) / self.n
+
+
+def _spherical_to_uv(w):
+    """spherical_to_normalize_phi_theta (math/mod.rs:136-142), then the caller's v flip."""
+    p = _atan2f(w[1], w[0])
+    u = (p + F(2) * PI if p < 0 else p) / F(2) * INV_PI
+    v = _acosf(clamp(w[2], F(-1), ONE)) * INV_PI
+    return [u, ONE - v]
+
+
+class InfiniteLight:
+    """InfiniteAreaLight (light/infinite_area.rs): the table weights a texel by sin((row + 0.5) / rows) -- no pi --
+    and Distribution2D's first coordinate runs over the rows."""
+    is_delta = False
+    le = None
+
+    def __init__(self, desc, tex_index):
+        t = desc.textures[tex_index]
+        self.evaluate = texture(desc, tex_index)
+        if t.kind == 0:
+            width = height = 1
+            pixels = np.array([[list(t.value)]], np.float32)
+        else:
+            width, height = int(t.width), int(t.height)
+            assert int(t.channels) == 3
+            texels = np.ctypeslib.as_array(desc.texels, shape=(int(desc.n_texels),))
+            pixels = texels[int(t.offset):int(t.offset) + width * height * 3].reshape(height, width, 3).astype(np.float32)
+        y = (F(0.212671) * pixels[..., 0] + F(0.715160) * pixels[..., 1]).astype(np.float32) + F(0.072169) * pixels[..., 2]
+        rows = []
+        for j in range(height):
+            theta = (F(j) + HALF) / F(height)
+            rows.append(Distribution1D((y[j] * _sinf(theta)).astype(np.float32)))
+        self.rows = rows
+        self.row_dist = Distribution1D([r.f_sum for r in rows])
+        self.n = (self.row_dist.n, rows[0].n)
+
+    def _solid_angle_pdf(self, pdf, uv):
+        sin_t = _sinf(uv[1] * PI)
+        return pdf / (F(2) * PI * PI * sin_t) if sin_t != 0 else ZERO
+
+    def sample_li(self, scene, sp, sampler):
+        u = sampler.get_2d()
+        row, row_pdf, x = self.row_dist.sample_continuous(u[0])
+        _, col_pdf, y = self.rows[row].sample_continuous(u[1])
+        pdf = row_pdf * col_pdf
+        uv = [x, ONE - y]
+        theta, phi = uv[1] * PI, uv[0] * PI * F(2)
+        wi = [_sinf(theta) * _cosf(phi), _sinf(theta) * _sinf(phi), _cosf(theta)]
+        return wi, self.evaluate(uv), self._solid_angle_pdf(pdf, uv), (sp.offset_by_error(wi), wi, F(np.finfo(np.float32).max))
+
+    def le_out_scene(self, d):
+        return self.evaluate(_spherical_to_uv(normalize(d)))
+
+    def out_scene_pdf(self, d):
+        uv = _spherical_to_uv(normalize(d))
+        n = self.n
+        i = f32_to_usize(_min(uv[0] * n[0], n[0] - ONE))
+        j = f32_to_usize(_min(uv[1] * n[1], n[1] - ONE))
+        pdf = self.row_dist.pdf[i] * self.rows[i].pdf[j] * n[0] * n[1]
+        return self._solid_angle_pdf(pdf, uv)
+
+
+def add_out_scene(scene, l, beta, d):
+    """`for light in lights { l += beta * light.le_out_scene(&ray) }`: None counts as black, and is still added."""
+    for light in scene.lights:
+        le = light.le_out_scene(d) if isinstance(light, InfiniteLight) else [ZERO, ZERO, ZERO]
+        l = add(l, mul(beta, le))
+    return l
+
+
 class Scene:
     def __init__(self, desc, abi, sah, trace):
         n = int(desc.n_primitives)
@@ -809,8 +909,10 @@ class Scene:
                 self.lights.append(PointLight([F(x) for x in lt.v], [F(x) for x in lt.L]))
             elif lt.type == 2:
                 self.lights.append(DistantLight([F(x) for x in lt.v], [F(x) for x in lt.L]))
+            elif lt.type == 3:
+                self.lights.append(InfiniteLight(desc, int(lt.tex)))
             else:
-                assert lt.type == 0, "infinite area lights are not restated"
+                assert lt.type == 0
                 prim = [i for i in range(n) if self.light_of[i] == k]
                 assert len(prim) == 1
                 shape = self.tris[prim[0]] if self.tris[prim[0]] is not None else SphereLightShape(prims[prim[0]], trace)
@@ -868,10 +970,15 @@ def uniform_sample_one_light(scene, sp, bsdf, wo, sampler):
             if f is not None and f_pdf != 0:
                 ld = [ZERO, ZERO, ZERO]
                 prim, hit = scene.intersect(sp.offset_by_error(wi), wi)
-                if prim is not None and scene.light_of[prim] == chosen:
-                    li_pdf = light.shape.by_point_pdf(sp.p, hit)
-                    if li_pdf != 0:
-                        ld = unscale(scale(scale(mul(light.le, f), abs(dot(n, wi))), power_heuristic(f_pdf, li_pdf)), f_pdf)
+                if prim is not None:
+                    if scene.light_of[prim] == chosen:
+                        li_pdf = light.shape.by_point_pdf(sp.p, hit)
+                        if li_pdf != 0:
+                            ld = unscale(scale(scale(mul(light.le, f), abs(dot(n, wi))), power_heuristic(f_pdf, li_pdf)), f_pdf)
+                elif isinstance(light, InfiniteLight):
+                    le_pdf = light.out_scene_pdf(wi)
+                    if le_pdf != 0:
+                        ld = unscale(scale(scale(mul(light.le_out_scene(wi), f), abs(dot(n, wi))), power_heuristic(f_pdf, le_pdf)), f_pdf)
                 l = add(l, ld)
     return scale(l, F(nl))
 
@@ -884,7 +991,9 @@ def path_li(scene, o, d, sampler):
     while True:
         prim, sp = scene.intersect(o, d)
         if bounce == 0 or specular_bounce:
-            if prim is not None and scene.light_of[prim] >= 0:
+            if prim is None:
+                l = add_out_scene(scene, l, beta, d)
+            elif scene.light_of[prim] >= 0:
                 l = add(l, mul(beta, scene.lights[scene.light_of[prim]].le))
         if prim is None or bounce >= scene.max_depth or scene.material[prim] is None:
             break
@@ -913,7 +1022,7 @@ def direct_li(scene, o, d, sampler, depth=0):
     l = [ZERO, ZERO, ZERO]
     prim, sp = scene.intersect(o, d)
     if prim is None:
-        return l
+        return add_out_scene(scene, l, [ONE, ONE, ONE], d)
     if scene.material[prim] is None:
         return add(l, scene.lights[scene.light_of[prim]].le)
     bsdf = make_bsdf(scene.material[prim], sp)

@@ -690,6 +690,41 @@ def test_thin_lens_against_independent_numpy_restatement(cpbrt, oracle):
     assert np.array_equal(film.view(np.uint32), ref.view(np.uint32))
 
 
+INFINITE_CASES = ["cornell constant path", "cornell envmap path", "cornell envmap directlighting", "furnace matte path",
+                  "furnace matte directlighting", "furnace glass"]
+
+
+@pytest.mark.parametrize("case", INFINITE_CASES)
+def test_infinite_area_light_against_independent_numpy_restatement(cpbrt, oracle, case):
+    """f1, second pin: InfiniteAreaLight of oracle/path_numpy.py -- the sin((row + 0.5) / rows) table weights, Distribution2D
+    with its first coordinate over the rows, the lat-long mapping (atan2f / acosf), le_out_scene for escaped camera and
+    specular rays, the escaped-ray MIS branch -- in the Cornell box next to the area light (constant and box-texture.png
+    environments) and in the open furnace scenes where every camera ray can escape: bit-equal image, equal ray counts."""
+    import re
+    width = height = 16
+    spp = 2
+    if case.startswith("cornell"):
+        light = 'LightSource "infinite"' + (' "string mapname" "box-texture.png"' if "envmap" in case else "")
+        text = scene_text("cornel_box.pbrt", xres=width, yres=height, spp=spp).replace("WorldBegin\n", "WorldBegin\n" + light + "\n", 1)
+        if "directlighting" in case:
+            text = re.sub(r'Integrator "path"[^\n]*\n(\s*"integer maxdepth"[^\n]*\n)?', 'Integrator "directlighting" "integer maxdepth" [1]\n', text)
+    elif case == "furnace glass":
+        text = specular_furnace_scene_text("glass", spp=spp, res=width)
+    else:
+        text = furnace_scene_text(case.split()[-1], 0.75, spp=spp, res=width)
+    scene = cpbrt.Scene.parse(text, base_dir=SCENES)
+    assert any(int(scene.desc.lights[k].type) == 3 for k in range(int(scene.desc.n_lights)))
+    sah, trace, path = (_load_oracle_py(n) for n in ("sah_numpy", "trace_numpy", "path_numpy"))
+    w = oracle.OracleWorld(scene)
+    mine = path.Scene(scene.desc, cpbrt.abi, sah, trace)
+    halton_value, camera_ray_at = _independent_front(scene)
+    film = path.render(mine, width, height, spp, halton_value, camera_ray_at, integrator="directlighting" if "directlighting" in case else "path")
+    ref, _, st = w.render()
+    assert (film > 0).any() and np.isfinite(film).all()
+    assert (mine.rays_closest, mine.rays_any) == (st["rays_closest"], st["rays_any"])
+    assert np.array_equal(film.view(np.uint32), ref.view(np.uint32))
+
+
 def test_render_is_deterministic_and_thread_count_independent(make_scene, oracle):
     scene = make_scene("cornel_box.pbrt", xres=40, yres=40, spp=2)
     w = oracle.OracleWorld(scene)
