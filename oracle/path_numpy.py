@@ -889,17 +889,30 @@ class Scene:
         prims = []
         for i in range(n):
             pr = desc.primitives[i]
+            chain = []                       # TransformShape wrappers, innermost first (cpbrt_transform.outer)
+            x = int(pr.shape.xform)
+            while x >= 0:
+                chain.append(desc.transforms[x])
+                x = int(desc.transforms[x].outer)
             if pr.shape.kind == abi.SHAPE_TRIANGLE:
-                assert pr.shape.xform < 0
                 verts = [[desc.triangles[pr.shape.data].p[k][c] for c in range(3)] for k in range(3)]
-                prims.append(trace.TrianglePrim(verts))
-                self.tris.append(Triangle(verts, [[desc.triangles[pr.shape.data].uv[k][c] for c in range(2)] for k in range(3)]))
+                tri = Triangle(verts, [[desc.triangles[pr.shape.data].uv[k][c] for c in range(2)] for k in range(3)])
+                obj = trace.TrianglePrim(verts)
+
+                def to_sp(b, tri=tri):
+                    sp = tri.hit_point(b)
+                    return sp.p, sp.n, sp.p_error, sp.uv
+                for k, t in enumerate(chain):
+                    obj = trace.TransformedPrim(obj, list(t.m), list(t.m_inv), to_sp if k == 0 else None)
+                self.tris.append(tri if not chain else None)
             else:
-                assert pr.shape.kind == abi.SHAPE_SPHERE and pr.shape.xform >= 0
-                t = desc.transforms[pr.shape.xform]
-                assert t.outer < 0
-                prims.append(trace.SpherePrim(desc.sphere_radius[pr.shape.data], list(t.m), list(t.m_inv)))
+                assert pr.shape.kind == abi.SHAPE_SPHERE and chain
+                obj = trace.SpherePrim(desc.sphere_radius[pr.shape.data], list(chain[0].m), list(chain[0].m_inv))
+                for t in chain[1:]:
+                    obj = trace.TransformedPrim(obj, list(t.m), list(t.m_inv))
                 self.tris.append(None)
+            assert pr.light < 0 or len(chain) <= 1, "emitters under nested transforms are not restated"
+            prims.append(obj)
             self.light_of.append(int(pr.light))
             self.material.append(self._material(desc, pr.material) if pr.material >= 0 else None)
         self.lights = []

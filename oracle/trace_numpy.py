@@ -197,22 +197,32 @@ class TrianglePrim:
         return None if t is None else (t, b)
 
 
-class SpherePrim:
-    """TransformShape{Sphere{radius}, transform} -- one wrapper, as `Shape "sphere"` under a CTM yields."""
+def _libm(name, nargs=1):
+    import ctypes
+    import ctypes.util
+    fn = getattr(ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6"), name)
+    fn.restype = ctypes.c_float
+    fn.argtypes = [ctypes.c_float] * nargs
+    return lambda *x: F(fn(*[float(v) for v in x]))
 
-    def __init__(self, radius, m16, m_inv16):
+
+_atan2f, _acosf = _libm("atan2f", 2), _libm("acosf")
+_PI, _INV_PI = F(3.14159265358979323846), F(0.31830988618379067154)
+
+
+class BareSpherePrim:
+    """Sphere{radius} in its own space (sphere.rs:14-53); intersect returns (t, (p, n, p_error, uv))."""
+
+    def __init__(self, radius):
         self.radius = F(radius)
-        self.m, self.m_inv = mat_rows(m16), mat_rows(m_inv16)
-        self.m3 = normal_matrix(self.m_inv)
 
     def bounds(self):
         r = self.radius
         lo, hi = [-r, -r, -r], [r, r, r]
-        return transformed_bounds([_min(lo[c], hi[c]) for c in range(3)], [_max(lo[c], hi[c]) for c in range(3)], self.m)
+        return [_min(lo[c], hi[c]) for c in range(3)], [_max(lo[c], hi[c]) for c in range(3)]
 
     def intersect(self, ray):
-        """(t, (p, n, p_error)) in world space, or None."""
-        o, d = apply_point(self.m_inv, ray.o), apply_vector(self.m_inv, ray.d)
+        o, d = ray.o, ray.d
         a = (d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]
         b = F(2) * ((d[0] * o[0] + d[1] * o[1]) + d[2] * o[2])
         c = ((o[0] * o[0] + o[1] * o[1]) + o[2] * o[2]) - self.radius * self.radius
@@ -239,13 +249,46 @@ class SpherePrim:
             length = np.sqrt((v[0] * v[0] + v[1] * v[1]) + v[2] * v[2])
             return [x / length for x in v]
         n = normalize(normalize(p))
-        # ShapeIntersect::apply(transform): the object-space p_error (gamma(5)|p|) is dropped
+        g5 = gamma(5)
+        uv = [(_atan2f(p[1], p[0]) + _PI) * F(0.5) * _INV_PI, _acosf(min(max(p[2] / self.radius, F(-1)), F(1))) * _INV_PI]
+        return t, (p, n, [g5 * abs(x) for x in p], uv)
+
+
+class TransformedPrim:
+    """TransformShape{shape, transform} (shape/transform.rs:52-59).  `to_shape_point` turns the inner primitive's hit
+    detail into (p, n, p_error, uv) in the inner space (identity for spheres and nested wrappers)."""
+
+    def __init__(self, inner, m16, m_inv16, to_shape_point=None):
+        self.inner = inner
+        self.m, self.m_inv = mat_rows(m16), mat_rows(m_inv16)
+        self.m3 = normal_matrix(self.m_inv)
+        self.to_shape_point = to_shape_point or (lambda detail: detail)
+
+    def bounds(self):
+        lo, hi = self.inner.bounds()
+        return transformed_bounds(lo, hi, self.m)
+
+    def intersect(self, ray):
+        """(t, (p, n, p_error, uv)) in the outer space, or None."""
+        hit = self.inner.intersect(_Ray(apply_point(self.m_inv, ray.o), apply_vector(self.m_inv, ray.d), ray.t_max))
+        if hit is None:
+            return None
+        p, n, _dropped, uv = self.to_shape_point(hit[1])
+        # ShapeIntersect::apply(transform): the inner p_error is dropped
         pw = apply_point(self.m, p)
         nw = [(self.m3[i][0] * n[0] + self.m3[i][1] * n[1]) + self.m3[i][2] * n[2] for i in range(3)]
         m = self.m
         g3 = gamma(3)
         err = [g3 * (((abs(m[i][0] * pw[0]) + abs(m[i][1] * pw[1])) + abs(m[i][2] * pw[2])) + m[i][3]) for i in range(3)]
-        return t, (pw, nw, err)
+        return hit[0], (pw, nw, err, uv)
+
+
+class SpherePrim(TransformedPrim):
+    """TransformShape{Sphere{radius}, transform} -- one wrapper, as `Shape "sphere"` under a CTM yields."""
+
+    def __init__(self, radius, m16, m_inv16):
+        TransformedPrim.__init__(self, BareSpherePrim(radius), m16, m_inv16)
+        self.radius = F(radius)
 
 
 class Searcher:

@@ -725,6 +725,51 @@ def test_infinite_area_light_against_independent_numpy_restatement(cpbrt, oracle
     assert np.array_equal(film.view(np.uint32), ref.view(np.uint32))
 
 
+def test_instances_under_transforms_against_independent_numpy_restatement(cpbrt, oracle):
+    """ObjectInstance under Translate / Rotate / Scale (src/scene.rs:119-140, src/primitive.rs:115-130): triangles and
+    spheres behind one and two nested TransformShapes -- rays through both inverses, hits back through both
+    ShapePoint::apply steps, bounds as unions of transformed corners -- plus an image texture on a mesh with its own uv
+    and on a sphere (Sphere::calc_uv: atan2f / acosf): bit-equal image, equal BVH order and ray counts."""
+    width = height = 22
+    spp = 2
+    text = ('LookAt 0 1.5 -6 0 0.5 0 0 1 0\nCamera "perspective" "float fov" [45]\nSampler "halton" "integer pixelsamples" [%d]\n'
+            'Film "image" "integer xresolution" [%d] "integer yresolution" [%d]\nIntegrator "path" "integer maxdepth" [4]\nWorldBegin\n'
+            'Texture "boxtex" "spectrum" "imagemap" "string filename" "box-texture.png"\n'
+            'LightSource "infinite"\n'
+            'AttributeBegin\nTranslate 0 4 0\nLightSource "point" "rgb I" [30 30 30]\nAttributeEnd\n'
+            'Material "matte" "rgb Kd" [0.6 0.6 0.6]\n'
+            'Shape "trianglemesh" "integer indices" [0 1 2 2 3 0] "point P" [-5 0 -5 5 0 -5 5 0 5 -5 0 5]\n'
+            'ObjectBegin "thing"\n'
+            'Material "matte" "texture Kd" "boxtex"\n'
+            'Shape "trianglemesh" "integer indices" [0 1 2 2 3 0] "point P" [-1 0 0 1 0 0 1 1.5 0.3 -1 1.5 0.3] "float uv" [0 0 1 0 1 1 0 1]\n'
+            'Translate 0 0.8 -1\n'
+            'Shape "sphere" "float radius" [0.5]\n'
+            'Material "glass"\nTranslate 1.2 0 0\nShape "sphere" "float radius" [0.4]\n'
+            'ObjectEnd\n'
+            'AttributeBegin\nTranslate -1.5 0 1\nRotate 35 0 1 0\nScale 1.2 0.8 1\nObjectInstance "thing"\nAttributeEnd\n'
+            'AttributeBegin\nTranslate 1.8 0.2 0\nRotate -20 0 0 1\nObjectInstance "thing"\nAttributeEnd\n'
+            'WorldEnd\n' % (spp, width, height))
+    scene = cpbrt.Scene.parse(text, base_dir=SCENES)
+    d = scene.desc
+    depth = []
+    for i in range(int(d.n_primitives)):
+        x, k = int(d.primitives[i].shape.xform), 0
+        while x >= 0:
+            x, k = int(d.transforms[x].outer), k + 1
+        depth.append((int(d.primitives[i].shape.kind), k))
+    assert (0, 1) in depth and (1, 2) in depth          # a triangle behind one wrapper, a sphere behind two
+    sah, trace, path = (_load_oracle_py(n) for n in ("sah_numpy", "trace_numpy", "path_numpy"))
+    w = oracle.OracleWorld(scene)
+    mine = path.Scene(d, cpbrt.abi, sah, trace)
+    assert np.array_equal(mine.search.tree.order, w.bvh_order())
+    halton_value, camera_ray_at = _independent_front(scene)
+    film = path.render(mine, width, height, spp, halton_value, camera_ray_at)
+    ref, _, st = w.render()
+    assert (film > 0).any() and np.isfinite(film).all()
+    assert (mine.rays_closest, mine.rays_any) == (st["rays_closest"], st["rays_any"])
+    assert np.array_equal(film.view(np.uint32), ref.view(np.uint32))
+
+
 def test_render_is_deterministic_and_thread_count_independent(make_scene, oracle):
     scene = make_scene("cornel_box.pbrt", xres=40, yres=40, spp=2)
     w = oracle.OracleWorld(scene)
