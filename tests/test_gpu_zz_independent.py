@@ -1,0 +1,185 @@
+"""The CUDA path (through the C-ABI) against the SECOND reading of the reference -- oracle/{front,sah,trace,path}_numpy.py,
+Python integers and scalar np.float32 written from the Rust alone -- with the C++ oracle out of the loop: the device is
+held to both readings separately, not to one of them through the other.  Small sizes: the numpy side runs a few
+hundred rays per second.  (Named to run last: every other GPU test goes first under `-x`.)"""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+from conftest import SCENES, lcg_rays, scene_text
+from test_oracle import _synthetic_mesh_scene
+
+pytestmark = pytest.mark.gpu
+
+PERM_LEN = 3682913
+NO_HIT = 0xFFFFFFFF
+
+
+def _load(name):
+    spec = importlib.util.spec_from_file_location(name, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle", name + ".py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+class _Second:
+    """One scene seen by the device and by the numpy restatement."""
+
+    def __init__(self, cpbrt, text):
+        self.cpbrt = cpbrt
+        self.front, self.sah, self.trace, self.path = (_load(n) for n in ("front_numpy", "sah_numpy", "trace_numpy", "path_numpy"))
+        self.scene = cpbrt.Scene.parse(text, base_dir=SCENES)
+        d = self.scene.desc
+        self.width, self.height, self.spp = int(d.film_width), int(d.film_height), int(d.sampler.spp)
+        self.renderer = cpbrt.Renderer(0)
+        self.renderer.upload(self.scene)
+        self.order = self.renderer.build_bvh()
+        self.numpy_scene = self.path.Scene(d, cpbrt.abi, self.sah, self.trace)
+        self.perm = np.ctypeslib.as_array(d.sampler.permutation, shape=(PERM_LEN,))
+        self.camera = self.front.PerspectiveCamera(list(d.camera.raster_to_camera), list(d.camera.camera_to_world) if d.camera.has_camera_to_world else None,
+                                                   d.camera.lens_radius if d.camera.has_lens else None, d.camera.focal_distance if d.camera.has_lens else None)
+        self.integrator = "path" if int(d.integrator) == 0 else "directlighting"
+
+    def sampler(self):
+        return self.front.HaltonSampler(self.spp, (self.width, self.height), self.perm)
+
+    def halton_value(self, x, y, s):
+        smp = self.sampler()
+        smp.set_pixel(x, y)
+        for _ in range(s):
+            smp.next_sample()
+
+        def value(dim):
+            smp.dim = dim
+            return smp.get_sample()
+        return value
+
+
+@pytest.fixture(scope="module")
+def cornell2(cpbrt):
+    return _Second(cpbrt, scene_text("cornel_box.pbrt", xres=24, yres=24, spp=2))
+
+
+@pytest.fixture(scope="module")
+def mesh2(cpbrt):
+    return _Second(cpbrt, _synthetic_mesh_scene(24, 17, seed=5, res=16))
+
+
+def test_bvh_order_equals_the_second_reading(cornell2, mesh2):
+    for s in (cornell2, mesh2):
+        assert np.array_equal(s.order, s.numpy_scene.search.tree.order)
+
+
+def test_halton_equals_the_second_reading(cornell2):
+    s = cornell2
+    rng = np.random.RandomState(3)
+    n = 400
+    px = rng.randint(0, s.width, n).astype(np.uint32); py = rng.randint(0, s.height, n).astype(np.uint32)
+    sample = rng.randint(0, 1 << 20, n).astype(np.uint32); sample[:50] = rng.randint(0, 4, 50)
+    dim = rng.randint(0, 1000, n).astype(np.uint32); dim[:8] = np.arange(8)
+    gi, gv = s.renderer.halton(px, py, sample, dim)
+    smp = s.sampler()
+    scale = smp.scale[0] * smp.scale[1]
+    for k in range(n):
+        smp.set_pixel(int(px[k]), int(py[k]))
+        smp.index += int(sample[k]) * scale
+        smp.dim = int(dim[k])
+        assert int(gi[k]) == smp.index
+        assert np.float32(smp.get_sample()).view(np.uint32) == gv[k].view(np.uint32), (k, int(dim[k]))
+
+
+def test_camera_rays_equal_the_second_reading(cornell2):
+    """Film-point drift included: sample 1's film point carries sample 0's offset."""
+    s = cornell2
+    for sample in (0, 1):
+        rays = s.renderer.camera_rays(sample)
+        mine = np.zeros_like(rays)
+        for y in range(s.height):
+            for x in range(s.width):
+                fx, fy = np.float32(x), np.float32(y)
+                for k in range(sample + 1):
+                    smp = s.path.PixelSampler(s.halton_value(x, y, k))
+                    u = smp.get_2d()
+                    fx, fy = fx + (u[0] - np.float32(0.5)), fy + (u[1] - np.float32(0.5))
+                o, d = s.camera.generate_ray(fx, fy)
+                mine[y * s.width + x, 0:3] = o
+                mine[y * s.width + x, 4:7] = d
+        assert np.array_equal(rays[:, [0, 1, 2, 4, 5, 6]].view(np.uint32), mine[:, [0, 1, 2, 4, 5, 6]].view(np.uint32)), sample
+
+
+@pytest.mark.parametrize("which", ["cornell", "mesh"])
+def test_hits_equal_the_second_reading(cornell2, mesh2, which):
+    """Closest hits (primitive and the bits of t) and occlusion answers: the flat search of the 33-primitive Cornell
+    box and the two-phase tree walk of the 818-triangle mesh against the reference-order search of trace_numpy."""
+    s = cornell2 if which == "cornell" else mesh2
+    search = s.numpy_scene.search
+    lo = np.min([p.bounds()[0] for p in search.prims], axis=0)
+    hi = np.max([p.bounds()[1] for p in search.prims], axis=0)
+    rays = np.concatenate([lcg_rays(500, lo, hi, seed=31), s.renderer.camera_rays(0)[::2][:200]])
+    got = s.renderer.trace_closest(rays)
+    prim = np.full(len(rays), NO_HIT, np.uint32); t = np.zeros(len(rays), np.float32)
+    for i, r in enumerate(rays):
+        hit, th = search.closest(r[0:3], r[4:7], r[3])
+        if hit is not None:
+            prim[i], t[i] = hit, th
+    assert (prim != NO_HIT).sum() > 60
+    assert np.array_equal(got["prim"], prim)
+    hit_mask = prim != NO_HIT
+    assert np.array_equal(got["t"][hit_mask].view(np.uint32), t[hit_mask].view(np.uint32))
+    seg = rays.copy(); seg[:, 3] = np.where(hit_mask, t * np.float32(1.5), np.float32(50.0))
+    both = np.concatenate([rays[:200], seg[::2]])
+    occluded = np.array([search.any_hit(r[0:3], r[4:7], r[3]) for r in both], np.uint8)
+    assert np.array_equal(np.asarray(s.renderer.trace_any(both)).astype(np.uint8), occluded)
+
+
+def test_image_against_the_second_reading(cornell2):
+    """The path-traced Cornell box, device against the numpy restatement, to the limits the oracle comparisons use."""
+    s = cornell2
+    film = s.path.render(s.numpy_scene, s.width, s.height, s.spp, s.halton_value, s.camera.generate_ray)
+    got, stats = s.renderer.render()
+    assert np.isfinite(got).all()
+    bad = (np.abs(got - film) / (np.abs(film) + 1e-3)).max(axis=2) > 1e-3
+    assert bad.sum() <= 1, int(bad.sum())
+    assert float(np.sqrt(np.mean((got - film) ** 2))) <= 1e-4 + 1e-3 * float(film.mean())
+    assert int(stats.rays_any) == s.numpy_scene.rays_any
+
+
+def _variant_text(name):
+    import re
+    from conftest import c3_text, furnace_scene_text
+    from test_gpu_parity import GENERAL_MATERIALS, _cornell_with_white_material
+    if name == "sphere.pbrt":
+        return scene_text("sphere.pbrt", xres=48, yres=27, spp=2)
+    if name == "textured":
+        text = c3_text()
+        for key, old, new in (("xresolution", 1920, 32), ("yresolution", 1080, 18), ("pixelsamples", 1024, 2)):
+            text = text.replace('"integer %s" [%d]' % (key, old), '"integer %s" [%d]' % (key, new))
+        return text
+    if name in GENERAL_MATERIALS:
+        return _cornell_with_white_material(GENERAL_MATERIALS[name], xres=20, yres=20, spp=2)
+    if name == "environment map":
+        return scene_text("cornel_box.pbrt", xres=20, yres=20, spp=2).replace("WorldBegin\n", 'WorldBegin\nLightSource "infinite" "string mapname" "box-texture.png"\n', 1)
+    if name == "furnace":
+        return furnace_scene_text("path", 0.75, spp=2, res=20)
+    if name == "thin lens":
+        return scene_text("cornel_box.pbrt", xres=20, yres=20, spp=2).replace('"float fov"', '"float lensradius" [12] "float focaldistance" [900] "float fov"', 1)
+    assert name == "directlighting"
+    return scene_text("cornel_box.pbrt", xres=20, yres=20, spp=2, integrator=("directlighting", 5))
+
+
+@pytest.mark.parametrize("name", ["sphere.pbrt", "textured", "plastic", "uber", "translucent", "mix", "environment map", "furnace", "thin lens", "directlighting"])
+def test_variant_images_against_the_second_reading(cpbrt, name):
+    """BASELINE configs C2 and C3 in small, the general materials, the infinite light, the thin lens and the recursive
+    direct-lighting integrator: device image against the numpy restatement, same limits, same shadow-ray count."""
+    s = _Second(cpbrt, _variant_text(name))
+    film = s.path.render(s.numpy_scene, s.width, s.height, s.spp, s.halton_value, s.camera.generate_ray,
+                         integrator=s.integrator, camera_draws=bool(s.scene.desc.camera.has_lens))
+    got, stats = s.renderer.render()
+    assert np.isfinite(got).all() and (film > 0).any()
+    bad = (np.abs(got - film) / (np.abs(film) + 1e-3)).max(axis=2) > 1e-3
+    assert bad.sum() <= 1, int(bad.sum())
+    assert float(np.sqrt(np.mean((got - film) ** 2))) <= 1e-4 + 1e-3 * float(film.mean())
+    assert int(stats.rays_any) == s.numpy_scene.rays_any
+    s.renderer.close()
