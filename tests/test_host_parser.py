@@ -318,3 +318,54 @@ def test_big_mesh_parallel_clipper_equals_sequential(cpbrt):
     import ctypes as C
     ia, pa = kept(a); ib, pb = kept(b)
     assert np.array_equal(ia, ib) and np.array_equal(pa.view(np.uint32), pb.view(np.uint32))
+
+
+def test_clipper_against_an_independent_restatement(cpbrt):
+    """The camera clipper is host code shared by the product and the oracle, so no parity test sees it.  Restated here
+    from the Rust alone (camera/mod.rs:58-63, camera/perspective.rs:54-77): a material primitive goes when BOTH its
+    camera-space bound's min and max points (`bound[corner]` indexes modulo 2 -- only those two of the eight corners are
+    ever looked at) project behind the camera or off the film; emitters always stay.  A height field seen from close by
+    loses half its triangles; which ones must agree for every triangle whose decision does not hinge on rounding
+    (the world-to-camera matrix is re-derived here in float64, so decisions within 1e-3 pixel are set aside)."""
+    from test_oracle import _synthetic_mesh_scene
+    nx, nz = 40, 30
+    text = _synthetic_mesh_scene(nx, nz, seed=5, res=64).replace("LookAt 278 273 -800 278 273 0 0 1 0", "LookAt 278 120 -100 278 20 300 0 1 0")
+    scene = cpbrt.Scene.parse(text)
+    d = scene.desc
+    import re
+    m = re.search(r'Material "matte"[^\n]*\nShape "trianglemesh" "integer indices" \[([^\]]*)\] "point P" \[([^\]]*)\]', text)
+    idx = np.array(m.group(1).split(), np.int64).reshape(-1, 3)
+    P = np.array([np.float32(float(v)) for v in m.group(2).split()], np.float32).reshape(-1, 3)
+    tris = P[idx]                                                   # every triangle of the mesh, file order
+    assert len(tris) == 2 * nx * nz
+    world_to_camera = np.linalg.inv(np.array(list(d.camera.camera_to_world), np.float64).reshape(4, 4))
+    camera_to_raster = np.array(list(d.camera.camera_to_raster), np.float64).reshape(4, 4)
+    width, height = float(d.film_width), float(d.film_height)
+
+    def decide(tri):
+        lo, hi = tri.min(0).astype(np.float64), tri.max(0).astype(np.float64)
+        corners = np.array([[(lo, hi)[(i >> c) & 1][c] for c in range(3)] + [1.0] for i in range(8)])
+        cam = corners @ world_to_camera.T
+        cam = cam[:, :3] / cam[:, 3:4]
+        keep, margin = False, np.inf
+        for p in (cam.min(0), cam.max(0)):
+            h = camera_to_raster @ np.append(p, 1.0)
+            x, y, z = h[:3] / h[3]
+            margin = min(margin, abs(z), abs(x), abs(x - width), abs(y), abs(y - height))
+            if not (z < 0 or x >= width or x < 0 or y >= height or y < 0):
+                keep = True
+        return keep, margin
+
+    kept_actual = set()
+    for i in range(int(d.n_primitives)):
+        if d.primitives[i].material >= 0:
+            kept_actual.add(np.array([[d.triangles[d.primitives[i].shape.data].p[k][c] for c in range(3)] for k in range(3)], np.float32).tobytes())
+    assert int(d.n_primitives) - len(kept_actual) == 2 and len({t.tobytes() for t in tris}) == len(tris)
+    robust = kept = 0
+    for tri in tris:
+        keep, margin = decide(tri)
+        if margin > 1e-3:
+            robust += 1
+            kept += keep
+            assert (tri.tobytes() in kept_actual) == keep
+    assert robust > 0.99 * len(tris) and 0.2 * len(tris) < kept < 0.8 * len(tris)
