@@ -28,6 +28,25 @@ def test_halton_works_kat(cpbrt, oracle):
         assert (rx, ry) == (x, y)
 
 
+def test_reference_kats_through_the_second_reading(cpbrt):
+    """The reference's two unit tests (halton.rs:232-249, perspective.rs:88-105) against oracle/front_numpy.py, which
+    builds the sampler from the resolution by itself (no scene description, no table: dimensions 0 and 1 are unscrambled)."""
+    front = _load_oracle_py("front_numpy")
+    smp = front.HaltonSampler(16, (9, 4), None)
+    assert (smp.scale, smp.exp) == ([16, 9], [4, 2])
+    for (x, y), index in {(3, 3): 28, (5, 3): 10, (4, 3): 82, (8, 0): 81}.items():
+        smp.set_pixel(x, y)
+        assert smp.index == index
+        rx = int(np.trunc(front.radical_inverse(smp.index, 0) * front.usize_to_f32(smp.scale[0])))
+        ry = int(np.trunc(front.radical_inverse(smp.index, 1) * front.usize_to_f32(smp.scale[1])))
+        assert (rx, ry) == (x, y)
+    s = cpbrt.Scene.parse('Camera "perspective" "float fov" [40]\nSampler "halton" "integer pixelsamples" [1]\n'
+                          'Film "image" "integer xresolution" [1024] "integer yresolution" [768]\nIntegrator "path"\nWorldBegin\nWorldEnd\n')
+    cam = front.PerspectiveCamera(list(s.desc.camera.raster_to_camera))
+    o, d = cam.generate_ray(512.0, 384.0)
+    assert [float(v) for v in o + d] == [0.0, 0.0, 0.0, 0.0, 0.0, 1.0]
+
+
 def test_halton_example_points(cpbrt, oracle):
     """examples/halton_sampler.rs prints get_2d() of samples 0.. for a 1024x768 sampler starting
     at index 0; dims 0,1 involve no permutation."""
