@@ -1,15 +1,13 @@
 """ORACLE -- TEST INFRASTRUCTURE ONLY.
 
-A second, independent restatement of the reference's render loop and path integrator for scenes
-of matte triangles under diffuse area lights (the Cornell box without its glass ball and mirror),
-in scalar np.float32 written directly from the Rust; it shares nothing with oracle/oracle.cpp.
-The tests render a few hundred paths with it and hold the C++ oracle to the same image and the same
-ray counts.  What it takes from outside, as inputs:
-  * the flattened scene (triangles, Kd, emitted radiance) -- `cpbrt_scene_desc`;
-  * the Halton value of (pixel, sample, dimension) and the raster -> camera-ray map, from callables
-    (the sampler and the camera are pinned on their own: exact-arithmetic radical inverses, the
-    reference's two unit tests, the closed-form camera);
-  * the BVH and its search: oracle/sah_numpy.py, oracle/trace_numpy.py.
+A second, independent restatement of the reference's render loop, both integrators, every material,
+every light and the shapes' sampling, in scalar np.float32 written directly from the Rust; it shares
+nothing with oracle/oracle.cpp.  The tests render a few hundred to a few thousand paths with it and
+hold the C++ oracle -- and, on the GPU box, the device -- to the same image and the same ray counts.
+Inputs: the flattened scene (`cpbrt_scene_desc`: vertices, matrices, texels as the host decoded them),
+the Halton value of (pixel, sample, dimension) and the raster -> camera-ray map as callables
+(oracle/front_numpy.py restates both), the BVH and its search (oracle/sah_numpy.py, trace_numpy.py).
+Not restated: a shading point inside a spherical emitter, emitters behind nested transforms.
 
   render loop, film-point drift, NaN drop, mean   src/render.rs:20-44, src/film.rs:11-18
   Sampler::get_1d / get_2d / get_usize            src/sampler/mod.rs:10-36
@@ -22,6 +20,8 @@ ray counts.  What it takes from outside, as inputs:
   Triangle::sample / area / normal / interpolate  src/geometry/shape/triangle.rs:76-126,255-261
   ShapePoint::point_offset_by_error               src/geometry/shape/mod.rs:117-124
   MatteMaterial, LambertianReflection, BxDF       src/material/matte.rs, bxdf/lambertian.rs, bxdf/mod.rs:17-44
+  OrenNayar, TrowbridgeReitz, Microfacet{Reflection,Transmission}   src/material/bxdf/{oren_nayar,microfacet}.rs
+  plastic / uber / translucent / mix, BSDF::mix   src/material/{plastic,uber,translucent,mix}.rs, bxdf/mod.rs:46-66,218-269
   MirrorMaterial, GlassMaterial, specular lobes   src/material/{mirror,glass}.rs, bxdf/specular.rs, math/mod.rs:202-211 (refract)
   ConstantTexture, ImageTexture::evaluate         src/texture/{constant,image}.rs (nearest texel, v flipped)
   PointLight, DistantLight, DeltaLight adaptor    src/light/{point,distant}.rs, light/mod.rs:76-98
@@ -34,7 +34,6 @@ ray counts.  What it takes from outside, as inputs:
 
 Vector arithmetic follows nalgebra for 3-vectors: dot = (x*x' + y*y') + z*z', norm = sqrt(dot),
 normalize divides each component by the norm."""
-import math
 
 import numpy as np
 
