@@ -183,3 +183,23 @@ def test_variant_images_against_the_second_reading(cpbrt, name):
     assert float(np.sqrt(np.mean((got - film) ** 2))) <= 1e-4 + 1e-3 * float(film.mean())
     assert int(stats.rays_any) == s.numpy_scene.rays_any
     s.renderer.close()
+
+
+# sha256 of the BVH primitive order (little-endian u32) that oracle/sah_numpy.py builds for _synthetic_mesh_scene(400, 250,
+# seed=2, res=16) -- 199 942 primitives after the clipper; about a minute of numpy, so the order itself is computed by
+# tools/independent_sah_check.py 400 250 (which also checks the C++ oracle against it) and only its digest is kept here.
+SAH_200K_ORDER_SHA256 = "e954872c6732b16e6a3b979af233c0f73a71461d0e38fa3282625c4f61873db4"
+
+
+def test_device_resident_build_equals_the_second_reading(cpbrt):
+    """199 942 primitives is above the size (131 072) from which cpbrt_build_bvh builds on the device: the order of
+    the device-resident exact SAH build against the digest of the numpy restatement's order."""
+    import hashlib
+    scene = cpbrt.Scene.parse(_synthetic_mesh_scene(400, 250, seed=2, res=16))
+    assert int(scene.desc.n_primitives) == 199942
+    r = cpbrt.Renderer(0)
+    r.upload(scene)
+    order = r.build_bvh()
+    assert r.bvh_gpu_levels() > 0
+    assert hashlib.sha256(np.asarray(order, "<u4").tobytes()).hexdigest() == SAH_200K_ORDER_SHA256
+    r.close()

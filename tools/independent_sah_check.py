@@ -20,5 +20,7 @@ P = np.array([[list(d.triangles[d.primitives[i].shape.data].p[k]) for k in range
 t0=time.time(); tree = sah.build(*sah.triangle_bounds(P)); t1=time.time()
 w = oracle_api.OracleWorld(sc)
 ref = w.bvh_nodes()
+import hashlib
+print("sha256 of the numpy order as little-endian u32:", hashlib.sha256(np.asarray(tree.order, "<u4").tobytes()).hexdigest())
 print(n, "numpy build s", round(t1-t0,1), "order equal", np.array_equal(tree.order, w.bvh_order()), "nodes", len(tree.a), len(ref["a"]),
       "links equal", np.array_equal(np.array(tree.a), ref["a"].astype(np.int64)) and np.array_equal(np.array(tree.b), ref["b"].astype(np.int64)))
