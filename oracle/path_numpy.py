@@ -7,7 +7,7 @@ hold the C++ oracle -- and, on the GPU box, the device -- to the same image and 
 Inputs: the flattened scene (`cpbrt_scene_desc`: vertices, matrices, texels as the host decoded them),
 the Halton value of (pixel, sample, dimension) and the raster -> camera-ray map as callables
 (oracle/front_numpy.py restates both), the BVH and its search (oracle/sah_numpy.py, trace_numpy.py).
-Not restated: a shading point inside a spherical emitter, emitters behind nested transforms.
+Not restated: emitters behind nested transforms.
 
   render loop, film-point drift, NaN drop, mean   src/render.rs:20-44, src/film.rs:11-18
   Sampler::get_1d / get_2d / get_usize            src/sampler/mod.rs:10-36
@@ -700,26 +700,52 @@ def texture(desc, index):
 
 # ---- the scene -------------------------------------------------------------------------------
 class SphereLightShape:
-    """TransformShape{Sphere} as a light's shape: sample_by_point / by_point_pdf go through the inverse transform
-    (transform.rs:60-70), Sphere::sample_by_point is the cone sampling of sphere.rs:66-99 (outside the sphere)."""
+    """Sphere, bare or behind one TransformShape, as a light's shape.  Behind a wrapper sample_by_point / by_point_pdf
+    go through the inverse transform and the sampled point comes back through ShapePoint::apply (transform.rs:60-70).
+    Sphere::sample_by_point (sphere.rs:66-99): cone sampling from outside, Shape::default_sample_by_point over
+    Sphere::sample (a uniform direction, sphere.rs:54-65) from inside or on the surface."""
 
     def __init__(self, prim, trace):
-        self.prim, self.trace = prim, trace
+        self.trace = trace
+        self.wrap = prim if isinstance(prim, trace.TransformedPrim) else None
+        self.radius = prim.radius
+        if self.wrap is not None:
+            self.m3_inverse = trace.normal_matrix(prim.m)        # Normal3f::apply with the inverse transform
 
-    def _to_world(self, p, n):
-        t, q = self.trace, self.prim
-        pw = t.apply_point(q.m, p)
-        nw = [(q.m3[i][0] * n[0] + q.m3[i][1] * n[1]) + q.m3[i][2] * n[2] for i in range(3)]
+    def _apply(self, m, m3, p, n):
+        pw = self.trace.apply_point(m, p)
+        nw = [(m3[i][0] * n[0] + m3[i][1] * n[1]) + m3[i][2] * n[2] for i in range(3)]
         g3 = gamma(3)
-        err = [g3 * (((abs(q.m[i][0] * pw[0]) + abs(q.m[i][1] * pw[1])) + abs(q.m[i][2] * pw[2])) + q.m[i][3]) for i in range(3)]
+        err = [g3 * (((abs(m[i][0] * pw[0]) + abs(m[i][1] * pw[1])) + abs(m[i][2] * pw[2])) + m[i][3]) for i in range(3)]
         return ShapePoint(pw, nw, err)
 
-    def sample_by_point(self, point, sampler):
-        r = self.prim.radius
-        point = self.trace.apply_point(self.prim.m_inv, point)
+    def area(self):
+        return self.radius * self.radius * PI * F(4)
+
+    def _sample(self, sampler):
+        """Sphere::sample."""
+        r = self.radius
+        u = sampler.get_2d()
+        z = ONE - F(2) * u[0]
+        rr = np.sqrt(_max(ZERO, ONE - z * z))
+        phi = F(2) * PI * u[1]
+        d = [rr * _cosf(phi), rr * _sinf(phi), z]
+        p = scale(d, r)
+        n = normalize(d)
+        p = scale(p, r / np.sqrt(norm2(p)))
+        return ShapePoint(p, n, scale(vabs(p), gamma(5))), ONE / self.area()
+
+    def _sample_by_point(self, point, sampler):
+        r = self.radius
         d2 = norm2(point)
         r2 = r * r
-        assert d2 > r2, "shading point inside the emitter: default_sample_by_point, not restated"
+        if d2 <= r2:
+            sp, pdf = self._sample(sampler)
+            wi = sub(sp.p, point)
+            if norm2(wi) == 0:
+                return sp, ZERO
+            pdf = pdf * norm2(wi) / -dot(normalize(wi), sp.n)
+            return sp, (ZERO if (np.isnan(pdf) or np.isinf(pdf)) else pdf)
         dist = np.sqrt(d2)
         z = unscale(point, dist)
         x, y = coordinate_system(z)
@@ -733,15 +759,26 @@ class SphereLightShape:
         cos_a = (d2 + r2 - ds * ds) / (F(2) * dist * r)
         sin_a = np.sqrt(_max(ONE - cos_a * cos_a, ZERO))
         d = add(add(scale(z, cos_a), scale(x, sin_a * _cosf(phi))), scale(y, sin_a * _sinf(phi)))
-        n = normalize(d)
         p = scale(d, r)
-        return self._to_world(p, n), ONE / (F(2) * PI * (ONE - cos_max))
+        return ShapePoint(p, normalize(d), scale(vabs(p), gamma(5))), ONE / (F(2) * PI * (ONE - cos_max))
+
+    def sample_by_point(self, point, sampler):
+        if self.wrap is None:
+            return self._sample_by_point(point, sampler)
+        sp, pdf = self._sample_by_point(self.trace.apply_point(self.wrap.m_inv, point), sampler)
+        return self._apply(self.wrap.m, self.wrap.m3, sp.p, sp.n), pdf
 
     def by_point_pdf(self, point, sp):
-        r = self.prim.radius
-        point = self.trace.apply_point(self.prim.m_inv, point)
+        r = self.radius
+        if self.wrap is not None:
+            point = self.trace.apply_point(self.wrap.m_inv, point)
+            sp = self._apply(self.wrap.m_inv, self.m3_inverse, sp.p, sp.n)
         d2 = norm2(point)
-        assert not d2 < r * r
+        if d2 < r * r:
+            d = sub(point, sp.p)
+            dd = norm2(d)
+            pdf = dd / (abs(dot(unscale(d, np.sqrt(dd)), sp.n)) * self.area())
+            return ZERO if (np.isnan(pdf) or np.isinf(pdf)) else pdf
         cos_max = np.sqrt(ONE - r * r / d2)
         return ONE / (F(2) * PI * (ONE - cos_max))
 
@@ -905,8 +942,11 @@ class Scene:
                     obj = trace.TransformedPrim(obj, list(t.m), list(t.m_inv), to_sp if k == 0 else None)
                 self.tris.append(tri if not chain else None)
             else:
-                assert pr.shape.kind == abi.SHAPE_SPHERE and chain
-                obj = trace.SpherePrim(desc.sphere_radius[pr.shape.data], list(chain[0].m), list(chain[0].m_inv))
+                assert pr.shape.kind == abi.SHAPE_SPHERE
+                if chain:
+                    obj = trace.SpherePrim(desc.sphere_radius[pr.shape.data], list(chain[0].m), list(chain[0].m_inv))
+                else:
+                    obj = trace.BareSpherePrim(desc.sphere_radius[pr.shape.data])
                 for t in chain[1:]:
                     obj = trace.TransformedPrim(obj, list(t.m), list(t.m_inv))
                 self.tris.append(None)

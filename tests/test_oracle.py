@@ -789,6 +789,32 @@ def test_instances_under_transforms_against_independent_numpy_restatement(cpbrt,
     assert np.array_equal(film.view(np.uint32), ref.view(np.uint32))
 
 
+@pytest.mark.parametrize("integrator", ["path", "directlighting"])
+@pytest.mark.parametrize("transform", ["", "Translate 0.5 -0.3 1\nScale 1 1.3 0.9\n"])
+def test_enclosing_sphere_emitter_against_independent_numpy_restatement(cpbrt, oracle, integrator, transform):
+    """Shading points INSIDE a spherical emitter (Shape::default_sample_by_point over Sphere::sample, the area-measure
+    pdf with its sign, default_by_point_pdf on the MIS side), the emitter bare (no TransformShape at all) and behind a
+    Translate + Scale: bit-equal image, equal ray counts."""
+    width = height = 18
+    spp = 2
+    text = ('Camera "perspective" "float fov" [40]\nSampler "halton" "integer pixelsamples" [%d]\n'
+            'Film "image" "integer xresolution" [%d] "integer yresolution" [%d]\nIntegrator "%s" "integer maxdepth" [3]\nWorldBegin\n'
+            'AttributeBegin\n%sAreaLightSource "diffuse" "rgb L" [1 0.9 0.8]\nShape "sphere" "float radius" [30]\nAttributeEnd\n'
+            'Material "matte" "rgb Kd" [0.5 0.6 0.7]\nAttributeBegin\nTranslate 0 0 5\nShape "sphere" "float radius" [1]\nAttributeEnd\n'
+            'Shape "trianglemesh" "integer indices" [0 1 2 2 3 0] "point P" [-3 -1 2 3 -1 2 3 -1 9 -3 -1 9]\nWorldEnd\n'
+            % (spp, width, height, integrator, transform))
+    scene = cpbrt.Scene.parse(text)
+    sah, trace, path = (_load_oracle_py(n) for n in ("sah_numpy", "trace_numpy", "path_numpy"))
+    w = oracle.OracleWorld(scene)
+    mine = path.Scene(scene.desc, cpbrt.abi, sah, trace)
+    halton_value, camera_ray_at = _independent_front(scene)
+    film = path.render(mine, width, height, spp, halton_value, camera_ray_at, integrator=integrator)
+    ref, _, st = w.render()
+    assert (film > 0).any() and np.isfinite(film).all()
+    assert (mine.rays_closest, mine.rays_any) == (st["rays_closest"], st["rays_any"])
+    assert np.array_equal(film.view(np.uint32), ref.view(np.uint32))
+
+
 def test_render_is_deterministic_and_thread_count_independent(make_scene, oracle):
     scene = make_scene("cornel_box.pbrt", xres=40, yres=40, spp=2)
     w = oracle.OracleWorld(scene)
