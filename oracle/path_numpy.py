@@ -699,31 +699,42 @@ def texture(desc, index):
 
 
 # ---- the scene -------------------------------------------------------------------------------
-class SphereLightShape:
-    """Sphere, bare or behind one TransformShape, as a light's shape.  Behind a wrapper sample_by_point / by_point_pdf
-    go through the inverse transform and the sampled point comes back through ShapePoint::apply (transform.rs:60-70).
-    Sphere::sample_by_point (sphere.rs:66-99): cone sampling from outside, Shape::default_sample_by_point over
-    Sphere::sample (a uniform direction, sphere.rs:54-65) from inside or on the surface."""
+class WrappedShape:
+    """TransformShape{shape, transform} as a light's shape (transform.rs:60-70): sample_by_point / by_point_pdf hand the
+    inner shape the point -- and, for the pdf, the shape point -- carried through the inverse transform; the sampled
+    point comes back through ShapePoint::apply."""
 
-    def __init__(self, prim, trace):
-        self.trace = trace
-        self.wrap = prim if isinstance(prim, trace.TransformedPrim) else None
-        self.radius = prim.radius
-        if self.wrap is not None:
-            self.m3_inverse = trace.normal_matrix(prim.m)        # Normal3f::apply with the inverse transform
+    def __init__(self, inner, prim, trace):
+        self.inner, self.prim, self.trace = inner, prim, trace
+        self.m3_inverse = trace.normal_matrix(prim.m)        # Normal3f::apply with the inverse transform
 
-    def _apply(self, m, m3, p, n):
-        pw = self.trace.apply_point(m, p)
-        nw = [(m3[i][0] * n[0] + m3[i][1] * n[1]) + m3[i][2] * n[2] for i in range(3)]
+    def _apply(self, m, m3, sp):
+        pw = self.trace.apply_point(m, sp.p)
+        nw = [(m3[i][0] * sp.n[0] + m3[i][1] * sp.n[1]) + m3[i][2] * sp.n[2] for i in range(3)]
         g3 = gamma(3)
         err = [g3 * (((abs(m[i][0] * pw[0]) + abs(m[i][1] * pw[1])) + abs(m[i][2] * pw[2])) + m[i][3]) for i in range(3)]
         return ShapePoint(pw, nw, err)
+
+    def sample_by_point(self, point, sampler):
+        sp, pdf = self.inner.sample_by_point(self.trace.apply_point(self.prim.m_inv, point), sampler)
+        return self._apply(self.prim.m, self.prim.m3, sp), pdf
+
+    def by_point_pdf(self, point, sp):
+        return self.inner.by_point_pdf(self.trace.apply_point(self.prim.m_inv, point), self._apply(self.prim.m_inv, self.m3_inverse, sp))
+
+
+class SphereShape:
+    """Sphere{radius} in its own space as a light's shape.  Sphere::sample_by_point (sphere.rs:66-99): cone sampling
+    from outside, Shape::default_sample_by_point over Sphere::sample (a uniform direction, sphere.rs:54-65) from inside
+    or on the surface; Sphere::by_point_pdf (sphere.rs:100-109)."""
+
+    def __init__(self, radius):
+        self.radius = F(radius)
 
     def area(self):
         return self.radius * self.radius * PI * F(4)
 
     def _sample(self, sampler):
-        """Sphere::sample."""
         r = self.radius
         u = sampler.get_2d()
         z = ONE - F(2) * u[0]
@@ -735,7 +746,7 @@ class SphereLightShape:
         p = scale(p, r / np.sqrt(norm2(p)))
         return ShapePoint(p, n, scale(vabs(p), gamma(5))), ONE / self.area()
 
-    def _sample_by_point(self, point, sampler):
+    def sample_by_point(self, point, sampler):
         r = self.radius
         d2 = norm2(point)
         r2 = r * r
@@ -762,17 +773,8 @@ class SphereLightShape:
         p = scale(d, r)
         return ShapePoint(p, normalize(d), scale(vabs(p), gamma(5))), ONE / (F(2) * PI * (ONE - cos_max))
 
-    def sample_by_point(self, point, sampler):
-        if self.wrap is None:
-            return self._sample_by_point(point, sampler)
-        sp, pdf = self._sample_by_point(self.trace.apply_point(self.wrap.m_inv, point), sampler)
-        return self._apply(self.wrap.m, self.wrap.m3, sp.p, sp.n), pdf
-
     def by_point_pdf(self, point, sp):
         r = self.radius
-        if self.wrap is not None:
-            point = self.trace.apply_point(self.wrap.m_inv, point)
-            sp = self._apply(self.wrap.m_inv, self.m3_inverse, sp.p, sp.n)
         d2 = norm2(point)
         if d2 < r * r:
             d = sub(point, sp.p)
@@ -922,6 +924,7 @@ class Scene:
     def __init__(self, desc, abi, sah, trace):
         n = int(desc.n_primitives)
         self.tris, self.material, self.light_of = [], [], []
+        object_shapes = []
         prims = []
         for i in range(n):
             pr = desc.primitives[i]
@@ -941,6 +944,7 @@ class Scene:
                 for k, t in enumerate(chain):
                     obj = trace.TransformedPrim(obj, list(t.m), list(t.m_inv), to_sp if k == 0 else None)
                 self.tris.append(tri if not chain else None)
+                object_shapes.append(tri)
             else:
                 assert pr.shape.kind == abi.SHAPE_SPHERE
                 if chain:
@@ -950,6 +954,7 @@ class Scene:
                 for t in chain[1:]:
                     obj = trace.TransformedPrim(obj, list(t.m), list(t.m_inv))
                 self.tris.append(None)
+                object_shapes.append(SphereShape(desc.sphere_radius[pr.shape.data]))
             assert pr.light < 0 or len(chain) <= 1, "emitters under nested transforms are not restated"
             prims.append(obj)
             self.light_of.append(int(pr.light))
@@ -967,7 +972,9 @@ class Scene:
                 assert lt.type == 0
                 prim = [i for i in range(n) if self.light_of[i] == k]
                 assert len(prim) == 1
-                shape = self.tris[prim[0]] if self.tris[prim[0]] is not None else SphereLightShape(prims[prim[0]], trace)
+                shape = object_shapes[prim[0]]
+                if isinstance(prims[prim[0]], trace.TransformedPrim):
+                    shape = WrappedShape(shape, prims[prim[0]], trace)
                 self.lights.append(AreaLight(shape, [F(x) for x in lt.L]))
         bounds = [q.bounds() for q in prims]
         lo = np.array([b[0] for b in bounds], np.float32)
