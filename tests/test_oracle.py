@@ -815,6 +815,19 @@ def test_enclosing_sphere_emitter_against_independent_numpy_restatement(cpbrt, o
     assert np.array_equal(film.view(np.uint32), ref.view(np.uint32))
 
 
+def test_random_scenes_against_independent_numpy_restatement(cpbrt, oracle):
+    """A slice of tools/independent_restatement_fuzz.py: ten random scenes (triangles and spheres bare, transformed and
+    instanced, every material and light type, both integrators, thin lens or not) -- bit-equal images, equal BVH order
+    and ray counts.  200 scenes of the same generator: profiles/r02_independent_restatement_fuzz.txt."""
+    import subprocess
+    import sys
+    tool = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tools", "independent_restatement_fuzz.py")
+    out = subprocess.run([sys.executable, tool, "--scenes", "10", "--seed", "7"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    summary = json.loads(out.stdout.strip().splitlines()[-1])
+    assert summary["scenes"] >= 8 and summary["mismatching_scenes"] == [] and summary["pixels_bit_equal"] == summary["pixels"]
+
+
 def test_render_is_deterministic_and_thread_count_independent(make_scene, oracle):
     scene = make_scene("cornel_box.pbrt", xres=40, yres=40, spp=2)
     w = oracle.OracleWorld(scene)
