@@ -976,10 +976,13 @@ class Scene:
                 if isinstance(prims[prim[0]], trace.TransformedPrim):
                     shape = WrappedShape(shape, prims[prim[0]], trace)
                 self.lights.append(AreaLight(shape, [F(x) for x in lt.L]))
-        bounds = [q.bounds() for q in prims]
-        lo = np.array([b[0] for b in bounds], np.float32)
-        hi = np.array([b[1] for b in bounds], np.float32)
-        self.search = trace.Searcher(sah.build(lo, hi), prims)
+        if prims:
+            bounds = [q.bounds() for q in prims]
+            lo = np.array([b[0] for b in bounds], np.float32)
+            hi = np.array([b[1] for b in bounds], np.float32)
+            self.search = trace.Searcher(sah.build(lo, hi), prims)
+        else:
+            self.search = None               # BVHAggregate::build returns before making a node; every query misses (bvh.rs:195-197,209-211)
         self.max_depth = int(desc.max_depth)
         self.rays_closest = 0
         self.rays_any = 0
@@ -992,6 +995,8 @@ class Scene:
 
     def intersect(self, o, d, t_max=np.finfo(np.float32).max):
         self.rays_closest += 1
+        if self.search is None:
+            return None, None
         prim, _ = self.search.closest(o, d, t_max)
         if prim is None:
             return None, None
@@ -1001,7 +1006,7 @@ class Scene:
 
     def occluded(self, o, d, t_max):
         self.rays_any += 1
-        return self.search.any_hit(o, d, t_max)
+        return self.search is not None and self.search.any_hit(o, d, t_max)
 
 
 def uniform_sample_one_light(scene, sp, bsdf, wo, sampler):

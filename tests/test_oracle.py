@@ -828,6 +828,29 @@ def test_random_scenes_against_independent_numpy_restatement(cpbrt, oracle):
     assert summary["scenes"] >= 8 and summary["mismatching_scenes"] == [] and summary["pixels_bit_equal"] == summary["pixels"]
 
 
+def test_degenerate_scenes_against_independent_numpy_restatement(cpbrt, oracle):
+    """An empty world, only an environment, a one-pixel film, no lights at all, everything missed: bit-equal images."""
+    head = ('Camera "perspective" "float fov" [40]\nSampler "halton" "integer pixelsamples" [%d]\n'
+            'Film "image" "integer xresolution" [%d] "integer yresolution" [%d]\nIntegrator "path" "integer maxdepth" [3]\nWorldBegin\n')
+    cases = [
+        (2, 8, 8, 'WorldEnd\n'),
+        (2, 8, 8, 'LightSource "infinite"\nWorldEnd\n'),
+        (1, 1, 1, 'LightSource "point" "point from" [0 2 0]\nMaterial "matte"\nTranslate 0 0 5\nShape "sphere"\nWorldEnd\n'),
+        (3, 16, 4, 'Material "matte"\nTranslate 0 0 5\nShape "sphere" "float radius" [0.5]\nWorldEnd\n'),
+        (2, 12, 12, 'LightSource "distant"\nMaterial "mirror"\nTranslate 100 0 5\nShape "sphere"\nWorldEnd\n'),
+    ]
+    sah, trace, path = (_load_oracle_py(n) for n in ("sah_numpy", "trace_numpy", "path_numpy"))
+    for spp, width, height, body in cases:
+        scene = cpbrt.Scene.parse(head % (spp, width, height) + body, base_dir=SCENES)
+        w = oracle.OracleWorld(scene)
+        mine = path.Scene(scene.desc, cpbrt.abi, sah, trace)
+        halton_value, camera_ray_at = _independent_front(scene)
+        film = path.render(mine, width, height, spp, halton_value, camera_ray_at)
+        ref, _, st = w.render()
+        assert (mine.rays_closest, mine.rays_any) == (st["rays_closest"], st["rays_any"]), body
+        assert np.array_equal(film.view(np.uint32), ref.view(np.uint32)), body
+
+
 def test_render_is_deterministic_and_thread_count_independent(make_scene, oracle):
     scene = make_scene("cornel_box.pbrt", xres=40, yres=40, spp=2)
     w = oracle.OracleWorld(scene)
