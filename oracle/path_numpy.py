@@ -7,7 +7,6 @@ hold the C++ oracle -- and, on the GPU box, the device -- to the same image and 
 Inputs: the flattened scene (`cpbrt_scene_desc`: vertices, matrices, texels as the host decoded them),
 the Halton value of (pixel, sample, dimension) and the raster -> camera-ray map as callables
 (oracle/front_numpy.py restates both), the BVH and its search (oracle/sah_numpy.py, trace_numpy.py).
-Not restated: emitters behind nested transforms.
 
   render loop, film-point drift, NaN drop, mean   src/render.rs:20-44, src/film.rs:11-18
   Sampler::get_1d / get_2d / get_usize            src/sampler/mod.rs:10-36
@@ -924,7 +923,6 @@ class Scene:
     def __init__(self, desc, abi, sah, trace):
         n = int(desc.n_primitives)
         self.tris, self.material, self.light_of = [], [], []
-        object_shapes = []
         prims = []
         for i in range(n):
             pr = desc.primitives[i]
@@ -944,7 +942,6 @@ class Scene:
                 for k, t in enumerate(chain):
                     obj = trace.TransformedPrim(obj, list(t.m), list(t.m_inv), to_sp if k == 0 else None)
                 self.tris.append(tri if not chain else None)
-                object_shapes.append(tri)
             else:
                 assert pr.shape.kind == abi.SHAPE_SPHERE
                 if chain:
@@ -954,8 +951,6 @@ class Scene:
                 for t in chain[1:]:
                     obj = trace.TransformedPrim(obj, list(t.m), list(t.m_inv))
                 self.tris.append(None)
-                object_shapes.append(SphereShape(desc.sphere_radius[pr.shape.data]))
-            assert pr.light < 0 or len(chain) <= 1, "emitters under nested transforms are not restated"
             prims.append(obj)
             self.light_of.append(int(pr.light))
             self.material.append(self._material(desc, pr.material) if pr.material >= 0 else None)
@@ -969,12 +964,19 @@ class Scene:
             elif lt.type == 3:
                 self.lights.append(InfiniteLight(desc, int(lt.tex)))
             else:
+                # AreaLight{shape}: the Arc the light was created from (scene.rs:86-90) -- for a shape declared inside an
+                # ObjectBegin block that is the un-instanced shape, whatever transform its instances are seen under
                 assert lt.type == 0
-                prim = [i for i in range(n) if self.light_of[i] == k]
-                assert len(prim) == 1
-                shape = object_shapes[prim[0]]
-                if isinstance(prims[prim[0]], trace.TransformedPrim):
-                    shape = WrappedShape(shape, prims[prim[0]], trace)
+                sh = lt.shape
+                if sh.kind == abi.SHAPE_TRIANGLE:
+                    shape = Triangle([[desc.triangles[sh.data].p[k][c] for c in range(3)] for k in range(3)])
+                else:
+                    shape = SphereShape(desc.sphere_radius[sh.data])
+                x = int(sh.xform)
+                while x >= 0:
+                    t = desc.transforms[x]
+                    shape = WrappedShape(shape, trace.TransformedPrim(None, list(t.m), list(t.m_inv)), trace)
+                    x = int(t.outer)
                 self.lights.append(AreaLight(shape, [F(x) for x in lt.L]))
         if prims:
             bounds = [q.bounds() for q in prims]
