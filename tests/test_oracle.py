@@ -818,7 +818,7 @@ def test_enclosing_sphere_emitter_against_independent_numpy_restatement(cpbrt, o
 def test_random_scenes_against_independent_numpy_restatement(cpbrt, oracle):
     """A slice of tools/independent_restatement_fuzz.py: ten random scenes (triangles and spheres bare, transformed and
     instanced, every material and light type, both integrators, thin lens or not) -- bit-equal images, equal BVH order
-    and ray counts.  200 scenes of the same generator: profiles/r02_independent_restatement_fuzz.txt."""
+    and ray counts.  500 scenes of the same generator: profiles/r02_independent_restatement_fuzz.txt."""
     import subprocess
     import sys
     tool = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tools", "independent_restatement_fuzz.py")
