@@ -988,6 +988,7 @@ class Scene:
         self.max_depth = int(desc.max_depth)
         self.rays_closest = 0
         self.rays_any = 0
+        self.nan_dropped = 0
 
     @staticmethod
     def _material(desc, index):
@@ -1059,8 +1060,11 @@ def path_li(scene, o, d, sampler):
         if bounce == 0 or specular_bounce:
             if prim is None:
                 l = add_out_scene(scene, l, beta, d)
-            elif scene.light_of[prim] >= 0:
-                l = add(l, mul(beta, scene.lights[scene.light_of[prim]].le))
+            else:
+                # `l += beta * intersect.le()`: le() is None off the emitters and None multiplies as black -- the term is
+                # still added, so a NaN or infinite beta poisons l here even when nothing emits
+                le = scene.lights[scene.light_of[prim]].le if scene.light_of[prim] >= 0 else [ZERO, ZERO, ZERO]
+                l = add(l, mul(beta, le))
         if prim is None or bounce >= scene.max_depth or scene.material[prim] is None:
             break
         bsdf = make_bsdf(scene.material[prim], sp)
@@ -1125,6 +1129,8 @@ def render(scene, width, height, spp, halton_value, camera_ray_at, rect=None, in
                     li = (path_li if integrator == "path" else direct_li)(scene, [F(v) for v in o], [F(v) for v in d], sampler)
                     if not has_nan(li):
                         kept.append(li)
+                    else:
+                        scene.nan_dropped += 1
                 total = [ZERO, ZERO, ZERO]
                 for li in kept:
                     total = add(total, li)

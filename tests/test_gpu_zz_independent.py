@@ -203,3 +203,24 @@ def test_device_resident_build_equals_the_second_reading(cpbrt):
     assert r.bvh_gpu_levels() > 0
     assert hashlib.sha256(np.asarray(order, "<u4").tobytes()).hexdigest() == SAH_200K_ORDER_SHA256
     r.close()
+
+
+def test_nan_samples_on_the_device(cpbrt, oracle):
+    """A black glass ball (Kr = Kt = 0) turns `beta` into NaN and the reference drops the samples it poisons
+    (tests/test_oracle.py::test_nan_samples_against_independent_numpy_restatement): the device drops the same number,
+    leaves the same pixels NaN (no sample kept: 0 / 0) and agrees on every other pixel
+    (profiles/r02_probe_black_glass.json: 151 samples, 23 pixels)."""
+    text = scene_text("cornel_box.pbrt", xres=20, yres=20, spp=3).replace('Material "glass"', 'Material "glass" "rgb Kr" [0 0 0] "rgb Kt" [0 0 0]')
+    scene = cpbrt.Scene.parse(text, base_dir=SCENES)
+    r = cpbrt.Renderer(0)
+    r.upload(scene)
+    r.build_bvh()
+    got, stats = r.render()
+    ref, _, st = oracle.OracleWorld(scene).render()
+    assert st["nan_dropped"] > 50 and int(stats.nan_dropped) == st["nan_dropped"]
+    nan_ref = np.isnan(ref).any(axis=2)
+    assert nan_ref.any() and np.array_equal(np.isnan(got).any(axis=2), nan_ref)
+    rel = (np.abs(got - ref) / (np.abs(ref) + 1e-3)).max(axis=2)
+    assert int((rel[~nan_ref] > 1e-3).sum()) <= 1
+    assert int(stats.rays_any) == st["rays_any"]
+    r.close()

@@ -851,6 +851,28 @@ def test_degenerate_scenes_against_independent_numpy_restatement(cpbrt, oracle):
         assert np.array_equal(film.view(np.uint32), ref.view(np.uint32)), body
 
 
+def test_nan_samples_against_independent_numpy_restatement(cpbrt, oracle):
+    """The NaN drop of the render loop (render.rs:33-40) and the per-pixel mean over the samples that were kept -- 0 / 0
+    where none was.  A glass ball with Kr = Kt = 0 makes them: both delta lobes are black, the luminance table is all
+    zero, its pmf NaN, and `beta` is NaN from there on; `l += beta * intersect.le()` then poisons `l` at the next specular
+    vertex even off the emitters (le() = None multiplies as black and is still added) -- the line the second reading got
+    wrong at first, by adding only on emitters.  Same dropped-sample count, same pixels NaN, every other pixel bit-equal."""
+    width = height = 20
+    spp = 3
+    text = scene_text("cornel_box.pbrt", xres=width, yres=height, spp=spp).replace('Material "glass"', 'Material "glass" "rgb Kr" [0 0 0] "rgb Kt" [0 0 0]')
+    scene = cpbrt.Scene.parse(text, base_dir=SCENES)
+    sah, trace, path = (_load_oracle_py(n) for n in ("sah_numpy", "trace_numpy", "path_numpy"))
+    w = oracle.OracleWorld(scene)
+    mine = path.Scene(scene.desc, cpbrt.abi, sah, trace)
+    halton_value, camera_ray_at = _independent_front(scene)
+    film = path.render(mine, width, height, spp, halton_value, camera_ray_at)
+    ref, _, st = w.render()
+    assert st["nan_dropped"] > 50 and mine.nan_dropped == st["nan_dropped"]
+    assert (mine.rays_closest, mine.rays_any) == (st["rays_closest"], st["rays_any"])
+    assert np.isnan(ref).any() and np.array_equal(np.isnan(film), np.isnan(ref))
+    assert np.array_equal(film.view(np.uint32)[~np.isnan(ref)], ref.view(np.uint32)[~np.isnan(ref)])
+
+
 def test_render_is_deterministic_and_thread_count_independent(make_scene, oracle):
     scene = make_scene("cornel_box.pbrt", xres=40, yres=40, spp=2)
     w = oracle.OracleWorld(scene)

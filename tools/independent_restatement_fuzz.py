@@ -29,6 +29,8 @@ def load(name):
 
 
 def rgb(rng, lo=0.05, hi=0.9):
+    if rng.rand() < 0.06:
+        return "0 0 0"                 # black now and then: empty lobe lists, all-zero luminance tables, NaN samples
     return "%.3g %.3g %.3g" % tuple(rng.uniform(lo, hi, 3))
 
 
