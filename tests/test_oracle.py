@@ -873,6 +873,79 @@ def test_nan_samples_against_independent_numpy_restatement(cpbrt, oracle):
     assert np.array_equal(film.view(np.uint32)[~np.isnan(ref)], ref.view(np.uint32)[~np.isnan(ref)])
 
 
+def _adversarial_triangles(kind):
+    rng = np.random.RandomState(23)
+    if kind in ("scaled up", "scaled down"):
+        soup = rng.rand(300, 1, 3) * 500 + (rng.rand(300, 3, 3) - 0.5) * rng.choice([0.5, 8.0, 120.0], (300, 1, 1))
+        return (soup * (1e3 if kind == "scaled up" else 1e-3)).astype(np.float32)
+    if kind == "coincident":
+        # the same quad stacked 0, 1, 2, 4 ... 64 ulp apart along z, twice over with opposite windings
+        z = np.float32(300.0)
+        layers = [z]
+        for step in (0, 1, 1, 2, 4, 8, 16, 32):
+            nxt = layers[-1]
+            for _ in range(step):
+                nxt = np.nextafter(nxt, np.float32(np.inf))
+            layers.append(nxt)
+        tris = []
+        for k, zz in enumerate(layers):
+            quad = np.array([[100, 100, zz], [400, 100, zz], [400, 400, zz], [100, 400, zz]], np.float32)
+            order = (0, 1, 2, 2, 3, 0) if k % 2 == 0 else (0, 2, 1, 0, 3, 2)
+            tris += [quad[list(order[:3])], quad[list(order[3:])]]
+        return np.array(tris, np.float32)
+    assert kind == "slivers"
+    base = rng.rand(200, 1, 3) * 400 + 50
+    long_edge = (rng.rand(200, 1, 3) - 0.5) * 300
+    thin = (rng.rand(200, 1, 3) - 0.5) * rng.choice([1e-4, 1e-2, 1.0], (200, 1, 1))
+    return np.concatenate([base, base + long_edge, base + long_edge * 0.5 + thin], axis=1).astype(np.float32)
+
+
+@pytest.mark.parametrize("kind", ["scaled up", "scaled down", "coincident", "slivers"])
+def test_adversarial_geometry_against_independent_numpy_restatement(cpbrt, oracle, kind):
+    """Coordinates of 1e5 and 1e-1, the same quad stacked 0 to 64 ulp apart with alternating windings, slivers down to
+    1e-4 wide: BVH order, closest primitive, the bits of t, occlusion and the visit / test counts of the C++ oracle
+    against the numpy restatement -- where ties in t are decided by traversal order alone."""
+    tris = _adversarial_triangles(kind)
+    look = {"scaled up": "LookAt 278000 273000 -800000 278000 273000 0 0 1 0", "scaled down": "LookAt 0.278 0.273 -0.8 0.278 0.273 0 0 1 0"}
+    scene = cpbrt.Scene.parse(_triangle_soup_scene(tris).replace("LookAt 278 273 -800 278 273 0 0 1 0", look.get(kind, "LookAt 278 273 -800 278 273 0 0 1 0")))
+    d = scene.desc
+    n = int(d.n_primitives)
+    assert n >= len(tris)                                            # the clipper kept the soup
+    P = np.array([[list(d.triangles[d.primitives[i].shape.data].p[k]) for k in range(3)] for i in range(n)], np.float32)
+    sah, trace = _load_oracle_py("sah_numpy"), _load_oracle_py("trace_numpy")
+    search = trace.Searcher(sah.build(*sah.triangle_bounds(P)), P)
+    w = oracle.OracleWorld(scene)
+    assert np.array_equal(search.tree.order, w.bvh_order()), kind
+    own = P[n - len(tris):]                                         # without the light quad of the scene template
+    lo, hi = own.reshape(-1, 3).min(0), own.reshape(-1, 3).max(0)
+    pad = (hi - lo) * 0.2 + 1e-3
+    rays = [lcg_rays(500, lo - pad, hi + pad, seed=41)]
+    rng = np.random.RandomState(5)
+    pick = rng.randint(0, len(own), 300)
+    eye = (lo + hi) * 0.5 + np.array([0.3, 0.2, -3.0], np.float32) * (hi - lo + 1.0)
+    aimed = np.zeros((600, 8), np.float32)
+    aimed[:, 0:3] = eye; aimed[:, 3] = np.finfo(np.float32).max
+    aimed[:300, 4:7] = own[pick, rng.randint(0, 3, 300)] - eye                       # through a vertex
+    aimed[300:, 4:7] = own[pick].mean(axis=1) - eye                                    # through a centroid
+    rays = np.concatenate(rays + [aimed]).astype(np.float32)
+    ref, ref_count = w.trace_closest(rays, count=True, threads=1)
+    prim = np.full(len(rays), 0xFFFFFFFF, np.uint32); t = np.zeros(len(rays), np.float32)
+    for i, r in enumerate(rays):
+        hit, th = search.closest(r[0:3], r[4:7], r[3])
+        if hit is not None:
+            prim[i], t[i] = hit, th
+    assert (prim != 0xFFFFFFFF).sum() > 100, kind
+    assert np.array_equal(prim, ref["prim"]), kind
+    assert np.array_equal(t.view(np.uint32), ref["t"].view(np.uint32)), kind
+    assert (search.visits, search.tests) == (int(ref_count[0]), int(ref_count[1])), kind
+    seg = rays.copy(); seg[:, 3] = np.where(prim != 0xFFFFFFFF, t * np.float32(1.0000001), np.float32(50.0))
+    search.visits = search.tests = 0
+    occluded = np.array([search.any_hit(r[0:3], r[4:7], r[3]) for r in seg], np.uint8)
+    ref_any, any_count = w.trace_any(seg, count=True, threads=1)
+    assert np.array_equal(occluded, ref_any), kind
+    assert (search.visits, search.tests) == (int(any_count[0]), int(any_count[1])), kind
+
+
 def test_render_is_deterministic_and_thread_count_independent(make_scene, oracle):
     scene = make_scene("cornel_box.pbrt", xres=40, yres=40, spp=2)
     w = oracle.OracleWorld(scene)
